@@ -1,0 +1,328 @@
+"""ctypes binding of the C ABI in include/b200pf.h (libb200pf.so, built in-tree by csrc/Makefile).
+
+This is plumbing for the Python tests and bench.py; it adds no computation.  There is no fallback:
+if the shared library is missing, or there is no sm_100 device, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200pf.so")
+_lib = None
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_i16p = C.POINTER(C.c_int16)
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("feat_dim", "d_model", "n_heads", "d_ff", "n_enc", "n_dec", "kernel", "vocab", "pred_residual")] + \
+               [(n, C.c_float) for n in ("cif_threshold", "tail_threshold", "ln_eps")] + \
+               [(n, C.c_int32) for n in ("sample_rate", "max_rows", "max_segments")]
+
+
+class Result(C.Structure):
+    _fields_ = [("token_counts", c_i32p), ("token_offsets", c_i32p), ("lfr_frames", c_i32p),
+                ("token_ids", c_i32p), ("fire_frames", c_i32p), ("cap_tokens", C.c_int64), ("n_tokens", C.c_int64)]
+
+
+class B200PFError(RuntimeError):
+    pass
+
+
+def build_library(verbose=False):
+    """nvcc-compile csrc/ for sm_100a into lib/libb200pf.so (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+
+
+EXPORTS = [
+    "b200pf_last_error", "b200pf_version", "b200pf_device_count", "b200pf_model_dir_probe", "b200pf_engine_create", "b200pf_engine_destroy",
+    "b200pf_engine_config", "b200pf_engine_vocab_size", "b200pf_engine_token", "b200pf_engine_lang",
+    "b200pf_engine_set_option", "b200pf_engine_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
+    "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
+    "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
+    "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_conv3",
+    "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
+]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200PFError("libb200pf.so is not built (run __graft_entry__.build() or make -C asr-2pass_b200/csrc); "
+                          "there is no fallback path")
+    L = C.CDLL(LIB_PATH)
+    L.b200pf_last_error.restype = C.c_char_p
+    L.b200pf_engine_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.b200pf_model_dir_probe.argtypes = [C.c_char_p, C.POINTER(Config), c_i32p, c_i32p]
+    L.b200pf_engine_destroy.argtypes = [C.c_void_p]
+    L.b200pf_engine_destroy.restype = None
+    L.b200pf_engine_config.argtypes = [C.c_void_p, C.POINTER(Config)]
+    L.b200pf_engine_vocab_size.argtypes = [C.c_void_p]
+    L.b200pf_engine_token.argtypes = [C.c_void_p, C.c_int]
+    L.b200pf_engine_token.restype = C.c_char_p
+    L.b200pf_engine_lang.argtypes = [C.c_void_p]
+    L.b200pf_engine_lang.restype = C.c_char_p
+    L.b200pf_engine_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.b200pf_engine_stream.argtypes = [C.c_void_p]
+    L.b200pf_engine_stream.restype = C.c_void_p
+    L.b200pf_num_fbank_frames.argtypes = [C.c_int64]
+    L.b200pf_num_lfr_frames.argtypes = [C.c_int64]
+    L.b200pf_rows_for.argtypes = [c_i64p, C.c_int]
+    L.b200pf_rows_for.restype = C.c_int64
+    L.b200pf_batch_create.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.b200pf_batch_destroy.argtypes = [C.c_void_p]
+    L.b200pf_batch_destroy.restype = None
+    L.b200pf_batch_stage_s16.argtypes = [C.c_void_p, C.c_void_p, c_i64p, C.c_int, C.c_void_p]
+    L.b200pf_batch_stage_f32.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, C.c_void_p]
+    L.b200pf_batch_run.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200pf_batch_collect.argtypes = [C.c_void_p, C.POINTER(Result), C.c_void_p]
+    L.b200pf_forward_s16.argtypes = [C.c_void_p, C.c_void_p, c_i64p, C.c_int, C.POINTER(Result)]
+    L.b200pf_forward_f32.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, C.POINTER(Result)]
+    L.b200pf_batch_launches.argtypes = [C.c_void_p]
+    L.b200pf_batch_launches.restype = C.c_int64
+    L.b200pf_batch_flops.argtypes = [C.c_void_p]
+    L.b200pf_batch_flops.restype = C.c_double
+    L.b200pf_batch_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_int, c_f32p, C.c_int64, c_i64p]
+    L.b200pf_op_gemm.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, c_f32p, c_i32p]
+    L.b200pf_op_conv3.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p]
+    L.b200pf_op_layernorm.argtypes = [C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, C.c_float, C.c_int, c_f32p, c_f32p]
+    L.b200pf_op_attention.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int,
+                                      C.c_int64, C.c_int64, C.c_int, c_f32p]
+    L.b200pf_op_fsmn.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, C.c_int, c_f32p]
+    L.b200pf_op_cif.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, C.c_int, C.c_float, c_i32p, c_f32p, c_f32p, c_i32p, C.c_int64]
+    L.b200pf_op_frontend.argtypes = [C.c_void_p, c_i16p, C.c_int64, c_f32p, c_f32p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200PFError("b200pf error %d: %s" % (rc, lib().b200pf_last_error().decode("utf-8", "replace")))
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, typ=c_f32p):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def model_dir_probe(model_dir):
+    cfg = Config()
+    nt, nw = C.c_int32(), C.c_int32()
+    _check(lib().b200pf_model_dir_probe(model_dir.encode(), C.byref(cfg), C.byref(nt), C.byref(nw)))
+    return cfg, nt.value, nw.value
+
+
+def device_count():
+    return lib().b200pf_device_count()
+
+
+class Engine:
+    """One GPU: resident bf16 weights + workspace (replaces Paraformer::InitAsr, paraformer.cpp:21-53)."""
+
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0):
+        self.h = C.c_void_p()
+        _check(lib().b200pf_engine_create(model_dir.encode(), device, max_rows, max_segments, C.byref(self.h)))
+        self.cfg = Config()
+        _check(lib().b200pf_engine_config(self.h, C.byref(self.cfg)))
+
+    def close(self):
+        if self.h:
+            lib().b200pf_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        _check(lib().b200pf_engine_set_option(self.h, key.encode(), int(value)))
+
+    @property
+    def stream(self):
+        return lib().b200pf_engine_stream(self.h)
+
+    def tokens(self):
+        n = lib().b200pf_engine_vocab_size(self.h)
+        return [lib().b200pf_engine_token(self.h, i).decode("utf-8") for i in range(n)]
+
+    @property
+    def lang(self):
+        return lib().b200pf_engine_lang(self.h).decode()
+
+    def frontend(self, pcm16):
+        pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+        nfb = lib().b200pf_num_fbank_frames(len(pcm16))
+        T = lib().b200pf_num_lfr_frames(len(pcm16))
+        fb = np.zeros((nfb, 80), np.float32)
+        feats = np.zeros((T, 560), np.float32)
+        if nfb:
+            _check(lib().b200pf_op_frontend(self.h, _p(pcm16, c_i16p), len(pcm16), _p(fb), _p(feats)))
+        return fb, feats
+
+
+class Batch:
+    """One batch of segments (device PCM + packed layout + results)."""
+
+    def __init__(self, engine, max_samples):
+        self.engine = engine
+        self.h = C.c_void_p()
+        _check(lib().b200pf_batch_create(engine.h, int(max_samples), C.byref(self.h)))
+        self._keep = None
+        self.n_seg = 0
+
+    def close(self):
+        if self.h:
+            lib().b200pf_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stage_s16(self, pcm16, offsets, stream=None):
+        """pcm16: int16 numpy array or an integer host address; offsets: int64 [n_seg+1]."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if isinstance(pcm16, np.ndarray):
+            pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+            ptr = pcm16.ctypes.data
+        else:
+            ptr = int(pcm16)
+        self._keep = (pcm16, offsets)
+        self.n_seg = len(offsets) - 1
+        _check(lib().b200pf_batch_stage_s16(self.h, C.c_void_p(ptr), _p(offsets, c_i64p), self.n_seg, C.c_void_p(stream or 0)))
+
+    def stage_f32(self, segments, stream=None):
+        segs = [np.ascontiguousarray(s, dtype=np.float32) for s in segments]
+        n = len(segs)
+        ptrs = (c_f32p * n)(*[s.ctypes.data_as(c_f32p) for s in segs])
+        lens = np.asarray([len(s) for s in segs], np.int32)
+        self._keep = (segs, ptrs, lens)
+        self.n_seg = n
+        _check(lib().b200pf_batch_stage_f32(self.h, ptrs, _p(lens, c_i32p), n, C.c_void_p(stream or 0)))
+
+    def run(self, stream=None):
+        _check(lib().b200pf_batch_run(self.h, C.c_void_p(stream or 0)))
+
+    def collect(self, cap_tokens=None, stream=None):
+        n = self.n_seg
+        cap = int(cap_tokens or self.engine.cfg.max_rows)
+        out = dict(token_counts=np.zeros(n, np.int32), token_offsets=np.zeros(n + 1, np.int32),
+                   lfr_frames=np.zeros(n, np.int32), token_ids=np.zeros(cap, np.int32), fire_frames=np.zeros(cap, np.int32))
+        r = Result(_p(out["token_counts"], c_i32p), _p(out["token_offsets"], c_i32p), _p(out["lfr_frames"], c_i32p),
+                   _p(out["token_ids"], c_i32p), _p(out["fire_frames"], c_i32p), cap, 0)
+        _check(lib().b200pf_batch_collect(self.h, C.byref(r), C.c_void_p(stream or 0)))
+        nt = int(r.n_tokens)
+        out["token_ids"] = out["token_ids"][:nt]
+        out["fire_frames"] = out["fire_frames"][:nt]
+        out["n_tokens"] = nt
+        return out
+
+    def forward_s16(self, pcm16, offsets):
+        self.stage_s16(pcm16, offsets)
+        self.run()
+        return self.collect()
+
+    def forward_f32(self, segments):
+        self.stage_f32(segments)
+        self.run()
+        return self.collect()
+
+    @property
+    def launches(self):
+        return int(lib().b200pf_batch_launches(self.h))
+
+    @property
+    def flops(self):
+        return float(lib().b200pf_batch_flops(self.h))
+
+    def tap(self, name, seg, cap=None):
+        cfg = self.engine.cfg
+        cap = int(cap or (2100 * max(cfg.vocab, 560)))
+        buf = np.zeros(cap, np.float32)
+        shape = (C.c_int64 * 2)()
+        _check(lib().b200pf_batch_tap(self.h, name.encode(), int(seg), _p(buf), cap, shape))
+        r, c = int(shape[0]), int(shape[1])
+        a = buf[: r * c].copy()
+        return a.reshape(r) if c == 1 else a.reshape(r, c)
+
+
+# ---- single-operator wrappers (parity tests) ---------------------------------------------------------
+def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=False, device=0):
+    A, W = _f32(A), _f32(W)
+    M, K = A.shape
+    N = W.shape[0]
+    bias, add, res = _f32(bias), _f32(add), _f32(res)
+    out = np.zeros((M, N), np.float32)
+    am = np.zeros(M, np.int32) if argmax else None
+    _check(lib().b200pf_op_gemm(device, _p(A), _p(W), _p(bias), _p(add), _p(res), M, N, K, int(relu), int(out_bf16),
+                                _p(out), _p(am, c_i32p)))
+    return (out, am) if argmax else out
+
+
+def op_conv3(X, Wr, bias, device=0):
+    X, Wr, bias = _f32(X), _f32(Wr), _f32(bias)
+    M, Cc = X.shape
+    out = np.zeros((M, Cc), np.float32)
+    _check(lib().b200pf_op_conv3(device, _p(X), _p(Wr), _p(bias), M, Cc, _p(out)))
+    return out
+
+
+def op_layernorm(x, gamma, beta, eps=1e-12, in_bf16=False, device=0):
+    x, gamma, beta = _f32(x), _f32(gamma), _f32(beta)
+    rows, D = x.shape
+    o32 = np.zeros((rows, D), np.float32)
+    o16 = np.zeros((rows, D), np.float32)
+    _check(lib().b200pf_op_layernorm(device, _p(x), rows, D, _p(gamma), _p(beta), eps, int(in_bf16), _p(o32), _p(o16)))
+    return o32, o16
+
+
+def op_attention(q, k, v, q_off, q_len, kv_off, kv_len, n_heads=4, impl=0, device=0):
+    q, k, v = _f32(q), _f32(k), _f32(v)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    q_off, q_len, kv_off, kv_len = i32(q_off), i32(q_len), i32(kv_off), i32(kv_len)
+    out = np.zeros_like(q)
+    _check(lib().b200pf_op_attention(device, _p(q), _p(k), _p(v), _p(q_off, c_i32p), _p(q_len, c_i32p), _p(kv_off, c_i32p),
+                                     _p(kv_len, c_i32p), len(q_len), n_heads, q.shape[0], k.shape[0], impl, _p(out)))
+    return out
+
+
+def op_fsmn(x, w, seg_off, device=0):
+    x, w = _f32(x), _f32(w).reshape(512, 11)
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)
+    out = np.zeros_like(x)
+    _check(lib().b200pf_op_fsmn(device, _p(x), _p(w), _p(seg_off, c_i32p), len(seg_off) - 1, _p(out)))
+    return out
+
+
+def op_cif(alphas, hidden, seg_off, threshold=1.0, device=0):
+    alphas, hidden = _f32(alphas), _f32(hidden)
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int32)
+    n = len(seg_off) - 1
+    rows = len(alphas)
+    n_tok = np.zeros(n, np.int32)
+    fires = np.zeros(rows, np.float32)
+    emb = np.zeros((rows, 512), np.float32)
+    ff = np.zeros(rows, np.int32)
+    _check(lib().b200pf_op_cif(device, _p(alphas), _p(hidden), _p(seg_off, c_i32p), n, threshold, _p(n_tok, c_i32p),
+                               _p(fires), _p(emb), _p(ff, c_i32p), rows))
+    tot = int(n_tok.sum())
+    return n_tok, fires, emb[:tot], ff[:tot]

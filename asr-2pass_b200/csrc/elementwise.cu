@@ -1,0 +1,381 @@
+// K3 LayerNorm, K6 FSMN memory block, K7/K8 CIF predictor tail, K11 argmax decode.  See kernels.cuh.
+#include "kernels.cuh"
+
+namespace pf {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (two-pass mean / variance in fp32).
+// ------------------------------------------------------------------------------------------------
+template <int D, bool IN_BF16>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                 float* __restrict__ out_f32, const int2* __restrict__ row_info, int zero_gap) {
+  constexpr int VW = IN_BF16 ? 8 : 4;            // elements per vector load
+  constexpr int NVEC = D / VW;                   // vectors per row
+  constexpr int PER = (NVEC + 31) / 32;          // vectors per lane
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nrows = rows_dev ? *rows_dev : rows;
+  if (row >= nrows) return;
+  const bool gap = zero_gap && row_info && row_info[row].x < 0;
+
+  float v[PER * VW];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < NVEC) {
+      if (IN_BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + (size_t)row * D + vi * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[i * 8 + 2 * k] = __low2float(h[k]); v[i * 8 + 2 * k + 1] = __high2float(h[k]); }
+      } else {
+        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + (size_t)row * D + vi * 4);
+        v[i * 4] = f.x; v[i * 4 + 1] = f.y; v[i * 4 + 2] = f.z; v[i * 4 + 3] = f.w;
+      }
+#pragma unroll
+      for (int k = 0; k < VW; ++k) sum += v[i * VW + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < VW; ++k) v[i * VW + k] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    if (lane + 32 * i < NVEC) {
+#pragma unroll
+      for (int k = 0; k < VW; ++k) { const float d = v[i * VW + k] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < NVEC) {
+      const int c = vi * VW;
+      float o[VW];
+#pragma unroll
+      for (int k = 0; k < VW; k += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c + k);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c + k);
+        o[k] = (v[i * VW + k] - mean) * rstd * g.x + b.x;
+        o[k + 1] = (v[i * VW + k + 1] - mean) * rstd * g.y + b.y;
+        o[k + 2] = (v[i * VW + k + 2] - mean) * rstd * g.z + b.z;
+        o[k + 3] = (v[i * VW + k + 3] - mean) * rstd * g.w + b.w;
+      }
+      if (gap) {
+#pragma unroll
+        for (int k = 0; k < VW; ++k) o[k] = 0.f;
+      }
+      if (out_f32) {
+#pragma unroll
+        for (int k = 0; k < VW; k += 4)
+          *reinterpret_cast<float4*>(out_f32 + (size_t)row * D + c + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+      }
+      if (out_bf16) {
+        uint32_t pk[VW / 2];
+#pragma unroll
+        for (int k = 0; k < VW / 2; ++k) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (VW == 8)
+          *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * D + c) = make_uint4(pk[0], pk[1], pk[VW / 2 - 2], pk[VW / 2 - 1]);
+        else
+          *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D + c) = make_uint2(pk[0], pk[1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FSMN: depthwise conv k=11 along time inside a segment + identity.  Thread = (row, 8 channels).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
+            const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
+            __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
+  const int nrows = rows_dev ? *rows_dev : rows;
+  const int row = blockIdx.x * 4 + threadIdx.y;
+  if (row >= nrows) return;
+  const int c = threadIdx.x * 8;
+  const int2 info = row_info[row];
+  if (info.x < 0) {
+    if (mode == 0) *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 512 + c) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 11; ++j) {
+    const int tt = info.x + j - 5;
+    if (tt >= 0 && tt < info.y) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + (size_t)(row + j - 5) * ld_in + col0 + c);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const float4 w0 = *reinterpret_cast<const float4*>(w_t + j * 512 + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_t + j * 512 + c + 4);
+      const float idn = (j == 5) ? 1.f : 0.f;  // + identity branch
+      acc[0] += (w0.x + idn) * __low2float(h[0]); acc[1] += (w0.y + idn) * __high2float(h[0]);
+      acc[2] += (w0.z + idn) * __low2float(h[1]); acc[3] += (w0.w + idn) * __high2float(h[1]);
+      acc[4] += (w1.x + idn) * __low2float(h[2]); acc[5] += (w1.y + idn) * __high2float(h[2]);
+      acc[6] += (w1.z + idn) * __low2float(h[3]); acc[7] += (w1.w + idn) * __high2float(h[3]);
+    }
+  }
+  if (mode == 0) {
+    uint4 o;
+    __nv_bfloat162 p;
+    p = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&p);
+    *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 512 + c) = o;
+  } else {
+    float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)row * 512 + c);
+    float4 a = yp[0], b = yp[1];
+    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
+    b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
+    yp[0] = a; yp[1] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CIF
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cif_alpha_kernel(const float* __restrict__ h, int M, const float* __restrict__ w, const float* __restrict__ b,
+                 const int2* __restrict__ row_info, float tail, float* __restrict__ alpha) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  if (row_info[row].x < 0) {
+    if (lane == 0) alpha[row] = tail;  // tail_process_fn: extra frame with alpha = tail_threshold
+    return;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(h + (size_t)row * 512 + (lane + 32 * i) * 4);
+    const float4 ww = *reinterpret_cast<const float4*>(w + (lane + 32 * i) * 4);
+    s += a.x * ww.x + a.y * ww.y + a.z * ww.z + a.w * ww.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float x = s + b[0];
+    float al = 1.0f / (1.0f + expf(-x));
+    al = fmaxf(al * 1.0f - 0.0f, 0.f);  // relu(alpha * smooth_factor - noise_threshold)
+    alpha[row] = al;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+cif_fire_kernel(const float* __restrict__ alpha, const int* __restrict__ row_off, const int* __restrict__ seg_T,
+                float threshold, float* __restrict__ cur_o, float* __restrict__ rem_o, float* __restrict__ fire_val,
+                int* __restrict__ n_tok, int* __restrict__ fire_row) {
+  const int seg = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int base = row_off[seg];
+  const int n = seg_T[seg] + 1;  // frames + tail frame
+  float integrate = 0.f;
+  int ntok = 0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int i = c0 + lane;
+    const float a = (i < n) ? alpha[base + i] : 0.f;
+    float my_cur = 0.f, my_rem = 0.f, my_fv = 0.f;
+    bool my_fire = false;
+    const int lim = min(32, n - c0);
+    for (int k = 0; k < lim; ++k) {
+      const float ak = __shfl_sync(0xffffffffu, a, k);
+      const float dc = __fsub_rn(1.0f, integrate);        // distribution_completion
+      integrate = __fadd_rn(integrate, ak);
+      const float fv = integrate;
+      const bool fire = integrate >= threshold;
+      const float cur = fire ? dc : ak;
+      const float rem = __fsub_rn(ak, cur);
+      if (fire) integrate = __fsub_rn(integrate, 1.0f);
+      if (lane == k) { my_cur = cur; my_rem = rem; my_fv = fv; my_fire = fire; }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, my_fire);
+    if (i < n) {
+      cur_o[base + i] = my_cur;
+      rem_o[base + i] = my_rem;
+      fire_val[base + i] = my_fv;
+    }
+    if (my_fire) fire_row[base + ntok + __popc(mask & ((1u << lane) - 1u))] = base + i;
+    ntok += __popc(mask);
+  }
+  if (lane == 0) n_tok[seg] = ntok;
+}
+
+__global__ void __launch_bounds__(1024)
+cif_scan_kernel(const int* __restrict__ n_tok, int n_seg, int* __restrict__ tok_off, int* __restrict__ total) {
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n_seg + 1023) / 1024;
+  const int b = tid * per;
+  int local = 0;
+  for (int i = 0; i < per; ++i) if (b + i < n_seg) local += n_tok[b + i];
+  int incl = local;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, off);
+      if (lane >= off) v += t;
+    }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  int run = incl - local + (warp > 0 ? wsum[warp - 1] : 0);
+  for (int i = 0; i < per; ++i) {
+    if (b + i < n_seg) { tok_off[b + i] = run; run += n_tok[b + i]; }
+  }
+  if (tid == 1023) { tok_off[n_seg] = wsum[31]; *total = wsum[31]; }
+}
+
+__global__ void __launch_bounds__(128)
+cif_embed_kernel(const float* __restrict__ enc, const float* __restrict__ cur, const float* __restrict__ rem,
+                 const int* __restrict__ fire_row, const int* __restrict__ row_off, const int* __restrict__ tok_off,
+                 int n_seg, float* __restrict__ emb, int2* __restrict__ tok_info, int* __restrict__ tok_frame) {
+  const int g = blockIdx.x;
+  if (g >= tok_off[n_seg]) return;
+  int lo = 0, hi = n_seg;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tok_off[mid] <= g) lo = mid; else hi = mid;
+  }
+  // segments with zero tokens share an offset with their successor: move to the last one that starts here
+  const int seg = lo;
+  const int j = g - tok_off[seg];
+  const int base = row_off[seg];
+  const int f = fire_row[base + j];
+  const int fprev = j > 0 ? fire_row[base + j - 1] : base - 1;
+  const int c = threadIdx.x * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j > 0) {
+    const float r = rem[fprev];
+    const float4 hv = *reinterpret_cast<const float4*>(enc + (size_t)fprev * 512 + c);
+    acc = make_float4(__fmul_rn(r, hv.x), __fmul_rn(r, hv.y), __fmul_rn(r, hv.z), __fmul_rn(r, hv.w));
+  }
+  for (int t = fprev + 1; t <= f; ++t) {
+    const float cw = cur[t];
+    const float4 hv = *reinterpret_cast<const float4*>(enc + (size_t)t * 512 + c);
+    acc.x = __fadd_rn(acc.x, __fmul_rn(cw, hv.x));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(cw, hv.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(cw, hv.z));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(cw, hv.w));
+  }
+  *reinterpret_cast<float4*>(emb + (size_t)g * 512 + c) = acc;
+  if (threadIdx.x == 0) {
+    tok_info[g] = make_int2(j, tok_off[seg + 1] - tok_off[seg]);
+    tok_frame[g] = f - base;
+  }
+}
+
+__global__ void argmax_decode_kernel(const unsigned long long* __restrict__ packed, const int* __restrict__ n_dev, int cap,
+                                     int* __restrict__ ids) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_dev ? min(*n_dev, cap) : cap;
+  if (g >= n) return;
+  ids[g] = (int)(0xFFFFFFFFu - (uint32_t)(packed[g] & 0xFFFFFFFFull));
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+template <int D>
+int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, const float* gamma, const float* beta,
+                float eps, __nv_bfloat16* ob, float* of, const int2* ri, int zg, cudaStream_t s) {
+  const int blocks = (rows + 7) / 8;
+  if (in_is_bf16)
+    layernorm_kernel<D, true><<<blocks, 256, 0, s>>>(in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
+  else
+    layernorm_kernel<D, false><<<blocks, 256, 0, s>>>(in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_dev, int D, const float* gamma,
+                     const float* beta, float eps, __nv_bfloat16* out_bf16, float* out_f32, const int2* row_info,
+                     int zero_gap, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  switch (D) {
+    case 512: return ln_dispatch<512>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
+    case 560: return ln_dispatch<560>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
+    case 2048: return ln_dispatch<2048>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  dim3 block(64, 4);
+  fsmn_kernel<<<(rows + 3) / 4, block, 0, s>>>(in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
+  return (int)cudaGetLastError();
+}
+
+int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,
+                     float* alpha, cudaStream_t s) {
+  if (M <= 0) return 0;
+  cif_alpha_kernel<<<(M + 7) / 8, 256, 0, s>>>(h, M, w, b, row_info, tail, alpha);
+  return (int)cudaGetLastError();
+}
+
+int cif_fire_launch(const float* alpha, const int* row_off, const int* seg_T, int n_seg, float threshold, float* cur,
+                    float* rem, float* fire_val, int* n_tok, int* fire_row, cudaStream_t s) {
+  if (n_seg <= 0) return 0;
+  cif_fire_kernel<<<n_seg, 32, 0, s>>>(alpha, row_off, seg_T, threshold, cur, rem, fire_val, n_tok, fire_row);
+  return (int)cudaGetLastError();
+}
+
+int cif_scan_launch(const int* n_tok, int n_seg, int* tok_off, int* n_tok_total, cudaStream_t s) {
+  if (n_seg <= 0) return 0;
+  cif_scan_kernel<<<1, 1024, 0, s>>>(n_tok, n_seg, tok_off, n_tok_total);
+  return (int)cudaGetLastError();
+}
+
+int cif_embed_launch(const float* enc_f32, const float* cur, const float* rem, const int* fire_row, const int* row_off,
+                     const int* tok_off, int n_seg, int tok_cap, float* emb, int2* tok_info, int* tok_frame,
+                     cudaStream_t s) {
+  if (tok_cap <= 0) return 0;
+  cif_embed_kernel<<<tok_cap, 128, 0, s>>>(enc_f32, cur, rem, fire_row, row_off, tok_off, n_seg, emb, tok_info, tok_frame);
+  return (int)cudaGetLastError();
+}
+
+int argmax_decode_launch(const unsigned long long* packed, const int* n_dev, int cap, int* ids, cudaStream_t s) {
+  if (cap <= 0) return 0;
+  argmax_decode_kernel<<<(cap + 255) / 256, 256, 0, s>>>(packed, n_dev, cap, ids);
+  return (int)cudaGetLastError();
+}
+
+int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_kernel<<<(int)blocks, 256, 0, s>>>(in, out, n);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pf

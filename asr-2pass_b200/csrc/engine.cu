@@ -1,0 +1,742 @@
+// b200pf engine: model loading, workspace, and the kernel schedule of one forward pass.
+// The schedule is the B200-native replacement of Paraformer::Forward (onnxruntime/src/paraformer.cpp:463-589):
+//   K1 fbank / LFR / CMVN / pos-enc  ->  50 x SAN-M encoder layer  ->  CIF predictor  ->  16(+1) x SAN-M decoder
+//   layer  ->  vocabulary projection with fused greedy argmax.
+// Everything is enqueued on one stream with no host synchronisation; token counts stay on the device.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "model_dir.h"
+
+namespace pf {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const std::string& last_error() { return g_err; }
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return B200PF_ERR_CUDA;
+}
+
+static uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int num_fbank_frames(int64_t n) { return n < 400 ? 0 : (int)(1 + (n - 400) / 160); }
+int num_lfr_frames(int64_t n) {
+  const int nfb = num_fbank_frames(n);
+  return nfb <= 0 ? 0 : (nfb + 5) / 6;
+}
+
+}  // namespace pf
+
+using namespace pf;
+
+#define CK(call, what)                           \
+  do {                                           \
+    int rc_ = check_cuda((call), what);          \
+    if (rc_) return rc_;                         \
+  } while (0)
+#define CKL(call, what)                                              \
+  do {                                                               \
+    int rc_ = (call);                                                \
+    if (rc_) return check_cuda((cudaError_t)rc_, what);              \
+  } while (0)
+
+namespace {
+
+struct Loader {
+  b200pf_engine* e;
+  WeightFile* wf;
+  std::string err;
+  bool ok = true;
+
+  const HostTensor* get(const std::string& name, std::vector<int64_t> shape) {
+    auto it = wf->tensors.find(name);
+    if (it == wf->tensors.end()) { fail("missing tensor " + name); return nullptr; }
+    if (it->second.shape != shape) { fail("bad shape for " + name); return nullptr; }
+    return &it->second;
+  }
+  void fail(const std::string& m) { if (ok) { ok = false; err = m; } }
+
+  float* up_f32(const float* h, size_t n) {
+    float* d = (float*)e->warena.take(n * 4);
+    if (!d) { fail("weight arena exhausted"); return nullptr; }
+    if (cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) fail("weight upload failed");
+    return d;
+  }
+  __nv_bfloat16* up_bf16(const float* h, size_t n) {
+    std::vector<uint16_t> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_bf16_rne(h[i]);
+    void* d = e->warena.take(n * 2);
+    if (!d) { fail("weight arena exhausted"); return nullptr; }
+    if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) fail("weight upload failed");
+    return (__nv_bfloat16*)d;
+  }
+  Norm norm(const std::string& p, int n) {
+    Norm r;
+    auto g = get(p + ".weight", {n}), b = get(p + ".bias", {n});
+    if (g && b) { r.g = up_f32(g->data.data(), n); r.b = up_f32(b->data.data(), n); }
+    return r;
+  }
+  Linear linear(const std::string& p, int out, int in, bool bias = true) {
+    Linear r;
+    r.out = out; r.in = in;
+    auto w = get(p + ".weight", {out, in});
+    if (w) r.w = up_bf16(w->data.data(), (size_t)out * in);
+    if (bias) {
+      auto b = get(p + ".bias", {out});
+      if (b) r.b = up_f32(b->data.data(), out);
+    }
+    return r;
+  }
+  float* fsmn(const std::string& p, int D, int K) {  // [D,1,K] -> tap-major [K][D]
+    auto w = get(p + ".weight", {D, 1, K});
+    if (!w) return nullptr;
+    std::vector<float> t((size_t)K * D);
+    for (int c = 0; c < D; ++c)
+      for (int k = 0; k < K; ++k) t[(size_t)k * D + c] = w->data[(size_t)c * K + k];
+    return up_f32(t.data(), t.size());
+  }
+};
+
+// Front-end tables: same formulas, in the same precision, as knf (feature-window.cc:25-55,
+// mel-computations.cc:107-200) and the encoder's sinusoidal position encoding.
+bool build_frontend_tables(b200pf_engine* e, Loader& L, const std::vector<float>& means, const std::vector<float>& vars) {
+  std::vector<float> window(400);
+  const double a = (2.0 * M_PI) / 399.0;
+  for (int i = 0; i < 400; ++i) window[i] = (float)(0.54 - 0.46 * cos(a * (double)i));
+  std::vector<double> tw(512);
+  for (int k = 0; k < 256; ++k) { tw[2 * k] = cos(-2.0 * M_PI * k / 512.0); tw[2 * k + 1] = sin(-2.0 * M_PI * k / 512.0); }
+  auto mel = [](float f) { return 1127.0f * logf(1.0f + f / 700.0f); };
+  const float sample_freq = 16000.0f, nyquist = 0.5f * sample_freq;
+  const float fft_bin_width = sample_freq / 512;
+  const float mel_low = mel(20.0f), mel_high = mel(nyquist + 0.0f);
+  const float delta = (mel_high - mel_low) / (80 + 1);
+  std::vector<int> range(160), woff(80);
+  std::vector<float> w(1024, 0.f);
+  int used = 0;
+  for (int bin = 0; bin < 80; ++bin) {
+    const float left = mel_low + bin * delta, center = mel_low + (bin + 1) * delta, right = mel_low + (bin + 2) * delta;
+    int first = -1, last = -1;
+    std::vector<float> tb(256, 0.f);
+    for (int i = 0; i < 256; ++i) {
+      const float freq = fft_bin_width * i;
+      const float m = mel(freq);
+      if (m > left && m < right) {
+        float wt;
+        if (m <= center) wt = (m - left) / (center - left);
+        else wt = (right - m) / (right - center);
+        tb[i] = wt;
+        if (first == -1) first = i;
+        last = i;
+      }
+    }
+    const int size = last + 1 - first;
+    if (first < 0 || used + size > 1024) { L.fail("mel table overflow"); return false; }
+    range[2 * bin] = first; range[2 * bin + 1] = size; woff[bin] = used;
+    for (int k = 0; k < size; ++k) w[used + k] = tb[first + k];
+    used += size;
+  }
+  const int F = e->cfg.feat_dim, half = F / 2, pe_rows = 2048;
+  std::vector<float> pe((size_t)pe_rows * F);
+  const float inc = (float)(-(log(10000.0) / (half - 1)));
+  for (int t = 0; t < pe_rows; ++t)
+    for (int i = 0; i < half; ++i) {
+      const float inv = expf((float)i * inc);
+      const float st = (float)(t + 1) * inv;
+      pe[(size_t)t * F + i] = sinf(st);
+      pe[(size_t)t * F + half + i] = cosf(st);
+    }
+  e->ft.window = L.up_f32(window.data(), 400);
+  e->ft.twiddle = (const double2*)L.up_f32((const float*)tw.data(), 1024);
+  e->ft.mel_range = (const int2*)L.up_f32((const float*)range.data(), 160);
+  e->ft.mel_w = L.up_f32(w.data(), 1024);
+  e->ft.mel_w_off = (const int*)L.up_f32((const float*)woff.data(), 80);
+  e->ft.cmvn_mean = L.up_f32(means.data(), means.size());
+  e->ft.cmvn_var = L.up_f32(vars.data(), vars.size());
+  e->ft.pos_enc = L.up_f32(pe.data(), pe.size());
+  e->ft.pe_rows = pe_rows;
+  return L.ok;
+}
+
+template <class T>
+bool ws_take(b200pf_engine* e, T** p, size_t n) {
+  *p = (T*)e->ws.take(n * sizeof(T));
+  return *p != nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200pf_last_error(void) { return last_error().c_str(); }
+int b200pf_version(void) { return 100; }
+
+int b200pf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int b200pf_num_fbank_frames(int64_t n) { return num_fbank_frames(n); }
+int b200pf_num_lfr_frames(int64_t n) { return num_lfr_frames(n); }
+int64_t b200pf_rows_for(const int64_t* n_samples, int n_seg) {
+  int64_t r = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    const int T = num_lfr_frames(n_samples[i]);
+    if (T > 0) r += T + 1;
+  }
+  return r;
+}
+
+static void fill_config(const WeightFile& wf, int fs, b200pf_config* c) {
+  auto cfgv = [&](const char* k, double dflt) { auto it = wf.cfg.find(k); return it == wf.cfg.end() ? dflt : it->second; };
+  c->feat_dim = (int)cfgv("feat_dim", 560); c->d_model = (int)cfgv("d_model", 512); c->n_heads = (int)cfgv("n_heads", 4);
+  c->d_ff = (int)cfgv("d_ff", 2048); c->n_enc = (int)cfgv("n_enc", 50); c->n_dec = (int)cfgv("n_dec", 16);
+  c->kernel = (int)cfgv("kernel", 11); c->vocab = (int)cfgv("vocab", 8404); c->pred_residual = (int)cfgv("pred_residual", 0);
+  c->cif_threshold = (float)cfgv("cif_threshold", 1.0); c->tail_threshold = (float)cfgv("tail_threshold", 0.45);
+  c->ln_eps = (float)cfgv("ln_eps", 1e-12);
+  c->sample_rate = fs;
+}
+
+int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors) {
+  if (!model_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  const std::string dir(model_dir);
+  std::string err, lang;
+  WeightFile wf;
+  std::vector<float> means, vars;
+  std::vector<std::string> toks;
+  int fs = 16000;
+  if (!read_weight_file(dir + "/model.b200pf", &wf, &err) || !read_am_mvn(dir + "/am.mvn", &means, &vars, &err) ||
+      !read_tokens_json(dir + "/tokens.json", &toks, &err) || !read_config_yaml(dir + "/config.yaml", &fs, &lang, &err)) {
+    set_error(err);
+    return B200PF_ERR_IO;
+  }
+  memset(out, 0, sizeof(*out));
+  fill_config(wf, fs, out);
+  if ((int)means.size() != out->feat_dim) { set_error("am.mvn dimension != feat_dim"); return B200PF_ERR_IO; }
+  if (n_tokens) *n_tokens = (int)toks.size();
+  if (n_tensors) *n_tensors = (int)wf.tensors.size();
+  return 0;
+}
+
+int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out) {
+  if (!model_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: the B200 path has no CPU fallback");
+    return B200PF_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) { set_error("bad device index"); return B200PF_ERR_INVALID; }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) { set_error("device is not sm_100 (Blackwell B200): kernels are built for sm_100a only"); return B200PF_ERR_NO_DEVICE; }
+  CK(cudaSetDevice(device), "cudaSetDevice");
+
+  const std::string dir(model_dir);
+  std::string err;
+  WeightFile wf;
+  if (!read_weight_file(dir + "/model.b200pf", &wf, &err)) { set_error(err); return B200PF_ERR_IO; }
+  std::vector<float> means, vars;
+  if (!read_am_mvn(dir + "/am.mvn", &means, &vars, &err)) { set_error(err); return B200PF_ERR_IO; }
+  std::unique_ptr<b200pf_engine> e(new b200pf_engine);
+  if (!read_tokens_json(dir + "/tokens.json", &e->tokens, &err)) { set_error(err); return B200PF_ERR_IO; }
+  int fs = 16000;
+  if (!read_config_yaml(dir + "/config.yaml", &fs, &e->lang, &err)) { set_error(err); return B200PF_ERR_IO; }
+
+  b200pf_config& c = e->cfg;
+  fill_config(wf, fs, &c);
+  c.max_rows = max_rows > 0 ? max_rows : 32768;
+  c.max_segments = max_segments > 0 ? max_segments : 4096;
+  if (c.feat_dim != 560 || c.d_model != 512 || c.n_heads != 4 || c.d_ff != 2048 || c.kernel != 11 || (c.vocab & 3) ||
+      c.n_enc < 1 || c.n_dec < 0) {
+    set_error("unsupported architecture: kernels are specialised for feat 560, d_model 512, 4 heads, d_ff 2048, kernel 11, vocab % 4 == 0");
+    return B200PF_ERR_INVALID;
+  }
+  if ((int)means.size() != c.feat_dim) { set_error("am.mvn dimension != feat_dim"); return B200PF_ERR_IO; }
+  if ((int)e->tokens.size() != c.vocab) { set_error("tokens.json size != vocab"); return B200PF_ERR_IO; }
+  e->device = device;
+  cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
+  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+
+  // ---- weights ----
+  size_t wbytes = 64 << 20;
+  for (auto& kv : wf.tensors) wbytes += (size_t)kv.second.numel() * 4 + 512;
+  CK(cudaMalloc((void**)&e->warena.base, wbytes), "cudaMalloc(weights)");
+  e->warena.size = wbytes;
+  Loader L{e.get(), &wf};
+  const int D = c.d_model, Fd = c.d_ff, K = c.kernel;
+  e->enc.resize(c.n_enc);
+  for (int l = 0; l < c.n_enc && L.ok; ++l) {
+    const std::string p = l == 0 ? "encoder.encoders0.0" : "encoder.encoders." + std::to_string(l - 1);
+    EncLayer& w = e->enc[l];
+    w.din = l == 0 ? c.feat_dim : D;
+    w.ln1 = L.norm(p + ".norm1", w.din);
+    w.qkv = L.linear(p + ".self_attn.linear_q_k_v", 3 * D, w.din);
+    w.fsmn_wt = L.fsmn(p + ".self_attn.fsmn_block", D, K);
+    w.out = L.linear(p + ".self_attn.linear_out", D, D);
+    w.ln2 = L.norm(p + ".norm2", D);
+    w.w1 = L.linear(p + ".feed_forward.w_1", Fd, D);
+    w.w2 = L.linear(p + ".feed_forward.w_2", D, Fd);
+  }
+  e->enc_after = L.norm("encoder.after_norm", D);
+  if (L.ok) {  // cif_conv1d [512,512,3] -> [512, 3*512] tap-major so each tap is one K pass of the GEMM
+    auto w = L.get("predictor.cif_conv1d.weight", {D, D, 3});
+    auto b = L.get("predictor.cif_conv1d.bias", {D});
+    auto ow = L.get("predictor.cif_output.weight", {1, D});
+    auto ob = L.get("predictor.cif_output.bias", {1});
+    if (w && b && ow && ob) {
+      std::vector<float> r((size_t)D * 3 * D);
+      for (int o = 0; o < D; ++o)
+        for (int i = 0; i < D; ++i)
+          for (int t = 0; t < 3; ++t) r[(size_t)o * 3 * D + (size_t)t * D + i] = w->data[((size_t)o * D + i) * 3 + t];
+      e->pred_conv.w = L.up_bf16(r.data(), r.size());
+      e->pred_conv.b = L.up_f32(b->data.data(), D);
+      e->pred_conv.out = D; e->pred_conv.in = 3 * D;
+      e->pred_out_w = L.up_f32(ow->data.data(), D);
+      e->pred_out_b = L.up_f32(ob->data.data(), 1);
+    }
+  }
+  auto load_dec = [&](const std::string& p, bool attn) {
+    DecLayer w;
+    w.has_attn = attn;
+    w.ln1 = L.norm(p + ".norm1", D);
+    w.w1 = L.linear(p + ".feed_forward.w_1", Fd, D);
+    w.lnff = L.norm(p + ".feed_forward.norm", Fd);
+    w.w2 = L.linear(p + ".feed_forward.w_2", D, Fd, false);
+    if (attn) {
+      w.ln2 = L.norm(p + ".norm2", D);
+      w.fsmn_wt = L.fsmn(p + ".self_attn.fsmn_block", D, K);
+      w.ln3 = L.norm(p + ".norm3", D);
+      w.q = L.linear(p + ".src_attn.linear_q", D, D);
+      w.kv = L.linear(p + ".src_attn.linear_k_v", 2 * D, D);
+      w.out = L.linear(p + ".src_attn.linear_out", D, D);
+    }
+    return w;
+  };
+  for (int l = 0; l < c.n_dec && L.ok; ++l) e->dec.push_back(load_dec("decoder.decoders." + std::to_string(l), true));
+  if (L.ok) e->dec3 = load_dec("decoder.decoders3.0", false);
+  e->dec_after = L.norm("decoder.after_norm", D);
+  e->vocab = L.linear("decoder.output_layer", c.vocab, D);
+  if (L.ok) build_frontend_tables(e.get(), L, means, vars);
+  if (!L.ok) {
+    set_error(L.err);
+    cudaFree(e->warena.base);
+    cudaStreamDestroy(e->stream);
+    return B200PF_ERR_IO;
+  }
+
+  // ---- workspace ----
+  const size_t R = (size_t)c.max_rows;
+  size_t bytes = R * (6 * 80 * 4 + 560 * 4 + 512 * 4 + 560 * 2 + 1536 * 2 + 512 * 2 + 512 * 2 + 2048 * 2 + 512 * 4 + 512 * 2 +
+                      512 * 4 + 4 * 4 + 4 + 8 + 8) + (1 << 20);
+  CK(cudaMalloc((void**)&e->ws.base, bytes), "cudaMalloc(workspace)");
+  e->ws.size = bytes;
+  bool ok = ws_take(e.get(), &e->fb, R * 6 * 80) && ws_take(e.get(), &e->x0, R * 560) && ws_take(e.get(), &e->x, R * 512) &&
+            ws_take(e.get(), &e->hb, R * 560) && ws_take(e.get(), &e->qkv, R * 1536) && ws_take(e.get(), &e->mem, R * 512) &&
+            ws_take(e.get(), &e->att, R * 512) && ws_take(e.get(), &e->ffn, R * 2048) && ws_take(e.get(), &e->enc_f32, R * 512) &&
+            ws_take(e.get(), &e->enc_bf16, R * 512) && ws_take(e.get(), &e->y, R * 512) && ws_take(e.get(), &e->alpha, R) &&
+            ws_take(e.get(), &e->cif_cur, R) && ws_take(e.get(), &e->cif_rem, R) && ws_take(e.get(), &e->fire_val, R) &&
+            ws_take(e.get(), &e->fire_row, R) && ws_take(e.get(), &e->amax, R) && ws_take(e.get(), &e->tok_info, R);
+  if (!ok) { set_error("workspace arena exhausted"); return B200PF_ERR_CUDA; }
+  CK(cudaMemset(e->ws.base, 0, bytes), "cudaMemset(workspace)");
+  CK(cudaDeviceSynchronize(), "engine init");
+  *out = e.release();
+  return B200PF_OK;
+}
+
+void b200pf_engine_destroy(b200pf_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaFree(e->warena.base);
+  cudaFree(e->ws.base);
+  cudaFree(e->tap_feats);
+  cudaFree(e->tap_emb);
+  cudaFree(e->tap_logits);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out) {
+  if (!e || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  *out = e->cfg;
+  return 0;
+}
+int b200pf_engine_vocab_size(const b200pf_engine* e) { return e ? (int)e->tokens.size() : 0; }
+const char* b200pf_engine_token(const b200pf_engine* e, int id) {
+  if (!e || id < 0 || id >= (int)e->tokens.size()) return "";
+  return e->tokens[id].c_str();
+}
+const char* b200pf_engine_lang(const b200pf_engine* e) { return e ? e->lang.c_str() : ""; }
+void* b200pf_engine_stream(b200pf_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
+  if (!e || !key) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  if (strcmp(key, "taps") == 0) {
+    CK(cudaSetDevice(e->device), "cudaSetDevice");
+    if (value && !e->tap_logits) {
+      const size_t R = (size_t)e->cfg.max_rows;
+      CK(cudaMalloc((void**)&e->tap_feats, R * 560 * 4), "cudaMalloc(tap)");
+      CK(cudaMalloc((void**)&e->tap_emb, R * 512 * 4), "cudaMalloc(tap)");
+      CK(cudaMalloc((void**)&e->tap_logits, R * (size_t)e->cfg.vocab * 4), "cudaMalloc(tap logits)");
+    }
+    e->taps = value ? 1 : 0;
+    return 0;
+  }
+  set_error(std::string("unknown option ") + key);
+  return B200PF_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batch
+// ---------------------------------------------------------------------------------------------------
+int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** out) {
+  if (!e || !out || max_samples <= 0) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  std::unique_ptr<b200pf_batch> b(new b200pf_batch);
+  b->e = e;
+  b->max_samples = max_samples;
+  const size_t S = (size_t)e->cfg.max_segments, R = (size_t)e->cfg.max_rows;
+  CK(cudaMalloc(&b->d_pcm, (size_t)max_samples * 4 + 64), "cudaMalloc(pcm)");
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 63) & ~size_t(63); return o; };
+  const size_t o_sample = carve((S + 1) * 8), o_fb = carve((S + 1) * 4), o_row = carve((S + 1) * 4), o_T = carve(S * 4),
+               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8);
+  b->meta_bytes = off;
+  CK(cudaMallocHost((void**)&b->h_meta, off), "cudaMallocHost(meta)");
+  CK(cudaMalloc((void**)&b->d_meta, off), "cudaMalloc(meta)");
+  b->h_sample_off = (int64_t*)(b->h_meta + o_sample); b->d_sample_off = (const int64_t*)(b->d_meta + o_sample);
+  b->h_fb_off = (int*)(b->h_meta + o_fb);             b->d_fb_off = (const int*)(b->d_meta + o_fb);
+  b->h_row_off = (int*)(b->h_meta + o_row);           b->d_row_off = (const int*)(b->d_meta + o_row);
+  b->h_seg_T = (int*)(b->h_meta + o_T);               b->d_seg_T = (const int*)(b->d_meta + o_T);
+  b->h_row_seg = (int*)(b->h_meta + o_rseg);          b->d_row_seg = (const int*)(b->d_meta + o_rseg);
+  b->h_row_info = (int2*)(b->h_meta + o_rinfo);       b->d_row_info = (const int2*)(b->d_meta + o_rinfo);
+  b->h_work = (AttnWork*)(b->h_meta + o_work);        b->d_work = (const AttnWork*)(b->d_meta + o_work);
+  CK(cudaMalloc((void**)&b->d_n_tok, (2 * S + 2 + 2 * R + 16) * 4), "cudaMalloc(results)");
+  b->d_tok_off = b->d_n_tok + S;
+  b->d_tok_total = b->d_tok_off + S + 1;
+  b->d_ids = b->d_tok_total + 1;
+  b->d_tok_frame = b->d_ids + R;
+  CK(cudaMallocHost((void**)&b->h_res, (2 * S + 2 + 2 * R + 16) * 4), "cudaMallocHost(results)");
+  CK(cudaEventCreateWithFlags(&b->staged, cudaEventDisableTiming), "cudaEventCreate");
+  *out = b.release();
+  return 0;
+}
+
+void b200pf_batch_destroy(b200pf_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->e->device);
+  cudaStreamSynchronize(b->e->stream);
+  cudaFree(b->d_pcm);
+  cudaFree(b->d_meta);
+  cudaFree(b->d_n_tok);
+  cudaFreeHost(b->h_meta);
+  cudaFreeHost(b->h_res);
+  cudaEventDestroy(b->staged);
+  delete b;
+}
+
+// Build the packed layout for segments with `n_samples[i]` samples.  Returns 0 or an error code.
+static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, const std::vector<int64_t>& sample_start) {
+  b200pf_engine* e = b->e;
+  const int n_in = (int)n_samples.size();
+  b->n_seg_in = n_in;
+  b->dev_of_in.assign(n_in, -1);
+  b->T_in.assign(n_in, 0);
+  int ns = 0, rows = 0, frames = 0, nwork = 0;
+  for (int i = 0; i < n_in; ++i) {
+    const int nfb = num_fbank_frames(n_samples[i]);
+    const int T = nfb > 0 ? (nfb + 5) / 6 : 0;
+    b->T_in[i] = T;
+    if (T <= 0) continue;  // reference: empty features -> "" (paraformer.cpp:477-480)
+    if (ns >= e->cfg.max_segments) { set_error("batch exceeds max_segments"); return B200PF_ERR_CAPACITY; }
+    if (rows + T + 1 > e->cfg.max_rows) { set_error("batch exceeds max_rows"); return B200PF_ERR_CAPACITY; }
+    if (T > e->ft.pe_rows) { set_error("segment longer than the position-encoding table (2048 LFR frames)"); return B200PF_ERR_CAPACITY; }
+    b->dev_of_in[i] = ns;
+    b->h_sample_off[ns] = sample_start[i];
+    b->h_fb_off[ns] = frames;
+    b->h_row_off[ns] = rows;
+    b->h_seg_T[ns] = T;
+    for (int t = 0; t < T; ++t) { b->h_row_seg[rows + t] = ns; b->h_row_info[rows + t] = make_int2(t, T); }
+    b->h_row_seg[rows + T] = -1;
+    b->h_row_info[rows + T] = make_int2(-1, T);
+    for (int q0 = 0; q0 < T; q0 += 128) { b->h_work[nwork].seg = ns; b->h_work[nwork].q0 = q0; ++nwork; }
+    rows += T + 1;
+    frames += nfb;
+    ++ns;
+  }
+  b->h_sample_off[ns] = 0;
+  b->h_fb_off[ns] = frames;
+  b->h_row_off[ns] = rows;
+  b->n_seg = ns; b->rows = rows; b->n_frames = frames; b->n_work = nwork;
+  b->collected = false;
+  return 0;
+}
+
+int b200pf_batch_stage_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, void* stream) {
+  if (!b || !offsets || n_seg < 0 || (n_seg > 0 && !pcm)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const int64_t base = n_seg ? offsets[0] : 0, total = n_seg ? offsets[n_seg] - offsets[0] : 0;
+  if (total > b->max_samples) { set_error("batch exceeds max_samples"); return B200PF_ERR_CAPACITY; }
+  std::vector<int64_t> ns(n_seg), st(n_seg);
+  for (int i = 0; i < n_seg; ++i) { ns[i] = offsets[i + 1] - offsets[i]; st[i] = offsets[i] - base; if (ns[i] < 0) { set_error("offsets not monotone"); return B200PF_ERR_INVALID; } }
+  int rc = build_layout(b, ns, st);
+  if (rc) return rc;
+  b->pcm_is_f32 = 0;
+  if (total > 0) CK(cudaMemcpyAsync(b->d_pcm, pcm + base, (size_t)total * 2, cudaMemcpyHostToDevice, s), "H2D pcm");
+  CK(cudaMemcpyAsync(b->d_meta, b->h_meta, b->meta_bytes, cudaMemcpyHostToDevice, s), "H2D meta");
+  CK(cudaEventRecord(b->staged, s), "cudaEventRecord");
+  return 0;
+}
+
+int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, void* stream) {
+  if (!b || n_seg < 0 || (n_seg > 0 && (!din || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  std::vector<int64_t> ns(n_seg), st(n_seg);
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) { if (len[i] < 0) { set_error("negative length"); return B200PF_ERR_INVALID; } ns[i] = len[i]; st[i] = total; total += len[i]; }
+  if (total > b->max_samples) { set_error("batch exceeds max_samples"); return B200PF_ERR_CAPACITY; }
+  int rc = build_layout(b, ns, st);
+  if (rc) return rc;
+  b->pcm_is_f32 = 1;
+  for (int i = 0; i < n_seg; ++i)
+    if (b->dev_of_in[i] >= 0)
+      CK(cudaMemcpyAsync((float*)b->d_pcm + st[i], din[i], (size_t)len[i] * 4, cudaMemcpyHostToDevice, s), "H2D pcm");
+  CK(cudaMemcpyAsync(b->d_meta, b->h_meta, b->meta_bytes, cudaMemcpyHostToDevice, s), "H2D meta");
+  CK(cudaEventRecord(b->staged, s), "cudaEventRecord");
+  return 0;
+}
+
+int b200pf_batch_run(b200pf_batch* b, void* stream) {
+  if (!b) { set_error("null batch"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  b->launches = 0;
+  if (b->n_seg == 0) return 0;
+  std::lock_guard<std::mutex> lock(e->mu);
+  CK(cudaStreamWaitEvent(s, b->staged, 0), "cudaStreamWaitEvent");
+  const b200pf_config& c = e->cfg;
+  const int M = b->rows, D = c.d_model, S = b->n_seg, sms = e->num_sms;
+  const int Lcap = M;  // tokens <= frames
+  int64_t& nl = b->launches;
+
+  auto gemm = [&](const __nv_bfloat16* A, int lda, int64_t rows_a, const Linear& W, int Mrows, const int* m_dev,
+                  const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0) {
+    GemmProblem p;
+    p.A = A; p.lda = lda; p.rows_a = rows_a; p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
+    p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0;
+    ++nl;
+    return gemm_bf16_tcgen05(p, ep, sms, s);
+  };
+
+  // ---- K1 front end ----
+  ++nl; CKL(fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames, e->ft, e->fb, s), "fbank");
+  ++nl; CKL(lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
+                                   e->taps ? e->tap_feats : nullptr, s), "lfr_cmvn");
+
+  // ---- SAN-M encoder ----
+  AttnProblem ap;
+  ap.q = e->qkv; ap.q_rows = M; ap.ldq = 3 * D; ap.q_col0 = 0;
+  ap.kv = e->qkv; ap.kv_rows = M; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
+  ap.out = e->att; ap.ldo = D;
+  ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
+  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads;
+  for (int l = 0; l < c.n_enc; ++l) {
+    const EncLayer& w = e->enc[l];
+    const float* xin = l == 0 ? e->x0 : e->x;
+    ++nl; CKL(layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
+    { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
+      CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep), "gemm qkv"); }
+    ++nl; CKL(fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, s), "fsmn");
+    ++nl; CKL(attention_tcgen05(ap, s), "attention");
+    { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
+      if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
+      ep.out_f32 = e->x; ep.ld_out_f32 = D;
+      CKL(gemm(e->att, D, M, w.out, M, nullptr, ep), "gemm out"); }
+    ++nl; CKL(layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln2");
+    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
+      CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep), "gemm ffn1"); }
+    { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
+      CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep), "gemm ffn2"); }
+  }
+  ++nl; CKL(layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
+                             b->d_row_info, 1, s), "after_norm");
+
+  // ---- CIF predictor ----
+  { GemmEpilogue ep; ep.bias = e->pred_conv.b; ep.out_f32 = e->x; ep.ld_out_f32 = D;
+    if (c.pred_residual) { ep.res_f32 = e->enc_f32; ep.ld_res = D; ep.relu = 2; } else { ep.relu = 1; }
+    CKL(gemm(e->enc_bf16, D, M, e->pred_conv, M, nullptr, ep, D, -1), "gemm cif_conv"); }
+  ++nl; CKL(cif_alpha_launch(e->x, M, e->pred_out_w, e->pred_out_b, b->d_row_info, c.tail_threshold, e->alpha, s), "cif_alpha");
+  ++nl; CKL(cif_fire_launch(e->alpha, b->d_row_off, b->d_seg_T, S, c.cif_threshold, e->cif_cur, e->cif_rem, e->fire_val,
+                            b->d_n_tok, e->fire_row, s), "cif_fire");
+  ++nl; CKL(cif_scan_launch(b->d_n_tok, S, b->d_tok_off, b->d_tok_total, s), "cif_scan");
+  ++nl; CKL(cif_embed_launch(e->enc_f32, e->cif_cur, e->cif_rem, e->fire_row, b->d_row_off, b->d_tok_off, S, Lcap, e->y,
+                             e->tok_info, b->d_tok_frame, s), "cif_embed");
+  if (e->taps) CK(cudaMemcpyAsync(e->tap_emb, e->y, (size_t)Lcap * D * 4, cudaMemcpyDeviceToDevice, s), "tap emb");
+
+  // ---- SAN-M decoder ----
+  const int* Ldev = b->d_tok_total;
+  float* tbuf = e->x0;  // [Lcap, 512] fp32 scratch
+  AttnProblem cp;
+  cp.q = e->mem; cp.q_rows = Lcap; cp.ldq = D; cp.q_col0 = 0;
+  cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
+  cp.out = e->att; cp.ldo = D;
+  cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
+  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads;
+  auto dec_ffn = [&](const DecLayer& w) -> int {
+    ++nl; CKL(layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
+    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
+      CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep), "dec gemm w1"); }
+    ++nl; CKL(layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s), "dec ln ff");
+    { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
+      CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep), "dec gemm w2"); }
+    return 0;
+  };
+  for (int l = 0; l < c.n_dec; ++l) {
+    const DecLayer& w = e->dec[l];
+    { int rc = dec_ffn(w); if (rc) return rc; }
+    ++nl; CKL(layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln2");
+    ++nl; CKL(fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s), "dec fsmn");
+    ++nl; CKL(layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln3");
+    { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
+      CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep), "dec gemm q"); }
+    { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
+      CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep), "dec gemm kv"); }
+    ++nl; CKL(attention_tcgen05(cp, s), "cross attention");
+    { GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
+      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep), "dec gemm out"); }
+  }
+  { int rc = dec_ffn(e->dec3); if (rc) return rc; }
+  ++nl; CKL(layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
+  CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
+  { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
+    if (e->taps) { ep.out_f32 = e->tap_logits; ep.ld_out_f32 = c.vocab; }
+    CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep), "gemm vocab"); }
+  ++nl; CKL(argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
+  return 0;
+}
+
+int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
+  if (!b || !res) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  const size_t S = (size_t)e->cfg.max_segments, R = (size_t)e->cfg.max_rows;
+  int* h_n_tok = (int*)b->h_res;
+  int* h_tok_off = h_n_tok + S;
+  int* h_ids = h_tok_off + S + 2;
+  int* h_frame = h_ids + R;
+  res->n_tokens = 0;
+  if (b->n_seg > 0) {
+    CK(cudaMemcpyAsync(h_n_tok, b->d_n_tok, (size_t)b->n_seg * 4, cudaMemcpyDeviceToHost, s), "D2H n_tok");
+    CK(cudaMemcpyAsync(h_tok_off, b->d_tok_off, ((size_t)b->n_seg + 1) * 4, cudaMemcpyDeviceToHost, s), "D2H tok_off");
+    CK(cudaMemcpyAsync(h_ids, b->d_ids, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H ids");
+    CK(cudaMemcpyAsync(h_frame, b->d_tok_frame, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H frames");
+  }
+  CK(cudaStreamSynchronize(s), "forward");
+  int64_t out = 0;
+  double fl = 0.0;
+  const b200pf_config& c = e->cfg;
+  for (int i = 0; i < b->n_seg_in; ++i) {
+    const int d = b->dev_of_in[i];
+    const int cnt = d >= 0 ? h_n_tok[d] : 0;
+    if (res->token_counts) res->token_counts[i] = cnt;
+    if (res->token_offsets) res->token_offsets[i] = (int32_t)out;
+    if (res->lfr_frames) res->lfr_frames[i] = b->T_in[i];
+    if (d >= 0) {
+      if (out + cnt > res->cap_tokens) { set_error("result token capacity too small"); return B200PF_ERR_CAPACITY; }
+      const int o = h_tok_off[d];
+      if (res->token_ids) memcpy(res->token_ids + out, h_ids + o, (size_t)cnt * 4);
+      if (res->fire_frames) memcpy(res->fire_frames + out, h_frame + o, (size_t)cnt * 4);
+      out += cnt;
+      const double T = b->T_in[i], L = cnt, Dm = c.d_model, Fd = c.d_ff;
+      double encf = 0;
+      for (int l = 0; l < c.n_enc; ++l) {
+        const double din = l == 0 ? c.feat_dim : Dm;
+        encf += 2 * T * din * 3 * Dm + 2 * T * Dm * Dm + 4 * T * Dm * Fd + 4 * T * T * Dm;
+      }
+      fl += encf + 2 * T * Dm * Dm * 3 + 2 * T * Dm +
+            c.n_dec * (4 * L * Dm * Fd + 4 * L * Dm * Dm + 4 * T * Dm * Dm + 4 * L * T * Dm) + 4 * L * Dm * Fd + 2 * L * Dm * c.vocab;
+    }
+  }
+  if (res->token_offsets) res->token_offsets[b->n_seg_in] = (int32_t)out;
+  res->n_tokens = out;
+  b->flops = fl;
+  b->collected = true;
+  return 0;
+}
+
+int b200pf_forward_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, b200pf_result* res) {
+  int rc = b200pf_batch_stage_s16(b, pcm, offsets, n_seg, nullptr);
+  if (rc) return rc;
+  rc = b200pf_batch_run(b, nullptr);
+  if (rc) return rc;
+  return b200pf_batch_collect(b, res, nullptr);
+}
+
+int b200pf_forward_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, b200pf_result* res) {
+  int rc = b200pf_batch_stage_f32(b, din, len, n_seg, nullptr);
+  if (rc) return rc;
+  rc = b200pf_batch_run(b, nullptr);
+  if (rc) return rc;
+  return b200pf_batch_collect(b, res, nullptr);
+}
+
+int64_t b200pf_batch_launches(const b200pf_batch* b) { return b ? b->launches : 0; }
+double b200pf_batch_flops(const b200pf_batch* b) { return b ? b->flops : 0.0; }
+
+int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int64_t cap, int64_t shape[2]) {
+  if (!b || !name || !out || !shape) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  if (!e->taps || !b->collected) { set_error("taps need option taps=1 before run and a collected batch"); return B200PF_ERR_INVALID; }
+  if (seg < 0 || seg >= b->n_seg_in) { set_error("bad segment index"); return B200PF_ERR_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  const int d = b->dev_of_in[seg];
+  shape[0] = shape[1] = 0;
+  if (d < 0) return 0;
+  const size_t S = (size_t)e->cfg.max_segments;
+  const int* h_n_tok = (const int*)b->h_res;
+  const int* h_tok_off = h_n_tok + S;
+  const int T = b->h_seg_T[d], r0 = b->h_row_off[d], f0 = b->h_fb_off[d], nfb = b->h_fb_off[d + 1] - f0;
+  const int L = h_n_tok[d], t0 = h_tok_off[d];
+  const float* src = nullptr;
+  int64_t rows = 0, cols = 0;
+  const std::string n(name);
+  if (n == "fbank") { src = e->fb + (size_t)f0 * 80; rows = nfb; cols = 80; }
+  else if (n == "feats") { src = e->tap_feats + (size_t)r0 * 560; rows = T; cols = 560; }
+  else if (n == "enc") { src = e->enc_f32 + (size_t)r0 * 512; rows = T; cols = 512; }
+  else if (n == "alphas") { src = e->alpha + r0; rows = T + 1; cols = 1; }
+  else if (n == "fires") { src = e->fire_val + r0; rows = T + 1; cols = 1; }
+  else if (n == "embeds") { src = e->tap_emb + (size_t)t0 * 512; rows = L; cols = 512; }
+  else if (n == "logits") { src = e->tap_logits + (size_t)t0 * e->cfg.vocab; rows = L; cols = e->cfg.vocab; }
+  else { set_error("unknown tap " + n); return B200PF_ERR_INVALID; }
+  if (rows * cols > cap) { set_error("tap buffer too small"); return B200PF_ERR_CAPACITY; }
+  if (rows * cols > 0) CK(cudaMemcpy(out, src, (size_t)(rows * cols) * 4, cudaMemcpyDeviceToHost), "tap D2H");
+  shape[0] = rows; shape[1] = cols;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// Engine (one GPU: weights + workspace) and Batch (one batch of segments) behind include/b200pf.h.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200pf.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace pf {
+
+void set_error(const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);  // 0 or B200PF_ERR_CUDA (and sets the error text)
+int num_fbank_frames(int64_t n_samples);  // feature-window.cc:73-87 (snip_edges)
+int num_lfr_frames(int64_t n_samples);    // paraformer.cpp:424
+
+struct Linear {
+  __nv_bfloat16* w = nullptr;  // [out, in] bf16
+  float* b = nullptr;          // [out] or null
+  int out = 0, in = 0;
+};
+struct Norm {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+struct EncLayer {
+  Norm ln1, ln2;
+  Linear qkv, out, w1, w2;
+  float* fsmn_wt = nullptr;  // [11][512]
+  int din = 512;
+};
+struct DecLayer {
+  Norm ln1, lnff, ln2, ln3;
+  Linear w1, w2, q, kv, out;
+  float* fsmn_wt = nullptr;
+  bool has_attn = true;
+};
+
+struct DeviceArena {
+  uint8_t* base = nullptr;
+  size_t size = 0, used = 0;
+  void* take(size_t bytes) {
+    size_t off = (used + 255) & ~size_t(255);
+    if (off + bytes > size) return nullptr;
+    used = off + bytes;
+    return base + off;
+  }
+};
+
+}  // namespace pf
+
+struct b200pf_engine {
+  b200pf_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string lang = "zh-cn";
+  std::vector<std::string> tokens;
+  std::mutex mu;  // one forward at a time per engine (the workspace is shared)
+
+  pf::DeviceArena warena;  // weights + tables
+  std::vector<pf::EncLayer> enc;
+  pf::Norm enc_after;
+  pf::Linear pred_conv;    // [512, 3*512] tap-major
+  float* pred_out_w = nullptr;
+  float* pred_out_b = nullptr;
+  std::vector<pf::DecLayer> dec;
+  pf::DecLayer dec3;
+  pf::Norm dec_after;
+  pf::Linear vocab;
+  pf::FrontendTables ft{};
+
+  // workspace (sized by cfg.max_rows = R)
+  pf::DeviceArena ws;
+  float* fb = nullptr;              // [6R, 80]
+  float* x0 = nullptr;              // [R, 560] fp32   (decoder: t [R,512])
+  float* x = nullptr;               // [R, 512] fp32   (after the encoder: predictor hidden)
+  __nv_bfloat16* hb = nullptr;      // [R, 560] bf16   LayerNorm output feeding the next GEMM
+  __nv_bfloat16* qkv = nullptr;     // [R, 1536] bf16  (decoder: cross k/v [R,1024])
+  __nv_bfloat16* mem = nullptr;     // [R, 512] bf16   FSMN memory (decoder: cross q)
+  __nv_bfloat16* att = nullptr;     // [R, 512] bf16
+  __nv_bfloat16* ffn = nullptr;     // [R, 2048] bf16
+  float* enc_f32 = nullptr;         // [R, 512]
+  __nv_bfloat16* enc_bf16 = nullptr;
+  float* y = nullptr;               // [R, 512] decoder residual stream
+  float *alpha = nullptr, *cif_cur = nullptr, *cif_rem = nullptr, *fire_val = nullptr;
+  int* fire_row = nullptr;
+  unsigned long long* amax = nullptr;
+  int2* tok_info = nullptr;
+  // taps
+  int taps = 0;
+  float* tap_feats = nullptr;   // [R, 560]
+  float* tap_emb = nullptr;     // [R, 512]
+  float* tap_logits = nullptr;  // [R, vocab]
+};
+
+struct b200pf_batch {
+  b200pf_engine* e = nullptr;
+  int64_t max_samples = 0;
+  void* d_pcm = nullptr;  // int16 or float
+  int pcm_is_f32 = 0;
+  // host-pinned meta mirrored on the device
+  uint8_t* h_meta = nullptr;
+  uint8_t* d_meta = nullptr;
+  size_t meta_bytes = 0;
+  // views into meta (host / device)
+  int64_t* h_sample_off = nullptr; const int64_t* d_sample_off = nullptr;
+  int* h_fb_off = nullptr;         const int* d_fb_off = nullptr;
+  int* h_row_off = nullptr;        const int* d_row_off = nullptr;
+  int* h_seg_T = nullptr;          const int* d_seg_T = nullptr;
+  int* h_row_seg = nullptr;        const int* d_row_seg = nullptr;
+  int2* h_row_info = nullptr;      const int2* d_row_info = nullptr;
+  pf::AttnWork* h_work = nullptr;  const pf::AttnWork* d_work = nullptr;
+  // device results
+  int* d_n_tok = nullptr;     // [S]
+  int* d_tok_off = nullptr;   // [S+1]
+  int* d_tok_total = nullptr; // [1]
+  int* d_ids = nullptr;       // [R]
+  int* d_tok_frame = nullptr; // [R]
+  uint8_t* h_res = nullptr;   // pinned: n_tok[S] tok_off[S+1] ids[R] tok_frame[R]
+  // staged state
+  int n_seg_in = 0;             // segments the caller passed
+  int n_seg = 0;                // segments on the device (T > 0)
+  std::vector<int> dev_of_in;   // caller index -> device segment or -1
+  std::vector<int> T_in;        // caller index -> T
+  int rows = 0, n_frames = 0, n_work = 0;
+  int64_t launches = 0;
+  double flops = 0.0;
+  cudaEvent_t staged = nullptr;
+  bool collected = false;
+};

@@ -1,0 +1,288 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a (see gemm.cuh for what it replaces).
+//
+//   warp 0      : TMA producer  (one elected lane)       A tile 128x64, W tile 256x64, SWIZZLE_128B
+//   warp 1      : MMA issuer    (one elected lane)       tcgen05.mma cta_group::1 kind::f16, 128x256x16
+//   warp 2      : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4..11 : epilogue      tcgen05.ld 32x32b.x32 -> bias / ReLU / residual / FSMN-memory add /
+//                               bf16 or fp32 store / fused argmax
+//
+// Pipelines: smem full/empty ring (4 stages, 48 KB each) between TMA and MMA; TMEM full/empty pair
+// between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace pf {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (4 + kEpiWarps) * 32;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+struct KArgs {
+  int M, N, K;
+  const int* m_dev;
+  int a_k_wrap, a_row_shift0;
+  GemmEpilogue e;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = a.m_dev ? *a.m_dev : a.M;
+  const int N = a.N;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  const int k_blocks = (a.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+          const int k0 = kb * BK;
+          int ac0 = k0, ac1 = m_blk * BM;
+          if (a.a_k_wrap > 0) {
+            const int pass = k0 / a.a_k_wrap;
+            ac0 = k0 - pass * a.a_k_wrap;
+            ac1 += pass + a.a_row_shift0;
+          }
+          tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], ac0, ac1);
+          tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], k0, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
+          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per 16-element K step inside the 128 B swizzle atom (address field is >>4)
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may address
+    const int half = ew >> 2;      // which 128-column half of the 256-wide tile
+    const GemmEpilogue& e = a.e;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      float best_v = -INFINITY;
+      int best_i = -1;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col0 = n_blk * BN + half * 128 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128 + c * 32);
+        tmem_ld_32x32(taddr, r);
+        // gather the addends while the TMEM load is in flight
+        float4 res[8];
+        uint2 add[8];
+        if (row_ok) {
+          if (e.res_f32) {
+            const float* rp = e.res_f32 + (size_t)row * e.ld_res + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              res[g] = (col0 + 4 * g < N) ? *reinterpret_cast<const float4*>(rp + 4 * g) : make_float4(0, 0, 0, 0);
+          }
+          if (e.add_bf16) {
+            const __nv_bfloat16* ap = e.add_bf16 + (size_t)row * e.ld_add + col0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              add[g] = (col0 + 4 * g < N) ? *reinterpret_cast<const uint2*>(ap + 4 * g) : make_uint2(0, 0);
+          }
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = col0 + 4 * g;
+            if (col < N) {
+              float v0 = __uint_as_float(r[4 * g + 0]), v1 = __uint_as_float(r[4 * g + 1]);
+              float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
+              if (e.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+                v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+              }
+              if (e.relu == 1) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+              }
+              if (e.add_bf16) {
+                const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&add[g].x);
+                const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&add[g].y);
+                v0 += __low2float(p0); v1 += __high2float(p0); v2 += __low2float(p1); v3 += __high2float(p1);
+              }
+              if (e.res_f32) {
+                v0 += res[g].x; v1 += res[g].y; v2 += res[g].z; v3 += res[g].w;
+              }
+              if (e.relu == 2) {
+                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+              }
+              if (e.out_f32)
+                *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld_out_f32 + col) = make_float4(v0, v1, v2, v3);
+              if (e.out_bf16) {
+                uint2 o;
+                o.x = pack_bf16x2(v0, v1);
+                o.y = pack_bf16x2(v2, v3);
+                *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)row * e.ld_out_bf16 + col) = o;
+              }
+              if (e.argmax) {
+                if (v0 > best_v) { best_v = v0; best_i = col; }
+                if (v1 > best_v) { best_v = v1; best_i = col + 1; }
+                if (v2 > best_v) { best_v = v2; best_i = col + 2; }
+                if (v3 > best_v) { best_v = v3; best_i = col + 3; }
+              }
+            }
+          }
+        }
+      }
+      if (e.argmax && row_ok && best_i >= 0) atomicMax(e.argmax + row, argmax_pack(best_v, best_i));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
+  if ((p.N & 3) || (p.lda & 7) || (p.ldw & 7)) return (int)cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;
+  int rc = make_tmap_bf16_sw128(&tmA, p.A, (uint64_t)(p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN);
+  if (rc) return rc;
+  KArgs a;
+  a.M = p.M; a.N = p.N; a.K = p.K; a.m_dev = p.m_dev;
+  a.a_k_wrap = p.a_k_wrap; a.a_row_shift0 = p.a_row_shift0;
+  a.e = e;
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  if (grid > num_sms) grid = num_sms;
+  gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pf

@@ -1,0 +1,55 @@
+// tcgen05 / TMEM / TMA GEMM:  C[M,N] = A[M,K] (bf16, K-major) x W[N,K]^T (bf16, K-major), fp32 accumulate,
+// fused epilogue.  Replaces every MatMul/Gemm node of the reference's ONNX graph
+// (Ort::Session::Run, onnxruntime/src/paraformer.cpp:541): QKV / out / FFN projections, decoder
+// projections, the predictor's k=3 convolution (as three row-shifted K passes) and the vocabulary
+// projection with a fused greedy argmax (FindMax, onnxruntime/src/util.cpp:63-74).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pf {
+
+struct GemmEpilogue {
+  const float* bias = nullptr;            // [N]
+  const float* res_f32 = nullptr;         // [M, ld_res]  added to the result
+  int ld_res = 0;
+  const __nv_bfloat16* add_bf16 = nullptr;  // [M, ld_add] added to the result (FSMN memory)
+  int ld_add = 0;
+  float* out_f32 = nullptr;               // [M, ld_out_f32]
+  int ld_out_f32 = 0;
+  __nv_bfloat16* out_bf16 = nullptr;      // [M, ld_out_bf16]
+  int ld_out_bf16 = 0;
+  int relu = 0;                           // 1: after bias, 2: after every addend
+  unsigned long long* argmax = nullptr;   // [M] packed (ordered value << 32 | ~index); caller zero-fills
+};
+
+struct GemmProblem {
+  const __nv_bfloat16* A = nullptr;  // [rows_a, lda]
+  int64_t rows_a = 0;                // rows addressable through the tensor map (>= M)
+  int lda = 0;
+  const __nv_bfloat16* W = nullptr;  // [N, ldw]
+  int ldw = 0;
+  int M = 0, N = 0, K = 0;
+  const int* m_dev = nullptr;        // optional: M read on device (decoder token count)
+  // convolution-as-GEMM: K is split in passes of a_k_wrap columns; pass p reads A rows shifted by
+  // (p + a_row_shift0).  a_k_wrap = 0 -> plain GEMM.
+  int a_k_wrap = 0;
+  int a_row_shift0 = 0;
+};
+
+// Returns cudaError_t as int.  `num_sms` caps the persistent grid.
+int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, cudaStream_t stream);
+
+// 2-D bf16 row-major tensor map with 128-byte swizzle, box = [box_rows x 64 elements].
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_rows, uint32_t box_cols = 64);
+
+__device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
+  uint32_t u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+}
+
+}  // namespace pf

@@ -1,0 +1,79 @@
+// Bandwidth-bound kernels of the Paraformer path (front end, LayerNorm, FSMN memory block, CIF).
+// Reference anchors are cited per function; paths are relative to /root/reference/onnxruntime.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pf {
+
+// Packed row layout shared by all kernels: segment i owns rows [row_off[i], row_off[i] + T_i) followed
+// by ONE gap row (zero features; it doubles as the CIF tail frame, tail_threshold 0.45).
+// row_info[r] = {t, T}: frame index inside its segment and the segment's frame count; t = -1 on gap rows.
+
+struct FrontendTables {           // device pointers, built once per engine
+  const float* window;            // [400]  hamming, feature-window.cc:25-55
+  const double2* twiddle;         // [256]  exp(-2 pi i k / 512)
+  const int2* mel_range;          // [80]   {first_bin, size}, mel-computations.cc:172-195
+  const float* mel_w;             // packed weights, bin b at mel_w_off[b]
+  const int* mel_w_off;           // [80]
+  const float* cmvn_mean;         // [560]  am.mvn <AddShift>   paraformer.cpp:325-360
+  const float* cmvn_var;          // [560]  am.mvn <Rescale>
+  const float* pos_enc;           // [pe_rows][560]  sinusoid, positions from 1 (paraformer-online.cpp:240-268)
+  int pe_rows;
+};
+
+// K1a  Kaldi fbank: Paraformer::FbankKaldi (src/paraformer.cpp:309-323) -> knf::OnlineFbank.
+//      pcm is int16 (is_f32 = 0) or float in [-1,1) (is_f32 = 1; multiplied by 32768 as the reference does).
+//      sample_off[n_seg+1] (int64), fb_off[n_seg+1] (frame offsets into fb), fb [n_frames_total][80] fp32.
+int fbank_launch(const void* pcm, int is_f32, const int64_t* sample_off, const int* fb_off, int n_seg,
+                 int n_frames_total, const FrontendTables& t, float* fb, cudaStream_t s);
+
+// K1b  LFR 7/6 stacking + CMVN (Paraformer::LfrCmvn, src/paraformer.cpp:421-461) fused with the encoder's
+//      input scale and position encoding (x * sqrt(512) + PE).  feats_tap (optional) gets the pre-scale
+//      LFR+CMVN features [M][560].
+int lfr_cmvn_posenc_launch(const float* fb, const int* fb_off, const int* row_seg, const int2* row_info, int M,
+                           const FrontendTables& t, float scale, float* x0, float* feats_tap, cudaStream_t s);
+
+// K3  LayerNorm over the last dim (eps 1e-12), fp32 statistics.  in: fp32 or bf16 [rows][D]; out bf16 and/or
+//     fp32.  zero_gap: rows with row_info.t < 0 are written as zeros.  rows_dev (optional) overrides rows.
+int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_dev, int D, const float* gamma,
+                     const float* beta, float eps, __nv_bfloat16* out_bf16, float* out_f32, const int2* row_info,
+                     int zero_gap, cudaStream_t s);
+
+// K6  FSMN memory block: depthwise conv1d k=11 (zero padded at SEGMENT edges) + identity.
+//     mode 0 (encoder): out_bf16[r][c] = conv(v)[r][c] + v[r][c]
+//     mode 1 (decoder): y_f32[r][c]   += conv(x)[r][c] + x[r][c]
+//     in: bf16 [rows][ld_in] starting at column col0; w_t: [11][512] fp32 (tap-major transpose of fsmn_block.weight).
+int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s);
+
+// K7  alpha = sigmoid(h . w + b) on frame rows, tail_threshold on gap rows (CifPredictorV2).
+int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,
+                     float* alpha, cudaStream_t s);
+
+// K8  integrate-and-fire (same recurrence as ParaformerOnline::CifSearch, paraformer-online.cpp:270-345):
+//     per segment, sequential fp32 integrate exactly as the reference; a warp prefetches alphas and ranks
+//     the fires with ballot/popc prefix counts.
+//     Outputs per row: cur (weight into the open token), rem (weight carried into the next token when the
+//     row fires), fire_val (integrate after adding alpha), tok_of_fire (local token index or -1).
+//     Per segment: n_tok.  Per (segment, local token j): fire_row[row_off[seg] + j] = absolute row of the fire.
+int cif_fire_launch(const float* alpha, const int* row_off, const int* seg_T, int n_seg, float threshold,
+                    float* cur, float* rem, float* fire_val, int* n_tok, int* fire_row, cudaStream_t s);
+
+//     exclusive scan of n_tok -> tok_off[n_seg+1]; total -> *n_tok_total (device)
+int cif_scan_launch(const int* n_tok, int n_seg, int* tok_off, int* n_tok_total, cudaStream_t s);
+
+//     token embeddings E[g][:] = rem[f_prev] h[f_prev] + sum_{t in (f_prev, f]} cur[t] h[t]  (fp32, mul then add
+//     as the reference does), plus tok_info[g] = {j, L_seg}, tok_frame[g] = frame index of the fire.
+int cif_embed_launch(const float* enc_f32, const float* cur, const float* rem, const int* fire_row, const int* row_off,
+                     const int* tok_off, int n_seg, int tok_cap, float* emb, int2* tok_info, int* tok_frame,
+                     cudaStream_t s);
+
+// K11 decode packed argmax keys -> token ids
+int argmax_decode_launch(const unsigned long long* packed, const int* n_dev, int cap, int* ids, cudaStream_t s);
+
+// fp32 -> bf16 conversion (weight upload)
+int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+
+}  // namespace pf

@@ -1,0 +1,166 @@
+"""Synthetic workloads and random-init model directories (SURVEY.md §8(d) "Weights" and configs 1-5).
+
+There is no network: real checkpoints and speech corpora are unavailable, so both sides of every parity
+test and every benchmark line use these seeded generators.  Nothing here is on the product hot path.
+"""
+import math
+
+import numpy as np
+
+# PfConfig defaults (mirrors csrc/config.h)
+DEFAULT_CFG = dict(feat_dim=560, d_model=512, n_heads=4, d_ff=2048, n_enc=50, n_dec=16, kernel=11,
+                   vocab=8404, cif_threshold=1.0, tail_threshold=0.45, pred_residual=0, ln_eps=1e-12)
+
+
+def param_shapes(cfg):
+    D, Fd, V, K = int(cfg["d_model"]), int(cfg["d_ff"]), int(cfg["vocab"]), int(cfg["kernel"])
+    out = {}
+
+    def ln(p, n):
+        out[p + ".weight"] = (n,)
+        out[p + ".bias"] = (n,)
+
+    def lin(p, o, i, bias=True):
+        out[p + ".weight"] = (o, i)
+        if bias:
+            out[p + ".bias"] = (o,)
+
+    for l in range(int(cfg["n_enc"])):
+        p = "encoder.encoders0.0" if l == 0 else "encoder.encoders.%d" % (l - 1)
+        din = int(cfg["feat_dim"]) if l == 0 else D
+        ln(p + ".norm1", din)
+        lin(p + ".self_attn.linear_q_k_v", 3 * D, din)
+        out[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+        lin(p + ".self_attn.linear_out", D, D)
+        ln(p + ".norm2", D)
+        lin(p + ".feed_forward.w_1", Fd, D)
+        lin(p + ".feed_forward.w_2", D, Fd)
+    ln("encoder.after_norm", D)
+    out["predictor.cif_conv1d.weight"] = (D, D, 3)
+    out["predictor.cif_conv1d.bias"] = (D,)
+    lin("predictor.cif_output", 1, D)
+    for l in range(int(cfg["n_dec"])):
+        p = "decoder.decoders.%d" % l
+        ln(p + ".norm1", D)
+        lin(p + ".feed_forward.w_1", Fd, D)
+        ln(p + ".feed_forward.norm", Fd)
+        lin(p + ".feed_forward.w_2", D, Fd, bias=False)
+        ln(p + ".norm2", D)
+        out[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+        ln(p + ".norm3", D)
+        lin(p + ".src_attn.linear_q", D, D)
+        lin(p + ".src_attn.linear_k_v", 2 * D, D)
+        lin(p + ".src_attn.linear_out", D, D)
+    p = "decoder.decoders3.0"
+    ln(p + ".norm1", D)
+    lin(p + ".feed_forward.w_1", Fd, D)
+    ln(p + ".feed_forward.norm", Fd)
+    lin(p + ".feed_forward.w_2", D, Fd, bias=False)
+    ln("decoder.after_norm", D)
+    lin("decoder.output_layer", V, D)
+    return out
+
+
+def make_weights(cfg=None, seed=0, jitter_ln=False):
+    """nn.Linear / nn.Conv1d default init U(+-1/sqrt(fan_in)) for weights and biases; LayerNorm
+    gamma=1, beta=0 (or jittered, to exercise gamma/beta in tests); cif_output.bias = 0."""
+    cfg = dict(DEFAULT_CFG, **(cfg or {}))
+    rng = np.random.default_rng(seed)
+    W = {}
+    shapes = param_shapes(cfg)
+    for name, shp in shapes.items():
+        is_ln = (".norm" in name) or name.endswith("after_norm.weight") or name.endswith("after_norm.bias")
+        if is_ln:
+            if name.endswith(".weight"):
+                W[name] = (1.0 + (0.1 * rng.uniform(-1, 1, shp) if jitter_ln else 0.0) * np.ones(shp)).astype(np.float32)
+            else:
+                W[name] = ((0.1 * rng.uniform(-1, 1, shp)) if jitter_ln else np.zeros(shp)).astype(np.float32)
+            continue
+        if name.endswith(".weight"):
+            fan_in = int(np.prod(shp[1:]))
+            W[name] = rng.uniform(-1, 1, shp).astype(np.float32) / np.float32(math.sqrt(fan_in))
+        else:
+            wshape = shapes[name[:-5] + ".weight"]
+            fan_in = int(np.prod(wshape[1:]))
+            W[name] = rng.uniform(-1, 1, shp).astype(np.float32) / np.float32(math.sqrt(fan_in))
+    W["predictor.cif_output.bias"] = np.zeros((1,), np.float32)
+    return cfg, W
+
+
+def make_cmvn(n=560):
+    j = np.arange(n, dtype=np.float64)
+    means = (-(8.0 + 2.0 * np.sin(j))).astype(np.float32)
+    vars_ = (0.15 + 0.05 * np.cos(j)).astype(np.float32)
+    return means, vars_
+
+
+def make_tokens(vocab=8404):
+    toks = ["<blank>", "<s>", "</s>"]
+    n_latin = 500 if vocab >= 2000 else max(4, vocab // 8)
+    n_cjk = vocab - 4 - n_latin
+    toks += [chr(0x4E00 + i) for i in range(n_cjk)]
+    latin = [chr(ord("a") + i) for i in range(26)]
+    i = 0
+    while len(latin) < n_latin:
+        a, b, c = i % 26, (i // 26) % 26, (i // 676) % 26
+        w = chr(97 + a) + chr(97 + b) + (chr(97 + c) if i % 3 == 0 else "")
+        latin.append(w + "@@" if i % 2 == 0 else w)
+        i += 1
+    # keep order but drop accidental duplicates deterministically
+    seen, uniq = set(), []
+    for w in latin:
+        while w in seen:
+            w = "x" + w
+        seen.add(w)
+        uniq.append(w)
+    toks += uniq[:n_latin]
+    toks.append("<unk>")
+    assert len(toks) == vocab, (len(toks), vocab)
+    return toks
+
+
+def make_audio(n_samples, seed, as_int16=True):
+    """Speech-like noise: white noise -> 2nd-order band-pass 100-4000 Hz -> 4 Hz raised-cosine syllable
+    envelope, peak 0.3 full scale."""
+    from scipy.signal import butter, lfilter
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(n_samples)
+    b, a = butter(1, [100.0, 4000.0], btype="bandpass", fs=16000.0)
+    x = lfilter(b, a, x)
+    t = np.arange(n_samples) / 16000.0
+    env = 0.5 * (1.0 - np.cos(2.0 * np.pi * 4.0 * t + rng.uniform(0, 2 * np.pi)))
+    x = x * (0.05 + 0.95 * env)
+    x = 0.3 * x / (np.abs(x).max() + 1e-12)
+    s = np.round(x * 32768.0).clip(-32768, 32767).astype(np.int16)
+    return s if as_int16 else (s.astype(np.float32) / np.float32(32768.0))
+
+
+def segment_lengths(n_segments=1024, lo_s=2.0, hi_s=20.0, seed=20260101):
+    """Durations U[lo,hi] s quantised to 10 ms -> sample counts (config 2)."""
+    rng = np.random.default_rng(seed)
+    dur = np.round(rng.uniform(lo_s, hi_s, n_segments) * 100.0) / 100.0
+    return (dur * 16000.0 + 0.5).astype(np.int64)
+
+
+def make_segments(n_segments=1024, lo_s=2.0, hi_s=20.0, seed=20260101, audio_seed=1234):
+    """Returns (pcm int16 concatenated, offsets int64 [n+1])."""
+    lens = segment_lengths(n_segments, lo_s, hi_s, seed)
+    offs = np.zeros(n_segments + 1, np.int64)
+    offs[1:] = np.cumsum(lens)
+    # one long generation pass, then per-segment envelopes are already varied by phase; re-seed per
+    # 64-segment group to stay O(minutes) -> O(seconds) at 1024 segments
+    pcm = np.empty(int(offs[-1]), np.int16)
+    g = 64
+    for s in range(0, n_segments, g):
+        e = min(n_segments, s + g)
+        pcm[offs[s]:offs[e]] = make_audio(int(offs[e] - offs[s]), audio_seed + s)
+    return pcm, offs
+
+
+def write_synthetic_model_dir(path, cfg=None, seed=0, jitter_ln=False, lang="zh-cn"):
+    from . import modelfile
+    cfg, W = make_weights(cfg, seed, jitter_ln)
+    means, vars_ = make_cmvn(int(cfg["feat_dim"]))
+    toks = make_tokens(int(cfg["vocab"]))
+    modelfile.write_model_dir(path, cfg, W, means, vars_, toks, lang=lang)
+    return cfg, W, means, vars_, toks

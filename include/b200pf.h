@@ -1,0 +1,144 @@
+/*
+ * b200pf — C ABI of the B200-native offline Paraformer acoustic-model path.
+ *
+ * This is the drop-in boundary for ONE hot path of duj12/ASR-2Pass: `funasr::Model::Forward` for the
+ * offline Paraformer (reference: onnxruntime/src/paraformer.cpp:463-589, batched form
+ * onnxruntime/src/paraformer-torch.cpp:301-475).  The reference's own exported API is C++
+ * (onnxruntime/include/funasrruntime.h:60-138 carries std::map / std::string / std::vector), so the C++
+ * shim in asr-2pass_b200/csrc/host/ re-exports those symbols and calls THIS header underneath; see
+ * INTEGRATION.md for the binding a maintainer adds on the reference side.
+ *
+ * Plain pointers and sizes only; no torch or STL types cross this boundary.  Every function returns 0 on
+ * success and a non-zero code on failure; b200pf_last_error() describes the last failure on this thread.
+ * There is no CPU fallback: without a CUDA device of compute capability 10.x every entry point that
+ * computes fails with B200PF_ERR_NO_DEVICE.
+ */
+#ifndef B200PF_H_
+#define B200PF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PF_OK 0
+#define B200PF_ERR_INVALID 1
+#define B200PF_ERR_NO_DEVICE 2
+#define B200PF_ERR_CUDA 3
+#define B200PF_ERR_IO 4
+#define B200PF_ERR_CAPACITY 5
+
+typedef struct b200pf_engine b200pf_engine; /* one GPU: resident weights + activation workspace */
+typedef struct b200pf_batch b200pf_batch;   /* one batch of segments: device PCM, layout, results */
+
+typedef struct b200pf_config {
+  int32_t feat_dim, d_model, n_heads, d_ff, n_enc, n_dec, kernel, vocab, pred_residual;
+  float cif_threshold, tail_threshold, ln_eps;
+  int32_t sample_rate;     /* frontend_conf.fs of config.yaml (paraformer.cpp:188-190) */
+  int32_t max_rows;        /* packed LFR rows (frames + one gap row per segment) one batch may hold */
+  int32_t max_segments;
+} b200pf_config;
+
+/* Per-batch results, written into caller-owned host buffers by b200pf_batch_collect.
+ * Segment i produced token_counts[i] tokens; its ids are token_ids[token_offsets[i] .. +count).
+ * fire_frames holds, per token, the LFR frame index (60 ms units) at which CIF fired; index T_i denotes
+ * the tail frame.  lfr_frames[i] = T_i (0 for a segment shorter than one fbank window: the reference
+ * returns "" for it, paraformer.cpp:477-480). */
+typedef struct b200pf_result {
+  int32_t* token_counts;   /* [n_seg]      */
+  int32_t* token_offsets;  /* [n_seg + 1]  */
+  int32_t* lfr_frames;     /* [n_seg]      */
+  int32_t* token_ids;      /* [cap_tokens] */
+  int32_t* fire_frames;    /* [cap_tokens] may be NULL */
+  int64_t cap_tokens;
+  int64_t n_tokens;        /* out: total tokens written */
+} b200pf_result;
+
+const char* b200pf_last_error(void);
+int b200pf_version(void);
+/* Number of CUDA devices with compute capability 10.x; 0 when there is none (never falls back). */
+int b200pf_device_count(void);
+
+/* Host-only: parse <model_dir>/{am.mvn, config.yaml, tokens.json, model.b200pf} exactly as
+ * b200pf_engine_create does and report the architecture (no GPU needed; max_rows/max_segments = 0). */
+int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors);
+
+/* Replaces Paraformer::InitAsr (paraformer.cpp:21-53): reads <model_dir>/{am.mvn, config.yaml,
+ * tokens.json, model.b200pf}, uploads bf16 weights to `device`, allocates workspace for batches of up to
+ * max_rows packed rows / max_segments segments (0 -> defaults 32768 / 4096). */
+int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out);
+void b200pf_engine_destroy(b200pf_engine* e);
+int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out);
+/* Vocabulary access for the host-side detokeniser (Vocab, onnxruntime/src/vocab.cpp:46-63). */
+int b200pf_engine_vocab_size(const b200pf_engine* e);
+const char* b200pf_engine_token(const b200pf_engine* e, int id);
+const char* b200pf_engine_lang(const b200pf_engine* e);
+/* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap. */
+int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
+/* The CUDA stream (cudaStream_t) the engine enqueues on when `stream` arguments are NULL. */
+void* b200pf_engine_stream(b200pf_engine* e);
+
+/* Number of fbank frames / LFR frames for a segment of n samples (feature-window.cc:73-87,
+ * paraformer.cpp:424).  Pure host arithmetic. */
+int b200pf_num_fbank_frames(int64_t n_samples);
+int b200pf_num_lfr_frames(int64_t n_samples);
+/* Packed rows a batch with these sample counts occupies (sum of T_i + 1 over segments with T_i > 0). */
+int64_t b200pf_rows_for(const int64_t* n_samples, int n_seg);
+
+int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** out);
+void b200pf_batch_destroy(b200pf_batch* b);
+
+/* Stage inputs (replaces the float copy + feature assembly of Paraformer::Forward, paraformer.cpp:482-532).
+ * s16: `pcm` holds the segments back to back, segment i = pcm[offsets[i] .. offsets[i+1]) (the int16 the
+ *      reference's LoadPcmwav turns into float/32768, audio.cpp:787-819).
+ * f32: the reference's own argument form, din[i] in [-1,1) with len[i] samples (model.h:31).
+ * Host buffers may be pageable or pinned; the copy is enqueued on `stream` (NULL -> engine stream). */
+int b200pf_batch_stage_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, void* stream);
+int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, void* stream);
+/* Enqueue the whole forward (fbank -> ... -> argmax) for the staged batch.  Asynchronous. */
+int b200pf_batch_run(b200pf_batch* b, void* stream);
+/* Copy results to the host (device->host on `stream`), synchronise, unpack.  */
+int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream);
+/* stage + run + collect. */
+int b200pf_forward_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, b200pf_result* res);
+int b200pf_forward_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, b200pf_result* res);
+/* Kernel launches enqueued by the last b200pf_batch_run on this batch. */
+int64_t b200pf_batch_launches(const b200pf_batch* b);
+/* Algorithmic FLOPs (2*M*N*K per contraction) of the last collected batch. */
+double b200pf_batch_flops(const b200pf_batch* b);
+
+/* Debug taps (engine option "taps" = 1, after b200pf_batch_collect).  Copies the named fp32 intermediate
+ * of segment `seg` to `out` (capacity `cap` floats) and writes its shape.  Names: "fbank" [n_fb,80],
+ * "feats" [T,560], "enc" [T,512], "alphas" [T+1], "fires" [T+1], "embeds" [L,512], "logits" [L,vocab]. */
+int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int64_t cap, int64_t shape[2]);
+
+/* ---- single-operator entry points (fp32 host buffers in/out; used by the parity tests) -------------- */
+/* C = A[M,K] * W[N,K]^T (+bias) (+relu: 1 after bias, 2 after all adds) (+add[M,N] rounded to bf16)
+ * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: round the result to bf16.
+ * argmax_out (optional, [M]) receives the fused greedy argmax (first maximum wins, util.cpp:63-74). */
+int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
+                   int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out);
+/* conv1d k=3 pad 1 over packed rows with zero rows at segment gaps, as three shifted K passes. */
+int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bias, int M, int C, float* out);
+int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
+                        int in_bf16, float* out_f32, float* out_bf16_as_f32);
+/* q [sum Tq,H*128], k,v [sum Tk,H*128]; segment s owns rows q_off[s].. and kv_off[s]..; impl 0 = tcgen05
+ * kernel (product), 1 = CUDA-core cross-check. */
+int b200pf_op_attention(int device, const float* q, const float* k, const float* v, const int32_t* q_off,
+                        const int32_t* q_len, const int32_t* kv_off, const int32_t* kv_len, int n_seg, int n_heads,
+                        int64_t q_rows, int64_t kv_rows, int impl, float* out);
+/* depthwise k=11 conv + identity over segments seg_off[n_seg+1]; x [rows,512], w [512,11]. */
+int b200pf_op_fsmn(int device, const float* x, const float* w, const int32_t* seg_off, int n_seg, float* out);
+/* CIF: alphas [sum (T_i+1)] (tail already appended), hidden [sum (T_i+1), 512]; seg_off[n_seg+1] over those rows.
+ * Outputs: n_tok [n_seg], fires [rows], embeds [cap_tok,512], fire_frames [cap_tok]. */
+int b200pf_op_cif(int device, const float* alphas, const float* hidden, const int32_t* seg_off, int n_seg,
+                  float threshold, int32_t* n_tok, float* fires, float* embeds, int32_t* fire_frames, int64_t cap_tok);
+/* fbank + LFR/CMVN of one segment (int16 PCM); fb_out [n_fb,80], feats_out [T,560] (either may be NULL). */
+int b200pf_op_frontend(b200pf_engine* e, const int16_t* pcm, int64_t n, float* fb_out, float* feats_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PF_H_ */

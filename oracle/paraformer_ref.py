@@ -1,0 +1,308 @@
+"""ORACLE (test infrastructure only) — fp32 CPU restatement of the Paraformer-large graph that the
+reference executes through onnxruntime (`Ort::Session::Run`, onnxruntime/src/paraformer.cpp:541).
+
+The arithmetic lives in a third-party dependency that is NOT under /root/reference: the graph is the
+FunASR export of `speech_paraformer-large_asr_nat-zh-cn-16k-common-vocab8404` rev v2.0.5
+(funasr==0.7.5, dj_py310_environment.yml:153; model ids websocket/bin/funasr-wss-server-2pass.cpp:45-58),
+run by onnxruntime 1.14.0 (websocket/onnxruntime-linux-x64-1.14.0/VERSION_NUMBER).  This file restates
+that published architecture (SANM encoder, CifPredictorV2, ParaformerSANMDecoder), batch 1, no padding,
+which is what ORT executes for the reference's B=1 call.
+
+PARITY UNPINNED for this file: the reference holds no golden vectors, tests or runnable model for the
+encoder/predictor/decoder and onnxruntime/onnx are absent here, so the restatement is
+anchored only on the reference's own call site contract (inputs speech[1,T,560] f32 + speech_lengths,
+outputs logits[1,L,8404] f32 + token_num: paraformer.cpp:496-562) and on in-repo corroboration:
+  * sqrt(512) input scale              onnxruntime/src/paraformer.h:28, paraformer-online.cpp:108
+  * sinusoidal position encoding       onnxruntime/src/paraformer-online.cpp:240-268
+  * CIF integrate-and-fire recurrence  onnxruntime/src/paraformer-online.cpp:270-345
+  * cif_threshold 1.0, tail 0.45, 512-d, kernel 11 (fsmn_lorder 10)   onnxruntime/src/paraformer.h:112-123
+
+`emulate_bf16=True` rounds to bfloat16 exactly where the CUDA path stores bf16 (GEMM operands and the
+bf16 activation buffers), keeping every reduction in fp32.  It is a second oracle used to separate
+"kernel is wrong" from "bf16 rounding moved a value"; the acceptance tolerances are stated against the
+plain fp32 oracle.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+
+import torch
+import torch.nn.functional as F
+
+
+@dataclass
+class PfConfig:
+    feat_dim: int = 560        # 80 mel x LFR 7   (paraformer.h:116, com-define PARA_LFR_M)
+    d_model: int = 512         # encoder_size      (paraformer.h:117)
+    n_heads: int = 4
+    d_ff: int = 2048
+    n_enc: int = 50            # encoders0[0] + encoders[0..48]
+    n_dec: int = 16            # fsmn_layers       (paraformer.h:118)
+    kernel: int = 11           # fsmn_lorder 10 +1 (paraformer.h:119)
+    vocab: int = 8404
+    cif_threshold: float = 1.0     # paraformer.h:121
+    tail_threshold: float = 0.45   # paraformer.h:122
+    pred_residual: int = 0     # 1: relu(conv(enc)+enc) (CifPredictor v1 / SURVEY a8); 0: relu(conv(enc)) (upstream CifPredictorV2)
+    ln_eps: float = 1e-12
+
+    def to_dict(self):
+        return asdict(self)
+
+
+def param_shapes(cfg: PfConfig):
+    """name -> shape, in upstream FunASR state_dict naming."""
+    D, Fd, V, K = cfg.d_model, cfg.d_ff, cfg.vocab, cfg.kernel
+    out = {}
+
+    def ln(p, n):
+        out[p + ".weight"] = (n,)
+        out[p + ".bias"] = (n,)
+
+    def lin(p, o, i, bias=True):
+        out[p + ".weight"] = (o, i)
+        if bias:
+            out[p + ".bias"] = (o,)
+
+    for l in range(cfg.n_enc):
+        p = "encoder.encoders0.0" if l == 0 else f"encoder.encoders.{l - 1}"
+        din = cfg.feat_dim if l == 0 else D
+        ln(p + ".norm1", din)
+        lin(p + ".self_attn.linear_q_k_v", 3 * D, din)
+        out[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+        lin(p + ".self_attn.linear_out", D, D)
+        ln(p + ".norm2", D)
+        lin(p + ".feed_forward.w_1", Fd, D)
+        lin(p + ".feed_forward.w_2", D, Fd)
+    ln("encoder.after_norm", D)
+    out["predictor.cif_conv1d.weight"] = (D, D, 3)
+    out["predictor.cif_conv1d.bias"] = (D,)
+    lin("predictor.cif_output", 1, D)
+    for l in range(cfg.n_dec):
+        p = f"decoder.decoders.{l}"
+        ln(p + ".norm1", D)
+        lin(p + ".feed_forward.w_1", Fd, D)
+        ln(p + ".feed_forward.norm", Fd)
+        lin(p + ".feed_forward.w_2", D, Fd, bias=False)
+        ln(p + ".norm2", D)
+        out[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+        ln(p + ".norm3", D)
+        lin(p + ".src_attn.linear_q", D, D)
+        lin(p + ".src_attn.linear_k_v", 2 * D, D)
+        lin(p + ".src_attn.linear_out", D, D)
+    p = "decoder.decoders3.0"
+    ln(p + ".norm1", D)
+    lin(p + ".feed_forward.w_1", Fd, D)
+    ln(p + ".feed_forward.norm", Fd)
+    lin(p + ".feed_forward.w_2", D, Fd, bias=False)
+    ln("decoder.after_norm", D)
+    lin("decoder.output_layer", V, D)
+    return out
+
+
+def _rb(x, on):
+    return x.bfloat16().float() if on else x
+
+
+def pos_enc(T: int, depth: int) -> torch.Tensor:
+    """SinusoidalPositionEncoder; same arithmetic as ParaformerOnline::GetPosEmb
+    (paraformer-online.cpp:240-268): positions from 1, timescale step ln(1e4)/(depth/2-1)."""
+    half = depth // 2
+    inc = math.log(10000.0) / (half - 1)
+    inv = torch.exp(torch.arange(half, dtype=torch.float32) * (-inc))
+    pos = torch.arange(1, T + 1, dtype=torch.float32)
+    st = pos[:, None] * inv[None, :]
+    return torch.cat([torch.sin(st), torch.cos(st)], dim=1)
+
+
+def _ln(x, W, p, eps):
+    return F.layer_norm(x, (x.shape[-1],), W[p + ".weight"], W[p + ".bias"], eps)
+
+
+def _lin(x, W, p, emu, bias=True):
+    y = _rb(x, emu) @ _rb(W[p + ".weight"], emu).t()
+    if bias and (p + ".bias") in W:
+        y = y + W[p + ".bias"]
+    return y
+
+
+def _fsmn(v, w, K):
+    """depthwise conv1d, kernel K, zero pad (K-1)//2 left / K-1-left right, no bias, + identity."""
+    left = (K - 1) // 2
+    x = v.t()[None]                      # [1, D, T]
+    x = F.pad(x, (left, K - 1 - left))
+    y = F.conv1d(x, w, None, groups=w.shape[0])[0].t()
+    return y + v
+
+
+def encoder(feats: torch.Tensor, W, cfg: PfConfig, emu=False, taps=None):
+    """feats [T,560] (LFR+CMVN output) -> enc [T,512].  SURVEY.md §8(a) a7 / Appendix B."""
+    D, H = cfg.d_model, cfg.n_heads
+    T = feats.shape[0]
+    x = feats * (D ** 0.5) + pos_enc(T, cfg.feat_dim)
+    if taps is not None:
+        taps["enc_in"] = x.clone()
+    scale = (D // H) ** -0.5
+    for l in range(cfg.n_enc):
+        p = "encoder.encoders0.0" if l == 0 else f"encoder.encoders.{l - 1}"
+        h = _ln(x, W, p + ".norm1", cfg.ln_eps)
+        qkv = _rb(_lin(h, W, p + ".self_attn.linear_q_k_v", emu), emu)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        mem = _rb(_fsmn(v, W[p + ".self_attn.fsmn_block.weight"], cfg.kernel), emu)
+        # 128^-1/2 is applied to the fp32 scores (upstream scales q first; same value to rounding)
+        att = _mha_scaled(q, k, v, H, scale, emu)
+        att = _rb(att, emu)
+        y = _lin(att, W, p + ".self_attn.linear_out", emu) + mem
+        x = x + y if l > 0 else y
+        h2 = _ln(x, W, p + ".norm2", cfg.ln_eps)
+        f1 = _rb(torch.relu(_lin(h2, W, p + ".feed_forward.w_1", emu)), emu)
+        x = x + _lin(f1, W, p + ".feed_forward.w_2", emu)
+        if taps is not None and (l == 0 or l == cfg.n_enc - 1):
+            taps[f"enc_l{l}"] = x.clone()
+    enc = _ln(x, W, "encoder.after_norm", cfg.ln_eps)
+    return enc
+
+
+def _mha_scaled(q, k, v, H, scale, emu):
+    Tq, D = q.shape
+    dk = D // H
+    qh = q.reshape(Tq, H, dk).transpose(0, 1)
+    kh = k.reshape(-1, H, dk).transpose(0, 1)
+    vh = v.reshape(-1, H, dk).transpose(0, 1)
+    s = (qh @ kh.transpose(1, 2)) * scale
+    p = torch.softmax(s, dim=-1)
+    o = _rb(p, emu) @ vh
+    return o.transpose(0, 1).reshape(Tq, D)
+
+
+def predictor_alphas(enc, W, cfg: PfConfig, emu=False):
+    """CifPredictorV2 alphas.  enc [T,512] -> alpha [T]."""
+    x = _rb(enc, emu).t()[None]
+    x = F.pad(x, (1, 1))
+    w = _rb(W["predictor.cif_conv1d.weight"], emu)
+    c = F.conv1d(x, w, W["predictor.cif_conv1d.bias"])[0].t()
+    if cfg.pred_residual:
+        c = c + enc
+    o = torch.relu(c)
+    logit = o @ W["predictor.cif_output.weight"].t() + W["predictor.cif_output.bias"]
+    alpha = torch.sigmoid(logit)[:, 0]
+    alpha = torch.relu(alpha * 1.0 - 0.0)       # smooth_factor 1.0, noise_threshold 0
+    return alpha
+
+
+def cif(hidden, alphas, threshold: float):
+    """Integrate-and-fire, literal sequential recurrence (same as ParaformerOnline::CifSearch,
+    paraformer-online.cpp:270-345, and upstream `cif`): returns embeds [L,D], fires [T'] (the value of
+    `integrate` after adding alpha_t, before the subtraction)."""
+    Tn, D = hidden.shape
+    integrate = torch.zeros((), dtype=torch.float32)
+    frame = torch.zeros(D, dtype=torch.float32)
+    one = torch.ones((), dtype=torch.float32)
+    fires = torch.zeros(Tn, dtype=torch.float32)
+    out = []
+    for t in range(Tn):
+        a = alphas[t]
+        dc = one - integrate
+        integrate = integrate + a
+        fires[t] = integrate
+        fire = bool(integrate >= threshold)
+        cur = dc if fire else a
+        remainds = a - cur
+        frame = frame + cur * hidden[t]
+        if fire:
+            out.append(frame.clone())
+            integrate = integrate - one
+            frame = remainds * hidden[t]
+    emb = torch.stack(out, 0) if out else torch.zeros(0, D)
+    return emb, fires
+
+
+def predictor(enc, W, cfg: PfConfig, emu=False):
+    """alphas -> tail -> CIF.  Returns embeds [L,512], token_num (int), alphas' [T+1], fires [T+1]."""
+    alpha = predictor_alphas(enc, W, cfg, emu)
+    # tail_process_fn (batch-1, mask all ones): append one frame with alpha = tail_threshold, hidden 0
+    alpha_t = torch.cat([alpha, torch.tensor([cfg.tail_threshold], dtype=torch.float32)])
+    hidden = torch.cat([_rb(enc, emu), torch.zeros(1, enc.shape[1])], 0)
+    token_num = int(torch.floor(alpha_t.sum()).item())
+    emb, fires = cif(hidden, alpha_t, cfg.cif_threshold)
+    return emb, token_num, alpha_t, fires
+
+
+def decoder(emb, enc, token_num, W, cfg: PfConfig, emu=False, taps=None):
+    """ParaformerSANMDecoder.  emb [L,512], enc [T,512] -> logits [L,V]
+    (before log_softmax)."""
+    D, H = cfg.d_model, cfg.n_heads
+    L = emb.shape[0]
+    scale = (D // H) ** -0.5
+    tmask = (torch.arange(L) < token_num).float()[:, None]
+    y = emb
+    memory = _rb(enc, emu)
+
+    def ffn(t, p):
+        f1 = torch.relu(_lin(t, W, p + ".feed_forward.w_1", emu))
+        f1 = _ln(_rb(f1, emu), W, p + ".feed_forward.norm", cfg.ln_eps)
+        return _lin(f1, W, p + ".feed_forward.w_2", emu, bias=False)
+
+    for l in range(cfg.n_dec):
+        p = f"decoder.decoders.{l}"
+        r = y
+        t = ffn(_ln(y, W, p + ".norm1", cfg.ln_eps), p)
+        t2 = _rb(_ln(t, W, p + ".norm2", cfg.ln_eps), emu) * tmask
+        m = _fsmn(t2, W[p + ".self_attn.fsmn_block.weight"], cfg.kernel) * tmask
+        y = r + m
+        q = _rb(_lin(_ln(y, W, p + ".norm3", cfg.ln_eps), W, p + ".src_attn.linear_q", emu), emu)
+        kv = _rb(_lin(memory, W, p + ".src_attn.linear_k_v", emu), emu)
+        att = _rb(_mha_scaled(q, kv[:, :D], kv[:, D:], H, scale, emu), emu)
+        y = y + _lin(att, W, p + ".src_attn.linear_out", emu)
+        if taps is not None and l == 0:
+            taps["dec_l0"] = y.clone()
+    p = "decoder.decoders3.0"
+    y = ffn(_ln(y, W, p + ".norm1", cfg.ln_eps), p)
+    y = _ln(y, W, "decoder.after_norm", cfg.ln_eps)
+    if taps is not None:
+        taps["dec_out"] = y.clone()
+    logits = _lin(y, W, "decoder.output_layer", emu)
+    return logits
+
+
+@torch.no_grad()
+def forward(feats, W, cfg: PfConfig, emulate_bf16=False, want_taps=True):
+    """feats: float32 [T,560] (numpy or tensor).  Returns dict of taps:
+    enc [T,512], alphas [T+1], fires [T+1], embeds [L,512], token_num, logits [L,V] (raw),
+    logprobs [L,V] (= what the reference graph outputs), ids (FindMax over the first token_num rows)."""
+    feats = torch.as_tensor(feats, dtype=torch.float32)
+    taps = {} if want_taps else None
+    enc = encoder(feats, W, cfg, emulate_bf16, taps)
+    emb, token_num, alphas, fires = predictor(enc, W, cfg, emulate_bf16)
+    out = dict(taps or {})
+    out.update(enc=enc, alphas=alphas, fires=fires, embeds=emb, token_num=token_num)
+    if emb.shape[0] == 0:
+        out.update(logits=torch.zeros(0, cfg.vocab), logprobs=torch.zeros(0, cfg.vocab), ids=[])
+        return out
+    logits = decoder(emb, enc, token_num, W, cfg, emulate_bf16, taps)
+    if taps:
+        out.update(taps)
+    out["logits"] = logits
+    out["logprobs"] = torch.log_softmax(logits, dim=-1)
+    n = min(token_num, logits.shape[0])
+    # FindMax: first maximum wins (util.cpp:63-74) == torch.argmax on CPU? not guaranteed -> do it literally
+    ids = []
+    lp = out["logprobs"]
+    for i in range(n):
+        row = lp[i]
+        m = row.max()
+        ids.append(int((row == m).nonzero()[0, 0]))
+    out["ids"] = ids
+    return out
+
+
+def flops(T: int, L: int, cfg: PfConfig = PfConfig()) -> float:
+    """Algorithmic FLOPs of one segment: 2*M*N*K per contraction."""
+    D, Fd, V = cfg.d_model, cfg.d_ff, cfg.vocab
+    enc = 0.0
+    for l in range(cfg.n_enc):
+        din = cfg.feat_dim if l == 0 else D
+        enc += 2 * T * din * 3 * D + 2 * T * D * D + 4 * T * D * Fd + 4 * T * T * D
+    pred = 2 * T * D * D * 3 + 2 * T * D
+    dec = cfg.n_dec * (4 * L * D * Fd + 4 * L * D * D + 4 * T * D * D + 4 * L * T * D) + 4 * L * D * Fd + 2 * L * D * V
+    return enc + pred + dec
