@@ -46,7 +46,7 @@ def build_library(verbose=False):
 EXPORTS = [
     "b200pf_last_error", "b200pf_version", "b200pf_device_count", "b200pf_model_dir_probe", "b200pf_engine_create", "b200pf_engine_destroy",
     "b200pf_engine_config", "b200pf_engine_vocab_size", "b200pf_engine_token", "b200pf_engine_lang",
-    "b200pf_engine_set_option", "b200pf_engine_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
+    "b200pf_engine_set_option", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
     "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_conv3",
@@ -74,6 +74,7 @@ def lib():
     L.b200pf_engine_lang.argtypes = [C.c_void_p]
     L.b200pf_engine_lang.restype = C.c_char_p
     L.b200pf_engine_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.b200pf_engine_profile_read.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.b200pf_engine_stream.argtypes = [C.c_void_p]
     L.b200pf_engine_stream.restype = C.c_void_p
     L.b200pf_num_fbank_frames.argtypes = [C.c_int64]
@@ -153,6 +154,14 @@ class Engine:
 
     def set_option(self, key, value):
         _check(lib().b200pf_engine_set_option(self.h, key.encode(), int(value)))
+
+    def profile_read(self, reset=True):
+        names = (C.c_char_p * 8)()
+        ms = (C.c_double * 8)()
+        work = (C.c_double * 8)()
+        n = (C.c_longlong * 8)()
+        _check(lib().b200pf_engine_profile_read(self.h, int(reset), names, ms, work, n))
+        return {names[i].decode(): dict(ms=ms[i], work=work[i], launches=int(n[i])) for i in range(8)}
 
     @property
     def stream(self):

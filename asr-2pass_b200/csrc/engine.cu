@@ -52,6 +52,16 @@ using namespace pf;
     if (rc_) return check_cuda((cudaError_t)rc_, what);              \
   } while (0)
 
+// one profiled launch inside b200pf_batch_run: category, algorithmic work (FLOPs or bytes), call
+#define LAUNCH(cat, work, call, what)      \
+  do {                                     \
+    ++nl;                                  \
+    const int h_ = prof_begin(cat, work);  \
+    const int rcl_ = (call);               \
+    prof_end(h_);                          \
+    if (rcl_) return check_cuda((cudaError_t)rcl_, what); \
+  } while (0)
+
 namespace {
 
 struct Loader {
@@ -401,8 +411,34 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
     e->taps = value ? 1 : 0;
     return 0;
   }
+  if (strcmp(key, "profile") == 0) {
+    e->profile = value ? 1 : 0;
+    return 0;
+  }
   set_error(std::string("unknown option ") + key);
   return B200PF_ERR_INVALID;
+}
+
+static const char* kProfNames[8] = {"frontend", "layernorm", "gemm_tcgen05", "attention_tcgen05", "fsmn", "cif", "argmax", "other"};
+
+int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches) {
+  if (!e) { set_error("null engine"); return B200PF_ERR_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  CK(cudaStreamSynchronize(e->stream), "profile sync");
+  for (auto& r : e->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { e->prof_ms[r.cat] += t; e->prof_work[r.cat] += r.work; e->prof_launches[r.cat] += 1; }
+    e->prof_pool.push_back(r.a); e->prof_pool.push_back(r.b);
+  }
+  e->prof_recs.clear();
+  for (int i = 0; i < 8; ++i) {
+    if (names) names[i] = kProfNames[i];
+    if (ms) ms[i] = e->prof_ms[i];
+    if (work) work[i] = e->prof_work[i];
+    if (launches) launches[i] = e->prof_launches[i];
+    if (reset) { e->prof_ms[i] = 0; e->prof_work[i] = 0; e->prof_launches[i] = 0; }
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -543,18 +579,39 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   const int Lcap = M;  // tokens <= frames
   int64_t& nl = b->launches;
 
+  // optional CUDA-event bracket around one launch: category, algorithmic work (FLOPs or bytes)
+  auto prof_begin = [&](int cat, double work) -> int {
+    if (!e->profile) return -1;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+      if (!e->prof_pool.empty()) { ev[i] = e->prof_pool.back(); e->prof_pool.pop_back(); }
+      else if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
+    }
+    e->prof_recs.push_back({ev[0], ev[1], cat, work});
+    cudaEventRecord(ev[0], s);
+    return (int)e->prof_recs.size() - 1;
+  };
+  auto prof_end = [&](int h) { if (h >= 0) cudaEventRecord(e->prof_recs[h].b, s); };
+  // the decoder's row count lives on the device; for the FLOP estimate use tokens ~ frames / 2 (random init)
+  const double Lest = 0.5 * (M - S);
+  double sumT2 = 0;
+  for (int i = 0; i < S; ++i) sumT2 += (double)b->h_seg_T[i] * b->h_seg_T[i];
+
   auto gemm = [&](const __nv_bfloat16* A, int lda, int64_t rows_a, const Linear& W, int Mrows, const int* m_dev,
                   const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0) {
     GemmProblem p;
     p.A = A; p.lda = lda; p.rows_a = rows_a; p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
     p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0;
     ++nl;
-    return gemm_bf16_tcgen05(p, ep, sms, s);
+    const int h = prof_begin(2, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
+    const int rc = gemm_bf16_tcgen05(p, ep, sms, s);
+    prof_end(h);
+    return rc;
   };
 
   // ---- K1 front end ----
-  ++nl; CKL(fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames, e->ft, e->fb, s), "fbank");
-  ++nl; CKL(lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
+  LAUNCH(0, (double)b->n_frames * (160 * 2 + 80 * 4), fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames, e->ft, e->fb, s), "fbank");
+  LAUNCH(0, (double)M * 560 * 4 * 2, lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
                                    e->taps ? e->tap_feats : nullptr, s), "lfr_cmvn");
 
   // ---- SAN-M encoder ----
@@ -567,33 +624,33 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   for (int l = 0; l < c.n_enc; ++l) {
     const EncLayer& w = e->enc[l];
     const float* xin = l == 0 ? e->x0 : e->x;
-    ++nl; CKL(layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
     { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
       CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep), "gemm qkv"); }
-    ++nl; CKL(fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, s), "fsmn");
-    ++nl; CKL(attention_tcgen05(ap, s), "attention");
+    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, s), "fsmn");
+    LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
       if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
       ep.out_f32 = e->x; ep.ld_out_f32 = D;
       CKL(gemm(e->att, D, M, w.out, M, nullptr, ep), "gemm out"); }
-    ++nl; CKL(layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln2");
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln2");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
       CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep), "gemm ffn1"); }
     { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
       CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep), "gemm ffn2"); }
   }
-  ++nl; CKL(layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
+  LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
                              b->d_row_info, 1, s), "after_norm");
 
   // ---- CIF predictor ----
   { GemmEpilogue ep; ep.bias = e->pred_conv.b; ep.out_f32 = e->x; ep.ld_out_f32 = D;
     if (c.pred_residual) { ep.res_f32 = e->enc_f32; ep.ld_res = D; ep.relu = 2; } else { ep.relu = 1; }
     CKL(gemm(e->enc_bf16, D, M, e->pred_conv, M, nullptr, ep, D, -1), "gemm cif_conv"); }
-  ++nl; CKL(cif_alpha_launch(e->x, M, e->pred_out_w, e->pred_out_b, b->d_row_info, c.tail_threshold, e->alpha, s), "cif_alpha");
-  ++nl; CKL(cif_fire_launch(e->alpha, b->d_row_off, b->d_seg_T, S, c.cif_threshold, e->cif_cur, e->cif_rem, e->fire_val,
+  LAUNCH(5, (double)M * 512 * 4, cif_alpha_launch(e->x, M, e->pred_out_w, e->pred_out_b, b->d_row_info, c.tail_threshold, e->alpha, s), "cif_alpha");
+  LAUNCH(5, (double)M * 512 * 4, cif_fire_launch(e->alpha, b->d_row_off, b->d_seg_T, S, c.cif_threshold, e->cif_cur, e->cif_rem, e->fire_val,
                             b->d_n_tok, e->fire_row, s), "cif_fire");
-  ++nl; CKL(cif_scan_launch(b->d_n_tok, S, b->d_tok_off, b->d_tok_total, s), "cif_scan");
-  ++nl; CKL(cif_embed_launch(e->enc_f32, e->cif_cur, e->cif_rem, e->fire_row, b->d_row_off, b->d_tok_off, S, Lcap, e->y,
+  LAUNCH(5, (double)M * 512 * 4, cif_scan_launch(b->d_n_tok, S, b->d_tok_off, b->d_tok_total, s), "cif_scan");
+  LAUNCH(5, (double)M * 512 * 4, cif_embed_launch(e->enc_f32, e->cif_cur, e->cif_rem, e->fire_row, b->d_row_off, b->d_tok_off, S, Lcap, e->y,
                              e->tok_info, b->d_tok_frame, s), "cif_embed");
   if (e->taps) CK(cudaMemcpyAsync(e->tap_emb, e->y, (size_t)Lcap * D * 4, cudaMemcpyDeviceToDevice, s), "tap emb");
 
@@ -607,10 +664,10 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
   cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads;
   auto dec_ffn = [&](const DecLayer& w) -> int {
-    ++nl; CKL(layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
       CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep), "dec gemm w1"); }
-    ++nl; CKL(layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s), "dec ln ff");
+    LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s), "dec ln ff");
     { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
       CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep), "dec gemm w2"); }
     return 0;
@@ -618,24 +675,24 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   for (int l = 0; l < c.n_dec; ++l) {
     const DecLayer& w = e->dec[l];
     { int rc = dec_ffn(w); if (rc) return rc; }
-    ++nl; CKL(layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln2");
-    ++nl; CKL(fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s), "dec fsmn");
-    ++nl; CKL(layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln3");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln2");
+    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s), "dec fsmn");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln3");
     { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
       CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep), "dec gemm q"); }
     { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
       CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep), "dec gemm kv"); }
-    ++nl; CKL(attention_tcgen05(cp, s), "cross attention");
+    LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
       CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep), "dec gemm out"); }
   }
   { int rc = dec_ffn(e->dec3); if (rc) return rc; }
-  ++nl; CKL(layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
+  LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
   CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
   { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
     if (e->taps) { ep.out_f32 = e->tap_logits; ep.ld_out_f32 = c.vocab; }
     CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep), "gemm vocab"); }
-  ++nl; CKL(argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
+  LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
   return 0;
 }
 

@@ -93,6 +93,13 @@ struct b200pf_engine {
   int* fire_row = nullptr;
   unsigned long long* amax = nullptr;
   int2* tok_info = nullptr;
+  // per-category CUDA-event timing of the launches (option "profile")
+  int profile = 0;
+  struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[8] = {0}, prof_work[8] = {0};
+  long long prof_launches[8] = {0};
   // taps
   int taps = 0;
   float* tap_feats = nullptr;   // [R, 560]

@@ -223,6 +223,9 @@ def _e2e(capi, cfg_over, seg_secs, max_rows):
     for i in range(len(lens)):
         pf = pcm[offs[i]:offs[i + 1]].astype(np.float32) / np.float32(32768)
         feats = F.lfr_cmvn(F.fbank(pf), means, vars_)
+        if feats.shape[0] == 0:
+            print("seg %d: too short, tokens %d" % (i, res["token_counts"][i]))
+            continue
         o = R.forward(feats, Wt, pc)
         o2 = R.forward(feats, Wt, pc, emulate_bf16=True)
         msg = ["seg %d T=%d" % (i, feats.shape[0])]
