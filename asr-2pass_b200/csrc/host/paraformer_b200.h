@@ -1,0 +1,99 @@
+// ParaformerB200 — the B200-native offline Paraformer behind the reference's plugin seam.
+//
+// The reference selects its acoustic model through the virtual class funasr::Model
+// (onnxruntime/include/model.h:13-46), instantiated in OfflineStream::OfflineStream
+// (onnxruntime/src/offline-stream.cpp:40-57).  `Model` below repeats, with the same names, argument order
+// and meaning, the virtuals that the offline Paraformer path uses, so that a maintainer can make
+// ParaformerB200 derive from funasr::Model by changing one base-class name (INTEGRATION.md shows the
+// patch).  All arithmetic happens in the CUDA engine behind include/b200pf.h; this file is host plumbing:
+// argument marshalling, batching by the engine's capacity, greedy-search string assembly.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../../include/b200pf.h"
+#include "text.h"
+
+namespace funasr_b200 {
+
+class Model {  // subset of funasr::Model used on the offline Paraformer path (model.h:13-46)
+ public:
+  virtual ~Model() {}
+  virtual void StartUtterance() = 0;
+  virtual void EndUtterance() = 0;
+  virtual void Reset() = 0;
+  virtual void InitAsr(const std::string& am_model, const std::string& am_cmvn, const std::string& am_config,
+                       const std::string& token_file, int thread_num) = 0;
+  virtual std::vector<std::string> Forward(float** din, int* len, bool input_finished,
+                                           const std::vector<std::vector<float>>& hw_emb = {{0.0}},
+                                           void* wfst_decoder = nullptr, int batch_in = 1) = 0;
+  virtual std::string Forward(float* din, int len, bool input_finished,
+                              const std::vector<std::vector<float>>& hw_emb = {{0.0}}, void* wfst_decoder = nullptr) = 0;
+  virtual std::string Rescoring() = 0;
+  virtual void InitHwCompiler(const std::string& hw_model, int thread_num) {}
+  virtual void InitSegDict(const std::string& seg_dict_model) {}
+  virtual std::vector<std::vector<float>> CompileHotwordEmbedding(std::string& hotwords) = 0;
+  virtual std::string GetLang() = 0;
+  virtual int GetAsrSampleRate() = 0;
+  virtual void SetBatchSize(int batch_size) = 0;
+  virtual int GetBatchSize() = 0;
+};
+
+class ParaformerB200 : public Model {
+ public:
+  // device: CUDA ordinal; max_rows / max_segments: engine capacity (0 = defaults)
+  explicit ParaformerB200(int device = 0, int max_rows = 0, int max_segments = 0);
+  ~ParaformerB200() override;
+
+  // am_model names a file inside the model directory (the reference passes <dir>/model.onnx or
+  // model_quant.onnx, offline-stream.cpp:74-89); this implementation reads <dir>/model.b200pf next to it.
+  // Exits the process on failure exactly as the reference does (paraformer.cpp:43-46).
+  void InitAsr(const std::string& am_model, const std::string& am_cmvn, const std::string& am_config,
+               const std::string& token_file, int thread_num) override;
+  // Non-exiting variant used by the C hooks and tests.
+  bool Init(const std::string& model_dir, std::string* err);
+
+  std::vector<std::string> Forward(float** din, int* len, bool input_finished,
+                                   const std::vector<std::vector<float>>& hw_emb = {{0.0}},
+                                   void* wfst_decoder = nullptr, int batch_in = 1) override;
+  // The reference's Paraformer does not override the single-segment overload, so FunASRInfer returns ""
+  // (SURVEY.md §8(b)); here it is the batch-1 case of the batched Forward.
+  std::string Forward(float* din, int len, bool input_finished, const std::vector<std::vector<float>>& hw_emb = {{0.0}},
+                      void* wfst_decoder = nullptr) override;
+  // int16 entry used by the buffer API when no resampling is needed (skips the float round trip of
+  // Audio::LoadPcmwav, audio.cpp:787-819, which is exact: int16 -> float/32768 -> *32768).
+  std::vector<std::string> ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg);
+
+  void StartUtterance() override {}
+  void EndUtterance() override {}
+  void Reset() override {}
+  std::string Rescoring() override { return ""; }
+  std::vector<std::vector<float>> CompileHotwordEmbedding(std::string& hotwords) override;  // {{0 x 512}} (paraformer.cpp:595-599)
+  std::string GetLang() override { return language_; }
+  int GetAsrSampleRate() override { return sample_rate_; }
+  void SetBatchSize(int batch_size) override { batch_size_ = batch_size; }
+  int GetBatchSize() override { return batch_size_; }
+
+  b200pf_engine* engine() { return engine_; }
+  pf::host::Detokenizer* vocab() { return vocab_.get(); }
+  // token ids / CIF fire frames of the last Forward on this thread's call (debug / tests)
+  const std::vector<std::vector<int>>& last_ids() const { return last_ids_; }
+
+ private:
+  std::vector<std::string> Decode(const b200pf_result& r, int n_seg);
+
+  int device_, max_rows_, max_segments_;
+  b200pf_engine* engine_ = nullptr;
+  b200pf_batch* batch_ = nullptr;
+  int64_t batch_samples_ = 0;
+  std::unique_ptr<pf::host::Detokenizer> vocab_;
+  std::string language_ = "zh-cn";
+  int sample_rate_ = 16000;
+  int batch_size_ = 1;
+  std::mutex mu_;  // Forward is called concurrently by decoder threads on one handle (websocket-server.cpp:387-403)
+  std::vector<std::vector<int>> last_ids_;
+};
+
+}  // namespace funasr_b200

@@ -234,6 +234,8 @@ def _check_segment(b, res, i, model, o, enc_tol=1e-2, logit_tol=4e-2):
             if a != c:
                 assert abs(a - c) == 1 and min(abs(fires_o[a] - 1.0), abs(fires_o[c] - 1.0)) <= 2e-2
         moved = int((fr != fr_o).sum())
+        if len(fr) == 0:
+            return
         lg_o = o["logits"].numpy()
         lg = b.tap("logits", i)
         if moved == 0:
