@@ -108,6 +108,127 @@ def lib():
     return L
 
 
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "libfunasr_b200.so")
+_host = None
+HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf_host_detok_text", "b200pf_host_timestamp_text",
+                "b200pf_host_stitch", "b200pf_host_offline_init", "b200pf_host_offline_uninit", "b200pf_host_offline_infer_buffer",
+                "b200pf_host_offline_infer_segments", "b200pf_host_model_forward"]
+
+
+def host_lib():
+    """libfunasr_b200.so: the C++ mirror of funasr::Model / funasrruntime.h (include/b200pf_host.h hooks)."""
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_LIB_PATH):
+        raise B200PFError("libfunasr_b200.so is not built")
+    lib()
+    H = C.CDLL(HOST_LIB_PATH)
+    H.b200pf_host_detok_create.argtypes = [C.POINTER(C.c_char_p), C.c_int]
+    H.b200pf_host_detok_create.restype = C.c_void_p
+    H.b200pf_host_detok_destroy.argtypes = [C.c_void_p]
+    H.b200pf_host_detok_destroy.restype = None
+    H.b200pf_host_detok_text.argtypes = [C.c_void_p, c_i32p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+    H.b200pf_host_timestamp_text.argtypes = [C.c_void_p, c_i32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_stitch.argtypes = [C.POINTER(C.c_char_p), c_f32p, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_offline_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    H.b200pf_host_offline_init.restype = C.c_void_p
+    H.b200pf_host_offline_uninit.argtypes = [C.c_void_p]
+    H.b200pf_host_offline_uninit.restype = None
+    H.b200pf_host_offline_infer_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, c_f32p]
+    H.b200pf_host_offline_infer_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, c_i64p, c_i64p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_model_forward.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, C.c_char_p, C.c_int]
+    _host = H
+    return H
+
+
+class HostDetok:
+    """pf::host::Detokenizer (Vocab::Vector2StringV2 / TimestampOnnx / PostProcess mirror)."""
+
+    def __init__(self, tokens):
+        arr = (C.c_char_p * len(tokens))(*[t.encode("utf-8") for t in tokens])
+        self.h = host_lib().b200pf_host_detok_create(arr, len(tokens))
+
+    def __del__(self):
+        try:
+            host_lib().b200pf_host_detok_destroy(self.h)
+        except Exception:
+            pass
+
+    def text(self, ids, lang=""):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        buf = C.create_string_buffer(1 << 16)
+        host_lib().b200pf_host_detok_text(self.h, _p(ids, c_i32p), len(ids), lang.encode(), buf, len(buf))
+        return buf.value.decode("utf-8")
+
+    def timestamp_text(self, ids, us_alphas, us_peaks):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        a, p = _f32(us_alphas), _f32(us_peaks)
+        buf = C.create_string_buffer(1 << 18)
+        host_lib().b200pf_host_timestamp_text(self.h, _p(ids, c_i32p), len(ids), _p(a), _p(p), len(a), buf, len(buf))
+        return buf.value.decode("utf-8")
+
+
+def host_stitch(msgs, starts, lang):
+    arr = (C.c_char_p * len(msgs))(*[m.encode("utf-8") for m in msgs])
+    st = _f32(starts)
+    t, s = C.create_string_buffer(1 << 18), C.create_string_buffer(1 << 18)
+    host_lib().b200pf_host_stitch(arr, _p(st), len(msgs), lang.encode(), t, len(t), s, len(s))
+    return t.value.decode("utf-8"), s.value.decode("utf-8")
+
+
+class OfflineHandle:
+    """FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit through the host shim."""
+
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64):
+        self.h = host_lib().b200pf_host_offline_init(model_dir.encode(), device, max_rows, max_segments, batch_size)
+        if not self.h:
+            raise B200PFError("FunOfflineInit failed: " + lib().b200pf_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self.h:
+            host_lib().b200pf_host_offline_uninit(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def infer_buffer(self, pcm16, vad_max_len=60000):
+        pcm16 = np.ascontiguousarray(pcm16, dtype="<i2")
+        buf = C.create_string_buffer(1 << 20)
+        sn = C.c_float()
+        n = host_lib().b200pf_host_offline_infer_buffer(self.h, C.c_void_p(pcm16.ctypes.data), pcm16.nbytes, vad_max_len, buf, len(buf),
+                                                        C.byref(sn))
+        if n < 0:
+            raise B200PFError("FunOfflineInferBuffer returned nullptr")
+        return buf.value.decode("utf-8"), sn.value
+
+    def infer_segments(self, pcm16, seg_begin, seg_end, cap=1 << 22):
+        pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+        b = np.ascontiguousarray(seg_begin, dtype=np.int64)
+        e = np.ascontiguousarray(seg_end, dtype=np.int64)
+        buf = C.create_string_buffer(cap)
+        n = host_lib().b200pf_host_offline_infer_segments(self.h, C.c_void_p(pcm16.ctypes.data), len(pcm16), _p(b, c_i64p), _p(e, c_i64p),
+                                                          len(b), buf, len(buf))
+        if n < 0:
+            raise B200PFError("FunOfflineInferSegmentsB200 returned nullptr")
+        return buf.value.decode("utf-8")
+
+    def model_forward(self, segments_f32):
+        segs = [np.ascontiguousarray(s, dtype=np.float32) for s in segments_f32]
+        n = len(segs)
+        ptrs = (c_f32p * n)(*[s.ctypes.data_as(c_f32p) for s in segs])
+        lens = np.asarray([len(s) for s in segs], np.int32)
+        buf = C.create_string_buffer(1 << 22)
+        r = host_lib().b200pf_host_model_forward(self.h, ptrs, _p(lens, c_i32p), n, buf, len(buf))
+        if r < 0:
+            raise B200PFError("Model::Forward failed")
+        return buf.value.decode("utf-8").split("\n")
+
+
 def _check(rc):
     if rc != 0:
         raise B200PFError("b200pf error %d: %s" % (rc, lib().b200pf_last_error().decode("utf-8", "replace")))

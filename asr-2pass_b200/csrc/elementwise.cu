@@ -4,6 +4,11 @@
 namespace pf {
 namespace {
 
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -100,53 +105,82 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// FSMN: depthwise conv k=11 along time inside a segment + identity.  Thread = (row, 8 channels).
+// FSMN: depthwise conv k=11 along time inside a segment + identity.
+// One thread owns 4 channels and walks a run of FSMN_RUN consecutive rows: every input row is loaded ONCE
+// and scattered into a ring of 11 open output accumulators (registers), so the kernel streams
+// (RUN+10)/RUN rows per output row instead of 11.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int FSMN_RUN = 44;  // multiple of 11 keeps the ring indices static
+
+__global__ void __launch_bounds__(128)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
             __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
   const int nrows = rows_dev ? *rows_dev : rows;
-  const int row = blockIdx.x * 4 + threadIdx.y;
-  if (row >= nrows) return;
-  const int c = threadIdx.x * 8;
-  const int2 info = row_info[row];
-  if (info.x < 0) {
-    if (mode == 0) *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 512 + c) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int r0 = blockIdx.x * FSMN_RUN;
+  if (r0 >= nrows) return;
+  const int c = threadIdx.x * 4;
+  float w[11][4];
 #pragma unroll
   for (int j = 0; j < 11; ++j) {
-    const int tt = info.x + j - 5;
-    if (tt >= 0 && tt < info.y) {
-      const uint4 u = *reinterpret_cast<const uint4*>(in + (size_t)(row + j - 5) * ld_in + col0 + c);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-      const float4 w0 = *reinterpret_cast<const float4*>(w_t + j * 512 + c);
-      const float4 w1 = *reinterpret_cast<const float4*>(w_t + j * 512 + c + 4);
-      const float idn = (j == 5) ? 1.f : 0.f;  // + identity branch
-      acc[0] += (w0.x + idn) * __low2float(h[0]); acc[1] += (w0.y + idn) * __high2float(h[0]);
-      acc[2] += (w0.z + idn) * __low2float(h[1]); acc[3] += (w0.w + idn) * __high2float(h[1]);
-      acc[4] += (w1.x + idn) * __low2float(h[2]); acc[5] += (w1.y + idn) * __high2float(h[2]);
-      acc[6] += (w1.z + idn) * __low2float(h[3]); acc[7] += (w1.w + idn) * __high2float(h[3]);
-    }
+    const float4 t = *reinterpret_cast<const float4*>(w_t + j * 512 + c);
+    w[j][0] = t.x; w[j][1] = t.y; w[j][2] = t.z; w[j][3] = t.w;
   }
-  if (mode == 0) {
-    uint4 o;
-    __nv_bfloat162 p;
-    p = __floats2bfloat162_rn(acc[0], acc[1]); o.x = *reinterpret_cast<uint32_t*>(&p);
-    p = __floats2bfloat162_rn(acc[2], acc[3]); o.y = *reinterpret_cast<uint32_t*>(&p);
-    p = __floats2bfloat162_rn(acc[4], acc[5]); o.z = *reinterpret_cast<uint32_t*>(&p);
-    p = __floats2bfloat162_rn(acc[6], acc[7]); o.w = *reinterpret_cast<uint32_t*>(&p);
-    *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 512 + c) = o;
-  } else {
-    float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)row * 512 + c);
-    float4 a = yp[0], b = yp[1];
-    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
-    b.x += acc[4]; b.y += acc[5]; b.z += acc[6]; b.w += acc[7];
-    yp[0] = a; yp[1] = b;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[5][k] += 1.0f;  // identity branch
+  float acc[11][4];
+#pragma unroll
+  for (int s = 0; s < 11; ++s)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[s][k] = 0.f;
+
+  // input i (row r0 - 5 + i) feeds outputs o = i - 5 - d, d = -5..5, with tap j = d + 5; output o is
+  // complete after input i = o + 10.
+#pragma unroll 1
+  for (int base = 0; base < FSMN_RUN + 10; base += 11) {
+#pragma unroll
+    for (int ii = 0; ii < 11; ++ii) {
+      const int i = base + ii;
+      const int rin = r0 - 5 + i;
+      int2 info = make_int2(-1, 0);
+      if (rin >= 0 && rin < nrows && i < FSMN_RUN + 10) info = row_info[rin];
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (info.x >= 0) {
+        const uint2 u = *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c);
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        x[0] = __low2float(h0); x[1] = __high2float(h0); x[2] = __low2float(h1); x[3] = __high2float(h1);
+      }
+#pragma unroll
+      for (int d = -5; d <= 5; ++d) {
+        // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
+        const bool ok = info.x >= 0 && (info.x - d) >= 0 && (info.x - d) < info.y;
+        const int slot = ((ii - 5 - d) % 11 + 11) % 11;
+        if (ok) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[slot][k] = fmaf(w[d + 5][k], x[k], acc[slot][k]);
+        }
+      }
+      // output o = i - 10 has now seen all of its inputs
+      const int o = i - 10;
+      const int slot_done = (ii + 1) % 11;
+      if (o >= 0 && o < FSMN_RUN && r0 + o < nrows) {
+        const int rout = r0 + o;
+        const int2 oi = row_info[rout];
+        if (mode == 0) {
+          uint2 pk = make_uint2(0, 0);
+          if (oi.x >= 0) { pk.x = pack2(acc[slot_done][0], acc[slot_done][1]); pk.y = pack2(acc[slot_done][2], acc[slot_done][3]); }
+          *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
+        } else if (oi.x >= 0) {
+          float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
+          float4 v = *yp;
+          v.x += acc[slot_done][0]; v.y += acc[slot_done][1]; v.z += acc[slot_done][2]; v.w += acc[slot_done][3];
+          *yp = v;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[slot_done][k] = 0.f;
+    }
   }
 }
 
@@ -331,8 +365,7 @@ int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_d
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
                 const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s) {
   if (rows <= 0) return 0;
-  dim3 block(64, 4);
-  fsmn_kernel<<<(rows + 3) / 4, block, 0, s>>>(in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
+  fsmn_kernel<<<(rows + FSMN_RUN - 1) / FSMN_RUN, 128, 0, s>>>(in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
   return (int)cudaGetLastError();
 }
 

@@ -1,13 +1,16 @@
-// Persistent warp-specialised tcgen05 GEMM for sm_100a (see gemm.cuh for what it replaces).
+// Persistent warp-specialised tcgen05 GEMM for sm_100a, CTA-pair edition (see gemm.cuh for what it replaces).
 //
-//   warp 0      : TMA producer  (one elected lane)       A tile 128x64, W tile 256x64, SWIZZLE_128B
-//   warp 1      : MMA issuer    (one elected lane)       tcgen05.mma cta_group::1 kind::f16, 128x256x16
-//   warp 2      : TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
-//   warps 4..11 : epilogue      tcgen05.ld 32x32b.x32 -> bias / ReLU / residual / FSMN-memory add /
-//                               bf16 or fp32 store / fused argmax
+// Two CTAs of a cluster (one TPC) work on one 256x256 output tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 rows of A and HALF of the 256 W rows per 64-wide K block (32 KB per stage instead of
+// 48 KB), which halves the L2->SMEM traffic per FLOP and the shared-memory read bandwidth the MMA needs.
 //
-// Pipelines: smem full/empty ring (4 stages, 48 KB each) between TMA and MMA; TMEM full/empty pair
-// between MMA and epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0      : TMA producer (both CTAs; completion bytes land on the even CTA's "full" barrier)
+//   warp 1      : MMA issuer   (even CTA only, one lane): 256x256x16 per instruction, accumulators in the TMEM
+//                 of both CTAs (128 lanes x 256 columns each, double buffered = 512 columns)
+//   warp 2      : TMEM allocator (cta_group::2)
+//   warps 4..11 : epilogue in each CTA: tcgen05.ld 32x32b.x32 -> bias / ReLU / FSMN-memory add / residual ->
+//                 bf16 or fp32, staged through a per-warp smem tile so every global load and store is a
+//                 run of full 32-byte sectors; optional fused argmax.
 #include "gemm.cuh"
 #include "ptx.cuh"
 
@@ -15,13 +18,17 @@ namespace pf {
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128;        // rows per CTA (256 per pair)
+constexpr int BN = 256;        // columns per pair tile; each CTA loads BN/2 rows of W
+constexpr int BK = 64, STAGES = 5;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
+constexpr int B_BYTES = (BN / 2) * BK * 2;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SCR_STRIDE = 144;                  // bytes per scratch row: 128 + 16 (bank-conflict-free 16 B accesses)
+constexpr int SCR_BYTES = 32 * SCR_STRIDE;       // per epilogue warp
+constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + kEpiWarps * SCR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct KArgs {
   int M, N, K;
@@ -30,24 +37,28 @@ struct KArgs {
   GemmEpilogue e;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = tfull + 2;
+  uint8_t* sScr = smem + STAGES * (A_BYTES + B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + kEpiWarps * SCR_BYTES);
+  uint64_t* full = bars;                 // used on the even CTA
+  uint64_t* empty = bars + STAGES;       // one set per CTA, signalled by the multicast commit
+  uint64_t* tfull = bars + 2 * STAGES;   // one set per CTA
+  uint64_t* tempty = tfull + 2;          // used on the even CTA: 2 x kEpiWarps arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int M = a.m_dev ? *a.m_dev : a.M;
   const int N = a.N;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   const int k_blocks = (a.K + BK - 1) / BK;
@@ -63,13 +74,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
+      mbar_init(&tempty[i], 2 * kEpiWarps);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -77,33 +89,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = pair; tile < total; tile += n_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m0 = m_blk * 2 * BM + (int)cta * BM;
+        const int n0 = n_blk * BN + (int)cta * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
           const int k0 = kb * BK;
-          int ac0 = k0, ac1 = m_blk * BM;
+          int ac0 = k0, ac1 = m0;
           if (a.a_k_wrap > 0) {
             const int pass = k0 / a.a_k_wrap;
             ac0 = k0 - pass * a.a_k_wrap;
             ac1 += pass + a.a_row_shift0;
           }
-          tma_load_2d(sA + stage * A_BYTES, &tmA, &full[stage], ac0, ac1);
-          tma_load_2d(sB + stage * B_BYTES, &tmB, &full[stage], k0, n_blk * BN);
+          tma_load_2d_2cta(sA + stage * A_BYTES, &tmA, &full[stage], ac0, ac1);
+          tma_load_2d_2cta(sB + stage * B_BYTES, &tmB, &full[stage], k0, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = pair; tile < total; tile += n_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -115,12 +129,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle atom (address field is >>4)
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          umma_commit_2cta_mc(&empty[stage], 0x3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_2cta_mc(&tfull[acc], 0x3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -131,13 +145,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;  // TMEM lane quarter this warp may address
     const int half = ew >> 2;      // which 128-column half of the 256-wide tile
     const GemmEpilogue& e = a.e;
+    uint8_t* scr = sScr + ew * SCR_BYTES;
+    uint8_t* my_row = scr + lane * SCR_STRIDE;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = pair; tile < total; tile += n_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
+      const int row_base = m_blk * 2 * BM + (int)cta * BM + quarter * 32;  // first of this warp's 32 rows
+      const int row = row_base + lane;
       const bool row_ok = row < M;
       float best_v = -INFINITY;
       int best_i = -1;
@@ -148,71 +165,108 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128 + c * 32);
         tmem_ld_32x32(taddr, r);
-        // gather the addends while the TMEM load is in flight
+        // Addends: coalesced global -> smem (8 or 4 lanes cover one row's 128 / 64 bytes), then each thread
+        // reads its own row back.  The TMEM load is in flight meanwhile.
         float4 res[8];
-        uint2 add[8];
-        if (row_ok) {
-          if (e.res_f32) {
-            const float* rp = e.res_f32 + (size_t)row * e.ld_res + col0;
+        uint4 add[4];
+        if (e.res_f32) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              res[g] = (col0 + 4 * g < N) ? *reinterpret_cast<const float4*>(rp + 4 * g) : make_float4(0, 0, 0, 0);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_base + rr < M && col0 + 4 * ch < N)
+              v = *reinterpret_cast<const float4*>(e.res_f32 + (size_t)(row_base + rr) * e.ld_res + col0 + 4 * ch);
+            *reinterpret_cast<float4*>(scr + rr * SCR_STRIDE + ch * 16) = v;
           }
-          if (e.add_bf16) {
-            const __nv_bfloat16* ap = e.add_bf16 + (size_t)row * e.ld_add + col0;
+          __syncwarp();
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              add[g] = (col0 + 4 * g < N) ? *reinterpret_cast<const uint2*>(ap + 4 * g) : make_uint2(0, 0);
+          for (int g = 0; g < 8; ++g) res[g] = *reinterpret_cast<const float4*>(my_row + g * 16);
+          __syncwarp();
+        }
+        if (e.add_bf16) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (row_base + rr < M && col0 + 8 * ch < N)
+              v = *reinterpret_cast<const uint4*>(e.add_bf16 + (size_t)(row_base + rr) * e.ld_add + col0 + 8 * ch);
+            *reinterpret_cast<uint4*>(scr + rr * SCR_STRIDE + ch * 16) = v;
           }
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) add[g] = *reinterpret_cast<const uint4*>(my_row + g * 16);
+          __syncwarp();
         }
         tmem_ld_wait();
-        if (row_ok) {
+        float v[32];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int col = col0 + 4 * g;
-            if (col < N) {
-              float v0 = __uint_as_float(r[4 * g + 0]), v1 = __uint_as_float(r[4 * g + 1]);
-              float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
-              if (e.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-                v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
-              }
-              if (e.relu == 1) {
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-              }
-              if (e.add_bf16) {
-                const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&add[g].x);
-                const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&add[g].y);
-                v0 += __low2float(p0); v1 += __high2float(p0); v2 += __low2float(p1); v3 += __high2float(p1);
-              }
-              if (e.res_f32) {
-                v0 += res[g].x; v1 += res[g].y; v2 += res[g].z; v3 += res[g].w;
-              }
-              if (e.relu == 2) {
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-              }
-              if (e.out_f32)
-                *reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ld_out_f32 + col) = make_float4(v0, v1, v2, v3);
-              if (e.out_bf16) {
-                uint2 o;
-                o.x = pack_bf16x2(v0, v1);
-                o.y = pack_bf16x2(v2, v3);
-                *reinterpret_cast<uint2*>(e.out_bf16 + (size_t)row * e.ld_out_bf16 + col) = o;
-              }
-              if (e.argmax) {
-                if (v0 > best_v) { best_v = v0; best_i = col; }
-                if (v1 > best_v) { best_v = v1; best_i = col + 1; }
-                if (v2 > best_v) { best_v = v2; best_i = col + 2; }
-                if (v3 > best_v) { best_v = v3; best_i = col + 3; }
-              }
-            }
+        for (int g = 0; g < 8; ++g) {
+          const int col = col0 + 4 * g;
+          float v0 = __uint_as_float(r[4 * g + 0]), v1 = __uint_as_float(r[4 * g + 1]);
+          float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
+          if (e.bias && col < N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+            v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
           }
+          if (e.relu == 1) {
+            v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+          }
+          if (e.add_bf16) {
+            const uint32_t w0 = (g & 1) ? add[g >> 1].z : add[g >> 1].x;
+            const uint32_t w1 = (g & 1) ? add[g >> 1].w : add[g >> 1].y;
+            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&w0);
+            const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&w1);
+            v0 += __low2float(p0); v1 += __high2float(p0); v2 += __low2float(p1); v3 += __high2float(p1);
+          }
+          if (e.res_f32) {
+            v0 += res[g].x; v1 += res[g].y; v2 += res[g].z; v3 += res[g].w;
+          }
+          if (e.relu == 2) {
+            v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+          }
+          v[4 * g] = v0; v[4 * g + 1] = v1; v[4 * g + 2] = v2; v[4 * g + 3] = v3;
+          if (e.argmax && row_ok && col < N) {
+            if (v0 > best_v) { best_v = v0; best_i = col; }
+            if (v1 > best_v) { best_v = v1; best_i = col + 1; }
+            if (v2 > best_v) { best_v = v2; best_i = col + 2; }
+            if (v3 > best_v) { best_v = v3; best_i = col + 3; }
+          }
+        }
+        if (e.out_f32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(my_row + g * 16) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+            if (row_base + rr < M && col0 + 4 * ch < N)
+              *reinterpret_cast<float4*>(e.out_f32 + (size_t)(row_base + rr) * e.ld_out_f32 + col0 + 4 * ch) =
+                  *reinterpret_cast<const float4*>(scr + rr * SCR_STRIDE + ch * 16);
+          }
+          __syncwarp();
+        }
+        if (e.out_bf16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(my_row + g * 16) =
+                make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                           pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
+            if (row_base + rr < M && col0 + 8 * ch < N)
+              *reinterpret_cast<uint4*>(e.out_bf16 + (size_t)(row_base + rr) * e.ld_out_bf16 + col0 + 8 * ch) =
+                  *reinterpret_cast<const uint4*>(scr + rr * SCR_STRIDE + ch * 16);
+          }
+          __syncwarp();
         }
       }
       if (e.argmax && row_ok && best_i >= 0) atomicMax(e.argmax + row, argmax_pack(best_v, best_i));
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -220,9 +274,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // both CTAs are done with each other's shared memory, barriers and TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
 
@@ -262,6 +317,8 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint
 int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return 0;
   if ((p.N & 3) || (p.lda & 7) || (p.ldw & 7)) return (int)cudaErrorInvalidValue;
+  if (e.out_bf16 && ((p.N & 7) || (e.ld_out_bf16 & 7))) return (int)cudaErrorInvalidValue;
+  if (e.add_bf16 && ((p.N & 7) || (e.ld_add & 7))) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -272,15 +329,15 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;
   int rc = make_tmap_bf16_sw128(&tmA, p.A, (uint64_t)(p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN);
+  rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
   KArgs a;
   a.M = p.M; a.N = p.N; a.K = p.K; a.m_dev = p.m_dev;
   a.a_k_wrap = p.a_k_wrap; a.a_row_shift0 = p.a_row_shift0;
   a.e = e;
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
-  if (grid > num_sms) grid = num_sms;
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
+  int grid = 2 * m_tiles * n_tiles;  // CTA pairs
+  if (grid > (num_sms & ~1)) grid = num_sms & ~1;
   gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, a);
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,203 @@
+#include "funasrruntime_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+
+#include "paraformer_b200.h"
+
+namespace {
+
+struct RecogResult {  // FUNASR_RECOG_RESULT, onnxruntime/src/commonfunc.h:8-15
+  std::string msg, stamp, stamp_sents, tpass_msg;
+  float snippet_time = 0.f;
+};
+
+struct OfflineHandle {  // stands where funasr::OfflineStream does; owns only the acoustic model
+  std::unique_ptr<funasr_b200::ParaformerB200> asr;
+};
+
+int ToInt(const std::map<std::string, std::string>& m, const char* key, int dflt) {
+  auto it = m.find(key);
+  return it == m.end() ? dflt : atoi(it->second.c_str());
+}
+
+// Audio::FetchDynamic (audio.cpp:1052-1108) over an ascending-length queue: <= batch_size items,
+// max_len * (n + 1) <= 300 s, a >= 60 s item travels alone.
+std::vector<std::vector<int>> FormBatches(const std::vector<long long>& len_sorted, int batch_size) {
+  const long long max_acc = 300LL * 1000 * 16, max_sent = 60LL * 1000 * 16;
+  std::vector<std::vector<int>> out;
+  size_t head = 0;
+  while (head < len_sorted.size()) {
+    std::vector<int> cur;
+    long long max_len = 0;
+    const size_t room = std::min<size_t>((size_t)std::max(batch_size, 1), len_sorted.size() - head);
+    for (size_t k = 0; k < room; ++k) {
+      const long long L = len_sorted[head];
+      if (L >= max_sent) {
+        if (cur.empty()) { cur.push_back((int)head); ++head; }
+        break;
+      }
+      max_len = std::max(max_len, L);
+      if (max_len * (long long)(cur.size() + 1) > max_acc) break;
+      cur.push_back((int)head);
+      ++head;
+    }
+    if (cur.empty()) break;
+    out.push_back(cur);
+  }
+  return out;
+}
+
+RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples, std::vector<long long> seg_b,
+                         std::vector<long long> seg_e) {
+  funasr_b200::ParaformerB200* asr = h->asr.get();
+  RecogResult* res = new RecogResult;
+  res->snippet_time = (float)n_samples / asr->GetAsrSampleRate();
+  if (res->snippet_time == 0) return res;
+  const int n = (int)seg_b.size();
+  // ascending length order + permutation (Audio::CutSplit, audio.cpp:1228-1238); std::sort like the reference
+  std::vector<int> index(n);
+  std::iota(index.begin(), index.end(), 0);
+  std::sort(index.begin(), index.end(), [&](int a, int b) { return seg_e[a] - seg_b[a] < seg_e[b] - seg_b[b]; });
+  std::vector<long long> len_sorted(n);
+  for (int k = 0; k < n; ++k) len_sorted[k] = seg_e[index[k]] - seg_b[index[k]];
+  std::vector<std::string> msgs(n);
+  std::vector<float> starts(n);
+  for (const auto& batch : FormBatches(len_sorted, asr->GetBatchSize())) {
+    // gather the batch contiguously (segments may overlap or be out of order in the source buffer)
+    std::vector<short> buf;
+    std::vector<int64_t> offs(1, 0);
+    for (int q : batch) {
+      const int s = index[q];
+      buf.insert(buf.end(), pcm + seg_b[s], pcm + seg_e[s]);
+      offs.push_back((int64_t)buf.size());
+    }
+    std::vector<std::string> out = asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size());
+    for (size_t k = 0; k < batch.size(); ++k) {
+      const int s = index[batch[k]];
+      msgs[s] = out[k];
+      starts[s] = (float)seg_b[s] / asr->GetAsrSampleRate();
+    }
+  }
+  pf::host::StitchSegments(msgs, starts, asr->GetLang(), &res->msg, &res->stamp);
+  return res;
+}
+
+}  // namespace
+
+FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int thread_num, bool use_gpu, int batch_size) {
+  (void)thread_num; (void)use_gpu;
+  auto it = model_path.find("model-dir");
+  if (it == model_path.end()) { fprintf(stderr, "FunOfflineInit: model-dir missing\n"); return nullptr; }
+  std::unique_ptr<OfflineHandle> h(new OfflineHandle);
+  h->asr.reset(new funasr_b200::ParaformerB200(ToInt(model_path, "device", 0), ToInt(model_path, "max-rows", 0),
+                                               ToInt(model_path, "max-segments", 0)));
+  std::string err;
+  if (!h->asr->Init(it->second, &err)) {
+    fprintf(stderr, "FunOfflineInit: %s\n", err.c_str());
+    return nullptr;
+  }
+  h->asr->SetBatchSize(batch_size);
+  return h.release();
+}
+
+void FunOfflineReset(FUNASR_HANDLE, FUNASR_DEC_HANDLE) {}
+
+funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->asr.get() : nullptr; }
+
+FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, const long long* seg_begin,
+                                          const long long* seg_end, int n_seg) {
+  OfflineHandle* h = (OfflineHandle*)handle;
+  if (!h || (!pcm && n_samples > 0)) return nullptr;
+  std::vector<long long> b(seg_begin, seg_begin + n_seg), e(seg_end, seg_end + n_seg);
+  for (int i = 0; i < n_seg; ++i)
+    if (b[i] < 0 || e[i] < b[i] || e[i] > n_samples) return nullptr;
+  return RunSegments(h, pcm, n_samples, b, e);
+}
+
+FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE, QM_CALLBACK,
+                                    const std::vector<std::vector<float>>&, int sampling_rate, std::string wav_format, bool,
+                                    int, int vad_max_len, FUNASR_DEC_HANDLE, std::string, bool) {
+  OfflineHandle* h = (OfflineHandle*)handle;
+  if (!h) return nullptr;  // funasrruntime.cpp:216-217
+  if (!(wav_format == "pcm" || wav_format == "PCM")) {
+    fprintf(stderr, "FunOfflineInferBuffer: only raw PCM is decoded here (ffmpeg stays on the reference host path)\n");
+    return nullptr;
+  }
+  if (sampling_rate != h->asr->GetAsrSampleRate()) {
+    fprintf(stderr, "FunOfflineInferBuffer: resampling stays on the reference host path\n");
+    return nullptr;
+  }
+  const long long n = n_len / 2;  // Audio::LoadPcmwav: little-endian int16 (audio.cpp:795-805)
+  std::vector<short> pcm((size_t)n);
+  const unsigned char* bytes = (const unsigned char*)sz_buf;
+  for (long long i = 0; i < n; ++i) pcm[i] = (short)((bytes[2 * i + 1] << 8) | bytes[2 * i]);
+  // no VAD here: one segment, hard-cut at vad_max_len so that a segment always fits the engine
+  const long long cut = std::max(1, vad_max_len) * 16LL;
+  std::vector<long long> b, e;
+  for (long long s = 0; s < n; s += cut) { b.push_back(s); e.push_back(std::min(n, s + cut)); }
+  if (n == 0) { b.push_back(0); e.push_back(0); }
+  return RunSegments(h, pcm.data(), n, b, e);
+}
+
+FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK cb,
+                              const std::vector<std::vector<float>>& hw_emb, int sampling_rate, bool itn, int vad_tail_sil,
+                              int vad_max_len, FUNASR_DEC_HANDLE dec_handle) {
+  if (!handle || !sz_filename) return nullptr;
+  std::ifstream f(sz_filename, std::ios::binary);
+  if (!f.is_open()) return nullptr;
+  std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  size_t off = 0;
+  int rate = sampling_rate;
+  if (data.size() >= 44 && memcmp(data.data(), "RIFF", 4) == 0 && memcmp(data.data() + 8, "WAVE", 4) == 0) {
+    // walk the chunks: "fmt " gives the rate, "data" the payload (Audio::LoadWav, audio.cpp:622-737)
+    size_t p = 12;
+    off = data.size();
+    size_t len = 0;
+    while (p + 8 <= data.size()) {
+      unsigned int sz;
+      memcpy(&sz, data.data() + p + 4, 4);
+      if (memcmp(data.data() + p, "fmt ", 4) == 0 && p + 8 + 16 <= data.size()) {
+        unsigned short fmt, ch, bits;
+        memcpy(&fmt, data.data() + p + 8, 2); memcpy(&ch, data.data() + p + 10, 2);
+        memcpy(&rate, data.data() + p + 12, 4); memcpy(&bits, data.data() + p + 22, 2);
+        if (ch != 1 || bits != 16) { fprintf(stderr, "FunOfflineInfer: only 16-bit mono wav is supported here\n"); return nullptr; }
+      } else if (memcmp(data.data() + p, "data", 4) == 0) {
+        off = p + 8;
+        len = std::min<size_t>(sz, data.size() - off);
+        break;
+      }
+      p += 8 + sz + (sz & 1);
+    }
+    if (off >= data.size() && len == 0) return nullptr;
+    return FunOfflineInferBuffer(handle, data.data() + off, (int)len, mode, cb, hw_emb, rate, "pcm", itn, vad_tail_sil,
+                                 vad_max_len, dec_handle);
+  }
+  return FunOfflineInferBuffer(handle, data.data(), (int)data.size(), mode, cb, hw_emb, rate, "pcm", itn, vad_tail_sil,
+                               vad_max_len, dec_handle);
+}
+
+const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE) {
+  OfflineHandle* h = (OfflineHandle*)handle;
+  std::vector<std::vector<float>> emb;
+  if (!h) return emb;
+  return h->asr->CompileHotwordEmbedding(hotwords);
+}
+
+void FunOfflineUninit(FUNASR_HANDLE handle) { delete (OfflineHandle*)handle; }
+
+const char* FunASRGetResult(FUNASR_RESULT result, int) { return result ? ((RecogResult*)result)->msg.c_str() : nullptr; }
+const char* FunASRGetStamp(FUNASR_RESULT result) { return result ? ((RecogResult*)result)->stamp.c_str() : nullptr; }
+const char* FunASRGetStampSents(FUNASR_RESULT result) { return result ? ((RecogResult*)result)->stamp_sents.c_str() : nullptr; }
+const char* FunASRGetTpassResult(FUNASR_RESULT result, int) { return result ? ((RecogResult*)result)->tpass_msg.c_str() : nullptr; }
+const int FunASRGetRetNumber(FUNASR_RESULT result) { return result ? 1 : 0; }
+void FunASRFreeResult(FUNASR_RESULT result) { delete (RecogResult*)result; }
+const float FunASRGetRetSnippetTime(FUNASR_RESULT result) { return result ? ((RecogResult*)result)->snippet_time : 0.0f; }
+
+FUNASR_DEC_HANDLE FunASRWfstDecoderInit(FUNASR_HANDLE, int, float, float, float) { return nullptr; }
+void FunASRWfstDecoderUninit(FUNASR_DEC_HANDLE) {}
+void FunWfstDecoderLoadHwsRes(FUNASR_DEC_HANDLE, int, std::unordered_map<std::string, int>&) {}
+void FunWfstDecoderUnloadHwsRes(FUNASR_DEC_HANDLE) {}

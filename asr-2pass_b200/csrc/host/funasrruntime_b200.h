@@ -1,0 +1,64 @@
+// Offline subset of the reference's exported API (onnxruntime/include/funasrruntime.h:60-138) re-exported with
+// IDENTICAL C++ signatures, so callers such as websocket/bin/websocket-server.cpp:81-84 or
+// onnxruntime/bin/funasr-onnx-offline-rtf.cpp:70-76 link against libfunasr_b200.so unchanged.
+// The reference's header is C++ (std::map / std::string / std::vector cross the boundary); the
+// true C ABI lives one level down in include/b200pf.h.
+//
+// What this shim does NOT contain, by design: VAD, punctuation, ITN, resampling, ffmpeg
+// decoding, WFST decoding.  Those stay on the reference's host path; the supported way to keep them is to
+// plug ParaformerB200 into the reference's own OfflineStream.  Standalone, this shim treats
+// the whole buffer as one segment (the reference's behaviour when no vad-dir is given,
+// funasrruntime.cpp:241-245) and hard-cuts audio longer than vad_max_len.
+#pragma once
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+typedef void* FUNASR_HANDLE;
+typedef void* FUNASR_RESULT;
+typedef void* FUNASR_DEC_HANDLE;
+
+typedef enum { RASR_NONE = -1, RASRM_CTC_GREEDY_SEARCH = 0, RASRM_CTC_RPEFIX_BEAM_SEARCH = 1, RASRM_ATTENSION_RESCORING = 2 } FUNASR_MODE;
+typedef enum { ASR_OFFLINE = 0, ASR_ONLINE = 1, ASR_TWO_PASS = 2 } ASR_TYPE;
+typedef void (*QM_CALLBACK)(int cur_step, int n_total);
+
+// model_path keys (onnxruntime/include/com-define.h:15-38): "model-dir" is required; "quantize", "vad-dir",
+// "punc-dir", "itn-dir", "lm-dir" are accepted and ignored here.  Extra keys: "device" (CUDA ordinal),
+// "max-rows", "max-segments".
+FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int thread_num, bool use_gpu = false, int batch_size = 1);
+void FunOfflineReset(FUNASR_HANDLE handle, FUNASR_DEC_HANDLE dec_handle = nullptr);
+FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE mode, QM_CALLBACK fn_callback,
+                                    const std::vector<std::vector<float>>& hw_emb, int sampling_rate = 16000,
+                                    std::string wav_format = "pcm", bool itn = true, int vad_tail_sil = 800,
+                                    int vad_max_len = 60000, FUNASR_DEC_HANDLE dec_handle = nullptr,
+                                    std::string svs_lang = "auto", bool svs_itn = true);
+FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK fn_callback,
+                              const std::vector<std::vector<float>>& hw_emb, int sampling_rate = 16000, bool itn = true,
+                              int vad_tail_sil = 800, int vad_max_len = 60000, FUNASR_DEC_HANDLE dec_handle = nullptr);
+const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE mode = ASR_OFFLINE);
+void FunOfflineUninit(FUNASR_HANDLE handle);
+
+const char* FunASRGetResult(FUNASR_RESULT result, int n_index);
+const char* FunASRGetStamp(FUNASR_RESULT result);
+const char* FunASRGetStampSents(FUNASR_RESULT result);
+const char* FunASRGetTpassResult(FUNASR_RESULT result, int n_index);
+const int FunASRGetRetNumber(FUNASR_RESULT result);
+void FunASRFreeResult(FUNASR_RESULT result);
+const float FunASRGetRetSnippetTime(FUNASR_RESULT result);
+
+// The decoder handle is only meaningful with an LM; greedy search needs none (funasrruntime.cpp:836-894).
+FUNASR_DEC_HANDLE FunASRWfstDecoderInit(FUNASR_HANDLE handle, int asr_type, float glob_beam, float lat_beam, float am_scale);
+void FunASRWfstDecoderUninit(FUNASR_DEC_HANDLE handle);
+void FunWfstDecoderLoadHwsRes(FUNASR_DEC_HANDLE handle, int inc_bias, std::unordered_map<std::string, int>& hws_map);
+void FunWfstDecoderUnloadHwsRes(FUNASR_DEC_HANDLE handle);
+
+namespace funasr_b200 { class ParaformerB200; }
+// The acoustic model behind an offline handle (what OfflineStream::asr_handle is in the reference).
+funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle);
+
+// Extension for callers that already hold VAD cut points (e.g. the reference's Audio::CutSplit output):
+// segment i = pcm[seg_begin[i] .. seg_end[i]) in samples.  Segments are length-sorted, batched with the
+// reference's FetchDynamic rules, decoded, un-permuted and stitched exactly like FunOfflineInferBuffer.
+FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, const long long* seg_begin,
+                                          const long long* seg_end, int n_seg);

@@ -1,0 +1,93 @@
+// C hooks (declared in include/b200pf_host.h) that expose the C++ host mirror to ctypes-based tests and to
+// bench.py's end-to-end leg: detokeniser, timestamp/post-processing, and the FunOffline* call sequence.
+#include <algorithm>
+#include <cstring>
+
+#include "../../../include/b200pf_host.h"
+#include "funasrruntime_b200.h"
+#include "paraformer_b200.h"
+
+namespace {
+int CopyOut(const std::string& s, char* out, int cap) {
+  if (!out || cap <= 0) return (int)s.size();
+  const int n = std::min<int>((int)s.size(), cap - 1);
+  memcpy(out, s.data(), n);
+  out[n] = 0;
+  return (int)s.size();
+}
+struct Detok { pf::host::Detokenizer d; explicit Detok(std::vector<std::string> t) : d(std::move(t)) {} };
+}  // namespace
+
+extern "C" {
+
+void* b200pf_host_detok_create(const char* const* tokens, int n) {
+  std::vector<std::string> t(tokens, tokens + n);
+  return new Detok(std::move(t));
+}
+void b200pf_host_detok_destroy(void* h) { delete (Detok*)h; }
+int b200pf_host_detok_text(void* h, const int32_t* ids, int n, const char* lang, char* out, int cap) {
+  std::vector<int> v(ids, ids + n);
+  return CopyOut(((Detok*)h)->d.ToText(v, lang ? lang : ""), out, cap);
+}
+int b200pf_host_timestamp_text(void* h, const int32_t* ids, int n, const float* us_alphas, const float* us_peaks, int n_frames,
+                               char* out, int cap) {
+  Detok* d = (Detok*)h;
+  std::vector<int> v(ids, ids + n);
+  std::vector<std::string> pieces = d->d.ToPieces(v);
+  std::vector<std::string> raw = pieces;
+  std::vector<float> al(us_alphas, us_alphas + n_frames), pk(us_peaks, us_peaks + n_frames);
+  std::vector<pf::host::Span> spans = pf::host::TimestampFromPeaks(&al, pk, &pieces, nullptr);
+  return CopyOut(pf::host::MergeWithStamps(raw, spans), out, cap);
+}
+int b200pf_host_stitch(const char* const* msgs, const float* start_s, int n, const char* lang, char* text, int text_cap, char* stamp,
+                       int stamp_cap) {
+  std::vector<std::string> m(msgs, msgs + n);
+  std::vector<float> st(start_s, start_s + n);
+  std::string t, s;
+  pf::host::StitchSegments(m, st, lang ? lang : "", &t, &s);
+  CopyOut(t, text, text_cap);
+  CopyOut(s, stamp, stamp_cap);
+  return 0;
+}
+
+void* b200pf_host_offline_init(const char* model_dir, int device, int max_rows, int max_segments, int batch_size) {
+  std::map<std::string, std::string> mp;
+  mp["model-dir"] = model_dir;
+  mp["device"] = std::to_string(device);
+  mp["max-rows"] = std::to_string(max_rows);
+  mp["max-segments"] = std::to_string(max_segments);
+  return FunOfflineInit(mp, 1, true, batch_size);
+}
+void b200pf_host_offline_uninit(void* h) { FunOfflineUninit(h); }
+int b200pf_host_offline_infer_buffer(void* h, const char* buf, int n_bytes, int vad_max_len, char* text, int text_cap, float* snippet_s) {
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  FUNASR_RESULT r = FunOfflineInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr, hw, 16000, "pcm", true, 800, vad_max_len);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  if (snippet_s) *snippet_s = FunASRGetRetSnippetTime(r);
+  FunASRFreeResult(r);
+  return n;
+}
+int b200pf_host_offline_infer_segments(void* h, const int16_t* pcm, int64_t n_samples, const int64_t* seg_begin, const int64_t* seg_end,
+                                       int n_seg, char* text, int text_cap) {
+  FUNASR_RESULT r = FunOfflineInferSegmentsB200(h, pcm, n_samples, (const long long*)seg_begin, (const long long*)seg_end, n_seg);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  FunASRFreeResult(r);
+  return n;
+}
+// Model::Forward over float segments (the plugin seam itself): returns the '\n'-joined result strings.
+int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap) {
+  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  if (!m) return -1;
+  std::vector<float*> ptrs(n);
+  for (int i = 0; i < n; ++i) ptrs[i] = const_cast<float*>(din[i]);
+  std::vector<int> l(len, len + n);
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  std::vector<std::string> r = m->Forward(ptrs.data(), l.data(), true, hw, nullptr, n);
+  std::string joined;
+  for (int i = 0; i < n; ++i) { if (i) joined += "\n"; joined += r[i]; }
+  return CopyOut(joined, out, cap);
+}
+
+}  // extern "C"

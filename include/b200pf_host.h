@@ -1,0 +1,36 @@
+/*
+ * C hooks into the C++ host mirror (asr-2pass_b200/csrc/host): the reference-facing layer above b200pf.h.
+ * They exist for ctypes-based tests and for bench.py's end-to-end leg; C++ callers use
+ * funasrruntime_b200.h / paraformer_b200.h directly.  Exported by libfunasr_b200.so.
+ */
+#ifndef B200PF_HOST_H_
+#define B200PF_HOST_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Vocab::Vector2StringV2 (onnxruntime/src/vocab.cpp:164-305); stateful across calls like the reference. */
+void* b200pf_host_detok_create(const char* const* tokens, int n);
+void b200pf_host_detok_destroy(void* h);
+int b200pf_host_detok_text(void* h, const int32_t* ids, int n, const char* lang, char* out, int cap);
+/* Vector2String + TimestampOnnx + PostProcess (vocab.cpp:98-104, util.cpp:838-963, :720-836). */
+int b200pf_host_timestamp_text(void* h, const int32_t* ids, int n, const float* us_alphas, const float* us_peaks, int n_frames,
+                               char* out, int cap);
+/* Result stitching of FunOfflineInferBuffer (funasrruntime.cpp:291-316). */
+int b200pf_host_stitch(const char* const* msgs, const float* start_s, int n, const char* lang, char* text, int text_cap, char* stamp,
+                       int stamp_cap);
+
+/* FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit (funasrruntime.h:100-117) through C types. */
+void* b200pf_host_offline_init(const char* model_dir, int device, int max_rows, int max_segments, int batch_size);
+void b200pf_host_offline_uninit(void* h);
+int b200pf_host_offline_infer_buffer(void* h, const char* buf, int n_bytes, int vad_max_len, char* text, int text_cap, float* snippet_s);
+int b200pf_host_offline_infer_segments(void* h, const int16_t* pcm, int64_t n_samples, const int64_t* seg_begin, const int64_t* seg_end,
+                                       int n_seg, char* text, int text_cap);
+/* funasr::Model::Forward(float**, int*, ...) (model.h:31) on the handle's ParaformerB200; strings joined by '\n'. */
+int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -224,15 +224,23 @@ def _check_segment(b, res, i, model, o, enc_tol=1e-2, logit_tol=4e-2):
     s, e = res["token_offsets"][i], res["token_offsets"][i + 1]
     ids, fr = res["token_ids"][s:e], res["fire_frames"][s:e]
     assert res["token_counts"][i] == e - s
-    # fires: given ITS OWN alphas the GPU scan is bit exact (test_cif_is_bit_exact); against the oracle a fire
-    # may move only where the oracle's integrate value sits at the threshold
+    # fires: the GPU scan applied to the GPU's alphas must equal the oracle's CIF recurrence applied to the SAME
+    # alphas bit for bit (the scan is integer/index work once the alphas are fixed)
+    import torch
+    _, fires_self = R.cif(torch.zeros(T + 1, 1), torch.from_numpy(al), 1.0)
+    assert np.array_equal(fr, np.where(fires_self.numpy() >= 1.0)[0])
+    assert np.array_equal(b.tap("fires", i), fires_self.numpy())
+    # against the oracle's own alphas a fire may move by one frame, and only where the oracle's integrate value is
+    # closer to the threshold than the accumulated alpha deviation (alphas agree to <= 5e-3 per frame)
     fires_o = o["fires"].numpy()
     fr_o = np.where(fires_o >= 1.0)[0]
     assert abs(len(fr) - len(fr_o)) <= 1
+    drift = np.abs(np.cumsum(al.astype(np.float64)) - np.cumsum(o["alphas"].numpy().astype(np.float64)))
     if len(fr) == len(fr_o):
         for a, c in zip(fr, fr_o):
             if a != c:
-                assert abs(a - c) == 1 and min(abs(fires_o[a] - 1.0), abs(fires_o[c] - 1.0)) <= 2e-2
+                lo, hi = min(a, c), max(a, c)
+                assert hi - lo == 1 and min(abs(fires_o[a] - 1.0), abs(fires_o[c] - 1.0)) <= drift[:hi + 1].max() + 1e-3
         moved = int((fr != fr_o).sum())
         if len(fr) == 0:
             return
