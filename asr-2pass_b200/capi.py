@@ -264,6 +264,10 @@ class Engine:
 
     def close(self):
         if self.h:
+            for ref in list(getattr(self, "_batches", [])):
+                b = ref()
+                if b is not None:
+                    b.close()          # a batch must not outlive its engine
             lib().b200pf_engine_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -314,6 +318,10 @@ class Batch:
         self.engine = engine
         self.h = C.c_void_p()
         _check(lib().b200pf_batch_create(engine.h, int(max_samples), C.byref(self.h)))
+        import weakref
+        if not hasattr(engine, "_batches"):
+            engine._batches = []
+        engine._batches.append(weakref.ref(self))
         self._keep = None
         self.n_seg = 0
 

@@ -110,7 +110,7 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
 // and scattered into a ring of 11 open output accumulators (registers), so the kernel streams
 // (RUN+10)/RUN rows per output row instead of 11.
 // ------------------------------------------------------------------------------------------------
-constexpr int FSMN_RUN = 44;  // multiple of 11 keeps the ring indices static
+constexpr int FSMN_RUN = 22;  // multiple of 11 keeps the ring indices static
 
 __global__ void __launch_bounds__(128)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
@@ -138,30 +138,38 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
   // complete after input i = o + 10.
 #pragma unroll 1
   for (int base = 0; base < FSMN_RUN + 10; base += 11) {
+    // batch the 11 row-info and 11 data loads of this step so they are all in flight together
+    int2 info[11];
+    uint2 raw[11];
 #pragma unroll
     for (int ii = 0; ii < 11; ++ii) {
       const int i = base + ii;
       const int rin = r0 - 5 + i;
-      int2 info = make_int2(-1, 0);
-      if (rin >= 0 && rin < nrows && i < FSMN_RUN + 10) info = row_info[rin];
+      const bool in_range = rin >= 0 && rin < nrows && i < FSMN_RUN + 10;
+      info[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
+      raw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 11; ++ii) {
+      const int i = base + ii;
       float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (info.x >= 0) {
-        const uint2 u = *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c);
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
-        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+      if (info[ii].x >= 0) {  // gap rows and rows outside the batch contribute nothing
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&raw[ii].x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&raw[ii].y);
         x[0] = __low2float(h0); x[1] = __high2float(h0); x[2] = __low2float(h1); x[3] = __high2float(h1);
       }
 #pragma unroll
       for (int d = -5; d <= 5; ++d) {
         // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
-        const bool ok = info.x >= 0 && (info.x - d) >= 0 && (info.x - d) < info.y;
+        const bool ok = info[ii].x >= 0 && (info[ii].x - d) >= 0 && (info[ii].x - d) < info[ii].y;
         const int slot = ((ii - 5 - d) % 11 + 11) % 11;
         if (ok) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) acc[slot][k] = fmaf(w[d + 5][k], x[k], acc[slot][k]);
         }
       }
-      // output o = i - 10 has now seen all of its inputs
+      // output o = i - 10 has now seen all of its inputs; its row info is the one loaded 5 steps ago,
+      // but re-deriving it from row_info keeps the ring logic independent of the batching
       const int o = i - 10;
       const int slot_done = (ii + 1) % 11;
       if (o >= 0 && o < FSMN_RUN && r0 + o < nrows) {

@@ -16,13 +16,25 @@ namespace pf {
 namespace {
 
 constexpr int WIN = 400, SHIFT = 160, NFFT = 512, NBIN = 80, FEAT = 560;
-constexpr int FB_WARPS = 8;
+constexpr int FB_WARPS = 8;           // 2 frames per warp (16 lanes each)
+constexpr int FB_FRAMES = 2 * FB_WARPS;
+
+// W_16^m = exp(-2 pi i m / 16), m = 0..7 (double)
+__constant__ double2 c_w16[8] = {
+    {1.0, -0.0},
+    {0.92387953251128673848, -0.38268343236508978178},
+    {0.70710678118654757274, -0.70710678118654757274},
+    {0.38268343236508983729, -0.92387953251128673848},
+    {0.0, -1.0},
+    {-0.38268343236508972627, -0.92387953251128673848},
+    {-0.70710678118654746172, -0.70710678118654757274},
+    {-0.92387953251128673848, -0.38268343236508989280}};
 
 struct FbSmem {
-  double2 buf[FB_WARPS][NFFT];
-  double2 tw[NFFT / 2];
+  double2 buf[FB_FRAMES][NFFT / 2];     // per frame: 256 complex doubles (transpose + partner exchange)
+  double2 tw[NFFT / 2];                 // exp(-2 pi i k / 512)
   float window[WIN];
-  float power[FB_WARPS][NFFT / 2 + 8];
+  float power[FB_FRAMES][NFFT / 2 + 8];
   float mel_w[1024];
   int2 mel_range[NBIN];
   int mel_w_off[NBIN];
@@ -34,90 +46,140 @@ __device__ __forceinline__ float load_sample(const void* pcm, int64_t i) {
   return (float)reinterpret_cast<const int16_t*>(pcm)[i];                        // == (s/32768.f)*32768 exactly
 }
 
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// 16-point DFT in registers, radix-2 decimation in frequency; on return v[bitrev4(k)] holds X[k].
+__device__ __forceinline__ void fft16(double2 (&v)[16]) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      if ((a & s) == 0) {
+        const int b = a + s;
+        const int m = (a & (s - 1)) * (8 / s);
+        const double2 t = csub(v[a], v[b]);
+        v[a] = cadd(v[a], v[b]);
+        v[b] = (m == 0) ? t : cmul(t, c_w16[m]);
+      }
+    }
+  }
+}
+__host__ __device__ constexpr int brev4(int k) { return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3); }
+
+// One frame per 16 lanes.  The 512-point real FFT is a 256-point complex FFT of z[n] = w[2n] + i w[2n+1]
+// (16 x 16 decomposition: one radix-16 pass in registers, twiddle, smem transpose, second radix-16 pass)
+// followed by the usual even/odd recombination; all in double like knf's Rfft (rfft.cc:41-47).
 template <bool F32>
 __global__ void __launch_bounds__(FB_WARPS * 32)
 fbank_kernel(const void* __restrict__ pcm, const int64_t* __restrict__ sample_off, const int* __restrict__ fb_off,
              int n_seg, int n_frames, FrontendTables t, int mel_w_total, float* __restrict__ fb) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   FbSmem& S = *reinterpret_cast<FbSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 15;                       // lane within the frame's half-warp
+  const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
+  const int slot = (threadIdx.x >> 5) * 2 + (lane >> 4);
   for (int i = threadIdx.x; i < NFFT / 2; i += blockDim.x) S.tw[i] = t.twiddle[i];
   for (int i = threadIdx.x; i < WIN; i += blockDim.x) S.window[i] = t.window[i];
   for (int i = threadIdx.x; i < mel_w_total; i += blockDim.x) S.mel_w[i] = t.mel_w[i];
   for (int i = threadIdx.x; i < NBIN; i += blockDim.x) { S.mel_range[i] = t.mel_range[i]; S.mel_w_off[i] = t.mel_w_off[i]; }
   __syncthreads();
 
-  double2* buf = S.buf[warp];
-  float* pw = S.power[warp];
-  for (int fg = blockIdx.x * FB_WARPS + warp; fg < n_frames; fg += gridDim.x * FB_WARPS) {
-    // frame -> segment (largest s with fb_off[s] <= fg)
-    int lo = 0, hi = n_seg;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (fb_off[mid] <= fg) lo = mid; else hi = mid;
+  double2* buf = S.buf[slot];
+  float* pw = S.power[slot];
+  const int n_iter = (n_frames + gridDim.x * FB_FRAMES - 1) / (gridDim.x * FB_FRAMES);
+  for (int it = 0; it < n_iter; ++it) {
+    const int fg = (it * gridDim.x + blockIdx.x) * FB_FRAMES + slot;
+    const bool active = fg < n_frames;   // both halves of a warp keep executing the shuffles / syncwarps
+    int64_t s0 = 0;
+    if (active) {
+      int lo = 0, hi = n_seg;  // frame -> segment (largest s with fb_off[s] <= fg)
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (fb_off[mid] <= fg) lo = mid; else hi = mid;
+      }
+      s0 = sample_off[lo] + (int64_t)(fg - fb_off[lo]) * SHIFT;
     }
-    const int64_t s0 = sample_off[lo] + (int64_t)(fg - fb_off[lo]) * SHIFT;
-
-    // RemoveDcOffset (feature-window.cc:179-190)
-    float x[13];
+    // lane `sub` owns samples 32 n1 + 2 sub + {0,1}, n1 = 0..15 (zero beyond 400)
+    float xe[13], xo[13];
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 13; ++k) {
-      const int i = lane + 32 * k;
-      x[k] = (i < WIN) ? load_sample<F32>(pcm, s0 + i) : 0.f;
-      sum += x[k];
+    for (int n1 = 0; n1 < 13; ++n1) {
+      const int i = 32 * n1 + 2 * sub;
+      xe[n1] = (active && i < WIN) ? load_sample<F32>(pcm, s0 + i) : 0.f;
+      xo[n1] = (active && i + 1 < WIN) ? load_sample<F32>(pcm, s0 + i + 1) : 0.f;
+      sum += xe[n1] + xo[n1];
     }
+    // RemoveDcOffset (feature-window.cc:179-190); integer-valued samples make the sum exact in any order
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    for (int off = 8; off > 0; off >>= 1) sum += __shfl_xor_sync(hmask, sum, off);
     const float mean = sum / (float)WIN;
-    // Preemphasize (:200-211) then window (:57-63); zero pad to 512 and bit-reverse for the DIT FFT
+    double2 v[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int i = lane + 32 * k;
-      float w = 0.f;
-      if (i < WIN) {
-        const float d = __fsub_rn(x[k < 13 ? k : 0], mean);
-        const float dp = (i > 0) ? __fsub_rn(load_sample<F32>(pcm, s0 + i - 1), mean) : d;
-        w = __fsub_rn(d, __fmul_rn(0.97f, dp));
-        w = __fmul_rn(w, S.window[i]);
+    for (int n1 = 0; n1 < 16; ++n1) {
+      float we = 0.f, wo = 0.f;
+      if (n1 < 13) {
+        const int i = 32 * n1 + 2 * sub;
+        if (active && i < WIN) {
+          // Preemphasize (:200-211): w[i] -= 0.97 w[i-1] on the DC-removed samples, w[0] -= 0.97 w[0]
+          const float de = __fsub_rn(xe[n1], mean);
+          const float dprev = (i > 0) ? __fsub_rn(load_sample<F32>(pcm, s0 + i - 1), mean) : de;
+          we = __fmul_rn(__fsub_rn(de, __fmul_rn(0.97f, dprev)), S.window[i]);
+          if (i + 1 < WIN) {
+            const float dod = __fsub_rn(xo[n1], mean);
+            wo = __fmul_rn(__fsub_rn(dod, __fmul_rn(0.97f, de)), S.window[i + 1]);
+          }
+        }
       }
-      buf[__brev((unsigned)i) >> 23] = make_double2((double)w, 0.0);
+      v[n1] = make_double2((double)we, (double)wo);
+    }
+    // pass 1: DFT over n1 (z index = 16 n1 + sub), twiddle W_256^(sub k1), transpose through smem
+    fft16(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const double2 y = v[brev4(k1)];
+      const int j = 2 * sub * k1;                      // W_256^m = W_512^(2m); W_512^(j) = -W_512^(j-256)
+      double2 w = S.tw[j & 255];
+      if (j >= 256) w = make_double2(-w.x, -w.y);
+      buf[k1 * 16 + sub] = (j == 0) ? y : cmul(y, w);
     }
     __syncwarp();
-    // 512-point complex FFT in double (rfft.cc:41-47 narrows the double result to float)
-#pragma unroll 1
-    for (int s = 1; s <= 9; ++s) {
-      const int half = 1 << (s - 1);
-      const int tstep = (NFFT / 2) >> (s - 1);
 #pragma unroll
-      for (int b = lane; b < NFFT / 2; b += 32) {
-        const int pos = b & (half - 1);
-        const int i0 = ((b >> (s - 1)) << s) + pos;
-        const int i1 = i0 + half;
-        const double2 tw = S.tw[pos * tstep];
-        const double2 u = buf[i0], v = buf[i1];
-        const double vr = v.x * tw.x - v.y * tw.y;
-        const double vi = v.x * tw.y + v.y * tw.x;
-        buf[i0] = make_double2(u.x + vr, u.y + vi);
-        buf[i1] = make_double2(u.x - vr, u.y - vi);
-      }
-      __syncwarp();
-    }
-    // ComputePowerSpectrum (feature-functions.cc:28-47); bin 256 is never used by the mel bank
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf[sub * 16 + n2];   // lane = k1, values over n2
+    __syncwarp();
+    // pass 2: DFT over n2 -> Z[k1 + 16 k2]
+    fft16(v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int i = lane + 32 * k;
-      const float re = (float)buf[i].x, im = (float)buf[i].y;
-      pw[i] = (i == 0) ? __fmul_rn(re, re) : __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    for (int k2 = 0; k2 < 16; ++k2) buf[sub + 16 * k2] = v[brev4(k2)];
+    __syncwarp();
+    // real-FFT recombination: X[k] = (Z[k] + conj Z[256-k])/2 - i W_512^k (Z[k] - conj Z[256-k])/2
+    // ComputePowerSpectrum (feature-functions.cc:28-47) on the float-narrowed spectrum
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = sub + 16 * j;
+      const double2 zk = buf[k];
+      const double2 zc = buf[(256 - k) & 255];
+      const double2 xe_ = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y - zc.y));
+      const double2 xo_ = make_double2(0.5 * (zk.y + zc.y), -0.5 * (zk.x - zc.x));   // -i/2 (Z[k] - conj Z[N-k])
+      const double2 w = S.tw[k];
+      const double2 x = cadd(xe_, cmul(w, xo_));
+      const float re = (float)x.x, im = (float)x.y;
+      pw[k] = (k == 0) ? __fmul_rn(re, re) : __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
     }
     __syncwarp();
     // MelBanks::Compute (mel-computations.cc:224-235) + log(max(e, eps)) (feature-fbank.cc:102-108)
-    for (int b = lane; b < NBIN; b += 32) {
-      const int2 rg = S.mel_range[b];
-      const float* wv = S.mel_w + S.mel_w_off[b];
-      float e = 0.f;
-      for (int k = 0; k < rg.y; ++k) e = __fadd_rn(e, __fmul_rn(wv[k], pw[rg.x + k]));
-      fb[(size_t)fg * NBIN + b] = logf(fmaxf(e, FLT_EPSILON));
+    if (active) {
+      for (int b = sub; b < NBIN; b += 16) {
+        const int2 rg = S.mel_range[b];
+        const float* wv = S.mel_w + S.mel_w_off[b];
+        float e = 0.f;
+        for (int k = 0; k < rg.y; ++k) e = __fadd_rn(e, __fmul_rn(wv[k], pw[rg.x + k]));
+        fb[(size_t)fg * NBIN + b] = logf(fmaxf(e, FLT_EPSILON));
+      }
     }
     __syncwarp();
   }
@@ -169,7 +231,7 @@ int fbank_launch(const void* pcm, int is_f32, const int64_t* sample_off, const i
     if (e2 != cudaSuccess) return (int)e2;
     attr_set = true;
   }
-  int blocks = (n_frames_total + FB_WARPS - 1) / FB_WARPS;
+  int blocks = (n_frames_total + FB_FRAMES - 1) / FB_FRAMES;
   const int cap = 148 * 2 * 8;
   if (blocks > cap) blocks = cap;
   // total packed mel weights is bounded by 2 * 256; pass the real count through mel_w_off[79] + range

@@ -28,7 +28,8 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;
 constexpr int kTmemCols = 512;
 constexpr int SCR_STRIDE = 144;                  // bytes per scratch row: 128 + 16 (bank-conflict-free 16 B accesses)
 constexpr int SCR_BYTES = 32 * SCR_STRIDE;       // per epilogue warp
-constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + kEpiWarps * SCR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int BIAS_BYTES = 128 * 4;                  // per epilogue warp: bias of its 128 columns
+constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + kEpiWarps * (SCR_BYTES + BIAS_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 
 struct KArgs {
   int M, N, K;
@@ -44,7 +45,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sScr = smem + STAGES * (A_BYTES + B_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sScr + kEpiWarps * SCR_BYTES);
+  uint8_t* sBias = sScr + kEpiWarps * SCR_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kEpiWarps * BIAS_BYTES);
   uint64_t* full = bars;                 // used on the even CTA
   uint64_t* empty = bars + STAGES;       // one set per CTA, signalled by the multicast commit
   uint64_t* tfull = bars + 2 * STAGES;   // one set per CTA
@@ -147,6 +149,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const GemmEpilogue& e = a.e;
     uint8_t* scr = sScr + ew * SCR_BYTES;
     uint8_t* my_row = scr + lane * SCR_STRIDE;
+    float* sbias = reinterpret_cast<float*>(sBias + ew * BIAS_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total; tile += n_pairs) {
@@ -158,6 +161,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < M;
       float best_v = -INFINITY;
       int best_i = -1;
+      if (e.bias) {  // this warp's 128 bias values: one coalesced load per tile, read back as smem broadcasts
+        const int bc = n_blk * BN + half * 128 + lane * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bc < N) b = __ldg(reinterpret_cast<const float4*>(e.bias + bc));
+        *reinterpret_cast<float4*>(sbias + lane * 4) = b;
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col0 = n_blk * BN + half * 128 + c * 32;
@@ -204,8 +214,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int col = col0 + 4 * g;
           float v0 = __uint_as_float(r[4 * g + 0]), v1 = __uint_as_float(r[4 * g + 1]);
           float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
-          if (e.bias && col < N) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+          if (e.bias) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + 4 * g);
             v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
           }
           if (e.relu == 1) {
