@@ -17,14 +17,16 @@
 namespace pf {
 namespace {
 
-constexpr int BQ = 128, BKV = 64, HD = 128, KV_STAGES = 3;
+constexpr int BQ = 128, BKV = 64, HD = 128, KV_STAGES = 2, P_BUFS = 1;
 constexpr int Q_BYTES = BQ * HD * 2;       // 32768: two 128x64 swizzled boxes
 constexpr int K_BYTES = BKV * HD * 2;      // 16384: two 64x64 boxes
 constexpr int STAGE_BYTES = 2 * K_BYTES;   // K + V
 constexpr int P_BYTES = BQ * BKV * 2;      // 16384
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 256;
-constexpr int kSmemBytes = Q_BYTES + KV_STAGES * STAGE_BYTES + 2 * P_BYTES + 1024 + 256;
+// 112 KB + barriers: two CTAs fit one SM (2 x 256 TMEM columns, 2 x (112.25 + 1) KB shared memory), so one CTA's
+// TMA / softmax latency is covered by the other's MMAs.
+constexpr int kSmemBytes = Q_BYTES + KV_STAGES * STAGE_BYTES + P_BUFS * P_BYTES + 256;
 
 struct AArgs {
   const int* q_row_off;
@@ -44,7 +46,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AArgs a) {
   const AttnWork w = a.work[blockIdx.x];
   const int h = blockIdx.y;
@@ -55,12 +57,12 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q_row = a.q_row_off[w.seg] + w.q0;
   const int kv_row = a.kv_row_off[w.seg];
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + Q_BYTES;
   uint8_t* sP = sKV + KV_STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BUFS * P_BYTES);
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* q_full = bars;                  // 1
   uint64_t* kv_full = bars + 1;             // 3
   uint64_t* kv_empty = bars + 4;            // 3
@@ -151,8 +153,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int jj = 0; jj < nb; ++jj) {
         const int it = nb + jj;
         if (jj + 1 < nb) issue_s(it + 1);
-        const int pb = jj & 1;
-        mbar_wait(&p_full[pb], (jj >> 1) & 1);
+        const int pb = jj % P_BUFS;
+        mbar_wait(&p_full[pb], (jj / P_BUFS) & 1);
         tc_fence_after();
         const uint32_t p_addr = smem_u32(sP + pb * P_BYTES);
         const uint32_t v_addr = smem_u32(sKV + (it % KV_STAGES) * STAGE_BYTES + K_BYTES);
@@ -199,7 +201,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int jj = 0; jj < nb; ++jj) {
       const int it = nb + jj;
       const int sb = it & 1;
-      const int pb = jj & 1;
+      const int pb = jj % P_BUFS;
       mbar_wait(&s_full[sb], (it >> 1) & 1);
       tc_fence_after();
       const int nvalid = Tk - jj * BKV;
@@ -221,13 +223,11 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
       // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
-      mbar_wait(&p_empty[pb], ((jj >> 1) & 1) ^ 1);
-      uint8_t* prow = sP + pb * P_BYTES + row * 128;
+      mbar_wait(&p_empty[pb], ((jj / P_BUFS) & 1) ^ 1);
+      const uint32_t prow = smem_u32(sP + pb * P_BYTES + row * 128);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 v = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        *reinterpret_cast<uint4*>(prow + ((j ^ (row & 7)) << 4)) = v;
-      }
+      for (int j = 0; j < 8; ++j)
+        sts128(prow + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
@@ -250,7 +250,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
           o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
           o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c4 * 32 + g * 8) = o;
+          stg128(orow + c4 * 32 + g * 8, o);
         }
       }
     }

@@ -112,7 +112,7 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int FSMN_RUN = 22;  // multiple of 11 keeps the ring indices static
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
             __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
@@ -136,50 +136,58 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
 
   // input i (row r0 - 5 + i) feeds outputs o = i - 5 - d, d = -5..5, with tap j = d + 5; output o is
   // complete after input i = o + 10.
-#pragma unroll 1
-  for (int base = 0; base < FSMN_RUN + 10; base += 11) {
-    // batch the 11 row-info and 11 data loads of this step so they are all in flight together
-    int2 info[11];
-    uint2 raw[11];
+  constexpr int NSTEP = (FSMN_RUN + 10 + 10) / 11;
+  int2 info[2][11];
+  uint2 raw[2][11];
+  auto load_step = [&](int step, int2 (&inf)[11], uint2 (&rw)[11]) {
 #pragma unroll
     for (int ii = 0; ii < 11; ++ii) {
-      const int i = base + ii;
+      const int i = step * 11 + ii;
       const int rin = r0 - 5 + i;
       const bool in_range = rin >= 0 && rin < nrows && i < FSMN_RUN + 10;
-      info[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
-      raw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
+      inf[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
+      rw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
     }
+  };
+  load_step(0, info[0], raw[0]);
+  unsigned prev_valid = 0;  // bit ii: input ii of the previous step was a real frame row
+#pragma unroll
+  for (int step = 0; step < NSTEP; ++step) {
+    const int cur = step & 1;
+    if (step + 1 < NSTEP) load_step(step + 1, info[cur ^ 1], raw[cur ^ 1]);  // in flight while this step computes
+    unsigned cur_valid = 0;
 #pragma unroll
     for (int ii = 0; ii < 11; ++ii) {
-      const int i = base + ii;
+      const int i = step * 11 + ii;
+      const int2 inf = info[cur][ii];
       float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (info[ii].x >= 0) {  // gap rows and rows outside the batch contribute nothing
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&raw[ii].x);
-        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&raw[ii].y);
+      if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
+        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&raw[cur][ii].x);
+        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&raw[cur][ii].y);
         x[0] = __low2float(h0); x[1] = __high2float(h0); x[2] = __low2float(h1); x[3] = __high2float(h1);
+        cur_valid |= 1u << ii;
       }
 #pragma unroll
       for (int d = -5; d <= 5; ++d) {
         // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
-        const bool ok = info[ii].x >= 0 && (info[ii].x - d) >= 0 && (info[ii].x - d) < info[ii].y;
+        const bool ok = inf.x >= 0 && (inf.x - d) >= 0 && (inf.x - d) < inf.y;
         const int slot = ((ii - 5 - d) % 11 + 11) % 11;
         if (ok) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) acc[slot][k] = fmaf(w[d + 5][k], x[k], acc[slot][k]);
         }
       }
-      // output o = i - 10 has now seen all of its inputs; its row info is the one loaded 5 steps ago,
-      // but re-deriving it from row_info keeps the ring logic independent of the batching
+      // output o = i - 10 (row rin - 5) has now seen all of its inputs; it was input i - 5
       const int o = i - 10;
       const int slot_done = (ii + 1) % 11;
       if (o >= 0 && o < FSMN_RUN && r0 + o < nrows) {
         const int rout = r0 + o;
-        const int2 oi = row_info[rout];
+        const bool out_valid = (ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u);
         if (mode == 0) {
           uint2 pk = make_uint2(0, 0);
-          if (oi.x >= 0) { pk.x = pack2(acc[slot_done][0], acc[slot_done][1]); pk.y = pack2(acc[slot_done][2], acc[slot_done][3]); }
+          if (out_valid) { pk.x = pack2(acc[slot_done][0], acc[slot_done][1]); pk.y = pack2(acc[slot_done][2], acc[slot_done][3]); }
           *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
-        } else if (oi.x >= 0) {
+        } else if (out_valid) {
           float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
           float4 v = *yp;
           v.x += acc[slot_done][0]; v.y += acc[slot_done][1]; v.z += acc[slot_done][2]; v.w += acc[slot_done][3];
@@ -189,6 +197,7 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[slot_done][k] = 0.f;
     }
+    prev_valid = cur_valid;
   }
 }
 

@@ -147,9 +147,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;  // TMEM lane quarter this warp may address
     const int half = ew >> 2;      // which 128-column half of the 256-wide tile
     const GemmEpilogue& e = a.e;
-    uint8_t* scr = sScr + ew * SCR_BYTES;
-    uint8_t* my_row = scr + lane * SCR_STRIDE;
-    float* sbias = reinterpret_cast<float*>(sBias + ew * BIAS_BYTES);
+    const uint32_t scr = smem_u32(sScr + ew * SCR_BYTES);          // shared-space addresses (STS/LDS, no generic ops)
+    const uint32_t my_row = scr + lane * SCR_STRIDE;
+    const uint32_t sbias = smem_u32(sBias + ew * BIAS_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total; tile += n_pairs) {
@@ -163,10 +163,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int best_i = -1;
       if (e.bias) {  // this warp's 128 bias values: one coalesced load per tile, read back as smem broadcasts
         const int bc = n_blk * BN + half * 128 + lane * 4;
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bc < N) b = __ldg(reinterpret_cast<const float4*>(e.bias + bc));
-        *reinterpret_cast<float4*>(sbias + lane * 4) = b;
-        __syncwarp();
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (bc < N) b = ldg128_nc(e.bias + bc);
+        sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+        warp_sync_smem();
       }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -180,32 +180,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float4 res[8];
         uint4 add[4];
         if (e.res_f32) {
+          float4 t[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row_base + rr < M && col0 + 4 * ch < N)
-              v = *reinterpret_cast<const float4*>(e.res_f32 + (size_t)(row_base + rr) * e.ld_res + col0 + 4 * ch);
-            *reinterpret_cast<float4*>(scr + rr * SCR_STRIDE + ch * 16) = v;
+              t[i] = ldg128f(e.res_f32 + (size_t)(row_base + rr) * e.ld_res + col0 + 4 * ch);
           }
-          __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 8; ++g) res[g] = *reinterpret_cast<const float4*>(my_row + g * 16);
-          __syncwarp();
+          for (int i = 0; i < 8; ++i)
+            sts128f(scr + ((lane >> 3) + 4 * i) * SCR_STRIDE + (lane & 7) * 16, t[i].x, t[i].y, t[i].z, t[i].w);
+          warp_sync_smem();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) res[g] = lds128f(my_row + g * 16);
+          warp_sync_smem();
         }
         if (e.add_bf16) {
+          uint4 t[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
-            uint4 v = make_uint4(0, 0, 0, 0);
+            t[i] = make_uint4(0, 0, 0, 0);
             if (row_base + rr < M && col0 + 8 * ch < N)
-              v = *reinterpret_cast<const uint4*>(e.add_bf16 + (size_t)(row_base + rr) * e.ld_add + col0 + 8 * ch);
-            *reinterpret_cast<uint4*>(scr + rr * SCR_STRIDE + ch * 16) = v;
+              t[i] = ldg128_nc(e.add_bf16 + (size_t)(row_base + rr) * e.ld_add + col0 + 8 * ch);
           }
-          __syncwarp();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) add[g] = *reinterpret_cast<const uint4*>(my_row + g * 16);
-          __syncwarp();
+          for (int i = 0; i < 4; ++i)
+            sts128(scr + ((lane >> 2) + 8 * i) * SCR_STRIDE + (lane & 3) * 16, t[i].x, t[i].y, t[i].z, t[i].w);
+          warp_sync_smem();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) add[g] = lds128(my_row + g * 16);
+          warp_sync_smem();
         }
         tmem_ld_wait();
         float v[32];
@@ -215,7 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v0 = __uint_as_float(r[4 * g + 0]), v1 = __uint_as_float(r[4 * g + 1]);
           float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
           if (e.bias) {
-            const float4 b = *reinterpret_cast<const float4*>(sbias + c * 32 + 4 * g);
+            const float4 b = lds128f(sbias + (c * 32 + 4 * g) * 4);
             v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
           }
           if (e.relu == 1) {
@@ -244,33 +250,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (e.out_f32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(my_row + g * 16) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          __syncwarp();
+          for (int g = 0; g < 8; ++g) sts128f(my_row + g * 16, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          warp_sync_smem();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+            const float4 o = lds128f(scr + rr * SCR_STRIDE + ch * 16);
             if (row_base + rr < M && col0 + 4 * ch < N)
-              *reinterpret_cast<float4*>(e.out_f32 + (size_t)(row_base + rr) * e.ld_out_f32 + col0 + 4 * ch) =
-                  *reinterpret_cast<const float4*>(scr + rr * SCR_STRIDE + ch * 16);
+              stg128f(e.out_f32 + (size_t)(row_base + rr) * e.ld_out_f32 + col0 + 4 * ch, o);
           }
-          __syncwarp();
+          warp_sync_smem();
         }
         if (e.out_bf16) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(my_row + g * 16) =
-                make_uint4(pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                           pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
-          __syncwarp();
+            sts128(my_row + g * 16, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                   pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+          warp_sync_smem();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
+            const uint4 o = lds128(scr + rr * SCR_STRIDE + ch * 16);
             if (row_base + rr < M && col0 + 8 * ch < N)
-              *reinterpret_cast<uint4*>(e.out_bf16 + (size_t)(row_base + rr) * e.ld_out_bf16 + col0 + 8 * ch) =
-                  *reinterpret_cast<const uint4*>(scr + rr * SCR_STRIDE + ch * 16);
+              stg128(e.out_bf16 + (size_t)(row_base + rr) * e.ld_out_bf16 + col0 + 8 * ch, o);
           }
-          __syncwarp();
+          warp_sync_smem();
         }
       }
       if (e.argmax && row_ok && best_i >= 0) atomicMax(e.argmax + row, argmax_pack(best_v, best_i));
