@@ -112,6 +112,13 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int FSMN_RUN = 22;  // multiple of 11 keeps the ring indices static
 
+// packed fp32x2 FMA (sm_100): two FMAs per issued instruction
+__device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2& b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<unsigned long long&>(acc))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+
 __global__ void __launch_bounds__(128, 3)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
@@ -120,22 +127,19 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
   const int r0 = blockIdx.x * FSMN_RUN;
   if (r0 >= nrows) return;
   const int c = threadIdx.x * 4;
-  float w[11][4];
+  float2 w[11][2];
 #pragma unroll
   for (int j = 0; j < 11; ++j) {
     const float4 t = *reinterpret_cast<const float4*>(w_t + j * 512 + c);
-    w[j][0] = t.x; w[j][1] = t.y; w[j][2] = t.z; w[j][3] = t.w;
+    w[j][0] = make_float2(t.x, t.y); w[j][1] = make_float2(t.z, t.w);
   }
+  w[5][0].x += 1.0f; w[5][0].y += 1.0f; w[5][1].x += 1.0f; w[5][1].y += 1.0f;  // identity branch
+  float2 acc[11][2];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) w[5][k] += 1.0f;  // identity branch
-  float acc[11][4];
-#pragma unroll
-  for (int s = 0; s < 11; ++s)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[s][k] = 0.f;
+  for (int s = 0; s < 11; ++s) { acc[s][0] = make_float2(0.f, 0.f); acc[s][1] = make_float2(0.f, 0.f); }
 
   // input i (row r0 - 5 + i) feeds outputs o = i - 5 - d, d = -5..5, with tap j = d + 5; output o is
-  // complete after input i = o + 10.
+  // complete after input i = o + 10.  Everything below is fully unrolled, so o and the ring slot are static.
   constexpr int NSTEP = (FSMN_RUN + 10 + 10) / 11;
   int2 info[2][11];
   uint2 raw[2][11];
@@ -160,42 +164,59 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
     for (int ii = 0; ii < 11; ++ii) {
       const int i = step * 11 + ii;
       const int2 inf = info[cur][ii];
-      float x[4] = {0.f, 0.f, 0.f, 0.f};
       if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
-        const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&raw[cur][ii].x);
-        const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&raw[cur][ii].y);
-        x[0] = __low2float(h0); x[1] = __high2float(h0); x[2] = __low2float(h1); x[3] = __high2float(h1);
+        // bf16 -> fp32 is a 16-bit shift
+        const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
+        const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
         cur_valid |= 1u << ii;
-      }
+        if (inf.x >= 5 && inf.x + 5 < inf.y) {
+          // interior frame: all 11 neighbours are in the same segment
 #pragma unroll
-      for (int d = -5; d <= 5; ++d) {
-        // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
-        const bool ok = inf.x >= 0 && (inf.x - d) >= 0 && (inf.x - d) < inf.y;
-        const int slot = ((ii - 5 - d) % 11 + 11) % 11;
-        if (ok) {
+          for (int d = -5; d <= 5; ++d) {
+            const int o = i - 5 - d;
+            if (o >= 0 && o < FSMN_RUN) {  // static: outputs of other runs are not accumulated here
+              const int slot = ((ii - 5 - d) % 11 + 11) % 11;
+              ffma2(acc[slot][0], w[d + 5][0], x0);
+              ffma2(acc[slot][1], w[d + 5][1], x1);
+            }
+          }
+        } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[slot][k] = fmaf(w[d + 5][k], x[k], acc[slot][k]);
+          for (int d = -5; d <= 5; ++d) {
+            const int o = i - 5 - d;
+            if (o >= 0 && o < FSMN_RUN) {
+              // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
+              const bool ok = (inf.x - d) >= 0 && (inf.x - d) < inf.y;
+              const int slot = ((ii - 5 - d) % 11 + 11) % 11;
+              if (ok) {
+                ffma2(acc[slot][0], w[d + 5][0], x0);
+                ffma2(acc[slot][1], w[d + 5][1], x1);
+              }
+            }
+          }
         }
       }
       // output o = i - 10 (row rin - 5) has now seen all of its inputs; it was input i - 5
       const int o = i - 10;
       const int slot_done = (ii + 1) % 11;
-      if (o >= 0 && o < FSMN_RUN && r0 + o < nrows) {
-        const int rout = r0 + o;
-        const bool out_valid = (ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u);
-        if (mode == 0) {
-          uint2 pk = make_uint2(0, 0);
-          if (out_valid) { pk.x = pack2(acc[slot_done][0], acc[slot_done][1]); pk.y = pack2(acc[slot_done][2], acc[slot_done][3]); }
-          *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
-        } else if (out_valid) {
-          float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
-          float4 v = *yp;
-          v.x += acc[slot_done][0]; v.y += acc[slot_done][1]; v.z += acc[slot_done][2]; v.w += acc[slot_done][3];
-          *yp = v;
+      if (o >= 0 && o < FSMN_RUN) {
+        if (r0 + o < nrows) {
+          const int rout = r0 + o;
+          const bool out_valid = (ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u);
+          if (mode == 0) {
+            uint2 pk = make_uint2(0, 0);
+            if (out_valid) { pk.x = pack2(acc[slot_done][0].x, acc[slot_done][0].y); pk.y = pack2(acc[slot_done][1].x, acc[slot_done][1].y); }
+            *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
+          } else if (out_valid) {
+            float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
+            float4 v = *yp;
+            v.x += acc[slot_done][0].x; v.y += acc[slot_done][0].y; v.z += acc[slot_done][1].x; v.w += acc[slot_done][1].y;
+            *yp = v;
+          }
         }
+        acc[slot_done][0] = make_float2(0.f, 0.f);
+        acc[slot_done][1] = make_float2(0.f, 0.f);
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[slot_done][k] = 0.f;
     }
     prev_valid = cur_valid;
   }
