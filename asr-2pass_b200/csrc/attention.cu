@@ -12,6 +12,7 @@
 // TMEM: S double buffered (2 x 64 columns) + O (128 columns) = 256 columns.
 #include "attention.cuh"
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace pf {
@@ -48,6 +49,8 @@ __device__ __forceinline__ float ex2(float x) {
 
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AArgs a) {
+  pdl_wait();   // q_len of the decoder is produced by the CIF kernels
+  pdl_launch_dependents();
   const AttnWork w = a.work[blockIdx.x];
   const int h = blockIdx.y;
   const int Tq = a.q_len[w.seg];
@@ -268,6 +271,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_check_kernel(AArgs a, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kv, int ldkv,
                                   float scale) {
+  pdl_wait();
+  pdl_launch_dependents();
   const AttnWork w = a.work[blockIdx.x];
   const int h = blockIdx.y;
   const int Tq = a.q_len[w.seg], Tk = a.kv_len[w.seg];
@@ -323,16 +328,14 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   if (rc) return rc;
   AArgs a = make_args(p);
   dim3 grid(p.n_work, p.n_heads);
-  attn_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmKV, a);
-  return (int)cudaGetLastError();
+  return launch_kernel(attn_tcgen05_kernel, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
 }
 
 int attention_check_kernel(const AttnProblem& p, cudaStream_t stream) {
   if (p.n_work <= 0) return 0;
   AArgs a = make_args(p);
   dim3 grid(p.n_work, p.n_heads);
-  attn_check_kernel<<<grid, 256, 0, stream>>>(a, p.q, p.ldq, p.kv, p.ldkv, p.scale);
-  return (int)cudaGetLastError();
+  return launch_kernel(attn_check_kernel, grid, dim3(256), 0, stream, a, p.q, p.ldq, p.kv, p.ldkv, p.scale);
 }
 
 }  // namespace pf

@@ -1,5 +1,6 @@
 // K3 LayerNorm, K6 FSMN memory block, K7/K8 CIF predictor tail, K11 argmax decode.  See kernels.cuh.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace pf {
 namespace {
@@ -23,6 +24,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
                  float* __restrict__ out_f32, const int2* __restrict__ row_info, int zero_gap) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int VW = IN_BF16 ? 8 : 4;            // elements per vector load
   constexpr int NVEC = D / VW;                   // vectors per row
   constexpr int PER = (NVEC + 31) / 32;          // vectors per lane
@@ -123,6 +126,8 @@ __global__ void __launch_bounds__(128, 3)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
             __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int nrows = rows_dev ? *rows_dev : rows;
   const int r0 = blockIdx.x * FSMN_RUN;
   if (r0 >= nrows) return;
@@ -228,6 +233,8 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
 __global__ void __launch_bounds__(256)
 cif_alpha_kernel(const float* __restrict__ h, int M, const float* __restrict__ w, const float* __restrict__ b,
                  const int2* __restrict__ row_info, float tail, float* __restrict__ alpha) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -255,6 +262,8 @@ __global__ void __launch_bounds__(32)
 cif_fire_kernel(const float* __restrict__ alpha, const int* __restrict__ row_off, const int* __restrict__ seg_T,
                 float threshold, float* __restrict__ cur_o, float* __restrict__ rem_o, float* __restrict__ fire_val,
                 int* __restrict__ n_tok, int* __restrict__ fire_row) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int seg = blockIdx.x;
   const int lane = threadIdx.x;
   const int base = row_off[seg];
@@ -292,6 +301,8 @@ cif_fire_kernel(const float* __restrict__ alpha, const int* __restrict__ row_off
 
 __global__ void __launch_bounds__(1024)
 cif_scan_kernel(const int* __restrict__ n_tok, int n_seg, int* __restrict__ tok_off, int* __restrict__ total) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ int wsum[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = (n_seg + 1023) / 1024;
@@ -327,6 +338,8 @@ __global__ void __launch_bounds__(128)
 cif_embed_kernel(const float* __restrict__ enc, const float* __restrict__ cur, const float* __restrict__ rem,
                  const int* __restrict__ fire_row, const int* __restrict__ row_off, const int* __restrict__ tok_off,
                  int n_seg, float* __restrict__ emb, int2* __restrict__ tok_info, int* __restrict__ tok_frame) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int g = blockIdx.x;
   if (g >= tok_off[n_seg]) return;
   int lo = 0, hi = n_seg;
@@ -364,6 +377,8 @@ cif_embed_kernel(const float* __restrict__ enc, const float* __restrict__ cur, c
 
 __global__ void argmax_decode_kernel(const unsigned long long* __restrict__ packed, const int* __restrict__ n_dev, int cap,
                                      int* __restrict__ ids) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n_dev ? min(*n_dev, cap) : cap;
   if (g >= n) return;
@@ -371,6 +386,8 @@ __global__ void argmax_decode_kernel(const unsigned long long* __restrict__ pack
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16(in[i]);
 }
@@ -380,10 +397,8 @@ int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, c
                 float eps, __nv_bfloat16* ob, float* of, const int2* ri, int zg, cudaStream_t s) {
   const int blocks = (rows + 7) / 8;
   if (in_is_bf16)
-    layernorm_kernel<D, true><<<blocks, 256, 0, s>>>(in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
-  else
-    layernorm_kernel<D, false><<<blocks, 256, 0, s>>>(in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
-  return (int)cudaGetLastError();
+    return launch_kernel(layernorm_kernel<D, true>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
+  return launch_kernel(layernorm_kernel<D, false>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
 }
 
 }  // namespace
@@ -403,50 +418,44 @@ int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_d
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
                 const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s) {
   if (rows <= 0) return 0;
-  fsmn_kernel<<<(rows + FSMN_RUN - 1) / FSMN_RUN, 128, 0, s>>>(in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
-  return (int)cudaGetLastError();
+  return launch_kernel(fsmn_kernel, dim3((rows + FSMN_RUN - 1) / FSMN_RUN), dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev,
+                       mode, out_bf16, y_f32);
 }
 
 int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,
                      float* alpha, cudaStream_t s) {
   if (M <= 0) return 0;
-  cif_alpha_kernel<<<(M + 7) / 8, 256, 0, s>>>(h, M, w, b, row_info, tail, alpha);
-  return (int)cudaGetLastError();
+  return launch_kernel(cif_alpha_kernel, dim3((M + 7) / 8), dim3(256), 0, s, h, M, w, b, row_info, tail, alpha);
 }
 
 int cif_fire_launch(const float* alpha, const int* row_off, const int* seg_T, int n_seg, float threshold, float* cur,
                     float* rem, float* fire_val, int* n_tok, int* fire_row, cudaStream_t s) {
   if (n_seg <= 0) return 0;
-  cif_fire_kernel<<<n_seg, 32, 0, s>>>(alpha, row_off, seg_T, threshold, cur, rem, fire_val, n_tok, fire_row);
-  return (int)cudaGetLastError();
+  return launch_kernel(cif_fire_kernel, dim3(n_seg), dim3(32), 0, s, alpha, row_off, seg_T, threshold, cur, rem, fire_val, n_tok, fire_row);
 }
 
 int cif_scan_launch(const int* n_tok, int n_seg, int* tok_off, int* n_tok_total, cudaStream_t s) {
   if (n_seg <= 0) return 0;
-  cif_scan_kernel<<<1, 1024, 0, s>>>(n_tok, n_seg, tok_off, n_tok_total);
-  return (int)cudaGetLastError();
+  return launch_kernel(cif_scan_kernel, dim3(1), dim3(1024), 0, s, n_tok, n_seg, tok_off, n_tok_total);
 }
 
 int cif_embed_launch(const float* enc_f32, const float* cur, const float* rem, const int* fire_row, const int* row_off,
                      const int* tok_off, int n_seg, int tok_cap, float* emb, int2* tok_info, int* tok_frame,
                      cudaStream_t s) {
   if (tok_cap <= 0) return 0;
-  cif_embed_kernel<<<tok_cap, 128, 0, s>>>(enc_f32, cur, rem, fire_row, row_off, tok_off, n_seg, emb, tok_info, tok_frame);
-  return (int)cudaGetLastError();
+  return launch_kernel(cif_embed_kernel, dim3(tok_cap), dim3(128), 0, s, enc_f32, cur, rem, fire_row, row_off, tok_off, n_seg, emb, tok_info, tok_frame);
 }
 
 int argmax_decode_launch(const unsigned long long* packed, const int* n_dev, int cap, int* ids, cudaStream_t s) {
   if (cap <= 0) return 0;
-  argmax_decode_kernel<<<(cap + 255) / 256, 256, 0, s>>>(packed, n_dev, cap, ids);
-  return (int)cudaGetLastError();
+  return launch_kernel(argmax_decode_kernel, dim3((cap + 255) / 256), dim3(256), 0, s, packed, n_dev, cap, ids);
 }
 
 int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
   if (n <= 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  f32_to_bf16_kernel<<<(int)blocks, 256, 0, s>>>(in, out, n);
-  return (int)cudaGetLastError();
+  return launch_kernel(f32_to_bf16_kernel, dim3((int)blocks), dim3(256), 0, s, in, out, n);
 }
 
 }  // namespace pf

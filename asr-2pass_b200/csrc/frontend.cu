@@ -11,6 +11,7 @@
 #include <float.h>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace pf {
 namespace {
@@ -88,6 +89,8 @@ fbank_kernel(const void* __restrict__ pcm, const int64_t* __restrict__ sample_of
   for (int i = threadIdx.x; i < mel_w_total; i += blockDim.x) S.mel_w[i] = t.mel_w[i];
   for (int i = threadIdx.x; i < NBIN; i += blockDim.x) { S.mel_range[i] = t.mel_range[i]; S.mel_w_off[i] = t.mel_w_off[i]; }
   __syncthreads();
+  pdl_wait();   // the tables above are constants; PCM and layout come from the stream
+  pdl_launch_dependents();
 
   double2* buf = S.buf[slot];
   float* pw = S.power[slot];
@@ -189,6 +192,8 @@ __global__ void __launch_bounds__(FEAT / 4)
 lfr_cmvn_posenc_kernel(const float* __restrict__ fb, const int* __restrict__ fb_off, const int* __restrict__ row_seg,
                        const int2* __restrict__ row_info, int M, FrontendTables t, float scale,
                        float* __restrict__ x0, float* __restrict__ feats_tap) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;
   if (row >= M) return;
   const int c = threadIdx.x * 4;
@@ -237,17 +242,16 @@ int fbank_launch(const void* pcm, int is_f32, const int64_t* sample_off, const i
   // total packed mel weights is bounded by 2 * 256; pass the real count through mel_w_off[79] + range
   const int mel_total = 1024;
   if (is_f32)
-    fbank_kernel<true><<<blocks, FB_WARPS * 32, sizeof(FbSmem), s>>>(pcm, sample_off, fb_off, n_seg, n_frames_total, t, mel_total, fb);
-  else
-    fbank_kernel<false><<<blocks, FB_WARPS * 32, sizeof(FbSmem), s>>>(pcm, sample_off, fb_off, n_seg, n_frames_total, t, mel_total, fb);
-  return (int)cudaGetLastError();
+    return launch_kernel(fbank_kernel<true>, dim3(blocks), dim3(FB_WARPS * 32), sizeof(FbSmem), s, pcm, sample_off, fb_off, n_seg,
+                         n_frames_total, t, mel_total, fb);
+  return launch_kernel(fbank_kernel<false>, dim3(blocks), dim3(FB_WARPS * 32), sizeof(FbSmem), s, pcm, sample_off, fb_off, n_seg,
+                       n_frames_total, t, mel_total, fb);
 }
 
 int lfr_cmvn_posenc_launch(const float* fb, const int* fb_off, const int* row_seg, const int2* row_info, int M,
                            const FrontendTables& t, float scale, float* x0, float* feats_tap, cudaStream_t s) {
   if (M <= 0) return 0;
-  lfr_cmvn_posenc_kernel<<<M, FEAT / 4, 0, s>>>(fb, fb_off, row_seg, row_info, M, t, scale, x0, feats_tap);
-  return (int)cudaGetLastError();
+  return launch_kernel(lfr_cmvn_posenc_kernel, dim3(M), dim3(FEAT / 4), 0, s, fb, fb_off, row_seg, row_info, M, t, scale, x0, feats_tap);
 }
 
 }  // namespace pf

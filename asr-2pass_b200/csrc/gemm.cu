@@ -12,6 +12,7 @@
 //                 bf16 or fp32, staged through a per-warp smem tile so every global load and store is a
 //                 run of full 32-byte sectors; optional fused argmax.
 #include "gemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace pf {
@@ -58,11 +59,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t cta = cluster_ctarank();
   const bool leader = cta == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int M = a.m_dev ? *a.m_dev : a.M;
   const int N = a.N;
-  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
   const int n_tiles = (N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles;
   const int k_blocks = (a.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -86,6 +84,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above overlaps the previous kernel's tail (PDL); activations are only touched from here on.
+  pdl_wait();
+  pdl_launch_dependents();
+  const int M = a.m_dev ? *a.m_dev : a.M;
+  const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int total = m_tiles * n_tiles;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -352,8 +356,7 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
-  gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, a);
-  return (int)cudaGetLastError();
+  return launch_kernel(gemm_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
 }
 
 }  // namespace pf
