@@ -49,7 +49,7 @@ EXPORTS = [
     "b200pf_engine_set_option", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
     "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
-    "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_conv3",
+    "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
 ]
 
@@ -97,6 +97,7 @@ def lib():
     L.b200pf_batch_tap.argtypes = [C.c_void_p, C.c_char_p, C.c_int, c_f32p, C.c_int64, c_i64p]
     L.b200pf_op_gemm.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, c_f32p, c_i32p]
+    L.b200pf_op_gemm_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p]
     L.b200pf_op_conv3.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p]
     L.b200pf_op_layernorm.argtypes = [C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, C.c_float, C.c_int, c_f32p, c_f32p]
     L.b200pf_op_attention.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int,
@@ -414,6 +415,12 @@ def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=
     _check(lib().b200pf_op_gemm(device, _p(A), _p(W), _p(bias), _p(add), _p(res), M, N, K, int(relu), int(out_bf16),
                                 _p(out), _p(am, c_i32p)))
     return (out, am) if argmax else out
+
+
+def op_gemm_bench(M, N, K, mode=0, iters=20, device=0):
+    ms = C.c_float()
+    _check(lib().b200pf_op_gemm_bench(device, M, N, K, mode, iters, C.byref(ms)))
+    return ms.value
 
 
 def op_conv3(X, Wr, bias, device=0):

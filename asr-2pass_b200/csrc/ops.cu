@@ -99,6 +99,38 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   return 0;
 }
 
+int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, float* ms_out) {
+  RC(select_device(device));
+  DevBuf dA, dW, dBias, dAdd, dX, dOutB, dAm;
+  RC(dA.alloc((size_t)M * K * 2)); RC(dW.alloc((size_t)N * K * 2)); RC(dBias.alloc((size_t)N * 4));
+  RC(dAdd.alloc((size_t)M * N * 2)); RC(dX.alloc((size_t)M * N * 4)); RC(dOutB.alloc((size_t)M * N * 2)); RC(dAm.alloc((size_t)M * 8));
+  // 0x3c3c... is bf16 0.0115, a harmless finite pattern
+  RC(check_cuda(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2), "memset")); RC(check_cuda(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2), "memset"));
+  RC(check_cuda(cudaMemset(dBias.p, 0, (size_t)N * 4), "memset")); RC(check_cuda(cudaMemset(dAdd.p, 0x3c, (size_t)M * N * 2), "memset"));
+  RC(check_cuda(cudaMemset(dX.p, 0, (size_t)M * N * 4), "memset")); RC(check_cuda(cudaMemset(dAm.p, 0, (size_t)M * 8), "memset"));
+  GemmProblem p;
+  p.A = dA.as<__nv_bfloat16>(); p.lda = K; p.rows_a = M; p.W = dW.as<__nv_bfloat16>(); p.ldw = K; p.M = M; p.N = N; p.K = K;
+  GemmEpilogue e;
+  e.bias = dBias.as<float>();
+  if (mode == 0 || mode == 1) { e.out_bf16 = dOutB.as<__nv_bfloat16>(); e.ld_out_bf16 = N; e.relu = mode; }
+  if (mode == 2 || mode == 3) { e.res_f32 = dX.as<float>(); e.ld_res = N; e.out_f32 = dX.as<float>(); e.ld_out_f32 = N; }
+  if (mode == 3) { e.add_bf16 = dAdd.as<__nv_bfloat16>(); e.ld_add = N; }
+  if (mode == 4) e.argmax = dAm.as<unsigned long long>();
+  const int sms = sm_count();
+  for (int i = 0; i < 3; ++i) { int rc = gemm_bf16_tcgen05(p, e, sms, 0); if (rc) return check_cuda((cudaError_t)rc, "gemm launch"); }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, 0);
+  for (int i = 0; i < iters; ++i) { int rc = gemm_bf16_tcgen05(p, e, sms, 0); if (rc) return check_cuda((cudaError_t)rc, "gemm launch"); }
+  cudaEventRecord(b, 0);
+  RC(sync_ok("op_gemm_bench"));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (ms_out) *ms_out = ms / iters;
+  return 0;
+}
+
 int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bias, int M, int C, float* out) {
   RC(select_device(device));
   DevBuf tx, tw, dX, dW, dB, dOut;

@@ -126,6 +126,10 @@ int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int
  * argmax_out (optional, [M]) receives the fused greedy argmax (first maximum wins, util.cpp:63-74). */
 int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
                    int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out);
+/* Times `iters` back-to-back launches of the GEMM on device-resident dummy operands (CUDA events); mode 0: bias ->
+ * bf16, 1: bias+ReLU -> bf16, 2: bias + fp32 residual in place, 3: bias + bf16 addend + fp32 residual in place,
+ * 4: bias + fused argmax only.  ms_out = average milliseconds per launch. */
+int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, float* ms_out);
 /* conv1d k=3 pad 1 over packed rows with zero rows at segment gaps, as three shifted K passes. */
 int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bias, int M, int C, float* out);
 int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
