@@ -282,12 +282,12 @@ class Engine:
         _check(lib().b200pf_engine_set_option(self.h, key.encode(), int(value)))
 
     def profile_read(self, reset=True):
-        names = (C.c_char_p * 8)()
-        ms = (C.c_double * 8)()
-        work = (C.c_double * 8)()
-        n = (C.c_longlong * 8)()
+        names = (C.c_char_p * 16)()
+        ms = (C.c_double * 16)()
+        work = (C.c_double * 16)()
+        n = (C.c_longlong * 16)()
         _check(lib().b200pf_engine_profile_read(self.h, int(reset), names, ms, work, n))
-        return {names[i].decode(): dict(ms=ms[i], work=work[i], launches=int(n[i])) for i in range(8)}
+        return {names[i].decode(): dict(ms=ms[i], work=work[i], launches=int(n[i])) for i in range(16) if names[i]}
 
     @property
     def stream(self):

@@ -419,7 +419,8 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   return B200PF_ERR_INVALID;
 }
 
-static const char* kProfNames[8] = {"frontend", "layernorm", "gemm_tcgen05", "attention_tcgen05", "fsmn", "cif", "argmax", "other"};
+static const char* kProfNames[16] = {"frontend", "layernorm", "gemm_other", "attention_tcgen05", "fsmn", "cif", "argmax", "other",
+                                      "gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2", "gemm_dec", "gemm_vocab", "", ""};
 
 int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches) {
   if (!e) { set_error("null engine"); return B200PF_ERR_INVALID; }
@@ -431,7 +432,7 @@ int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, 
     e->prof_pool.push_back(r.a); e->prof_pool.push_back(r.b);
   }
   e->prof_recs.clear();
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     if (names) names[i] = kProfNames[i];
     if (ms) ms[i] = e->prof_ms[i];
     if (work) work[i] = e->prof_work[i];
@@ -598,12 +599,12 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   for (int i = 0; i < S; ++i) sumT2 += (double)b->h_seg_T[i] * b->h_seg_T[i];
 
   auto gemm = [&](const __nv_bfloat16* A, int lda, int64_t rows_a, const Linear& W, int Mrows, const int* m_dev,
-                  const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0) {
+                  const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0, int cat = 2) {
     GemmProblem p;
     p.A = A; p.lda = lda; p.rows_a = rows_a; p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
     p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0;
     ++nl;
-    const int h = prof_begin(2, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
+    const int h = prof_begin(cat, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
     const int rc = gemm_bf16_tcgen05(p, ep, sms, s);
     prof_end(h);
     return rc;
@@ -626,18 +627,18 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     const float* xin = l == 0 ? e->x0 : e->x;
     LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
     { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
-      CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep), "gemm qkv"); }
+      CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
     LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, s), "fsmn");
     LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
       if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
       ep.out_f32 = e->x; ep.ld_out_f32 = D;
-      CKL(gemm(e->att, D, M, w.out, M, nullptr, ep), "gemm out"); }
+      CKL(gemm(e->att, D, M, w.out, M, nullptr, ep, 0, 0, 9), "gemm out"); }
     LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln2");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
-      CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep), "gemm ffn1"); }
+      CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep, 0, 0, 10), "gemm ffn1"); }
     { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
-      CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep), "gemm ffn2"); }
+      CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep, 0, 0, 11), "gemm ffn2"); }
   }
   LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
                              b->d_row_info, 1, s), "after_norm");
@@ -666,10 +667,10 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   auto dec_ffn = [&](const DecLayer& w) -> int {
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
-      CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep), "dec gemm w1"); }
+      CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w1"); }
     LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s), "dec ln ff");
     { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
-      CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep), "dec gemm w2"); }
+      CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
     return 0;
   };
   for (int l = 0; l < c.n_dec; ++l) {
@@ -679,19 +680,19 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s), "dec fsmn");
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln3");
     { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
-      CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep), "dec gemm q"); }
+      CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }
     { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
-      CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep), "dec gemm kv"); }
+      CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep, 0, 0, 12), "dec gemm kv"); }
     LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
-      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep), "dec gemm out"); }
+      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "dec gemm out"); }
   }
   { int rc = dec_ffn(e->dec3); if (rc) return rc; }
   LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
   CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
   { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
     if (e->taps) { ep.out_f32 = e->tap_logits; ep.ld_out_f32 = c.vocab; }
-    CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep), "gemm vocab"); }
+    CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep, 0, 0, 13), "gemm vocab"); }
   LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
   return 0;
 }

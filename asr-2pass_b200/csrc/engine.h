@@ -98,8 +98,8 @@ struct b200pf_engine {
   struct ProfRec { cudaEvent_t a, b; int cat; double work; };
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
-  double prof_ms[8] = {0}, prof_work[8] = {0};
-  long long prof_launches[8] = {0};
+  double prof_ms[16] = {0}, prof_work[16] = {0};
+  long long prof_launches[16] = {0};
   // taps
   int taps = 0;
   float* tap_feats = nullptr;   // [R, 560]

@@ -165,6 +165,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < M;
       float best_v = -INFINITY;
       int best_i = -1;
+      {  // pull the NEXT tile's addends towards L2 while this tile is processed
+        const int nt = tile + n_pairs;
+        if (nt < total && (e.res_f32 || e.add_bf16)) {
+          const int nrow = (nt / n_tiles) * 2 * BM + (int)cta * BM + quarter * 32 + lane;
+          const int ncol = (nt % n_tiles) * BN + half * 128;
+          if (nrow < M && ncol < N) {
+            if (e.res_f32) {
+              const char* q = reinterpret_cast<const char*>(e.res_f32 + (size_t)nrow * e.ld_res + ncol);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * i));
+            }
+            if (e.add_bf16) {
+              const char* q = reinterpret_cast<const char*>(e.add_bf16 + (size_t)nrow * e.ld_add + ncol);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * i));
+            }
+          }
+        }
+      }
       if (e.bias) {  // this warp's 128 bias values: one coalesced load per tile, read back as smem broadcasts
         const int bc = n_blk * BN + half * 128 + lane * 4;
         uint4 b = make_uint4(0, 0, 0, 0);
@@ -183,6 +202,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // reads its own row back.  The TMEM load is in flight meanwhile.
         float4 res[8];
         uint4 add[4];
+        if (e.add_bf16) {
+          // each thread reads its own row's 64 bytes (two full sectors); issued first so that it is in flight
+          // together with the residual loads below (one memory latency per chunk instead of two)
+          const __nv_bfloat16* ap = e.add_bf16 + (size_t)row * e.ld_add + col0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            add[g] = (row_ok && col0 + 8 * g < N) ? ldg128_nc(ap + 8 * g) : make_uint4(0, 0, 0, 0);
+        }
         if (e.res_f32) {
           float4 t[8];
 #pragma unroll
@@ -198,23 +225,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           warp_sync_smem();
 #pragma unroll
           for (int g = 0; g < 8; ++g) res[g] = lds128f(my_row + g * 16);
-          warp_sync_smem();
-        }
-        if (e.add_bf16) {
-          uint4 t[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
-            t[i] = make_uint4(0, 0, 0, 0);
-            if (row_base + rr < M && col0 + 8 * ch < N)
-              t[i] = ldg128_nc(e.add_bf16 + (size_t)(row_base + rr) * e.ld_add + col0 + 8 * ch);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            sts128(scr + ((lane >> 2) + 8 * i) * SCR_STRIDE + (lane & 3) * 16, t[i].x, t[i].y, t[i].z, t[i].w);
-          warp_sync_smem();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) add[g] = lds128(my_row + g * 16);
           warp_sync_smem();
         }
         tmem_ld_wait();

@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--segments", type=int, default=1024)
-    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "24576")))
+    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "65536")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
@@ -321,13 +321,14 @@ def main():
     value = world * audio_s / (ms_resident / 1e3)
     e2e_v = world * audio_s / (ms_e2e / 1e3)
     step_tf = flops / (ms_resident / 1e3) / 1e12
-    g = prof["gemm_tcgen05"]
+    gk = [k for k in prof if k.startswith("gemm_")]
+    g = dict(ms=sum(prof[k]["ms"] for k in gk), work=sum(prof[k]["work"] for k in gk), launches=sum(prof[k]["launches"] for k in gk))
     gemm_tf = g["work"] / max(g["ms"], 1e-9) / 1e9 if g["launches"] else 0.0
     prof_total = sum(v["ms"] for v in prof.values()) or 1.0
     kernels = {k: dict(ms_per_step=v["ms"] / args.steps, share=v["ms"] / prof_total, launches_per_step=v["launches"] // args.steps,
-                       achieved=(v["work"] / max(v["ms"], 1e-9) / 1e9 if k in ("gemm_tcgen05", "attention_tcgen05")
+                       achieved=(v["work"] / max(v["ms"], 1e-9) / 1e9 if (k.startswith("gemm_") or k == "attention_tcgen05")
                                  else v["work"] / max(v["ms"], 1e-9) / 1e6),
-                       unit=("TFLOP/s" if k in ("gemm_tcgen05", "attention_tcgen05") else "GB/s"))
+                       unit=("TFLOP/s" if (k.startswith("gemm_") or k == "attention_tcgen05") else "GB/s"))
                for k, v in prof.items() if v["launches"]}
     out = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -338,7 +339,7 @@ def main():
                     tokens=n_tok, sharding="each rank runs the full per-GPU workload (weak scaling), no collective"),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
         gpu_launches=int(launches * args.steps),
-        roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=gemm_tf, peak=tflops_peak, unit="TFLOP/s",
+        roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all %d GEMM launches of a step)" % (g["launches"] // args.steps), achieved=gemm_tf, peak=tflops_peak, unit="TFLOP/s",
                       frac=gemm_tf / tflops_peak, traffic=None,
                       note="sum of 2*M*N*K over the GEMM launches of a step / their CUDA-event time, vs %s sustained bf16 peak; "
                            "whole step: %.1f TFLOP/s (%.3f of peak)" % (which, step_tf, step_tf / tflops_peak)),

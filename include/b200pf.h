@@ -78,10 +78,11 @@ const char* b200pf_engine_lang(const b200pf_engine* e);
 /* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 /* Option "profile" = 1 brackets every launch of b200pf_batch_run with CUDA events on the launching stream.
- * b200pf_engine_profile_read synchronises, folds the finished brackets into 8 categories (names[i]:
- * frontend, layernorm, gemm_tcgen05, attention_tcgen05, fsmn, cif, argmax, other) and returns accumulated
+ * b200pf_engine_profile_read synchronises, folds the finished brackets into 16 categories (names[i]:
+ * frontend, layernorm, gemm_other, attention_tcgen05, fsmn, cif, argmax, other, gemm_qkv, gemm_out, gemm_ffn1,
+ * gemm_ffn2, gemm_dec, gemm_vocab, two unused) and returns accumulated
  * milliseconds, algorithmic work (FLOPs for the two tensor-core categories, bytes for the rest) and launch
- * counts; `reset` clears the accumulators.  Arrays have 8 entries. */
+ * counts; `reset` clears the accumulators.  Arrays have 16 entries. */
 int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches);
 /* The CUDA stream (cudaStream_t) the engine enqueues on when `stream` arguments are NULL. */
 void* b200pf_engine_stream(b200pf_engine* e);
