@@ -285,6 +285,9 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
   e->device = device;
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
   CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  CK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking), "cudaStreamCreate");
+  CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+  CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming), "cudaEventCreate");
 
   // ---- weights ----
   size_t wbytes = 64 << 20;
@@ -381,6 +384,10 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   cudaFree(e->tap_feats);
   cudaFree(e->tap_emb);
   cudaFree(e->tap_logits);
+  cudaStreamSynchronize(e->side);
+  cudaStreamDestroy(e->side);
+  cudaEventDestroy(e->ev_fork);
+  cudaEventDestroy(e->ev_join);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -409,6 +416,10 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
       CK(cudaMalloc((void**)&e->tap_logits, R * (size_t)e->cfg.vocab * 4), "cudaMalloc(tap logits)");
     }
     e->taps = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(key, "overlap") == 0) {
+    e->overlap = value ? 1 : 0;
     return 0;
   }
   if (strcmp(key, "profile") == 0) {
@@ -628,8 +639,18 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
     { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
       CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
-    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, s), "fsmn");
+    // The FSMN memory block and the attention both depend only on the QKV projection: run them concurrently
+    // (CUDA-core FMA work next to tensor-core / MUFU work) and join before the output projection.
+    const bool fork = e->overlap && !e->profile;
+    cudaStream_t fs = fork ? e->side : s;
+    if (fork) {
+      CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
+      CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
+    }
+    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs), "fsmn");
+    if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
     LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
+    if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
       if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
       ep.out_f32 = e->x; ep.ld_out_f32 = D;

@@ -60,6 +60,9 @@ struct b200pf_engine {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;          // FSMN memory block runs here, concurrently with the attention kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int overlap = 1;
   std::string lang = "zh-cn";
   std::vector<std::string> tokens;
   std::mutex mu;  // one forward at a time per engine (the workspace is shared)

@@ -75,7 +75,8 @@ int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out);
 int b200pf_engine_vocab_size(const b200pf_engine* e);
 const char* b200pf_engine_token(const b200pf_engine* e, int id);
 const char* b200pf_engine_lang(const b200pf_engine* e);
-/* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap. */
+/* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (default 1) runs the
+ * FSMN memory block on a side stream concurrently with the attention kernel; "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 /* Option "profile" = 1 brackets every launch of b200pf_batch_run with CUDA events on the launching stream.
  * b200pf_engine_profile_read synchronises, folds the finished brackets into 16 categories (names[i]:
