@@ -267,228 +267,6 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-pass variant for sequences of at most 320 keys (19.2 s segments): one CTA per (segment, head) keeps
-// ALL of K and V in shared memory (loaded once, not once per query tile and pass) and the full score row
-// S = Q K^T (<= 320 fp32 columns) in TMEM, so the softmax sees its exact row maximum in one pass and the
-// dependent TMA -> MMA -> softmax round trips per key block of the two-pass kernel disappear.  The CTA
-// walks the segment's query tiles; longer sequences use attn_tcgen05_kernel above.
-// ---------------------------------------------------------------------------------------------
-constexpr int SH_MAXB = 5;                                  // key blocks of 64
-constexpr int SH_SMEM = Q_BYTES + 2 * SH_MAXB * K_BYTES + 2 * P_BYTES + 256;
-constexpr int SH_TMEM = 512;                                // S: 320 columns, O: 128 columns at 384
-
-__global__ void __launch_bounds__(kThreads, 1)
-attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + Q_BYTES;
-  uint8_t* sV = sK + SH_MAXB * K_BYTES;
-  uint8_t* sP = sV + SH_MAXB * K_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* q_empty = bars + 1;       // 1
-  uint64_t* k_full = bars + 2;        // 5
-  uint64_t* v_full = bars + 7;        // 5
-  uint64_t* s_full = bars + 12;       // 1
-  uint64_t* s_free = bars + 13;       // 1 (4 warps)
-  uint64_t* p_full = bars + 14;       // 2 (4 warps)
-  uint64_t* p_empty = bars + 16;      // 2
-  uint64_t* o_full = bars + 18;       // 1
-  uint64_t* o_free = bars + 19;       // 1 (4 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 1 && lane == 0) {
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    for (int i = 0; i < SH_MAXB; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_free, 4);
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
-    mbar_init(o_full, 1); mbar_init(o_free, 4);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
-    __syncwarp();
-    tmem_alloc(tmem_slot, SH_TMEM);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 384;
-
-  pdl_wait();
-  pdl_launch_dependents();
-  const int seg = a.work[blockIdx.x].seg;
-  const int h = blockIdx.y;
-  const int Tq = a.q_len[seg];
-  const int Tk = a.kv_len[seg];
-  const int nq = (Tq + BQ - 1) / BQ;
-  const int nbk = (Tk + BKV - 1) / BKV;   // <= SH_MAXB by construction of the work list
-  const int q_row0 = a.q_row_off[seg];
-  const int kv_row = a.kv_row_off[seg];
-
-  if (nq > 0 && nbk > 0 && nbk <= SH_MAXB) {
-    if (warp == 0) {
-      if (lane == 0) {
-        // everything the CTA will ever need from K and V, issued at once
-        for (int j = 0; j < nbk; ++j) {
-          mbar_arrive_expect_tx(&k_full[j], K_BYTES);
-          tma_load_2d(sK + j * K_BYTES, &tmKV, &k_full[j], a.k_col0 + h * HD, kv_row + j * BKV);
-          tma_load_2d(sK + j * K_BYTES + K_BYTES / 2, &tmKV, &k_full[j], a.k_col0 + h * HD + 64, kv_row + j * BKV);
-          if (j == 0) {
-            mbar_arrive_expect_tx(q_full, Q_BYTES);
-            tma_load_2d(sQ, &tmQ, q_full, a.q_col0 + h * HD, q_row0);
-            tma_load_2d(sQ + Q_BYTES / 2, &tmQ, q_full, a.q_col0 + h * HD + 64, q_row0);
-          }
-        }
-        for (int j = 0; j < nbk; ++j) {
-          mbar_arrive_expect_tx(&v_full[j], K_BYTES);
-          tma_load_2d(sV + j * K_BYTES, &tmKV, &v_full[j], a.v_col0 + h * HD, kv_row + j * BKV);
-          tma_load_2d(sV + j * K_BYTES + K_BYTES / 2, &tmKV, &v_full[j], a.v_col0 + h * HD + 64, kv_row + j * BKV);
-        }
-        for (int qi = 1; qi < nq; ++qi) {
-          mbar_wait(q_empty, (qi & 1) ^ 1);   // the S MMAs of tile qi-1 have consumed Q
-          mbar_arrive_expect_tx(q_full, Q_BYTES);
-          tma_load_2d(sQ, &tmQ, q_full, a.q_col0 + h * HD, q_row0 + qi * BQ);
-          tma_load_2d(sQ + Q_BYTES / 2, &tmQ, q_full, a.q_col0 + h * HD + 64, q_row0 + qi * BQ);
-        }
-      }
-      __syncwarp();
-    } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);
-        const uint32_t q_addr = smem_u32(sQ);
-        for (int qi = 0; qi < nq; ++qi) {
-          mbar_wait(q_full, qi & 1);
-          mbar_wait(s_free, (qi & 1) ^ 1);
-          tc_fence_after();
-          for (int j = 0; j < nbk; ++j) {
-            mbar_wait(&k_full[j], 0);
-            tc_fence_after();
-            const uint32_t k_addr = smem_u32(sK + j * K_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < HD / 16; ++ks) {
-              const uint64_t da = umma_desc_sw128(q_addr + (ks >> 2) * (Q_BYTES / 2)) + 2 * (ks & 3);
-              const uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (K_BYTES / 2)) + 2 * (ks & 3);
-              umma_bf16(tmem_base + j * BKV, da, db, idesc_s, ks != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(s_full);
-          umma_commit(q_empty);
-          mbar_wait(o_free, (qi & 1) ^ 1);   // the epilogue of tile qi-1 has read O
-          for (int j = 0; j < nbk; ++j) {
-            const int g = qi * nbk + j, pb = g & 1;
-            mbar_wait(&v_full[j], 0);
-            mbar_wait(&p_full[pb], (g >> 1) & 1);
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP + pb * P_BYTES);
-            const uint32_t v_addr = smem_u32(sV + j * K_BYTES);
-#pragma unroll
-            for (int ks = 0; ks < BKV / 16; ++ks) {
-              const uint64_t da = umma_desc_sw128(p_addr) + 2 * ks;
-              const uint64_t db = umma_desc_sw128_mn(v_addr + ks * 2048, K_BYTES / 2);
-              umma_bf16(tmem_o, da, db, idesc_pv, (j | ks) != 0 ? 1u : 0u);
-            }
-            umma_commit(&p_empty[pb]);
-          }
-          umma_commit(o_full);
-        }
-      }
-      __syncwarp();
-    } else {
-      const int quarter = warp & 3;
-      const int row = quarter * 32 + lane;
-      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      uint32_t r[32];
-      for (int qi = 0; qi < nq; ++qi) {
-        mbar_wait(s_full, qi & 1);
-        tc_fence_after();
-        // exact row maximum over the whole score row (TMEM is read twice; it is cheap)
-        float m = -INFINITY;
-        for (int j = 0; j < nbk; ++j) {
-          const int nvalid = Tk - j * BKV;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            tmem_ld_32x32(tmem_base + lane_addr + j * BKV + half * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (half * 32 + c < nvalid) m = fmaxf(m, __uint_as_float(r[c]));
-          }
-        }
-        const float mc = m * a.scale_log2e;
-        float l = 0.f;
-        for (int j = 0; j < nbk; ++j) {
-          const int g = qi * nbk + j, pb = g & 1;
-          const int nvalid = Tk - j * BKV;
-          uint32_t pk[32];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            tmem_ld_32x32(tmem_base + lane_addr + j * BKV + half * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const int k0 = half * 32 + c;
-              const float p0 = (k0 < nvalid) ? ex2(fmaf(__uint_as_float(r[c]), a.scale_log2e, -mc)) : 0.f;
-              const float p1 = (k0 + 1 < nvalid) ? ex2(fmaf(__uint_as_float(r[c + 1]), a.scale_log2e, -mc)) : 0.f;
-              l += p0 + p1;
-              pk[half * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
-            }
-          }
-          mbar_wait(&p_empty[pb], ((g >> 1) & 1) ^ 1);
-          const uint32_t prow = smem_u32(sP + pb * P_BYTES + row * 128);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            sts128(prow + ((jj ^ (row & 7)) << 4), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[pb]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);   // S may be overwritten by the next query tile
-        // epilogue
-        mbar_wait(o_full, qi & 1);
-        tc_fence_after();
-        const float inv = 1.f / l;
-        const bool row_ok = (qi * BQ + row) < Tq;
-        __nv_bfloat16* orow = a.out + (size_t)(q_row0 + qi * BQ + row) * a.ldo + h * HD;
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          tmem_ld_32x32(tmem_o + lane_addr + c4 * 32, r);
-          tmem_ld_wait();
-          if (c4 == 3) {  // all of O is in registers: the next tile's P V may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(o_free);
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
-              o.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
-              o.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
-              o.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
-              stg128(orow + c4 * 32 + g * 8, o);
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, SH_TMEM);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check (test-only): one warp per query row, online softmax in fp32.
 // ---------------------------------------------------------------------------------------------
 __global__ void attn_check_kernel(AArgs a, const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kv, int ldkv,
@@ -536,12 +314,10 @@ AArgs make_args(const AttnProblem& p) {
 }  // namespace
 
 int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
-  if (p.n_work <= 0 && p.n_short <= 0) return 0;
+  if (p.n_work <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err = cudaFuncSetAttribute(attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(attn_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM);
     if (err != cudaSuccess) return (int)err;
     attr_set = true;
   }
@@ -551,13 +327,6 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   rc = make_tmap_bf16_sw128(&tmKV, p.kv, (uint64_t)p.kv_rows, (uint64_t)p.ldkv, (uint64_t)p.ldkv, BKV);
   if (rc) return rc;
   AArgs a = make_args(p);
-  if (p.n_short > 0) {  // segments with <= 320 keys: single-pass kernel, one CTA per (segment, head)
-    AArgs b = a;
-    b.work = p.work_short;
-    rc = launch_kernel(attn_short_kernel, dim3(p.n_short, p.n_heads), dim3(kThreads), SH_SMEM, stream, tmQ, tmKV, b);
-    if (rc) return rc;
-  }
-  if (p.n_work <= 0) return 0;
   dim3 grid(p.n_work, p.n_heads);
   return launch_kernel(attn_tcgen05_kernel, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
 }

@@ -28,15 +28,11 @@ struct AttnProblem {
   const int* q_len = nullptr;         // [n_seg] query rows per segment            (device)
   const int* kv_row_off = nullptr;    // [n_seg] first key row                     (device)
   const int* kv_len = nullptr;        // [n_seg] keys per segment                  (device)
-  const AttnWork* work = nullptr;     // [n_work]  (segment, query tile) items for the two-pass kernel   (device)
+  const AttnWork* work = nullptr;     // [n_work]                                  (device)
   int n_work = 0;
-  const AttnWork* work_short = nullptr;  // [n_short] segments with <= kAttnShortMaxKeys keys (q0 unused)  (device)
-  int n_short = 0;
   int n_heads = 4;
   float scale = 0.08838834764831845f;  // 128^-1/2
 };
-
-constexpr int kAttnShortMaxKeys = 320;  // 5 key blocks of 64: K and V of the whole segment stay in shared memory
 
 int attention_tcgen05(const AttnProblem& p, cudaStream_t stream);
 

@@ -467,7 +467,7 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 63) & ~size_t(63); return o; };
   const size_t o_sample = carve((S + 1) * 8), o_fb = carve((S + 1) * 4), o_row = carve((S + 1) * 4), o_T = carve(S * 4),
-               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8), o_short = carve(S * 8);
+               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8);
   b->meta_bytes = off;
   CK(cudaMallocHost((void**)&b->h_meta, off), "cudaMallocHost(meta)");
   CK(cudaMalloc((void**)&b->d_meta, off), "cudaMalloc(meta)");
@@ -478,7 +478,6 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   b->h_row_seg = (int*)(b->h_meta + o_rseg);          b->d_row_seg = (const int*)(b->d_meta + o_rseg);
   b->h_row_info = (int2*)(b->h_meta + o_rinfo);       b->d_row_info = (const int2*)(b->d_meta + o_rinfo);
   b->h_work = (AttnWork*)(b->h_meta + o_work);        b->d_work = (const AttnWork*)(b->d_meta + o_work);
-  b->h_work_short = (AttnWork*)(b->h_meta + o_short); b->d_work_short = (const AttnWork*)(b->d_meta + o_short);
   CK(cudaMalloc((void**)&b->d_n_tok, (2 * S + 2 + 2 * R + 16) * 4), "cudaMalloc(results)");
   b->d_tok_off = b->d_n_tok + S;
   b->d_tok_total = b->d_tok_off + S + 1;
@@ -510,7 +509,7 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
   b->n_seg_in = n_in;
   b->dev_of_in.assign(n_in, -1);
   b->T_in.assign(n_in, 0);
-  int ns = 0, rows = 0, frames = 0, nwork = 0, nshort = 0;
+  int ns = 0, rows = 0, frames = 0, nwork = 0;
   for (int i = 0; i < n_in; ++i) {
     const int nfb = num_fbank_frames(n_samples[i]);
     const int T = nfb > 0 ? (nfb + 5) / 6 : 0;
@@ -527,11 +526,7 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
     for (int t = 0; t < T; ++t) { b->h_row_seg[rows + t] = ns; b->h_row_info[rows + t] = make_int2(t, T); }
     b->h_row_seg[rows + T] = -1;
     b->h_row_info[rows + T] = make_int2(-1, T);
-    if (T <= kAttnShortMaxKeys) {  // whole K/V fits shared memory: single-pass kernel, one item per segment
-      b->h_work_short[nshort].seg = ns; b->h_work_short[nshort].q0 = 0; ++nshort;
-    } else {
-      for (int q0 = 0; q0 < T; q0 += 128) { b->h_work[nwork].seg = ns; b->h_work[nwork].q0 = q0; ++nwork; }
-    }
+    for (int q0 = 0; q0 < T; q0 += 128) { b->h_work[nwork].seg = ns; b->h_work[nwork].q0 = q0; ++nwork; }
     rows += T + 1;
     frames += nfb;
     ++ns;
@@ -539,7 +534,7 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
   b->h_sample_off[ns] = 0;
   b->h_fb_off[ns] = frames;
   b->h_row_off[ns] = rows;
-  b->n_seg = ns; b->rows = rows; b->n_frames = frames; b->n_work = nwork; b->n_short = nshort;
+  b->n_seg = ns; b->rows = rows; b->n_frames = frames; b->n_work = nwork;
   b->collected = false;
   return 0;
 }
@@ -637,7 +632,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   ap.kv = e->qkv; ap.kv_rows = M; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
   ap.out = e->att; ap.ldo = D;
   ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
-  ap.work = b->d_work; ap.n_work = b->n_work; ap.work_short = b->d_work_short; ap.n_short = b->n_short; ap.n_heads = c.n_heads;
+  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads;
   for (int l = 0; l < c.n_enc; ++l) {
     const EncLayer& w = e->enc[l];
     const float* xin = l == 0 ? e->x0 : e->x;
@@ -689,7 +684,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
   cp.out = e->att; cp.ldo = D;
   cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
-  cp.work = b->d_work; cp.n_work = b->n_work; cp.work_short = b->d_work_short; cp.n_short = b->n_short; cp.n_heads = c.n_heads;
+  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads;
   auto dec_ffn = [&](const DecLayer& w) -> int {
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;

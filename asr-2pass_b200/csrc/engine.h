@@ -127,7 +127,6 @@ struct b200pf_batch {
   int* h_row_seg = nullptr;        const int* d_row_seg = nullptr;
   int2* h_row_info = nullptr;      const int2* d_row_info = nullptr;
   pf::AttnWork* h_work = nullptr;  const pf::AttnWork* d_work = nullptr;
-  pf::AttnWork* h_work_short = nullptr;  const pf::AttnWork* d_work_short = nullptr;
   // device results
   int* d_n_tok = nullptr;     // [S]
   int* d_tok_off = nullptr;   // [S+1]
@@ -140,7 +139,7 @@ struct b200pf_batch {
   int n_seg = 0;                // segments on the device (T > 0)
   std::vector<int> dev_of_in;   // caller index -> device segment or -1
   std::vector<int> T_in;        // caller index -> T
-  int rows = 0, n_frames = 0, n_work = 0, n_short = 0;
+  int rows = 0, n_frames = 0, n_work = 0;
   int64_t launches = 0;
   double flops = 0.0;
   cudaEvent_t staged = nullptr;

@@ -189,23 +189,17 @@ int b200pf_op_attention(int device, const float* q, const float* k, const float*
   RC(dOutB.alloc((size_t)q_rows * D * 2)); RC(dOut.alloc((size_t)q_rows * D * 4));
   RC(check_cuda(cudaMemset(dOutB.p, 0, (size_t)q_rows * D * 2), "memset"));
   RC(up_raw(q_off, n_seg, &dqo)); RC(up_raw(q_len, n_seg, &dql)); RC(up_raw(kv_off, n_seg, &dko)); RC(up_raw(kv_len, n_seg, &dkl));
-  // impl 0: product dispatch (single-pass kernel for <= 320 keys, two-pass otherwise); 2: two-pass for everything
-  std::vector<AttnWork> work, work_short;
-  for (int s = 0; s < n_seg; ++s) {
-    if (impl == 0 && kv_len[s] <= kAttnShortMaxKeys) { work_short.push_back(AttnWork{s, 0}); continue; }
+  std::vector<AttnWork> work;
+  for (int s = 0; s < n_seg; ++s)
     for (int q0 = 0; q0 < q_len[s]; q0 += 128) work.push_back(AttnWork{s, q0});
-  }
-  DevBuf dShort;
   RC(up_raw(work.data(), work.size(), &dWork));
-  RC(up_raw(work_short.data(), work_short.size(), &dShort));
   AttnProblem p;
   p.q = dQ.as<__nv_bfloat16>(); p.q_rows = q_rows; p.ldq = D; p.q_col0 = 0;
   p.kv = dKV.as<__nv_bfloat16>(); p.kv_rows = kv_rows; p.ldkv = 2 * D; p.k_col0 = 0; p.v_col0 = D;
   p.out = dOutB.as<__nv_bfloat16>(); p.ldo = D;
   p.q_row_off = dqo.as<int>(); p.q_len = dql.as<int>(); p.kv_row_off = dko.as<int>(); p.kv_len = dkl.as<int>();
   p.work = dWork.as<AttnWork>(); p.n_work = (int)work.size(); p.n_heads = n_heads;
-  p.work_short = dShort.as<AttnWork>(); p.n_short = (int)work_short.size();
-  int rc = impl != 1 ? attention_tcgen05(p, 0) : attention_check_kernel(p, 0);
+  int rc = impl == 0 ? attention_tcgen05(p, 0) : attention_check_kernel(p, 0);
   if (rc) return check_cuda((cudaError_t)rc, "attention launch");
   bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)q_rows * D);
   RC(sync_ok("op_attention"));

@@ -137,8 +137,7 @@ int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bi
 int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
                         int in_bf16, float* out_f32, float* out_bf16_as_f32);
 /* q [sum Tq,H*128], k,v [sum Tk,H*128]; segment s owns rows q_off[s].. and kv_off[s]..; impl 0 = tcgen05
- * kernels as the product dispatches them (single-pass for <= 320 keys, two-pass otherwise), 1 = CUDA-core cross-check,
- * 2 = two-pass tcgen05 kernel for every segment. */
+ * kernel (product), 1 = CUDA-core cross-check. */
 int b200pf_op_attention(int device, const float* q, const float* k, const float* v, const int32_t* q_off,
                         const int32_t* q_len, const int32_t* kv_off, const int32_t* kv_len, int n_seg, int n_heads,
                         int64_t q_rows, int64_t kv_rows, int impl, float* out);
