@@ -155,6 +155,16 @@ def make_batches(lens, max_rows, max_segments, capi):
 
 
 def main():
+    # Exactly ONE line may reach stdout.  Libraries (NCCL's version banner, torchrun notices) print there too,
+    # so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -190,10 +200,10 @@ def main():
         v = float(np.mean([c["value"] for c in vals]))
         cb = vals[-1]
         cb["value"] = v
-        print(json.dumps(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                              ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                              data="synthetic", impl="reference", config=dict(workload=workload), cpu_baseline=cb,
-                              e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        emit(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                  ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                  data="synthetic", impl="reference", config=dict(workload=workload), cpu_baseline=cb,
+                  e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)))
         return
 
     pcm, offs = synth.make_segments(args.segments)
@@ -348,7 +358,7 @@ def main():
     )
     if cb is not None:
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
