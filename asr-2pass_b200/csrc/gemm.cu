@@ -194,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int col0 = n_blk * BN + half * 128 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
+        if (col0 >= N || e.dbg == 2) break;  // warp-uniform
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128 + c * 32);
         tmem_ld_32x32(taddr, r);
@@ -270,7 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 8; ++i) {
             const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
             const float4 o = lds128f(scr + rr * SCR_STRIDE + ch * 16);
-            if (row_base + rr < M && col0 + 4 * ch < N)
+            if (row_base + rr < M && col0 + 4 * ch < N && e.dbg == 0)
               stg128f(e.out_f32 + (size_t)(row_base + rr) * e.ld_out_f32 + col0 + 4 * ch, o);
           }
           warp_sync_smem();
@@ -285,7 +285,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
             const uint4 o = lds128(scr + rr * SCR_STRIDE + ch * 16);
-            if (row_base + rr < M && col0 + 8 * ch < N)
+            if (row_base + rr < M && col0 + 8 * ch < N && e.dbg == 0)
               stg128(e.out_bf16 + (size_t)(row_base + rr) * e.ld_out_bf16 + col0 + 8 * ch, o);
           }
           warp_sync_smem();

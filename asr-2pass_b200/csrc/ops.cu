@@ -116,6 +116,7 @@ int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, f
   if (mode == 2 || mode == 3) { e.res_f32 = dX.as<float>(); e.ld_res = N; e.out_f32 = dX.as<float>(); e.ld_out_f32 = N; }
   if (mode == 3) { e.add_bf16 = dAdd.as<__nv_bfloat16>(); e.ld_add = N; }
   if (mode == 4) e.argmax = dAm.as<unsigned long long>();
+  if (const char* d = getenv("B200PF_GEMM_DBG")) e.dbg = atoi(d);
   const int sms = sm_count();
   for (int i = 0; i < 3; ++i) { int rc = gemm_bf16_tcgen05(p, e, sms, 0); if (rc) return check_cuda((cudaError_t)rc, "gemm launch"); }
   cudaEvent_t a, b;
