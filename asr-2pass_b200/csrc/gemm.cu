@@ -39,6 +39,9 @@ struct KArgs {
   GemmEpilogue e;
 };
 
+// FAST = epilogue is bias (+ReLU) -> bf16 only (QKV, FFN1, decoder q / kv projections): TMEM loads are double
+// buffered in registers and each thread stores its own row segment directly (64 contiguous bytes per chunk).
+template <bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -156,6 +159,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t sbias = smem_u32(sBias + ew * BIAS_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (FAST) {
+      for (int tile = pair; tile < total; tile += n_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const int row = m_blk * 2 * BM + (int)cta * BM + quarter * 32 + lane;
+        const bool row_ok = row < M;
+        const int ncol0 = n_blk * BN + half * 128;
+        if (e.bias) {
+          const int bc = ncol0 + lane * 4;
+          uint4 b = make_uint4(0, 0, 0, 0);
+          if (bc < N) b = ldg128_nc(e.bias + bc);
+          sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          warp_sync_smem();
+        }
+        int nch = (N - ncol0 + 31) / 32;   // valid 32-column chunks of this warp's half (warp-uniform)
+        nch = nch < 0 ? 0 : (nch > 4 ? 4 : nch);
+        if (e.dbg == 2) nch = 0;
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        uint32_t ra[32], rb[32];
+        if (nch > 0) tmem_ld_32x32(tbase, ra);
+        __nv_bfloat16* orow = e.out_bf16 + (size_t)row * e.ld_out_bf16 + ncol0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {
+            tmem_ld_wait();
+            if (c + 1 < nch) {  // next chunk's TMEM load is in flight while this one is processed
+              if (c & 1) tmem_ld_32x32(tbase + (c + 1) * 32, ra); else tmem_ld_32x32(tbase + (c + 1) * 32, rb);
+            }
+            const uint32_t (&r)[32] = (c & 1) ? rb : ra;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[8 * g + k]);
+              if (e.bias) {
+                const float4 b0 = lds128f(sbias + (c * 32 + 8 * g) * 4);
+                const float4 b1 = lds128f(sbias + (c * 32 + 8 * g + 4) * 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (e.relu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+              }
+              if (row_ok && ncol0 + c * 32 + 8 * g < N && e.dbg == 0)
+                stg128(orow + c * 32 + 8 * g, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    } else
     for (int tile = pair; tile < total; tile += n_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
@@ -349,7 +410,9 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (e.add_bf16 && ((p.N & 7) || (e.ld_add & 7))) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     attr_set = true;
   }
@@ -366,7 +429,9 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
-  return launch_kernel(gemm_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
+  const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2;
+  if (fast) return launch_kernel(gemm_tcgen05_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
+  return launch_kernel(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
 }
 
 }  // namespace pf
