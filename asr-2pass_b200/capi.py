@@ -23,12 +23,13 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("feat_dim", "d_model", "n_heads", "d_ff", "n_enc", "n_dec", "kernel", "vocab", "pred_residual")] + \
                [(n, C.c_float) for n in ("cif_threshold", "tail_threshold", "ln_eps")] + \
-               [(n, C.c_int32) for n in ("sample_rate", "max_rows", "max_segments")]
+               [(n, C.c_int32) for n in ("sample_rate", "max_rows", "max_segments", "timestamp", "contextual")]
 
 
 class Result(C.Structure):
     _fields_ = [("token_counts", c_i32p), ("token_offsets", c_i32p), ("lfr_frames", c_i32p),
-                ("token_ids", c_i32p), ("fire_frames", c_i32p), ("cap_tokens", C.c_int64), ("n_tokens", C.c_int64)]
+                ("token_ids", c_i32p), ("fire_frames", c_i32p), ("cap_tokens", C.c_int64), ("n_tokens", C.c_int64),
+                ("us_alphas", c_f32p), ("us_peaks", c_f32p), ("us_offsets", c_i32p), ("cap_us", C.c_int64)]
 
 
 class B200PFError(RuntimeError):
@@ -51,6 +52,7 @@ EXPORTS = [
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks",
 ]
 
 
@@ -113,7 +115,8 @@ HOST_LIB_PATH = os.path.join(_HERE, "lib", "libfunasr_b200.so")
 _host = None
 HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf_host_detok_text", "b200pf_host_timestamp_text",
                 "b200pf_host_stitch", "b200pf_host_offline_init", "b200pf_host_offline_uninit", "b200pf_host_offline_infer_buffer",
-                "b200pf_host_offline_infer_segments", "b200pf_host_model_forward"]
+                "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
+                "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw"]
 
 
 def host_lib():
@@ -139,6 +142,11 @@ def host_lib():
     H.b200pf_host_offline_infer_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int, c_f32p]
     H.b200pf_host_offline_infer_segments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, c_i64p, c_i64p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_model_forward.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_compile_hotwords.argtypes = [C.c_void_p, C.c_char_p, c_f32p, C.c_int, C.c_int]
+    H.b200pf_host_init_seg_dict.argtypes = [C.c_void_p, C.c_char_p]
+    H.b200pf_host_model_forward_hw.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_offline_infer_buffer_hw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p,
+                                                      C.c_int, C.c_char_p, C.c_int]
     _host = H
     return H
 
@@ -218,16 +226,45 @@ class OfflineHandle:
             raise B200PFError("FunOfflineInferSegmentsB200 returned nullptr")
         return buf.value.decode("utf-8")
 
-    def model_forward(self, segments_f32):
+    def model_forward(self, segments_f32, hw_emb=None):
+        """funasr::Model::Forward(float**, int*, ..., hw_emb, ..., batch_in) -> list of result strings."""
         segs = [np.ascontiguousarray(s, dtype=np.float32) for s in segments_f32]
         n = len(segs)
         ptrs = (c_f32p * n)(*[s.ctypes.data_as(c_f32p) for s in segs])
         lens = np.asarray([len(s) for s in segs], np.int32)
         buf = C.create_string_buffer(1 << 22)
-        r = host_lib().b200pf_host_model_forward(self.h, ptrs, _p(lens, c_i32p), n, buf, len(buf))
+        if hw_emb is None:
+            r = host_lib().b200pf_host_model_forward(self.h, ptrs, _p(lens, c_i32p), n, buf, len(buf))
+        else:
+            hw = np.ascontiguousarray(hw_emb, dtype=np.float32)
+            r = host_lib().b200pf_host_model_forward_hw(self.h, ptrs, _p(lens, c_i32p), n, _p(hw), hw.shape[0],
+                                                        hw.shape[1] if hw.ndim == 2 else 0, buf, len(buf))
         if r < 0:
             raise B200PFError("Model::Forward failed")
         return buf.value.decode("utf-8").split("\n")
+
+    def init_seg_dict(self, path):
+        host_lib().b200pf_host_init_seg_dict(self.h, path.encode())
+
+    def compile_hotwords(self, hotwords, dim=512, cap_rows=4096):
+        """CompileHotwordEmbedding(handle, hotwords) -> float32 [n_rows, dim]."""
+        out = np.zeros((cap_rows, dim), np.float32)
+        n = host_lib().b200pf_host_compile_hotwords(self.h, hotwords.encode("utf-8"), _p(out), cap_rows, dim)
+        if n < 0:
+            raise B200PFError("CompileHotwordEmbedding failed")
+        return out[:n].copy()
+
+    def infer_buffer_hw(self, pcm16, hw_emb, vad_max_len=60000):
+        """FunOfflineInferBuffer with a hotword matrix -> (text, stamp)."""
+        pcm16 = np.ascontiguousarray(pcm16, dtype="<i2")
+        hw = np.ascontiguousarray(hw_emb, dtype=np.float32)
+        t = C.create_string_buffer(1 << 20)
+        st = C.create_string_buffer(1 << 20)
+        n = host_lib().b200pf_host_offline_infer_buffer_hw(self.h, C.c_void_p(pcm16.ctypes.data), pcm16.nbytes, vad_max_len, _p(hw),
+                                                           hw.shape[0], hw.shape[1], t, len(t), st, len(st))
+        if n < 0:
+            raise B200PFError("FunOfflineInferBuffer returned nullptr")
+        return t.value.decode("utf-8"), st.value.decode("utf-8")
 
 
 def _check(rc):
@@ -301,6 +338,14 @@ class Engine:
     def lang(self):
         return lib().b200pf_engine_lang(self.h).decode()
 
+    def hotword_embed(self, ids, lengths):
+        """Embedding + LSTM of the hotword compiler: ids int32 [n, max_len], lengths [n] -> float32 [n, d_model]."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        out = np.zeros((ids.shape[0], self.cfg.d_model), np.float32)
+        _check(lib().b200pf_engine_hotword_embed(self.h, _p(ids, c_i32p), _p(lengths, c_i32p), ids.shape[0], ids.shape[1], _p(out)))
+        return out
+
     def frontend(self, pcm16):
         pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
         nfb = lib().b200pf_num_fbank_frames(len(pcm16))
@@ -358,6 +403,11 @@ class Batch:
         self.n_seg = n
         _check(lib().b200pf_batch_stage_f32(self.h, ptrs, _p(lens, c_i32p), n, C.c_void_p(stream or 0)))
 
+    def set_hotwords(self, hw_emb):
+        """hw_emb float32 [n_hw, d_model] (what Forward receives as hw_emb); call before stage_*."""
+        hw = np.ascontiguousarray(hw_emb, dtype=np.float32)
+        _check(lib().b200pf_batch_set_hotwords(self.h, _p(hw), hw.shape[0], hw.shape[1] if hw.ndim == 2 else 0))
+
     def run(self, stream=None):
         _check(lib().b200pf_batch_run(self.h, C.c_void_p(stream or 0)))
 
@@ -366,9 +416,20 @@ class Batch:
         cap = int(cap_tokens or self.engine.cfg.max_rows)
         out = dict(token_counts=np.zeros(n, np.int32), token_offsets=np.zeros(n + 1, np.int32),
                    lfr_frames=np.zeros(n, np.int32), token_ids=np.zeros(cap, np.int32), fire_frames=np.zeros(cap, np.int32))
+        out["us_offsets"] = np.zeros(n + 1, np.int32)
+        ts = bool(self.engine.cfg.timestamp)
+        cap_us = 3 * int(self.engine.cfg.max_rows) if ts else 0
+        if ts:
+            out["us_alphas"] = np.zeros(cap_us, np.float32)
+            out["us_peaks"] = np.zeros(cap_us, np.float32)
         r = Result(_p(out["token_counts"], c_i32p), _p(out["token_offsets"], c_i32p), _p(out["lfr_frames"], c_i32p),
-                   _p(out["token_ids"], c_i32p), _p(out["fire_frames"], c_i32p), cap, 0)
+                   _p(out["token_ids"], c_i32p), _p(out["fire_frames"], c_i32p), cap, 0,
+                   _p(out.get("us_alphas")), _p(out.get("us_peaks")), _p(out["us_offsets"], c_i32p), cap_us)
         _check(lib().b200pf_batch_collect(self.h, C.byref(r), C.c_void_p(stream or 0)))
+        if ts:
+            nu = int(out["us_offsets"][n])
+            out["us_alphas"] = out["us_alphas"][:nu]
+            out["us_peaks"] = out["us_peaks"][:nu]
         nt = int(r.n_tokens)
         out["token_ids"] = out["token_ids"][:nt]
         out["fire_frames"] = out["fire_frames"][:nt]
@@ -415,6 +476,29 @@ def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=
     _check(lib().b200pf_op_gemm(device, _p(A), _p(W), _p(bias), _p(add), _p(res), M, N, K, int(relu), int(out_bf16),
                                 _p(out), _p(am, c_i32p)))
     return (out, am) if argmax else out
+
+
+def op_lstm(x, seq_off, seq_len, w_ih, w_hh, b_ih, b_hh, bf16_out=False, device=0):
+    """x [rows,512]; weights [n_dir*2048,512] (forward then reverse), biases [n_dir*2048] -> [rows, 512*n_dir]."""
+    x, w_ih, w_hh, b_ih, b_hh = _f32(x), _f32(w_ih), _f32(w_hh), _f32(b_ih), _f32(b_hh)
+    n_dir = w_ih.shape[0] // 2048
+    so = np.ascontiguousarray(seq_off, dtype=np.int32)
+    sl = np.ascontiguousarray(seq_len, dtype=np.int32)
+    out = np.zeros((x.shape[0], 512 * n_dir), np.float32)
+    _check(lib().b200pf_op_lstm(device, _p(x), x.shape[0], _p(so, c_i32p), _p(sl, c_i32p), len(so), n_dir, _p(w_ih), _p(w_hh),
+                                _p(b_ih), _p(b_hh), int(bf16_out), _p(out)))
+    return out
+
+
+def op_us_peaks(alpha2, seq_off, seq_len, n_tok, threshold, device=0):
+    a = _f32(alpha2)
+    so = np.ascontiguousarray(seq_off, dtype=np.int32)
+    sl = np.ascontiguousarray(seq_len, dtype=np.int32)
+    nt = np.ascontiguousarray(n_tok, dtype=np.int32)
+    ua, up = np.zeros_like(a), np.zeros_like(a)
+    _check(lib().b200pf_op_us_peaks(device, _p(a), _p(so, c_i32p), _p(sl, c_i32p), _p(nt, c_i32p), len(so), len(a),
+                                    C.c_float(threshold), _p(ua), _p(up)))
+    return ua, up
 
 
 def op_gemm_bench(M, N, K, mode=0, iters=20, device=0):

@@ -222,6 +222,8 @@ static void fill_config(const WeightFile& wf, int fs, b200pf_config* c) {
   c->cif_threshold = (float)cfgv("cif_threshold", 1.0); c->tail_threshold = (float)cfgv("tail_threshold", 0.45);
   c->ln_eps = (float)cfgv("ln_eps", 1e-12);
   c->sample_rate = fs;
+  c->timestamp = (int)cfgv("timestamp", 0);
+  c->contextual = (int)cfgv("contextual", 0);
 }
 
 int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors) {
@@ -344,10 +346,64 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
     }
     return w;
   };
-  for (int l = 0; l < c.n_dec && L.ok; ++l) e->dec.push_back(load_dec("decoder.decoders." + std::to_string(l), true));
+  // contextual models keep their last attention layer under `decoder.last_decoder` (ContextualParaformerDecoder)
+  for (int l = 0; l < c.n_dec && L.ok; ++l)
+    e->dec.push_back(load_dec(c.contextual && l == c.n_dec - 1 ? std::string("decoder.last_decoder") : "decoder.decoders." + std::to_string(l), true));
   if (L.ok) e->dec3 = load_dec("decoder.decoders3.0", false);
   e->dec_after = L.norm("decoder.after_norm", D);
   e->vocab = L.linear("decoder.output_layer", c.vocab, D);
+  {
+    auto cfgv = [&](const char* k, double dflt) { auto it = wf.cfg.find(k); return it == wf.cfg.end() ? dflt : it->second; };
+    e->us_times = (int)cfgv("us_times", 3);
+    e->smooth2 = (float)cfgv("smooth_factor2", 0.25);
+    e->noise2 = (float)cfgv("noise_threshold2", 0.01);
+  }
+  // sum of the two LSTM bias vectors; W_ih / W_hh of the listed directions stacked
+  auto lstm_in = [&](const std::string& p, const std::vector<std::string>& sfx, Linear* ih, __nv_bfloat16** hh) {
+    const int nd = (int)sfx.size();
+    std::vector<float> wi((size_t)nd * 4 * D * D), wh((size_t)nd * 4 * D * D), bs((size_t)nd * 4 * D);
+    for (int d = 0; d < nd && L.ok; ++d) {
+      auto a = L.get(p + ".weight_ih_l0" + sfx[d], {4 * D, D}), b = L.get(p + ".weight_hh_l0" + sfx[d], {4 * D, D});
+      auto c1 = L.get(p + ".bias_ih_l0" + sfx[d], {4 * D}), c2 = L.get(p + ".bias_hh_l0" + sfx[d], {4 * D});
+      if (!a || !b || !c1 || !c2) return;
+      memcpy(&wi[(size_t)d * 4 * D * D], a->data.data(), (size_t)4 * D * D * 4);
+      memcpy(&wh[(size_t)d * 4 * D * D], b->data.data(), (size_t)4 * D * D * 4);
+      for (int i = 0; i < 4 * D; ++i) bs[(size_t)d * 4 * D + i] = c1->data[i] + c2->data[i];
+    }
+    ih->w = L.up_bf16(wi.data(), wi.size()); ih->b = L.up_f32(bs.data(), bs.size()); ih->out = nd * 4 * D; ih->in = D;
+    *hh = L.up_bf16(wh.data(), wh.size());
+  };
+  if (L.ok && c.timestamp) {
+    if (e->us_times != 3) L.fail("timestamp head: only upsample_times 3 is supported (TIME_RATE, util.cpp:851)");
+    auto w = L.get("predictor.upsample_cnn.weight", {D, D, 3});
+    auto b = L.get("predictor.upsample_cnn.bias", {D});
+    auto ow = L.get("predictor.cif_output2.weight", {1, 2 * D});
+    auto ob = L.get("predictor.cif_output2.bias", {1});
+    if (w && b && ow && ob) {
+      std::vector<float> r((size_t)3 * D * D), rb((size_t)3 * D);
+      for (int i = 0; i < D; ++i)
+        for (int o = 0; o < D; ++o)
+          for (int j = 0; j < 3; ++j) r[((size_t)j * D + o) * D + i] = w->data[((size_t)i * D + o) * 3 + j];
+      for (int j = 0; j < 3; ++j) memcpy(&rb[(size_t)j * D], b->data.data(), (size_t)D * 4);
+      e->us_cnn.w = L.up_bf16(r.data(), r.size()); e->us_cnn.b = L.up_f32(rb.data(), rb.size()); e->us_cnn.out = 3 * D; e->us_cnn.in = D;
+      e->us_out_w = L.up_f32(ow->data.data(), 2 * D);
+      e->us_out_b = L.up_f32(ob->data.data(), 1);
+      lstm_in("predictor.blstm", {"", "_reverse"}, &e->blstm_ih, &e->blstm_hh);
+    }
+  }
+  if (L.ok && c.contextual) {
+    e->bias_ln3 = L.norm("decoder.bias_decoder.norm3", D);
+    e->bias_q = L.linear("decoder.bias_decoder.src_attn.linear_q", D, D);
+    e->bias_kv = L.linear("decoder.bias_decoder.src_attn.linear_k_v", 2 * D, D);
+    e->bias_out = L.linear("decoder.bias_decoder.src_attn.linear_out", D, D);
+    auto w = L.get("decoder.bias_output.weight", {D, 2 * D, 1});
+    auto tb = L.get("bias_embed.weight", {c.vocab, D});
+    if (w && tb) {
+      e->bias_output.w = L.up_bf16(w->data.data(), (size_t)D * 2 * D); e->bias_output.out = D; e->bias_output.in = 2 * D;
+      e->hw_table = L.up_bf16(tb->data.data(), (size_t)c.vocab * D);
+      lstm_in("bias_encoder", {""}, &e->hw_ih, &e->hw_hh);
+    }
+  }
   if (L.ok) build_frontend_tables(e.get(), L, means, vars);
   if (!L.ok) {
     set_error(L.err);
@@ -360,6 +416,8 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
   const size_t R = (size_t)c.max_rows;
   size_t bytes = R * (6 * 80 * 4 + 560 * 4 + 512 * 4 + 560 * 2 + 1536 * 2 + 512 * 2 + 512 * 2 + 2048 * 2 + 512 * 4 + 512 * 2 +
                       512 * 4 + 4 * 4 + 4 + 8 + 8) + (1 << 20);
+  if (c.timestamp) bytes += R * 3 * (4096 * 2 + 1024 * 2 + 3 * 4) + (1 << 16);
+  if (c.contextual) bytes += (size_t)B200PF_MAX_HOTWORDS * 1024 * 2 + (1 << 16);
   CK(cudaMalloc((void**)&e->ws.base, bytes), "cudaMalloc(workspace)");
   e->ws.size = bytes;
   bool ok = ws_take(e.get(), &e->fb, R * 6 * 80) && ws_take(e.get(), &e->x0, R * 560) && ws_take(e.get(), &e->x, R * 512) &&
@@ -368,6 +426,10 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
             ws_take(e.get(), &e->enc_bf16, R * 512) && ws_take(e.get(), &e->y, R * 512) && ws_take(e.get(), &e->alpha, R) &&
             ws_take(e.get(), &e->cif_cur, R) && ws_take(e.get(), &e->cif_rem, R) && ws_take(e.get(), &e->fire_val, R) &&
             ws_take(e.get(), &e->fire_row, R) && ws_take(e.get(), &e->amax, R) && ws_take(e.get(), &e->tok_info, R);
+  if (ok && c.timestamp)
+    ok = ws_take(e.get(), &e->us_gx, R * 3 * 4096) && ws_take(e.get(), &e->us_h, R * 3 * 1024) && ws_take(e.get(), &e->us_a2, R * 3) &&
+         ws_take(e.get(), &e->us_alphas, R * 3) && ws_take(e.get(), &e->us_peaks, R * 3);
+  if (ok && c.contextual) ok = ws_take(e.get(), &e->hw_kv, (size_t)B200PF_MAX_HOTWORDS * 1024);
   if (!ok) { set_error("workspace arena exhausted"); return B200PF_ERR_CUDA; }
   CK(cudaMemset(e->ws.base, 0, bytes), "cudaMemset(workspace)");
   CK(cudaDeviceSynchronize(), "engine init");
@@ -431,7 +493,7 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
 }
 
 static const char* kProfNames[16] = {"frontend", "layernorm", "gemm_other", "attention_tcgen05", "fsmn", "cif", "argmax", "other",
-                                      "gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2", "gemm_dec", "gemm_vocab", "", ""};
+                                      "gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2", "gemm_dec", "gemm_vocab", "lstm", "timestamp_head"};
 
 int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches) {
   if (!e) { set_error("null engine"); return B200PF_ERR_INVALID; }
@@ -467,7 +529,8 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 63) & ~size_t(63); return o; };
   const size_t o_sample = carve((S + 1) * 8), o_fb = carve((S + 1) * 4), o_row = carve((S + 1) * 4), o_T = carve(S * 4),
-               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8);
+               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8), o_usoff = carve(S * 4), o_uslen = carve(S * 4),
+               o_zero = carve(S * 4), o_hwlen = carve(S * 4);
   b->meta_bytes = off;
   CK(cudaMallocHost((void**)&b->h_meta, off), "cudaMallocHost(meta)");
   CK(cudaMalloc((void**)&b->d_meta, off), "cudaMalloc(meta)");
@@ -478,6 +541,13 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   b->h_row_seg = (int*)(b->h_meta + o_rseg);          b->d_row_seg = (const int*)(b->d_meta + o_rseg);
   b->h_row_info = (int2*)(b->h_meta + o_rinfo);       b->d_row_info = (const int2*)(b->d_meta + o_rinfo);
   b->h_work = (AttnWork*)(b->h_meta + o_work);        b->d_work = (const AttnWork*)(b->d_meta + o_work);
+  b->h_us_off = (int*)(b->h_meta + o_usoff);          b->d_us_off = (const int*)(b->d_meta + o_usoff);
+  b->h_us_len = (int*)(b->h_meta + o_uslen);          b->d_us_len = (const int*)(b->d_meta + o_uslen);
+  b->h_zero = (int*)(b->h_meta + o_zero);             b->d_zero = (const int*)(b->d_meta + o_zero);
+  b->h_hw_len = (int*)(b->h_meta + o_hwlen);          b->d_hw_len = (const int*)(b->d_meta + o_hwlen);
+  memset(b->h_meta, 0, off);
+  if (e->cfg.timestamp) CK(cudaMallocHost((void**)&b->h_us, R * 3 * 2 * sizeof(float)), "cudaMallocHost(us)");
+  if (e->cfg.contextual) CK(cudaMalloc((void**)&b->d_hw, (size_t)B200PF_MAX_HOTWORDS * 512 * 2), "cudaMalloc(hotwords)");
   CK(cudaMalloc((void**)&b->d_n_tok, (2 * S + 2 + 2 * R + 16) * 4), "cudaMalloc(results)");
   b->d_tok_off = b->d_n_tok + S;
   b->d_tok_total = b->d_tok_off + S + 1;
@@ -498,6 +568,8 @@ void b200pf_batch_destroy(b200pf_batch* b) {
   cudaFree(b->d_n_tok);
   cudaFreeHost(b->h_meta);
   cudaFreeHost(b->h_res);
+  if (b->h_us) cudaFreeHost(b->h_us);
+  if (b->d_hw) cudaFree(b->d_hw);
   cudaEventDestroy(b->staged);
   delete b;
 }
@@ -523,6 +595,10 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
     b->h_fb_off[ns] = frames;
     b->h_row_off[ns] = rows;
     b->h_seg_T[ns] = T;
+    b->h_us_off[ns] = 3 * rows;
+    b->h_us_len[ns] = 3 * T;
+    b->h_zero[ns] = 0;
+    b->h_hw_len[ns] = b->n_hw;
     for (int t = 0; t < T; ++t) { b->h_row_seg[rows + t] = ns; b->h_row_info[rows + t] = make_int2(t, T); }
     b->h_row_seg[rows + T] = -1;
     b->h_row_info[rows + T] = make_int2(-1, T);
@@ -536,6 +612,72 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
   b->h_row_off[ns] = rows;
   b->n_seg = ns; b->rows = rows; b->n_frames = frames; b->n_work = nwork;
   b->collected = false;
+  return 0;
+}
+
+int b200pf_batch_set_hotwords(b200pf_batch* b, const float* hw_emb, int n_hw, int dim) {
+  if (!b || n_hw < 0 || (n_hw > 0 && !hw_emb)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  if (!e->cfg.contextual) { set_error("model has no hotword (contextual) decoder"); return B200PF_ERR_INVALID; }
+  if (n_hw > B200PF_MAX_HOTWORDS) { set_error("too many hotwords"); return B200PF_ERR_CAPACITY; }
+  if (n_hw > 0 && dim != e->cfg.d_model) { set_error("hotword embedding dimension != d_model"); return B200PF_ERR_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  if (n_hw > 0) {
+    std::vector<uint16_t> tmp((size_t)n_hw * dim);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = f32_to_bf16_rne(hw_emb[i]);
+    CK(cudaStreamSynchronize(e->stream), "sync");  // a forward that still reads the previous embeddings may be in flight
+    CK(cudaMemcpy(b->d_hw, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice), "H2D hotwords");
+  }
+  b->n_hw = n_hw;
+  return 0;
+}
+
+int b200pf_engine_hotword_embed(b200pf_engine* e, const int32_t* ids, const int32_t* lengths, int n_words, int max_len, float* out) {
+  if (!e || !ids || !lengths || !out || n_words <= 0 || max_len <= 0) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  if (!e->cfg.contextual) { set_error("model has no hotword compiler"); return B200PF_ERR_INVALID; }
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  const int D = e->cfg.d_model;
+  const size_t rows = (size_t)n_words * max_len;
+  std::vector<int> off(n_words), len(n_words);
+  for (int j = 0; j < n_words; ++j) {
+    if (lengths[j] < 1 || lengths[j] > max_len) { set_error("hotword length out of range"); return B200PF_ERR_INVALID; }
+    off[j] = j * max_len;
+    len[j] = lengths[j];  // steps past the word's length cannot change the row that is returned
+  }
+  std::lock_guard<std::mutex> lock(e->mu);
+  uint8_t* scratch = nullptr;
+  const size_t b_ids = (rows * 4 + 255) & ~size_t(255), b_x = rows * D * 2, b_gx = rows * 4 * D * 2, b_h = rows * D * 4,
+               b_seq = ((size_t)n_words * 4 + 255) & ~size_t(255);
+  CK(cudaMalloc((void**)&scratch, b_ids + b_x + b_gx + b_h + 2 * b_seq), "cudaMalloc(hotword scratch)");
+  int* d_ids = (int*)scratch;
+  __nv_bfloat16* d_x = (__nv_bfloat16*)(scratch + b_ids);
+  __nv_bfloat16* d_gx = (__nv_bfloat16*)(scratch + b_ids + b_x);
+  float* d_h = (float*)(scratch + b_ids + b_x + b_gx);
+  int* d_off = (int*)(scratch + b_ids + b_x + b_gx + b_h);
+  int* d_len = (int*)(scratch + b_ids + b_x + b_gx + b_h + b_seq);
+  cudaStream_t s = e->stream;
+  int rc = 0;
+  auto fin = [&](int code, const char* what) { cudaStreamSynchronize(s); cudaFree(scratch); return code ? check_cuda((cudaError_t)code, what) : 0; };
+  if ((rc = (int)cudaMemcpyAsync(d_ids, ids, rows * 4, cudaMemcpyHostToDevice, s))) return fin(rc, "H2D ids");
+  if ((rc = (int)cudaMemcpyAsync(d_off, off.data(), (size_t)n_words * 4, cudaMemcpyHostToDevice, s))) return fin(rc, "H2D off");
+  if ((rc = (int)cudaMemcpyAsync(d_len, len.data(), (size_t)n_words * 4, cudaMemcpyHostToDevice, s))) return fin(rc, "H2D len");
+  if ((rc = (int)cudaMemsetAsync(d_h, 0, b_h, s))) return fin(rc, "memset");
+  if ((rc = embed_gather_launch(e->hw_table, e->cfg.vocab, d_ids, (int)rows, d_x, s))) return fin(rc, "embed gather");
+  GemmProblem gp;
+  gp.A = d_x; gp.lda = D; gp.rows_a = (int64_t)rows; gp.W = e->hw_ih.w; gp.ldw = D; gp.M = (int)rows; gp.N = 4 * D; gp.K = D;
+  GemmEpilogue ge;
+  ge.bias = e->hw_ih.b; ge.out_bf16 = d_gx; ge.ld_out_bf16 = 4 * D;
+  if ((rc = gemm_bf16_tcgen05(gp, ge, e->num_sms, s))) return fin(rc, "hotword input projection");
+  LstmParams lp;
+  lp.gx = d_gx; lp.ld_gx = 4 * D; lp.whh = e->hw_hh; lp.seq_off = d_off; lp.seq_len = d_len; lp.n_seq = n_words; lp.n_dir = 1;
+  lp.out_f32 = d_h; lp.ld_out_f32 = D;
+  if ((rc = lstm_launch(lp, s))) return fin(rc, "hotword lstm");
+  std::vector<float> h(rows * D);
+  if ((rc = (int)cudaMemcpyAsync(h.data(), d_h, b_h, cudaMemcpyDeviceToHost, s))) return fin(rc, "D2H");
+  if ((rc = (int)cudaStreamSynchronize(s))) return fin(rc, "hotword embed");
+  for (int j = 0; j < n_words; ++j)  // the step the reference selects (paraformer.cpp:676-682)
+    memcpy(out + (size_t)j * D, &h[((size_t)j * max_len + lengths[j] - 1) * D], (size_t)D * 4);
+  cudaFree(scratch);
   return 0;
 }
 
@@ -584,9 +726,15 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
   b->launches = 0;
   if (b->n_seg == 0) return 0;
+  const b200pf_config& c = e->cfg;
+  if (c.contextual && (b->n_hw <= 0 || b->h_hw_len[0] != b->n_hw)) {
+    // the reference logs "hw_emb is null" and returns "" (paraformer.cpp:516-520)
+    set_error(b->n_hw <= 0 ? "hw_emb is null: a contextual model needs b200pf_batch_set_hotwords before the batch is staged"
+                           : "hotwords changed after the batch was staged");
+    return B200PF_ERR_INVALID;
+  }
   std::lock_guard<std::mutex> lock(e->mu);
   CK(cudaStreamWaitEvent(s, b->staged, 0), "cudaStreamWaitEvent");
-  const b200pf_config& c = e->cfg;
   const int M = b->rows, D = c.d_model, S = b->n_seg, sms = e->num_sms;
   const int Lcap = M;  // tokens <= frames
   int64_t& nl = b->launches;
@@ -676,6 +824,22 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
                              e->tok_info, b->d_tok_frame, s), "cif_embed");
   if (e->taps) CK(cudaMemcpyAsync(e->tap_emb, e->y, (size_t)Lcap * D * 4, cudaMemcpyDeviceToDevice, s), "tap emb");
 
+  // ---- timestamp head (config 3, a16): ConvTranspose x3 -> BiLSTM -> alpha2 -> rescale to token_num -> cif_wo_hidden ----
+  if (c.timestamp) {
+    __nv_bfloat16* up = e->qkv;  // [M, 1536] == [3M, 512]; free between the encoder and the decoder
+    { GemmEpilogue ep; ep.bias = e->us_cnn.b; ep.out_bf16 = up; ep.ld_out_bf16 = 3 * D;
+      CKL(gemm(e->enc_bf16, D, M, e->us_cnn, M, nullptr, ep, 0, 0, 15), "gemm upsample"); }
+    { GemmEpilogue ep; ep.bias = e->blstm_ih.b; ep.out_bf16 = e->us_gx; ep.ld_out_bf16 = 8 * D;
+      CKL(gemm(up, D, (int64_t)3 * M, e->blstm_ih, 3 * M, nullptr, ep, 0, 0, 15), "gemm blstm input"); }
+    LstmParams lp;
+    lp.gx = e->us_gx; lp.ld_gx = 8 * D; lp.whh = e->blstm_hh; lp.seq_off = b->d_us_off; lp.seq_len = b->d_us_len; lp.n_seq = S;
+    lp.n_dir = 2; lp.reverse_mask = 2; lp.out_bf16 = e->us_h; lp.ld_out = 2 * D;
+    LAUNCH(14, 2.0 * 3 * (M - S) * 2 * 4 * D * D, lstm_launch(lp, s), "blstm");
+    LAUNCH(15, (double)3 * M * 1024 * 2, us_alpha_launch(e->us_h, 3 * M, e->us_out_w, e->us_out_b, e->smooth2, e->noise2, e->us_a2, s), "us_alpha");
+    LAUNCH(15, (double)3 * M * 12, us_peak_launch(e->us_a2, b->d_us_off, b->d_us_len, b->d_n_tok, S, (float)((double)c.cif_threshold - 1e-4),
+                                                 e->us_alphas, e->us_peaks, s), "us_peak");
+  }
+
   // ---- SAN-M decoder ----
   const int* Ldev = b->d_tok_total;
   float* tbuf = e->x0;  // [Lcap, 512] fp32 scratch
@@ -705,8 +869,28 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
       CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep, 0, 0, 12), "dec gemm kv"); }
     LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
-    { GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
-      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "dec gemm out"); }
+    if (!(c.contextual && l == c.n_dec - 1)) {
+      GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
+      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "dec gemm out");
+    } else {
+      // ContextualParaformerDecoder (a16): y is x_self_attn here.  cat = [x_src_attn ; cx] with
+      // cx = bias_decoder(x_self_attn, hotword embeddings); y = x_self_attn + bias_output(cat).
+      __nv_bfloat16* cat = e->qkv;  // [Lcap, 1024]; the cross k/v it held were consumed by the attention above
+      { GemmEpilogue ep; ep.bias = w.out.b; ep.out_bf16 = cat; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm out"); }
+      LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, e->bias_ln3.g, e->bias_ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ctx ln3");
+      { GemmEpilogue ep; ep.bias = e->bias_q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
+        CKL(gemm(e->hb, D, Lcap, e->bias_q, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm q"); }
+      { GemmEpilogue ep; ep.bias = e->bias_kv.b; ep.out_bf16 = e->hw_kv; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(b->d_hw, D, b->n_hw, e->bias_kv, b->n_hw, nullptr, ep, 0, 0, 12), "ctx gemm kv"); }
+      AttnProblem bp = cp;
+      bp.kv = e->hw_kv; bp.kv_rows = b->n_hw; bp.kv_row_off = b->d_zero; bp.kv_len = b->d_hw_len;
+      LAUNCH(3, 4.0 * Lest * b->n_hw * 512, attention_tcgen05(bp, s), "bias attention");
+      { GemmEpilogue ep; ep.bias = e->bias_out.b; ep.out_bf16 = cat + D; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(e->att, D, Lcap, e->bias_out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias out"); }
+      { GemmEpilogue ep; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
+        CKL(gemm(cat, 2 * D, Lcap, e->bias_output, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias_output"); }
+    }
   }
   { int rc = dec_ffn(e->dec3); if (rc) return rc; }
   LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
@@ -734,14 +918,27 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
     CK(cudaMemcpyAsync(h_tok_off, b->d_tok_off, ((size_t)b->n_seg + 1) * 4, cudaMemcpyDeviceToHost, s), "D2H tok_off");
     CK(cudaMemcpyAsync(h_ids, b->d_ids, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H ids");
     CK(cudaMemcpyAsync(h_frame, b->d_tok_frame, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H frames");
+    if (e->cfg.timestamp && res->us_alphas && res->us_peaks) {
+      CK(cudaMemcpyAsync(b->h_us, e->us_alphas, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_alphas");
+      CK(cudaMemcpyAsync(b->h_us + R * 3, e->us_peaks, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_peaks");
+    }
   }
   CK(cudaStreamSynchronize(s), "forward");
-  int64_t out = 0;
+  int64_t out = 0, us_out = 0;
   double fl = 0.0;
   const b200pf_config& c = e->cfg;
+  const bool want_us = c.timestamp && res->us_alphas && res->us_peaks;
   for (int i = 0; i < b->n_seg_in; ++i) {
     const int d = b->dev_of_in[i];
     const int cnt = d >= 0 ? h_n_tok[d] : 0;
+    if (res->us_offsets) res->us_offsets[i] = (int32_t)us_out;
+    if (want_us && d >= 0) {
+      const int n3 = b->h_us_len[d];
+      if (us_out + n3 > res->cap_us) { set_error("result us_alphas capacity too small"); return B200PF_ERR_CAPACITY; }
+      memcpy(res->us_alphas + us_out, b->h_us + b->h_us_off[d], (size_t)n3 * 4);
+      memcpy(res->us_peaks + us_out, b->h_us + R * 3 + b->h_us_off[d], (size_t)n3 * 4);
+      us_out += n3;
+    }
     if (res->token_counts) res->token_counts[i] = cnt;
     if (res->token_offsets) res->token_offsets[i] = (int32_t)out;
     if (res->lfr_frames) res->lfr_frames[i] = b->T_in[i];
@@ -759,8 +956,11 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
       }
       fl += encf + 2 * T * Dm * Dm * 3 + 2 * T * Dm +
             c.n_dec * (4 * L * Dm * Fd + 4 * L * Dm * Dm + 4 * T * Dm * Dm + 4 * L * T * Dm) + 4 * L * Dm * Fd + 2 * L * Dm * c.vocab;
+      if (c.timestamp) fl += 2 * T * Dm * 3 * Dm + 2 * 3 * T * Dm * 8 * Dm + 2 * 3 * T * Dm * 8 * Dm + 2 * 3 * T * 2 * Dm;
+      if (c.contextual) fl += 4 * L * Dm * Dm + 4 * L * b->n_hw * Dm + 2 * L * 2 * Dm * Dm;
     }
   }
+  if (res->us_offsets) res->us_offsets[b->n_seg_in] = (int32_t)us_out;
   if (res->token_offsets) res->token_offsets[b->n_seg_in] = (int32_t)out;
   res->n_tokens = out;
   b->flops = fl;

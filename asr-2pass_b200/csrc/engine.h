@@ -78,6 +78,20 @@ struct b200pf_engine {
   pf::Norm dec_after;
   pf::Linear vocab;
   pf::FrontendTables ft{};
+  // config 3.  timestamp: CifPredictorV3 upsample head; contextual: bias decoder + hotword LSTM.
+  int us_times = 3;
+  float smooth2 = 0.25f, noise2 = 0.01f;
+  pf::Linear us_cnn;                    // ConvTranspose1d(512,512,k=3,s=3) as [3*512, 512]: row j*512+o = W[i][o][j]
+  pf::Linear blstm_ih;                  // [2*2048, 512] forward then reverse; bias = b_ih + b_hh
+  __nv_bfloat16* blstm_hh = nullptr;    // [2][2048][512]
+  float* us_out_w = nullptr;            // cif_output2 [1024]
+  float* us_out_b = nullptr;
+  pf::Norm bias_ln3;                    // decoder.bias_decoder.norm3
+  pf::Linear bias_q, bias_kv, bias_out; // decoder.bias_decoder.src_attn.*
+  pf::Linear bias_output;               // decoder.bias_output [512, 1024] (1x1 conv, no bias)
+  __nv_bfloat16* hw_table = nullptr;    // bias_embed.weight [vocab, 512]
+  pf::Linear hw_ih;                     // bias_encoder W_ih [2048, 512], bias = b_ih + b_hh
+  __nv_bfloat16* hw_hh = nullptr;       // [2048][512]
 
   // workspace (sized by cfg.max_rows = R)
   pf::DeviceArena ws;
@@ -96,6 +110,11 @@ struct b200pf_engine {
   int* fire_row = nullptr;
   unsigned long long* amax = nullptr;
   int2* tok_info = nullptr;
+  // config-3 workspace
+  __nv_bfloat16* us_gx = nullptr;       // [3R, 4096] bf16  BiLSTM input projection
+  __nv_bfloat16* us_h = nullptr;        // [3R, 1024] bf16  BiLSTM output
+  float *us_a2 = nullptr, *us_alphas = nullptr, *us_peaks = nullptr;   // [3R]
+  __nv_bfloat16* hw_kv = nullptr;       // [max_hotwords, 1024] bf16  bias_decoder k/v of the hotword embeddings
   // per-category CUDA-event timing of the launches (option "profile")
   int profile = 0;
   struct ProfRec { cudaEvent_t a, b; int cat; double work; };
@@ -124,6 +143,10 @@ struct b200pf_batch {
   int* h_fb_off = nullptr;         const int* d_fb_off = nullptr;
   int* h_row_off = nullptr;        const int* d_row_off = nullptr;
   int* h_seg_T = nullptr;          const int* d_seg_T = nullptr;
+  int* h_us_off = nullptr;         const int* d_us_off = nullptr;   // [S] 3 * row_off (upsampled rows)
+  int* h_us_len = nullptr;         const int* d_us_len = nullptr;   // [S] 3 * T
+  int* h_zero = nullptr;           const int* d_zero = nullptr;     // [S] zeros: every segment reads the same hotword rows
+  int* h_hw_len = nullptr;         const int* d_hw_len = nullptr;   // [S] n_hw
   int* h_row_seg = nullptr;        const int* d_row_seg = nullptr;
   int2* h_row_info = nullptr;      const int2* d_row_info = nullptr;
   pf::AttnWork* h_work = nullptr;  const pf::AttnWork* d_work = nullptr;
@@ -134,6 +157,9 @@ struct b200pf_batch {
   int* d_ids = nullptr;       // [R]
   int* d_tok_frame = nullptr; // [R]
   uint8_t* h_res = nullptr;   // pinned: n_tok[S] tok_off[S+1] ids[R] tok_frame[R]
+  float* h_us = nullptr;      // pinned: us_alphas[3R] us_peaks[3R] (timestamp models)
+  __nv_bfloat16* d_hw = nullptr;  // [max_hotwords, 512] bf16 hotword embeddings of this batch (contextual models)
+  int n_hw = 0;
   // staged state
   int n_seg_in = 0;             // segments the caller passed
   int n_seg = 0;                // segments on the device (T > 0)

@@ -52,7 +52,7 @@ std::vector<std::vector<int>> FormBatches(const std::vector<long long>& len_sort
 }
 
 RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples, std::vector<long long> seg_b,
-                         std::vector<long long> seg_e) {
+                         std::vector<long long> seg_e, const std::vector<std::vector<float>>& hw_emb) {
   funasr_b200::ParaformerB200* asr = h->asr.get();
   RecogResult* res = new RecogResult;
   res->snippet_time = (float)n_samples / asr->GetAsrSampleRate();
@@ -75,7 +75,7 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
       buf.insert(buf.end(), pcm + seg_b[s], pcm + seg_e[s]);
       offs.push_back((int64_t)buf.size());
     }
-    std::vector<std::string> out = asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size());
+    std::vector<std::string> out = asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size(), hw_emb);
     for (size_t k = 0; k < batch.size(); ++k) {
       const int s = index[batch[k]];
       msgs[s] = out[k];
@@ -109,17 +109,17 @@ void FunOfflineReset(FUNASR_HANDLE, FUNASR_DEC_HANDLE) {}
 funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->asr.get() : nullptr; }
 
 FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, const long long* seg_begin,
-                                          const long long* seg_end, int n_seg) {
+                                          const long long* seg_end, int n_seg, const std::vector<std::vector<float>>& hw_emb) {
   OfflineHandle* h = (OfflineHandle*)handle;
   if (!h || (!pcm && n_samples > 0)) return nullptr;
   std::vector<long long> b(seg_begin, seg_begin + n_seg), e(seg_end, seg_end + n_seg);
   for (int i = 0; i < n_seg; ++i)
     if (b[i] < 0 || e[i] < b[i] || e[i] > n_samples) return nullptr;
-  return RunSegments(h, pcm, n_samples, b, e);
+  return RunSegments(h, pcm, n_samples, b, e, hw_emb);
 }
 
 FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE, QM_CALLBACK,
-                                    const std::vector<std::vector<float>>&, int sampling_rate, std::string wav_format, bool,
+                                    const std::vector<std::vector<float>>& hw_emb, int sampling_rate, std::string wav_format, bool,
                                     int, int vad_max_len, FUNASR_DEC_HANDLE, std::string, bool) {
   OfflineHandle* h = (OfflineHandle*)handle;
   if (!h) return nullptr;  // funasrruntime.cpp:216-217
@@ -140,7 +140,7 @@ FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, in
   std::vector<long long> b, e;
   for (long long s = 0; s < n; s += cut) { b.push_back(s); e.push_back(std::min(n, s + cut)); }
   if (n == 0) { b.push_back(0); e.push_back(0); }
-  return RunSegments(h, pcm.data(), n, b, e);
+  return RunSegments(h, pcm.data(), n, b, e, hw_emb);
 }
 
 FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK cb,

@@ -61,4 +61,4 @@ funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle);
 // segment i = pcm[seg_begin[i] .. seg_end[i]) in samples.  Segments are length-sorted, batched with the
 // reference's FetchDynamic rules, decoded, un-permuted and stitched exactly like FunOfflineInferBuffer.
 FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, const long long* seg_begin,
-                                          const long long* seg_end, int n_seg);
+                                          const long long* seg_end, int n_seg, const std::vector<std::vector<float>>& hw_emb = {{0.0}});

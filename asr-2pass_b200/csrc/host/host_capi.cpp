@@ -76,6 +76,48 @@ int b200pf_host_offline_infer_segments(void* h, const int16_t* pcm, int64_t n_sa
   FunASRFreeResult(r);
   return n;
 }
+int b200pf_host_offline_infer_buffer_hw(void* h, const char* buf, int n_bytes, int vad_max_len, const float* hw, int n_hw, int dim,
+                                        char* text, int text_cap, char* stamp, int stamp_cap) {
+  std::vector<std::vector<float>> emb;
+  for (int j = 0; j < n_hw; ++j) emb.emplace_back(hw + (size_t)j * dim, hw + (size_t)(j + 1) * dim);
+  FUNASR_RESULT r = FunOfflineInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr, emb, 16000, "pcm", true, 800, vad_max_len);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  CopyOut(FunASRGetStamp(r), stamp, stamp_cap);
+  FunASRFreeResult(r);
+  return n;
+}
+// CompileHotwordEmbedding(handle, hotwords) (funasrruntime.h:118): rows are written to out [cap_rows][dim]; returns the row count.
+int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* out, int cap_rows, int dim) {
+  std::string hw(hotwords ? hotwords : "");
+  const std::vector<std::vector<float>> emb = CompileHotwordEmbedding(h_offline, hw);
+  if ((int)emb.size() > cap_rows) return -1;
+  for (size_t j = 0; j < emb.size(); ++j) {
+    if ((int)emb[j].size() != dim) return -1;
+    memcpy(out + j * dim, emb[j].data(), (size_t)dim * sizeof(float));
+  }
+  return (int)emb.size();
+}
+int b200pf_host_init_seg_dict(void* h_offline, const char* path) {
+  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  if (!m || !path) return -1;
+  m->InitSegDict(path);
+  return 0;
+}
+int b200pf_host_model_forward_hw(void* h_offline, const float* const* din, const int* len, int n, const float* hw, int n_hw, int dim,
+                                 char* out, int cap) {
+  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  if (!m) return -1;
+  std::vector<float*> ptrs(n);
+  for (int i = 0; i < n; ++i) ptrs[i] = const_cast<float*>(din[i]);
+  std::vector<int> l(len, len + n);
+  std::vector<std::vector<float>> emb;
+  for (int j = 0; j < n_hw; ++j) emb.emplace_back(hw + (size_t)j * dim, hw + (size_t)(j + 1) * dim);
+  std::vector<std::string> r = m->Forward(ptrs.data(), l.data(), true, emb, nullptr, n);
+  std::string joined;
+  for (int i = 0; i < n; ++i) { if (i) joined += "\n"; joined += r[i]; }
+  return CopyOut(joined, out, cap);
+}
 // Model::Forward over float segments (the plugin seam itself): returns the '\n'-joined result strings.
 int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap) {
   funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);

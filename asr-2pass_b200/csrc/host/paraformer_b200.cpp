@@ -1,5 +1,6 @@
 #include "paraformer_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,10 @@ bool ParaformerB200::Init(const std::string& model_dir, std::string* err) {
   vocab_.reset(new pf::host::Detokenizer(std::move(toks)));
   max_rows_ = cfg.max_rows;
   max_segments_ = cfg.max_segments;
+  d_model_ = cfg.d_model;
+  use_hotword_ = cfg.contextual != 0;
+  has_timestamp_ = cfg.timestamp != 0;
+  for (size_t i = 0; i < vocab_->tokens().size(); ++i) token_id_.emplace(vocab_->tokens()[i], (int)i);  // PhoneSet: first id wins
   return true;
 }
 
@@ -48,9 +53,113 @@ void ParaformerB200::InitAsr(const std::string& am_model, const std::string& am_
   }
 }
 
+namespace {
+
+// UTF-8 -> code points (BMP is all the reference's UTF-16 path distinguishes here)
+std::vector<std::pair<uint32_t, std::string>> CodePoints(const std::string& s) {
+  std::vector<std::pair<uint32_t, std::string>> out;
+  size_t i = 0;
+  while (i < s.size()) {
+    const unsigned char c = (unsigned char)s[i];
+    int n = 1;
+    uint32_t cp = c;
+    if ((c & 0xe0) == 0xc0) { n = 2; cp = c & 0x1f; }
+    else if ((c & 0xf0) == 0xe0) { n = 3; cp = c & 0x0f; }
+    else if ((c & 0xf8) == 0xf0) { n = 4; cp = c & 0x07; }
+    if (i + n > s.size()) n = (int)(s.size() - i);
+    for (int k = 1; k < n; ++k) cp = (cp << 6) | ((unsigned char)s[i + k] & 0x3f);
+    out.emplace_back(cp, s.substr(i, n));
+    i += n;
+  }
+  return out;
+}
+
+std::vector<std::string> SplitChar(const std::string& s, char delim) {  // util.cpp:639-647 (std::getline semantics)
+  std::vector<std::string> elems;
+  size_t start = 0;
+  if (s.empty()) return elems;
+  while (true) {
+    const size_t p = s.find(delim, start);
+    if (p == std::string::npos) {
+      if (start < s.size()) elems.push_back(s.substr(start));
+      break;
+    }
+    elems.push_back(s.substr(start, p - start));
+    start = p + 1;
+  }
+  return elems;
+}
+
+}  // namespace
+
+void ParaformerB200::InitHwCompiler(const std::string& hw_model, int thread_num) {
+  (void)hw_model; (void)thread_num;
+  if (!use_hotword_) fprintf(stderr, "InitHwCompiler: model.b200pf carries no hotword compiler (contextual = 0); hotwords are ignored\n");
+}
+
+void ParaformerB200::InitSegDict(const std::string& seg_dict_model) {
+  FILE* f = fopen(seg_dict_model.c_str(), "rb");
+  if (!f) { fprintf(stderr, "%s open failed !!\n", seg_dict_model.c_str()); return; }
+  std::string text;
+  char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  for (const std::string& line : SplitChar(text, '\n')) {
+    const std::vector<std::string> item = SplitChar(line, '\t');
+    if (item.size() > 1) seg_dict_[item[0]] = SplitChar(item[1], ' ');
+  }
+}
+
 std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::string& hotwords) {
-  (void)hotwords;
-  return std::vector<std::vector<float>>(1, std::vector<float>(512, 0.0f));
+  const int dim = d_model_;
+  if (!use_hotword_) return std::vector<std::vector<float>>(1, std::vector<float>(dim, 0.0f));  // paraformer.cpp:595-599
+  const int max_len = B200PF_HOTWORD_LEN;
+  std::vector<int32_t> matrix, lengths;
+  if (!hotwords.empty()) {
+    for (const std::string& hotword : SplitChar(hotwords, ' ')) {
+      std::vector<std::string> chars;
+      const auto cps = CodePoints(hotword);
+      bool all_cjk = !hotword.empty();
+      for (const auto& cp : cps) all_cjk = all_cjk && cp.first >= 0x4e00 && cp.first <= 0x9fff;   // IsAllChineseCharactor
+      if (all_cjk) {
+        for (const auto& cp : cps)  // KeepChineseCharacterAndSplit (util.cpp:192-209)
+          if ((cp.first >= 0x4e00 && cp.first <= 0x9fff) || (cp.first >= 0x3400 && cp.first <= 0x4dff)) chars.push_back(cp.second);
+      } else {
+        for (const std::string& word : SplitChar(hotword, ' ')) {
+          auto it = seg_dict_.find(word);  // SegDict::GetTokensByWord: OOV -> no tokens
+          if (it != seg_dict_.end()) chars.insert(chars.end(), it->second.begin(), it->second.end());
+        }
+      }
+      if (chars.empty()) continue;
+      std::vector<int32_t> row(max_len, 0);
+      const int len = std::min(max_len, (int)chars.size());
+      bool oov = false;
+      for (int i = 0; i < len && !oov; ++i) {
+        auto it = token_id_.find(chars[i]);
+        if (it == token_id_.end()) oov = true; else row[i] = it->second;
+      }
+      if (oov) continue;
+      lengths.push_back(len);
+      matrix.insert(matrix.end(), row.begin(), row.end());
+    }
+  }
+  std::vector<int32_t> blank(max_len, 0);
+  blank[0] = 1;
+  matrix.insert(matrix.end(), blank.begin(), blank.end());
+  lengths.push_back(1);
+  const int n = (int)lengths.size();
+  std::vector<float> flat((size_t)n * dim);
+  std::vector<std::vector<float>> result;
+  {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (b200pf_engine_hotword_embed(engine_, matrix.data(), lengths.data(), n, max_len, flat.data()) != 0) {
+      fprintf(stderr, "CompileHotwordEmbedding: %s\n", b200pf_last_error());  // the reference logs and returns {} too
+      return result;
+    }
+  }
+  for (int j = 0; j < n; ++j) result.emplace_back(flat.begin() + (size_t)j * dim, flat.begin() + (size_t)(j + 1) * dim);
+  return result;
 }
 
 std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg) {
@@ -60,52 +169,90 @@ std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_se
     const int cnt = r.token_counts[i];
     if (r.lfr_frames[i] <= 0) continue;  // empty features -> "" (paraformer.cpp:477-480)
     std::vector<int> ids(r.token_ids + r.token_offsets[i], r.token_ids + r.token_offsets[i] + cnt);
-    out[i] = vocab_->ToText(ids, language_);  // GreedySearch, paraformer.cpp:386-397
+    if (!has_timestamp_) {
+      out[i] = vocab_->ToText(ids, language_);  // GreedySearch, paraformer.cpp:386-397
+    } else {
+      // GreedySearch with is_stamp (paraformer.cpp:398-407): Vector2String -> TimestampOnnx -> PostProcess
+      std::vector<std::string> pieces = vocab_->ToPieces(ids);
+      std::vector<std::string> raw(pieces);
+      std::vector<float> us_alphas(r.us_alphas + r.us_offsets[i], r.us_alphas + r.us_offsets[i + 1]);
+      std::vector<float> us_peaks(r.us_peaks + r.us_offsets[i], r.us_peaks + r.us_offsets[i + 1]);
+      std::string dbg;
+      std::vector<pf::host::Span> spans = pf::host::TimestampFromPeaks(&us_alphas, us_peaks, &pieces, &dbg);
+      out[i] = pf::host::MergeWithStamps(raw, spans);
+    }
     last_ids_[i].swap(ids);
   }
   return out;
 }
 
+bool ParaformerB200::RunBatch(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
+                              const std::vector<std::vector<float>>& hw_emb, std::vector<std::string>* out) {
+  if (!batch_ || samples > batch_samples_) {
+    if (batch_) b200pf_batch_destroy(batch_);
+    batch_ = nullptr;
+    hw_set_ = nullptr;
+    batch_samples_ = samples + samples / 4 + 16000;
+    if (b200pf_batch_create(engine_, batch_samples_, &batch_) != 0) { fprintf(stderr, "ParaformerB200: %s\n", b200pf_last_error()); return false; }
+  }
+  if (use_hotword_) {
+    if (hw_emb.empty()) { fprintf(stderr, "hw_emb is null\n"); return false; }  // paraformer.cpp:516-520
+    // flatten [n_hw][dim] like the reference (paraformer.cpp:521-526); re-upload only when the matrix changed
+    std::vector<float> flat;
+    flat.reserve(hw_emb.size() * hw_emb[0].size());
+    for (const auto& row : hw_emb) flat.insert(flat.end(), row.begin(), row.end());
+    if (flat != hw_flat_ || hw_set_ == nullptr) {
+      if (flat.size() != hw_emb.size() * (size_t)d_model_ ||
+          b200pf_batch_set_hotwords(batch_, flat.data(), (int)hw_emb.size(), (int)hw_emb[0].size()) != 0) {
+        fprintf(stderr, "ParaformerB200: bad hotword embedding (%zu x %zu): %s\n", hw_emb.size(), hw_emb[0].size(), b200pf_last_error());
+        return false;  // ORT would throw on the shape mismatch -> "" (paraformer.cpp:582-587)
+      }
+      hw_flat_.swap(flat);
+      hw_set_ = hw_flat_.data();
+    }
+  }
+  std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_), us_offs(n + 1);
+  std::vector<float> us_a, us_p;
+  b200pf_result r;
+  memset(&r, 0, sizeof(r));
+  r.token_counts = counts.data(); r.token_offsets = offs.data(); r.lfr_frames = frames.data();
+  r.token_ids = ids.data(); r.fire_frames = fire.data(); r.cap_tokens = max_rows_;
+  r.us_offsets = us_offs.data();
+  if (has_timestamp_) {
+    us_a.resize((size_t)3 * max_rows_); us_p.resize((size_t)3 * max_rows_);
+    r.us_alphas = us_a.data(); r.us_peaks = us_p.data(); r.cap_us = (int64_t)3 * max_rows_;
+  }
+  const int rc = pcm ? b200pf_forward_s16(batch_, pcm, offsets, n, &r) : b200pf_forward_f32(batch_, din, len, n, &r);
+  if (rc != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
+  *out = Decode(r, n);
+  return true;
+}
+
 std::vector<std::string> ParaformerB200::Forward(float** din, int* len, bool input_finished,
                                                  const std::vector<std::vector<float>>& hw_emb, void* wfst_decoder,
                                                  int batch_in) {
-  (void)input_finished; (void)hw_emb; (void)wfst_decoder;
+  (void)input_finished; (void)wfst_decoder;
   std::vector<std::string> results(batch_in > 0 ? batch_in : 0);
   if (batch_in <= 0 || !engine_) return results;
   std::lock_guard<std::mutex> lock(mu_);
-  try {
-    // split the caller's batch by the engine's capacity; results keep the caller's order
-    int start = 0;
-    while (start < batch_in) {
-      int64_t rows = 0, samples = 0;
-      int end = start;
-      while (end < batch_in && end - start < max_segments_) {
-        const int T = b200pf_num_lfr_frames(len[end]);
-        const int64_t r = T > 0 ? T + 1 : 0;
-        if (end > start && rows + r > max_rows_) break;
-        rows += r;
-        samples += len[end];
-        ++end;
-      }
-      const int n = end - start;
-      if (!batch_ || samples > batch_samples_) {
-        if (batch_) b200pf_batch_destroy(batch_);
-        batch_ = nullptr;
-        batch_samples_ = samples + samples / 4 + 16000;
-        if (b200pf_batch_create(engine_, batch_samples_, &batch_) != 0) throw std::string(b200pf_last_error());
-      }
-      std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_);
-      b200pf_result r;
-      r.token_counts = counts.data(); r.token_offsets = offs.data(); r.lfr_frames = frames.data();
-      r.token_ids = ids.data(); r.fire_frames = fire.data(); r.cap_tokens = max_rows_; r.n_tokens = 0;
-      if (b200pf_forward_f32(batch_, din + start, len + start, n, &r) != 0) throw std::string(b200pf_last_error());
-      std::vector<std::string> part = Decode(r, n);
-      for (int i = 0; i < n; ++i) results[start + i] = part[i];
-      start = end;
+  // split the caller's batch by the engine's capacity; results keep the caller's order.  A failing call logs and
+  // leaves "" for its items, never throws (paraformer.cpp:582-587).
+  int start = 0;
+  while (start < batch_in) {
+    int64_t rows = 0, samples = 0;
+    int end = start;
+    while (end < batch_in && end - start < max_segments_) {
+      const int T = b200pf_num_lfr_frames(len[end]);
+      const int64_t r = T > 0 ? T + 1 : 0;
+      if (end > start && rows + r > max_rows_) break;
+      rows += r;
+      samples += len[end];
+      ++end;
     }
-  } catch (const std::string& e) {
-    // the reference logs and returns "" for the failing call, never throws (paraformer.cpp:582-587)
-    fprintf(stderr, "ParaformerB200::Forward: %s\n", e.c_str());
+    std::vector<std::string> part;
+    if (RunBatch(nullptr, nullptr, din + start, len + start, end - start, samples, hw_emb, &part))
+      for (int i = 0; i < end - start; ++i) results[start + i] = part[i];
+    start = end;
   }
   return results;
 }
@@ -118,7 +265,8 @@ std::string ParaformerB200::Forward(float* din, int len, bool input_finished, co
   return r.empty() ? std::string() : r[0];
 }
 
-std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg) {
+std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,
+                                                      const std::vector<std::vector<float>>& hw_emb) {
   std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
   if (n_seg <= 0 || !engine_) return results;
   std::lock_guard<std::mutex> lock(mu_);
@@ -133,21 +281,9 @@ std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const 
       rows += r;
       ++end;
     }
-    const int n = end - start;
-    const int64_t samples = offsets[end] - offsets[start];
-    if (!batch_ || samples > batch_samples_) {
-      if (batch_) b200pf_batch_destroy(batch_);
-      batch_ = nullptr;
-      batch_samples_ = samples + samples / 4 + 16000;
-      if (b200pf_batch_create(engine_, batch_samples_, &batch_) != 0) { fprintf(stderr, "%s\n", b200pf_last_error()); return results; }
-    }
-    std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_);
-    b200pf_result r;
-    r.token_counts = counts.data(); r.token_offsets = offs.data(); r.lfr_frames = frames.data();
-    r.token_ids = ids.data(); r.fire_frames = fire.data(); r.cap_tokens = max_rows_; r.n_tokens = 0;
-    if (b200pf_forward_s16(batch_, pcm, offsets + start, n, &r) != 0) { fprintf(stderr, "%s\n", b200pf_last_error()); return results; }
-    std::vector<std::string> part = Decode(r, n);
-    for (int i = 0; i < n; ++i) results[start + i] = part[i];
+    std::vector<std::string> part;
+    if (RunBatch(pcm, offsets + start, nullptr, nullptr, end - start, offsets[end] - offsets[start], hw_emb, &part))
+      for (int i = 0; i < end - start; ++i) results[start + i] = part[i];
     start = end;
   }
   return results;

@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/b200pf.h"
@@ -64,13 +65,22 @@ class ParaformerB200 : public Model {
                       void* wfst_decoder = nullptr) override;
   // int16 entry used by the buffer API when no resampling is needed (skips the float round trip of
   // Audio::LoadPcmwav, audio.cpp:787-819, which is exact: int16 -> float/32768 -> *32768).
-  std::vector<std::string> ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg);
+  std::vector<std::string> ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,
+                                        const std::vector<std::vector<float>>& hw_emb = {{0.0}});
 
   void StartUtterance() override {}
   void EndUtterance() override {}
   void Reset() override {}
   std::string Rescoring() override { return ""; }
-  std::vector<std::vector<float>> CompileHotwordEmbedding(std::string& hotwords) override;  // {{0 x 512}} (paraformer.cpp:595-599)
+  // Contextual models: hotword string -> ids -> Embedding + LSTM on the GPU -> one 512-vector per hotword plus the
+  // blank row (paraformer.cpp:592-693).  Other models: {{0 x 512}} (paraformer.cpp:595-599).
+  std::vector<std::vector<float>> CompileHotwordEmbedding(std::string& hotwords) override;
+  // The reference loads model_eb.onnx here and flips use_hotword (paraformer.cpp:243-272).  The B200 model file
+  // already carries the hotword compiler's weights, so this only checks that it does.
+  void InitHwCompiler(const std::string& hw_model, int thread_num) override;
+  void InitSegDict(const std::string& seg_dict_model) override;  // SegDict::SegDict, seg_dict.cpp:19-38
+  bool use_hotword() const { return use_hotword_; }
+  bool has_timestamp() const { return has_timestamp_; }
   std::string GetLang() override { return language_; }
   int GetAsrSampleRate() override { return sample_rate_; }
   void SetBatchSize(int batch_size) override { batch_size_ = batch_size; }
@@ -83,6 +93,9 @@ class ParaformerB200 : public Model {
 
  private:
   std::vector<std::string> Decode(const b200pf_result& r, int n_seg);
+  // one engine-sized batch through the C ABI: pcm16 (offsets) or float (din/len); false = error already logged
+  bool RunBatch(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
+                const std::vector<std::vector<float>>& hw_emb, std::vector<std::string>* out);
 
   int device_, max_rows_, max_segments_;
   b200pf_engine* engine_ = nullptr;
@@ -94,6 +107,12 @@ class ParaformerB200 : public Model {
   int batch_size_ = 1;
   std::mutex mu_;  // Forward is called concurrently by decoder threads on one handle (websocket-server.cpp:387-403)
   std::vector<std::vector<int>> last_ids_;
+  bool use_hotword_ = false, has_timestamp_ = false;
+  int d_model_ = 512;
+  std::unordered_map<std::string, std::vector<std::string>> seg_dict_;
+  std::unordered_map<std::string, int> token_id_;  // PhoneSet::String2Id (phone-set.cpp:38-68)
+  const float* hw_set_ = nullptr;  // identity of the hotword matrix currently attached to batch_
+  std::vector<float> hw_flat_;
 };
 
 }  // namespace funasr_b200

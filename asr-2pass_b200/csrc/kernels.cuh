@@ -73,6 +73,36 @@ int cif_embed_launch(const float* enc_f32, const float* cur, const float* rem, c
 // K11 decode packed argmax keys -> token ids
 int argmax_decode_launch(const unsigned long long* packed, const int* n_dev, int cap, int* ids, cudaStream_t s);
 
+// K12 LSTM recurrence, hidden 512, gate order i,f,g,o (torch.nn.LSTM).  Config 3 only: the timestamp predictor's
+//     BiLSTM (outputs read at src/paraformer.cpp:549-563) and the hotword compiler's LSTM (src/paraformer.cpp:592-693).
+//     gx = x W_ih^T + b_ih + b_hh comes from the GEMM; sequences are row ranges [seq_off[s], seq_off[s] + seq_len[s]).
+struct LstmParams {
+  const __nv_bfloat16* gx = nullptr;   // [rows, ld_gx] bf16; direction d at columns [2048 d, 2048 d + 2048)
+  int ld_gx = 0;
+  const __nv_bfloat16* whh = nullptr;  // [n_dir][2048][512] bf16
+  const int* seq_off = nullptr;        // [n_seq] (device)
+  const int* seq_len = nullptr;        // [n_seq] (device)
+  int n_seq = 0;
+  int n_dir = 1;
+  int reverse_mask = 0;                // bit d: direction d runs from the last row to the first
+  __nv_bfloat16* out_bf16 = nullptr;   // [rows, ld_out]; direction d at columns [512 d, 512 d + 512)   (optional)
+  int ld_out = 0;
+  float* out_f32 = nullptr;            // same layout, fp32                                             (optional)
+  int ld_out_f32 = 0;
+};
+int lstm_launch(const LstmParams& p, cudaStream_t s);
+
+// K13 timestamp head tail (CifPredictorV3.get_upsample_timestmap): alpha2 = relu(sigmoid(h . w + b) * smooth - noise)
+//     over the BiLSTM output h [rows, 1024] bf16 ...
+int us_alpha_launch(const __nv_bfloat16* h, int rows, const float* w, const float* b, float smooth, float noise, float* alpha,
+                    cudaStream_t s);
+//     ... then per segment: us_alphas = alpha2 * token_num / sum(alpha2); us_cif_peak = cif_wo_hidden(us_alphas, threshold)
+//     (the arrays TimestampOnnx consumes, src/util.cpp:838-870).
+int us_peak_launch(const float* alpha2, const int* seq_off, const int* seq_len, const int* n_tok, int n_seg, float threshold,
+                   float* us_alphas, float* us_peaks, cudaStream_t s);
+// hotword Embedding lookup: out[j] = table[ids[j]] (bf16 rows of 512)
+int embed_gather_launch(const __nv_bfloat16* table, int vocab, const int* ids, int n, __nv_bfloat16* out, cudaStream_t s);
+
 // fp32 -> bf16 conversion (weight upload)
 int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
 

@@ -259,6 +259,55 @@ int b200pf_op_cif(int device, const float* alphas, const float* hidden, const in
   return 0;
 }
 
+int b200pf_op_lstm(int device, const float* x, int rows, const int32_t* seq_off, const int32_t* seq_len, int n_seq, int n_dir,
+                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int bf16_out, float* out) {
+  RC(select_device(device));
+  if (n_dir < 1 || n_dir > 2 || rows <= 0 || n_seq <= 0) { set_error("op_lstm: bad argument"); return B200PF_ERR_INVALID; }
+  const int G = 2048 * n_dir;
+  DevBuf tx, dX, tw, dWih, th, dWhh, dB, dGx, dOff, dLen, dOutB, dOut;
+  RC(up_bf16(x, (size_t)rows * 512, &tx, &dX));
+  RC(up_bf16(w_ih, (size_t)G * 512, &tw, &dWih));
+  RC(up_bf16(w_hh, (size_t)G * 512, &th, &dWhh));
+  std::vector<float> bsum(G);
+  for (int i = 0; i < G; ++i) bsum[i] = b_ih[i] + b_hh[i];
+  RC(up_f32(bsum.data(), G, &dB));
+  RC(dGx.alloc((size_t)rows * G * 2));
+  RC(up_raw(seq_off, n_seq, &dOff)); RC(up_raw(seq_len, n_seq, &dLen));
+  RC(dOut.alloc((size_t)rows * 512 * n_dir * 4)); RC(dOutB.alloc((size_t)rows * 512 * n_dir * 2));
+  RC(check_cuda(cudaMemset(dOut.p, 0, (size_t)rows * 512 * n_dir * 4), "memset"));
+  RC(check_cuda(cudaMemset(dOutB.p, 0, (size_t)rows * 512 * n_dir * 2), "memset"));
+  GemmProblem gp;
+  gp.A = dX.as<__nv_bfloat16>(); gp.lda = 512; gp.rows_a = rows; gp.W = dWih.as<__nv_bfloat16>(); gp.ldw = 512; gp.M = rows; gp.N = G; gp.K = 512;
+  GemmEpilogue ge;
+  ge.bias = dB.as<float>(); ge.out_bf16 = dGx.as<__nv_bfloat16>(); ge.ld_out_bf16 = G;
+  int rc = gemm_bf16_tcgen05(gp, ge, sm_count(), 0);
+  if (rc) return check_cuda((cudaError_t)rc, "lstm input projection");
+  LstmParams lp;
+  lp.gx = dGx.as<__nv_bfloat16>(); lp.ld_gx = G; lp.whh = dWhh.as<__nv_bfloat16>(); lp.seq_off = dOff.as<int>(); lp.seq_len = dLen.as<int>();
+  lp.n_seq = n_seq; lp.n_dir = n_dir; lp.reverse_mask = n_dir == 2 ? 2 : 0;
+  lp.out_bf16 = dOutB.as<__nv_bfloat16>(); lp.ld_out = 512 * n_dir;
+  if (!bf16_out) { lp.out_f32 = dOut.as<float>(); lp.ld_out_f32 = 512 * n_dir; }
+  rc = lstm_launch(lp, 0);
+  if (rc) return check_cuda((cudaError_t)rc, "lstm launch");
+  if (bf16_out) bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)rows * 512 * n_dir);
+  RC(sync_ok("op_lstm"));
+  return check_cuda(cudaMemcpy(out, dOut.p, (size_t)rows * 512 * n_dir * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
+int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, const int32_t* seq_len, const int32_t* n_tok,
+                       int n_seg, int rows, float threshold, float* us_alphas, float* us_peaks) {
+  RC(select_device(device));
+  DevBuf dA, dOff, dLen, dTok, dUa, dUp;
+  RC(up_f32(alpha2, rows, &dA)); RC(up_raw(seq_off, n_seg, &dOff)); RC(up_raw(seq_len, n_seg, &dLen)); RC(up_raw(n_tok, n_seg, &dTok));
+  RC(dUa.alloc((size_t)rows * 4)); RC(dUp.alloc((size_t)rows * 4));
+  RC(check_cuda(cudaMemset(dUa.p, 0, (size_t)rows * 4), "memset")); RC(check_cuda(cudaMemset(dUp.p, 0, (size_t)rows * 4), "memset"));
+  int rc = us_peak_launch(dA.as<float>(), dOff.as<int>(), dLen.as<int>(), dTok.as<int>(), n_seg, threshold, dUa.as<float>(), dUp.as<float>(), 0);
+  if (rc) return check_cuda((cudaError_t)rc, "us_peak launch");
+  RC(sync_ok("op_us_peaks"));
+  RC(check_cuda(cudaMemcpy(us_alphas, dUa.p, (size_t)rows * 4, cudaMemcpyDeviceToHost), "D2H"));
+  return check_cuda(cudaMemcpy(us_peaks, dUp.p, (size_t)rows * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
 int b200pf_op_frontend(b200pf_engine* e, const int16_t* pcm, int64_t n, float* fb_out, float* feats_out) {
   if (!e || !pcm) { set_error("null argument"); return B200PF_ERR_INVALID; }
   RC(check_cuda(cudaSetDevice(e->device), "cudaSetDevice"));

@@ -9,7 +9,8 @@ import numpy as np
 
 # PfConfig defaults (mirrors csrc/config.h)
 DEFAULT_CFG = dict(feat_dim=560, d_model=512, n_heads=4, d_ff=2048, n_enc=50, n_dec=16, kernel=11,
-                   vocab=8404, cif_threshold=1.0, tail_threshold=0.45, pred_residual=0, ln_eps=1e-12)
+                   vocab=8404, cif_threshold=1.0, tail_threshold=0.45, pred_residual=0, ln_eps=1e-12,
+                   timestamp=0, contextual=0, us_times=3, smooth_factor2=0.25, noise_threshold2=0.01)
 
 
 def param_shapes(cfg):
@@ -39,8 +40,30 @@ def param_shapes(cfg):
     out["predictor.cif_conv1d.weight"] = (D, D, 3)
     out["predictor.cif_conv1d.bias"] = (D,)
     lin("predictor.cif_output", 1, D)
-    for l in range(int(cfg["n_dec"])):
-        p = "decoder.decoders.%d" % l
+    ctx = int(cfg.get("contextual", 0))
+    if int(cfg.get("timestamp", 0)):   # CifPredictorV3 upsample head (SURVEY.md Appendix B, config-3 extras)
+        out["predictor.upsample_cnn.weight"] = (D, D, int(cfg.get("us_times", 3)))
+        out["predictor.upsample_cnn.bias"] = (D,)
+        for sfx in ("", "_reverse"):
+            out["predictor.blstm.weight_ih_l0" + sfx] = (4 * D, D)
+            out["predictor.blstm.weight_hh_l0" + sfx] = (4 * D, D)
+            out["predictor.blstm.bias_ih_l0" + sfx] = (4 * D,)
+            out["predictor.blstm.bias_hh_l0" + sfx] = (4 * D,)
+        lin("predictor.cif_output2", 1, 2 * D)
+    dec_names = ["decoder.decoders.%d" % l for l in range(int(cfg["n_dec"]) - (1 if ctx else 0))]
+    if ctx:                            # ContextualParaformerDecoder + hotword compiler (model_eb)
+        dec_names.append("decoder.last_decoder")
+        ln("decoder.bias_decoder.norm3", D)
+        lin("decoder.bias_decoder.src_attn.linear_q", D, D)
+        lin("decoder.bias_decoder.src_attn.linear_k_v", 2 * D, D)
+        lin("decoder.bias_decoder.src_attn.linear_out", D, D)
+        out["decoder.bias_output.weight"] = (D, 2 * D, 1)
+        out["bias_embed.weight"] = (V, D)
+        out["bias_encoder.weight_ih_l0"] = (4 * D, D)
+        out["bias_encoder.weight_hh_l0"] = (4 * D, D)
+        out["bias_encoder.bias_ih_l0"] = (4 * D,)
+        out["bias_encoder.bias_hh_l0"] = (4 * D,)
+    for p in dec_names:
         ln(p + ".norm1", D)
         lin(p + ".feed_forward.w_1", Fd, D)
         ln(p + ".feed_forward.norm", Fd)
@@ -76,7 +99,11 @@ def make_weights(cfg=None, seed=0, jitter_ln=False):
             else:
                 W[name] = ((0.1 * rng.uniform(-1, 1, shp)) if jitter_ln else np.zeros(shp)).astype(np.float32)
             continue
-        if name.endswith(".weight"):
+        if name == "bias_embed.weight":      # nn.Embedding
+            W[name] = rng.uniform(-1, 1, shp).astype(np.float32)
+        elif "weight_ih_l0" in name or "weight_hh_l0" in name or "bias_ih_l0" in name or "bias_hh_l0" in name:
+            W[name] = rng.uniform(-1, 1, shp).astype(np.float32) / np.float32(math.sqrt(int(cfg["d_model"])))  # nn.LSTM: 1/sqrt(hidden)
+        elif name.endswith(".weight"):
             fan_in = int(np.prod(shp[1:]))
             W[name] = rng.uniform(-1, 1, shp).astype(np.float32) / np.float32(math.sqrt(fan_in))
         else:

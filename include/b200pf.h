@@ -39,7 +39,12 @@ typedef struct b200pf_config {
   int32_t sample_rate;     /* frontend_conf.fs of config.yaml (paraformer.cpp:188-190) */
   int32_t max_rows;        /* packed LFR rows (frames + one gap row per segment) one batch may hold */
   int32_t max_segments;
+  int32_t timestamp;       /* 1: the 4-output model (us_alphas, us_cif_peak; paraformer.cpp:549-563) */
+  int32_t contextual;      /* 1: the hotword model (bias_embed input, paraformer.cpp:515-531; model_eb, :592-693) */
 } b200pf_config;
+
+#define B200PF_MAX_HOTWORDS 4096  /* rows of the hotword embedding a batch may carry (incl. the blank row) */
+#define B200PF_HOTWORD_LEN 10     /* max_hotword_len, paraformer.cpp:600 */
 
 /* Per-batch results, written into caller-owned host buffers by b200pf_batch_collect.
  * Segment i produced token_counts[i] tokens; its ids are token_ids[token_offsets[i] .. +count).
@@ -54,6 +59,12 @@ typedef struct b200pf_result {
   int32_t* fire_frames;    /* [cap_tokens] may be NULL */
   int64_t cap_tokens;
   int64_t n_tokens;        /* out: total tokens written */
+  /* timestamp models only (all may be NULL): the two extra graph outputs, 3 * T_i values per segment starting at
+   * us_offsets[i] (paraformer.cpp:549-563 reads them per item; paraformer-torch.cpp:431-446 the batched form). */
+  float* us_alphas;        /* [cap_us] */
+  float* us_peaks;         /* [cap_us] */
+  int32_t* us_offsets;     /* [n_seg + 1] */
+  int64_t cap_us;
 } b200pf_result;
 
 const char* b200pf_last_error(void);
@@ -97,6 +108,15 @@ int64_t b200pf_rows_for(const int64_t* n_samples, int n_seg);
 
 int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** out);
 void b200pf_batch_destroy(b200pf_batch* b);
+
+/* Contextual models: the hotword embedding matrix Forward receives (hw_emb [n_hw][dim], model.h:31; the reference
+ * replicates it per batch item, paraformer-torch.cpp:373-388).  dim must be d_model; it stays attached to the batch
+ * until replaced.  A contextual model run without it fails like the reference ("hw_emb is null", paraformer.cpp:516-520). */
+int b200pf_batch_set_hotwords(b200pf_batch* b, const float* hw_emb, int n_hw, int dim);
+/* Replaces the model_eb.onnx session of Paraformer::CompileHotwordEmbedding (paraformer.cpp:651-688): Embedding +
+ * LSTM over ids [n_words][max_len] (int32, zero padded) and returns the LSTM output at step lengths[j]-1 of word j:
+ * out [n_words][d_model] fp32. */
+int b200pf_engine_hotword_embed(b200pf_engine* e, const int32_t* ids, const int32_t* lengths, int n_words, int max_len, float* out);
 
 /* Stage inputs (replaces the float copy + feature assembly of Paraformer::Forward, paraformer.cpp:482-532).
  * s16: `pcm` holds the segments back to back, segment i = pcm[offsets[i] .. offsets[i+1]) (the int16 the
@@ -147,6 +167,14 @@ int b200pf_op_fsmn(int device, const float* x, const float* w, const int32_t* se
  * Outputs: n_tok [n_seg], fires [rows], embeds [cap_tok,512], fire_frames [cap_tok]. */
 int b200pf_op_cif(int device, const float* alphas, const float* hidden, const int32_t* seg_off, int n_seg,
                   float threshold, int32_t* n_tok, float* fires, float* embeds, int32_t* fire_frames, int64_t cap_tok);
+/* LSTM (torch.nn.LSTM, one layer, hidden = input = 512, gate order i,f,g,o) over sequences x[seq_off[s] .. +seq_len[s]);
+ * n_dir = 2 adds the reverse direction; weights [n_dir][2048][512], biases [n_dir][2048]; out [rows][512 n_dir] fp32
+ * (bf16_out: the bf16 output path, widened). */
+int b200pf_op_lstm(int device, const float* x, int rows, const int32_t* seq_off, const int32_t* seq_len, int n_seq, int n_dir,
+                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int bf16_out, float* out);
+/* us_alphas / us_cif_peak from raw alpha2 (already relu(sigmoid*s-n)): per segment scale to n_tok and cif_wo_hidden. */
+int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, const int32_t* seq_len, const int32_t* n_tok,
+                       int n_seg, int rows, float threshold, float* us_alphas, float* us_peaks);
 /* fbank + LFR/CMVN of one segment (int16 PCM); fb_out [n_fb,80], feats_out [T,560] (either may be NULL). */
 int b200pf_op_frontend(b200pf_engine* e, const int16_t* pcm, int64_t n, float* fb_out, float* feats_out);
 

@@ -29,6 +29,17 @@ int b200pf_host_offline_infer_segments(void* h, const int16_t* pcm, int64_t n_sa
                                        int n_seg, char* text, int text_cap);
 /* funasr::Model::Forward(float**, int*, ...) (model.h:31) on the handle's ParaformerB200; strings joined by '\n'. */
 int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap);
+/* Same with the hw_emb argument of Forward: hw [n_hw][dim] (contextual models, paraformer.cpp:515-531). */
+int b200pf_host_model_forward_hw(void* h_offline, const float* const* din, const int* len, int n, const float* hw, int n_hw, int dim,
+                                 char* out, int cap);
+/* FunOfflineInferBuffer with hw_emb; also returns the stitched "[[b,e],...]" stamp string (funasrruntime.cpp:302-316). */
+int b200pf_host_offline_infer_buffer_hw(void* h, const char* buf, int n_bytes, int vad_max_len, const float* hw, int n_hw, int dim,
+                                        char* text, int text_cap, char* stamp, int stamp_cap);
+/* CompileHotwordEmbedding(handle, hotwords) (funasrruntime.h:118; Paraformer::CompileHotwordEmbedding, paraformer.cpp:592-693):
+ * writes rows of `dim` floats, returns the row count (hotwords kept + the blank row) or -1. */
+int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* out, int cap_rows, int dim);
+/* Model::InitSegDict (model.h:27; SegDict, seg_dict.cpp:19-38) for English hotwords. */
+int b200pf_host_init_seg_dict(void* h_offline, const char* path);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@ The arithmetic lives in a third-party dependency that is NOT under /root/referen
 FunASR export of `speech_paraformer-large_asr_nat-zh-cn-16k-common-vocab8404` rev v2.0.5
 (funasr==0.7.5, dj_py310_environment.yml:153; model ids websocket/bin/funasr-wss-server-2pass.cpp:45-58),
 run by onnxruntime 1.14.0 (websocket/onnxruntime-linux-x64-1.14.0/VERSION_NUMBER).  This file restates
-that published architecture (SANM encoder, CifPredictorV2, ParaformerSANMDecoder), batch 1, no padding,
+that published architecture (SANM encoder, CifPredictorV2, ParaformerSANMDecoder; for config 3 the
+CifPredictorV3 timestamp head, ContextualParaformerDecoder and the hotword Embedding+LSTM), batch 1, no padding,
 which is what ORT executes for the reference's B=1 call.
 
 PARITY UNPINNED for this file: the reference holds no golden vectors, tests or runnable model for the
@@ -45,6 +46,12 @@ class PfConfig:
     tail_threshold: float = 0.45   # paraformer.h:122
     pred_residual: int = 0     # 1: relu(conv(enc)+enc) (CifPredictor v1 / SURVEY a8); 0: relu(conv(enc)) (upstream CifPredictorV2)
     ln_eps: float = 1e-12
+    # config 3 (SURVEY.md §8(a) a15/a16, Appendix B "Config-3 extras"); both default off = the 2-output model
+    timestamp: int = 0         # 1: CifPredictorV3 upsample head -> us_alphas / us_cif_peak (4-output model, paraformer.cpp:549-563)
+    contextual: int = 0        # 1: ContextualParaformerDecoder (bias_embed input, paraformer.cpp:515-531) + hotword LSTM (model_eb)
+    us_times: int = 3          # upsample_times; TIME_RATE in util.cpp:851 encodes the x3
+    smooth_factor2: float = 0.25
+    noise_threshold2: float = 0.01
 
     def to_dict(self):
         return asdict(self)
@@ -78,8 +85,29 @@ def param_shapes(cfg: PfConfig):
     out["predictor.cif_conv1d.weight"] = (D, D, 3)
     out["predictor.cif_conv1d.bias"] = (D,)
     lin("predictor.cif_output", 1, D)
-    for l in range(cfg.n_dec):
-        p = f"decoder.decoders.{l}"
+    if cfg.timestamp:
+        out["predictor.upsample_cnn.weight"] = (D, D, cfg.us_times)     # ConvTranspose1d: [in, out, k], stride k
+        out["predictor.upsample_cnn.bias"] = (D,)
+        for sfx in ("", "_reverse"):
+            out["predictor.blstm.weight_ih_l0" + sfx] = (4 * D, D)
+            out["predictor.blstm.weight_hh_l0" + sfx] = (4 * D, D)
+            out["predictor.blstm.bias_ih_l0" + sfx] = (4 * D,)
+            out["predictor.blstm.bias_hh_l0" + sfx] = (4 * D,)
+        lin("predictor.cif_output2", 1, 2 * D)
+    dec_names = [f"decoder.decoders.{l}" for l in range(cfg.n_dec - (1 if cfg.contextual else 0))]
+    if cfg.contextual:
+        dec_names.append("decoder.last_decoder")
+        ln("decoder.bias_decoder.norm3", D)
+        lin("decoder.bias_decoder.src_attn.linear_q", D, D)
+        lin("decoder.bias_decoder.src_attn.linear_k_v", 2 * D, D)
+        lin("decoder.bias_decoder.src_attn.linear_out", D, D)
+        out["decoder.bias_output.weight"] = (D, 2 * D, 1)
+        out["bias_embed.weight"] = (V, D)
+        out["bias_encoder.weight_ih_l0"] = (4 * D, D)
+        out["bias_encoder.weight_hh_l0"] = (4 * D, D)
+        out["bias_encoder.bias_ih_l0"] = (4 * D,)
+        out["bias_encoder.bias_hh_l0"] = (4 * D,)
+    for p in dec_names:
         ln(p + ".norm1", D)
         lin(p + ".feed_forward.w_1", Fd, D)
         ln(p + ".feed_forward.norm", Fd)
@@ -228,9 +256,79 @@ def predictor(enc, W, cfg: PfConfig, emu=False):
     return emb, token_num, alpha_t, fires
 
 
-def decoder(emb, enc, token_num, W, cfg: PfConfig, emu=False, taps=None):
-    """ParaformerSANMDecoder.  emb [L,512], enc [T,512] -> logits [L,V]
-    (before log_softmax)."""
+def lstm(x, W, prefix, sfx="", reverse=False, emu=False):
+    """One direction of a single-layer torch.nn.LSTM (gate order i, f, g, o), literal recurrence.
+    x [T, I] -> h [T, H].  With emu the input projection, the hidden state fed back into the recurrence and the
+    output are rounded to bf16 where the CUDA path stores bf16; the cell state stays fp32."""
+    w_ih, w_hh = W[prefix + ".weight_ih_l0" + sfx], W[prefix + ".weight_hh_l0" + sfx]
+    b = W[prefix + ".bias_ih_l0" + sfx] + W[prefix + ".bias_hh_l0" + sfx]
+    H = w_hh.shape[1]
+    gx = _rb(_rb(x, emu) @ _rb(w_ih, emu).t() + b, emu)
+    whh_t = _rb(w_hh, emu).t()
+    h = torch.zeros(H)
+    c = torch.zeros(H)
+    out = torch.zeros(x.shape[0], H)
+    order = range(x.shape[0] - 1, -1, -1) if reverse else range(x.shape[0])
+    for t in order:
+        g = gx[t] + _rb(h, emu) @ whh_t
+        i, f, gg, o = g[:H], g[H:2 * H], g[2 * H:3 * H], g[3 * H:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[t] = h
+    return _rb(out, emu)
+
+
+def cif_wo_hidden(alphas, threshold):
+    """Upstream `cif_wo_hidden`: running sum, value recorded BEFORE the subtraction, subtract `threshold` on fire.
+    The consumer is TimestampOnnx (util.cpp:866-870: a peak is `> 1 - 1e-4`)."""
+    th = torch.tensor(threshold, dtype=torch.float32)
+    integrate = torch.zeros((), dtype=torch.float32)
+    fires = torch.zeros(alphas.shape[0], dtype=torch.float32)
+    for t in range(alphas.shape[0]):
+        integrate = integrate + alphas[t]
+        fires[t] = integrate
+        if bool(integrate >= th):
+            integrate = integrate - th
+    return fires
+
+
+def upsample_timestamp(enc, token_num, W, cfg: PfConfig, emu=False):
+    """CifPredictorV3.get_upsample_timestmap, upsample_type cnn_blstm, use_cif1_cnn false (SURVEY.md Appendix B
+    "Config-3 extras"; consumer contract util.cpp:838-870, paraformer.cpp:549-563).  enc [T,512] ->
+    us_alphas [3T], us_cif_peak [3T]."""
+    T, D = enc.shape
+    k = cfg.us_times
+    wt = _rb(W["predictor.upsample_cnn.weight"], emu)            # ConvTranspose1d weight [in, out, k], stride k
+    x = _rb(enc, emu)
+    up = torch.stack([x @ wt[:, :, j] for j in range(k)], 1) + W["predictor.upsample_cnn.bias"]   # [T, k, D]
+    up = _rb(up.reshape(T * k, D), emu)
+    hcat = torch.cat([lstm(up, W, "predictor.blstm", "", False, emu), lstm(up, W, "predictor.blstm", "_reverse", True, emu)], 1)
+    a2 = torch.sigmoid(hcat @ W["predictor.cif_output2.weight"].t() + W["predictor.cif_output2.bias"])[:, 0]
+    a2 = torch.relu(a2 * cfg.smooth_factor2 - cfg.noise_threshold2)
+    tok = a2.sum()
+    a2 = a2 * (torch.tensor(float(token_num), dtype=torch.float32) / tok)
+    peaks = cif_wo_hidden(a2, cfg.cif_threshold - 1e-4)
+    return a2, peaks
+
+
+def hotword_embed(ids, W, emu=False):
+    """model_eb.onnx (paraformer.cpp:592-693): hotword ids [N, 10] -> Embedding -> LSTM -> [10, N, 512]."""
+    ids = torch.as_tensor(ids, dtype=torch.long)
+    emb = W["bias_embed.weight"][ids]                                  # [N, 10, D]
+    out = torch.stack([lstm(emb[n], W, "bias_encoder", "", False, emu) for n in range(emb.shape[0])], 1)
+    return out                                                         # [10, N, D]
+
+
+def select_hotword_rows(hw_out, lengths):
+    """CompileHotwordEmbedding's pick of step len_j - 1 for word j (paraformer.cpp:676-682)."""
+    return torch.stack([hw_out[int(lengths[j]) - 1, j] for j in range(hw_out.shape[1])], 0)
+
+
+def decoder(emb, enc, token_num, W, cfg: PfConfig, emu=False, taps=None, hw_emb=None):
+    """ParaformerSANMDecoder; with cfg.contextual the ContextualParaformerDecoder
+    (a16: the last attention layer is `last_decoder`, its self-attention output attends over the hotword
+    embeddings through `bias_decoder`, and `bias_output` (1x1 conv over [x_src_attn ; cx]) replaces the
+    cross-attention residual).  emb [L,512], enc [T,512], hw_emb [N,512] -> logits [L,V] (before log_softmax)."""
     D, H = cfg.d_model, cfg.n_heads
     L = emb.shape[0]
     scale = (D // H) ** -0.5
@@ -243,19 +341,34 @@ def decoder(emb, enc, token_num, W, cfg: PfConfig, emu=False, taps=None):
         f1 = _ln(_rb(f1, emu), W, p + ".feed_forward.norm", cfg.ln_eps)
         return _lin(f1, W, p + ".feed_forward.w_2", emu, bias=False)
 
-    for l in range(cfg.n_dec):
-        p = f"decoder.decoders.{l}"
-        r = y
+    def self_block(y, p):
         t = ffn(_ln(y, W, p + ".norm1", cfg.ln_eps), p)
         t2 = _rb(_ln(t, W, p + ".norm2", cfg.ln_eps), emu) * tmask
         m = _fsmn(t2, W[p + ".self_attn.fsmn_block.weight"], cfg.kernel) * tmask
-        y = r + m
-        q = _rb(_lin(_ln(y, W, p + ".norm3", cfg.ln_eps), W, p + ".src_attn.linear_q", emu), emu)
-        kv = _rb(_lin(memory, W, p + ".src_attn.linear_k_v", emu), emu)
+        return y + m
+
+    def cross(y, p_norm, p_att, mem):
+        q = _rb(_lin(_ln(y, W, p_norm, cfg.ln_eps), W, p_att + ".linear_q", emu), emu)
+        kv = _rb(_lin(mem, W, p_att + ".linear_k_v", emu), emu)
         att = _rb(_mha_scaled(q, kv[:, :D], kv[:, D:], H, scale, emu), emu)
-        y = y + _lin(att, W, p + ".src_attn.linear_out", emu)
+        return _lin(att, W, p_att + ".linear_out", emu)
+
+    n_plain = cfg.n_dec - (1 if cfg.contextual else 0)
+    for l in range(n_plain):
+        p = f"decoder.decoders.{l}"
+        y = self_block(y, p)
+        y = y + cross(y, p + ".norm3", p + ".src_attn", memory)
         if taps is not None and l == 0:
             taps["dec_l0"] = y.clone()
+    if cfg.contextual:
+        p = "decoder.last_decoder"
+        x_self = self_block(y, p)
+        x_src = cross(x_self, p + ".norm3", p + ".src_attn", memory)
+        cx = cross(x_self, "decoder.bias_decoder.norm3", "decoder.bias_decoder.src_attn", _rb(torch.as_tensor(hw_emb, dtype=torch.float32), emu))
+        cat = _rb(torch.cat([x_src, cx], 1), emu)
+        y = x_self + cat @ _rb(W["decoder.bias_output.weight"][:, :, 0], emu).t()
+        if taps is not None:
+            taps["dec_ctx"] = y.clone()
     p = "decoder.decoders3.0"
     y = ffn(_ln(y, W, p + ".norm1", cfg.ln_eps), p)
     y = _ln(y, W, "decoder.after_norm", cfg.ln_eps)
@@ -266,20 +379,23 @@ def decoder(emb, enc, token_num, W, cfg: PfConfig, emu=False, taps=None):
 
 
 @torch.no_grad()
-def forward(feats, W, cfg: PfConfig, emulate_bf16=False, want_taps=True):
+def forward(feats, W, cfg: PfConfig, emulate_bf16=False, want_taps=True, hw_emb=None):
     """feats: float32 [T,560] (numpy or tensor).  Returns dict of taps:
     enc [T,512], alphas [T+1], fires [T+1], embeds [L,512], token_num, logits [L,V] (raw),
-    logprobs [L,V] (= what the reference graph outputs), ids (FindMax over the first token_num rows)."""
+    logprobs [L,V] (= what the reference graph outputs), ids (FindMax over the first token_num rows);
+    with cfg.timestamp also us_alphas [3T], us_peaks [3T]; cfg.contextual needs hw_emb [N,512]."""
     feats = torch.as_tensor(feats, dtype=torch.float32)
     taps = {} if want_taps else None
     enc = encoder(feats, W, cfg, emulate_bf16, taps)
     emb, token_num, alphas, fires = predictor(enc, W, cfg, emulate_bf16)
     out = dict(taps or {})
     out.update(enc=enc, alphas=alphas, fires=fires, embeds=emb, token_num=token_num)
+    if cfg.timestamp:
+        out["us_alphas"], out["us_peaks"] = upsample_timestamp(enc, token_num, W, cfg, emulate_bf16)
     if emb.shape[0] == 0:
         out.update(logits=torch.zeros(0, cfg.vocab), logprobs=torch.zeros(0, cfg.vocab), ids=[])
         return out
-    logits = decoder(emb, enc, token_num, W, cfg, emulate_bf16, taps)
+    logits = decoder(emb, enc, token_num, W, cfg, emulate_bf16, taps, hw_emb)
     if taps:
         out.update(taps)
     out["logits"] = logits
