@@ -78,7 +78,7 @@ def cpu_baseline(synth, cfg, W, means, vars_, seg_pcm16, budget_s=20.0, procs=No
     from oracle import paraformer_ref as R
     F.lib()
     P = procs or min(os.cpu_count() or 1, 32)
-    pc = R.PfConfig(**{k: (float(v) if k in ("cif_threshold", "tail_threshold", "ln_eps") else int(v)) for k, v in cfg.items()})
+    pc = R.PfConfig.from_dict(cfg)
     _CPU.update(W={k: torch.from_numpy(v) for k, v in W.items()}, pc=pc, means=means, vars=vars_)
     # probe one segment to size the sample to ~budget_s of work per worker
     probe = seg_pcm16[len(seg_pcm16) // 2].astype(np.float32) / np.float32(32768)

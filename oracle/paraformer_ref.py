@@ -56,6 +56,12 @@ class PfConfig:
     def to_dict(self):
         return asdict(self)
 
+    @classmethod
+    def from_dict(cls, d):
+        """Build from a model-file config dict (values arrive as floats); unknown keys are ignored."""
+        f = cls.__dataclass_fields__
+        return cls(**{k: (float(v) if isinstance(f[k].default, float) else int(v)) for k, v in d.items() if k in f})
+
 
 def param_shapes(cfg: PfConfig):
     """name -> shape, in upstream FunASR state_dict naming."""

@@ -70,7 +70,7 @@ def main():
     import torch
     from oracle import paraformer_ref as R
     cfg, W = synth.make_weights(dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
-    pc = R.PfConfig(**{k: (float(v) if k in ("cif_threshold", "tail_threshold", "ln_eps") else int(v)) for k, v in cfg.items()})
+    pc = R.PfConfig.from_dict(cfg)
     Wt = {k: torch.from_numpy(v) for k, v in W.items()}
     m = {}
     for n in (16000, 52800):
@@ -86,6 +86,32 @@ def main():
         top2 = np.sort(lg, axis=1)[:, -2:]
         m["top_gap_%d" % n] = (top2[:, 1] - top2[:, 0]).astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "model_small_golden.npz"), **m)
+
+    # config 3 (timestamp head + contextual decoder + hotword compiler), same small architecture, fp32 oracle
+    cfg, W = synth.make_weights(dict(n_enc=2, n_dec=2, timestamp=1, contextual=1), seed=3, jitter_ln=True)
+    pc = R.PfConfig.from_dict(cfg)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    rng = np.random.default_rng(77)
+    hw_ids = np.zeros((9, 10), np.int32)
+    hw_len = np.zeros(9, np.int32)
+    for j in range(8):
+        L = int(rng.integers(1, 8))
+        hw_ids[j, :L] = rng.integers(3, pc.vocab - 1, L)
+        hw_len[j] = L
+    hw_ids[8, 0], hw_len[8] = 1, 1
+    hw = R.select_hotword_rows(R.hotword_embed(hw_ids, Wt), hw_len)
+    c3 = dict(hw_ids=hw_ids, hw_len=hw_len, hw_emb=hw.numpy())
+    for n in (16000, 52800):
+        feats = F.lfr_cmvn(g["fbank_%d" % n], means, vars_)
+        o = R.forward(feats, Wt, pc, hw_emb=hw)
+        c3["us_alphas_%d" % n] = o["us_alphas"].numpy()
+        c3["us_peaks_%d" % n] = o["us_peaks"].numpy()
+        c3["ids_%d" % n] = np.asarray(o["ids"], np.int32)
+        c3["token_num_%d" % n] = np.asarray([o["token_num"]], np.int32)
+        lg = o["logits"].numpy()
+        top2 = np.sort(lg, axis=1)[:, -2:]
+        c3["top_gap_%d" % n] = (top2[:, 1] - top2[:, 0]).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "model_cfg3_golden.npz"), **c3)
     print("wrote", os.listdir(HERE))
 
 

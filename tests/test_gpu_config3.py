@@ -99,8 +99,7 @@ def cfg3(capi, synth, gpu, tmp_path_factory):
     import torch
     d = str(tmp_path_factory.mktemp("cfg3"))
     cfg, W, means, vars_, toks = synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2, timestamp=1, contextual=1), seed=3, jitter_ln=True)
-    keys = R.PfConfig.__dataclass_fields__.keys()
-    pc = R.PfConfig(**{k: (float(v) if isinstance(R.PfConfig.__dataclass_fields__[k].default, float) else int(v)) for k, v in cfg.items() if k in keys})
+    pc = R.PfConfig.from_dict(cfg)
     eng = capi.Engine(d, max_rows=2048, max_segments=64)
     eng.set_option("taps", 1)
     return dict(dir=d, eng=eng, W={k: torch.from_numpy(v) for k, v in W.items()}, pc=pc, means=means, vars=vars_, toks=toks)
@@ -203,6 +202,27 @@ def test_forward_config3_small_model(capi, synth, cfg3):
             gap = top2[:, 1] - top2[:, 0]
             for j, (a, c) in enumerate(zip(ids, o["ids"])):
                 assert a == c or gap[j] < 0.15, (i, j, gap[j])
+
+
+def test_config3_against_committed_golden(capi, cfg3):
+    """Committed fixtures (tests/golden/model_cfg3_golden.npz, made by make_golden.py from the fp32 oracle)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = np.load(os.path.join(root, "tests", "golden", "frontend_golden.npz"))
+    c3 = np.load(os.path.join(root, "tests", "golden", "model_cfg3_golden.npz"))
+    hw = cfg3["eng"].hotword_embed(c3["hw_ids"], c3["hw_len"])
+    assert np.abs(hw - c3["hw_emb"]).max() <= 4e-2
+    for n in (16000, 52800):
+        pcm = g["pcm_%d" % n]
+        b = capi.Batch(cfg3["eng"], len(pcm) + 16)
+        b.set_hotwords(c3["hw_emb"])
+        res = b.forward_s16(pcm, np.array([0, len(pcm)], np.int64))
+        assert abs(int(res["token_counts"][0]) - int(c3["token_num_%d" % n][0])) <= 1
+        if res["token_counts"][0] == c3["token_num_%d" % n][0]:
+            assert rel(res["us_alphas"], c3["us_alphas_%d" % n]) <= 3e-2
+            assert abs(len(_peaks(res["us_peaks"])) - len(_peaks(c3["us_peaks_%d" % n]))) <= 1
+            ids = res["token_ids"]
+            bad = [(j, c3["top_gap_%d" % n][j]) for j in range(len(ids)) if ids[j] != c3["ids_%d" % n][j]]
+            assert all(gap < 0.15 for _, gap in bad), bad
 
 
 def test_hotwords_change_the_logits_and_batch_invariance(capi, synth, cfg3):

@@ -181,7 +181,7 @@ def small(capi, synth, gpu, tmp_path_factory):
     import torch
     d = str(tmp_path_factory.mktemp("small"))
     cfg, W, means, vars_, toks = synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
-    pc = R.PfConfig(**{k: (float(v) if k in ("cif_threshold", "tail_threshold", "ln_eps") else int(v)) for k, v in cfg.items()})
+    pc = R.PfConfig.from_dict(cfg)
     eng = capi.Engine(d, max_rows=2048, max_segments=64)
     eng.set_option("taps", 1)
     return dict(eng=eng, W={k: torch.from_numpy(v) for k, v in W.items()}, pc=pc, means=means, vars=vars_, toks=toks)

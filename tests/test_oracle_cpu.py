@@ -87,7 +87,7 @@ def test_model_oracle_reproduces_committed_taps(gold, synth):
     from oracle import paraformer_ref as R
     mg = np.load(os.path.join(GOLD, "model_small_golden.npz"))
     cfg, W = synth.make_weights(dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
-    pc = R.PfConfig(**{k: (float(v) if k in ("cif_threshold", "tail_threshold", "ln_eps") else int(v)) for k, v in cfg.items()})
+    pc = R.PfConfig.from_dict(cfg)
     Wt = {k: torch.from_numpy(v) for k, v in W.items()}
     means, vars_ = synth.make_cmvn()
     for n in (16000, 52800):
@@ -99,6 +99,76 @@ def test_model_oracle_reproduces_committed_taps(gold, synth):
         gap = mg["top_gap_%d" % n]
         ids = np.asarray(o["ids"])
         assert np.all((ids == mg["ids_%d" % n]) | (gap < 1e-4))
+
+
+def test_config3_oracle_reproduces_committed_taps(gold, synth):
+    import torch
+    from oracle import paraformer_ref as R
+    c3 = np.load(os.path.join(GOLD, "model_cfg3_golden.npz"))
+    cfg, W = synth.make_weights(dict(n_enc=2, n_dec=2, timestamp=1, contextual=1), seed=3, jitter_ln=True)
+    pc = R.PfConfig.from_dict(cfg)
+    assert pc.timestamp == 1 and pc.contextual == 1 and pc.smooth_factor2 == 0.25
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    hw = R.select_hotword_rows(R.hotword_embed(c3["hw_ids"], Wt), c3["hw_len"])
+    np.testing.assert_allclose(hw.numpy(), c3["hw_emb"], atol=1e-5)
+    means, vars_ = synth.make_cmvn()
+    n = 16000
+    o = R.forward(F.lfr_cmvn(gold["fbank_%d" % n], means, vars_), Wt, pc, hw_emb=hw)
+    assert o["token_num"] == int(c3["token_num_%d" % n][0])
+    np.testing.assert_allclose(o["us_alphas"].numpy(), c3["us_alphas_%d" % n], atol=1e-5)
+    assert np.array_equal(np.where(o["us_peaks"].numpy() > 1 - 1e-4)[0], np.where(c3["us_peaks_%d" % n] > 1 - 1e-4)[0])
+    ids = np.asarray(o["ids"])
+    assert np.all((ids == c3["ids_%d" % n]) | (c3["top_gap_%d" % n] < 1e-4))
+
+
+def test_lstm_restatement_equals_torch_nn_lstm():
+    """The literal recurrence in the oracle (gate order i,f,g,o, both directions) against torch.nn.LSTM itself."""
+    import torch
+    from oracle import paraformer_ref as R
+    torch.manual_seed(1)
+    m = torch.nn.LSTM(512, 512, 1, batch_first=True, bidirectional=True)
+    W = {"p." + k: v.detach() for k, v in m.state_dict().items()}
+    x = torch.randn(29, 512)
+    with torch.no_grad():
+        ref, _ = m(x[None])
+    got = torch.cat([R.lstm(x, W, "p", "", False), R.lstm(x, W, "p", "_reverse", True)], 1)
+    assert float((got - ref[0]).abs().max()) <= 2e-6
+
+
+def test_upsample_restatement_equals_conv_transpose1d(synth):
+    """ConvTranspose1d(512,512,k=3,stride=3) written as three matmuls == torch's own op; cif_wo_hidden closed form."""
+    import torch
+    from oracle import paraformer_ref as R
+    torch.manual_seed(2)
+    ct = torch.nn.ConvTranspose1d(512, 512, 3, 3)
+    enc = torch.randn(11, 512)
+    with torch.no_grad():
+        ref = ct(enc.t()[None])[0].t()                                   # [33, 512]
+    wt, b = ct.weight.detach(), ct.bias.detach()
+    up = (torch.stack([enc @ wt[:, :, j] for j in range(3)], 1) + b).reshape(33, 512)
+    assert float((up - ref).abs().max()) <= 1e-5
+    fires = R.cif_wo_hidden(torch.full((12,), 0.25), 1.0 - 1e-4)
+    # running sum 0.25, 0.5, 0.75, 1.0 (fire, minus 0.9999) ...
+    assert np.array_equal(np.where(fires.numpy() > 1 - 1e-4)[0], [3, 7, 11])
+    assert abs(float(fires[4]) - (0.25 + 1e-4)) < 1e-6
+
+
+def test_contextual_decoder_reduces_to_self_attention_path_when_bias_output_is_zero(synth):
+    """With bias_output = 0 the last layer contributes only x_self_attn, whatever the hotwords are."""
+    import torch
+    from oracle import paraformer_ref as R
+    cfg, W = synth.make_weights(dict(n_enc=1, n_dec=2, contextual=1, vocab=64), seed=5)
+    pc = R.PfConfig.from_dict(cfg)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    Wt["decoder.bias_output.weight"] = torch.zeros_like(Wt["decoder.bias_output.weight"])
+    torch.manual_seed(0)
+    emb, enc = torch.randn(7, 512), torch.randn(19, 512)
+    a = R.decoder(emb, enc, 7, Wt, pc, hw_emb=torch.randn(5, 512))
+    b = R.decoder(emb, enc, 7, Wt, pc, hw_emb=torch.randn(3, 512) * 9)
+    assert torch.equal(a, b)
+    Wt["decoder.bias_output.weight"] = torch.from_numpy(W["decoder.bias_output.weight"])
+    c = R.decoder(emb, enc, 7, Wt, pc, hw_emb=torch.randn(5, 512))
+    assert not torch.equal(a, c)
 
 
 def test_cif_matches_closed_form():

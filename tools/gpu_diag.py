@@ -209,7 +209,7 @@ def _e2e(capi, cfg_over, seg_secs, max_rows):
     from oracle import paraformer_ref as R
     tmp = tempfile.mkdtemp()
     synth, cfg, W, means, vars_, toks = _model(tmp, cfg_over)
-    pc = R.PfConfig(**{k: (float(v) if k in ("cif_threshold", "tail_threshold", "ln_eps") else int(v)) for k, v in cfg.items()})
+    pc = R.PfConfig.from_dict(cfg)
     Wt = {k: torch.from_numpy(v) for k, v in W.items()}
     eng = capi.Engine(tmp, max_rows=max_rows, max_segments=64)
     eng.set_option("taps", 1)
