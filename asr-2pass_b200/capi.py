@@ -116,7 +116,9 @@ _host = None
 HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf_host_detok_text", "b200pf_host_timestamp_text",
                 "b200pf_host_stitch", "b200pf_host_offline_init", "b200pf_host_offline_uninit", "b200pf_host_offline_infer_buffer",
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
-                "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw"]
+                "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
+                "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
+                "b200pf_host_mb_stats"]
 
 
 def host_lib():
@@ -147,6 +149,14 @@ def host_lib():
     H.b200pf_host_model_forward_hw.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_offline_infer_buffer_hw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p,
                                                       C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    H.b200pf_host_mb_create.restype = C.c_void_p
+    H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    H.b200pf_host_mb_create_mock.restype = C.c_void_p
+    H.b200pf_host_mb_destroy.argtypes = [C.c_void_p]
+    H.b200pf_host_mb_destroy.restype = None
+    H.b200pf_host_mb_forward.argtypes = [C.c_void_p, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_mb_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _host = H
     return H
 
@@ -265,6 +275,48 @@ class OfflineHandle:
         if n < 0:
             raise B200PFError("FunOfflineInferBuffer returned nullptr")
         return t.value.decode("utf-8"), st.value.decode("utf-8")
+
+
+class MicroBatcher:
+    """funasr_b200::MicroBatcher through its C hooks: merges concurrent batch-1 Forward calls (the 2-pass offline leg,
+    funasrruntime.cpp:570-586) into batched forwards.  offline=None builds the host-only mock model (tests)."""
+
+    def __init__(self, offline=None, max_wait_us=20000, max_batch=256, max_rows=32768, mock_latency_us=0):
+        self._offline = offline
+        if offline is None:
+            self.h = host_lib().b200pf_host_mb_create_mock(max_wait_us, max_batch, max_rows, mock_latency_us)
+        else:
+            self.h = host_lib().b200pf_host_mb_create(offline.h, max_wait_us, max_batch, max_rows)
+        if not self.h:
+            raise B200PFError("MicroBatcher creation failed")
+
+    def close(self):
+        if self.h:
+            host_lib().b200pf_host_mb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def forward(self, pcm_f32, hw_emb=None):
+        """Blocking batch-1 call of one connection; returns the result string."""
+        x = np.ascontiguousarray(pcm_f32, dtype=np.float32)
+        buf = C.create_string_buffer(1 << 16)
+        if hw_emb is None:
+            host_lib().b200pf_host_mb_forward(self.h, _p(x), len(x), None, 0, 0, buf, len(buf))
+        else:
+            hw = np.ascontiguousarray(hw_emb, dtype=np.float32)
+            host_lib().b200pf_host_mb_forward(self.h, _p(x), len(x), _p(hw), hw.shape[0], hw.shape[1], buf, len(buf))
+        return buf.value.decode("utf-8")
+
+    def stats(self):
+        out = (C.c_double * 7)()
+        host_lib().b200pf_host_mb_stats(self.h, out)
+        keys = ("segments", "batches", "closed_by_deadline", "closed_by_size", "max_batch_seen", "mean_wait_us", "max_wait_us")
+        return dict(zip(keys, [float(v) for v in out]))
 
 
 def _check(rc):

@@ -4,7 +4,11 @@
 #include <cstring>
 
 #include "../../../include/b200pf_host.h"
+#include <chrono>
+#include <thread>
+
 #include "funasrruntime_b200.h"
+#include "micro_batcher.h"
 #include "paraformer_b200.h"
 
 namespace {
@@ -130,6 +134,52 @@ int b200pf_host_model_forward(void* h_offline, const float* const* din, const in
   std::string joined;
   for (int i = 0; i < n; ++i) { if (i) joined += "\n"; joined += r[i]; }
   return CopyOut(joined, out, cap);
+}
+
+
+// ---- MicroBatcher ------------------------------------------------------------
+// Mock inner model for host-only tests: "n=<len>;b=<batch size>;x=<first sample>;hw=<rows of hw_emb>", after
+// sleeping latency_us once per batch (a stand-in for the GPU forward).
+void* b200pf_host_mb_create_mock(int max_wait_us, int max_batch, int max_rows, int latency_us) {
+  funasr_b200::MicroBatcherOptions o;
+  o.max_wait_us = max_wait_us; o.max_batch = max_batch; o.max_rows = max_rows;
+  return new funasr_b200::MicroBatcher(
+      [latency_us](float** din, int* len, int n, const std::vector<std::vector<float>>& hw) {
+        if (latency_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(latency_us));
+        std::vector<std::string> out(n);
+        for (int i = 0; i < n; ++i) {
+          if (i > 0 && len[i] < len[i - 1]) { out[i] = "unsorted"; continue; }
+          out[i] = "n=" + std::to_string(len[i]) + ";b=" + std::to_string(n) + ";x=" + std::to_string(len[i] > 0 ? (int)din[i][0] : 0) +
+                   ";hw=" + std::to_string(hw.size());
+        }
+        return out;
+      },
+      o);
+}
+void* b200pf_host_mb_create(void* h_offline, int max_wait_us, int max_batch, int max_rows) {
+  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  if (!m) return nullptr;
+  funasr_b200::MicroBatcherOptions o;
+  o.max_wait_us = max_wait_us; o.max_batch = max_batch; o.max_rows = max_rows;
+  return new funasr_b200::MicroBatcher(m, o);
+}
+void b200pf_host_mb_destroy(void* mb) { delete (funasr_b200::MicroBatcher*)mb; }
+// One connection's batch-1 call: Model::Forward(buff, len, true, hw_emb, dec_handle, 1) (funasrruntime.cpp:570-586).
+int b200pf_host_mb_forward(void* mb, const float* pcm, int len, const float* hw, int n_hw, int dim, char* out, int cap) {
+  std::vector<std::vector<float>> emb;
+  for (int j = 0; j < n_hw; ++j) emb.emplace_back(hw + (size_t)j * dim, hw + (size_t)(j + 1) * dim);
+  if (n_hw == 0) emb.assign(1, std::vector<float>(1, 0.0f));  // the reference's default argument {{0.0}}
+  float* one[1] = {const_cast<float*>(pcm)};
+  int l[1] = {len};
+  std::vector<std::string> r = ((funasr_b200::MicroBatcher*)mb)->Forward(one, l, true, emb, nullptr, 1);
+  return CopyOut(r.empty() ? std::string() : r[0], out, cap);
+}
+// segments, batches, closed_by_deadline, closed_by_size, max_batch_seen, mean wait us, max wait us
+int b200pf_host_mb_stats(void* mb, double* out7) {
+  const funasr_b200::MicroBatcherStats s = ((funasr_b200::MicroBatcher*)mb)->stats();
+  out7[0] = (double)s.segments; out7[1] = (double)s.batches; out7[2] = (double)s.closed_by_deadline; out7[3] = (double)s.closed_by_size;
+  out7[4] = (double)s.max_batch_seen; out7[5] = s.segments ? s.wait_us_sum / (double)s.segments : 0.0; out7[6] = s.wait_us_max;
+  return 0;
 }
 
 }  // extern "C"

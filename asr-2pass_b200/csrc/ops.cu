@@ -54,6 +54,16 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* in, float* out, int64_t 
     out[i] = __bfloat162float(in[i]);
 }
 
+// pseudo-random bf16 in about [-1, 1): the micro-benchmark must toggle the tensor-core datapath like real activations do
+// (constant operands draw far less power and flatter the clock, hence the TFLOP/s)
+__global__ void fill_random_bf16_kernel(__nv_bfloat16* out, int64_t n, uint32_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    out[i] = __float2bfloat16(((float)(x >> 8) * (1.0f / 8388608.0f)) - 1.0f);
+  }
+}
+
 int sync_ok(const char* what) { return check_cuda(cudaDeviceSynchronize(), what); }
 
 int sm_count() { int n = 148, d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }
@@ -104,9 +114,15 @@ int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, f
   DevBuf dA, dW, dBias, dAdd, dX, dOutB, dAm;
   RC(dA.alloc((size_t)M * K * 2)); RC(dW.alloc((size_t)N * K * 2)); RC(dBias.alloc((size_t)N * 4));
   RC(dAdd.alloc((size_t)M * N * 2)); RC(dX.alloc((size_t)M * N * 4)); RC(dOutB.alloc((size_t)M * N * 2)); RC(dAm.alloc((size_t)M * 8));
-  // 0x3c3c... is bf16 0.0115, a harmless finite pattern
-  RC(check_cuda(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2), "memset")); RC(check_cuda(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2), "memset"));
-  RC(check_cuda(cudaMemset(dBias.p, 0, (size_t)N * 4), "memset")); RC(check_cuda(cudaMemset(dAdd.p, 0x3c, (size_t)M * N * 2), "memset"));
+  if (getenv("B200PF_GEMM_CONST")) {  // 0x3c3c... is bf16 0.0115: constant operands, for comparison only
+    RC(check_cuda(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2), "memset")); RC(check_cuda(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2), "memset"));
+    RC(check_cuda(cudaMemset(dAdd.p, 0x3c, (size_t)M * N * 2), "memset"));
+  } else {
+    fill_random_bf16_kernel<<<1024, 256>>>(dA.as<__nv_bfloat16>(), (int64_t)M * K, 1u);
+    fill_random_bf16_kernel<<<1024, 256>>>(dW.as<__nv_bfloat16>(), (int64_t)N * K, 2u);
+    fill_random_bf16_kernel<<<1024, 256>>>(dAdd.as<__nv_bfloat16>(), (int64_t)M * N, 3u);
+  }
+  RC(check_cuda(cudaMemset(dBias.p, 0, (size_t)N * 4), "memset"));
   RC(check_cuda(cudaMemset(dX.p, 0, (size_t)M * N * 4), "memset")); RC(check_cuda(cudaMemset(dAm.p, 0, (size_t)M * 8), "memset"));
   GemmProblem p;
   p.A = dA.as<__nv_bfloat16>(); p.lda = K; p.rows_a = M; p.W = dW.as<__nv_bfloat16>(); p.ldw = K; p.M = M; p.N = N; p.K = K;

@@ -41,6 +41,16 @@ int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* o
 /* Model::InitSegDict (model.h:27; SegDict, seg_dict.cpp:19-38) for English hotwords. */
 int b200pf_host_init_seg_dict(void* h_offline, const char* path);
 
+/* MicroBatcher (asr-2pass_b200/csrc/host/micro_batcher.h): merges the batch-1 Forward calls that the 2-pass server makes
+ * per closed VAD segment (funasrruntime.cpp:570-586) across connections into batched forwards.  `mock` variant: host-only
+ * inner model for tests.  forward blocks until the segment is decoded; hw may be NULL (n_hw 0). */
+void* b200pf_host_mb_create(void* h_offline, int max_wait_us, int max_batch, int max_rows);
+void* b200pf_host_mb_create_mock(int max_wait_us, int max_batch, int max_rows, int latency_us);
+void b200pf_host_mb_destroy(void* mb);
+int b200pf_host_mb_forward(void* mb, const float* pcm, int len, const float* hw, int n_hw, int dim, char* out, int cap);
+/* out7: segments, batches, closed_by_deadline, closed_by_size, max_batch_seen, mean wait us, max wait us */
+int b200pf_host_mb_stats(void* mb, double* out7);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,3 +361,32 @@ def test_max_length_segment_full_size_properties(capi, synth, small):
     assert np.all((res["token_ids"] >= 0) & (res["token_ids"] < 8404))
     emb = b.tap("embeds", 0)
     assert emb.shape == (L, 512) and np.isfinite(emb).all()
+
+
+def test_microbatcher_results_equal_direct_calls(capi, synth, small, tmp_path_factory):
+    """batch-1 Forward calls of many connections merged into batched forwards give, per
+    segment, exactly the string a direct call gives (the engine is batch invariant)."""
+    import threading
+    d = str(tmp_path_factory.mktemp("mb"))
+    synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    h = capi.OfflineHandle(d, max_rows=4096, max_segments=64, batch_size=64)
+    segs = [synth.make_audio(int(n), 4000 + i).astype(np.float32) / np.float32(32768)
+            for i, n in enumerate([16000, 52800, 33000, 8000, 120000, 20000, 64000, 300, 48000, 25000, 90000, 16000])]
+    direct = [h.model_forward([s])[0] for s in segs]
+    mb = capi.MicroBatcher(h, max_wait_us=30000, max_batch=64, max_rows=4096)
+    out = [None] * len(segs)
+
+    def call(i):
+        out[i] = mb.forward(segs[i])
+
+    th = [threading.Thread(target=call, args=(i,)) for i in range(len(segs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out == direct
+    assert out[7] == ""                                            # too short -> "" also through the batcher
+    st = mb.stats()
+    assert st["segments"] == len(segs) and st["batches"] <= 3 and st["max_batch_seen"] >= 4
+    mb.close()
+    h.close()
