@@ -52,7 +52,7 @@ EXPORTS = [
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
-    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench",
 ]
 
 
@@ -540,6 +540,13 @@ def op_lstm(x, seq_off, seq_len, w_ih, w_hh, b_ih, b_hh, bf16_out=False, device=
     _check(lib().b200pf_op_lstm(device, _p(x), x.shape[0], _p(so, c_i32p), _p(sl, c_i32p), len(so), n_dir, _p(w_ih), _p(w_hh),
                                 _p(b_ih), _p(b_hh), int(bf16_out), _p(out)))
     return out
+
+
+def op_lstm_bench(n_seq, length, n_dir=1, iters=3, device=0):
+    ms = C.c_float()
+    mc = C.c_int()
+    _check(lib().b200pf_op_lstm_bench(device, n_seq, length, n_dir, iters, C.byref(ms), C.byref(mc)))
+    return ms.value, mc.value
 
 
 def op_us_peaks(alpha2, seq_off, seq_len, n_tok, threshold, device=0):

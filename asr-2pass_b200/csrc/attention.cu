@@ -47,6 +47,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ONLINE = single pass over the keys with a running row maximum (flash-attention style): S_j -> P_j -> O += P_j V_j per key
+// block, no separate maximum pass, so a CTA makes half as many dependent TMA -> MMA -> softmax round trips (the kernel is
+// latency bound at this path's 30-340-key segments).  The maximum the exponentials are taken against ("m_used") is only
+// advanced when the true running maximum has moved by more than 8 in the log2 domain; then, and only then, O (TMEM) and
+// l are rescaled by 2^(m_used_old - m_used_new).  Probabilities therefore stay <= 2^8 and the normalised result O / l
+// is the same softmax(S) V up to rounding.  ONLINE = false is the exact two-pass variant described at the top.
+template <bool ONLINE>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AArgs a) {
   pdl_wait();   // q_len of the decoder is produced by the CIF kernels
@@ -106,11 +113,12 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_arrive_expect_tx(q_full, Q_BYTES);
       tma_load_2d(sQ, &tmQ, q_full, a.q_col0 + h * HD, q_row);
       tma_load_2d(sQ + Q_BYTES / 2, &tmQ, q_full, a.q_col0 + h * HD + 64, q_row);
-      for (int it = 0; it < 2 * nb; ++it) {
+      const int n_it = ONLINE ? nb : 2 * nb;
+      for (int it = 0; it < n_it; ++it) {
         const int stage = it % KV_STAGES;
         const uint32_t phase = (it / KV_STAGES) & 1;
-        const bool pass2 = it >= nb;
-        const int j = pass2 ? it - nb : it;
+        const bool pass2 = ONLINE || it >= nb;
+        const int j = (!ONLINE && pass2) ? it - nb : it;
         mbar_wait(&kv_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&kv_full[stage], pass2 ? STAGE_BYTES : K_BYTES);
         uint8_t* dst = sKV + stage * STAGE_BYTES;
@@ -146,15 +154,18 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         umma_commit(&s_full[sb]);
       };
-      // pass 1: row maxima only
-      for (int it = 0; it < nb; ++it) {
-        issue_s(it);
-        umma_commit(&kv_empty[it % KV_STAGES]);
+      const int it0 = ONLINE ? 0 : nb;
+      if (!ONLINE) {
+        // pass 1: row maxima only
+        for (int it = 0; it < nb; ++it) {
+          issue_s(it);
+          umma_commit(&kv_empty[it % KV_STAGES]);
+        }
       }
-      // pass 2: S of block j+1 is issued before P V of block j so the tensor pipe overlaps the softmax
-      issue_s(nb);
+      // (pass 2) S of block j+1 is issued before P V of block j so the tensor pipe overlaps the softmax
+      issue_s(it0);
       for (int jj = 0; jj < nb; ++jj) {
-        const int it = nb + jj;
+        const int it = it0 + jj;
         if (jj + 1 < nb) issue_s(it + 1);
         const int pb = jj % P_BUFS;
         mbar_wait(&p_full[pb], (jj / P_BUFS) & 1);
@@ -180,6 +191,80 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     float m = -INFINITY;
     uint32_t r[32];
+    float l = 0.f;
+    if constexpr (ONLINE) {
+      float m_used = 0.f;   // the maximum the exponentials are taken against (set by the first block)
+      uint32_t r2[32];
+      for (int jj = 0; jj < nb; ++jj) {
+        const int sb = jj & 1;
+        mbar_wait(&s_full[sb], (jj >> 1) & 1);
+        tc_fence_after();
+        const int nvalid = Tk - jj * BKV;
+        tmem_ld_32x32(tmem_base + lane_addr + sb * BKV, r);
+        tmem_ld_32x32(tmem_base + lane_addr + sb * BKV + 32, r2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);   // the scores are in registers
+        float mb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nvalid) mb = fmaxf(mb, __uint_as_float(r[c]));
+          if (32 + c < nvalid) mb = fmaxf(mb, __uint_as_float(r2[c]));
+        }
+        m = fmaxf(m, mb);
+        float factor = 1.f;
+        bool need = false;
+        if (jj == 0) {
+          m_used = m;
+        } else if ((m - m_used) * a.scale_log2e > 8.f) {
+          need = true;
+          factor = ex2((m_used - m) * a.scale_log2e);
+          m_used = m;
+          l *= factor;
+        }
+        const float mc = m_used * a.scale_log2e;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = (c < nvalid) ? ex2(fmaf(__uint_as_float(r[c]), a.scale_log2e, -mc)) : 0.f;
+          const float p1 = (c + 1 < nvalid) ? ex2(fmaf(__uint_as_float(r[c + 1]), a.scale_log2e, -mc)) : 0.f;
+          const float p2 = (32 + c < nvalid) ? ex2(fmaf(__uint_as_float(r2[c]), a.scale_log2e, -mc)) : 0.f;
+          const float p3 = (33 + c < nvalid) ? ex2(fmaf(__uint_as_float(r2[c + 1]), a.scale_log2e, -mc)) : 0.f;
+          l += (p0 + p1) + (p2 + p3);
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+          pk[16 + (c >> 1)] = pack_bf16x2(p2, p3);
+        }
+        // P V of the previous block has completed once p_empty flips: P's buffer is free and O is quiescent
+        mbar_wait(&p_empty[0], (jj & 1) ^ 1);
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: this warp's 32 rows of O are rescaled in TMEM (rows that did not move use factor 1)
+          tc_fence_after();
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld_32x32(tmem_o + lane_addr + c4 * 32, r);
+            tmem_ld_wait();
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              lo[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+              hi[c] = __float_as_uint(__uint_as_float(r[16 + c]) * factor);
+            }
+            tmem_st_32x16(tmem_o + lane_addr + c4 * 32, lo);
+            tmem_st_32x16(tmem_o + lane_addr + c4 * 32 + 16, hi);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        const uint32_t prow = smem_u32(sP + row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(prow + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[0]);
+      }
+    } else {
     // ---- pass 1 ----
     for (int it = 0; it < nb; ++it) {
       const int sb = it & 1;
@@ -200,7 +285,6 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     // ---- pass 2 ----
     const float mc = m * a.scale_log2e;
-    float l = 0.f;
     for (int jj = 0; jj < nb; ++jj) {
       const int it = nb + jj;
       const int sb = it & 1;
@@ -234,6 +318,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
+    }
     }
     // ---- epilogue ----
     mbar_wait(o_full, 0);
@@ -317,7 +402,9 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   if (p.n_work <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(attn_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(attn_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     attr_set = true;
   }
@@ -328,7 +415,8 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   if (rc) return rc;
   AArgs a = make_args(p);
   dim3 grid(p.n_work, p.n_heads);
-  return launch_kernel(attn_tcgen05_kernel, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+  if (p.online) return launch_kernel(attn_tcgen05_kernel<true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+  return launch_kernel(attn_tcgen05_kernel<false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
 }
 
 int attention_check_kernel(const AttnProblem& p, cudaStream_t stream) {

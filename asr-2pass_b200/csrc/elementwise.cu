@@ -122,7 +122,9 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 
-__global__ void __launch_bounds__(128, 3)
+// <= 128 registers (44 bytes of spill): one FSMN CTA then fits next to two resident attention CTAs (2 x 24.6K + 16.4K
+// registers = one SM), which is what lets the two kernels really run side by side (engine.cu, "overlap").
+__global__ void __launch_bounds__(128, 4)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
             __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {

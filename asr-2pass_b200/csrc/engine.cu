@@ -286,8 +286,12 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
   if ((int)e->tokens.size() != c.vocab) { set_error("tokens.json size != vocab"); return B200PF_ERR_IO; }
   e->device = device;
   cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
-  CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  CK(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking), "cudaStreamCreate");
+  {  // the side stream (FSMN memory block, a bandwidth-bound filler) yields to the main stream's kernels
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), "cudaDeviceGetStreamPriorityRange");
+    CK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
+    CK(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+  }
   CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming), "cudaEventCreate");
 
@@ -481,7 +485,11 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
     return 0;
   }
   if (strcmp(key, "overlap") == 0) {
-    e->overlap = value ? 1 : 0;
+    e->overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return 0;
+  }
+  if (strcmp(key, "attn_online") == 0) {
+    e->attn_online = value ? 1 : 0;
     return 0;
   }
   if (strcmp(key, "profile") == 0) {
@@ -780,7 +788,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   ap.kv = e->qkv; ap.kv_rows = M; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
   ap.out = e->att; ap.ldo = D;
   ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
-  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads;
+  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads; ap.online = e->attn_online;
   for (int l = 0; l < c.n_enc; ++l) {
     const EncLayer& w = e->enc[l];
     const float* xin = l == 0 ? e->x0 : e->x;
@@ -789,15 +797,18 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
       CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
     // The FSMN memory block and the attention both depend only on the QKV projection: run them concurrently
     // (CUDA-core FMA work next to tensor-core / MUFU work) and join before the output projection.
+    // overlap 1: FSMN enqueued first; overlap 2: attention enqueued first, so its CTAs (two per SM) take the SMs and the
+    // FSMN CTAs fill the register space left over (one per SM) instead of the other way round.
     const bool fork = e->overlap && !e->profile;
     cudaStream_t fs = fork ? e->side : s;
     if (fork) {
       CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
       CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
     }
+    if (fork && e->overlap == 2) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs), "fsmn");
     if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
-    LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
+    if (!(fork && e->overlap == 2)) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
     { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
       if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
@@ -848,7 +859,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
   cp.out = e->att; cp.ldo = D;
   cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
-  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads;
+  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.online = e->attn_online;
   auto dec_ffn = [&](const DecLayer& w) -> int {
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;

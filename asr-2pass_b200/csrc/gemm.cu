@@ -9,8 +9,10 @@
 //                 of both CTAs (128 lanes x 256 columns each, double buffered = 512 columns)
 //   warp 2      : TMEM allocator (cta_group::2)
 //   warps 4..11 : epilogue in each CTA: tcgen05.ld 32x32b.x32 -> bias / ReLU / FSMN-memory add / residual ->
-//                 bf16 or fp32, staged through a per-warp smem tile so every global load and store is a
-//                 run of full 32-byte sectors; optional fused argmax.
+//                 bf16 or fp32.  bf16-only outputs (FAST) leave through TMA stores: each warp packs 32 rows x 64
+//                 columns into a swizzled 4 KB smem tile and one lane issues cp.async.bulk.tensor (full 128-byte
+//                 lines, no LSU / register traffic, asynchronous).  The general path stages through a per-warp smem
+//                 tile so every global load and store is a run of full 32-byte sectors; optional fused argmax.
 #include "gemm.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -43,7 +45,8 @@ struct KArgs {
 // buffered in registers and each thread stores its own row segment directly (64 contiguous bytes per chunk).
 template <bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KArgs a) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -70,6 +73,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (FAST) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -78,7 +82,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], FAST ? 8 : 2 * kEpiWarps);   // FAST: 4 reader warps per CTA
+      mbar_init(&tempty[i], 2 * kEpiWarps);
     }
     for (int i = 0; i < 24; ++i) mbar_init(&obar[i], 1);
     fence_barrier_init();
@@ -162,99 +166,81 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     if constexpr (FAST) {
-      // Reader / storer split.  tcgen05.wait::ld stalls until the warp's outstanding global stores have drained
-      // (measured: with stores in the same warp the epilogue took 1.6x the MMA time, without the wait 1.0x), so
-      // the warps that read TMEM never touch global memory: warp 4+q (reader) loads the accumulator rows of
-      // lane quarter q, applies bias / ReLU, packs to bf16 and hands 32x32 chunks through a double-buffered smem
-      // tile to warp 8+q (storer), which does every global access (bias fetch, coalesced 16-byte row stores).
-      const int q = quarter;
-      const bool reader = ew < 4;
-      const uint32_t buf0 = smem_u32(sScr + (q * 2) * SCR_BYTES);
-      const uint32_t bias_s = smem_u32(sBias + q * 2 * BN * 4);   // [2][256] floats per pair
-      uint64_t* ofull = obar + q * 4;
-      uint64_t* oempty = ofull + 2;
-      uint64_t* bfull = obar + 16 + q * 2;
-      uint32_t n = 0;     // chunks handed over so far (both roles count identically)
-      uint32_t t = 0;     // tiles processed so far
-      for (int tile = pair; tile < total; tile += n_pairs, ++t) {
+      // bias (+ReLU) -> bf16 -> TMA store.  Warp (quarter, half) owns rows 32 quarter.. of the CTA's 128 and columns
+      // 128 half.. of the 256-wide tile, as two 64-column boxes.  Its 4 KB staging tile is written in the tensor map's
+      // SWIZZLE_128B layout (16-byte chunk j of row r at chunk j ^ (r & 7)), which also makes the 32 row-wise 16-byte
+      // stores of a warp conflict free.  One lane issues the store and is the only one to wait on it
+      // (bulk async-groups are per thread); the next TMEM load is already in flight by then.
+      const uint32_t stage_tile = smem_u32(sScr + ew * 4096);
+      const uint32_t my_stage_row = stage_tile + lane * 128;
+      for (int tile = pair; tile < total; tile += n_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int row_base = m_blk * 2 * BM + (int)cta * BM + q * 32;
-        const int ncol0 = n_blk * BN;
-        if (reader) {
-          mbar_wait(&tfull[acc], acc_phase);
-          tc_fence_after();
-          mbar_wait(&bfull[t & 1], (t >> 1) & 1);
-          const uint32_t bsm = bias_s + (t & 1) * BN * 4;
-          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32(tbase, ra);
+        const int row_base = m_blk * 2 * BM + (int)cta * BM + quarter * 32;
+        const int col_base = n_blk * BN + half * 128;
+        if (e.bias) {  // this warp's 128 bias values: one coalesced load per tile, read back as smem broadcasts
+          const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
+          sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          warp_sync_smem();
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        uint32_t ra[32], rb[32];
+        if (e.dbg == 3) {  // micro-benchmark only: no TMEM reads
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            tmem_ld_wait();
-            if (c + 1 < 8) {  // next chunk's TMEM load is in flight while this one is processed
-              if (c & 1) tmem_ld_32x32(tbase + (c + 1) * 32, ra); else tmem_ld_32x32(tbase + (c + 1) * 32, rb);
-            } else {
-              // the accumulator is in registers: hand the TMEM buffer back to the MMA issuer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
-            }
-            const uint32_t (&r)[32] = (c & 1) ? rb : ra;
-            uint32_t pk[16];
+          for (int i = 0; i < 32; ++i) { ra[i] = 0; rb[i] = 0; }
+        }
+        if (e.dbg != 3) {
+          tmem_ld_32x32(tbase, ra);
+          tmem_ld_32x32(tbase + 32, rb);
+        }
+#pragma unroll
+        for (int c64 = 0; c64 < 2; ++c64) {
+          tmem_ld_wait();
+          uint32_t pk[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t (&r)[32] = hh ? rb : ra;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]);
               float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
               if (e.bias) {
-                const float4 bb = lds128f(bsm + (c * 32 + 4 * g) * 4);
+                const float4 bb = lds128f(sbias + (c64 * 64 + hh * 32 + 4 * g) * 4);
                 v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
               }
               if (e.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-              pk[2 * g] = pack_bf16x2(v0, v1);
-              pk[2 * g + 1] = pack_bf16x2(v2, v3);
+              pk[hh * 16 + 2 * g] = pack_bf16x2(v0, v1);
+              pk[hh * 16 + 2 * g + 1] = pack_bf16x2(v2, v3);
             }
-            const uint32_t b = n & 1;
-            mbar_wait(&oempty[b], ((n >> 1) & 1) ^ 1);
-            const uint32_t dst = buf0 + b * SCR_BYTES + lane * SCR_STRIDE;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) sts128(dst + g * 16, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ofull[b]);
-            ++n;
           }
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-        } else {
-          {  // bias of this tile's 256 columns -> smem (buffer t&1 was last read two tiles ago)
-            const uint32_t bsm = bias_s + (t & 1) * BN * 4;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              uint4 bv = make_uint4(0, 0, 0, 0);
-              if (e.bias) bv = ldg128_nc(e.bias + ncol0 + (i * 32 + lane) * 4);
-              sts128(bsm + (i * 32 + lane) * 16, bv.x, bv.y, bv.z, bv.w);
+          if (c64 == 0) {  // the second half's TMEM loads fly while this half is stored
+            if (e.dbg != 3) {
+              tmem_ld_32x32(tbase + 64, ra);
+              tmem_ld_32x32(tbase + 96, rb);
             }
+          } else {         // the accumulator is in registers: hand the TMEM buffer back to the MMA issuer
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bfull[t & 1]);
+            if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
           }
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t b = n & 1;
-            mbar_wait(&ofull[b], (n >> 1) & 1);
-            const uint32_t src = buf0 + b * SCR_BYTES;
-            uint4 o[4];
+          if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = lds128(src + ((lane >> 2) + 8 * i) * SCR_STRIDE + (lane & 3) * 16);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&oempty[b]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = row_base + (lane >> 2) + 8 * i;
-              if (rr < M) stg128(e.out_bf16 + (size_t)rr * e.ld_out_bf16 + ncol0 + c * 32 + (lane & 3) * 8, o[i]);
-            }
-            ++n;
+          for (int j = 0; j < 8; ++j)
+            sts128(my_stage_row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && e.dbg != 1) {
+            tma_store_2d(&tmC, stage_tile, col_base + c64 * 64, row_base);  // rows / columns past the tensor are clipped
+            tma_store_commit();
           }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
+      if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the last store
+      __syncwarp();
     } else
     for (int tile = pair; tile < total; tile += n_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -461,6 +447,13 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (rc) return rc;
   rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
+  const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 &&
+                    (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0;
+  CUtensorMap tmC = tmA;  // placeholder for the general path
+  if (fast) {
+    rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);
+    if (rc) return rc;
+  }
   KArgs a;
   a.M = p.M; a.N = p.N; a.K = p.K; a.m_dev = p.m_dev;
   a.a_k_wrap = p.a_k_wrap; a.a_row_shift0 = p.a_row_shift0;
@@ -468,9 +461,8 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
-  const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 && e.dbg == 0;
-  if (fast) return launch_kernel(gemm_tcgen05_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
-  return launch_kernel(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, a);
+  if (fast) return launch_kernel(gemm_tcgen05_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
+  return launch_kernel(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
 }
 
 }  // namespace pf

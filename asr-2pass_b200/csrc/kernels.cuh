@@ -91,6 +91,7 @@ struct LstmParams {
   int ld_out_f32 = 0;
 };
 int lstm_launch(const LstmParams& p, cudaStream_t s);
+int lstm_max_active_clusters();  // co-resident 16-CTA clusters on the current device (diagnostics)
 
 // K13 timestamp head tail (CifPredictorV3.get_upsample_timestmap): alpha2 = relu(sigmoid(h . w + b) * smooth - noise)
 //     over the BiLSTM output h [rows, 1024] bf16 ...

@@ -51,7 +51,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void st_cluster_128(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// exp through the MUFU unit (ex2.approx, ~2 ulp) and an approximate reciprocal: ~1e-6 relative, far inside the bf16
+// rounding of the recurrent state, at a tenth of the instructions of expf()/tanhf()
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_kernel(LstmParams p) {
@@ -196,8 +199,8 @@ lstm_kernel(LstmParams p) {
       const float go = (kh ? acc[1][2 + jj][2 + c] : acc[1][jj][2 + c]) + __uint_as_float((uint32_t)gxv[x][3] << 16);
       float h = 0.f;
       if (act) {
-        c_state[x] = sigmoidf_(gf) * c_state[x] + sigmoidf_(gi) * tanhf(gg);
-        h = sigmoidf_(go) * tanhf(c_state[x]);
+        c_state[x] = sigmoidf_(gf) * c_state[x] + sigmoidf_(gi) * tanhf_(gg);
+        h = sigmoidf_(go) * tanhf_(c_state[x]);
         if (p.out_f32) {
           const int t = rev ? c_len[x] - 1 - k : k;
           p.out_f32[(size_t)(c_off[x] + t) * p.ld_out_f32 + dir * 512 + (int)rank * 32 + unit_local] = h;
@@ -329,6 +332,23 @@ int lstm_launch(const LstmParams& p, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, lstm_kernel, p);
+}
+
+int lstm_max_active_clusters() {
+  cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCluster * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
 }
 
 int us_alpha_launch(const __nv_bfloat16* h, int rows, const float* w, const float* b, float smooth, float noise, float* alpha,

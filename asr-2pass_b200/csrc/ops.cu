@@ -216,7 +216,8 @@ int b200pf_op_attention(int device, const float* q, const float* k, const float*
   p.out = dOutB.as<__nv_bfloat16>(); p.ldo = D;
   p.q_row_off = dqo.as<int>(); p.q_len = dql.as<int>(); p.kv_row_off = dko.as<int>(); p.kv_len = dkl.as<int>();
   p.work = dWork.as<AttnWork>(); p.n_work = (int)work.size(); p.n_heads = n_heads;
-  int rc = impl == 0 ? attention_tcgen05(p, 0) : attention_check_kernel(p, 0);
+  p.online = impl == 2 ? 0 : 1;
+  int rc = impl == 1 ? attention_check_kernel(p, 0) : attention_tcgen05(p, 0);
   if (rc) return check_cuda((cudaError_t)rc, "attention launch");
   bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)q_rows * D);
   RC(sync_ok("op_attention"));
@@ -308,6 +309,37 @@ int b200pf_op_lstm(int device, const float* x, int rows, const int32_t* seq_off,
   if (bf16_out) bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)rows * 512 * n_dir);
   RC(sync_ok("op_lstm"));
   return check_cuda(cudaMemcpy(out, dOut.p, (size_t)rows * 512 * n_dir * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
+int b200pf_op_lstm_bench(int device, int n_seq, int len, int n_dir, int iters, float* ms_out, int* max_clusters) {
+  RC(select_device(device));
+  if (n_seq <= 0 || len <= 0 || n_dir < 1 || n_dir > 2) { set_error("op_lstm_bench: bad argument"); return B200PF_ERR_INVALID; }
+  const size_t rows = (size_t)n_seq * len;
+  const int G = 2048 * n_dir;
+  DevBuf dGx, dWhh, dOff, dLen, dOut;
+  RC(dGx.alloc(rows * G * 2)); RC(dWhh.alloc((size_t)G * 512 * 2)); RC(dOut.alloc(rows * 512 * n_dir * 2));
+  fill_random_bf16_kernel<<<1024, 256>>>(dGx.as<__nv_bfloat16>(), (int64_t)rows * G, 5u);
+  fill_random_bf16_kernel<<<1024, 256>>>(dWhh.as<__nv_bfloat16>(), (int64_t)G * 512, 6u);  // |w| < 1: saturating, still finite
+  std::vector<int> off(n_seq), ln(n_seq, len);
+  for (int i = 0; i < n_seq; ++i) off[i] = i * len;
+  RC(up_raw(off.data(), off.size(), &dOff)); RC(up_raw(ln.data(), ln.size(), &dLen));
+  LstmParams lp;
+  lp.gx = dGx.as<__nv_bfloat16>(); lp.ld_gx = G; lp.whh = dWhh.as<__nv_bfloat16>(); lp.seq_off = dOff.as<int>(); lp.seq_len = dLen.as<int>();
+  lp.n_seq = n_seq; lp.n_dir = n_dir; lp.reverse_mask = n_dir == 2 ? 2 : 0; lp.out_bf16 = dOut.as<__nv_bfloat16>(); lp.ld_out = 512 * n_dir;
+  int rc = lstm_launch(lp, 0);
+  if (rc) return check_cuda((cudaError_t)rc, "lstm launch");
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, 0);
+  for (int i = 0; i < iters; ++i) { rc = lstm_launch(lp, 0); if (rc) return check_cuda((cudaError_t)rc, "lstm launch"); }
+  cudaEventRecord(b, 0);
+  RC(sync_ok("op_lstm_bench"));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (ms_out) *ms_out = ms / iters;
+  if (max_clusters) *max_clusters = lstm_max_active_clusters();
+  return 0;
 }
 
 int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, const int32_t* seq_len, const int32_t* n_tok,

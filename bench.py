@@ -228,6 +228,10 @@ def main():
     mf.write_model_dir(tmp, cfg, W, means, vars_, synth.make_tokens(int(cfg["vocab"])))
     del W
     eng = capi.Engine(tmp, device=local, max_rows=args.max_rows, max_segments=4096)
+    if os.environ.get("B200PF_OVERLAP"):
+        eng.set_option("overlap", int(os.environ["B200PF_OVERLAP"]))
+    if os.environ.get("B200PF_ATTN_ONLINE"):
+        eng.set_option("attn_online", int(os.environ["B200PF_ATTN_ONLINE"]))
     groups = make_batches(lens, args.max_rows, 4096, capi)
     audio_s = float(lens.sum()) / 16000.0
 

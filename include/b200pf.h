@@ -86,8 +86,10 @@ int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out);
 int b200pf_engine_vocab_size(const b200pf_engine* e);
 const char* b200pf_engine_token(const b200pf_engine* e, int id);
 const char* b200pf_engine_lang(const b200pf_engine* e);
-/* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (default 1) runs the
- * FSMN memory block on a side stream concurrently with the attention kernel; "profile" see below. */
+/* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (0 off, 1 FSMN enqueued
+ * first, 2 = default: attention enqueued first) runs the FSMN memory block on a low-priority side stream concurrently
+ * with the attention kernel; "attn_online" (default 1) selects the single-pass attention kernel, 0 the two-pass one;
+ * "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 /* Option "profile" = 1 brackets every launch of b200pf_batch_run with CUDA events on the launching stream.
  * b200pf_engine_profile_read synchronises, folds the finished brackets into 16 categories (names[i]:
@@ -157,7 +159,7 @@ int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bi
 int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
                         int in_bf16, float* out_f32, float* out_bf16_as_f32);
 /* q [sum Tq,H*128], k,v [sum Tk,H*128]; segment s owns rows q_off[s].. and kv_off[s]..; impl 0 = tcgen05
- * kernel (product), 1 = CUDA-core cross-check. */
+ * kernel (product: single pass, running maximum), 1 = CUDA-core cross-check, 2 = tcgen05 exact two-pass variant. */
 int b200pf_op_attention(int device, const float* q, const float* k, const float* v, const int32_t* q_off,
                         const int32_t* q_len, const int32_t* kv_off, const int32_t* kv_len, int n_seg, int n_heads,
                         int64_t q_rows, int64_t kv_rows, int impl, float* out);
@@ -172,6 +174,9 @@ int b200pf_op_cif(int device, const float* alphas, const float* hidden, const in
  * (bf16_out: the bf16 output path, widened). */
 int b200pf_op_lstm(int device, const float* x, int rows, const int32_t* seq_off, const int32_t* seq_len, int n_seq, int n_dir,
                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int bf16_out, float* out);
+/* Times the LSTM recurrence alone: n_seq sequences of `len` steps on random operands; ms_out = milliseconds per launch,
+ * max_clusters = co-resident 16-CTA clusters the device grants the kernel. */
+int b200pf_op_lstm_bench(int device, int n_seq, int len, int n_dir, int iters, float* ms_out, int* max_clusters);
 /* us_alphas / us_cif_peak from raw alpha2 (already relu(sigmoid*s-n)): per segment scale to n_tok and cif_wo_hidden. */
 int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, const int32_t* seq_len, const int32_t* n_tok,
                        int n_seg, int rows, float threshold, float* us_alphas, float* us_peaks);

@@ -122,7 +122,7 @@ def _attn_ref(q, k, v, q_off, q_len, kv_off, kv_len, H=4):
 
 @pytest.mark.parametrize("case", [([33], [33]), ([1], [1]), ([64], [64]), ([65], [65]), ([128], [128]), ([129], [129]), ([167], [167]),
                                   ([200, 1, 64, 129], [200, 1, 64, 129]), ([40, 90], [83, 167]), ([1000], [1000])])
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 def test_attention(capi, gpu, case, impl):
     q_lens, kv_lens = case
     rng = np.random.default_rng(sum(q_lens) + 13 * sum(kv_lens))
@@ -134,6 +134,28 @@ def test_attention(capi, gpu, case, impl):
     ref = _attn_ref(q, k, v, q_off, q_lens, kv_off, kv_lens)
     out = capi.op_attention(q, k, v, q_off, q_lens, kv_off, kv_lens, impl=impl)
     assert rel(out, ref) <= 8e-3  # bf16 P (product kernel) + bf16 output rounding
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+def test_attention_large_scores_force_the_running_maximum_to_move(capi, gpu, impl):
+    """Scores grow along the keys (each 64-key block's maximum is far above the previous one), so the single-pass kernel
+    must take its rare path: rescale O and l in TMEM.  Both tcgen05 variants against the fp32 softmax."""
+    rng = np.random.default_rng(21)
+    q_lens, kv_lens = [130, 70, 200], [300, 129, 640]
+    q_off = np.concatenate([[0], np.cumsum(q_lens)[:-1]]).astype(np.int32)
+    kv_off = np.concatenate([[0], np.cumsum(np.asarray(kv_lens) + 1)[:-1]]).astype(np.int32)
+    q = rng.standard_normal((int(sum(q_lens)), 512)).astype(np.float32)
+    k = rng.standard_normal((int(sum(kv_lens) + len(kv_lens)), 512)).astype(np.float32)
+    v = rng.standard_normal(k.shape).astype(np.float32)
+    q[:, :4] = 6.0                                                    # a shared direction ...
+    for s in range(len(kv_lens)):
+        ramp = np.linspace(-8.0, 8.0, kv_lens[s]).astype(np.float32)  # ... along which the keys ramp up: +~19 in log2 per 64 keys
+        k[kv_off[s]:kv_off[s] + kv_lens[s], :4] = ramp[:, None]
+    q[5] *= 0.01                                                      # one flat row inside a tile whose neighbours move
+    ref = _attn_ref(q, k, v, q_off, q_lens, kv_off, kv_lens)
+    out = capi.op_attention(q, k, v, q_off, q_lens, kv_off, kv_lens, impl=impl)
+    assert np.isfinite(out).all()
+    assert rel(out, ref) <= 8e-3
 
 
 def test_fsmn(capi, gpu):
