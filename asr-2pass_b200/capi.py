@@ -518,14 +518,14 @@ class Batch:
 
 
 # ---- single-operator wrappers (parity tests) ---------------------------------------------------------
-def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=False, device=0):
+def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=False, device=0, general=False):
     A, W = _f32(A), _f32(W)
     M, K = A.shape
     N = W.shape[0]
     bias, add, res = _f32(bias), _f32(add), _f32(res)
     out = np.zeros((M, N), np.float32)
     am = np.zeros(M, np.int32) if argmax else None
-    _check(lib().b200pf_op_gemm(device, _p(A), _p(W), _p(bias), _p(add), _p(res), M, N, K, int(relu), int(out_bf16),
+    _check(lib().b200pf_op_gemm(device, _p(A), _p(W), _p(bias), _p(add), _p(res), M, N, K, int(relu), 2 if general else int(out_bf16),
                                 _p(out), _p(am, c_i32p)))
     return (out, am) if argmax else out
 

@@ -41,9 +41,15 @@ struct KArgs {
   GemmEpilogue e;
 };
 
-// FAST = epilogue is bias (+ReLU) -> bf16 only (QKV, FFN1, decoder q / kv projections): TMEM loads are double
+// EPI selects the epilogue:
+//   0  general: any combination of GemmEpilogue's fields (argmax, separate residual source, fp32 + bf16 outputs ...)
+//   1  bias (+ReLU) -> bf16 through TMA stores (QKV, FFN1, decoder q / kv projections, LSTM input projections)
+//   2  bias (+ReLU) (+bf16 addend) -> fp32 through TMA; when the residual is the output buffer itself (x += ..., every
+//      out-projection and FFN2) the tile leaves as a TMA REDUCE-ADD, so the SMs never load the residual stream: the
+//      read-modify-write of x happens in L2.
+// (old note) FAST = epilogue is bias (+ReLU) -> bf16 only (QKV, FFN1, decoder q / kv projections): TMEM loads are double
 // buffered in registers and each thread stores its own row segment directly (64 contiguous bytes per chunk).
-template <bool FAST>
+template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, KArgs a) {
@@ -73,7 +79,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (FAST) tma_prefetch_desc(&tmC);
+    if (EPI != 0) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -165,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t sbias = smem_u32(sBias + ew * BIAS_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
-    if constexpr (FAST) {
+    if constexpr (EPI == 1) {
       // bias (+ReLU) -> bf16 -> TMA store.  Warp (quarter, half) owns rows 32 quarter.. of the CTA's 128 and columns
       // 128 half.. of the 256-wide tile, as two 64-column boxes.  Its 4 KB staging tile is written in the tensor map's
       // SWIZZLE_128B layout (16-byte chunk j of row r at chunk j ^ (r & 7)), which also makes the 32 row-wise 16-byte
@@ -240,6 +246,82 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
       if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the last store
+      __syncwarp();
+    } else if constexpr (EPI == 2) {
+      // bias (+ReLU) (+bf16 addend) -> fp32 -> TMA store / reduce-add.  Warp (quarter, half): rows 32 quarter.., columns
+      // 128 half.. of the tile as four 32-column boxes (32 fp32 = one 128-byte row of the SWIZZLE_128B staging tile).
+      const uint32_t stage_tile = smem_u32(sScr + ew * 4096);
+      const uint32_t my_stage_row = stage_tile + lane * 128;
+      const bool reduce = e.res_f32 != nullptr;   // the launcher guarantees res == out here
+      for (int tile = pair; tile < total; tile += n_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int row_base = m_blk * 2 * BM + (int)cta * BM + quarter * 32;
+        const int row = row_base + lane;
+        const bool row_ok = row < M;
+        const int col_base = n_blk * BN + half * 128;
+        if (e.bias) {
+          const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
+          sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          warp_sync_smem();
+        }
+        // this thread's row of the addend for the whole 128-column span: issued before the accumulator is even ready
+        uint4 add[16];
+        if (e.add_bf16) {
+          const __nv_bfloat16* ap = e.add_bf16 + (size_t)row * e.ld_add + col_base;
+#pragma unroll
+          for (int g = 0; g < 16; ++g) add[g] = row_ok ? ldg128_nc(ap + 8 * g) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tbase, ra);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < 4) {
+            if (c & 1) tmem_ld_32x32(tbase + (c + 1) * 32, ra); else tmem_ld_32x32(tbase + (c + 1) * 32, rb);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
+          }
+          const uint32_t (&r)[32] = (c & 1) ? rb : ra;
+          float v[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]);
+            float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
+            if (e.bias) {
+              const float4 bb = lds128f(sbias + (c * 32 + 4 * g) * 4);
+              v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
+            }
+            if (e.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            if (e.add_bf16) {
+              const uint4 aa = add[c * 4 + (g >> 1)];
+              const uint32_t w0 = (g & 1) ? aa.z : aa.x, w1 = (g & 1) ? aa.w : aa.y;
+              v0 += __uint_as_float(w0 << 16); v1 += __uint_as_float(w0 & 0xffff0000u);
+              v2 += __uint_as_float(w1 << 16); v3 += __uint_as_float(w1 & 0xffff0000u);
+            }
+            v[4 * g] = v0; v[4 * g + 1] = v1; v[4 * g + 2] = v2; v[4 * g + 3] = v3;
+          }
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128f(my_stage_row + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (reduce) tma_reduce_add_2d(&tmC, stage_tile, col_base + c * 32, row_base);
+            else tma_store_2d(&tmC, stage_tile, col_base + c * 32, row_base);
+            tma_store_commit();
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (lane == 0) tma_store_wait_all();
       __syncwarp();
     } else
     for (int tile = pair; tile < total; tile += n_pairs) {
@@ -356,7 +438,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 8; ++i) {
             const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
             const float4 o = lds128f(scr + rr * SCR_STRIDE + ch * 16);
-            if (row_base + rr < M && col0 + 4 * ch < N && e.dbg == 0)
+            if (row_base + rr < M && col0 + 4 * ch < N && e.dbg != 1)
               stg128f(e.out_f32 + (size_t)(row_base + rr) * e.ld_out_f32 + col0 + 4 * ch, o);
           }
           warp_sync_smem();
@@ -371,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 4; ++i) {
             const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
             const uint4 o = lds128(scr + rr * SCR_STRIDE + ch * 16);
-            if (row_base + rr < M && col0 + 8 * ch < N && e.dbg == 0)
+            if (row_base + rr < M && col0 + 8 * ch < N && e.dbg != 1)
               stg128(e.out_bf16 + (size_t)(row_base + rr) * e.ld_out_bf16 + col0 + 8 * ch, o);
           }
           warp_sync_smem();
@@ -414,15 +496,23 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                          uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_rows, box_cols);
+}
+
+static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
+                           uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld_elems * 2};
+  cuuint64_t gstride[1] = {ld_elems * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -435,9 +525,11 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (e.add_bf16 && ((p.N & 7) || (e.ld_add & 7))) return (int)cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     attr_set = true;
   }
@@ -447,11 +539,19 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (rc) return rc;
   rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
-  const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 &&
+  const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 && e.dbg != 2 && e.dbg != 4 &&
                     (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0;
+  // fp32 output through TMA: residual (if any) must be the output buffer itself, so that "x += tile" is one reduce-add
+  static const bool no_f32_tma = getenv("B200PF_NO_F32_TMA") != nullptr;
+  const bool f32tma = !fast && !no_f32_tma && e.out_f32 && !e.out_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 && e.dbg == 0 &&
+                      (e.res_f32 == nullptr || (e.res_f32 == e.out_f32 && e.ld_res == e.ld_out_f32)) &&
+                      (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (e.ld_out_f32 & 3) == 0;
   CUtensorMap tmC = tmA;  // placeholder for the general path
   if (fast) {
     rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);
+    if (rc) return rc;
+  } else if (f32tma) {
+    rc = make_tmap_sw128(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.out_f32, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)e.ld_out_f32, 32, 32);
     if (rc) return rc;
   }
   KArgs a;
@@ -461,8 +561,9 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
-  if (fast) return launch_kernel(gemm_tcgen05_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
-  return launch_kernel(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
+  if (fast) return launch_kernel(gemm_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
+  if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
+  return launch_kernel(gemm_tcgen05_kernel<0>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
 }
 
 }  // namespace pf

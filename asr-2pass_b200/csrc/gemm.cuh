@@ -22,7 +22,8 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16 = nullptr;      // [M, ld_out_bf16]
   int ld_out_bf16 = 0;
   int relu = 0;                           // 1: after bias, 2: after every addend
-  int dbg = 0;                            // micro-benchmark only: 1 = skip global stores, 2 = skip the whole epilogue body
+  int dbg = 0;                            // micro-benchmark / tests only: 1 = skip global stores, 2 = skip the whole epilogue body,
+                                          // 3 = bf16 TMA epilogue without TMEM reads, 4 = force the general epilogue
   unsigned long long* argmax = nullptr;   // [M] packed (ordered value << 32 | ~index); caller zero-fills
 };
 

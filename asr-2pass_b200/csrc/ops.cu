@@ -86,9 +86,15 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   GemmEpilogue e;
   if (bias) { RC(up_f32(bias, N, &dBias)); e.bias = dBias.as<float>(); }
   if (add) { RC(up_bf16(add, (size_t)M * N, &tadd, &dAdd)); e.add_bf16 = dAdd.as<__nv_bfloat16>(); e.ld_add = N; }
-  if (res) { RC(up_f32(res, (size_t)M * N, &dRes)); e.res_f32 = dRes.as<float>(); e.ld_res = N; }
   e.relu = relu;
   RC(dOut.alloc((size_t)M * N * 4));
+  // out_bf16_round: 0 = fp32 out, with `res` IN PLACE (x += ..., the form every residual GEMM of the forward has: TMA
+  // reduce-add epilogue); 1 = bf16 out; 2 = fp32 out through the general epilogue with a separate residual buffer
+  if (res && out_bf16_round == 0) {
+    RC(check_cuda(cudaMemcpy(dOut.p, res, (size_t)M * N * 4, cudaMemcpyHostToDevice), "H2D"));
+    e.res_f32 = dOut.as<float>(); e.ld_res = N;
+  } else if (res) { RC(up_f32(res, (size_t)M * N, &dRes)); e.res_f32 = dRes.as<float>(); e.ld_res = N; }
+  if (out_bf16_round == 2) { e.dbg = 4; out_bf16_round = 0; }
   if (out_bf16_round) { RC(dOutB.alloc((size_t)M * N * 2)); e.out_bf16 = dOutB.as<__nv_bfloat16>(); e.ld_out_bf16 = N; }
   else { e.out_f32 = dOut.as<float>(); e.ld_out_f32 = N; }
   if (argmax_out) {

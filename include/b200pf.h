@@ -146,7 +146,8 @@ int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int
 
 /* ---- single-operator entry points (fp32 host buffers in/out; used by the parity tests) -------------- */
 /* C = A[M,K] * W[N,K]^T (+bias) (+relu: 1 after bias, 2 after all adds) (+add[M,N] rounded to bf16)
- * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: round the result to bf16.
+ * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: 1 rounds the result to bf16; 0 = fp32 with the
+ * residual applied in place (the TMA epilogues, as in the forward); 2 = fp32 through the general epilogue.
  * argmax_out (optional, [M]) receives the fused greedy argmax (first maximum wins, util.cpp:63-74). */
 int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
                    int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out);

@@ -53,7 +53,11 @@ def test_gemm_tcgen05(capi, gpu, shape):
     res = rng.standard_normal((M, N)).astype(np.float32)
     ref = bf(A) @ bf(W).T
     assert rel(capi.op_gemm(A, W), ref) <= 1e-5
-    assert rel(capi.op_gemm(A, W, bias=bias, add=add, res=res, relu=1), np.maximum(ref + bias, 0) + bf(add) + res) <= 1e-5
+    assert rel(capi.op_gemm(A, W, general=True), ref) <= 1e-5
+    full = np.maximum(ref + bias, 0) + bf(add) + res
+    assert rel(capi.op_gemm(A, W, bias=bias, add=add, res=res, relu=1), full) <= 1e-5                 # in place: TMA reduce-add
+    assert rel(capi.op_gemm(A, W, bias=bias, add=add, res=res, relu=1, general=True), full) <= 1e-5   # separate residual buffer
+    assert np.array_equal(capi.op_gemm(A, W, bias=bias, add=add, res=res, relu=1), capi.op_gemm(A, W, bias=bias, add=add, res=res, relu=1, general=True))
     assert rel(capi.op_gemm(A, W, bias=bias, res=res, relu=2, out_bf16=True), bf(np.maximum(ref + bias + res, 0))) <= 4e-3
 
 
