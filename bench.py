@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--segments", type=int, default=1024)
-    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "65536")))
+    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "98304")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
@@ -332,6 +332,12 @@ def main():
             dist.destroy_process_group()
         return
     hbm, tflops_peak, which = load_peaks()
+    traffic = None   # DRAM bytes per GEMM launch from the committed ncu --set full capture (tools/make_traffic.py)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tj["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     value = world * audio_s / (ms_resident / 1e3)
     e2e_v = world * audio_s / (ms_e2e / 1e3)
     step_tf = flops / (ms_resident / 1e3) / 1e12
@@ -354,7 +360,7 @@ def main():
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
         gpu_launches=int(launches * args.steps),
         roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all %d GEMM launches of a step)" % (g["launches"] // args.steps), achieved=gemm_tf, peak=tflops_peak, unit="TFLOP/s",
-                      frac=gemm_tf / tflops_peak, traffic=None,
+                      frac=gemm_tf / tflops_peak, traffic=traffic,
                       note="sum of 2*M*N*K over the GEMM launches of a step / their CUDA-event time, vs %s sustained bf16 peak; "
                            "whole step: %.1f TFLOP/s (%.3f of peak)" % (which, step_tf, step_tf / tflops_peak)),
         kernels=kernels,
