@@ -89,6 +89,7 @@ struct LstmParams {
   int ld_out = 0;
   float* out_f32 = nullptr;            // same layout, fp32                                             (optional)
   int ld_out_f32 = 0;
+  int dbg = 0;                         // micro-benchmark ablations only (B200PF_LSTM_DBG); 0 in the product
 };
 int lstm_launch(const LstmParams& p, cudaStream_t s);
 int lstm_max_active_clusters();  // co-resident 16-CTA clusters on the current device (diagnostics)
