@@ -29,7 +29,8 @@ class Config(C.Structure):
 class Result(C.Structure):
     _fields_ = [("token_counts", c_i32p), ("token_offsets", c_i32p), ("lfr_frames", c_i32p),
                 ("token_ids", c_i32p), ("fire_frames", c_i32p), ("cap_tokens", C.c_int64), ("n_tokens", C.c_int64),
-                ("us_alphas", c_f32p), ("us_peaks", c_f32p), ("us_offsets", c_i32p), ("cap_us", C.c_int64)]
+                ("us_alphas", c_f32p), ("us_peaks", c_f32p), ("us_offsets", c_i32p), ("cap_us", C.c_int64),
+                ("token_lse", c_f32p), ("topk_logprob", c_f32p), ("topk_ids", c_i32p), ("topk_k", C.c_int32)]
 
 
 class B200PFError(RuntimeError):
@@ -52,7 +53,7 @@ EXPORTS = [
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
-    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk",
 ]
 
 
@@ -369,6 +370,8 @@ class Engine:
 
     def set_option(self, key, value):
         _check(lib().b200pf_engine_set_option(self.h, key.encode(), int(value)))
+        if key == "logprob_topk":
+            self._topk = int(value)
 
     def profile_read(self, reset=True):
         names = (C.c_char_p * 16)()
@@ -476,8 +479,17 @@ class Batch:
             out["us_peaks"] = np.zeros(cap_us, np.float32)
         r = Result(_p(out["token_counts"], c_i32p), _p(out["token_offsets"], c_i32p), _p(out["lfr_frames"], c_i32p),
                    _p(out["token_ids"], c_i32p), _p(out["fire_frames"], c_i32p), cap, 0,
-                   _p(out.get("us_alphas")), _p(out.get("us_peaks")), _p(out["us_offsets"], c_i32p), cap_us)
+                   _p(out.get("us_alphas")), _p(out.get("us_peaks")), _p(out["us_offsets"], c_i32p), cap_us, None, None, None, 0)
+        k = int(getattr(self.engine, "_topk", 0))
+        if k > 0:
+            out["token_lse"] = np.zeros(cap, np.float32)
+            out["topk_logprob"] = np.zeros((cap, k), np.float32)
+            out["topk_ids"] = np.zeros((cap, k), np.int32)
+            r.token_lse, r.topk_logprob, r.topk_ids = _p(out["token_lse"]), _p(out["topk_logprob"]), _p(out["topk_ids"], c_i32p)
         _check(lib().b200pf_batch_collect(self.h, C.byref(r), C.c_void_p(stream or 0)))
+        if k > 0:
+            for key in ("token_lse", "topk_logprob", "topk_ids"):
+                out[key] = out[key][:int(r.n_tokens)]
         if ts:
             nu = int(out["us_offsets"][n])
             out["us_alphas"] = out["us_alphas"][:nu]
@@ -540,6 +552,16 @@ def op_lstm(x, seq_off, seq_len, w_ih, w_hh, b_ih, b_hh, bf16_out=False, device=
     _check(lib().b200pf_op_lstm(device, _p(x), x.shape[0], _p(so, c_i32p), _p(sl, c_i32p), len(so), n_dir, _p(w_ih), _p(w_hh),
                                 _p(b_ih), _p(b_hh), int(bf16_out), _p(out)))
     return out
+
+
+def op_logprob_topk(logits, k, device=0):
+    x = _f32(logits)
+    rows, V = x.shape
+    lse = np.zeros(rows, np.float32)
+    lp = np.zeros((rows, k), np.float32)
+    ids = np.zeros((rows, k), np.int32)
+    _check(lib().b200pf_op_logprob_topk(device, _p(x), rows, V, k, _p(lse), _p(lp), _p(ids, c_i32p)))
+    return lse, lp, ids
 
 
 def op_lstm_bench(n_seq, length, n_dir=1, iters=3, device=0):

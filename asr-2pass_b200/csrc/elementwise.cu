@@ -387,6 +387,67 @@ __global__ void argmax_decode_kernel(const unsigned long long* __restrict__ pack
   ids[g] = (int)(0xFFFFFFFFu - (uint32_t)(packed[g] & 0xFFFFFFFFull));
 }
 
+// K10  log-softmax statistics + top-k per decoder row (the pruned posterior the host-side log-prob consumers read:
+// WfstDecoder::Search, wfst-decoder.cpp:27-57; CtcPrefixDecoder).  One warp per row.  The order is total and
+// deterministic: value descending, index ascending (so entry 0 is FindMax's first-max-wins argmax, util.cpp:63-74).
+__global__ void __launch_bounds__(256)
+logprob_topk_kernel(const float* __restrict__ logits, int V, const int* __restrict__ n_dev, int cap, int k,
+                    float* __restrict__ lse_out, float* __restrict__ lp_out, int* __restrict__ id_out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n = n_dev ? min(*n_dev, cap) : cap;
+  if (row >= n) return;
+  const float* x = logits + (size_t)row * V;
+  float m = -INFINITY;
+  for (int i = lane * 4; i < V; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float sum = 0.f;
+  for (int i = lane * 4; i < V; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+  }
+  sum = warp_sum(sum);
+  const float lse = m + logf(sum);
+  if (lane == 0) lse_out[row] = lse;
+  // k rounds of "largest key strictly below the previous winner"; key = (value desc, index asc)
+  float pv = INFINITY;
+  int pi = -1;
+  for (int j = 0; j < k; ++j) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane * 4; i < V; i += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float val = e[q];
+        const int idx = i + q;
+        const bool below_prev = (val < pv) || (val == pv && idx > pi);
+        const bool better = (val > bv) || (val == bv && idx < bi);
+        if (below_prev && better) { bv = val; bi = idx; }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      lp_out[(size_t)row * k + j] = bv - lse;
+      id_out[(size_t)row * k + j] = bi;
+    }
+    pv = bv;
+    pi = bi;
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
   pdl_wait();
   pdl_launch_dependents();
@@ -451,6 +512,12 @@ int cif_embed_launch(const float* enc_f32, const float* cur, const float* rem, c
 int argmax_decode_launch(const unsigned long long* packed, const int* n_dev, int cap, int* ids, cudaStream_t s) {
   if (cap <= 0) return 0;
   return launch_kernel(argmax_decode_kernel, dim3((cap + 255) / 256), dim3(256), 0, s, packed, n_dev, cap, ids);
+}
+
+int logprob_topk_launch(const float* logits, int V, const int* n_dev, int cap, int k, float* lse, float* lp, int* ids, cudaStream_t s) {
+  if (cap <= 0 || k <= 0) return 0;
+  if (V & 3) return (int)cudaErrorInvalidValue;
+  return launch_kernel(logprob_topk_kernel, dim3((cap + 7) / 8), dim3(256), 0, s, logits, V, n_dev, cap, k, lse, lp, ids);
 }
 
 int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {

@@ -450,6 +450,10 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   cudaFree(e->tap_feats);
   cudaFree(e->tap_emb);
   cudaFree(e->tap_logits);
+  cudaFree(e->full_logits);
+  cudaFree(e->topk_lse);
+  cudaFree(e->topk_lp);
+  cudaFree(e->topk_id);
   cudaStreamSynchronize(e->side);
   cudaStreamDestroy(e->side);
   cudaEventDestroy(e->ev_fork);
@@ -486,6 +490,19 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   }
   if (strcmp(key, "overlap") == 0) {
     e->overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return 0;
+  }
+  if (strcmp(key, "logprob_topk") == 0) {
+    if (value < 0 || value > B200PF_MAX_TOPK) { set_error("logprob_topk must be in [0, 32]"); return B200PF_ERR_INVALID; }
+    CK(cudaSetDevice(e->device), "cudaSetDevice");
+    if (value > 0 && !e->topk_lp) {
+      const size_t R = (size_t)e->cfg.max_rows;
+      CK(cudaMalloc((void**)&e->full_logits, R * (size_t)e->cfg.vocab * 4), "cudaMalloc(logits)");
+      CK(cudaMalloc((void**)&e->topk_lse, R * 4), "cudaMalloc(topk)");
+      CK(cudaMalloc((void**)&e->topk_lp, R * B200PF_MAX_TOPK * 4), "cudaMalloc(topk)");
+      CK(cudaMalloc((void**)&e->topk_id, R * B200PF_MAX_TOPK * 4), "cudaMalloc(topk)");
+    }
+    e->topk = value;
     return 0;
   }
   if (strcmp(key, "attn_online") == 0) {
@@ -577,6 +594,7 @@ void b200pf_batch_destroy(b200pf_batch* b) {
   cudaFreeHost(b->h_meta);
   cudaFreeHost(b->h_res);
   if (b->h_us) cudaFreeHost(b->h_us);
+  if (b->h_topk) cudaFreeHost(b->h_topk);
   if (b->d_hw) cudaFree(b->d_hw);
   cudaEventDestroy(b->staged);
   delete b;
@@ -906,10 +924,14 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   { int rc = dec_ffn(e->dec3); if (rc) return rc; }
   LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
   CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
+  float* logits_out = e->taps ? e->tap_logits : (e->topk > 0 ? e->full_logits : nullptr);
   { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
-    if (e->taps) { ep.out_f32 = e->tap_logits; ep.ld_out_f32 = c.vocab; }
+    if (logits_out) { ep.out_f32 = logits_out; ep.ld_out_f32 = c.vocab; }
     CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep, 0, 0, 13), "gemm vocab"); }
   LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
+  if (e->topk > 0)
+    LAUNCH(6, Lest * c.vocab * 4 * 2, logprob_topk_launch(logits_out, c.vocab, Ldev, Lcap, e->topk, e->topk_lse, e->topk_lp, e->topk_id, s), "logprob topk");
+  b->topk_run = e->topk;
   return 0;
 }
 
@@ -934,7 +956,19 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
       CK(cudaMemcpyAsync(b->h_us + R * 3, e->us_peaks, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_peaks");
     }
   }
+  const int tk = b->topk_run;
+  const bool want_topk = tk > 0 && res->topk_logprob && res->topk_ids && b->n_seg > 0;
+  float* h_lse = nullptr; float* h_lp = nullptr; int* h_tid = nullptr;
+  if (want_topk) {
+    if (!b->h_topk) CK(cudaMallocHost((void**)&b->h_topk, R * (4 + 2 * 4 * B200PF_MAX_TOPK)), "cudaMallocHost(topk)");
+    h_lse = (float*)b->h_topk; h_lp = h_lse + R; h_tid = (int*)(h_lp + R * B200PF_MAX_TOPK);
+    // token count is only known on the device: copy the capacity-bounded prefix that can hold tokens (<= rows)
+    CK(cudaMemcpyAsync(h_lse, e->topk_lse, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H lse");
+    CK(cudaMemcpyAsync(h_lp, e->topk_lp, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk lp");
+    CK(cudaMemcpyAsync(h_tid, e->topk_id, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk ids");
+  }
   CK(cudaStreamSynchronize(s), "forward");
+  res->topk_k = want_topk ? tk : 0;
   int64_t out = 0, us_out = 0;
   double fl = 0.0;
   const b200pf_config& c = e->cfg;
@@ -957,6 +991,11 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
       if (out + cnt > res->cap_tokens) { set_error("result token capacity too small"); return B200PF_ERR_CAPACITY; }
       const int o = h_tok_off[d];
       if (res->token_ids) memcpy(res->token_ids + out, h_ids + o, (size_t)cnt * 4);
+      if (want_topk) {
+        if (res->token_lse) memcpy(res->token_lse + out, h_lse + o, (size_t)cnt * 4);
+        memcpy(res->topk_logprob + out * tk, h_lp + (size_t)o * tk, (size_t)cnt * tk * 4);
+        memcpy(res->topk_ids + out * tk, h_tid + (size_t)o * tk, (size_t)cnt * tk * 4);
+      }
       if (res->fire_frames) memcpy(res->fire_frames + out, h_frame + o, (size_t)cnt * 4);
       out += cnt;
       const double T = b->T_in[i], L = cnt, Dm = c.d_model, Fd = c.d_ff;

@@ -128,6 +128,12 @@ struct b200pf_engine {
   float* tap_feats = nullptr;   // [R, 560]
   float* tap_emb = nullptr;     // [R, 512]
   float* tap_logits = nullptr;  // [R, vocab]
+  // pruned posteriors (option "logprob_topk" = k)
+  int topk = 0;
+  float* full_logits = nullptr;   // [R, vocab] fp32, only allocated when topk > 0 (shared with tap_logits when taps are on)
+  float* topk_lse = nullptr;      // [R]
+  float* topk_lp = nullptr;       // [R, 32]
+  int* topk_id = nullptr;         // [R, 32]
 };
 
 struct b200pf_batch {
@@ -159,8 +165,10 @@ struct b200pf_batch {
   int* d_tok_frame = nullptr; // [R]
   uint8_t* h_res = nullptr;   // pinned: n_tok[S] tok_off[S+1] ids[R] tok_frame[R]
   float* h_us = nullptr;      // pinned: us_alphas[3R] us_peaks[3R] (timestamp models)
+  uint8_t* h_topk = nullptr;  // pinned: lse[R] lp[R*32] ids[R*32], allocated on first use
   __nv_bfloat16* d_hw = nullptr;  // [max_hotwords, 512] bf16 hotword embeddings of this batch (contextual models)
   int n_hw = 0;
+  int topk_run = 0;   // k the last run produced pruned posteriors with
   // staged state
   int n_seg_in = 0;             // segments the caller passed
   int n_seg = 0;                // segments on the device (T > 0)

@@ -105,6 +105,11 @@ int us_peak_launch(const float* alpha2, const int* seq_off, const int* seq_len, 
 // hotword Embedding lookup: out[j] = table[ids[j]] (bf16 rows of 512)
 int embed_gather_launch(const __nv_bfloat16* table, int vocab, const int* ids, int n, __nv_bfloat16* out, cudaStream_t s);
 
+// K10 pruned posteriors for the host-side log-prob consumers (WfstDecoder::Search src/wfst-decoder.cpp:27-57,
+//     CtcPrefixDecoder): per decoder row, logsumexp and the k largest log-softmax values with their token ids, ordered
+//     by (value descending, index ascending).  logits [cap, V] fp32; outputs lse [cap], lp / ids [cap, k].
+int logprob_topk_launch(const float* logits, int V, const int* n_dev, int cap, int k, float* lse, float* lp, int* ids, cudaStream_t s);
+
 // fp32 -> bf16 conversion (weight upload)
 int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
 

@@ -362,6 +362,20 @@ int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, 
   return check_cuda(cudaMemcpy(us_peaks, dUp.p, (size_t)rows * 4, cudaMemcpyDeviceToHost), "D2H");
 }
 
+int b200pf_op_logprob_topk(int device, const float* logits, int rows, int V, int k, float* lse, float* lp, int32_t* ids) {
+  RC(select_device(device));
+  if (rows <= 0 || k <= 0 || k > B200PF_MAX_TOPK || (V & 3)) { set_error("op_logprob_topk: bad argument"); return B200PF_ERR_INVALID; }
+  DevBuf dL, dLse, dLp, dId;
+  RC(up_f32(logits, (size_t)rows * V, &dL));
+  RC(dLse.alloc((size_t)rows * 4)); RC(dLp.alloc((size_t)rows * k * 4)); RC(dId.alloc((size_t)rows * k * 4));
+  int rc = logprob_topk_launch(dL.as<float>(), V, nullptr, rows, k, dLse.as<float>(), dLp.as<float>(), dId.as<int>(), 0);
+  if (rc) return check_cuda((cudaError_t)rc, "logprob_topk launch");
+  RC(sync_ok("op_logprob_topk"));
+  RC(check_cuda(cudaMemcpy(lse, dLse.p, (size_t)rows * 4, cudaMemcpyDeviceToHost), "D2H"));
+  RC(check_cuda(cudaMemcpy(lp, dLp.p, (size_t)rows * k * 4, cudaMemcpyDeviceToHost), "D2H"));
+  return check_cuda(cudaMemcpy(ids, dId.p, (size_t)rows * k * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
 int b200pf_op_frontend(b200pf_engine* e, const int16_t* pcm, int64_t n, float* fb_out, float* feats_out) {
   if (!e || !pcm) { set_error("null argument"); return B200PF_ERR_INVALID; }
   RC(check_cuda(cudaSetDevice(e->device), "cudaSetDevice"));

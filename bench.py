@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--segments", type=int, default=1024)
     ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "98304")))
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 (default, the bench line): BASELINE.json configs[1]; config5: 32 segments x 60 s per GPU "
+                         "(configs[4]: 256 x 60 s over 8 GPUs, T = 1000 LFR frames) - an extra measurement, not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
@@ -183,6 +186,10 @@ def main():
     cfg, W = synth.make_weights()
     means, vars_ = synth.make_cmvn()
     workload = "configs[1]: %d synthetic VAD segments U[2,20] s, length-bucketed, Paraformer-large random-init" % args.segments
+    if args.workload == "config5":
+        args.segments = 32
+        lens = np.full(32, 960000, np.int64)
+        workload = "configs[4]: max-length stress, 32 segments x 60 s per GPU (256 over 8 GPUs), T = 1000 LFR frames"
 
     if args.impl == "reference":
         # The reference's own CPU implementation cannot be built or installed here (its neural graph lives in an
@@ -207,6 +214,11 @@ def main():
         return
 
     pcm, offs = synth.make_segments(args.segments)
+    if args.workload == "config5":
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        one = synth.make_audio(960000, 4321)
+        pcm = np.tile(one, 32)
+        args.no_cpu_baseline = True
     cb = None
     if rank == 0 and world == 1 and args.gpus == 1 and not args.no_cpu_baseline:
         segs = [pcm[offs[i]:offs[i + 1]] for i in range(args.segments)]

@@ -45,6 +45,7 @@ typedef struct b200pf_config {
 
 #define B200PF_MAX_HOTWORDS 4096  /* rows of the hotword embedding a batch may carry (incl. the blank row) */
 #define B200PF_HOTWORD_LEN 10     /* max_hotword_len, paraformer.cpp:600 */
+#define B200PF_MAX_TOPK 32        /* largest k of the pruned-posterior output */
 
 /* Per-batch results, written into caller-owned host buffers by b200pf_batch_collect.
  * Segment i produced token_counts[i] tokens; its ids are token_ids[token_offsets[i] .. +count).
@@ -65,6 +66,13 @@ typedef struct b200pf_result {
   float* us_peaks;         /* [cap_us] */
   int32_t* us_offsets;     /* [n_seg + 1] */
   int64_t cap_us;
+  /* pruned posteriors (engine option "logprob_topk" = k > 0; all may be NULL): per token, logsumexp of its logits row and
+   * the k largest log-softmax values with their ids, ordered by (value descending, id ascending) - what the reference's
+   * log-prob consumers (WfstDecoder::Search, wfst-decoder.cpp:27-57; CtcPrefixDecoder) need instead of [L,8404] rows. */
+  float* token_lse;        /* [cap_tokens] */
+  float* topk_logprob;     /* [cap_tokens * k] */
+  int32_t* topk_ids;       /* [cap_tokens * k] */
+  int32_t topk_k;          /* out: k of this result (0 when the option is off) */
 } b200pf_result;
 
 const char* b200pf_last_error(void);
@@ -89,6 +97,7 @@ const char* b200pf_engine_lang(const b200pf_engine* e);
 /* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (0 off, 1 FSMN enqueued
  * first, 2 = default: attention enqueued first) runs the FSMN memory block on a low-priority side stream concurrently
  * with the attention kernel; "attn_online" (default 1) selects the single-pass attention kernel, 0 the two-pass one;
+ * "logprob_topk" = k (0..32, default 0) also produces pruned log-softmax posteriors per token (b200pf_result.topk_*);
  * "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 /* Option "profile" = 1 brackets every launch of b200pf_batch_run with CUDA events on the launching stream.
@@ -181,6 +190,8 @@ int b200pf_op_lstm_bench(int device, int n_seq, int len, int n_dir, int iters, f
 /* us_alphas / us_cif_peak from raw alpha2 (already relu(sigmoid*s-n)): per segment scale to n_tok and cif_wo_hidden. */
 int b200pf_op_us_peaks(int device, const float* alpha2, const int32_t* seq_off, const int32_t* seq_len, const int32_t* n_tok,
                        int n_seg, int rows, float threshold, float* us_alphas, float* us_peaks);
+/* logsumexp + top-k log-softmax of logits [rows, V] (V % 4 == 0): lse [rows], lp / ids [rows, k]. */
+int b200pf_op_logprob_topk(int device, const float* logits, int rows, int V, int k, float* lse, float* lp, int32_t* ids);
 /* fbank + LFR/CMVN of one segment (int16 PCM); fb_out [n_fb,80], feats_out [T,560] (either may be NULL). */
 int b200pf_op_frontend(b200pf_engine* e, const int16_t* pcm, int64_t n, float* fb_out, float* feats_out);
 

@@ -418,6 +418,22 @@ def forward(feats, W, cfg: PfConfig, emulate_bf16=False, want_taps=True, hw_emb=
     return out
 
 
+def logprob_topk(logits, k: int):
+    """What the reference's log-prob consumers read from the graph's log_softmax output (WfstDecoder::Search,
+    wfst-decoder.cpp:27-57), pruned to the k best entries per row.  Order: value descending, index ascending, so
+    entry 0 is FindMax's first-max-wins argmax (util.cpp:63-74).  Returns (lse [L], logprob [L,k], ids [L,k])."""
+    import numpy as np
+    x = torch.as_tensor(logits, dtype=torch.float32)
+    lse = torch.logsumexp(x, dim=-1)
+    lp = (x - lse[:, None]).numpy()
+    xn = x.numpy()
+    ids = np.zeros((x.shape[0], k), np.int64)
+    for r in range(x.shape[0]):
+        order = np.lexsort((np.arange(x.shape[1]), -xn[r]))   # primary: -value, secondary: index
+        ids[r] = order[:k]
+    return lse.numpy(), np.take_along_axis(lp, ids, 1), ids
+
+
 def flops(T: int, L: int, cfg: PfConfig = PfConfig()) -> float:
     """Algorithmic FLOPs of one segment: 2*M*N*K per contraction."""
     D, Fd, V = cfg.d_model, cfg.d_ff, cfg.vocab

@@ -416,3 +416,36 @@ def test_microbatcher_results_equal_direct_calls(capi, synth, small, tmp_path_fa
     assert st["segments"] == len(segs) and st["batches"] <= 3 and st["max_batch_seen"] >= 4
     mb.close()
     h.close()
+
+
+def test_logprob_topk_kernel(capi, gpu):
+    """Pruned posteriors: logsumexp + top-k log-softmax with the (value desc, index asc) order."""
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((37, 8404)) * 3).astype(np.float32)
+    x[3, 100] = x[3, 7000] = x[3].max() + 1.0            # exact tie at the top: the lower index comes first
+    x[5, :] = 0.25                                        # a constant row: ids 0..k-1
+    lse, lp, ids = capi.op_logprob_topk(x, 16)
+    lse_o, lp_o, ids_o = R.logprob_topk(x, 16)
+    assert np.array_equal(ids, ids_o)
+    assert np.abs(lse - lse_o).max() <= 1e-5 and np.abs(lp - lp_o).max() <= 1e-5
+    assert list(ids[3, :2]) == [100, 7000] and list(ids[5]) == list(range(16))
+    assert np.all(np.diff(lp, axis=1) <= 0)
+
+
+def test_forward_returns_pruned_posteriors(capi, synth, small):
+    eng = small["eng"]
+    pcm = synth.make_audio(52800, 321)
+    b = capi.Batch(eng, len(pcm) + 16)
+    eng.set_option("logprob_topk", 8)
+    try:
+        res = b.forward_s16(pcm, np.array([0, len(pcm)], np.int64))
+        lg = b.tap("logits", 0)
+        lse_o, lp_o, ids_o = R.logprob_topk(lg, 8)
+        assert res["topk_ids"].shape == (res["n_tokens"], 8)
+        assert np.array_equal(res["topk_ids"], ids_o)
+        assert np.array_equal(res["topk_ids"][:, 0], res["token_ids"])            # entry 0 is the greedy token
+        assert np.abs(res["topk_logprob"] - lp_o).max() <= 1e-5 and np.abs(res["token_lse"] - lse_o).max() <= 1e-5
+    finally:
+        eng.set_option("logprob_topk", 0)
+    res = b.forward_s16(pcm, np.array([0, len(pcm)], np.int64))
+    assert "topk_ids" not in res

@@ -171,6 +171,17 @@ def test_contextual_decoder_reduces_to_self_attention_path_when_bias_output_is_z
     assert not torch.equal(a, c)
 
 
+def test_logprob_topk_oracle_order_and_values():
+    import torch
+    from oracle import paraformer_ref as R
+    x = np.array([[0.0, 2.0, 2.0, -1.0, 1.0, 2.0, 0.5, 0.0]], np.float32)
+    lse, lp, ids = R.logprob_topk(x, 4)
+    assert list(ids[0]) == [1, 2, 5, 4]                                   # ties by ascending index
+    ref = torch.log_softmax(torch.from_numpy(x), -1).numpy()
+    assert np.allclose(lp[0], ref[0, ids[0]], atol=1e-6) and abs(lse[0] - np.log(np.exp(x).sum())) < 1e-5
+    assert ids[0, 0] == F.find_max(x[0])[1]
+
+
 def test_cif_matches_closed_form():
     import torch
     from oracle import paraformer_ref as R
