@@ -351,6 +351,249 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Product kernel: single pass (running maximum, lazy rescale — see above) AND all heads of one (segment, query tile)
+// pipelined through ONE CTA.  At this path's lengths a (tile, head) work item is only 1-6 key blocks, so a CTA per item
+// spends most of its life in set-up, first-load latency and drain.  Here the TMA producer, the MMA issuer and the softmax
+// warps run one continuous stream of n_heads x nb key blocks: barriers, TMEM and the K/V ring are set up once, the K/V
+// loads of head h+1 are in flight while head h finishes, and head h's output is written while S of head h+1 is computed.
+// Q is single buffered: its reload waits for the last S MMA of the previous head (q_empty), O is handed over through
+// o_full / o_empty.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AArgs a, int n_heads) {
+  pdl_wait();   // q_len of the decoder is produced by the CIF kernels
+  pdl_launch_dependents();
+  const AttnWork w = a.work[blockIdx.x];
+  const int Tq = a.q_len[w.seg];
+  const int Tk = a.kv_len[w.seg];
+  if (w.q0 >= Tq || Tk <= 0) return;  // whole CTA, before any barrier
+  const int nb = (Tk + BKV - 1) / BKV;
+  const int q_row = a.q_row_off[w.seg] + w.q0;
+  const int kv_row = a.kv_row_off[w.seg];
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + Q_BYTES;
+  uint8_t* sP = sKV + KV_STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BUFS * P_BYTES);
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* q_empty = bars + 1;             // 1
+  uint64_t* kv_full = bars + 2;             // 2
+  uint64_t* kv_empty = bars + 4;            // 2
+  uint64_t* s_full = bars + 6;              // 2
+  uint64_t* s_empty = bars + 8;             // 2
+  uint64_t* p_full = bars + 10;             // 1
+  uint64_t* p_empty = bars + 11;            // 1
+  uint64_t* o_full = bars + 12;             // 1
+  uint64_t* o_empty = bars + 13;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
+    mbar_init(p_full, 4); mbar_init(p_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;   // key blocks streamed so far, over all heads
+      for (int h = 0; h < n_heads; ++h) {
+        mbar_wait(q_empty, (uint32_t)((h & 1) ^ 1));
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, a.q_col0 + h * HD, q_row);
+        tma_load_2d(sQ + Q_BYTES / 2, &tmQ, q_full, a.q_col0 + h * HD + 64, q_row);
+        for (int j = 0; j < nb; ++j, ++g) {
+          const int stage = g % KV_STAGES;
+          mbar_wait(&kv_empty[stage], (uint32_t)(((g / KV_STAGES) & 1) ^ 1));
+          mbar_arrive_expect_tx(&kv_full[stage], STAGE_BYTES);
+          uint8_t* dst = sKV + stage * STAGE_BYTES;
+          const int r = kv_row + j * BKV;
+          tma_load_2d(dst, &tmKV, &kv_full[stage], a.k_col0 + h * HD, r);
+          tma_load_2d(dst + K_BYTES / 2, &tmKV, &kv_full[stage], a.k_col0 + h * HD + 64, r);
+          tma_load_2d(dst + K_BYTES, &tmKV, &kv_full[stage], a.v_col0 + h * HD, r);
+          tma_load_2d(dst + K_BYTES + K_BYTES / 2, &tmKV, &kv_full[stage], a.v_col0 + h * HD + 64, r);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, HD, 0, 1);  // B (=V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](int g, bool last_of_head) {
+        const int stage = g % KV_STAGES;
+        const int sb = g & 1;
+        mbar_wait(&kv_full[stage], (uint32_t)((g / KV_STAGES) & 1));
+        mbar_wait(&s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + stage * STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint64_t da = umma_desc_sw128(q_addr + (ks >> 2) * (Q_BYTES / 2)) + 2 * (ks & 3);
+          const uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (K_BYTES / 2)) + 2 * (ks & 3);
+          umma_bf16(tmem_base + sb * BKV, da, db, idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[sb]);
+        if (last_of_head) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
+      };
+      int g0 = 0;
+      for (int h = 0; h < n_heads; ++h, g0 += nb) {
+        mbar_wait(q_full, (uint32_t)(h & 1));
+        tc_fence_after();
+        issue_s(g0, nb == 1);
+        for (int jj = 0; jj < nb; ++jj) {
+          const int g = g0 + jj;
+          if (jj + 1 < nb) issue_s(g + 1, jj + 2 == nb);
+          mbar_wait(p_full, (uint32_t)(g & 1));
+          if (jj == 0) mbar_wait(o_empty, (uint32_t)((h & 1) ^ 1));   // the previous head's O has been read out
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(sP);
+          const uint32_t v_addr = smem_u32(sKV + (g % KV_STAGES) * STAGE_BYTES + K_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks) {
+            const uint64_t da = umma_desc_sw128(p_addr) + 2 * ks;
+            const uint64_t db = umma_desc_sw128_mn(v_addr + ks * 2048, K_BYTES / 2);
+            umma_bf16(tmem_o, da, db, idesc_pv, (jj | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[g % KV_STAGES]);
+          umma_commit(p_empty);
+        }
+        umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const bool row_ok = (w.q0 + row) < Tq;
+    uint32_t r[32], r2[32];
+    int g0 = 0;
+    for (int h = 0; h < n_heads; ++h, g0 += nb) {
+      float m = -INFINITY, l = 0.f, m_used = 0.f;
+      for (int jj = 0; jj < nb; ++jj) {
+        const int g = g0 + jj;
+        const int sb = g & 1;
+        mbar_wait(&s_full[sb], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        const int nvalid = Tk - jj * BKV;
+        tmem_ld_32x32(tmem_base + lane_addr + sb * BKV, r);
+        tmem_ld_32x32(tmem_base + lane_addr + sb * BKV + 32, r2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);   // the scores are in registers
+        float mb = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nvalid) mb = fmaxf(mb, __uint_as_float(r[c]));
+          if (32 + c < nvalid) mb = fmaxf(mb, __uint_as_float(r2[c]));
+        }
+        m = fmaxf(m, mb);
+        float factor = 1.f;
+        bool need = false;
+        if (jj == 0) {
+          m_used = m;
+        } else if ((m - m_used) * a.scale_log2e > 8.f) {
+          need = true;
+          factor = ex2((m_used - m) * a.scale_log2e);
+          m_used = m;
+          l *= factor;
+        }
+        const float mc = m_used * a.scale_log2e;
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = (c < nvalid) ? ex2(fmaf(__uint_as_float(r[c]), a.scale_log2e, -mc)) : 0.f;
+          const float p1 = (c + 1 < nvalid) ? ex2(fmaf(__uint_as_float(r[c + 1]), a.scale_log2e, -mc)) : 0.f;
+          const float p2 = (32 + c < nvalid) ? ex2(fmaf(__uint_as_float(r2[c]), a.scale_log2e, -mc)) : 0.f;
+          const float p3 = (33 + c < nvalid) ? ex2(fmaf(__uint_as_float(r2[c + 1]), a.scale_log2e, -mc)) : 0.f;
+          l += (p0 + p1) + (p2 + p3);
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+          pk[16 + (c >> 1)] = pack_bf16x2(p2, p3);
+        }
+        // P V of the previous block has completed once p_empty flips: P's buffer is free and O is quiescent
+        mbar_wait(p_empty, (uint32_t)((g & 1) ^ 1));
+        if (__any_sync(0xffffffffu, need)) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld_32x32(tmem_o + lane_addr + c4 * 32, r);
+            tmem_ld_wait();
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              lo[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+              hi[c] = __float_as_uint(__uint_as_float(r[16 + c]) * factor);
+            }
+            tmem_st_32x16(tmem_o + lane_addr + c4 * 32, lo);
+            tmem_st_32x16(tmem_o + lane_addr + c4 * 32 + 16, hi);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        const uint32_t prow = smem_u32(sP + row * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(prow + ((j ^ (row & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- this head's output ----
+      mbar_wait(o_full, (uint32_t)(h & 1));
+      tc_fence_after();
+      const float inv = 1.f / l;
+      __nv_bfloat16* orow = a.out + (size_t)(q_row + row) * a.ldo + h * HD;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        tmem_ld_32x32(tmem_o + lane_addr + c4 * 32, r);
+        tmem_ld_wait();
+        if (c4 == 3) {   // O is in registers: the next head's first P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[8 * gq + 0]) * inv, __uint_as_float(r[8 * gq + 1]) * inv);
+            o.y = pack_bf16x2(__uint_as_float(r[8 * gq + 2]) * inv, __uint_as_float(r[8 * gq + 3]) * inv);
+            o.z = pack_bf16x2(__uint_as_float(r[8 * gq + 4]) * inv, __uint_as_float(r[8 * gq + 5]) * inv);
+            o.w = pack_bf16x2(__uint_as_float(r[8 * gq + 6]) * inv, __uint_as_float(r[8 * gq + 7]) * inv);
+            stg128(orow + c4 * 32 + gq * 8, o);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check (test-only): one warp per query row, online softmax in fp32.
 // ---------------------------------------------------------------------------------------------
@@ -406,6 +649,8 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
     if (err != cudaSuccess) return (int)err;
     err = cudaFuncSetAttribute(attn_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(attn_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (err != cudaSuccess) return (int)err;
     attr_set = true;
   }
   CUtensorMap tmQ, tmKV;
@@ -414,6 +659,7 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   rc = make_tmap_bf16_sw128(&tmKV, p.kv, (uint64_t)p.kv_rows, (uint64_t)p.ldkv, (uint64_t)p.ldkv, BKV);
   if (rc) return rc;
   AArgs a = make_args(p);
+  if (p.online == 2) return launch_kernel(attn_heads_kernel, dim3(p.n_work), dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a, p.n_heads);
   dim3 grid(p.n_work, p.n_heads);
   if (p.online) return launch_kernel(attn_tcgen05_kernel<true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
   return launch_kernel(attn_tcgen05_kernel<false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);

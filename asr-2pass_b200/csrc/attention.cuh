@@ -32,7 +32,8 @@ struct AttnProblem {
   int n_work = 0;
   int n_heads = 4;
   float scale = 0.08838834764831845f;  // 128^-1/2
-  int online = 1;                      // 1: single pass with a running maximum (default); 0: exact two-pass variant
+  int online = 2;                      // 2: single pass, all heads pipelined through one CTA (product); 1: single pass, one CTA
+                                       // per head; 0: exact two-pass variant, one CTA per head
 };
 
 int attention_tcgen05(const AttnProblem& p, cudaStream_t stream);

@@ -506,7 +506,7 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
     return 0;
   }
   if (strcmp(key, "attn_online") == 0) {
-    e->attn_online = value ? 1 : 0;
+    e->attn_online = value < 0 ? 0 : (value > 2 ? 2 : value);
     return 0;
   }
   if (strcmp(key, "profile") == 0) {

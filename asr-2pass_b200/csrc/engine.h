@@ -63,7 +63,7 @@ struct b200pf_engine {
   cudaStream_t side = nullptr;          // FSMN memory block runs here, concurrently with the attention kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 2;
-  int attn_online = 1;
+  int attn_online = 2;
   std::string lang = "zh-cn";
   std::vector<std::string> tokens;
   std::mutex mu;  // one forward at a time per engine (the workspace is shared)

@@ -222,7 +222,7 @@ int b200pf_op_attention(int device, const float* q, const float* k, const float*
   p.out = dOutB.as<__nv_bfloat16>(); p.ldo = D;
   p.q_row_off = dqo.as<int>(); p.q_len = dql.as<int>(); p.kv_row_off = dko.as<int>(); p.kv_len = dkl.as<int>();
   p.work = dWork.as<AttnWork>(); p.n_work = (int)work.size(); p.n_heads = n_heads;
-  p.online = impl == 2 ? 0 : 1;
+  p.online = impl == 2 ? 0 : (impl == 3 ? 1 : 2);
   int rc = impl == 1 ? attention_check_kernel(p, 0) : attention_tcgen05(p, 0);
   if (rc) return check_cuda((cudaError_t)rc, "attention launch");
   bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)q_rows * D);

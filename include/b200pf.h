@@ -96,7 +96,8 @@ const char* b200pf_engine_token(const b200pf_engine* e, int id);
 const char* b200pf_engine_lang(const b200pf_engine* e);
 /* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (0 off, 1 FSMN enqueued
  * first, 2 = default: attention enqueued first) runs the FSMN memory block on a low-priority side stream concurrently
- * with the attention kernel; "attn_online" (default 1) selects the single-pass attention kernel, 0 the two-pass one;
+ * with the attention kernel; "attn_online" selects the attention kernel (2 = default: single pass, heads pipelined per CTA; 1: single pass, CTA
+ * per head; 0: two-pass);
  * "logprob_topk" = k (0..32, default 0) also produces pruned log-softmax posteriors per token (b200pf_result.topk_*);
  * "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
@@ -169,7 +170,8 @@ int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bi
 int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
                         int in_bf16, float* out_f32, float* out_bf16_as_f32);
 /* q [sum Tq,H*128], k,v [sum Tk,H*128]; segment s owns rows q_off[s].. and kv_off[s]..; impl 0 = tcgen05
- * kernel (product: single pass, running maximum), 1 = CUDA-core cross-check, 2 = tcgen05 exact two-pass variant. */
+ * kernel (product: single pass, running maximum, all heads pipelined through one CTA), 1 = CUDA-core cross-check,
+ * 2 = tcgen05 exact two-pass variant, 3 = tcgen05 single pass with one CTA per head. */
 int b200pf_op_attention(int device, const float* q, const float* k, const float* v, const int32_t* q_off,
                         const int32_t* q_len, const int32_t* kv_off, const int32_t* kv_len, int n_seg, int n_heads,
                         int64_t q_rows, int64_t kv_rows, int impl, float* out);

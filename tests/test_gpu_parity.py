@@ -126,7 +126,7 @@ def _attn_ref(q, k, v, q_off, q_len, kv_off, kv_len, H=4):
 
 @pytest.mark.parametrize("case", [([33], [33]), ([1], [1]), ([64], [64]), ([65], [65]), ([128], [128]), ([129], [129]), ([167], [167]),
                                   ([200, 1, 64, 129], [200, 1, 64, 129]), ([40, 90], [83, 167]), ([1000], [1000])])
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_attention(capi, gpu, case, impl):
     q_lens, kv_lens = case
     rng = np.random.default_rng(sum(q_lens) + 13 * sum(kv_lens))
@@ -140,7 +140,7 @@ def test_attention(capi, gpu, case, impl):
     assert rel(out, ref) <= 8e-3  # bf16 P (product kernel) + bf16 output rounding
 
 
-@pytest.mark.parametrize("impl", [0, 2])
+@pytest.mark.parametrize("impl", [0, 2, 3])
 def test_attention_large_scores_force_the_running_maximum_to_move(capi, gpu, impl):
     """Scores grow along the keys (each 64-key block's maximum is far above the previous one), so the single-pass kernel
     must take its rare path: rescale O and l in TMEM.  Both tcgen05 variants against the fp32 softmax."""
