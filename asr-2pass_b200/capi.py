@@ -119,7 +119,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
-                "b200pf_host_mb_stats"]
+                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device"]
 
 
 def host_lib():
@@ -150,6 +150,10 @@ def host_lib():
     H.b200pf_host_model_forward_hw.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_offline_infer_buffer_hw.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, c_f32p, C.c_int, C.c_int, C.c_char_p,
                                                       C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_offline_init_devices.argtypes = [C.c_char_p, c_i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+    H.b200pf_host_offline_init_devices.restype = C.c_void_p
+    H.b200pf_host_partition.argtypes = [c_i32p, C.c_int, C.c_int, c_i32p]
+    H.b200pf_host_segments_per_device.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -200,8 +204,13 @@ def host_stitch(msgs, starts, lang):
 class OfflineHandle:
     """FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit through the host shim."""
 
-    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64):
-        self.h = host_lib().b200pf_host_offline_init(model_dir.encode(), device, max_rows, max_segments, batch_size)
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64, devices=None):
+        """devices=[0, 1, ...]: one engine per listed GPU behind this handle (funasr_b200::MultiGpuParaformer)."""
+        if devices is not None and len(devices) > 1:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            self.h = host_lib().b200pf_host_offline_init_devices(model_dir.encode(), _p(dv, c_i32p), len(dv), max_rows, max_segments, batch_size)
+        else:
+            self.h = host_lib().b200pf_host_offline_init(model_dir.encode(), device if not devices else devices[0], max_rows, max_segments, batch_size)
         if not self.h:
             raise B200PFError("FunOfflineInit failed: " + lib().b200pf_last_error().decode("utf-8", "replace"))
 
@@ -253,6 +262,11 @@ class OfflineHandle:
         if r < 0:
             raise B200PFError("Model::Forward failed")
         return buf.value.decode("utf-8").split("\n")
+
+    def segments_per_device(self):
+        out = (C.c_longlong * 16)()
+        n = host_lib().b200pf_host_segments_per_device(self.h, out, 16)
+        return [int(out[i]) for i in range(n)]
 
     def init_seg_dict(self, path):
         host_lib().b200pf_host_init_seg_dict(self.h, path.encode())
@@ -318,6 +332,14 @@ class MicroBatcher:
         host_lib().b200pf_host_mb_stats(self.h, out)
         keys = ("segments", "batches", "closed_by_deadline", "closed_by_size", "max_batch_seen", "mean_wait_us", "max_wait_us")
         return dict(zip(keys, [float(v) for v in out]))
+
+
+def host_partition(lens, n_dev):
+    """MultiGpuParaformer's LPT assignment of segments (sample counts) to n_dev queues."""
+    l = np.ascontiguousarray(lens, dtype=np.int32)
+    a = np.zeros(len(l), np.int32)
+    host_lib().b200pf_host_partition(_p(l, c_i32p), len(l), n_dev, _p(a, c_i32p))
+    return a
 
 
 def _check(rc):

@@ -643,15 +643,14 @@ AArgs make_args(const AttnProblem& p) {
 
 int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   if (p.n_work <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t err = cudaFuncSetAttribute(attn_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     err = cudaFuncSetAttribute(attn_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     err = cudaFuncSetAttribute(attn_heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
-    attr_set = true;
   }
   CUtensorMap tmQ, tmKV;
   int rc = make_tmap_bf16_sw128(&tmQ, p.q, (uint64_t)p.q_rows, (uint64_t)p.ldq, (uint64_t)p.ldq, BQ);

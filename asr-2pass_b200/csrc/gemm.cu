@@ -523,15 +523,14 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if ((p.N & 3) || (p.lda & 7) || (p.ldw & 7)) return (int)cudaErrorInvalidValue;
   if (e.out_bf16 && ((p.N & 7) || (e.ld_out_bf16 & 7))) return (int)cudaErrorInvalidValue;
   if (e.add_bf16 && ((p.N & 7) || (e.ld_add & 7))) return (int)cudaErrorInvalidValue;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};
+  if (first_use_on_device(attr_set)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     err = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
     err = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (err != cudaSuccess) return (int)err;
-    attr_set = true;
   }
   CUtensorMap tmA, tmB;
   const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;

@@ -6,6 +6,7 @@
 #include <fstream>
 #include <numeric>
 
+#include "multi_gpu.h"
 #include "paraformer_b200.h"
 
 namespace {
@@ -16,7 +17,10 @@ struct RecogResult {  // FUNASR_RECOG_RESULT, onnxruntime/src/commonfunc.h:8-15
 };
 
 struct OfflineHandle {  // stands where funasr::OfflineStream does; owns only the acoustic model
-  std::unique_ptr<funasr_b200::ParaformerB200> asr;
+  std::unique_ptr<funasr_b200::ParaformerB200> asr;        // single GPU
+  std::unique_ptr<funasr_b200::MultiGpuParaformer> pool;   // "devices" = "0,1,...": one engine per GPU, independent queues
+  funasr_b200::Model* model() { return pool ? (funasr_b200::Model*)pool.get() : (funasr_b200::Model*)asr.get(); }
+  funasr_b200::ParaformerB200* first() { return pool ? pool->model(0) : asr.get(); }
 };
 
 int ToInt(const std::map<std::string, std::string>& m, const char* key, int dflt) {
@@ -53,7 +57,7 @@ std::vector<std::vector<int>> FormBatches(const std::vector<long long>& len_sort
 
 RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples, std::vector<long long> seg_b,
                          std::vector<long long> seg_e, const std::vector<std::vector<float>>& hw_emb) {
-  funasr_b200::ParaformerB200* asr = h->asr.get();
+  funasr_b200::Model* asr = h->model();
   RecogResult* res = new RecogResult;
   res->snippet_time = (float)n_samples / asr->GetAsrSampleRate();
   if (res->snippet_time == 0) return res;
@@ -75,7 +79,18 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
       buf.insert(buf.end(), pcm + seg_b[s], pcm + seg_e[s]);
       offs.push_back((int64_t)buf.size());
     }
-    std::vector<std::string> out = asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size(), hw_emb);
+    std::vector<std::string> out;
+    if (!h->pool) {
+      out = h->asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size(), hw_emb);
+    } else {
+      // the multi-GPU handle takes the reference's own argument form: float = int16 / 32768 (Audio::LoadPcmwav, audio.cpp:803-804)
+      std::vector<float> fbuf(buf.size());
+      for (size_t i = 0; i < buf.size(); ++i) fbuf[i] = (float)buf[i] / 32768.0f;
+      std::vector<float*> ptrs(batch.size());
+      std::vector<int> lens(batch.size());
+      for (size_t k = 0; k < batch.size(); ++k) { ptrs[k] = fbuf.data() + offs[k]; lens[k] = (int)(offs[k + 1] - offs[k]); }
+      out = h->pool->Forward(ptrs.data(), lens.data(), true, hw_emb, nullptr, (int)batch.size());
+    }
     for (size_t k = 0; k < batch.size(); ++k) {
       const int s = index[batch[k]];
       msgs[s] = out[k];
@@ -93,9 +108,29 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
   auto it = model_path.find("model-dir");
   if (it == model_path.end()) { fprintf(stderr, "FunOfflineInit: model-dir missing\n"); return nullptr; }
   std::unique_ptr<OfflineHandle> h(new OfflineHandle);
-  h->asr.reset(new funasr_b200::ParaformerB200(ToInt(model_path, "device", 0), ToInt(model_path, "max-rows", 0),
-                                               ToInt(model_path, "max-segments", 0)));
   std::string err;
+  auto dv = model_path.find("devices");   // extra key: "0,1,2,3" -> one engine per listed GPU behind this one handle
+  std::vector<int> devices;
+  if (dv != model_path.end()) {
+    size_t p = 0;
+    while (p < dv->second.size()) {
+      size_t q = dv->second.find(',', p);
+      if (q == std::string::npos) q = dv->second.size();
+      if (q > p) devices.push_back(atoi(dv->second.substr(p, q - p).c_str()));
+      p = q + 1;
+    }
+  }
+  if (devices.size() > 1) {
+    h->pool.reset(new funasr_b200::MultiGpuParaformer(devices, ToInt(model_path, "max-rows", 0), ToInt(model_path, "max-segments", 0)));
+    if (!h->pool->Init(it->second, &err)) {
+      fprintf(stderr, "FunOfflineInit: %s\n", err.c_str());
+      return nullptr;
+    }
+    h->pool->SetBatchSize(batch_size);
+    return h.release();
+  }
+  h->asr.reset(new funasr_b200::ParaformerB200(devices.size() == 1 ? devices[0] : ToInt(model_path, "device", 0),
+                                               ToInt(model_path, "max-rows", 0), ToInt(model_path, "max-segments", 0)));
   if (!h->asr->Init(it->second, &err)) {
     fprintf(stderr, "FunOfflineInit: %s\n", err.c_str());
     return nullptr;
@@ -106,7 +141,9 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
 
 void FunOfflineReset(FUNASR_HANDLE, FUNASR_DEC_HANDLE) {}
 
-funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->asr.get() : nullptr; }
+funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->first() : nullptr; }
+funasr_b200::Model* FunOfflineModel(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->model() : nullptr; }
+funasr_b200::MultiGpuParaformer* FunOfflinePoolB200(FUNASR_HANDLE handle) { return handle ? ((OfflineHandle*)handle)->pool.get() : nullptr; }
 
 FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, const long long* seg_begin,
                                           const long long* seg_end, int n_seg, const std::vector<std::vector<float>>& hw_emb) {
@@ -127,7 +164,7 @@ FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, in
     fprintf(stderr, "FunOfflineInferBuffer: only raw PCM is decoded here (ffmpeg stays on the reference host path)\n");
     return nullptr;
   }
-  if (sampling_rate != h->asr->GetAsrSampleRate()) {
+  if (sampling_rate != h->model()->GetAsrSampleRate()) {
     fprintf(stderr, "FunOfflineInferBuffer: resampling stays on the reference host path\n");
     return nullptr;
   }
@@ -184,7 +221,7 @@ const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE hand
   OfflineHandle* h = (OfflineHandle*)handle;
   std::vector<std::vector<float>> emb;
   if (!h) return emb;
-  return h->asr->CompileHotwordEmbedding(hotwords);
+  return h->model()->CompileHotwordEmbedding(hotwords);
 }
 
 void FunOfflineUninit(FUNASR_HANDLE handle) { delete (OfflineHandle*)handle; }

@@ -24,7 +24,8 @@ typedef enum { ASR_OFFLINE = 0, ASR_ONLINE = 1, ASR_TWO_PASS = 2 } ASR_TYPE;
 typedef void (*QM_CALLBACK)(int cur_step, int n_total);
 
 // model_path keys (onnxruntime/include/com-define.h:15-38): "model-dir" is required; "quantize", "vad-dir",
-// "punc-dir", "itn-dir", "lm-dir" are accepted and ignored here.  Extra keys: "device" (CUDA ordinal),
+// "punc-dir", "itn-dir", "lm-dir" are accepted and ignored here.  Extra keys: "device" (CUDA ordinal), "devices"
+// ("0,1,...": one engine per listed GPU behind this handle, segments sharded over independent per-GPU queues),
 // "max-rows", "max-segments".
 FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int thread_num, bool use_gpu = false, int batch_size = 1);
 void FunOfflineReset(FUNASR_HANDLE handle, FUNASR_DEC_HANDLE dec_handle = nullptr);
@@ -53,9 +54,12 @@ void FunASRWfstDecoderUninit(FUNASR_DEC_HANDLE handle);
 void FunWfstDecoderLoadHwsRes(FUNASR_DEC_HANDLE handle, int inc_bias, std::unordered_map<std::string, int>& hws_map);
 void FunWfstDecoderUnloadHwsRes(FUNASR_DEC_HANDLE handle);
 
-namespace funasr_b200 { class ParaformerB200; }
-// The acoustic model behind an offline handle (what OfflineStream::asr_handle is in the reference).
+namespace funasr_b200 { class ParaformerB200; class MultiGpuParaformer; class Model; }
+// The acoustic model behind an offline handle (what OfflineStream::asr_handle is in the reference): the model object the
+// handle forwards to (single engine or multi-GPU pool), its first engine, and the pool (nullptr on one GPU).
+funasr_b200::Model* FunOfflineModel(FUNASR_HANDLE handle);
 funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle);
+funasr_b200::MultiGpuParaformer* FunOfflinePoolB200(FUNASR_HANDLE handle);
 
 // Extension for callers that already hold VAD cut points (e.g. the reference's Audio::CutSplit output):
 // segment i = pcm[seg_begin[i] .. seg_end[i]) in samples.  Segments are length-sorted, batched with the

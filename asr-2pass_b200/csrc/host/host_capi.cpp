@@ -9,6 +9,7 @@
 
 #include "funasrruntime_b200.h"
 #include "micro_batcher.h"
+#include "multi_gpu.h"
 #include "paraformer_b200.h"
 
 namespace {
@@ -62,6 +63,29 @@ void* b200pf_host_offline_init(const char* model_dir, int device, int max_rows, 
   mp["max-segments"] = std::to_string(max_segments);
   return FunOfflineInit(mp, 1, true, batch_size);
 }
+void* b200pf_host_offline_init_devices(const char* model_dir, const int* devices, int n_dev, int max_rows, int max_segments, int batch_size) {
+  std::map<std::string, std::string> mp;
+  mp["model-dir"] = model_dir;
+  std::string d;
+  for (int i = 0; i < n_dev; ++i) d += (i ? "," : "") + std::to_string(devices[i]);
+  mp["devices"] = d;
+  mp["max-rows"] = std::to_string(max_rows);
+  mp["max-segments"] = std::to_string(max_segments);
+  return FunOfflineInit(mp, 1, true, batch_size);
+}
+int b200pf_host_partition(const int* len, int n, int n_dev, int* assign) {
+  std::vector<int> a;
+  funasr_b200::PartitionSegments(len, n, n_dev, &a);
+  for (int i = 0; i < n; ++i) assign[i] = a[i];
+  return 0;
+}
+int b200pf_host_segments_per_device(void* h_offline, long long* out, int cap) {
+  funasr_b200::MultiGpuParaformer* p = FunOfflinePoolB200(h_offline);
+  if (!p) return 0;
+  const std::vector<long long> v = p->segments_per_device();
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
 void b200pf_host_offline_uninit(void* h) { FunOfflineUninit(h); }
 int b200pf_host_offline_infer_buffer(void* h, const char* buf, int n_bytes, int vad_max_len, char* text, int text_cap, float* snippet_s) {
   std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
@@ -110,7 +134,7 @@ int b200pf_host_init_seg_dict(void* h_offline, const char* path) {
 }
 int b200pf_host_model_forward_hw(void* h_offline, const float* const* din, const int* len, int n, const float* hw, int n_hw, int dim,
                                  char* out, int cap) {
-  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  funasr_b200::Model* m = FunOfflineModel(h_offline);
   if (!m) return -1;
   std::vector<float*> ptrs(n);
   for (int i = 0; i < n; ++i) ptrs[i] = const_cast<float*>(din[i]);
@@ -124,7 +148,7 @@ int b200pf_host_model_forward_hw(void* h_offline, const float* const* din, const
 }
 // Model::Forward over float segments (the plugin seam itself): returns the '\n'-joined result strings.
 int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap) {
-  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  funasr_b200::Model* m = FunOfflineModel(h_offline);
   if (!m) return -1;
   std::vector<float*> ptrs(n);
   for (int i = 0; i < n; ++i) ptrs[i] = const_cast<float*>(din[i]);
@@ -157,10 +181,15 @@ void* b200pf_host_mb_create_mock(int max_wait_us, int max_batch, int max_rows, i
       o);
 }
 void* b200pf_host_mb_create(void* h_offline, int max_wait_us, int max_batch, int max_rows) {
-  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
-  if (!m) return nullptr;
   funasr_b200::MicroBatcherOptions o;
   o.max_wait_us = max_wait_us; o.max_batch = max_batch; o.max_rows = max_rows;
+  if (funasr_b200::MultiGpuParaformer* pool = FunOfflinePoolB200(h_offline)) {
+    // connections -> micro-batcher -> per-GPU queues: one batch is split over all GPUs of the handle
+    return new funasr_b200::MicroBatcher(
+        [pool](float** din, int* len, int n, const std::vector<std::vector<float>>& hw) { return pool->Forward(din, len, true, hw, nullptr, n); }, o);
+  }
+  funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
+  if (!m) return nullptr;
   return new funasr_b200::MicroBatcher(m, o);
 }
 void b200pf_host_mb_destroy(void* mb) { delete (funasr_b200::MicroBatcher*)mb; }

@@ -17,6 +17,16 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: with one engine per GPU inside one process (MultiGpuParaformer)
+// every device needs its own call.  `flags` is a per-call-site static array; returns true the first time on each device.
+inline bool first_use_on_device(bool (&flags)[64]) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+  if (flags[d]) return false;
+  flags[d] = true;
+  return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};

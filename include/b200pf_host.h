@@ -23,6 +23,13 @@ int b200pf_host_stitch(const char* const* msgs, const float* start_s, int n, con
 
 /* FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit (funasrruntime.h:100-117) through C types. */
 void* b200pf_host_offline_init(const char* model_dir, int device, int max_rows, int max_segments, int batch_size);
+/* Same over several GPUs of the box: one engine per device behind one handle, every call's segments are sharded over
+ * independent per-GPU queues (funasr_b200::MultiGpuParaformer; no collective). */
+void* b200pf_host_offline_init_devices(const char* model_dir, const int* devices, int n_dev, int max_rows, int max_segments, int batch_size);
+/* The pool's longest-processing-time-first assignment of segments (sample counts) to n_dev queues; host arithmetic only. */
+int b200pf_host_partition(const int* len, int n, int n_dev, int* assign);
+/* Segments decoded per device so far; returns the number of devices (0 for a single-GPU handle). */
+int b200pf_host_segments_per_device(void* h_offline, long long* out, int cap);
 void b200pf_host_offline_uninit(void* h);
 int b200pf_host_offline_infer_buffer(void* h, const char* buf, int n_bytes, int vad_max_len, char* text, int text_cap, float* snippet_s);
 int b200pf_host_offline_infer_segments(void* h, const int16_t* pcm, int64_t n_samples, const int64_t* seg_begin, const int64_t* seg_end,

@@ -108,3 +108,19 @@ def test_destruction_drains_the_queue(capi):
     for t in th:
         t.join(timeout=5)
     assert all(o is not None and o.startswith("n=1600") for o in out)
+
+
+def test_multi_gpu_partition_is_balanced_and_complete(capi, synth):
+    """MultiGpuParaformer::PartitionSegments: every segment gets exactly one queue; LPT keeps the per-queue FLOP estimate
+    within a few percent; too-short segments are spread as well."""
+    sch = __import__("importlib").import_module("asr-2pass_b200.scheduler")
+    lens = synth.segment_lengths(1024).astype(np.int32)
+    for n_dev in (2, 4, 8):
+        a = capi.host_partition(lens, n_dev)
+        assert a.min() == 0 and a.max() == n_dev - 1
+        load = np.zeros(n_dev)
+        for n, d in zip(lens, a):
+            load[d] += sch.segment_cost(sch.num_lfr_frames(int(n)))
+        assert load.max() / load.min() < 1.02
+    assert list(capi.host_partition(np.array([16000, 100, 100, 100], np.int32), 2)) in ([0, 1, 1, 1], [0, 1, 1, 0], [0, 1, 0, 1])
+    assert list(capi.host_partition(np.array([5, 6, 7], np.int32), 1)) == [0, 0, 0]
