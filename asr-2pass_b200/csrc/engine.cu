@@ -291,6 +291,7 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi), "cudaDeviceGetStreamPriorityRange");
     CK(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate");
     CK(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_lo), "cudaStreamCreate");
+    CK(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking), "cudaStreamCreate");
   }
   CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming), "cudaEventCreate");
   CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming), "cudaEventCreate");
@@ -456,6 +457,8 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   cudaFree(e->topk_id);
   cudaStreamSynchronize(e->side);
   cudaStreamDestroy(e->side);
+  cudaStreamSynchronize(e->copy);
+  cudaStreamDestroy(e->copy);
   cudaEventDestroy(e->ev_fork);
   cudaEventDestroy(e->ev_join);
   cudaStreamDestroy(e->stream);
@@ -474,6 +477,7 @@ const char* b200pf_engine_token(const b200pf_engine* e, int id) {
 }
 const char* b200pf_engine_lang(const b200pf_engine* e) { return e ? e->lang.c_str() : ""; }
 void* b200pf_engine_stream(b200pf_engine* e) { return e ? (void*)e->stream : nullptr; }
+void* b200pf_engine_copy_stream(b200pf_engine* e) { return e ? (void*)e->copy : nullptr; }
 
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   if (!e || !key) { set_error("null argument"); return B200PF_ERR_INVALID; }

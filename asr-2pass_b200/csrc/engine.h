@@ -61,6 +61,7 @@ struct b200pf_engine {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;          // FSMN memory block runs here, concurrently with the attention kernel
+  cudaStream_t copy = nullptr;          // host<->device staging of the NEXT batch (b200pf_engine_copy_stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 2;
   int attn_online = 2;

@@ -18,7 +18,7 @@ ParaformerB200::ParaformerB200(int device, int max_rows, int max_segments)
     : device_(device), max_rows_(max_rows), max_segments_(max_segments) {}
 
 ParaformerB200::~ParaformerB200() {
-  if (batch_) b200pf_batch_destroy(batch_);
+  for (Slot& sl : slots_) if (sl.batch) b200pf_batch_destroy(sl.batch);
   if (engine_) b200pf_engine_destroy(engine_);
 }
 
@@ -186,14 +186,17 @@ std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_se
   return out;
 }
 
-bool ParaformerB200::RunBatch(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
-                              const std::vector<std::vector<float>>& hw_emb, std::vector<std::string>* out) {
-  if (!batch_ || samples > batch_samples_) {
-    if (batch_) b200pf_batch_destroy(batch_);
-    batch_ = nullptr;
-    hw_set_ = nullptr;
-    batch_samples_ = samples + samples / 4 + 16000;
-    if (b200pf_batch_create(engine_, batch_samples_, &batch_) != 0) { fprintf(stderr, "ParaformerB200: %s\n", b200pf_last_error()); return false; }
+// One engine-sized sub-batch is staged into slot `k` (its own b200pf_batch: device PCM + layout) on the engine's COPY
+// stream, so that the host-to-device copies of sub-batch i+1 run while sub-batch i computes.
+bool ParaformerB200::StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
+                               const std::vector<std::vector<float>>& hw_emb) {
+  Slot& sl = slots_[k];
+  if (!sl.batch || samples > sl.samples) {
+    if (sl.batch) b200pf_batch_destroy(sl.batch);
+    sl.batch = nullptr;
+    sl.hw_valid = false;
+    sl.samples = samples + samples / 4 + 16000;
+    if (b200pf_batch_create(engine_, sl.samples, &sl.batch) != 0) { fprintf(stderr, "ParaformerB200: %s\n", b200pf_last_error()); return false; }
   }
   if (use_hotword_) {
     if (hw_emb.empty()) { fprintf(stderr, "hw_emb is null\n"); return false; }  // paraformer.cpp:516-520
@@ -201,16 +204,23 @@ bool ParaformerB200::RunBatch(const int16_t* pcm, const int64_t* offsets, float*
     std::vector<float> flat;
     flat.reserve(hw_emb.size() * hw_emb[0].size());
     for (const auto& row : hw_emb) flat.insert(flat.end(), row.begin(), row.end());
-    if (flat != hw_flat_ || hw_set_ == nullptr) {
+    if (!sl.hw_valid || flat != sl.hw_flat) {
       if (flat.size() != hw_emb.size() * (size_t)d_model_ ||
-          b200pf_batch_set_hotwords(batch_, flat.data(), (int)hw_emb.size(), (int)hw_emb[0].size()) != 0) {
+          b200pf_batch_set_hotwords(sl.batch, flat.data(), (int)hw_emb.size(), (int)hw_emb[0].size()) != 0) {
         fprintf(stderr, "ParaformerB200: bad hotword embedding (%zu x %zu): %s\n", hw_emb.size(), hw_emb[0].size(), b200pf_last_error());
         return false;  // ORT would throw on the shape mismatch -> "" (paraformer.cpp:582-587)
       }
-      hw_flat_.swap(flat);
-      hw_set_ = hw_flat_.data();
+      sl.hw_flat.swap(flat);
+      sl.hw_valid = true;
     }
   }
+  void* cs = b200pf_engine_copy_stream(engine_);
+  const int rc = pcm ? b200pf_batch_stage_s16(sl.batch, pcm, offsets, n, cs) : b200pf_batch_stage_f32(sl.batch, din, len, n, cs);
+  if (rc != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
+  return true;
+}
+
+bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out) {
   std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_), us_offs(n + 1);
   std::vector<float> us_a, us_p;
   b200pf_result r;
@@ -222,39 +232,65 @@ bool ParaformerB200::RunBatch(const int16_t* pcm, const int64_t* offsets, float*
     us_a.resize((size_t)3 * max_rows_); us_p.resize((size_t)3 * max_rows_);
     r.us_alphas = us_a.data(); r.us_peaks = us_p.data(); r.cap_us = (int64_t)3 * max_rows_;
   }
-  const int rc = pcm ? b200pf_forward_s16(batch_, pcm, offsets, n, &r) : b200pf_forward_f32(batch_, din, len, n, &r);
-  if (rc != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
+  if (b200pf_batch_collect(slots_[k].batch, &r, nullptr) != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
   *out = Decode(r, n);
   return true;
+}
+
+// Shared driver of both Forward flavours: split the caller's batch by the engine's capacity, then run the sub-batches
+// through two slots: stage(i+1) overlaps compute(i).  A failing sub-batch logs and leaves "" for its items, never throws
+// (paraformer.cpp:582-587).  Results keep the caller's order.
+std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
+                                                const std::vector<std::vector<float>>& hw_emb) {
+  std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
+  if (n_seg <= 0 || !engine_) return results;
+  std::lock_guard<std::mutex> lock(mu_);
+  struct Sub { int start, end; int64_t samples; };
+  std::vector<Sub> subs;
+  int start = 0;
+  while (start < n_seg) {
+    int64_t rows = 0, samples = 0;
+    int end = start;
+    while (end < n_seg && end - start < max_segments_) {
+      const int64_t ns = pcm ? offsets[end + 1] - offsets[end] : (int64_t)len[end];
+      const int T = b200pf_num_lfr_frames(ns);
+      const int64_t r = T > 0 ? T + 1 : 0;
+      if (end > start && rows + r > max_rows_) break;
+      rows += r;
+      samples += ns;
+      ++end;
+    }
+    subs.push_back(Sub{start, end, samples});
+    start = end;
+  }
+  auto stage = [&](size_t i) {
+    const Sub& sb = subs[i];
+    return StageSlot((int)(i & 1), pcm, pcm ? offsets + sb.start : nullptr, pcm ? nullptr : din + sb.start, pcm ? nullptr : len + sb.start,
+                     sb.end - sb.start, sb.samples, hw_emb);
+  };
+  std::vector<char> ok(subs.size(), 0);
+  ok[0] = stage(0);
+  for (size_t i = 0; i < subs.size(); ++i) {
+    bool running = false;
+    if (ok[i]) {
+      running = b200pf_batch_run(slots_[i & 1].batch, nullptr) == 0;   // asynchronous; waits for the slot's staged event
+      if (!running) fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error());
+    }
+    if (i + 1 < subs.size()) ok[i + 1] = stage(i + 1);                  // host copies while the GPU computes sub-batch i
+    if (running) {
+      std::vector<std::string> part;
+      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part))
+        for (int k = 0; k < subs[i].end - subs[i].start; ++k) results[subs[i].start + k] = part[k];
+    }
+  }
+  return results;
 }
 
 std::vector<std::string> ParaformerB200::Forward(float** din, int* len, bool input_finished,
                                                  const std::vector<std::vector<float>>& hw_emb, void* wfst_decoder,
                                                  int batch_in) {
   (void)input_finished; (void)wfst_decoder;
-  std::vector<std::string> results(batch_in > 0 ? batch_in : 0);
-  if (batch_in <= 0 || !engine_) return results;
-  std::lock_guard<std::mutex> lock(mu_);
-  // split the caller's batch by the engine's capacity; results keep the caller's order.  A failing call logs and
-  // leaves "" for its items, never throws (paraformer.cpp:582-587).
-  int start = 0;
-  while (start < batch_in) {
-    int64_t rows = 0, samples = 0;
-    int end = start;
-    while (end < batch_in && end - start < max_segments_) {
-      const int T = b200pf_num_lfr_frames(len[end]);
-      const int64_t r = T > 0 ? T + 1 : 0;
-      if (end > start && rows + r > max_rows_) break;
-      rows += r;
-      samples += len[end];
-      ++end;
-    }
-    std::vector<std::string> part;
-    if (RunBatch(nullptr, nullptr, din + start, len + start, end - start, samples, hw_emb, &part))
-      for (int i = 0; i < end - start; ++i) results[start + i] = part[i];
-    start = end;
-  }
-  return results;
+  return RunAll(nullptr, nullptr, din, len, batch_in, hw_emb);
 }
 
 std::string ParaformerB200::Forward(float* din, int len, bool input_finished, const std::vector<std::vector<float>>& hw_emb,
@@ -267,26 +303,7 @@ std::string ParaformerB200::Forward(float* din, int len, bool input_finished, co
 
 std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,
                                                       const std::vector<std::vector<float>>& hw_emb) {
-  std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
-  if (n_seg <= 0 || !engine_) return results;
-  std::lock_guard<std::mutex> lock(mu_);
-  int start = 0;
-  while (start < n_seg) {
-    int64_t rows = 0;
-    int end = start;
-    while (end < n_seg && end - start < max_segments_) {
-      const int T = b200pf_num_lfr_frames(offsets[end + 1] - offsets[end]);
-      const int64_t r = T > 0 ? T + 1 : 0;
-      if (end > start && rows + r > max_rows_) break;
-      rows += r;
-      ++end;
-    }
-    std::vector<std::string> part;
-    if (RunBatch(pcm, offsets + start, nullptr, nullptr, end - start, offsets[end] - offsets[start], hw_emb, &part))
-      for (int i = 0; i < end - start; ++i) results[start + i] = part[i];
-    start = end;
-  }
-  return results;
+  return RunAll(pcm, offsets, nullptr, nullptr, n_seg, hw_emb);
 }
 
 }  // namespace funasr_b200

@@ -93,14 +93,22 @@ class ParaformerB200 : public Model {
 
  private:
   std::vector<std::string> Decode(const b200pf_result& r, int n_seg);
-  // one engine-sized batch through the C ABI: pcm16 (offsets) or float (din/len); false = error already logged
-  bool RunBatch(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
-                const std::vector<std::vector<float>>& hw_emb, std::vector<std::string>* out);
+  // engine-sized sub-batches through the C ABI, double buffered: pcm16 (offsets) or float (din/len)
+  struct Slot {
+    b200pf_batch* batch = nullptr;
+    int64_t samples = 0;
+    bool hw_valid = false;           // hw_flat is what is attached to `batch`
+    std::vector<float> hw_flat;
+  };
+  bool StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
+                 const std::vector<std::vector<float>>& hw_emb);
+  bool CollectSlot(int k, int n, std::vector<std::string>* out);
+  std::vector<std::string> RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
+                                  const std::vector<std::vector<float>>& hw_emb);
 
   int device_, max_rows_, max_segments_;
   b200pf_engine* engine_ = nullptr;
-  b200pf_batch* batch_ = nullptr;
-  int64_t batch_samples_ = 0;
+  Slot slots_[2];
   std::unique_ptr<pf::host::Detokenizer> vocab_;
   std::string language_ = "zh-cn";
   int sample_rate_ = 16000;
@@ -111,8 +119,6 @@ class ParaformerB200 : public Model {
   int d_model_ = 512;
   std::unordered_map<std::string, std::vector<std::string>> seg_dict_;
   std::unordered_map<std::string, int> token_id_;  // PhoneSet::String2Id (phone-set.cpp:38-68)
-  const float* hw_set_ = nullptr;  // identity of the hotword matrix currently attached to batch_
-  std::vector<float> hw_flat_;
 };
 
 }  // namespace funasr_b200

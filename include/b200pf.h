@@ -110,6 +110,9 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches);
 /* The CUDA stream (cudaStream_t) the engine enqueues on when `stream` arguments are NULL. */
 void* b200pf_engine_stream(b200pf_engine* e);
+/* A second stream owned by the engine, meant for b200pf_batch_stage_*: copies of the next batch then overlap the
+ * compute of the current one (b200pf_batch_run waits for its batch's staging through an event). */
+void* b200pf_engine_copy_stream(b200pf_engine* e);
 
 /* Number of fbank frames / LFR frames for a segment of n samples (feature-window.cc:73-87,
  * paraformer.cpp:424).  Pure host arithmetic. */
