@@ -119,7 +119,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
-                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device"]
+                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer"]
 
 
 def host_lib():
@@ -154,6 +154,7 @@ def host_lib():
     H.b200pf_host_offline_init_devices.restype = C.c_void_p
     H.b200pf_host_partition.argtypes = [c_i32p, C.c_int, C.c_int, c_i32p]
     H.b200pf_host_segments_per_device.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]
+    H.b200pf_host_funasr_infer.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -332,6 +333,19 @@ class MicroBatcher:
         host_lib().b200pf_host_mb_stats(self.h, out)
         keys = ("segments", "batches", "closed_by_deadline", "closed_by_size", "max_batch_seen", "mean_wait_us", "max_wait_us")
         return dict(zip(keys, [float(v) for v in out]))
+
+
+def funasr_infer(model_dir, wav_path=None, pcm16=None, device=0, max_rows=0):
+    """FunASRInit -> FunASRInfer / FunASRInferBuffer -> FunASRGetResult -> FunASRUninit (the plain-model API)."""
+    buf = C.create_string_buffer(1 << 20)
+    if wav_path is not None:
+        n = host_lib().b200pf_host_funasr_infer(model_dir.encode(), device, max_rows, wav_path.encode(), None, 0, buf, len(buf))
+    else:
+        a = np.ascontiguousarray(pcm16, dtype="<i2")
+        n = host_lib().b200pf_host_funasr_infer(model_dir.encode(), device, max_rows, None, C.c_void_p(a.ctypes.data), a.nbytes, buf, len(buf))
+    if n < 0:
+        raise B200PFError("FunASRInit / FunASRInfer failed (%d)" % n)
+    return buf.value.decode("utf-8")
 
 
 def host_partition(lens, n_dev):

@@ -180,15 +180,74 @@ FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, in
   return RunSegments(h, pcm.data(), n, b, e, hw_emb);
 }
 
+namespace {
+// Reads a .wav (16-bit mono PCM) or raw .pcm file; returns false when it cannot be used.  *payload points into *data.
+bool LoadAudioFile(const char* path, int default_rate, std::vector<char>* data, const char** payload, size_t* n_bytes, int* rate);
+}  // namespace
+
+FUNASR_HANDLE FunASRInit(std::map<std::string, std::string>& model_path, int thread_num, ASR_TYPE type) {
+  (void)thread_num;
+  if (type != ASR_OFFLINE) { fprintf(stderr, "FunASRInit: only the offline Paraformer is implemented here\n"); return nullptr; }
+  auto it = model_path.find("model-dir");
+  if (it == model_path.end()) { fprintf(stderr, "FunASRInit: model-dir missing\n"); return nullptr; }
+  std::unique_ptr<funasr_b200::ParaformerB200> m(new funasr_b200::ParaformerB200(ToInt(model_path, "device", 0), ToInt(model_path, "max-rows", 0),
+                                                                                  ToInt(model_path, "max-segments", 0)));
+  std::string err;
+  if (!m->Init(it->second, &err)) { fprintf(stderr, "FunASRInit: %s\n", err.c_str()); return nullptr; }
+  return (funasr_b200::Model*)m.release();   // like the reference, the handle IS the model (funasrruntime.cpp:13-17)
+}
+void FunASRReset(FUNASR_HANDLE, FUNASR_DEC_HANDLE) {}
+void FunASRUninit(FUNASR_HANDLE handle) { delete (funasr_b200::Model*)handle; }
+
+FUNASR_RESULT FunASRInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE, QM_CALLBACK, bool input_finished,
+                                int sampling_rate, std::string wav_format) {
+  funasr_b200::Model* m = (funasr_b200::Model*)handle;
+  if (!m) return nullptr;  // funasrruntime.cpp:59-61
+  if (!(wav_format == "pcm" || wav_format == "PCM") || sampling_rate != m->GetAsrSampleRate()) {
+    fprintf(stderr, "FunASRInferBuffer: only raw PCM at the model's rate is decoded here (ffmpeg / resampling stay on the reference host path)\n");
+    return nullptr;
+  }
+  const int n = n_len / 2;
+  RecogResult* res = new RecogResult;
+  res->snippet_time = (float)n / m->GetAsrSampleRate();
+  if (res->snippet_time == 0) return res;
+  std::vector<float> pcm((size_t)n);
+  const unsigned char* bytes = (const unsigned char*)sz_buf;
+  for (int i = 0; i < n; ++i) pcm[i] = (float)(short)((bytes[2 * i + 1] << 8) | bytes[2 * i]) / 32768.0f;  // Audio::LoadPcmwav
+  res->msg += m->Forward(pcm.data(), n, input_finished);   // Audio::Fetch yields the whole audio once (no VAD on this API)
+  return res;
+}
+
+FUNASR_RESULT FunASRInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK cb, int sampling_rate) {
+  if (!handle || !sz_filename) return nullptr;
+  std::vector<char> data;
+  const char* payload = nullptr;
+  size_t n_bytes = 0;
+  int rate = sampling_rate;
+  if (!LoadAudioFile(sz_filename, sampling_rate, &data, &payload, &n_bytes, &rate)) return nullptr;
+  return FunASRInferBuffer(handle, payload, (int)n_bytes, mode, cb, true, rate, "pcm");
+}
+
 FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK cb,
                               const std::vector<std::vector<float>>& hw_emb, int sampling_rate, bool itn, int vad_tail_sil,
                               int vad_max_len, FUNASR_DEC_HANDLE dec_handle) {
   if (!handle || !sz_filename) return nullptr;
-  std::ifstream f(sz_filename, std::ios::binary);
-  if (!f.is_open()) return nullptr;
-  std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-  size_t off = 0;
+  std::vector<char> data;
+  const char* payload = nullptr;
+  size_t n_bytes = 0;
   int rate = sampling_rate;
+  if (!LoadAudioFile(sz_filename, sampling_rate, &data, &payload, &n_bytes, &rate)) return nullptr;
+  return FunOfflineInferBuffer(handle, payload, (int)n_bytes, mode, cb, hw_emb, rate, "pcm", itn, vad_tail_sil, vad_max_len, dec_handle);
+}
+
+namespace {
+bool LoadAudioFile(const char* path, int default_rate, std::vector<char>* data_out, const char** payload, size_t* n_bytes, int* rate_out) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f.is_open()) return false;
+  data_out->assign((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::vector<char>& data = *data_out;
+  size_t off = 0;
+  int rate = default_rate;
   if (data.size() >= 44 && memcmp(data.data(), "RIFF", 4) == 0 && memcmp(data.data() + 8, "WAVE", 4) == 0) {
     // walk the chunks: "fmt " gives the rate, "data" the payload (Audio::LoadWav, audio.cpp:622-737)
     size_t p = 12;
@@ -201,7 +260,7 @@ FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUN
         unsigned short fmt, ch, bits;
         memcpy(&fmt, data.data() + p + 8, 2); memcpy(&ch, data.data() + p + 10, 2);
         memcpy(&rate, data.data() + p + 12, 4); memcpy(&bits, data.data() + p + 22, 2);
-        if (ch != 1 || bits != 16) { fprintf(stderr, "FunOfflineInfer: only 16-bit mono wav is supported here\n"); return nullptr; }
+        if (ch != 1 || bits != 16) { fprintf(stderr, "only 16-bit mono wav is supported here\n"); return false; }
       } else if (memcmp(data.data() + p, "data", 4) == 0) {
         off = p + 8;
         len = std::min<size_t>(sz, data.size() - off);
@@ -209,13 +268,14 @@ FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUN
       }
       p += 8 + sz + (sz & 1);
     }
-    if (off >= data.size() && len == 0) return nullptr;
-    return FunOfflineInferBuffer(handle, data.data() + off, (int)len, mode, cb, hw_emb, rate, "pcm", itn, vad_tail_sil,
-                                 vad_max_len, dec_handle);
+    if (off >= data.size() && len == 0) return false;
+    *payload = data.data() + off; *n_bytes = len; *rate_out = rate;
+    return true;
   }
-  return FunOfflineInferBuffer(handle, data.data(), (int)data.size(), mode, cb, hw_emb, rate, "pcm", itn, vad_tail_sil,
-                               vad_max_len, dec_handle);
+  *payload = data.data(); *n_bytes = data.size(); *rate_out = rate;
+  return true;
 }
+}  // namespace
 
 const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE) {
   OfflineHandle* h = (OfflineHandle*)handle;

@@ -23,6 +23,16 @@ typedef enum { RASR_NONE = -1, RASRM_CTC_GREEDY_SEARCH = 0, RASRM_CTC_RPEFIX_BEA
 typedef enum { ASR_OFFLINE = 0, ASR_ONLINE = 1, ASR_TWO_PASS = 2 } ASR_TYPE;
 typedef void (*QM_CALLBACK)(int cur_step, int n_total);
 
+// Plain-model API (funasrruntime.h:60-78): the handle is the funasr::Model itself, and FunASRInfer / FunASRInferBuffer feed
+// the WHOLE audio to the single-segment overload Forward(float*, int, bool) (funasrruntime.cpp:57-114).  The reference's
+// Paraformer does not override that overload, so it answers "" there; ParaformerB200 does (the batch-1 case).
+FUNASR_HANDLE FunASRInit(std::map<std::string, std::string>& model_path, int thread_num, ASR_TYPE type = ASR_OFFLINE);
+void FunASRReset(FUNASR_HANDLE handle, FUNASR_DEC_HANDLE dec_handle = nullptr);
+FUNASR_RESULT FunASRInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE mode, QM_CALLBACK fn_callback,
+                                bool input_finished = true, int sampling_rate = 16000, std::string wav_format = "pcm");
+FUNASR_RESULT FunASRInfer(FUNASR_HANDLE handle, const char* sz_filename, FUNASR_MODE mode, QM_CALLBACK fn_callback, int sampling_rate = 16000);
+void FunASRUninit(FUNASR_HANDLE handle);
+
 // model_path keys (onnxruntime/include/com-define.h:15-38): "model-dir" is required; "quantize", "vad-dir",
 // "punc-dir", "itn-dir", "lm-dir" are accepted and ignored here.  Extra keys: "device" (CUDA ordinal), "devices"
 // ("0,1,...": one engine per listed GPU behind this handle, segments sharded over independent per-GPU queues),

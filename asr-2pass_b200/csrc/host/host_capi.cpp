@@ -161,6 +161,21 @@ int b200pf_host_model_forward(void* h_offline, const float* const* din, const in
 }
 
 
+// FunASRInit -> FunASRInfer(file) or FunASRInferBuffer(buf) -> FunASRGetResult -> FunASRUninit (funasrruntime.h:60-78)
+int b200pf_host_funasr_infer(const char* model_dir, int device, int max_rows, const char* wav_path, const char* buf, int n_bytes, char* out, int cap) {
+  std::map<std::string, std::string> mp;
+  mp["model-dir"] = model_dir;
+  mp["device"] = std::to_string(device);
+  mp["max-rows"] = std::to_string(max_rows);
+  FUNASR_HANDLE h = FunASRInit(mp, 1);
+  if (!h) return -1;
+  FUNASR_RESULT r = wav_path ? FunASRInfer(h, wav_path, RASR_NONE, nullptr) : FunASRInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr);
+  int n = -2;
+  if (r) { n = CopyOut(FunASRGetResult(r, 0), out, cap); FunASRFreeResult(r); }
+  FunASRUninit(h);
+  return n;
+}
+
 // ---- MicroBatcher ------------------------------------------------------------
 // Mock inner model for host-only tests: "n=<len>;b=<batch size>;x=<first sample>;hw=<rows of hw_emb>", after
 // sleeping latency_us once per batch (a stand-in for the GPU forward).

@@ -48,6 +48,10 @@ int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* o
 /* Model::InitSegDict (model.h:27; SegDict, seg_dict.cpp:19-38) for English hotwords. */
 int b200pf_host_init_seg_dict(void* h_offline, const char* path);
 
+/* FunASRInit -> FunASRInfer (wav_path != NULL) or FunASRInferBuffer (buf) -> FunASRGetResult -> FunASRUninit
+ * (funasrruntime.h:60-78; the plain-model API that funasr-onnx-offline style callers use).  Returns the text length,
+ * -1 when Init fails, -2 when inference returns nullptr. */
+int b200pf_host_funasr_infer(const char* model_dir, int device, int max_rows, const char* wav_path, const char* buf, int n_bytes, char* out, int cap);
 /* MicroBatcher (asr-2pass_b200/csrc/host/micro_batcher.h): merges the batch-1 Forward calls that the 2-pass server makes
  * per closed VAD segment (funasrruntime.cpp:570-586) across connections into batched forwards.  `mock` variant: host-only
  * inner model for tests.  forward blocks until the segment is decoded; hw may be NULL (n_hw 0). */

@@ -1,0 +1,76 @@
+"""Reference-facing host API on the GPU (-m gpu): the funasrruntime.h call sequences of configs[0]
+(FunOfflineInit -> FunOfflineInfer*/FunASRInfer -> FunASRGetResult) through libfunasr_b200.so, checked against the C ABI's
+token ids run through the Python restatement of Vocab::Vector2StringV2 / the stitching rules."""
+import os
+import wave
+
+import numpy as np
+import pytest
+
+from oracle import postproc_ref as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model(capi, synth, gpu, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("host"))
+    cfg, W, means, vars_, toks = synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    eng = capi.Engine(d, max_rows=4096, max_segments=64)
+    return dict(dir=d, toks=toks, eng=eng)
+
+
+def _ids(capi, model, pcm16):
+    b = capi.Batch(model["eng"], len(pcm16) + 16)
+    r = b.forward_s16(pcm16, np.array([0, len(pcm16)], np.int64))
+    return list(r["token_ids"])
+
+
+def _strip(s):
+    return s.replace(" ", "")   # a leading space depends on Vocab's cross-call state (vocab.cpp:177), i.e. on call order
+
+
+def test_config1_call_sequence_10s_wav(capi, synth, model, tmp_path):
+    """configs[0]: one 10 s 16 kHz wav through FunOfflineInit(...,1,false,1) -> FunOfflineInfer -> FunASRGetResult."""
+    pcm = synth.make_audio(160000, 42)
+    h = capi.OfflineHandle(model["dir"], max_rows=4096, max_segments=64, batch_size=1)
+    text, snippet = h.infer_buffer(pcm, vad_max_len=20000)
+    assert abs(snippet - 10.0) < 1e-6
+    expect = P.Vocab(model["toks"]).vector2string_v2(_ids(capi, model, pcm), "zh-cn")
+    assert _strip(text) == _strip(expect) and len(text) > 0
+    # the plain-model API on a wav file and on the raw buffer
+    path = os.path.join(str(tmp_path), "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(pcm.astype("<i2").tobytes())
+    t_file = capi.funasr_infer(model["dir"], wav_path=path, max_rows=4096)
+    t_buf = capi.funasr_infer(model["dir"], pcm16=pcm, max_rows=4096)
+    assert t_file == t_buf and _strip(t_file) == _strip(expect)
+    h.close()
+
+
+def test_hard_cut_and_segment_stitching(capi, synth, model):
+    """No VAD in the stand-alone shim: audio longer than vad_max_len is hard-cut; texts of the pieces are concatenated in
+    time order (funasrruntime.cpp:291-300); externally cut segments go through the FetchDynamic-style batching."""
+    pcm = synth.make_audio(16000 * 25, 7)
+    h = capi.OfflineHandle(model["dir"], max_rows=4096, max_segments=64, batch_size=8)
+    text, snippet = h.infer_buffer(pcm, vad_max_len=10000)
+    assert abs(snippet - 25.0) < 1e-6
+    v = P.Vocab(model["toks"])
+    pieces = [pcm[0:160000], pcm[160000:320000], pcm[320000:]]
+    expect = "".join(v.vector2string_v2(_ids(capi, model, p), "zh-cn") for p in pieces)
+    assert _strip(text) == _strip(expect)
+    b, e = [320000, 0, 160000], [400000, 160000, 320000]                 # out of time order, different lengths
+    seg_text = h.infer_segments(pcm, b, e)
+    expect2 = "".join(v.vector2string_v2(_ids(capi, model, pcm[s:t]), "zh-cn") for s, t in zip(b, e))
+    assert _strip(seg_text) == _strip(expect2)                           # results come back in the caller's segment order
+    assert h.infer_buffer(np.zeros(0, np.int16))[0] == ""               # zero-length audio -> empty result object
+    assert h.infer_buffer(np.zeros(300, np.int16))[0] == ""             # shorter than one fbank window -> ""
+    h.close()
+
+
+def test_init_failure_is_reported_not_fatal_through_the_hooks(capi, tmp_path):
+    with pytest.raises(capi.B200PFError):
+        capi.OfflineHandle(str(tmp_path))                                 # no model files
+    with pytest.raises(capi.B200PFError):
+        capi.funasr_infer(str(tmp_path), pcm16=np.zeros(16000, np.int16))
