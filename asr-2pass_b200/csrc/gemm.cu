@@ -9,7 +9,7 @@
 //                 of both CTAs (128 lanes x 256 columns each, double buffered = 512 columns)
 //   warp 2      : TMEM allocator (cta_group::2)
 //   warps 4..11 : epilogue in each CTA: tcgen05.ld 32x32b.x32 -> bias / ReLU / FSMN-memory add / residual ->
-//                 bf16 or fp32.  bf16-only outputs (FAST) leave through TMA stores: each warp packs 32 rows x 64
+//                 bf16 or fp32.  bf16-only outputs (EPI 1) leave through TMA stores: each warp packs 32 rows x 64
 //                 columns into a swizzled 4 KB smem tile and one lane issues cp.async.bulk.tensor (full 128-byte
 //                 lines, no LSU / register traffic, asynchronous).  The general path stages through a per-warp smem
 //                 tile so every global load and store is a run of full 32-byte sectors; optional fused argmax.
@@ -31,7 +31,7 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;
 constexpr int kTmemCols = 512;
 constexpr int SCR_STRIDE = 144;                  // bytes per scratch row: 128 + 16 (bank-conflict-free 16 B accesses)
 constexpr int SCR_BYTES = 32 * SCR_STRIDE;       // per epilogue warp
-constexpr int BIAS_BYTES = 256 * 4;                  // per epilogue warp (general: 128 used; FAST: [pair][2][256] over 8 warps' worth)
+constexpr int BIAS_BYTES = 256 * 4;                  // per epilogue warp (128 floats used)
 constexpr int kSmemBytes = STAGES * (A_BYTES + B_BYTES) + kEpiWarps * (SCR_BYTES + BIAS_BYTES) + 1024 /*align*/ + 512 /*barriers*/;
 
 struct KArgs {
@@ -47,8 +47,6 @@ struct KArgs {
 //   2  bias (+ReLU) (+bf16 addend) -> fp32 through TMA; when the residual is the output buffer itself (x += ..., every
 //      out-projection and FFN2) the tile leaves as a TMA REDUCE-ADD, so the SMs never load the residual stream: the
 //      read-modify-write of x happens in L2.
-// (old note) FAST = epilogue is bias (+ReLU) -> bf16 only (QKV, FFN1, decoder q / kv projections): TMEM loads are double
-// buffered in registers and each thread stores its own row segment directly (64 contiguous bytes per chunk).
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -64,8 +62,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty = bars + STAGES;       // one set per CTA, signalled by the multicast commit
   uint64_t* tfull = bars + 2 * STAGES;   // one set per CTA
   uint64_t* tempty = tfull + 2;          // used on the even CTA: 2 x kEpiWarps arrivals
-  uint64_t* obar = tempty + 2;           // FAST epilogue: per lane quarter {ofull[2], oempty[2]} (16) + bfull[2] (8)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(obar + 24);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +87,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 2 * kEpiWarps);
     }
-    for (int i = 0; i < 24; ++i) mbar_init(&obar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, kTmemCols);
