@@ -53,7 +53,7 @@ EXPORTS = [
     "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
-    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln",
 ]
 
 
@@ -588,6 +588,17 @@ def op_lstm(x, seq_off, seq_len, w_ih, w_hh, b_ih, b_hh, bf16_out=False, device=
     _check(lib().b200pf_op_lstm(device, _p(x), x.shape[0], _p(so, c_i32p), _p(sl, c_i32p), len(so), n_dir, _p(w_ih), _p(w_hh),
                                 _p(b_ih), _p(b_hh), int(bf16_out), _p(out)))
     return out
+
+
+def op_gemm_ln(x, gamma, beta, W, bias=None, relu=0, eps=1e-12, iters=0, device=0):
+    """LN(x) @ W^T (+bias)(+relu) -> bf16, the fused LayerNorm + GEMM kernel.  Returns (out fp32 [M,N], ms per launch or None)."""
+    x, gamma, beta, W, bias = _f32(x), _f32(gamma), _f32(beta), _f32(W), _f32(bias)
+    M, N = x.shape[0], W.shape[0]
+    out = np.zeros((M, N), np.float32)
+    ms = C.c_float(0)
+    _check(lib().b200pf_op_gemm_ln(device, _p(x), _p(gamma), _p(beta), C.c_float(eps), _p(W), _p(bias), M, N, int(relu), int(iters),
+                                   _p(out), C.byref(ms)))
+    return out, (ms.value if iters > 0 else None)
 
 
 def op_logprob_topk(logits, k, device=0):

@@ -115,6 +115,41 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   return 0;
 }
 
+int b200pf_op_gemm_ln(int device, const float* x, const float* gamma, const float* beta, float eps, const float* W, const float* bias,
+                      int M, int N, int relu, int iters, float* out, float* ms_out) {
+  RC(select_device(device));
+  if (N % 256) { set_error("op_gemm_ln: N % 256 required"); return B200PF_ERR_INVALID; }
+  DevBuf dX, dG, dBt, tw, dW, dBias, dOutB, dOut;
+  RC(up_f32(x, (size_t)M * 512, &dX)); RC(up_f32(gamma, 512, &dG)); RC(up_f32(beta, 512, &dBt));
+  RC(up_bf16(W, (size_t)N * 512, &tw, &dW));
+  if (bias) RC(up_f32(bias, N, &dBias));
+  RC(dOutB.alloc((size_t)M * N * 2)); RC(dOut.alloc((size_t)M * N * 4));
+  const int sms = sm_count();
+  int rc = gemm_ln_bf16_tcgen05(dX.as<float>(), 512, M, dG.as<float>(), dBt.as<float>(), eps, dW.as<__nv_bfloat16>(), N,
+                                bias ? dBias.as<float>() : nullptr, relu, dOutB.as<__nv_bfloat16>(), N, sms, 0);
+  if (rc) return check_cuda((cudaError_t)rc, "gemm_ln launch");
+  RC(sync_ok("op_gemm_ln"));
+  if (iters > 0) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, 0);
+    for (int i = 0; i < iters; ++i) {
+      rc = gemm_ln_bf16_tcgen05(dX.as<float>(), 512, M, dG.as<float>(), dBt.as<float>(), eps, dW.as<__nv_bfloat16>(), N,
+                                bias ? dBias.as<float>() : nullptr, relu, dOutB.as<__nv_bfloat16>(), N, sms, 0);
+      if (rc) return check_cuda((cudaError_t)rc, "gemm_ln launch");
+    }
+    cudaEventRecord(b, 0);
+    RC(sync_ok("op_gemm_ln"));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (ms_out) *ms_out = ms / iters;
+  }
+  bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)M * N);
+  RC(sync_ok("op_gemm_ln"));
+  return check_cuda(cudaMemcpy(out, dOut.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
 int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, float* ms_out) {
   RC(select_device(device));
   DevBuf dA, dW, dBias, dAdd, dX, dOutB, dAm;

@@ -262,6 +262,12 @@ __device__ __forceinline__ void mbar_arrive_even_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// Same with release semantics at cluster scope: the arriving thread's earlier shared-memory writes (made visible to the
+// async proxy by fence.proxy.async) are ordered before the even CTA's observation of the phase.
+__device__ __forceinline__ void mbar_arrive_even_cta_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // registers -> TMEM, 32 lanes x 16 columns of 32 bit (used to park bf16x2-packed P for the TS MMA)
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(

@@ -164,6 +164,10 @@ int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int
  * argmax_out (optional, [M]) receives the fused greedy argmax (first maximum wins, util.cpp:63-74). */
 int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
                    int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out);
+/* LayerNorm fused into its consumer GEMM: out[M,N] = bf16(act(LN(x[M,512]; gamma, beta, eps) W[N,512]^T + bias)) widened to fp32;
+ * N % 256 == 0.  iters > 0 additionally times that many launches (ms_out = milliseconds per launch). */
+int b200pf_op_gemm_ln(int device, const float* x, const float* gamma, const float* beta, float eps, const float* W, const float* bias,
+                      int M, int N, int relu, int iters, float* out, float* ms_out);
 /* Times `iters` back-to-back launches of the GEMM on device-resident dummy operands (CUDA events); mode 0: bias ->
  * bf16, 1: bias+ReLU -> bf16, 2: bias + fp32 residual in place, 3: bias + bf16 addend + fp32 residual in place,
  * 4: bias + fused argmax only.  ms_out = average milliseconds per launch. */

@@ -61,6 +61,25 @@ def test_gemm_tcgen05(capi, gpu, shape):
     assert rel(capi.op_gemm(A, W, bias=bias, res=res, relu=2, out_bf16=True), bf(np.maximum(ref + bias + res, 0))) <= 4e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 256), (100, 512), (256, 1536), (257, 2048), (1000, 1536), (5000, 2048), (20000, 1536)])
+def test_gemm_with_fused_layernorm(capi, gpu, shape):
+    """LN -> GEMM fused (gemm_ln.cu) against LayerNorm in fp32, rounded to bf16, times bf16 weights."""
+    import torch
+    M, N = shape
+    rng = np.random.default_rng(M + N)
+    x = (rng.standard_normal((M, 512)) * rng.uniform(0.5, 4.0, (M, 1)) + rng.uniform(-2, 2, (M, 1))).astype(np.float32)
+    g = rng.uniform(0.5, 1.5, 512).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, 512).astype(np.float32)
+    W = (rng.standard_normal((N, 512)) / np.sqrt(512)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ln = torch.nn.functional.layer_norm(torch.from_numpy(x), (512,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
+    ref = np.maximum(bf(ln) @ bf(W).T + bias, 0)
+    out, _ = capi.op_gemm_ln(x, g, b, W, bias=bias, relu=1)
+    assert rel(out, bf(ref)) <= 6e-3      # a bf16 rounding of LN(x) that falls the other way moves one product term
+    out2, _ = capi.op_gemm_ln(x, g, b, W)
+    assert rel(out2, bf(bf(ln) @ bf(W).T)) <= 6e-3
+
+
 def test_gemm_vocab_argmax_first_max_wins(capi, gpu):
     rng = np.random.default_rng(7)
     M, N, K = 257, 8404, 512
