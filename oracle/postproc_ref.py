@@ -8,10 +8,13 @@ timestamp post-processing on the Paraformer::Forward path.
   stitch_offline           FunOfflineInferBuffer    onnxruntime/src/funasrruntime.cpp:291-316
   fetch_dynamic            Audio::FetchDynamic      onnxruntime/src/audio.cpp:1052-1108
 
-PARITY UNPINNED: the reference has no tests or golden vectors for these functions and
-util.cpp cannot be linked here without the reference's cmake-generated gflags/glog headers, so this file
-follows the source line by line instead.  float arithmetic is done in numpy float32 where the C++ uses
-float, and `std::to_string(float)` is reproduced as '%f' of the float promoted to double.
+PARITY PINNED for Vector2StringV2 / Vector2String / TimestampOnnx / PostProcess: the reference's own vocab.cpp and util.cpp
+are compiled in place into oracle/_ref/libfunasr_text_ref.so (oracle/Makefile, oracle/text_ref.py) and this file reproduces
+them string for string on thousands of random inputs (tests/test_oracle_cpu.py, live when oracle/_ref is built) and on the
+committed vectors generated from the compiled reference (tests/golden/text_golden.json).  stitch_offline and fetch_dynamic
+follow the source line by line (funasrruntime.cpp / audio.cpp do not compile stand-alone: ffmpeg, ORT sessions) and stay
+unpinned.  float arithmetic is done in numpy float32 where the C++ uses float, and `std::to_string(float)` is reproduced as
+'%f' of the float promoted to double.
 """
 import numpy as np
 

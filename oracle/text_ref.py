@@ -1,0 +1,58 @@
+"""ORACLE (test infrastructure only): ctypes access to the REFERENCE's own host text code, compiled in place from
+/root/reference by `make -C oracle ref` into oracle/_ref/libfunasr_text_ref.so (funasr::Vocab::Vector2StringV2 /
+Vector2String, funasr::TimestampOnnx, funasr::PostProcess).  Only available in the build container; the golden vectors
+generated from it (tests/golden/text_golden.json, tests/golden/make_golden.py) travel to the GPU box instead."""
+import ctypes as C
+import json
+import os
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libfunasr_text_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_PATH)
+        L.ref_vocab_create.restype = C.c_void_p
+        L.ref_vocab_create.argtypes = [C.c_char_p]
+        L.ref_vocab_destroy.argtypes = [C.c_void_p]
+        L.ref_vector2string_v2.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_greedy_with_stamps.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             C.c_int, C.c_char_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+class RefVocab:
+    """funasr::Vocab loaded from a tokens.json written to a temp file (Vocab::LoadVocabFromJson, vocab.cpp:46-63)."""
+
+    def __init__(self, tokens):
+        self._dir = tempfile.mkdtemp(prefix="ref_vocab_")
+        p = os.path.join(self._dir, "tokens.json")
+        with open(p, "w", encoding="utf-8") as f:
+            json.dump(list(tokens), f, ensure_ascii=False)
+        self.h = lib().ref_vocab_create(p.encode())
+
+    def vector2string_v2(self, ids, language=""):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        buf = C.create_string_buffer(1 << 18)
+        lib().ref_vector2string_v2(self.h, a.ctypes.data_as(C.POINTER(C.c_int)), len(a), language.encode(), buf, len(buf))
+        return buf.value.decode("utf-8")
+
+    def greedy_with_stamps(self, ids, us_alphas, us_peaks):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        al = np.ascontiguousarray(us_alphas, dtype=np.float32)
+        pk = np.ascontiguousarray(us_peaks, dtype=np.float32)
+        buf = C.create_string_buffer(1 << 18)
+        lib().ref_greedy_with_stamps(self.h, a.ctypes.data_as(C.POINTER(C.c_int)), len(a), al.ctypes.data_as(C.POINTER(C.c_float)),
+                                     pk.ctypes.data_as(C.POINTER(C.c_float)), len(al), buf, len(buf))
+        return buf.value.decode("utf-8")

@@ -112,6 +112,49 @@ def main():
         top2 = np.sort(lg, axis=1)[:, -2:]
         c3["top_gap_%d" % n] = (top2[:, 1] - top2[:, 0]).astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "model_cfg3_golden.npz"), **c3)
+    # host text path from the reference's OWN compiled code (oracle/_ref/libfunasr_text_ref.so: Vocab::Vector2StringV2,
+    # Vector2String -> TimestampOnnx -> PostProcess)
+    import json
+    from oracle import text_ref as T
+    from oracle import postproc_ref as P
+    assert T.available(), "needs oracle/_ref/libfunasr_text_ref.so (make -C oracle ref in the build container)"
+    toks = synth.make_tokens(8404)
+    rv = T.RefVocab(toks)
+    ov = P.Vocab(toks)
+    rng = np.random.default_rng(2026)
+    text_cases, stamp_cases = [], []
+    for lang in ("zh-cn", "en-bpe", ""):
+        rvl = T.RefVocab(toks)      # Vector2StringV2 is stateful across calls: one vocabulary per sequence of calls
+        for _ in range(40):
+            n = int(rng.integers(0, 30))
+            ids = np.where(rng.random(n) < 0.6, rng.integers(3, 7903, n), rng.integers(7903, 8404, n))
+            ids = np.where(rng.random(n) < 0.06, rng.integers(0, 3, n), ids).astype(np.int32)
+            text_cases.append(dict(lang=lang, ids=[int(i) for i in ids], text=rvl.vector2string_v2(ids, lang)))
+    while len(stamp_cases) < 60:
+        n = int(rng.integers(1, 25))
+        ids = np.where(rng.random(n) < 0.7, rng.integers(3, 7903, n), rng.integers(7903, 8403, n)).astype(np.int32)
+        nf = int(rng.integers(3 * n, 12 * n + 10))
+        al = rng.uniform(0, 0.4, nf).astype(np.float32)
+        k = n + (0 if rng.random() < 0.6 else int(rng.integers(-2, 3))) + 1      # != n + 1 exercises the rescale branch
+        al = (al * (k / al.sum())).astype(np.float32)
+        if rng.random() < 0.15:
+            al[: nf // 3] = 0                                                     # long leading silence -> <sil> / token split
+        pk = np.zeros(nf, np.float32)
+        s = np.float32(0)
+        for i in range(nf):
+            s = np.float32(s + al[i])
+            pk[i] = s
+            if s >= np.float32(1 - 1e-4):
+                s = np.float32(s - np.float32(1 - 1e-4))
+        try:
+            P.greedy_search_text(ov, list(ids), "zh-cn", list(al), list(pk))
+        except IndexError:
+            continue                # the reference reads out of bounds for this input (undefined there): no golden value
+        stamp_cases.append(dict(ids=[int(i) for i in ids], us_alphas=[float(x) for x in al], us_peaks=[float(x) for x in pk],
+                                text=rv.greedy_with_stamps(ids, al, pk)))
+    with open(os.path.join(HERE, "text_golden.json"), "w", encoding="utf-8") as f:
+        json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
+                  f, ensure_ascii=False)
     print("wrote", os.listdir(HERE))
 
 

@@ -73,6 +73,22 @@ def test_timestamp_postprocess_matches_oracle(capi, toks):
     assert checked > 400
 
 
+def test_host_text_matches_reference_compiled_golden(capi, toks):
+    """The C++ host mirror (csrc/host/text.cpp) against strings produced by the reference's own compiled code."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_golden.json"), encoding="utf-8"))
+    cur_lang, d = None, None
+    for c in g["text"]:
+        if c["lang"] != cur_lang:
+            cur_lang, d = c["lang"], capi.HostDetok(toks)
+        assert d.text(np.asarray(c["ids"], np.int32), c["lang"]) == c["text"]
+    d = capi.HostDetok(toks)
+    for c in g["stamps"]:
+        got = d.timestamp_text(np.asarray(c["ids"], np.int32), np.asarray(c["us_alphas"], np.float32), np.asarray(c["us_peaks"], np.float32))
+        assert got == c["text"]
+
+
 def test_stitch_matches_oracle(capi):
     rng = np.random.default_rng(3)
     for _ in range(200):

@@ -212,6 +212,61 @@ def _vocab():
     return P.Vocab(toks), {t: i for i, t in enumerate(toks)}
 
 
+def test_text_oracle_matches_reference_compiled_golden():
+    """tests/golden/text_golden.json comes from the reference's own compiled vocab.cpp / util.cpp (make_golden.py)."""
+    import json
+    from oracle import postproc_ref as PP
+    g = json.load(open(os.path.join(GOLD, "text_golden.json"), encoding="utf-8"))
+    synth = __import__("importlib").import_module("asr-2pass_b200.synth")
+    toks = synth.make_tokens(8404)
+    cur_lang, v = None, None
+    for c in g["text"]:
+        if c["lang"] != cur_lang:                       # one stateful vocabulary per language block, as generated
+            cur_lang, v = c["lang"], PP.Vocab(toks)
+        assert v.vector2string_v2(c["ids"], c["lang"]) == c["text"]
+    v = PP.Vocab(toks)
+    assert len(g["stamps"]) >= 50
+    for c in g["stamps"]:
+        assert PP.greedy_search_text(v, c["ids"], "zh-cn", c["us_alphas"], c["us_peaks"]) == c["text"]
+
+
+def test_text_oracle_matches_live_reference_when_built():
+    """In the build container the compiled reference is present: compare on fresh random inputs too."""
+    from oracle import postproc_ref as PP
+    from oracle import text_ref as T
+    if not T.available():
+        pytest.skip("oracle/_ref/libfunasr_text_ref.so not built (needs /root/reference)")
+    synth = __import__("importlib").import_module("asr-2pass_b200.synth")
+    toks = synth.make_tokens(8404)
+    rv, ov = T.RefVocab(toks), PP.Vocab(toks)
+    rng = np.random.default_rng(99)
+    for _ in range(300):
+        n = int(rng.integers(0, 30))
+        ids = np.where(rng.random(n) < 0.6, rng.integers(3, 7903, n), rng.integers(7903, 8404, n)).astype(np.int32)
+        assert rv.vector2string_v2(ids, "zh-cn") == ov.vector2string_v2([int(i) for i in ids], "zh-cn")
+    checked = 0
+    for _ in range(300):
+        n = int(rng.integers(1, 25))
+        ids = np.where(rng.random(n) < 0.7, rng.integers(3, 7903, n), rng.integers(7903, 8403, n)).astype(np.int32)
+        nf = int(rng.integers(3 * n, 12 * n + 10))
+        al = rng.uniform(0, 0.4, nf).astype(np.float32)
+        al = (al * ((n + int(rng.integers(-1, 2)) + 1) / al.sum())).astype(np.float32)
+        pk = np.zeros(nf, np.float32)
+        s = np.float32(0)
+        for i in range(nf):
+            s = np.float32(s + al[i])
+            pk[i] = s
+            if s >= np.float32(1 - 1e-4):
+                s = np.float32(s - np.float32(1 - 1e-4))
+        try:
+            want = PP.greedy_search_text(ov, [int(i) for i in ids], "zh-cn", list(al), list(pk))
+        except IndexError:
+            continue            # undefined in the reference (out-of-bounds read)
+        assert rv.greedy_with_stamps(ids, al, pk) == want
+        checked += 1
+    assert checked > 250
+
+
 def test_vector2string_v2_rules():
     v, ix = _vocab()
     ids = [ix[t] for t in ["<s>", "你", "好", "hel@@", "lo", "wor@@", "ld", "</s>"]]
