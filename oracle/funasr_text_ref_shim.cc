@@ -2,14 +2,26 @@
 // /root/reference by oracle/Makefile (target `ref`) into oracle/_ref/libfunasr_text_ref.so:
 //     funasr::Vocab::Vector2StringV2 / Vector2String   onnxruntime/src/vocab.cpp:98-104,164-305
 //     funasr::TimestampOnnx, funasr::PostProcess        onnxruntime/src/util.cpp:720-963
+//     funasr::ParaformerOnline::GetPosEmb / CifSearch   onnxruntime/src/paraformer-online.cpp:240-345
 // Nothing of the reference is copied: this file only calls it.  Two things are supplied here because the reference gets
 // them from CMake: a stand-in <gflags/gflags.h> (oracle/stubs; the vendored gflags header is generated) and the few glog
 // LogMessage symbols the sources reference through LOG(...) (the vendored glog library is not built).
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <numeric>
 #include <sstream>
 #include <string>
 #include <vector>
 
+// ParaformerOnline::GetPosEmb / CifSearch (paraformer-online.cpp:240-345) are private members; they are reached by opening
+// the access specifiers for the reference headers only (the standard headers above are already included and guarded).
+#define private public
+#define protected public
 #include "precomp.h"
+#undef private
+#undef protected
 
 namespace google {
 static std::ostringstream g_sink;
@@ -53,6 +65,50 @@ int ref_greedy_with_stamps(void* v, const int* ids, int n, const float* us_alpha
   std::vector<float> al(us_alphas, us_alphas + n_frames), pk(us_peaks, us_peaks + n_frames);
   funasr::TimestampOnnx(al, pk, char_list, res_str, timestamp_list);
   return CopyOut(funasr::PostProcess(raw_char, timestamp_list), out, cap);
+}
+
+// ---- ParaformerOnline::GetPosEmb / CifSearch, called on an object whose constructor (ORT sessions) is bypassed --------
+// Zero-filled storage is a valid state for the std::vector members of libstdc++; the scalar members the two functions
+// read are set explicitly.  chunk_size {0, T, 0} + is_last_chunk reproduces the offline predictor: no alpha is zeroed
+// and the tail frame (alpha = tail_alphas, zero hidden) is appended (paraformer-online.cpp:281-300).
+void* ref_online_create(float cif_threshold, float tail_alphas) {
+  void* mem = calloc(1, sizeof(funasr::ParaformerOnline));
+  funasr::ParaformerOnline* po = (funasr::ParaformerOnline*)mem;
+  po->cif_threshold = cif_threshold;
+  po->tail_alphas = tail_alphas;
+  return po;
+}
+void ref_online_destroy(void* h) { free(h); }  // no destructor: nothing but vectors we clear below
+
+// hidden [T][D], alphas [T] -> frames written to out [cap_tok][D]; returns the number of fired tokens
+int ref_cif_search(void* h, const float* hidden, const float* alphas, int T, int D, float* out, int cap_tok) {
+  funasr::ParaformerOnline* po = (funasr::ParaformerOnline*)h;
+  po->chunk_size.clear();
+  po->chunk_size.push_back(0); po->chunk_size.push_back(T); po->chunk_size.push_back(0);
+  po->is_last_chunk = true;
+  po->hidden_cache_.clear();
+  po->alphas_cache_.clear();
+  std::vector<std::vector<float>> hid(T, std::vector<float>(D));
+  for (int t = 0; t < T; ++t) std::copy(hidden + (size_t)t * D, hidden + (size_t)(t + 1) * D, hid[t].begin());
+  std::vector<float> al(alphas, alphas + T);
+  std::vector<std::vector<float>> frames;
+  po->CifSearch(hid, al, true, frames);
+  const int n = (int)frames.size();
+  for (int i = 0; i < n && i < cap_tok; ++i) std::copy(frames[i].begin(), frames[i].end(), out + (size_t)i * D);
+  po->hidden_cache_.clear();
+  po->alphas_cache_.clear();
+  std::vector<int>().swap(po->chunk_size);
+  return n;
+}
+
+// feats [T][D] += position encoding for positions 1..T (start_idx_cache_ = 0), in place
+void ref_pos_emb(void* h, float* feats, int T, int D) {
+  funasr::ParaformerOnline* po = (funasr::ParaformerOnline*)h;
+  po->start_idx_cache_ = 0;
+  std::vector<std::vector<float>> f(T, std::vector<float>(D));
+  for (int t = 0; t < T; ++t) std::copy(feats + (size_t)t * D, feats + (size_t)(t + 1) * D, f[t].begin());
+  po->GetPosEmb(f, T, D);
+  for (int t = 0; t < T; ++t) std::copy(f[t].begin(), f[t].end(), feats + (size_t)t * D);
 }
 
 }  // extern "C"

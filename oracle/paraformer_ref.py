@@ -18,6 +18,11 @@ outputs logits[1,L,8404] f32 + token_num: paraformer.cpp:496-562) and on in-repo
   * CIF integrate-and-fire recurrence  onnxruntime/src/paraformer-online.cpp:270-345
   * cif_threshold 1.0, tail 0.45, 512-d, kernel 11 (fsmn_lorder 10)   onnxruntime/src/paraformer.h:112-123
 
+Two pieces of this file ARE pinned against the reference's own compiled code (oracle/_ref/libfunasr_text_ref.so, built
+from onnxruntime/src/paraformer-online.cpp where it lies; golden vectors tests/golden/cif_posenc_golden.npz): `cif`
+(ParaformerOnline::CifSearch run in its offline form: token counts exact, frames to 1e-6) and `pos_enc`
+(ParaformerOnline::GetPosEmb: 1e-6, 1e-5 at position 1000).
+
 `emulate_bf16=True` rounds to bfloat16 exactly where the CUDA path stores bf16 (GEMM operands and the
 bf16 activation buffers), keeping every reduction in fp32.  It is a second oracle used to separate
 "kernel is wrong" from "bf16 rounding moved a value"; the acceptance tolerances are stated against the

@@ -28,8 +28,36 @@ def lib():
         L.ref_vector2string_v2.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_char_p, C.c_char_p, C.c_int]
         L.ref_greedy_with_stamps.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.c_int, C.c_char_p, C.c_int]
+        L.ref_online_create.restype = C.c_void_p
+        L.ref_online_create.argtypes = [C.c_float, C.c_float]
+        L.ref_online_destroy.argtypes = [C.c_void_p]
+        L.ref_cif_search.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.ref_pos_emb.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int]
         _lib = L
     return _lib
+
+
+def cif_search(hidden, alphas, threshold=1.0, tail=0.45):
+    """ParaformerOnline::CifSearch (paraformer-online.cpp:270-345) with chunk_size {0, T, 0} and is_last_chunk: the offline
+    predictor's integrate-and-fire incl. the tail frame.  hidden [T,D], alphas [T] -> token frames [L,D]."""
+    h = np.ascontiguousarray(hidden, dtype=np.float32)
+    a = np.ascontiguousarray(alphas, dtype=np.float32)
+    T_, D = h.shape
+    out = np.zeros((T_ + 2, D), np.float32)
+    po = lib().ref_online_create(C.c_float(threshold), C.c_float(tail))
+    n = lib().ref_cif_search(po, h.ctypes.data_as(C.POINTER(C.c_float)), a.ctypes.data_as(C.POINTER(C.c_float)), T_, D,
+                             out.ctypes.data_as(C.POINTER(C.c_float)), T_ + 2)
+    lib().ref_online_destroy(po)
+    return out[:n].copy()
+
+
+def pos_emb(T_, depth):
+    """ParaformerOnline::GetPosEmb (paraformer-online.cpp:240-268) applied to zeros: the sinusoid table for positions 1..T."""
+    f = np.zeros((T_, depth), np.float32)
+    po = lib().ref_online_create(C.c_float(1.0), C.c_float(0.45))
+    lib().ref_pos_emb(po, f.ctypes.data_as(C.POINTER(C.c_float)), T_, depth)
+    lib().ref_online_destroy(po)
+    return f
 
 
 class RefVocab:

@@ -152,6 +152,20 @@ def main():
             continue                # the reference reads out of bounds for this input (undefined there): no golden value
         stamp_cases.append(dict(ids=[int(i) for i in ids], us_alphas=[float(x) for x in al], us_peaks=[float(x) for x in pk],
                                 text=rv.greedy_with_stamps(ids, al, pk)))
+    # CIF integrate-and-fire and the sinusoidal position encoding from the reference's own compiled
+    # ParaformerOnline::CifSearch / GetPosEmb (paraformer-online.cpp:240-345)
+    cg = {}
+    for Tn in (1, 7, 33, 167, 1000):
+        h = rng.standard_normal((Tn, 8)).astype(np.float32)
+        a = rng.uniform(0, 1, Tn).astype(np.float32)
+        if Tn > 20:
+            a[10:14] = 0.5                      # exact threshold hits
+        cg["cif_hidden_%d" % Tn] = h
+        cg["cif_alphas_%d" % Tn] = a
+        cg["cif_frames_%d" % Tn] = T.cif_search(h, a)
+    cg["pos_emb_64x560"] = T.pos_emb(64, 560)
+    cg["pos_emb_row1000"] = T.pos_emb(1000, 560)[999]
+    np.savez_compressed(os.path.join(HERE, "cif_posenc_golden.npz"), **cg)
     with open(os.path.join(HERE, "text_golden.json"), "w", encoding="utf-8") as f:
         json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
                   f, ensure_ascii=False)

@@ -212,6 +212,42 @@ def _vocab():
     return P.Vocab(toks), {t: i for i, t in enumerate(toks)}
 
 
+def test_cif_and_posenc_oracle_match_reference_compiled_golden():
+    """tests/golden/cif_posenc_golden.npz comes from the reference's own compiled ParaformerOnline::CifSearch / GetPosEmb
+    (paraformer-online.cpp:240-345) run in offline form (chunk {0,T,0}, last chunk -> tail frame 0.45).  Token counts are
+    exact; frames agree to 1e-6 (the online code carries `integrate - threshold` where the offline graph carries
+    `alpha - (threshold - integrate)`: equal in exact arithmetic, one rounding apart in fp32)."""
+    import torch
+    from oracle import paraformer_ref as R
+    g = np.load(os.path.join(GOLD, "cif_posenc_golden.npz"))
+    for Tn in (1, 7, 33, 167, 1000):
+        h, a, ref = g["cif_hidden_%d" % Tn], g["cif_alphas_%d" % Tn], g["cif_frames_%d" % Tn]
+        hh = torch.cat([torch.from_numpy(h), torch.zeros(1, h.shape[1])], 0)
+        aa = torch.cat([torch.from_numpy(a), torch.tensor([0.45])])
+        emb, fires = R.cif(hh, aa, 1.0)
+        assert emb.shape[0] == ref.shape[0] == int((fires >= 1.0).sum())
+        if ref.size:
+            assert np.abs(emb.numpy() - ref).max() <= 1e-6
+    pe = R.pos_enc(1000, 560).numpy()
+    assert np.abs(pe[:64] - g["pos_emb_64x560"]).max() <= 1e-6
+    assert np.abs(pe[999] - g["pos_emb_row1000"]).max() <= 1e-5     # sin/cos of arguments up to 1000 in float
+
+
+def test_cif_oracle_matches_live_reference_when_built():
+    import torch
+    from oracle import paraformer_ref as R
+    from oracle import text_ref as T
+    if not T.available():
+        pytest.skip("oracle/_ref/libfunasr_text_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(12)
+    for Tn in (2, 50, 333):
+        h = rng.standard_normal((Tn, 16)).astype(np.float32)
+        a = rng.uniform(0, 1, Tn).astype(np.float32)
+        ref = T.cif_search(h, a)
+        emb, _ = R.cif(torch.cat([torch.from_numpy(h), torch.zeros(1, 16)], 0), torch.cat([torch.from_numpy(a), torch.tensor([0.45])]), 1.0)
+        assert emb.shape[0] == ref.shape[0] and (ref.size == 0 or np.abs(emb.numpy() - ref).max() <= 1e-6)
+
+
 def test_text_oracle_matches_reference_compiled_golden():
     """tests/golden/text_golden.json comes from the reference's own compiled vocab.cpp / util.cpp (make_golden.py)."""
     import json
