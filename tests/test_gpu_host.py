@@ -74,3 +74,27 @@ def test_init_failure_is_reported_not_fatal_through_the_hooks(capi, tmp_path):
         capi.OfflineHandle(str(tmp_path))                                 # no model files
     with pytest.raises(capi.B200PFError):
         capi.funasr_infer(str(tmp_path), pcm16=np.zeros(16000, np.int16))
+
+
+def test_concurrent_forward_calls_on_one_handle(capi, synth, model):
+    """decoder-thread-num threads share one handle in the reference's servers (websocket-server.cpp:387-403): concurrent
+    Forward calls must each get their own, correct result."""
+    import threading
+    h = capi.OfflineHandle(model["dir"], max_rows=4096, max_segments=64, batch_size=8)
+    segs = [synth.make_audio(int(n), 8000 + i).astype(np.float32) / np.float32(32768)
+            for i, n in enumerate([16000, 40000, 52800, 24000, 90000, 33000, 64000, 20000])]
+    ref = [_strip(h.model_forward([s])[0]) for s in segs]
+    out = [[None] * 6 for _ in segs]
+
+    def worker(i):
+        for k in range(6):
+            out[i][k] = _strip(h.model_forward([segs[i], segs[(i + k) % len(segs)]])[0])
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(segs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for i in range(len(segs)):
+        assert out[i] == [ref[i]] * 6
+    h.close()
