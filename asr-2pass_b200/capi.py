@@ -50,7 +50,7 @@ EXPORTS = [
     "b200pf_engine_config", "b200pf_engine_vocab_size", "b200pf_engine_token", "b200pf_engine_lang",
     "b200pf_engine_set_option", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_engine_copy_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
     "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
-    "b200pf_batch_stage_f32", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
+    "b200pf_batch_stage_f32", "b200pf_batch_stage_s16_ptrs", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
     "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln",

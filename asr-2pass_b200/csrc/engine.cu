@@ -749,6 +749,31 @@ int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* 
   return 0;
 }
 
+int b200pf_batch_stage_s16_ptrs(b200pf_batch* b, const int16_t* const* seg, const int64_t* len, int n_seg, void* stream) {
+  if (!b || n_seg < 0 || (n_seg > 0 && (!seg || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  b200pf_engine* e = b->e;
+  CK(cudaSetDevice(e->device), "cudaSetDevice");
+  cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+  std::vector<int64_t> ns(n_seg), st(n_seg);
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (len[i] < 0) { set_error("negative length"); return B200PF_ERR_INVALID; }
+    ns[i] = len[i];
+    st[i] = total;
+    total += (len[i] + 7) & ~int64_t(7);   // 16-byte aligned starts
+  }
+  if (total > 2 * b->max_samples) { set_error("batch exceeds max_samples"); return B200PF_ERR_CAPACITY; }  // d_pcm holds 4 bytes per sample
+  int rc = build_layout(b, ns, st);
+  if (rc) return rc;
+  b->pcm_is_f32 = 0;
+  for (int i = 0; i < n_seg; ++i)
+    if (b->dev_of_in[i] >= 0)
+      CK(cudaMemcpyAsync((int16_t*)b->d_pcm + st[i], seg[i], (size_t)len[i] * 2, cudaMemcpyHostToDevice, s), "H2D pcm");
+  CK(cudaMemcpyAsync(b->d_meta, b->h_meta, b->meta_bytes, cudaMemcpyHostToDevice, s), "H2D meta");
+  CK(cudaEventRecord(b->staged, s), "cudaEventRecord");
+  return 0;
+}
+
 int b200pf_batch_run(b200pf_batch* b, void* stream) {
   if (!b) { set_error("null batch"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;

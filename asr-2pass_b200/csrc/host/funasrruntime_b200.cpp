@@ -70,27 +70,29 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
   for (int k = 0; k < n; ++k) len_sorted[k] = seg_e[index[k]] - seg_b[index[k]];
   std::vector<std::string> msgs(n);
   std::vector<float> starts(n);
-  for (const auto& batch : FormBatches(len_sorted, asr->GetBatchSize())) {
-    // gather the batch contiguously (segments may overlap or be out of order in the source buffer)
-    std::vector<short> buf;
-    std::vector<int64_t> offs(1, 0);
-    for (int q : batch) {
-      const int s = index[q];
-      buf.insert(buf.end(), pcm + seg_b[s], pcm + seg_e[s]);
-      offs.push_back((int64_t)buf.size());
+  // The reference forms batches with Audio::FetchDynamic's padded-audio rule (max_len * (n + 1) <= 300 s, FormBatches above),
+  // which exists because its GPU path PADS every item to the longest.  The B200 engine packs variable-length rows and a
+  // segment's result does not depend on its batch, so the only cap that matters is the engine's own capacity:
+  // ParaformerB200 splits by max_rows / max_segments itself.  B200PF_FETCH_DYNAMIC=1 restores the reference's rule.
+  static const bool fetch_dynamic = getenv("B200PF_FETCH_DYNAMIC") != nullptr;
+  std::vector<std::vector<int>> batches;
+  if (fetch_dynamic) {
+    batches = FormBatches(len_sorted, asr->GetBatchSize());
+  } else {
+    batches.emplace_back(n);
+    std::iota(batches[0].begin(), batches[0].end(), 0);
+  }
+  for (const auto& batch : batches) {
+    // segments are handed over by pointer (they may overlap or be out of order in the source buffer): no host-side gather
+    std::vector<const int16_t*> ptrs(batch.size());
+    std::vector<int64_t> lens(batch.size());
+    for (size_t k = 0; k < batch.size(); ++k) {
+      const int s = index[batch[k]];
+      ptrs[k] = (const int16_t*)pcm + seg_b[s];
+      lens[k] = seg_e[s] - seg_b[s];
     }
-    std::vector<std::string> out;
-    if (!h->pool) {
-      out = h->asr->ForwardPcm16(buf.data(), offs.data(), (int)batch.size(), hw_emb);
-    } else {
-      // the multi-GPU handle takes the reference's own argument form: float = int16 / 32768 (Audio::LoadPcmwav, audio.cpp:803-804)
-      std::vector<float> fbuf(buf.size());
-      for (size_t i = 0; i < buf.size(); ++i) fbuf[i] = (float)buf[i] / 32768.0f;
-      std::vector<float*> ptrs(batch.size());
-      std::vector<int> lens(batch.size());
-      for (size_t k = 0; k < batch.size(); ++k) { ptrs[k] = fbuf.data() + offs[k]; lens[k] = (int)(offs[k + 1] - offs[k]); }
-      out = h->pool->Forward(ptrs.data(), lens.data(), true, hw_emb, nullptr, (int)batch.size());
-    }
+    std::vector<std::string> out = h->pool ? h->pool->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb)
+                                           : h->asr->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb);
     for (size_t k = 0; k < batch.size(); ++k) {
       const int s = index[batch[k]];
       msgs[s] = out[k];

@@ -134,6 +134,50 @@ std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool
   return results;
 }
 
+std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                                               const std::vector<std::vector<float>>& hw_emb) {
+  std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
+  if (n_seg <= 0 || models_.empty()) return results;
+  const int nd = (int)models_.size();
+  if (nd == 1) return models_[0]->ForwardSegments16(seg, len, n_seg, hw_emb);
+  std::vector<int> len32(n_seg), assign;
+  for (int i = 0; i < n_seg; ++i) len32[i] = (int)len[i];
+  PartitionSegments(len32.data(), n_seg, nd, &assign);
+  struct Share { std::vector<const int16_t*> ptr; std::vector<int64_t> len; std::vector<int> idx; std::vector<std::string> out; };
+  std::vector<Share> share(nd);
+  for (int i = 0; i < n_seg; ++i) {
+    Share& s = share[assign[i]];
+    s.ptr.push_back(seg[i]); s.len.push_back(len[i]); s.idx.push_back(i);
+  }
+  std::mutex mu;
+  std::condition_variable cv;
+  int pending = 0;
+  for (int d = 0; d < nd; ++d) if (!share[d].idx.empty()) ++pending;
+  for (int d = 0; d < nd; ++d) {
+    if (share[d].idx.empty()) continue;
+    Share* s = &share[d];
+    ParaformerB200* m = models_[d].get();
+    Worker* w = workers_[d].get();
+    Post(d, [=, &hw_emb, &mu, &cv, &pending]() {
+      s->out = m->ForwardSegments16(s->ptr.data(), s->len.data(), (int)s->idx.size(), hw_emb);
+      {
+        std::lock_guard<std::mutex> wl(w->mu);
+        w->segments += (long long)s->idx.size();
+      }
+      std::lock_guard<std::mutex> lk(mu);
+      if (--pending == 0) cv.notify_all();
+    });
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return pending == 0; });
+  }
+  for (int d = 0; d < nd; ++d)
+    for (size_t k = 0; k < share[d].idx.size(); ++k)
+      if (k < share[d].out.size()) results[share[d].idx[k]] = std::move(share[d].out[k]);
+  return results;
+}
+
 std::string MultiGpuParaformer::Forward(float* din, int len, bool input_finished, const std::vector<std::vector<float>>& hw_emb,
                                         void* wfst_decoder) {
   float* one[1] = {din};

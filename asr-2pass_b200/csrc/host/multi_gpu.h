@@ -40,6 +40,9 @@ class MultiGpuParaformer : public Model {
                                    void* wfst_decoder = nullptr, int batch_in = 1) override;
   std::string Forward(float* din, int len, bool input_finished, const std::vector<std::vector<float>>& hw_emb = {{0.0}},
                       void* wfst_decoder = nullptr) override;
+  // int16 segments by pointer (the stand-alone shim's VAD cut points): same sharding, each GPU's worker copies its own share
+  std::vector<std::string> ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                             const std::vector<std::vector<float>>& hw_emb = {{0.0}});
   void StartUtterance() override {}
   void EndUtterance() override {}
   void Reset() override {}

@@ -189,13 +189,17 @@ std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_se
 // One engine-sized sub-batch is staged into slot `k` (its own b200pf_batch: device PCM + layout) on the engine's COPY
 // stream, so that the host-to-device copies of sub-batch i+1 run while sub-batch i computes.
 bool ParaformerB200::StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
-                               const std::vector<std::vector<float>>& hw_emb) {
+                               const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16, const int64_t* len16) {
   Slot& sl = slots_[k];
   if (!sl.batch || samples > sl.samples) {
     if (sl.batch) b200pf_batch_destroy(sl.batch);
     sl.batch = nullptr;
     sl.hw_valid = false;
-    sl.samples = samples + samples / 4 + 16000;
+    // Sized ONCE for anything the engine can hold (a packed row is 6 fbank shifts = 960 samples; every segment adds at most
+    // one partial row and the 240-sample window overlap): re-creating a batch object costs tens of milliseconds of
+    // cudaMalloc / cudaMallocHost, which showed up as 100 ms stalls when batch sizes grew from call to call.
+    const int64_t full = (int64_t)max_rows_ * 960 + (int64_t)max_segments_ * 1200;
+    sl.samples = samples > full ? samples + 16000 : full;
     if (b200pf_batch_create(engine_, sl.samples, &sl.batch) != 0) { fprintf(stderr, "ParaformerB200: %s\n", b200pf_last_error()); return false; }
   }
   if (use_hotword_) {
@@ -215,7 +219,8 @@ bool ParaformerB200::StageSlot(int k, const int16_t* pcm, const int64_t* offsets
     }
   }
   void* cs = b200pf_engine_copy_stream(engine_);
-  const int rc = pcm ? b200pf_batch_stage_s16(sl.batch, pcm, offsets, n, cs) : b200pf_batch_stage_f32(sl.batch, din, len, n, cs);
+  const int rc = seg16 ? b200pf_batch_stage_s16_ptrs(sl.batch, seg16, len16, n, cs)
+                       : (pcm ? b200pf_batch_stage_s16(sl.batch, pcm, offsets, n, cs) : b200pf_batch_stage_f32(sl.batch, din, len, n, cs));
   if (rc != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
   return true;
 }
@@ -241,7 +246,8 @@ bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out) {
 // through two slots: stage(i+1) overlaps compute(i).  A failing sub-batch logs and leaves "" for its items, never throws
 // (paraformer.cpp:582-587).  Results keep the caller's order.
 std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
-                                                const std::vector<std::vector<float>>& hw_emb) {
+                                                const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16,
+                                                const int64_t* len16) {
   std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
   if (n_seg <= 0 || !engine_) return results;
   std::lock_guard<std::mutex> lock(mu_);
@@ -252,7 +258,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
     int64_t rows = 0, samples = 0;
     int end = start;
     while (end < n_seg && end - start < max_segments_) {
-      const int64_t ns = pcm ? offsets[end + 1] - offsets[end] : (int64_t)len[end];
+      const int64_t ns = seg16 ? len16[end] : (pcm ? offsets[end + 1] - offsets[end] : (int64_t)len[end]);
       const int T = b200pf_num_lfr_frames(ns);
       const int64_t r = T > 0 ? T + 1 : 0;
       if (end > start && rows + r > max_rows_) break;
@@ -265,6 +271,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
   }
   auto stage = [&](size_t i) {
     const Sub& sb = subs[i];
+    if (seg16) return StageSlot((int)(i & 1), nullptr, nullptr, nullptr, nullptr, sb.end - sb.start, sb.samples, hw_emb, seg16 + sb.start, len16 + sb.start);
     return StageSlot((int)(i & 1), pcm, pcm ? offsets + sb.start : nullptr, pcm ? nullptr : din + sb.start, pcm ? nullptr : len + sb.start,
                      sb.end - sb.start, sb.samples, hw_emb);
   };
@@ -299,6 +306,11 @@ std::string ParaformerB200::Forward(float* din, int len, bool input_finished, co
   int l[1] = {len};
   std::vector<std::string> r = Forward(one, l, input_finished, hw_emb, wfst_decoder, 1);
   return r.empty() ? std::string() : r[0];
+}
+
+std::vector<std::string> ParaformerB200::ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                                           const std::vector<std::vector<float>>& hw_emb) {
+  return RunAll(nullptr, nullptr, nullptr, nullptr, n_seg, hw_emb, seg, len);
 }
 
 std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,

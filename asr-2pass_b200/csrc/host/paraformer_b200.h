@@ -67,6 +67,10 @@ class ParaformerB200 : public Model {
   // Audio::LoadPcmwav, audio.cpp:787-819, which is exact: int16 -> float/32768 -> *32768).
   std::vector<std::string> ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,
                                         const std::vector<std::vector<float>>& hw_emb = {{0.0}});
+  // int16 segments that live anywhere (e.g. VAD cut points of one recording, any order): copied to the GPU from where they
+  // are, without a host-side gather.
+  std::vector<std::string> ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                             const std::vector<std::vector<float>>& hw_emb = {{0.0}});
 
   void StartUtterance() override {}
   void EndUtterance() override {}
@@ -101,10 +105,11 @@ class ParaformerB200 : public Model {
     std::vector<float> hw_flat;
   };
   bool StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
-                 const std::vector<std::vector<float>>& hw_emb);
+                 const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr, const int64_t* len16 = nullptr);
   bool CollectSlot(int k, int n, std::vector<std::string>* out);
   std::vector<std::string> RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
-                                  const std::vector<std::vector<float>>& hw_emb);
+                                  const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr,
+                                  const int64_t* len16 = nullptr);
 
   int device_, max_rows_, max_segments_;
   b200pf_engine* engine_ = nullptr;

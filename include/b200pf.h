@@ -140,6 +140,9 @@ int b200pf_engine_hotword_embed(b200pf_engine* e, const int32_t* ids, const int3
  * Host buffers may be pageable or pinned; the copy is enqueued on `stream` (NULL -> engine stream). */
 int b200pf_batch_stage_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, void* stream);
 int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, void* stream);
+/* s16 from separate segments (seg[i] holds len[i] samples): no host-side gather, each segment is copied straight from where
+ * the caller keeps it (e.g. the VAD cut points inside one long recording, in any order). */
+int b200pf_batch_stage_s16_ptrs(b200pf_batch* b, const int16_t* const* seg, const int64_t* len, int n_seg, void* stream);
 /* Enqueue the whole forward (fbank -> ... -> argmax) for the staged batch.  Asynchronous. */
 int b200pf_batch_run(b200pf_batch* b, void* stream);
 /* Copy results to the host (device->host on `stream`), synchronise, unpack.  */
