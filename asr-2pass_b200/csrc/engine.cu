@@ -637,6 +637,9 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
     frames += nfb;
     ++ns;
   }
+  // attention work items longest segment first: a CTA's run time grows with its segment's key count, and the grid is only
+  // ~2.3 waves deep, so the long items must not be the ones that start last
+  std::stable_sort(b->h_work, b->h_work + nwork, [&](const AttnWork& x, const AttnWork& y) { return b->h_seg_T[x.seg] > b->h_seg_T[y.seg]; });
   b->h_sample_off[ns] = 0;
   b->h_fb_off[ns] = frames;
   b->h_row_off[ns] = rows;
