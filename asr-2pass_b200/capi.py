@@ -53,7 +53,7 @@ EXPORTS = [
     "b200pf_batch_stage_f32", "b200pf_batch_stage_s16_ptrs", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
-    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln", "b200pf_vad_create", "b200pf_vad_destroy", "b200pf_vad_scores_s16",
 ]
 
 
@@ -446,6 +446,43 @@ class Engine:
         if nfb:
             _check(lib().b200pf_op_frontend(self.h, _p(pcm16, c_i16p), len(pcm16), _p(fb), _p(feats)))
         return fb, feats
+
+
+class VadEngine:
+    """FSMN-VAD scores on the GPU (replaces FsmnVad::Forward's onnxruntime session, fsmn-vad.cpp:72-135)."""
+
+    def __init__(self, vad_dir, device=0, max_frames=0):
+        self.h = C.c_void_p()
+        lib().b200pf_vad_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib().b200pf_vad_destroy.argtypes = [C.c_void_p]
+        lib().b200pf_vad_destroy.restype = None
+        lib().b200pf_vad_scores_s16.argtypes = [C.c_void_p, C.c_void_p, c_i64p, C.c_int, c_f32p, C.c_int64, c_i32p, c_f32p, c_f32p]
+        _check(lib().b200pf_vad_create(vad_dir.encode(), device, max_frames, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().b200pf_vad_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def scores(self, pcm16, offsets, all_probs=False, feats=False):
+        """-> (sil_prob [F], frame_off [n+1], probs [F,248] or None, feats [F,400] or None)"""
+        pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        cap = int(sum(lib().b200pf_num_fbank_frames(int(offsets[i + 1] - offsets[i])) for i in range(n)))
+        p0 = np.zeros(max(cap, 1), np.float32)
+        fo = np.zeros(n + 1, np.int32)
+        pr = np.zeros((max(cap, 1), 248), np.float32) if all_probs else None
+        ft = np.zeros((max(cap, 1), 400), np.float32) if feats else None
+        _check(lib().b200pf_vad_scores_s16(self.h, C.c_void_p(pcm16.ctypes.data), _p(offsets, c_i64p), n, _p(p0), cap, _p(fo, c_i32p),
+                                           _p(pr), _p(ft)))
+        return p0[:cap], fo, (pr[:cap] if pr is not None else None), (ft[:cap] if ft is not None else None)
 
 
 class Batch:

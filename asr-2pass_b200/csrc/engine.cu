@@ -122,41 +122,10 @@ struct Loader {
 // Front-end tables: same formulas, in the same precision, as knf (feature-window.cc:25-55,
 // mel-computations.cc:107-200) and the encoder's sinusoidal position encoding.
 bool build_frontend_tables(b200pf_engine* e, Loader& L, const std::vector<float>& means, const std::vector<float>& vars) {
-  std::vector<float> window(400);
-  const double a = (2.0 * M_PI) / 399.0;
-  for (int i = 0; i < 400; ++i) window[i] = (float)(0.54 - 0.46 * cos(a * (double)i));
-  std::vector<double> tw(512);
-  for (int k = 0; k < 256; ++k) { tw[2 * k] = cos(-2.0 * M_PI * k / 512.0); tw[2 * k + 1] = sin(-2.0 * M_PI * k / 512.0); }
-  auto mel = [](float f) { return 1127.0f * logf(1.0f + f / 700.0f); };
-  const float sample_freq = 16000.0f, nyquist = 0.5f * sample_freq;
-  const float fft_bin_width = sample_freq / 512;
-  const float mel_low = mel(20.0f), mel_high = mel(nyquist + 0.0f);
-  const float delta = (mel_high - mel_low) / (80 + 1);
-  std::vector<int> range(160), woff(80);
-  std::vector<float> w(1024, 0.f);
-  int used = 0;
-  for (int bin = 0; bin < 80; ++bin) {
-    const float left = mel_low + bin * delta, center = mel_low + (bin + 1) * delta, right = mel_low + (bin + 2) * delta;
-    int first = -1, last = -1;
-    std::vector<float> tb(256, 0.f);
-    for (int i = 0; i < 256; ++i) {
-      const float freq = fft_bin_width * i;
-      const float m = mel(freq);
-      if (m > left && m < right) {
-        float wt;
-        if (m <= center) wt = (m - left) / (center - left);
-        else wt = (right - m) / (right - center);
-        tb[i] = wt;
-        if (first == -1) first = i;
-        last = i;
-      }
-    }
-    const int size = last + 1 - first;
-    if (first < 0 || used + size > 1024) { L.fail("mel table overflow"); return false; }
-    range[2 * bin] = first; range[2 * bin + 1] = size; woff[bin] = used;
-    for (int k = 0; k < size; ++k) w[used + k] = tb[first + k];
-    used += size;
-  }
+  std::vector<float> window, w;
+  std::vector<double> tw;
+  std::vector<int> range, woff;
+  if (!fbank_tables_host(&window, &tw, &range, &w, &woff)) { L.fail("mel table overflow"); return false; }
   const int F = e->cfg.feat_dim, half = F / 2, pe_rows = 2048;
   std::vector<float> pe((size_t)pe_rows * F);
   const float inc = (float)(-(log(10000.0) / (half - 1)));

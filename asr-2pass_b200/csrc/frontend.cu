@@ -10,6 +10,10 @@
 // everything except the FFT (double, like knf, but a different butterfly order) and logf is bit-identical.
 #include <float.h>
 
+#include <math.h>
+
+#include <vector>
+
 #include "kernels.cuh"
 #include "launch.cuh"
 
@@ -224,6 +228,50 @@ lfr_cmvn_posenc_kernel(const float* __restrict__ fb, const int* __restrict__ fb_
 }
 
 }  // namespace
+
+// Host-side tables of the Kaldi fbank front end (shared by the acoustic model and the VAD engine): hamming window [400],
+// forward twiddles of the 512-point FFT [256] as (cos, sin) doubles, and the 80 triangular mel filters packed as
+// {first_bin, size} ranges + weights (at most 1024 weights).
+bool fbank_tables_host(std::vector<float>* window_o, std::vector<double>* tw_o, std::vector<int>* range_o, std::vector<float>* w_o,
+                       std::vector<int>* woff_o) {
+  std::vector<float> window(400);
+  const double a = (2.0 * M_PI) / 399.0;
+  for (int i = 0; i < 400; ++i) window[i] = (float)(0.54 - 0.46 * cos(a * (double)i));
+  std::vector<double> tw(512);
+  for (int k = 0; k < 256; ++k) { tw[2 * k] = cos(-2.0 * M_PI * k / 512.0); tw[2 * k + 1] = sin(-2.0 * M_PI * k / 512.0); }
+  auto mel = [](float f) { return 1127.0f * logf(1.0f + f / 700.0f); };
+  const float sample_freq = 16000.0f, nyquist = 0.5f * sample_freq;
+  const float fft_bin_width = sample_freq / 512;
+  const float mel_low = mel(20.0f), mel_high = mel(nyquist + 0.0f);
+  const float delta = (mel_high - mel_low) / (80 + 1);
+  std::vector<int> range(160), woff(80);
+  std::vector<float> w(1024, 0.f);
+  int used = 0;
+  for (int bin = 0; bin < 80; ++bin) {
+    const float left = mel_low + bin * delta, center = mel_low + (bin + 1) * delta, right = mel_low + (bin + 2) * delta;
+    int first = -1, last = -1;
+    std::vector<float> tb(256, 0.f);
+    for (int i = 0; i < 256; ++i) {
+      const float freq = fft_bin_width * i;
+      const float m = mel(freq);
+      if (m > left && m < right) {
+        float wt;
+        if (m <= center) wt = (m - left) / (center - left);
+        else wt = (right - m) / (right - center);
+        tb[i] = wt;
+        if (first == -1) first = i;
+        last = i;
+      }
+    }
+    const int size = last + 1 - first;
+    if (first < 0 || used + size > 1024) return false;
+    range[2 * bin] = first; range[2 * bin + 1] = size; woff[bin] = used;
+    for (int k = 0; k < size; ++k) w[used + k] = tb[first + k];
+    used += size;
+  }
+  window_o->swap(window); tw_o->swap(tw); range_o->swap(range); w_o->swap(w); woff_o->swap(woff);
+  return true;
+}
 
 int fbank_launch(const void* pcm, int is_f32, const int64_t* sample_off, const int* fb_off, int n_seg,
                  int n_frames_total, const FrontendTables& t, float* fb, cudaStream_t s) {

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace pf {
 
 // Packed row layout shared by all kernels: segment i owns rows [row_off[i], row_off[i] + T_i) followed
@@ -22,6 +24,10 @@ struct FrontendTables {           // device pointers, built once per engine
   const float* pos_enc;           // [pe_rows][560]  sinusoid, positions from 1 (paraformer-online.cpp:240-268)
   int pe_rows;
 };
+
+// Host-side tables of the fbank front end (window, FFT twiddles, packed mel filters); false on overflow of the packed table.
+bool fbank_tables_host(std::vector<float>* window, std::vector<double>* twiddle, std::vector<int>* mel_range, std::vector<float>* mel_w,
+                       std::vector<int>* mel_w_off);
 
 // K1a  Kaldi fbank: Paraformer::FbankKaldi (src/paraformer.cpp:309-323) -> knf::OnlineFbank.
 //      pcm is int16 (is_f32 = 0) or float in [-1,1) (is_f32 = 1; multiplied by 32768 as the reference does).

@@ -114,6 +114,58 @@ def make_weights(cfg=None, seed=0, jitter_ln=False):
     return cfg, W
 
 
+VAD_DIMS = dict(input_dim=400, input_affine_dim=140, linear_dim=250, proj_dim=128, lorder=20, n_layers=4, output_affine_dim=140, output_dim=248)
+
+
+def vad_param_shapes(d=VAD_DIMS):
+    """FSMN-VAD (FunASR fsmn_vad_streaming `FSMN`) parameter names and shapes; mirrors oracle/vad_ref.py."""
+    out = {}
+    out["encoder.in_linear1.linear.weight"] = (d["input_affine_dim"], d["input_dim"])
+    out["encoder.in_linear1.linear.bias"] = (d["input_affine_dim"],)
+    out["encoder.in_linear2.linear.weight"] = (d["linear_dim"], d["input_affine_dim"])
+    out["encoder.in_linear2.linear.bias"] = (d["linear_dim"],)
+    for i in range(d["n_layers"]):
+        p = "encoder.fsmn.%d" % i
+        out[p + ".linear.linear.weight"] = (d["proj_dim"], d["linear_dim"])
+        out[p + ".fsmn_block.conv_left.weight"] = (d["proj_dim"], 1, d["lorder"], 1)
+        out[p + ".affine.linear.weight"] = (d["linear_dim"], d["proj_dim"])
+        out[p + ".affine.linear.bias"] = (d["linear_dim"],)
+    out["encoder.out_linear1.linear.weight"] = (d["output_affine_dim"], d["linear_dim"])
+    out["encoder.out_linear1.linear.bias"] = (d["output_affine_dim"],)
+    out["encoder.out_linear2.linear.weight"] = (d["output_dim"], d["output_affine_dim"])
+    out["encoder.out_linear2.linear.bias"] = (d["output_dim"],)
+    return out
+
+
+def make_vad_weights(seed=0):
+    rng = np.random.default_rng(seed)
+    W = {}
+    shapes = vad_param_shapes()
+    for name, shp in shapes.items():
+        fan_in = int(np.prod(shp[1:])) if name.endswith(".weight") else int(np.prod(shapes[name[:-5] + ".weight"][1:]))
+        gain = 2.45 if name.endswith(".weight") and "conv_left" not in name else 1.0   # He-like: keeps activations O(1) through the ReLUs
+        W[name] = (rng.uniform(-1, 1, shp) * gain).astype(np.float32) / np.float32(math.sqrt(fan_in))
+    # a posterior a VAD could plausibly produce: moderate logits, and pdf 0 (silence) competing with the other 247 classes so
+    # that the silence probability really moves between frames
+    W["encoder.out_linear2.linear.weight"] *= np.float32(0.05)
+    W["encoder.out_linear2.linear.weight"][0] *= np.float32(6.0)
+    W["encoder.out_linear2.linear.bias"][0] += np.float32(5.5)
+    return W
+
+
+def write_synthetic_vad_dir(path, seed=0):
+    """<vad-dir>/{am.mvn (400-dim), vad.b200pf}: the reference's VAD directory layout (com-define.h:56-58) with the flat weight
+    file in place of model.onnx."""
+    import os
+    from . import modelfile
+    W = make_vad_weights(seed)
+    means, vars_ = make_cmvn(400)
+    os.makedirs(path, exist_ok=True)
+    modelfile.write_weights(os.path.join(path, "vad.b200pf"), dict(VAD_DIMS), W)
+    modelfile.write_am_mvn(os.path.join(path, "am.mvn"), means, vars_)
+    return W, means, vars_
+
+
 def make_cmvn(n=560):
     j = np.arange(n, dtype=np.float64)
     means = (-(8.0 + 2.0 * np.sin(j))).astype(np.float32)

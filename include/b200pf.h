@@ -160,6 +160,21 @@ double b200pf_batch_flops(const b200pf_batch* b);
  * "feats" [T,560], "enc" [T,512], "alphas" [T+1], "fires" [T+1], "embeds" [L,512], "logits" [L,vocab]. */
 int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int64_t cap, int64_t shape[2]);
 
+/* ---- FSMN-VAD scores ------------------------------------------------------------------------
+ * Replaces the onnxruntime session of FsmnVad::Forward (onnxruntime/src/fsmn-vad.cpp:72-135) and its front end (FbankKaldi /
+ * LfrCmvn, :137-224) for whole recordings; the E2E state machine that turns scores into segments (e2e-vad.h) stays on the
+ * host and reads scores[t][0] (sil_pdf_ids = {0}).  <vad_dir> holds am.mvn (400-dim) and vad.b200pf (upstream FunASR
+ * fsmn_vad encoder parameter names).  max_frames: 10 ms frames one call may hold (0 -> 400000). */
+typedef struct b200pf_vad b200pf_vad;
+int b200pf_vad_create(const char* vad_dir, int device, int max_frames, b200pf_vad** out);
+void b200pf_vad_destroy(b200pf_vad* v);
+/* pcm: recordings back to back, recording i = pcm[offsets[i] .. offsets[i+1]).  frame_off [n_rec + 1] receives the first
+ * frame of every recording (T_i = 1 + (n_i - 400) / 160 frames, 0 when shorter than one window); sil_prob [cap_frames]
+ * the probability of pdf 0 per frame; all_probs (optional) [cap_frames, 248]; feats (optional) [cap_frames, 400] the
+ * LFR + CMVN features (debug / parity). */
+int b200pf_vad_scores_s16(b200pf_vad* v, const int16_t* pcm, const int64_t* offsets, int n_rec, float* sil_prob, int64_t cap_frames,
+                          int32_t* frame_off, float* all_probs, float* feats);
+
 /* ---- single-operator entry points (fp32 host buffers in/out; used by the parity tests) -------------- */
 /* C = A[M,K] * W[N,K]^T (+bias) (+relu: 1 after bias, 2 after all adds) (+add[M,N] rounded to bf16)
  * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: 1 rounds the result to bf16; 0 = fp32 with the

@@ -1,0 +1,109 @@
+"""FSMN-VAD scores: oracle consistency on the CPU, GPU parity through the C ABI (-m gpu).
+
+Tolerances: LFR + CMVN features <= 1e-4 (measured 1e-6; fbank in fp32 + a double FFT, as for the acoustic model); silence
+probability and the 248-way softmax <= 5e-2 absolute, log-probabilities <= 0.3, against the fp32 oracle (measured 4e-2 /
+0.22: bf16 GEMM operands through ten layers of a synthetic model whose silence logit was made deliberately large and
+sensitive; the consumer compares 1 - p_sil against speech_noise_thres = 0.6-0.9, e2e-vad.h:602-640)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import frontend as F
+from oracle import vad_ref as V
+
+
+def test_vad_oracle_chunked_equals_whole(synth):
+    """The reference feeds 1 s chunks and carries four [128 x 19] caches (fsmn-vad.cpp:96-133); with a left-context-only
+    memory block that equals one pass over the whole recording, which is what the GPU path computes."""
+    import torch
+    W = synth.make_vad_weights(0)
+    x = np.random.default_rng(0).standard_normal((237, 400)).astype(np.float32)
+    full, _ = V.forward(x, W)
+    caches, parts = None, []
+    for a in range(0, 237, 100):
+        s, caches = V.forward(x[a:a + 100], W, caches)
+        assert all(c.shape == (128, 19) for c in caches)
+        parts.append(s)
+    assert torch.equal(torch.cat(parts), full)
+    assert torch.allclose(full.sum(-1), torch.ones(237), atol=1e-5)
+    assert float(full.std()) > 1e-3          # the synthetic weights give a non-trivial posterior
+
+
+def test_vad_lfr_matches_literal_transcription():
+    """FsmnVad::LfrCmvn (fsmn-vad.cpp:182-224) transcribed with its vector inserts vs the oracle's index formula."""
+    rng = np.random.default_rng(1)
+    for T in (1, 2, 3, 5, 17):
+        fb = rng.standard_normal((T, 80)).astype(np.float32)
+        means, vars_ = rng.standard_normal(400).astype(np.float32), rng.uniform(0.5, 2, 400).astype(np.float32)
+        feats = [list(f) for f in fb]
+        m, n = 5, 1
+        T_lfr = int(np.ceil(T / n))
+        for _ in range((m - 1) // 2):
+            feats.insert(0, list(feats[0]))
+        Tp = T + (m - 1) // 2
+        out = []
+        for i in range(T_lfr):
+            p = []
+            if m <= Tp - i * n:
+                for j in range(m):
+                    p.extend(feats[i * n + j])
+            else:
+                for j in range(len(feats) - i * n):
+                    p.extend(feats[i * n + j])
+                for _ in range(m - (Tp - i * n)):
+                    p.extend(feats[-1])
+            out.append(p)
+        lit = ((np.asarray(out, np.float32) + means[None]) * vars_[None]).astype(np.float32)
+        assert np.array_equal(V.lfr_cmvn(fb, means, vars_), lit)
+
+
+@pytest.mark.gpu
+def test_vad_scores_against_oracle(capi, synth, gpu, tmp_path):
+    d = str(tmp_path)
+    W, means, vars_ = synth.write_synthetic_vad_dir(d, seed=0)
+    eng = capi.VadEngine(d, max_frames=20000)
+    lens = [16000, 400, 399, 52800, 160000, 0, 1359]
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = np.concatenate([synth.make_audio(n, 40 + i) if n else np.zeros(0, np.int16) for i, n in enumerate(lens)])
+    p0, fo, probs, feats = eng.scores(pcm, offs, all_probs=True, feats=True)
+    assert list(np.diff(fo)) == [F.num_fbank_frames(n) for n in lens]
+    for i, n in enumerate(lens):
+        T = F.num_fbank_frames(n)
+        if T == 0:
+            continue
+        x = pcm[offs[i]:offs[i + 1]].astype(np.float32) / np.float32(32768)
+        ref_feats = V.lfr_cmvn(F.fbank(x), means, vars_)
+        assert np.abs(feats[fo[i]:fo[i + 1]] - ref_feats).max() <= 1e-4
+        ref, _ = V.forward(ref_feats, W)
+        ref = ref.numpy()
+        assert np.abs(probs[fo[i]:fo[i + 1]] - ref).max() <= 5e-2
+        assert np.abs(p0[fo[i]:fo[i + 1]] - ref[:, 0]).max() <= 5e-2
+        assert np.abs(np.log(probs[fo[i]:fo[i + 1]] + 1e-30) - np.log(ref + 1e-30)).max() <= 0.3
+        assert np.allclose(probs[fo[i]:fo[i + 1]].sum(1), 1.0, atol=1e-4)
+        assert np.array_equal(p0[fo[i]:fo[i + 1]], probs[fo[i]:fo[i + 1], 0])
+    # batch invariance: a recording's scores do not depend on what it is processed with
+    one, fo1, _, _ = eng.scores(pcm[offs[3]:offs[4]], np.array([0, lens[3]], np.int64))
+    assert np.array_equal(one, p0[fo[3]:fo[4]])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_vad_one_hour_stream(capi, synth, gpu, tmp_path):
+    """Throughput sanity at the size the survey names (a 1 h stream): scores for 360 k frames in one call."""
+    import time
+    d = str(tmp_path)
+    synth.write_synthetic_vad_dir(d, seed=0)
+    eng = capi.VadEngine(d, max_frames=400000)
+    blk = synth.make_audio(16000 * 60, 9)
+    pcm = np.tile(blk, 60)
+    offs = np.array([0, len(pcm)], np.int64)
+    eng.scores(pcm[:16000 * 60], np.array([0, 16000 * 60], np.int64))
+    t0 = time.perf_counter()
+    p0, fo, _, _ = eng.scores(pcm, offs)
+    dt = time.perf_counter() - t0
+    assert len(p0) == 1 + (len(pcm) - 400) // 160 and np.isfinite(p0).all()
+    assert np.array_equal(p0[100:5000], p0[6000 + 100:6000 + 5000])       # the tiled minute repeats once the 19-frame history is the same
+    print("VAD 1 h stream: %.1f ms -> %.0f x real time" % (dt * 1e3, 3600.0 / dt))
+    assert 3600.0 / dt > 1000
+    eng.close()
