@@ -6,6 +6,7 @@
 #include <fstream>
 #include <numeric>
 
+#include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
 
@@ -19,6 +20,9 @@ struct RecogResult {  // FUNASR_RECOG_RESULT, onnxruntime/src/commonfunc.h:8-15
 struct OfflineHandle {  // stands where funasr::OfflineStream does; owns only the acoustic model
   std::unique_ptr<funasr_b200::ParaformerB200> asr;        // single GPU
   std::unique_ptr<funasr_b200::MultiGpuParaformer> pool;   // "devices" = "0,1,...": one engine per GPU, independent queues
+  // "micro-batch-us" = deadline: concurrent FunOfflineInfer* calls (the servers' decoder-thread-num threads, one request each)
+  // are merged into batched forwards instead of queueing up as latency-bound small ones
+  std::unique_ptr<funasr_b200::MicroBatcher> batcher;
   funasr_b200::Model* model() { return pool ? (funasr_b200::Model*)pool.get() : (funasr_b200::Model*)asr.get(); }
   funasr_b200::ParaformerB200* first() { return pool ? pool->model(0) : asr.get(); }
 };
@@ -91,8 +95,23 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
       ptrs[k] = (const int16_t*)pcm + seg_b[s];
       lens[k] = seg_e[s] - seg_b[s];
     }
-    std::vector<std::string> out = h->pool ? h->pool->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb)
-                                           : h->asr->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb);
+    std::vector<std::string> out;
+    if (h->batcher) {
+      // through the micro-batcher: it speaks the reference's float form (float = int16 / 32768, Audio::LoadPcmwav)
+      std::vector<std::vector<float>> fl(batch.size());
+      std::vector<float*> fp(batch.size());
+      std::vector<int> li(batch.size());
+      for (size_t k = 0; k < batch.size(); ++k) {
+        fl[k].resize((size_t)lens[k]);
+        for (int64_t i = 0; i < lens[k]; ++i) fl[k][i] = (float)ptrs[k][i] / 32768.0f;
+        fp[k] = fl[k].data();
+        li[k] = (int)lens[k];
+      }
+      out = h->batcher->Forward(fp.data(), li.data(), true, hw_emb, nullptr, (int)batch.size());
+    } else {
+      out = h->pool ? h->pool->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb)
+                    : h->asr->ForwardSegments16(ptrs.data(), lens.data(), (int)batch.size(), hw_emb);
+    }
     for (size_t k = 0; k < batch.size(); ++k) {
       const int s = index[batch[k]];
       msgs[s] = out[k];
@@ -129,6 +148,13 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
       return nullptr;
     }
     h->pool->SetBatchSize(batch_size);
+    if (ToInt(model_path, "micro-batch-us", 0) > 0) {
+      funasr_b200::MicroBatcherOptions o;
+      o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
+      funasr_b200::MultiGpuParaformer* pool = h->pool.get();
+      h->batcher.reset(new funasr_b200::MicroBatcher(
+          [pool](float** din, int* len, int n, const std::vector<std::vector<float>>& hw) { return pool->Forward(din, len, true, hw, nullptr, n); }, o));
+    }
     return h.release();
   }
   h->asr.reset(new funasr_b200::ParaformerB200(devices.size() == 1 ? devices[0] : ToInt(model_path, "device", 0),
@@ -138,6 +164,11 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
     return nullptr;
   }
   h->asr->SetBatchSize(batch_size);
+  if (ToInt(model_path, "micro-batch-us", 0) > 0) {
+    funasr_b200::MicroBatcherOptions o;
+    o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
+    h->batcher.reset(new funasr_b200::MicroBatcher(h->asr.get(), o));
+  }
   return h.release();
 }
 

@@ -36,7 +36,8 @@ void FunASRUninit(FUNASR_HANDLE handle);
 // model_path keys (onnxruntime/include/com-define.h:15-38): "model-dir" is required; "quantize", "vad-dir",
 // "punc-dir", "itn-dir", "lm-dir" are accepted and ignored here.  Extra keys: "device" (CUDA ordinal), "devices"
 // ("0,1,...": one engine per listed GPU behind this handle, segments sharded over independent per-GPU queues),
-// "max-rows", "max-segments".
+// "max-rows", "max-segments", "micro-batch-us" (> 0: concurrent FunOfflineInfer* calls on this handle are merged into batched
+// forwards by a MicroBatcher with that deadline in microseconds).
 FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int thread_num, bool use_gpu = false, int batch_size = 1);
 void FunOfflineReset(FUNASR_HANDLE handle, FUNASR_DEC_HANDLE dec_handle = nullptr);
 FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE mode, QM_CALLBACK fn_callback,

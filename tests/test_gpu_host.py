@@ -98,3 +98,28 @@ def test_concurrent_forward_calls_on_one_handle(capi, synth, model):
     for i in range(len(segs)):
         assert out[i] == [ref[i]] * 6
     h.close()
+
+
+def test_reference_style_rtf_harness_runs(capi, synth, model, tmp_path):
+    """tools/funasr_b200_offline_rtf.cpp (the reference's funasr-onnx-offline-rtf pattern against the shim): P threads on one
+    handle, with and without the shim's micro-batcher; both must decode every wav."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "asr-2pass_b200", "lib", "funasr-b200-offline-rtf")
+    assert os.path.exists(exe), "built by asr-2pass_b200/csrc/Makefile"
+    scp = os.path.join(str(tmp_path), "wav.scp")
+    with open(scp, "w") as f:
+        for k, n in enumerate([16000, 52800, 33000, 24000, 80000, 20000]):
+            path = os.path.join(str(tmp_path), "u%d.wav" % k)
+            with wave.open(path, "wb") as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+                w.writeframes(synth.make_audio(n, 70 + k).astype("<i2").tobytes())
+            f.write("u%d %s\n" % (k, path))
+    for extra in ([], ["--micro-batch-us", "10000"]):
+        r = subprocess.run([exe, "--model-dir", model["dir"], "--wav-scp", scp, "--thread-num", "3", "--max-rows", "4096"] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert j["wavs"] == 6 and abs(j["audio_s"] - sum([16000, 52800, 33000, 24000, 80000, 20000]) / 16000.0) < 1e-2
+        assert "speedup" in r.stdout and "total_rtf" in r.stdout
