@@ -362,6 +362,8 @@ def main():
                                  else v["work"] / max(v["ms"], 1e-9) / 1e6),
                        unit=("TFLOP/s" if (k.startswith("gemm_") or k == "attention_tcgen05") else "GB/s"))
                for k, v in prof.items() if v["launches"]}
+    for k, v in kernels.items():   # fraction of the roofline that bounds the kernel class (measured peaks, MEASURED_PEAKS.json)
+        v["frac"] = v["achieved"] / (tflops_peak if v["unit"] == "TFLOP/s" else hbm)
     out = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
