@@ -119,7 +119,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
-                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer"]
+                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments"]
 
 
 def host_lib():
@@ -155,6 +155,7 @@ def host_lib():
     H.b200pf_host_partition.argtypes = [c_i32p, C.c_int, C.c_int, c_i32p]
     H.b200pf_host_segments_per_device.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]
     H.b200pf_host_funasr_infer.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_vad_segments.argtypes = [c_f32p, C.c_int, C.c_int, C.c_int, C.c_float, c_i32p, C.c_int]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -346,6 +347,14 @@ def funasr_infer(model_dir, wav_path=None, pcm16=None, device=0, max_rows=0):
     if n < 0:
         raise B200PFError("FunASRInit / FunASRInfer failed (%d)" % n)
     return buf.value.decode("utf-8")
+
+
+def host_vad_segments(sil_prob, max_end_sil=800, max_seg_ms=15000, thres=0.8):
+    """pf::host::SegmentVad -> int32 [n, 2] of [start_ms, end_ms]."""
+    p = np.ascontiguousarray(sil_prob, dtype=np.float32)
+    out = np.zeros((len(p) + 4, 2), np.int32)
+    n = host_lib().b200pf_host_vad_segments(_p(p), len(p), int(max_end_sil), int(max_seg_ms), C.c_float(thres), _p(out, c_i32p), len(out))
+    return out[:n].copy()
 
 
 def host_partition(lens, n_dev):

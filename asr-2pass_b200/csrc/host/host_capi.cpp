@@ -11,6 +11,7 @@
 #include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
+#include "vad_segmenter.h"
 
 namespace {
 int CopyOut(const std::string& s, char* out, int cap) {
@@ -174,6 +175,15 @@ int b200pf_host_funasr_infer(const char* model_dir, int device, int max_rows, co
   if (r) { n = CopyOut(FunASRGetResult(r, 0), out, cap); FunASRFreeResult(r); }
   FunASRUninit(h);
   return n;
+}
+
+// pf::host::SegmentVad (E2EVadModel's job, e2e-vad.h): silence probabilities -> [start_ms, end_ms] pairs; returns the count
+int b200pf_host_vad_segments(const float* sil_prob, int n_frames, int max_end_sil_ms, int max_seg_ms, float thres, int* out, int cap) {
+  pf::host::VadOptions o;
+  o.max_end_silence_ms = max_end_sil_ms; o.max_single_segment_ms = max_seg_ms; o.speech_noise_thres = thres;
+  const std::vector<std::pair<int, int>> segs = pf::host::SegmentVad(sil_prob, n_frames, o);
+  for (size_t i = 0; i < segs.size() && (int)i < cap; ++i) { out[2 * i] = segs[i].first; out[2 * i + 1] = segs[i].second; }
+  return (int)segs.size();
 }
 
 // ---- MicroBatcher ------------------------------------------------------------

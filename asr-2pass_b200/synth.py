@@ -118,7 +118,7 @@ VAD_DIMS = dict(input_dim=400, input_affine_dim=140, linear_dim=250, proj_dim=12
 
 
 def vad_param_shapes(d=VAD_DIMS):
-    """FSMN-VAD (FunASR fsmn_vad_streaming `FSMN`) parameter names and shapes; mirrors oracle/vad_ref.py."""
+    """FSMN-VAD (FunASR fsmn_vad_streaming `FSMN`) parameter names and shapes."""
     out = {}
     out["encoder.in_linear1.linear.weight"] = (d["input_affine_dim"], d["input_dim"])
     out["encoder.in_linear1.linear.bias"] = (d["input_affine_dim"],)

@@ -52,6 +52,10 @@ int b200pf_host_init_seg_dict(void* h_offline, const char* path);
  * (funasrruntime.h:60-78; the plain-model API that funasr-onnx-offline style callers use).  Returns the text length,
  * -1 when Init fails, -2 when inference returns nullptr. */
 int b200pf_host_funasr_infer(const char* model_dir, int device, int max_rows, const char* wav_path, const char* buf, int n_bytes, char* out, int cap);
+/* pf::host::SegmentVad: what funasr::E2EVadModel (onnxruntime/src/e2e-vad.h) does for a whole recording with its default
+ * options: sil_prob [n_frames] (probability of pdf 0 per 10 ms frame) -> [start_ms, end_ms] pairs in out[2*cap]; returns the
+ * number of segments.  max_end_sil_ms = vad_tail_sil, max_seg_ms = vad_max_len, thres = speech_noise_thres. */
+int b200pf_host_vad_segments(const float* sil_prob, int n_frames, int max_end_sil_ms, int max_seg_ms, float thres, int* out, int cap);
 /* MicroBatcher (asr-2pass_b200/csrc/host/micro_batcher.h): merges the batch-1 Forward calls that the 2-pass server makes
  * per closed VAD segment (funasrruntime.cpp:570-586) across connections into batched forwards.  `mock` variant: host-only
  * inner model for tests.  forward blocks until the segment is decoded; hw may be NULL (n_hw 0). */

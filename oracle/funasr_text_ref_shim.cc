@@ -3,6 +3,7 @@
 //     funasr::Vocab::Vector2StringV2 / Vector2String   onnxruntime/src/vocab.cpp:98-104,164-305
 //     funasr::TimestampOnnx, funasr::PostProcess        onnxruntime/src/util.cpp:720-963
 //     funasr::ParaformerOnline::GetPosEmb / CifSearch   onnxruntime/src/paraformer-online.cpp:240-345
+//     funasr::E2EVadModel (scores -> speech segments)   onnxruntime/src/e2e-vad.h
 // Nothing of the reference is copied: this file only calls it.  Two things are supplied here because the reference gets
 // them from CMake: a stand-in <gflags/gflags.h> (oracle/stubs; the vendored gflags header is generated) and the few glog
 // LogMessage symbols the sources reference through LOG(...) (the vendored glog library is not built).
@@ -109,6 +110,51 @@ void ref_pos_emb(void* h, float* feats, int T, int D) {
   for (int t = 0; t < T; ++t) std::copy(feats + (size_t)t * D, feats + (size_t)(t + 1) * D, f[t].begin());
   po->GetPosEmb(f, T, D);
   for (int t = 0; t < T; ++t) std::copy(f[t].begin(), f[t].end(), feats + (size_t)t * D);
+}
+
+// ---- E2EVadModel (onnxruntime/src/e2e-vad.h, header-only) -------------------------------------------------------------
+// sil_prob [T]: probability of pdf 0 per 10 ms frame (the only column the model reads, sil_pdf_ids = {0}).  The waveform only
+// feeds the decibel gate, which the default options switch off (decibel_thres = snr_thres = -100), so silence of the right
+// length is passed.  out receives [start_ms, end_ms] pairs; the return value is their count.
+static std::vector<std::vector<float>> ScoreRows(const float* sil_prob, int a, int b) {
+  std::vector<std::vector<float>> rows;
+  for (int t = a; t < b; ++t) rows.push_back(std::vector<float>{sil_prob[t], 1.0f - sil_prob[t]});
+  return rows;
+}
+
+// one call over the whole recording: is_final = true, online = false (FsmnVad::Infer's form, fsmn-vad.cpp:226-240)
+int ref_e2e_vad_offline(const float* sil_prob, int T, int max_end_sil, int max_seg_ms, float thres, int* out, int cap) {
+  funasr::E2EVadModel m;
+  std::vector<float> wave((size_t)T * 160 + 240, 0.f);
+  std::vector<std::vector<int>> segs = m(ScoreRows(sil_prob, 0, T), wave, true, false, max_end_sil, max_seg_ms, thres, 16000);
+  int n = 0;
+  for (auto& s : segs) { if (n < cap) { out[2 * n] = s[0]; out[2 * n + 1] = s[1]; } ++n; }
+  return n;
+}
+
+// the way Audio::CutSplit drives it (audio.cpp:1172-1226): chunk_frames scores per call through ONE model object with
+// online = true, is_final on the last chunk, then CutSplit's pairing of (start, -1) / (-1, end) into segments
+int ref_e2e_vad_online(const float* sil_prob, int T, int chunk_frames, int max_end_sil, int max_seg_ms, float thres, int* out, int cap) {
+  funasr::E2EVadModel m;
+  std::vector<std::vector<int>> vad_segments;
+  for (int a = 0; a < T; a += chunk_frames) {
+    const int b = std::min(T, a + chunk_frames);
+    std::vector<float> wave((size_t)(b - a) * 160 + 240, 0.f);
+    std::vector<std::vector<int>> cut = m(ScoreRows(sil_prob, a, b), wave, b == T, true, max_end_sil, max_seg_ms, thres, 16000);
+    vad_segments.insert(vad_segments.end(), cut.begin(), cut.end());
+  }
+  int n = 0, start_i = -1, end_i = -1;
+  for (auto& seg : vad_segments) {
+    if (seg.size() != 2) break;
+    if (seg[0] != -1) start_i = seg[0];
+    if (seg[1] != -1) end_i = seg[1];
+    if (start_i != -1 && end_i != -1) {
+      if (n < cap) { out[2 * n] = start_i; out[2 * n + 1] = end_i; }
+      ++n;
+      start_i = -1; end_i = -1;
+    }
+  }
+  return n;
 }
 
 }  // extern "C"

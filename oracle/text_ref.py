@@ -33,8 +33,23 @@ def lib():
         L.ref_online_destroy.argtypes = [C.c_void_p]
         L.ref_cif_search.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
         L.ref_pos_emb.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int]
+        L.ref_e2e_vad_offline.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.c_int]
+        L.ref_e2e_vad_online.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.c_int]
         _lib = L
     return _lib
+
+
+def e2e_vad(sil_prob, max_end_sil=800, max_seg_ms=15000, thres=0.8, chunk_frames=None):
+    """funasr::E2EVadModel (e2e-vad.h) on per-frame silence probabilities -> [[start_ms, end_ms], ...].  chunk_frames=None: one
+    offline call; otherwise the chunked online form exactly as Audio::CutSplit drives it (audio.cpp:1172-1226)."""
+    p = np.ascontiguousarray(sil_prob, dtype=np.float32)
+    out = np.zeros((len(p) + 4, 2), np.int32)
+    fp, ip = p.ctypes.data_as(C.POINTER(C.c_float)), out.ctypes.data_as(C.POINTER(C.c_int))
+    if chunk_frames is None:
+        n = lib().ref_e2e_vad_offline(fp, len(p), max_end_sil, max_seg_ms, C.c_float(thres), ip, len(out))
+    else:
+        n = lib().ref_e2e_vad_online(fp, len(p), int(chunk_frames), max_end_sil, max_seg_ms, C.c_float(thres), ip, len(out))
+    return out[:n].copy()
 
 
 def cif_search(hidden, alphas, threshold=1.0, tail=0.45):

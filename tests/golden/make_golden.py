@@ -166,6 +166,26 @@ def main():
     cg["pos_emb_64x560"] = T.pos_emb(64, 560)
     cg["pos_emb_row1000"] = T.pos_emb(1000, 560)[999]
     np.savez_compressed(os.path.join(HERE, "cif_posenc_golden.npz"), **cg)
+    # VAD segments from the reference's own compiled E2EVadModel (e2e-vad.h), driven in 1 s chunks as Audio::CutSplit does
+    vg = {}
+    vr = np.random.default_rng(31)
+    for k in range(24):
+        n = int(vr.integers(1, 6000)) if k % 4 else int(vr.integers(1, 140))
+        p = np.full(n, 0.95, np.float32)
+        t = int(vr.integers(0, 120))
+        while t < n:
+            d = int(vr.integers(5, 2500))
+            p[t:t + d] = vr.uniform(0.0, 0.08, min(d, n - t)).astype(np.float32)
+            t += d + int(vr.integers(5, 300))
+        flip = vr.random(n) < float(vr.choice([0.0, 0.02, 0.2]))
+        p[flip] = 1 - p[flip]
+        if k % 6 == 5:
+            p = vr.uniform(0, 1, n).astype(np.float32)
+        opts = (int(vr.choice([250, 500, 800])), int(vr.choice([3000, 15000, 20000, 60000])), float(vr.choice([0.6, 0.8, 0.9])))
+        vg["p_%d" % k] = p
+        vg["opts_%d" % k] = np.asarray(opts, np.float64)
+        vg["segs_%d" % k] = T.e2e_vad(p, opts[0], opts[1], opts[2], chunk_frames=100)
+    np.savez_compressed(os.path.join(HERE, "vad_segments_golden.npz"), **vg)
     with open(os.path.join(HERE, "text_golden.json"), "w", encoding="utf-8") as f:
         json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
                   f, ensure_ascii=False)

@@ -58,6 +58,47 @@ def test_vad_lfr_matches_literal_transcription():
         assert np.array_equal(V.lfr_cmvn(fb, means, vars_), lit)
 
 
+def test_vad_segmenter_matches_reference_compiled_golden(capi):
+    """pf::host::SegmentVad against segments produced by the reference's own compiled E2EVadModel (tests/golden/
+    vad_segments_golden.npz, make_golden.py), driven in 1 s chunks the way Audio::CutSplit drives it."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vad_segments_golden.npz"))
+    total = 0
+    for k in range(24):
+        mes, msl, th = g["opts_%d" % k]
+        got = capi.host_vad_segments(g["p_%d" % k], int(mes), int(msl), float(th))
+        assert np.array_equal(got, g["segs_%d" % k]), k
+        total += len(got)
+    assert total > 50
+
+
+def test_vad_segmenter_matches_live_reference_when_built(capi):
+    from oracle import text_ref as T
+    if not T.available():
+        pytest.skip("oracle/_ref/libfunasr_text_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    segs = 0
+    for k in range(400):
+        n = int(rng.integers(1, 5000)) if k % 3 else int(rng.integers(1, 130))
+        p = np.full(n, 0.95, np.float32)
+        t = int(rng.integers(0, 120))
+        while t < n:
+            d = int(rng.integers(5, 2500))
+            p[t:t + d] = rng.uniform(0.0, 0.08, min(d, n - t)).astype(np.float32)
+            t += d + int(rng.integers(5, 300))
+        flip = rng.random(n) < float(rng.choice([0.0, 0.02, 0.2, 0.4]))
+        p[flip] = 1 - p[flip]
+        if k % 7 == 0:
+            p = rng.uniform(0, 1, n).astype(np.float32)
+        if k % 17 == 0:
+            p = np.where(rng.random(n) < 0.5, np.float32(0.1), np.float32(0.1000001)).astype(np.float32)   # on the threshold
+        mes, msl, th = int(rng.choice([250, 500, 800])), int(rng.choice([3000, 15000, 60000])), float(rng.choice([0.6, 0.8, 0.9]))
+        ref = T.e2e_vad(p, mes, msl, th, chunk_frames=int(rng.choice([100, 98, 37])))
+        assert np.array_equal(capi.host_vad_segments(p, mes, msl, th), ref)
+        segs += len(ref)
+    assert segs > 1000
+
+
 @pytest.mark.gpu
 def test_vad_scores_against_oracle(capi, synth, gpu, tmp_path):
     d = str(tmp_path)
