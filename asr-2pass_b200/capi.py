@@ -119,7 +119,8 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
-                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments"]
+                "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
+                "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad"]
 
 
 def host_lib():
@@ -156,6 +157,10 @@ def host_lib():
     H.b200pf_host_segments_per_device.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]
     H.b200pf_host_funasr_infer.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_vad_segments.argtypes = [c_f32p, C.c_int, C.c_int, C.c_int, C.c_float, c_i32p, C.c_int]
+    H.b200pf_host_offline_init_vad.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+    H.b200pf_host_offline_init_vad.restype = C.c_void_p
+    H.b200pf_host_offline_vad_cut.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_i32p, C.c_int]
+    H.b200pf_host_offline_infer_buffer_vad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -206,9 +211,13 @@ def host_stitch(msgs, starts, lang):
 class OfflineHandle:
     """FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit through the host shim."""
 
-    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64, devices=None):
-        """devices=[0, 1, ...]: one engine per listed GPU behind this handle (funasr_b200::MultiGpuParaformer)."""
-        if devices is not None and len(devices) > 1:
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64, devices=None, vad_dir=None, vad_thres=0.0):
+        """devices=[0, 1, ...]: one engine per listed GPU behind this handle (funasr_b200::MultiGpuParaformer).
+        vad_dir: FSMN-VAD model directory; infer_buffer then cuts recordings the way the reference's UseVad() branch does."""
+        if vad_dir is not None:
+            self.h = host_lib().b200pf_host_offline_init_vad(model_dir.encode(), vad_dir.encode(), device, max_rows, max_segments, batch_size,
+                                                             C.c_float(vad_thres))
+        elif devices is not None and len(devices) > 1:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
             self.h = host_lib().b200pf_host_offline_init_devices(model_dir.encode(), _p(dv, c_i32p), len(dv), max_rows, max_segments, batch_size)
         else:
@@ -236,6 +245,25 @@ class OfflineHandle:
         if n < 0:
             raise B200PFError("FunOfflineInferBuffer returned nullptr")
         return buf.value.decode("utf-8"), sn.value
+
+    def vad_cut(self, pcm16, vad_tail_sil=800, vad_max_len=60000):
+        """[n, 2] int32 of [start_ms, end_ms): the cut FunOfflineInferBuffer applies when the handle has a VAD model."""
+        pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
+        out = np.zeros((len(pcm16) // 160 + 8, 2), np.int32)
+        n = host_lib().b200pf_host_offline_vad_cut(self.h, C.c_void_p(pcm16.ctypes.data), len(pcm16), vad_tail_sil, vad_max_len,
+                                                   _p(out, c_i32p), len(out))
+        if n < 0:
+            raise B200PFError("VAD cut failed: " + lib().b200pf_last_error().decode("utf-8", "replace"))
+        return out[:n].copy()
+
+    def infer_buffer_vad(self, pcm16, vad_tail_sil=800, vad_max_len=60000, cap=1 << 22):
+        pcm16 = np.ascontiguousarray(pcm16, dtype="<i2")
+        buf, st = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        n = host_lib().b200pf_host_offline_infer_buffer_vad(self.h, C.c_void_p(pcm16.ctypes.data), pcm16.nbytes, vad_tail_sil, vad_max_len,
+                                                            buf, len(buf), st, len(st))
+        if n < 0:
+            raise B200PFError("FunOfflineInferBuffer returned nullptr")
+        return buf.value.decode("utf-8"), st.value.decode("utf-8")
 
     def infer_segments(self, pcm16, seg_begin, seg_end, cap=1 << 22):
         pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)

@@ -4,11 +4,13 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <numeric>
 
 #include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
+#include "vad_segmenter.h"
 
 namespace {
 
@@ -23,6 +25,12 @@ struct OfflineHandle {  // stands where funasr::OfflineStream does; owns only th
   // "micro-batch-us" = deadline: concurrent FunOfflineInfer* calls (the servers' decoder-thread-num threads, one request each)
   // are merged into batched forwards instead of queueing up as latency-bound small ones
   std::unique_ptr<funasr_b200::MicroBatcher> batcher;
+  // "vad-dir": FSMN-VAD scores on the GPU + the E2E state machine on the host cut a recording into speech segments the way
+  // Audio::CutSplit does (audio.cpp:1172-1226); without it FunOfflineInferBuffer falls back to hard cuts at vad_max_len
+  b200pf_vad* vad = nullptr;
+  std::mutex vad_mu;   // one VAD workspace per handle
+  float vad_thres = 0.6f;
+  ~OfflineHandle() { if (vad) b200pf_vad_destroy(vad); }
   funasr_b200::Model* model() { return pool ? (funasr_b200::Model*)pool.get() : (funasr_b200::Model*)asr.get(); }
   funasr_b200::ParaformerB200* first() { return pool ? pool->model(0) : asr.get(); }
 };
@@ -66,6 +74,7 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
   res->snippet_time = (float)n_samples / asr->GetAsrSampleRate();
   if (res->snippet_time == 0) return res;
   const int n = (int)seg_b.size();
+  if (n == 0) return res;   // a recording the VAD found no speech in
   // ascending length order + permutation (Audio::CutSplit, audio.cpp:1228-1238); std::sort like the reference
   std::vector<int> index(n);
   std::iota(index.begin(), index.end(), 0);
@@ -124,6 +133,35 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
 
 }  // namespace
 
+namespace {
+// model_conf.speech_noise_thres of the VAD's config.yaml (fsmn-vad.cpp:38); a flat "key: value" scan is all this needs
+float ReadVadThreshold(const std::string& vad_dir, float dflt) {
+  std::ifstream f(vad_dir + "/config.yaml");
+  std::string line;
+  while (std::getline(f, line)) {
+    const size_t k = line.find("speech_noise_thres:");
+    if (k == std::string::npos || line.find('#') < k) continue;
+    const float v = (float)atof(line.c_str() + k + strlen("speech_noise_thres:"));
+    if (v > 0.f) return v;
+  }
+  return dflt;
+}
+
+bool InitVad(OfflineHandle* h, const std::map<std::string, std::string>& model_path, int device) {
+  auto vd = model_path.find("vad-dir");
+  if (vd == model_path.end() || vd->second.empty()) return true;
+  const int rc = b200pf_vad_create(vd->second.c_str(), device, ToInt(model_path, "vad-max-frames", 0), &h->vad);
+  if (rc != 0) {
+    fprintf(stderr, "FunOfflineInit: vad-dir %s: %s\n", vd->second.c_str(), b200pf_last_error());
+    return false;
+  }
+  h->vad_thres = ReadVadThreshold(vd->second, 0.6f);
+  auto th = model_path.find("vad-speech-noise-thres");
+  if (th != model_path.end() && atof(th->second.c_str()) > 0) h->vad_thres = (float)atof(th->second.c_str());
+  return true;
+}
+}  // namespace
+
 FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int thread_num, bool use_gpu, int batch_size) {
   (void)thread_num; (void)use_gpu;
   auto it = model_path.find("model-dir");
@@ -148,6 +186,7 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
       return nullptr;
     }
     h->pool->SetBatchSize(batch_size);
+    if (!InitVad(h.get(), model_path, devices[0])) return nullptr;
     if (ToInt(model_path, "micro-batch-us", 0) > 0) {
       funasr_b200::MicroBatcherOptions o;
       o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
@@ -164,6 +203,7 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
     return nullptr;
   }
   h->asr->SetBatchSize(batch_size);
+  if (!InitVad(h.get(), model_path, devices.size() == 1 ? devices[0] : ToInt(model_path, "device", 0))) return nullptr;
   if (ToInt(model_path, "micro-batch-us", 0) > 0) {
     funasr_b200::MicroBatcherOptions o;
     o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
@@ -188,9 +228,39 @@ FUNASR_RESULT FunOfflineInferSegmentsB200(FUNASR_HANDLE handle, const short* pcm
   return RunSegments(h, pcm, n_samples, b, e, hw_emb);
 }
 
+namespace {
+bool VadCut(OfflineHandle* h, const short* pcm, long long n, int vad_tail_sil, int vad_max_len, std::vector<std::pair<int, int>>* segs) {
+  const long long n_frames = n >= 400 ? 1 + (n - 400) / 160 : 0;
+  std::vector<float> sil((size_t)std::max<long long>(1, n_frames));
+  int64_t off[2] = {0, (int64_t)n};
+  int32_t frame_off[2] = {0, 0};
+  {
+    std::lock_guard<std::mutex> lk(h->vad_mu);
+    if (b200pf_vad_scores_s16(h->vad, (const int16_t*)pcm, off, 1, sil.data(), (int64_t)sil.size(), frame_off, nullptr, nullptr) != 0) {
+      fprintf(stderr, "FunOfflineInferBuffer: VAD: %s\n", b200pf_last_error());
+      return false;
+    }
+  }
+  pf::host::VadOptions vo;
+  vo.max_end_silence_ms = vad_tail_sil;
+  vo.max_single_segment_ms = vad_max_len;
+  vo.speech_noise_thres = h->vad_thres;
+  *segs = pf::host::SegmentVad(sil.data(), frame_off[1] - frame_off[0], vo);
+  return true;
+}
+}  // namespace
+
+// The VAD cut alone (the job of Audio::CutSplit, audio.cpp:1172-1226): [start_ms, end_ms) pairs for one recording.
+int FunOfflineVadSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, int vad_tail_sil, int vad_max_len,
+                              std::vector<std::pair<int, int>>* out) {
+  OfflineHandle* h = (OfflineHandle*)handle;
+  if (!h || !h->vad || !out) return -1;
+  return VadCut(h, pcm, n_samples, vad_tail_sil, vad_max_len, out) ? 0 : -2;
+}
+
 FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_len, FUNASR_MODE, QM_CALLBACK,
                                     const std::vector<std::vector<float>>& hw_emb, int sampling_rate, std::string wav_format, bool,
-                                    int, int vad_max_len, FUNASR_DEC_HANDLE, std::string, bool) {
+                                    int vad_tail_sil, int vad_max_len, FUNASR_DEC_HANDLE, std::string, bool) {
   OfflineHandle* h = (OfflineHandle*)handle;
   if (!h) return nullptr;  // funasrruntime.cpp:216-217
   if (!(wav_format == "pcm" || wav_format == "PCM")) {
@@ -205,9 +275,22 @@ FUNASR_RESULT FunOfflineInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, in
   std::vector<short> pcm((size_t)n);
   const unsigned char* bytes = (const unsigned char*)sz_buf;
   for (long long i = 0; i < n; ++i) pcm[i] = (short)((bytes[2 * i + 1] << 8) | bytes[2 * i]);
-  // no VAD here: one segment, hard-cut at vad_max_len so that a segment always fits the engine
-  const long long cut = std::max(1, vad_max_len) * 16LL;
   std::vector<long long> b, e;
+  if (h->vad) {
+    // UseVad() branch of the reference (funasrruntime.cpp:243-245): scores for the whole recording in one GPU pass, then the
+    // E2E state machine; segment bounds are milliseconds * (sample_rate / 1000) like Audio::CutSplit (audio.cpp:1214-1215)
+    if (n == 0) return RunSegments(h, pcm.data(), 0, b, e, hw_emb);
+    std::vector<std::pair<int, int>> segs;
+    if (!VadCut(h, pcm.data(), n, vad_tail_sil, vad_max_len, &segs)) return nullptr;
+    const long long per_ms = h->model()->GetAsrSampleRate() / 1000;
+    for (const auto& sg : segs) {
+      const long long sb = std::min<long long>(n, sg.first * per_ms), se = std::min<long long>(n, sg.second * per_ms);
+      if (se > sb) { b.push_back(sb); e.push_back(se); }
+    }
+    return RunSegments(h, pcm.data(), n, b, e, hw_emb);
+  }
+  // no VAD model: one segment, hard-cut at vad_max_len so that a segment always fits the engine
+  const long long cut = std::max(1, vad_max_len) * 16LL;
   for (long long s = 0; s < n; s += cut) { b.push_back(s); e.push_back(std::min(n, s + cut)); }
   if (n == 0) { b.push_back(0); e.push_back(0); }
   return RunSegments(h, pcm.data(), n, b, e, hw_emb);

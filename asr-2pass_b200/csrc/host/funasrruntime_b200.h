@@ -72,6 +72,11 @@ funasr_b200::Model* FunOfflineModel(FUNASR_HANDLE handle);
 funasr_b200::ParaformerB200* FunOfflineModelB200(FUNASR_HANDLE handle);
 funasr_b200::MultiGpuParaformer* FunOfflinePoolB200(FUNASR_HANDLE handle);
 
+// With "vad-dir" in FunOfflineInit's map, FunOfflineInferBuffer cuts the recording with FSMN-VAD (scores on the GPU, the E2E state
+// machine on the host) the way the reference's UseVad() branch does; this returns that cut alone: [start_ms, end_ms) pairs.
+int FunOfflineVadSegmentsB200(FUNASR_HANDLE handle, const short* pcm, long long n_samples, int vad_tail_sil, int vad_max_len,
+                              std::vector<std::pair<int, int>>* out);
+
 // Extension for callers that already hold VAD cut points (e.g. the reference's Audio::CutSplit output):
 // segment i = pcm[seg_begin[i] .. seg_end[i]) in samples.  Segments are length-sorted, batched with the
 // reference's FetchDynamic rules, decoded, un-permuted and stitched exactly like FunOfflineInferBuffer.

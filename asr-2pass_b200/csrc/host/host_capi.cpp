@@ -74,6 +74,34 @@ void* b200pf_host_offline_init_devices(const char* model_dir, const int* devices
   mp["max-segments"] = std::to_string(max_segments);
   return FunOfflineInit(mp, 1, true, batch_size);
 }
+void* b200pf_host_offline_init_vad(const char* model_dir, const char* vad_dir, int device, int max_rows, int max_segments, int batch_size,
+                                   float speech_noise_thres) {
+  std::map<std::string, std::string> mp;
+  mp["model-dir"] = model_dir;
+  mp["vad-dir"] = vad_dir;
+  mp["device"] = std::to_string(device);
+  mp["max-rows"] = std::to_string(max_rows);
+  mp["max-segments"] = std::to_string(max_segments);
+  if (speech_noise_thres > 0.f) mp["vad-speech-noise-thres"] = std::to_string(speech_noise_thres);
+  return FunOfflineInit(mp, 1, true, batch_size);
+}
+int b200pf_host_offline_vad_cut(void* h, const int16_t* pcm, int64_t n_samples, int vad_tail_sil, int vad_max_len, int* seg_ms, int cap) {
+  std::vector<std::pair<int, int>> segs;
+  if (FunOfflineVadSegmentsB200(h, pcm, n_samples, vad_tail_sil, vad_max_len, &segs) != 0) return -1;
+  if ((int)segs.size() > cap) return -2;
+  for (size_t i = 0; i < segs.size(); ++i) { seg_ms[2 * i] = segs[i].first; seg_ms[2 * i + 1] = segs[i].second; }
+  return (int)segs.size();
+}
+int b200pf_host_offline_infer_buffer_vad(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
+                                         char* stamp, int stamp_cap) {
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  FUNASR_RESULT r = FunOfflineInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr, hw, 16000, "pcm", true, vad_tail_sil, vad_max_len);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  CopyOut(FunASRGetStamp(r), stamp, stamp_cap);
+  FunASRFreeResult(r);
+  return n;
+}
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign) {
   std::vector<int> a;
   funasr_b200::PartitionSegments(len, n, n_dev, &a);

@@ -26,6 +26,16 @@ void* b200pf_host_offline_init(const char* model_dir, int device, int max_rows, 
 /* Same over several GPUs of the box: one engine per device behind one handle, every call's segments are sharded over
  * independent per-GPU queues (funasr_b200::MultiGpuParaformer; no collective). */
 void* b200pf_host_offline_init_devices(const char* model_dir, const int* devices, int n_dev, int max_rows, int max_segments, int batch_size);
+/* FunOfflineInit with a VAD model ("vad-dir"; funasrruntime.cpp:35-39 / OfflineStream's vad_handle): FunOfflineInferBuffer then cuts
+ * every recording with FSMN-VAD scores (GPU) + the E2E state machine (host) as the reference's UseVad() branch does
+ * (funasrruntime.cpp:243-245, Audio::CutSplit audio.cpp:1172-1226).  speech_noise_thres <= 0: read <vad_dir>/config.yaml, else 0.6. */
+void* b200pf_host_offline_init_vad(const char* model_dir, const char* vad_dir, int device, int max_rows, int max_segments, int batch_size,
+                                   float speech_noise_thres);
+/* The cut alone: seg_ms receives [start_ms, end_ms) pairs (cap pairs); returns the number of segments, < 0 on error. */
+int b200pf_host_offline_vad_cut(void* h, const int16_t* pcm, int64_t n_samples, int vad_tail_sil, int vad_max_len, int* seg_ms, int cap);
+/* FunOfflineInferBuffer with the reference's vad_tail_sil / vad_max_len arguments (funasrruntime.h:101-105); text and stamp out. */
+int b200pf_host_offline_infer_buffer_vad(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
+                                         char* stamp, int stamp_cap);
 /* The pool's longest-processing-time-first assignment of segments (sample counts) to n_dev queues; host arithmetic only. */
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign);
 /* Segments decoded per device so far; returns the number of devices (0 for a single-GPU handle). */

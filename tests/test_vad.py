@@ -148,3 +148,42 @@ def test_vad_one_hour_stream(capi, synth, gpu, tmp_path):
     print("VAD 1 h stream: %.1f ms -> %.0f x real time" % (dt * 1e3, 3600.0 / dt))
     assert 3600.0 / dt > 1000
     eng.close()
+
+
+@pytest.mark.gpu
+def test_offline_shim_vad_cut_path(capi, synth, gpu, tmp_path):
+    """FunOfflineInit with "vad-dir": FunOfflineInferBuffer cuts the recording with GPU scores + the E2E state machine
+    (the reference's UseVad() branch, funasrruntime.cpp:243-245 -> Audio::CutSplit) and decodes exactly those segments."""
+    vd, md = str(tmp_path / "vad"), str(tmp_path / "am")
+    import os
+    os.makedirs(vd), os.makedirs(md)
+    synth.write_synthetic_vad_dir(vd, seed=0)
+    synth.write_synthetic_model_dir(md, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    # bursts of synthetic speech separated by digital silence, 34 s
+    parts = []
+    for i, (n_speech, n_sil) in enumerate([(48000, 24000), (80000, 40000), (16000, 16000), (160000, 32000), (64000, 44000)]):
+        parts += [synth.make_audio(n_speech, 70 + i), np.zeros(n_sil, np.int16)]
+    pcm = np.concatenate(parts)
+    eng = capi.VadEngine(vd, max_frames=20000)
+    p0, fo, _, _ = eng.scores(pcm, np.array([0, len(pcm)], np.int64))
+    eng.close()
+    # synthetic weights: put the speech/noise threshold where the scores actually are (speech <=> p_sil <= (1 - thres) / 2)
+    thres = float(np.clip(1.0 - 2.0 * np.median(p0), 0.05, 0.95))
+    h = capi.OfflineHandle(md, max_rows=8192, max_segments=256, batch_size=8, vad_dir=vd, vad_thres=thres)
+    for tail, mx in ((800, 15000), (250, 3000)):
+        cut = h.vad_cut(pcm, tail, mx)
+        assert np.array_equal(cut, capi.host_vad_segments(p0, tail, mx, thres))
+        assert len(cut) >= 1 and (cut[:, 1] > cut[:, 0]).all() and (np.diff(cut[:, 0]) > 0).all()
+        assert (cut[:, 1] - cut[:, 0]).max() <= mx + 1000
+        text, stamp = h.infer_buffer_vad(pcm, tail, mx)
+        b = np.minimum(cut[:, 0].astype(np.int64) * 16, len(pcm))
+        e = np.minimum(cut[:, 1].astype(np.int64) * 16, len(pcm))
+        keep = e > b
+        expect = h.infer_segments(pcm, b[keep], e[keep])
+        expect = expect[0] if isinstance(expect, tuple) else expect
+        assert text.replace(" ", "") == expect.replace(" ", "")
+    # all-silence recording: no segments, empty text, still a result
+    sil = np.zeros(48000, np.int16)
+    if len(h.vad_cut(sil, 800, 15000)) == 0:
+        assert h.infer_buffer_vad(sil, 800, 15000)[0] == ""
+    h.close()
