@@ -120,7 +120,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
                 "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
-                "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad"]
+                "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords"]
 
 
 def host_lib():
@@ -161,6 +161,7 @@ def host_lib():
     H.b200pf_host_offline_init_vad.restype = C.c_void_p
     H.b200pf_host_offline_vad_cut.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_i32p, C.c_int]
     H.b200pf_host_offline_infer_buffer_vad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_pack_hotwords.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, c_i32p, c_i32p, C.c_int]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -383,6 +384,18 @@ def host_vad_segments(sil_prob, max_end_sil=800, max_seg_ms=15000, thres=0.8):
     out = np.zeros((len(p) + 4, 2), np.int32)
     n = host_lib().b200pf_host_vad_segments(_p(p), len(p), int(max_end_sil), int(max_seg_ms), C.c_float(thres), _p(out, c_i32p), len(out))
     return out[:n].copy()
+
+
+def host_pack_hotwords(tokens, hotwords, seg_dict_path=None, cap=4200):
+    """funasr_b200::PackHotwords -> (ids int32 [n, 10], lengths int32 [n]); blank row last."""
+    arr = (C.c_char_p * len(tokens))(*[t.encode("utf-8") for t in tokens])
+    ids = np.zeros((cap, 10), np.int32)
+    lens = np.zeros(cap, np.int32)
+    n = host_lib().b200pf_host_pack_hotwords(arr, len(tokens), seg_dict_path.encode() if seg_dict_path else None,
+                                             hotwords.encode("utf-8"), _p(ids, c_i32p), _p(lens, c_i32p), cap)
+    if n < 0:
+        raise B200PFError("too many hotwords")
+    return ids[:n].copy(), lens[:n].copy()
 
 
 def host_partition(lens, n_dev):

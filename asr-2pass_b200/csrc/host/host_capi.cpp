@@ -155,6 +155,19 @@ int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* o
   }
   return (int)emb.size();
 }
+int b200pf_host_pack_hotwords(const char* const* tokens, int n_tokens, const char* seg_dict_path, const char* hotwords, int32_t* ids,
+                              int32_t* lengths, int cap_rows) {
+  std::unordered_map<std::string, int> token_id;
+  for (int i = 0; i < n_tokens; ++i) token_id.emplace(tokens[i], i);   // PhoneSet: first id wins (phone-set.cpp:51-56)
+  std::unordered_map<std::string, std::vector<std::string>> seg_dict;
+  if (seg_dict_path && seg_dict_path[0]) funasr_b200::LoadSegDict(seg_dict_path, &seg_dict);
+  std::vector<int32_t> m, l;
+  funasr_b200::PackHotwords(hotwords ? hotwords : "", token_id, seg_dict, &m, &l);
+  if ((int)l.size() > cap_rows) return -1;
+  memcpy(ids, m.data(), m.size() * sizeof(int32_t));
+  memcpy(lengths, l.data(), l.size() * sizeof(int32_t));
+  return (int)l.size();
+}
 int b200pf_host_init_seg_dict(void* h_offline, const char* path) {
   funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);
   if (!m || !path) return -1;

@@ -97,25 +97,18 @@ void ParaformerB200::InitHwCompiler(const std::string& hw_model, int thread_num)
   if (!use_hotword_) fprintf(stderr, "InitHwCompiler: model.b200pf carries no hotword compiler (contextual = 0); hotwords are ignored\n");
 }
 
-void ParaformerB200::InitSegDict(const std::string& seg_dict_model) {
-  FILE* f = fopen(seg_dict_model.c_str(), "rb");
-  if (!f) { fprintf(stderr, "%s open failed !!\n", seg_dict_model.c_str()); return; }
-  std::string text;
-  char buf[65536];
-  size_t n;
-  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
-  fclose(f);
-  for (const std::string& line : SplitChar(text, '\n')) {
-    const std::vector<std::string> item = SplitChar(line, '\t');
-    if (item.size() > 1) seg_dict_[item[0]] = SplitChar(item[1], ' ');
-  }
-}
+void ParaformerB200::InitSegDict(const std::string& seg_dict_model) { LoadSegDict(seg_dict_model, &seg_dict_); }
 
-std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::string& hotwords) {
-  const int dim = d_model_;
-  if (!use_hotword_) return std::vector<std::vector<float>>(1, std::vector<float>(dim, 0.0f));  // paraformer.cpp:595-599
+// Hotword string -> id matrix [n, 10] + lengths, the host half of Paraformer::CompileHotwordEmbedding (paraformer.cpp:600-648):
+// split on ' '; an all-CJK word becomes its characters, anything else goes through the seg_dict; words with no pieces or with a
+// piece missing from the token list (PhoneSet::String2Id == -1 among the first 10) are dropped; the blank row {1, 0, ...} of
+// length 1 is appended last.
+void PackHotwords(const std::string& hotwords, const std::unordered_map<std::string, int>& token_id,
+                  const std::unordered_map<std::string, std::vector<std::string>>& seg_dict, std::vector<int32_t>* matrix,
+                  std::vector<int32_t>* lengths) {
   const int max_len = B200PF_HOTWORD_LEN;
-  std::vector<int32_t> matrix, lengths;
+  matrix->clear();
+  lengths->clear();
   if (!hotwords.empty()) {
     for (const std::string& hotword : SplitChar(hotwords, ' ')) {
       std::vector<std::string> chars;
@@ -127,8 +120,8 @@ std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::str
           if ((cp.first >= 0x4e00 && cp.first <= 0x9fff) || (cp.first >= 0x3400 && cp.first <= 0x4dff)) chars.push_back(cp.second);
       } else {
         for (const std::string& word : SplitChar(hotword, ' ')) {
-          auto it = seg_dict_.find(word);  // SegDict::GetTokensByWord: OOV -> no tokens
-          if (it != seg_dict_.end()) chars.insert(chars.end(), it->second.begin(), it->second.end());
+          auto it = seg_dict.find(word);  // SegDict::GetTokensByWord: OOV -> no tokens
+          if (it != seg_dict.end()) chars.insert(chars.end(), it->second.begin(), it->second.end());
         }
       }
       if (chars.empty()) continue;
@@ -136,18 +129,40 @@ std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::str
       const int len = std::min(max_len, (int)chars.size());
       bool oov = false;
       for (int i = 0; i < len && !oov; ++i) {
-        auto it = token_id_.find(chars[i]);
-        if (it == token_id_.end()) oov = true; else row[i] = it->second;
+        auto it = token_id.find(chars[i]);
+        if (it == token_id.end()) oov = true; else row[i] = it->second;
       }
       if (oov) continue;
-      lengths.push_back(len);
-      matrix.insert(matrix.end(), row.begin(), row.end());
+      lengths->push_back(len);
+      matrix->insert(matrix->end(), row.begin(), row.end());
     }
   }
   std::vector<int32_t> blank(max_len, 0);
   blank[0] = 1;
-  matrix.insert(matrix.end(), blank.begin(), blank.end());
-  lengths.push_back(1);
+  matrix->insert(matrix->end(), blank.begin(), blank.end());
+  lengths->push_back(1);
+}
+
+void LoadSegDict(const std::string& path, std::unordered_map<std::string, std::vector<std::string>>* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "%s open failed !!\n", path.c_str()); return; }
+  std::string text;
+  char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+  fclose(f);
+  for (const std::string& line : SplitChar(text, '\n')) {
+    const std::vector<std::string> item = SplitChar(line, '\t');
+    if (item.size() > 1) (*out)[item[0]] = SplitChar(item[1], ' ');
+  }
+}
+
+std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::string& hotwords) {
+  const int dim = d_model_;
+  if (!use_hotword_) return std::vector<std::vector<float>>(1, std::vector<float>(dim, 0.0f));  // paraformer.cpp:595-599
+  const int max_len = B200PF_HOTWORD_LEN;
+  std::vector<int32_t> matrix, lengths;
+  PackHotwords(hotwords, token_id_, seg_dict_, &matrix, &lengths);
   const int n = (int)lengths.size();
   std::vector<float> flat((size_t)n * dim);
   std::vector<std::vector<float>> result;

@@ -42,6 +42,14 @@ class Model {  // subset of funasr::Model used on the offline Paraformer path (m
   virtual int GetBatchSize() = 0;
 };
 
+// Host half of Paraformer::CompileHotwordEmbedding (paraformer.cpp:600-648): hotword string -> id matrix [n, B200PF_HOTWORD_LEN]
+// and lengths, blank row last.  Pure host code (pinned against the reference's compiled function, tests/test_host_cpu.py).
+void PackHotwords(const std::string& hotwords, const std::unordered_map<std::string, int>& token_id,
+                  const std::unordered_map<std::string, std::vector<std::string>>& seg_dict, std::vector<int32_t>* matrix,
+                  std::vector<int32_t>* lengths);
+// SegDict::SegDict (seg_dict.cpp:19-38): "word \t piece piece ..." per line.
+void LoadSegDict(const std::string& path, std::unordered_map<std::string, std::vector<std::string>>* out);
+
 class ParaformerB200 : public Model {
  public:
   // device: CUDA ordinal; max_rows / max_segments: engine capacity (0 = defaults)

@@ -55,6 +55,10 @@ int b200pf_host_offline_infer_buffer_hw(void* h, const char* buf, int n_bytes, i
 /* CompileHotwordEmbedding(handle, hotwords) (funasrruntime.h:118; Paraformer::CompileHotwordEmbedding, paraformer.cpp:592-693):
  * writes rows of `dim` floats, returns the row count (hotwords kept + the blank row) or -1. */
 int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* out, int cap_rows, int dim);
+/* The host half of CompileHotwordEmbedding alone (paraformer.cpp:600-648; no GPU): hotword string -> ids [n][10] + lengths [n],
+ * blank row last.  tokens = tokens.json in id order; seg_dict_path may be NULL.  Returns n, -1 when n > cap_rows. */
+int b200pf_host_pack_hotwords(const char* const* tokens, int n_tokens, const char* seg_dict_path, const char* hotwords, int32_t* ids,
+                              int32_t* lengths, int cap_rows);
 /* Model::InitSegDict (model.h:27; SegDict, seg_dict.cpp:19-38) for English hotwords. */
 int b200pf_host_init_seg_dict(void* h_offline, const char* path);
 

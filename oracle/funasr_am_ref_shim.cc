@@ -1,0 +1,65 @@
+// ORACLE-SIDE (test infrastructure; only tests/, smoke() and bench.py's cpu_baseline leg may use anything under oracle/).
+//
+// C entry points over the reference's OWN compiled acoustic-model and punctuation host classes -- funasr::Paraformer
+// (onnxruntime/src/paraformer.cpp: InitAsr :21-52, LfrCmvn :378-418, Forward :420-582, CompileHotwordEmbedding :592-693) and
+// funasr::CTTransformer (ct-transformer.cpp: AddPunc :40-157, Infer :164-203) -- built where the sources lie (oracle/Makefile,
+// target `ref`).  Their onnxruntime sessions are served by oracle/fake_ort.cc: the network behind a session is whatever callback
+// the test registered (the oracle's numpy/torch restatement of the graph), everything around it is the reference's code.
+#include "precomp.h"
+
+namespace google {
+// LogMessage symbols the sources reference through LOG(...) (the vendored glog library is not built).
+static std::ostringstream g_sink;
+LogMessageTime::LogMessageTime() : time_struct_(), timestamp_(0), usecs_(0), gmtoffset_(0) {}
+LogMessage::LogMessage(const char*, int) : allocated_(nullptr), data_(nullptr) {}
+LogMessage::LogMessage(const char*, int, int) : allocated_(nullptr), data_(nullptr) {}
+LogMessage::~LogMessage() { g_sink.str(""); }
+std::ostream& LogMessage::stream() { return g_sink; }
+}  // namespace google
+
+static int CopyOut(const std::string& s, char* out, int cap) {
+  if ((int)s.size() + 1 > cap) return -1;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+extern "C" {
+void* ref_am_create(const char* am_model, const char* am_cmvn, const char* am_config, const char* token_file) {
+  funasr::Paraformer* p = new funasr::Paraformer();
+  p->InitAsr(am_model, am_cmvn, am_config, token_file, 1);
+  return p;
+}
+void ref_am_destroy(void* h) { delete (funasr::Paraformer*)h; }
+void ref_am_init_hw(void* h, const char* hw_model) { ((funasr::Paraformer*)h)->InitHwCompiler(hw_model, 1); }
+void ref_am_init_seg_dict(void* h, const char* path) { ((funasr::Paraformer*)h)->InitSegDict(path); }
+// Paraformer::Forward(float** din, int* len, true, hw_emb, nullptr, 1): pcm in the reference's float form (int16 / 32768).
+int ref_am_forward(void* h, const float* pcm, int n, const float* hw, int n_hw, int dim, char* out, int cap) {
+  std::vector<std::vector<float>> emb;
+  for (int j = 0; j < n_hw; ++j) emb.emplace_back(hw + (size_t)j * dim, hw + (size_t)(j + 1) * dim);
+  if (emb.empty()) emb.push_back(std::vector<float>(1, 0.0f));
+  float* din[1] = {const_cast<float*>(pcm)};
+  int len[1] = {n};
+  std::vector<std::string> r = ((funasr::Paraformer*)h)->Forward(din, len, true, emb, nullptr, 1);
+  return CopyOut(r.empty() ? std::string() : r[0], out, cap);
+}
+int ref_am_compile_hotwords(void* h, const char* hotwords, float* out, int cap_rows, int dim) {
+  std::string hw(hotwords);
+  std::vector<std::vector<float>> emb = ((funasr::Paraformer*)h)->CompileHotwordEmbedding(hw);
+  if ((int)emb.size() > cap_rows) return -1;
+  for (size_t j = 0; j < emb.size(); ++j) {
+    if ((int)emb[j].size() != dim) return -2;
+    memcpy(out + j * dim, emb[j].data(), dim * sizeof(float));
+  }
+  return (int)emb.size();
+}
+
+void* ref_punc_create(const char* punc_model, const char* punc_config, const char* token_file) {
+  funasr::CTTransformer* p = new funasr::CTTransformer();
+  p->InitPunc(punc_model, punc_config, token_file, 1);
+  return p;
+}
+void ref_punc_destroy(void* h) { delete (funasr::CTTransformer*)h; }
+int ref_punc_add(void* h, const char* text, const char* lang, char* out, int cap) {
+  return CopyOut(((funasr::CTTransformer*)h)->AddPunc(text, std::string(lang)), out, cap);
+}
+}  // extern "C"

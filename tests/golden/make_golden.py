@@ -7,6 +7,7 @@ oracle's index formula; model taps from the fp32 oracle (parity unpinned, see or
     python tests/golden/make_golden.py
 """
 import importlib
+import json
 import os
 import sys
 
@@ -189,7 +190,70 @@ def main():
     with open(os.path.join(HERE, "text_golden.json"), "w", encoding="utf-8") as f:
         json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
                   f, ensure_ascii=False)
+    make_am_golden(synth)
     print("wrote", os.listdir(HERE))
+
+
+def make_am_golden(synth):
+    """The reference's own compiled funasr::Paraformer (Forward / CompileHotwordEmbedding) over the stand-in onnxruntime with the
+    oracle's network behind the sessions (oracle/am_ref.py): features handed to the session, result strings, hotword id matrices."""
+    import tempfile
+    import torch
+    from oracle import am_ref as A
+    from oracle import paraformer_ref as R
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_am_ref_cpu as TA
+    assert A.available(), "needs oracle/_ref/libfunasr_am_ref.so (make -C oracle ref in the build container)"
+    out = dict(source="reference onnxruntime/src/paraformer.cpp compiled in place over oracle/fake_ort.cc; network = oracle/paraformer_ref.py",
+               vocab=8404, seg_dict=TA.SEG_DICT, hotwords=[], forward=[])
+    arrays = {}
+    for name, extra, seed, hotwords, cases in (
+            ("plain", {}, 0, None, ((42, 160000), (3, 16000), (4, 5000), (6, 7120), (11, 48000), (12, 399))),
+            ("config3", dict(timestamp=1, contextual=1), 3, "一丁 七万丈 hello", ((42, 160000), (3, 48000), (9, 80000)))):
+        d = tempfile.mkdtemp(prefix="am_golden_")
+        pc, Wt, means, vars_, toks = TA._model(synth, d, extra, seed)
+        sd = os.path.join(d, "seg_dict")
+        with open(sd, "w", encoding="utf-8") as f:
+            f.write(TA.SEG_DICT)
+        seen, hseen = {}, {}
+        m = A.RefParaformer(d, TA._net(pc, Wt, seen), n_out=4 if pc.timestamp else 2, hw_net=TA._hw_net(Wt, hseen) if pc.contextual else None,
+                            seg_dict=sd, tag="g" + name)
+        hw_emb = None
+        if pc.contextual:
+            # id matrices AND lengths as the reference computes them: a probe network whose output at step t is t + 1 makes the
+            # reference's own row selection (paraformer.cpp:678-684) report lengths[j]
+            pseen = {}
+
+            def probe(ins):
+                pseen["ids"] = ins[0].copy()
+                n_hw = ins[0].shape[0]
+                return [np.broadcast_to(np.arange(1, 11, dtype=np.float32)[:, None, None], (10, n_hw, pc.d_model)).copy()]
+            mp = A.RefParaformer(d, TA._net(pc, Wt, {}), n_out=4, hw_net=probe, seg_dict=sd, tag="probe")
+            for hw in TA.HOTWORDS:
+                emb = mp.compile_hotwords(hw, dim=pc.d_model)
+                out["hotwords"].append(dict(text=hw, ids=pseen["ids"].tolist(), lengths=[int(v) for v in emb[:, 0]]))
+            mp.close()
+            hw_emb = m.compile_hotwords(hotwords, dim=pc.d_model)
+        for k, (aseed, n) in enumerate(cases):
+            pcm = synth.make_audio(n, aseed)
+            x = pcm.astype(np.float32) / np.float32(32768)
+            seen.clear()
+            text = m.forward(x, hw_emb)
+            case = dict(model=name, cfg=dict(dict(n_enc=2, n_dec=2), **extra), model_seed=seed, audio_seed=aseed, n_samples=n, text=text,
+                        hotwords=hotwords)
+            if "out" in seen:
+                o = seen["out"]
+                lp = o["logprobs"].numpy()
+                case["ids"] = [int(i) for i in o["ids"]]
+                top2 = np.sort(lp[:len(o["ids"])], axis=1)[:, -2:]
+                case["gaps"] = [round(float(v), 5) for v in (top2[:, 1] - top2[:, 0])]   # top-1 margin per token (log-prob)
+                if n <= 16000:
+                    arrays["feats_%s_%d" % (name, k)] = seen["feats"][0]
+            out["forward"].append(case)
+        m.close()
+    np.savez_compressed(os.path.join(HERE, "am_forward_golden.npz"), **arrays)
+    with open(os.path.join(HERE, "am_forward_golden.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
 
 
 if __name__ == "__main__":
