@@ -21,7 +21,10 @@ outputs logits[1,L,8404] f32 + token_num: paraformer.cpp:496-562) and on in-repo
 Two pieces of this file ARE pinned against the reference's own compiled code (oracle/_ref/libfunasr_text_ref.so, built
 from onnxruntime/src/paraformer-online.cpp where it lies; golden vectors tests/golden/cif_posenc_golden.npz): `cif`
 (ParaformerOnline::CifSearch run in its offline form: token counts exact, frames to 1e-6) and `pos_enc`
-(ParaformerOnline::GetPosEmb: 1e-6, 1e-5 at position 1000).
+(ParaformerOnline::GetPosEmb: 1e-6, 1e-5 at position 1000).  The INTERFACE of `forward` / `hotword_embed` (tensor layouts, token_num
+semantics, the 4-output timestamp form, the [10, N, D] hotword output and its row selection) is pinned too: the reference's own
+compiled Paraformer::Forward / CompileHotwordEmbedding run with this file as the network behind their sessions
+(oracle/am_ref.py, oracle/fake_ort.cc) and produce the strings the oracle's host restatement predicts (tests/test_am_ref_cpu.py).
 
 `emulate_bf16=True` rounds to bfloat16 exactly where the CUDA path stores bf16 (GEMM operands and the
 bf16 activation buffers), keeping every reduction in fp32.  It is a second oracle used to separate
