@@ -54,6 +54,7 @@ EXPORTS = [
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
     "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln", "b200pf_vad_create", "b200pf_vad_destroy", "b200pf_vad_scores_s16",
+    "b200pf_punc_create", "b200pf_punc_destroy", "b200pf_punc_info", "b200pf_punc_infer", "b200pf_punc_launches",
 ]
 
 
@@ -120,7 +121,9 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
                 "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
-                "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords"]
+                "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords", "b200pf_host_punc_tokenize",
+                "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_add",
+                "b200pf_host_punc_add_batch"]
 
 
 def host_lib():
@@ -162,6 +165,15 @@ def host_lib():
     H.b200pf_host_offline_vad_cut.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_i32p, C.c_int]
     H.b200pf_host_offline_infer_buffer_vad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_pack_hotwords.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, c_i32p, c_i32p, C.c_int]
+    H.b200pf_host_punc_tokenize.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, c_i32p, C.c_int]
+    H.b200pf_host_punc_add_scripted.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p,
+                                                C.c_int, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_punc_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    H.b200pf_host_punc_create.restype = C.c_void_p
+    H.b200pf_host_punc_destroy.argtypes = [C.c_void_p]
+    H.b200pf_host_punc_destroy.restype = None
+    H.b200pf_host_punc_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    H.b200pf_host_punc_add_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, c_i32p]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     H.b200pf_host_mb_create.restype = C.c_void_p
     H.b200pf_host_mb_create_mock.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
@@ -398,6 +410,71 @@ def host_pack_hotwords(tokens, hotwords, seg_dict_path=None, cap=4200):
     return ids[:n].copy(), lens[:n].copy()
 
 
+class HostPuncTokenizer:
+    """funasr_b200::PuncTokenizer + the AddPunc walk with a scripted network (CPU only)."""
+
+    def __init__(self, tokens, punc_list):
+        self.tokens = (C.c_char_p * len(tokens))(*[t.encode("utf-8") for t in tokens])
+        self.n = len(tokens)
+        self.punc = (C.c_char_p * len(punc_list))(*[t.encode("utf-8") for t in punc_list])
+        self.n_punc = len(punc_list)
+
+    def tokenize(self, text):
+        raw = text.encode("utf-8")
+        ids = np.zeros(len(raw) + 4, np.int32)
+        n = host_lib().b200pf_host_punc_tokenize(self.tokens, self.n, raw, _p(ids, c_i32p), len(ids))
+        assert n >= 0
+        return ids[:n].tolist()
+
+    def add_punc_scripted(self, text, lang, seed, every):
+        raw = text.encode("utf-8")
+        buf = C.create_string_buffer(16 * len(raw) + 4096)
+        n = host_lib().b200pf_host_punc_add_scripted(self.tokens, self.n, self.punc, self.n_punc, raw, lang.encode(), seed, every, buf, len(buf))
+        assert n >= 0
+        return buf.value.decode("utf-8", "replace")
+
+
+class HostPunc:
+    """CTTransformerInit / CTTransformerInfer / CTTransformerUninit through the host shim (funasr_b200::CTTransformerB200)."""
+
+    def __init__(self, punc_dir, device=0, max_tokens=0):
+        self.h = host_lib().b200pf_host_punc_create(punc_dir.encode(), device, max_tokens)
+        if not self.h:
+            raise B200PFError("CTTransformerInit failed: " + lib().b200pf_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self.h:
+            host_lib().b200pf_host_punc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_punc(self, text, lang="zh-cn"):
+        raw = text.encode("utf-8")
+        buf = C.create_string_buffer(16 * len(raw) + 4096)
+        n = host_lib().b200pf_host_punc_add(self.h, raw, lang.encode(), buf, len(buf))
+        if n < 0:
+            raise B200PFError("AddPunc failed")
+        return buf.value.decode("utf-8", "replace")
+
+    def add_punc_batch(self, texts, lang="zh-cn"):
+        """-> (list of punctuated texts, engine calls made)"""
+        raws = [t.encode("utf-8") for t in texts]
+        arr = (C.c_char_p * len(raws))(*raws)
+        cap = 16 * sum(len(r) for r in raws) + 4096 * (len(raws) + 1)
+        buf = C.create_string_buffer(cap)
+        rounds = np.zeros(1, np.int32)
+        n = host_lib().b200pf_host_punc_add_batch(self.h, arr, len(raws), lang.encode(), buf, cap, _p(rounds, c_i32p))
+        if n < 0:
+            raise B200PFError("AddPuncBatch failed")
+        parts = buf.raw[:n].split(b"\0")[:len(raws)]
+        return [p.decode("utf-8", "replace") for p in parts], int(rounds[0])
+
+
 def host_partition(lens, n_dev):
     """MultiGpuParaformer's LPT assignment of segments (sample counts) to n_dev queues."""
     l = np.ascontiguousarray(lens, dtype=np.int32)
@@ -533,6 +610,49 @@ class VadEngine:
         _check(lib().b200pf_vad_scores_s16(self.h, C.c_void_p(pcm16.ctypes.data), _p(offsets, c_i64p), n, _p(p0), cap, _p(fo, c_i32p),
                                            _p(pr), _p(ft)))
         return p0[:cap], fo, (pr[:cap] if pr is not None else None), (ft[:cap] if ft is not None else None)
+
+
+class PuncEngine:
+    """CT-Transformer punctuation network on the GPU (replaces CTTransformer::Infer's onnxruntime session, ct-transformer.cpp:164-203)."""
+
+    def __init__(self, punc_dir, device=0, max_tokens=0):
+        self.h = C.c_void_p()
+        L = lib()
+        L.b200pf_punc_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.b200pf_punc_destroy.argtypes = [C.c_void_p]
+        L.b200pf_punc_destroy.restype = None
+        L.b200pf_punc_info.argtypes = [C.c_void_p, c_i32p, c_i32p, c_i32p, c_i32p]
+        L.b200pf_punc_infer.argtypes = [C.c_void_p, c_i32p, c_i32p, C.c_int, c_i32p, c_f32p]
+        L.b200pf_punc_launches.argtypes = [C.c_void_p]
+        L.b200pf_punc_launches.restype = C.c_longlong
+        _check(L.b200pf_punc_create(punc_dir.encode(), device, max_tokens, C.byref(self.h)))
+        info = np.zeros(4, np.int32)
+        _check(L.b200pf_punc_info(self.h, _p(info[0:1], c_i32p), _p(info[1:2], c_i32p), _p(info[2:3], c_i32p), _p(info[3:4], c_i32p)))
+        self.vocab, self.n_punc, self.d_model, self.max_tokens = (int(v) for v in info)
+
+    def close(self):
+        if self.h:
+            lib().b200pf_punc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().b200pf_punc_launches(self.h))
+
+    def infer(self, ids, offsets, logits=False):
+        """-> (punc ids int32 [T], logits [T, n_punc] or None) for sequences ids[offsets[i]:offsets[i+1]]."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        out = np.zeros(max(1, len(ids)), np.int32)
+        lg = np.zeros((max(1, len(ids)), self.n_punc), np.float32) if logits else None
+        _check(lib().b200pf_punc_infer(self.h, _p(ids, c_i32p), _p(offsets, c_i32p), len(offsets) - 1, _p(out, c_i32p), _p(lg)))
+        return out[:len(ids)], (lg[:len(ids)] if lg is not None else None)
 
 
 class Batch:

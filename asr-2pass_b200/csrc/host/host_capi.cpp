@@ -2,6 +2,7 @@
 // bench.py's end-to-end leg: detokeniser, timestamp/post-processing, and the FunOffline* call sequence.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 
 #include "../../../include/b200pf_host.h"
 #include <chrono>
@@ -11,6 +12,7 @@
 #include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
+#include "punc_b200.h"
 #include "vad_segmenter.h"
 
 namespace {
@@ -167,6 +169,59 @@ int b200pf_host_pack_hotwords(const char* const* tokens, int n_tokens, const cha
   memcpy(ids, m.data(), m.size() * sizeof(int32_t));
   memcpy(lengths, l.data(), l.size() * sizeof(int32_t));
   return (int)l.size();
+}
+// ---- punctuation (CTTransformer mirror) ----
+int b200pf_host_punc_tokenize(const char* const* tokens, int n_tokens, const char* text, int32_t* ids, int cap) {
+  funasr_b200::PuncTokenizer tk;
+  tk.Open(std::vector<std::string>(tokens, tokens + n_tokens), std::vector<std::string>());
+  std::vector<std::string> pieces;
+  std::vector<int32_t> v;
+  tk.Tokenize(text, &pieces, &v);
+  if ((int)v.size() > cap) return -1;
+  if (!v.empty()) memcpy(ids, v.data(), v.size() * sizeof(int32_t));
+  return (int)v.size();
+}
+int b200pf_host_punc_add_scripted(const char* const* tokens, int n_tokens, const char* const* punc_list, int n_punc, const char* text,
+                                  const char* lang, int seed, int every, char* out, int cap) {
+  funasr_b200::PuncTokenizer tk;
+  tk.Open(std::vector<std::string>(tokens, tokens + n_tokens), std::vector<std::string>(punc_list, punc_list + n_punc));
+  // the scripted stand-in network of tests/test_punc.py::scripted_punc
+  auto infer = [&](const std::vector<int32_t>& ids) {
+    std::vector<int32_t> r(ids.size());
+    for (size_t pos = 0; pos < ids.size(); ++pos) {
+      uint32_t h = (uint32_t)((uint64_t)(uint32_t)ids[pos] * 2654435761ull + (uint64_t)pos * 40503ull + (uint64_t)seed * 97ull);
+      h = (h >> 7) & 0xFFFF;
+      if (every && h % (uint32_t)every == 0) r[pos] = h % 3 ? 3 : 4;
+      else if (h % 11 == 1) r[pos] = 2;
+      else if (h % 37 == 2) r[pos] = 0;
+      else r[pos] = 1;
+    }
+    return r;
+  };
+  return CopyOut(funasr_b200::AddPuncWith(tk, text, lang ? lang : "zh-cn", infer), out, cap);
+}
+void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens) {
+  std::unique_ptr<funasr_b200::CTTransformerB200> p(new funasr_b200::CTTransformerB200(device, max_tokens));
+  std::string err;
+  if (!p->Init(punc_dir, &err)) { fprintf(stderr, "b200pf_host_punc_create: %s\n", err.c_str()); return nullptr; }
+  return p.release();
+}
+void b200pf_host_punc_destroy(void* h) { delete (funasr_b200::CTTransformerB200*)h; }
+int b200pf_host_punc_add(void* h, const char* text, const char* lang, char* out, int cap) {
+  if (!h) return -1;
+  return CopyOut(((funasr_b200::PuncModel*)(funasr_b200::CTTransformerB200*)h)->AddPunc(text, std::string(lang ? lang : "zh-cn")).c_str(), out, cap);
+}
+int b200pf_host_punc_add_batch(void* h, const char* const* texts, int n, const char* lang, char* out, int cap, int* rounds) {
+  if (!h) return -1;
+  std::vector<std::string> in(texts, texts + n);
+  const std::vector<std::string> r = ((funasr_b200::CTTransformerB200*)h)->AddPuncBatch(in, lang ? lang : "zh-cn", rounds);
+  size_t used = 0;
+  for (const std::string& s : r) {     // results back to back, each NUL-terminated
+    if (used + s.size() + 1 > (size_t)cap) return -1;
+    memcpy(out + used, s.c_str(), s.size() + 1);
+    used += s.size() + 1;
+  }
+  return (int)used;
 }
 int b200pf_host_init_seg_dict(void* h_offline, const char* path) {
   funasr_b200::ParaformerB200* m = FunOfflineModelB200(h_offline);

@@ -243,3 +243,106 @@ def write_synthetic_model_dir(path, cfg=None, seed=0, jitter_ln=False, lang="zh-
     toks = make_tokens(int(cfg["vocab"]))
     modelfile.write_model_dir(path, cfg, W, means, vars_, toks, lang=lang)
     return cfg, W, means, vars_, toks
+
+
+# ---- CT-Transformer punctuation model ---------------------------------------------------------
+PUNC_CFG = dict(vocab=272727, d_model=256, n_heads=8, d_ff=1024, n_layers=4, kernel=11, n_punc=6, ln_eps=1e-12)
+PUNC_LIST = ["<unk>", "_", "，", "。", "？", "、"]
+
+
+def punc_param_shapes(cfg):
+    D, Fd, K = int(cfg["d_model"]), int(cfg["d_ff"]), int(cfg["kernel"])
+    out = {"embed.weight": (int(cfg["vocab"]), D)}
+    for l in range(int(cfg["n_layers"])):
+        p = "encoder.encoders0.0" if l == 0 else "encoder.encoders.%d" % (l - 1)
+        for nm, shp in ((".norm1.weight", (D,)), (".norm1.bias", (D,)), (".self_attn.linear_q_k_v.weight", (3 * D, D)),
+                        (".self_attn.linear_q_k_v.bias", (3 * D,)), (".self_attn.fsmn_block.weight", (D, 1, K)),
+                        (".self_attn.linear_out.weight", (D, D)), (".self_attn.linear_out.bias", (D,)), (".norm2.weight", (D,)),
+                        (".norm2.bias", (D,)), (".feed_forward.w_1.weight", (Fd, D)), (".feed_forward.w_1.bias", (Fd,)),
+                        (".feed_forward.w_2.weight", (D, Fd)), (".feed_forward.w_2.bias", (D,))):
+            out[p + nm] = shp
+    out["encoder.after_norm.weight"] = (D,)
+    out["encoder.after_norm.bias"] = (D,)
+    out["decoder.weight"] = (int(cfg["n_punc"]), D)
+    out["decoder.bias"] = (int(cfg["n_punc"]),)
+    return out
+
+
+def make_punc_weights(cfg=None, seed=0):
+    """Default torch inits (Embedding N(0,1), Linear / Conv1d U(+-1/sqrt(fan_in)), LayerNorm jittered); the classifier is scaled up
+    and biased so that the five reachable classes all occur (a punctuation model that never fires would not exercise AddPunc)."""
+    cfg = dict(PUNC_CFG, **(cfg or {}))
+    rng = np.random.default_rng(seed)
+    W = {}
+    shapes = punc_param_shapes(cfg)
+    for name, shp in shapes.items():
+        if name == "embed.weight":
+            W[name] = rng.standard_normal(shp).astype(np.float32)
+        elif ".norm" in name or "after_norm" in name:
+            W[name] = ((1.0 if name.endswith(".weight") else 0.0) + 0.1 * rng.uniform(-1, 1, shp)).astype(np.float32)
+        elif name.endswith(".weight"):
+            W[name] = (rng.uniform(-1, 1, shp) / math.sqrt(int(np.prod(shp[1:])))).astype(np.float32)
+        else:
+            wshape = shapes[name[:-5] + ".weight"]
+            W[name] = (rng.uniform(-1, 1, shp) / math.sqrt(int(np.prod(wshape[1:])))).astype(np.float32)
+    W["decoder.weight"] *= np.float32(3.0)
+    W["decoder.bias"] = np.asarray([-1.5, 1.8, 0.6, 0.0, -0.6, 0.0][:int(cfg["n_punc"])], np.float32)
+    return cfg, W
+
+
+def make_punc_tokens(vocab):
+    """<unk> first (the reference looks it up by name), CJK from U+4E00, lower-case latin words, digits."""
+    toks = ["<unk>"]
+    n_latin = min(2000, max(8, vocab // 8))
+    toks += [chr(0x4E00 + i) for i in range(min(20000, vocab - 1 - n_latin))]
+    i = 0
+    while len(toks) < vocab:
+        a, b, c, d = i % 26, (i // 26) % 26, (i // 676) % 26, i // 17576
+        toks.append(chr(97 + a) + chr(97 + b) + (chr(97 + c) if i % 3 else "") + (str(d) if d else ""))
+        i += 1
+    assert len(toks) == vocab and len(set(toks)) == vocab
+    return toks
+
+
+def write_synthetic_punc_dir(path, cfg=None, seed=0):
+    """<punc-dir>/{punc.b200pf, tokens.json, punc_list.json, config.yaml}: config.yaml carries model_conf.punc_list the way the
+    reference's CTokenizer::OpenYaml reads it (tokenizer.cpp:136-160); punc_list.json is the same list for the B200 host side."""
+    import json
+    import os
+    from . import modelfile
+    cfg, W = make_punc_weights(cfg, seed)
+    toks = make_punc_tokens(int(cfg["vocab"]))
+    os.makedirs(path, exist_ok=True)
+    modelfile.write_weights(os.path.join(path, "punc.b200pf"), cfg, W)
+    with open(os.path.join(path, "tokens.json"), "w", encoding="utf-8") as f:
+        json.dump(toks, f, ensure_ascii=False)
+    with open(os.path.join(path, "punc_list.json"), "w", encoding="utf-8") as f:
+        json.dump(PUNC_LIST, f, ensure_ascii=False)
+    with open(os.path.join(path, "config.yaml"), "w", encoding="utf-8") as f:
+        f.write("model: CTTransformer\nmodel_conf:\n  punc_list:\n" + "".join('  - "%s"\n' % p for p in PUNC_LIST))
+    return cfg, W, toks
+
+
+def make_text(n_tokens, seed, toks, english_frac=0.15):
+    """Unpunctuated transcript-like text over the punctuation vocabulary: runs of CJK characters, lower/upper-case latin words
+    separated by spaces, the odd out-of-vocabulary character."""
+    rng = np.random.default_rng(seed)
+    cjk = [t for t in toks[1:4000] if ord(t[0]) >= 0x4E00]
+    lat = [t for t in toks if t and ord(t[0]) < 128 and t != "<unk>"][:500]
+    out, n = [], 0
+    while n < n_tokens:
+        if rng.random() < english_frac and lat:
+            k = int(rng.integers(1, 4))
+            ws = [lat[int(rng.integers(len(lat)))] for _ in range(k)]
+            if rng.random() < 0.2:
+                ws[0] = ws[0].upper()
+            out.append(" " + " ".join(ws) + " ")
+            n += k
+        else:
+            k = int(rng.integers(1, 12))
+            s = "".join(cjk[int(rng.integers(len(cjk)))] for _ in range(k))
+            if rng.random() < 0.05:
+                s += "㐀"            # not in the vocabulary -> <unk>
+            out.append(s)
+            n += len(s)
+    return "".join(out).strip()

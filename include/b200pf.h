@@ -175,6 +175,22 @@ void b200pf_vad_destroy(b200pf_vad* v);
 int b200pf_vad_scores_s16(b200pf_vad* v, const int16_t* pcm, const int64_t* offsets, int n_rec, float* sil_prob, int64_t cap_frames,
                           int32_t* frame_off, float* all_probs, float* feats);
 
+/* ---- CT-Transformer punctuation network ------------------------------------------------------
+ * Replaces the onnxruntime session of CTTransformer::Infer (onnxruntime/src/ct-transformer.cpp:164-203): int32 token ids in, one
+ * punctuation class per token out, for many token sequences per call (the reference runs one 20-token mini-sentence of one
+ * request per session call).  <punc_dir> holds punc.b200pf (upstream FunASR CTTransformer parameter names: embed, encoder.*,
+ * decoder; config keys vocab, d_model, n_heads, d_ff, n_layers, kernel, n_punc).  max_tokens: tokens one call may hold (0 -> 65536). */
+typedef struct b200pf_punc b200pf_punc;
+int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_punc** out);
+void b200pf_punc_destroy(b200pf_punc* p);
+int b200pf_punc_info(const b200pf_punc* p, int* vocab, int* n_punc, int* d_model, int* max_tokens);
+/* ids: sequences back to back, sequence i = ids[offsets[i] .. offsets[i+1]) (each <= 4096 tokens).  punc_out [offsets[n_seq]]
+ * receives the first maximum over classes [0, n_punc - 1) of every token -- the reference's Argmax(row, row + CANDIDATE_NUM - 1)
+ * never selects the last class (ct-transformer.cpp:191-195).  logits_out (optional) [offsets[n_seq], n_punc]. */
+int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets, int n_seq, int32_t* punc_out, float* logits_out);
+/* Kernels launched by b200pf_punc_infer so far. */
+long long b200pf_punc_launches(const b200pf_punc* p);
+
 /* ---- single-operator entry points (fp32 host buffers in/out; used by the parity tests) -------------- */
 /* C = A[M,K] * W[N,K]^T (+bias) (+relu: 1 after bias, 2 after all adds) (+add[M,N] rounded to bf16)
  * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: 1 rounds the result to bf16; 0 = fp32 with the

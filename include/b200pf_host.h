@@ -55,6 +55,20 @@ int b200pf_host_offline_infer_buffer_hw(void* h, const char* buf, int n_bytes, i
 /* CompileHotwordEmbedding(handle, hotwords) (funasrruntime.h:118; Paraformer::CompileHotwordEmbedding, paraformer.cpp:592-693):
  * writes rows of `dim` floats, returns the row count (hotwords kept + the blank row) or -1. */
 int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* out, int cap_rows, int dim);
+/* ---- punctuation: funasr::CTTransformer mirror (csrc/host/punc_b200.h) -----------------------
+ * CTokenizer::Tokenize without jieba (tokenizer.cpp:312-365): text -> token ids (lower-cased lookup, <unk> otherwise).  No GPU. */
+int b200pf_host_punc_tokenize(const char* const* tokens, int n_tokens, const char* text, int32_t* ids, int cap);
+/* CTTransformer::AddPunc's mini-sentence walk (ct-transformer.cpp:40-157) with a SCRIPTED network in place of the session (class =
+ * hash of token id, position and seed; tests/test_punc.py::scripted_punc): pins the host logic on machines without a GPU. */
+int b200pf_host_punc_add_scripted(const char* const* tokens, int n_tokens, const char* const* punc_list, int n_punc, const char* text,
+                                  const char* lang, int seed, int every, char* out, int cap);
+/* CTTransformerInit / CTTransformerInfer(PUNC_OFFLINE) / CTTransformerUninit (funasrruntime.h:92-96) over the B200 punctuation
+ * engine: <punc_dir>/{punc.b200pf, tokens.json, punc_list.json}.  add_batch punctuates n texts in lock step (one engine call per
+ * round for all of them); results are written back to back, each NUL-terminated; returns the bytes used. */
+void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens);
+void b200pf_host_punc_destroy(void* h);
+int b200pf_host_punc_add(void* h, const char* text, const char* lang, char* out, int cap);
+int b200pf_host_punc_add_batch(void* h, const char* const* texts, int n, const char* lang, char* out, int cap, int* rounds);
 /* The host half of CompileHotwordEmbedding alone (paraformer.cpp:600-648; no GPU): hotword string -> ids [n][10] + lengths [n],
  * blank row last.  tokens = tokens.json in id order; seg_dict_path may be NULL.  Returns n, -1 when n > cap_rows. */
 int b200pf_host_pack_hotwords(const char* const* tokens, int n_tokens, const char* seg_dict_path, const char* hotwords, int32_t* ids,

@@ -191,7 +191,45 @@ def main():
         json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
                   f, ensure_ascii=False)
     make_am_golden(synth)
+    make_punc_golden(synth)
     print("wrote", os.listdir(HERE))
+
+
+def make_punc_golden(synth):
+    """Strings from the reference's own compiled CTTransformer::AddPunc + CTokenizer (oracle/am_ref.py) with the scripted network of
+    tests/test_punc.py behind the session."""
+    import tempfile
+    from oracle import am_ref as A
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_punc as TP
+    d = tempfile.mkdtemp(prefix="punc_golden_")
+    cfg, W, toks = synth.write_synthetic_punc_dir(d, TP.SMALL, seed=0)
+    state = dict(seed=0, every=0, seen=[])
+
+    def net(ins):
+        state["seen"].append(ins[0][0].tolist())
+        cls = TP.scripted_punc(ins[0][0], state["seed"], state["every"]) if state["every"] >= 0 else [1] * ins[0].shape[1]
+        lg = np.full((1, len(cls), 6), -5.0, np.float32)
+        lg[0, np.arange(len(cls)), cls] = 5.0
+        lg[0, :, 5] = 9.0
+        return [lg]
+
+    ref = A.RefPunc(d, net, tag="golden")
+    cases = []
+    for s, text in enumerate(TP._texts(synth, toks, 60)):
+        lang = "en-bpe" if s % 5 == 0 else "zh-cn"
+        # the reference tokenizer's ids: with a network that never punctuates nothing is ever cut off the cache, so the LAST session
+        # call of a request sees every token of the text
+        state.update(seed=s, every=-1, seen=[])
+        ref.add_punc(text, lang)
+        ids = state["seen"][-1] if state["seen"] else []
+        for every in (0, 50, 7):
+            state.update(seed=s, every=every, seen=[])
+            cases.append(dict(text=text, lang=lang, seed=s, every=every, out=ref.add_punc(text, lang), ids=ids))
+    ref.close()
+    with open(os.path.join(HERE, "punc_golden.json"), "w", encoding="utf-8") as f:
+        json.dump(dict(source="reference onnxruntime/src/{ct-transformer,tokenizer}.cpp compiled in place over oracle/fake_ort.cc; scripted network",
+                       vocab=TP.SMALL["vocab"], cases=cases), f, ensure_ascii=False)
 
 
 def make_am_golden(synth):
