@@ -123,7 +123,8 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
                 "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords", "b200pf_host_punc_tokenize",
                 "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_add",
-                "b200pf_host_punc_add_batch"]
+                "b200pf_host_punc_add_batch", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
+                "b200pf_host_offline_infer_full"]
 
 
 def host_lib():
@@ -165,6 +166,11 @@ def host_lib():
     H.b200pf_host_offline_vad_cut.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, c_i32p, C.c_int]
     H.b200pf_host_offline_infer_buffer_vad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_pack_hotwords.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, c_i32p, c_i32p, C.c_int]
+    H.b200pf_host_offline_init_kv.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int]
+    H.b200pf_host_offline_init_kv.restype = C.c_void_p
+    H.b200pf_host_offline_infer_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                                 C.c_char_p, C.c_int]
+    H.b200pf_host_sentence_stamps.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     H.b200pf_host_punc_tokenize.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, c_i32p, C.c_int]
     H.b200pf_host_punc_add_scripted.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p,
                                                 C.c_int, C.c_int, C.c_char_p, C.c_int]
@@ -224,10 +230,19 @@ def host_stitch(msgs, starts, lang):
 class OfflineHandle:
     """FunOfflineInit / FunOfflineInferBuffer / FunOfflineUninit through the host shim."""
 
-    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64, devices=None, vad_dir=None, vad_thres=0.0):
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, batch_size=64, devices=None, vad_dir=None, vad_thres=0.0, options=None):
         """devices=[0, 1, ...]: one engine per listed GPU behind this handle (funasr_b200::MultiGpuParaformer).
         vad_dir: FSMN-VAD model directory; infer_buffer then cuts recordings the way the reference's UseVad() branch does."""
-        if vad_dir is not None:
+        if options is not None:   # the reference's own key/value map, e.g. {"vad-dir": ..., "punc-dir": ...}
+            kv = dict(options)
+            kv.setdefault("model-dir", model_dir)
+            kv.setdefault("device", str(device))
+            kv.setdefault("max-rows", str(max_rows))
+            kv.setdefault("max-segments", str(max_segments))
+            keys = (C.c_char_p * len(kv))(*[k.encode() for k in kv])
+            vals = (C.c_char_p * len(kv))(*[str(v).encode() for v in kv.values()])
+            self.h = host_lib().b200pf_host_offline_init_kv(keys, vals, len(kv), batch_size)
+        elif vad_dir is not None:
             self.h = host_lib().b200pf_host_offline_init_vad(model_dir.encode(), vad_dir.encode(), device, max_rows, max_segments, batch_size,
                                                              C.c_float(vad_thres))
         elif devices is not None and len(devices) > 1:
@@ -277,6 +292,16 @@ class OfflineHandle:
         if n < 0:
             raise B200PFError("FunOfflineInferBuffer returned nullptr")
         return buf.value.decode("utf-8"), st.value.decode("utf-8")
+
+    def infer_full(self, pcm16, vad_tail_sil=800, vad_max_len=60000, cap=1 << 22):
+        """FunOfflineInferBuffer -> (text, stamp, stamp_sents)."""
+        pcm16 = np.ascontiguousarray(pcm16, dtype="<i2")
+        t, st, ss = C.create_string_buffer(cap), C.create_string_buffer(cap), C.create_string_buffer(4 * cap)
+        n = host_lib().b200pf_host_offline_infer_full(self.h, C.c_void_p(pcm16.ctypes.data), pcm16.nbytes, vad_tail_sil, vad_max_len,
+                                                      t, len(t), st, len(st), ss, len(ss))
+        if n < 0:
+            raise B200PFError("FunOfflineInferBuffer returned nullptr")
+        return t.value.decode("utf-8", "replace"), st.value.decode("utf-8"), ss.value.decode("utf-8", "replace")
 
     def infer_segments(self, pcm16, seg_begin, seg_end, cap=1 << 22):
         pcm16 = np.ascontiguousarray(pcm16, dtype=np.int16)
@@ -408,6 +433,14 @@ def host_pack_hotwords(tokens, hotwords, seg_dict_path=None, cap=4200):
     if n < 0:
         raise B200PFError("too many hotwords")
     return ids[:n].copy(), lens[:n].copy()
+
+
+def host_sentence_stamps(text, stamp):
+    """pf::host::SentenceStamps (TimestampSentence)."""
+    buf = C.create_string_buffer(64 * (len(text.encode("utf-8")) + len(stamp)) + 4096)
+    n = host_lib().b200pf_host_sentence_stamps(text.encode("utf-8"), stamp.encode("utf-8"), buf, len(buf))
+    assert n >= 0
+    return buf.value.decode("utf-8", "replace")
 
 
 class HostPuncTokenizer:

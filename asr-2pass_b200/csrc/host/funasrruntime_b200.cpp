@@ -10,6 +10,7 @@
 #include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
+#include "punc_b200.h"
 #include "vad_segmenter.h"
 
 namespace {
@@ -30,6 +31,8 @@ struct OfflineHandle {  // stands where funasr::OfflineStream does; owns only th
   b200pf_vad* vad = nullptr;
   std::mutex vad_mu;   // one VAD workspace per handle
   float vad_thres = 0.6f;
+  // "punc-dir": CT-Transformer punctuation on the GPU after stitching (the UsePunc() branch, funasrruntime.cpp:317-320)
+  std::unique_ptr<funasr_b200::CTTransformerB200> punc;
   ~OfflineHandle() { if (vad) b200pf_vad_destroy(vad); }
   funasr_b200::Model* model() { return pool ? (funasr_b200::Model*)pool.get() : (funasr_b200::Model*)asr.get(); }
   funasr_b200::ParaformerB200* first() { return pool ? pool->model(0) : asr.get(); }
@@ -65,6 +68,13 @@ std::vector<std::vector<int>> FormBatches(const std::vector<long long>& len_sort
     out.push_back(cur);
   }
   return out;
+}
+
+// What FunOfflineInferBuffer does after stitching (funasrruntime.cpp:317-335): punctuation, then the per-sentence stamps.  (ITN
+// and its TimestampSmooth stay on the reference host path.)
+void FinishResult(OfflineHandle* h, RecogResult* res) {
+  if (h->punc) res->msg = h->punc->AddPunc(res->msg.c_str(), h->model()->GetLang());
+  if (!res->stamp.empty()) res->stamp_sents = pf::host::SentenceStamps(res->msg, res->stamp);
 }
 
 RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples, std::vector<long long> seg_b,
@@ -128,6 +138,7 @@ RecogResult* RunSegments(OfflineHandle* h, const short* pcm, long long n_samples
     }
   }
   pf::host::StitchSegments(msgs, starts, asr->GetLang(), &res->msg, &res->stamp);
+  FinishResult(h, res);
   return res;
 }
 
@@ -145,6 +156,18 @@ float ReadVadThreshold(const std::string& vad_dir, float dflt) {
     if (v > 0.f) return v;
   }
   return dflt;
+}
+
+bool InitPunc(OfflineHandle* h, const std::map<std::string, std::string>& model_path, int device) {
+  auto pd = model_path.find("punc-dir");
+  if (pd == model_path.end() || pd->second.empty()) return true;
+  h->punc.reset(new funasr_b200::CTTransformerB200(device, ToInt(model_path, "punc-max-tokens", 0)));
+  std::string err;
+  if (!h->punc->Init(pd->second, &err)) {
+    fprintf(stderr, "FunOfflineInit: punc-dir %s: %s\n", pd->second.c_str(), err.c_str());
+    return false;
+  }
+  return true;
 }
 
 bool InitVad(OfflineHandle* h, const std::map<std::string, std::string>& model_path, int device) {
@@ -186,7 +209,7 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
       return nullptr;
     }
     h->pool->SetBatchSize(batch_size);
-    if (!InitVad(h.get(), model_path, devices[0])) return nullptr;
+    if (!InitVad(h.get(), model_path, devices[0]) || !InitPunc(h.get(), model_path, devices[0])) return nullptr;
     if (ToInt(model_path, "micro-batch-us", 0) > 0) {
       funasr_b200::MicroBatcherOptions o;
       o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
@@ -203,7 +226,8 @@ FUNASR_HANDLE FunOfflineInit(std::map<std::string, std::string>& model_path, int
     return nullptr;
   }
   h->asr->SetBatchSize(batch_size);
-  if (!InitVad(h.get(), model_path, devices.size() == 1 ? devices[0] : ToInt(model_path, "device", 0))) return nullptr;
+  const int dev0 = devices.size() == 1 ? devices[0] : ToInt(model_path, "device", 0);
+  if (!InitVad(h.get(), model_path, dev0) || !InitPunc(h.get(), model_path, dev0)) return nullptr;
   if (ToInt(model_path, "micro-batch-us", 0) > 0) {
     funasr_b200::MicroBatcherOptions o;
     o.max_wait_us = ToInt(model_path, "micro-batch-us", 0);
@@ -409,6 +433,42 @@ const char* FunASRGetTpassResult(FUNASR_RESULT result, int) { return result ? ((
 const int FunASRGetRetNumber(FUNASR_RESULT result) { return result ? 1 : 0; }
 void FunASRFreeResult(FUNASR_RESULT result) { delete (RecogResult*)result; }
 const float FunASRGetRetSnippetTime(FUNASR_RESULT result) { return result ? ((RecogResult*)result)->snippet_time : 0.0f; }
+
+// ---- punctuation API (funasrruntime.h:92-96) ----
+namespace {
+struct PuncResult {  // FUNASR_PUNC_RESULT, commonfunc.h
+  std::string msg;
+  std::vector<std::string> arr_cache;
+};
+}  // namespace
+
+FUNASR_HANDLE CTTransformerInit(std::map<std::string, std::string>& model_path, int thread_num, PUNC_TYPE type) {
+  (void)thread_num;
+  if (type != PUNC_OFFLINE) { fprintf(stderr, "CTTransformerInit: the online (realtime) punctuation model stays on the reference host path\n"); return nullptr; }
+  auto it = model_path.find("punc-dir");
+  if (it == model_path.end()) { fprintf(stderr, "CTTransformerInit: punc-dir missing\n"); return nullptr; }
+  std::unique_ptr<funasr_b200::CTTransformerB200> p(new funasr_b200::CTTransformerB200(ToInt(model_path, "device", 0), ToInt(model_path, "punc-max-tokens", 0)));
+  std::string err;
+  if (!p->Init(it->second, &err)) { fprintf(stderr, "CTTransformerInit: %s\n", err.c_str()); return nullptr; }
+  return (funasr_b200::PuncModel*)p.release();
+}
+
+FUNASR_RESULT CTTransformerInfer(FUNASR_HANDLE handle, const char* sz_sentence, FUNASR_MODE, QM_CALLBACK, PUNC_TYPE type, FUNASR_RESULT pre_result) {
+  funasr_b200::PuncModel* punc = (funasr_b200::PuncModel*)handle;
+  if (!punc) return nullptr;
+  if (type == PUNC_OFFLINE) {
+    PuncResult* r = new PuncResult;
+    r->msg = punc->AddPunc(sz_sentence);
+    return r;
+  }
+  PuncResult* r = pre_result ? (PuncResult*)pre_result : new PuncResult;   // funasrruntime.cpp:193-198
+  r->msg = punc->AddPunc(sz_sentence, r->arr_cache);
+  return r;
+}
+
+const char* CTTransformerGetResult(FUNASR_RESULT result, int) { return result ? ((PuncResult*)result)->msg.c_str() : nullptr; }
+void CTTransformerFreeResult(FUNASR_RESULT result) { delete (PuncResult*)result; }
+void CTTransformerUninit(FUNASR_HANDLE handle) { delete (funasr_b200::PuncModel*)handle; }
 
 FUNASR_DEC_HANDLE FunASRWfstDecoderInit(FUNASR_HANDLE, int, float, float, float) { return nullptr; }
 void FunASRWfstDecoderUninit(FUNASR_DEC_HANDLE) {}

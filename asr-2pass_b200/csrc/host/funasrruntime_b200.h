@@ -21,6 +21,7 @@ typedef void* FUNASR_DEC_HANDLE;
 
 typedef enum { RASR_NONE = -1, RASRM_CTC_GREEDY_SEARCH = 0, RASRM_CTC_RPEFIX_BEAM_SEARCH = 1, RASRM_ATTENSION_RESCORING = 2 } FUNASR_MODE;
 typedef enum { ASR_OFFLINE = 0, ASR_ONLINE = 1, ASR_TWO_PASS = 2 } ASR_TYPE;
+typedef enum { PUNC_OFFLINE = 0, PUNC_ONLINE = 1 } PUNC_TYPE;   // funasrruntime.h:52-55
 typedef void (*QM_CALLBACK)(int cur_step, int n_total);
 
 // Plain-model API (funasrruntime.h:60-78): the handle is the funasr::Model itself, and FunASRInfer / FunASRInferBuffer feed
@@ -58,6 +59,15 @@ const char* FunASRGetTpassResult(FUNASR_RESULT result, int n_index);
 const int FunASRGetRetNumber(FUNASR_RESULT result);
 void FunASRFreeResult(FUNASR_RESULT result);
 const float FunASRGetRetSnippetTime(FUNASR_RESULT result);
+
+// PUNC (funasrruntime.h:92-96): model_path["punc-dir"] = <dir>/{punc.b200pf, tokens.json, punc_list.json}; extra keys "device",
+// "punc-max-tokens".  Only PUNC_OFFLINE (CTTransformer) is built; the realtime variant (CTTransformerOnline) is not.
+FUNASR_HANDLE CTTransformerInit(std::map<std::string, std::string>& model_path, int thread_num, PUNC_TYPE type = PUNC_OFFLINE);
+FUNASR_RESULT CTTransformerInfer(FUNASR_HANDLE handle, const char* sz_sentence, FUNASR_MODE mode, QM_CALLBACK fn_callback,
+                                 PUNC_TYPE type = PUNC_OFFLINE, FUNASR_RESULT pre_result = nullptr);
+const char* CTTransformerGetResult(FUNASR_RESULT result, int n_index);
+void CTTransformerFreeResult(FUNASR_RESULT result);
+void CTTransformerUninit(FUNASR_HANDLE handle);
 
 // The decoder handle is only meaningful with an LM; greedy search needs none (funasrruntime.cpp:836-894).
 FUNASR_DEC_HANDLE FunASRWfstDecoderInit(FUNASR_HANDLE handle, int asr_type, float glob_beam, float lat_beam, float am_scale);

@@ -104,6 +104,22 @@ int b200pf_host_offline_infer_buffer_vad(void* h, const char* buf, int n_bytes, 
   FunASRFreeResult(r);
   return n;
 }
+void* b200pf_host_offline_init_kv(const char* const* keys, const char* const* values, int n, int batch_size) {
+  std::map<std::string, std::string> mp;
+  for (int i = 0; i < n; ++i) mp[keys[i]] = values[i];
+  return FunOfflineInit(mp, 1, true, batch_size);
+}
+int b200pf_host_offline_infer_full(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
+                                   char* stamp, int stamp_cap, char* stamp_sents, int sents_cap) {
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  FUNASR_RESULT r = FunOfflineInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr, hw, 16000, "pcm", true, vad_tail_sil, vad_max_len);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  if (stamp) CopyOut(FunASRGetStamp(r), stamp, stamp_cap);
+  if (stamp_sents) CopyOut(FunASRGetStampSents(r), stamp_sents, sents_cap);
+  FunASRFreeResult(r);
+  return n;
+}
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign) {
   std::vector<int> a;
   funasr_b200::PartitionSegments(len, n, n_dev, &a);
@@ -169,6 +185,9 @@ int b200pf_host_pack_hotwords(const char* const* tokens, int n_tokens, const cha
   memcpy(ids, m.data(), m.size() * sizeof(int32_t));
   memcpy(lengths, l.data(), l.size() * sizeof(int32_t));
   return (int)l.size();
+}
+int b200pf_host_sentence_stamps(const char* text, const char* stamp, char* out, int cap) {
+  return CopyOut(pf::host::SentenceStamps(text ? text : "", stamp ? stamp : ""), out, cap);
 }
 // ---- punctuation (CTTransformer mirror) ----
 int b200pf_host_punc_tokenize(const char* const* tokens, int n_tokens, const char* text, int32_t* ids, int cap) {

@@ -1,6 +1,8 @@
 #include "text.h"
 
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace pf {
@@ -288,6 +290,116 @@ void StitchSegments(const std::vector<std::string>& msgs, const std::vector<floa
     acc.erase(acc.size() - 1);
     *stamp = acc + "]";
   }
+}
+
+
+namespace {
+// "[[b,e],[b,e]]" -> pairs; anything that is not a pair empties the result (ParseTimestamps, util.cpp:268-297)
+std::vector<std::pair<int, int>> ParseStampList(const std::string& str) {
+  std::vector<std::pair<int, int>> out;
+  size_t pos = str.empty() ? 0 : 1;   // the opening '['
+  while (pos < str.size()) {
+    size_t close = str.find(']', pos);
+    const bool had_delim = close != std::string::npos;
+    if (!had_delim) close = str.size();
+    std::string seg = str.substr(pos, close - pos);
+    if (!seg.empty()) seg.erase(0, 1);   // its own '['
+    std::vector<int> nums;
+    size_t a = 0;
+    while (a <= seg.size() && !seg.empty()) {
+      size_t b = seg.find(',', a);
+      if (b == std::string::npos) b = seg.size();
+      nums.push_back(atoi(seg.substr(a, b - a).c_str()));
+      a = b + 1;
+      if (b == seg.size()) break;
+    }
+    if (nums.size() != 2) return std::vector<std::pair<int, int>>();
+    out.emplace_back(nums[0], nums[1]);
+    pos = had_delim ? close + 2 : str.size();   // the ']' and the ',' (or the closing ']') after it
+  }
+  return out;
+}
+
+// every BYTE of s occurs among the bytes of "，。？、,?" (TimestampIsPunctuation(const std::string&), util.cpp:257-266)
+bool AllPunctuationBytes(const std::string& s) {
+  static const std::string set = "\xEF\xBC\x8C\xE3\x80\x82\xEF\xBC\x9F\xE3\x80\x81,?";
+  for (char c : s)
+    if (set.find(c) == std::string::npos) return false;
+  return true;
+}
+
+bool PunctuationCodePoint(uint32_t u) {   // TimestampIsPunctuation(U16CHAR_T&), util.cpp:307-318
+  if (u == 0x26 || u == 0x27 || u == 0x2D) return false;
+  return (u >= 0x21 && u <= 0x2F) || (u >= 0x3A && u <= 0x40) || (u >= 0x5B && u <= 0x60) || (u >= 0x7B && u <= 0x7E) ||
+         (u >= 0x2000 && u <= 0x206F) || (u >= 0x3000 && u <= 0x303F);
+}
+
+// CJK characters, digits and punctuation marks stand alone, other characters accumulate into words, spaces separate
+// (TimestampSplitChiEngCharacters, util.cpp:320-366)
+std::vector<std::string> SplitForStamps(const std::string& s) {
+  std::vector<std::string> out;
+  std::string word;
+  size_t i = 0;
+  while (i < s.size()) {
+    const unsigned char c = (unsigned char)s[i];
+    size_t n = 1;
+    uint32_t u = c;
+    if ((c & 0xF0) == 0xE0 && i + 2 < s.size()) { n = 3; u = ((c & 0x0F) << 12) | (((unsigned char)s[i + 1] & 0x3F) << 6) | ((unsigned char)s[i + 2] & 0x3F); }
+    else if ((c & 0xE0) == 0xC0 && i + 1 < s.size()) { n = 2; u = ((c & 0x1F) << 6) | ((unsigned char)s[i + 1] & 0x3F); }
+    const std::string ch = s.substr(i, n);
+    i += n;
+    const bool cjk = (u >= 0x4e00 && u <= 0x9fff) || (u >= 0x3400 && u <= 0x4dff);
+    if (cjk || (u >= '0' && u <= '9') || PunctuationCodePoint(u)) {
+      if (!word.empty()) { out.push_back(word); word.clear(); }
+      out.push_back(ch);
+    } else if (u == 0x20) {
+      if (!word.empty()) { out.push_back(word); word.clear(); }
+    } else {
+      word += ch;
+    }
+  }
+  if (!word.empty()) out.push_back(word);
+  return out;
+}
+
+std::string StampListJson(const std::vector<std::pair<int, int>>& v) {
+  if (v.empty()) return "[]";
+  std::string s = "[";
+  for (size_t i = 0; i < v.size(); ++i) {
+    s += "[" + std::to_string(v[i].first) + "," + std::to_string(v[i].second) + "]";
+    if (i + 1 < v.size()) s += ",";
+  }
+  return s + "]";
+}
+}  // namespace
+
+std::string SentenceStamps(const std::string& text, const std::string& stamp) {
+  const std::vector<std::string> chars = SplitForStamps(text);
+  const std::vector<std::pair<int, int>> ts = ParseStampList(stamp);
+  size_t it = 0;
+  int start = -1, end = -1;
+  std::string seg_text, out;
+  std::vector<std::pair<int, int>> seg;
+  auto emit = [&](const std::string& punc) {
+    if (!seg.empty()) { start = seg.front().first; end = seg.back().second; }
+    out += "{\"text_seg\":\"" + seg_text + "\",\"punc\":\"" + punc + "\",\"start\":" + std::to_string(start) + ",\"end\":" + std::to_string(end) +
+           ",\"ts_list\":" + StampListJson(seg) + "}";
+  };
+  for (size_t k = 0; k < chars.size(); ++k) {
+    if (AllPunctuationBytes(chars[k])) {
+      emit(chars[k]);
+      if (k + 1 != chars.size()) out += ",";
+      seg_text.clear();
+      seg.clear();
+      start = 0;
+      end = 0;
+    } else if (it < ts.size()) {
+      seg_text += seg_text.empty() ? chars[k] : " " + chars[k];
+      seg.push_back(ts[it++]);
+    }
+  }
+  if (!seg.empty()) emit("");
+  return "[" + out + "]";
 }
 
 }  // namespace host

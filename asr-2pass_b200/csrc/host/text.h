@@ -5,6 +5,7 @@
 //   TimestampFromPeaks         TimestampOnnx            onnxruntime/src/util.cpp:838-963
 //   MergeWithStamps            PostProcess              onnxruntime/src/util.cpp:720-836
 //   StitchSegments             FunOfflineInferBuffer    onnxruntime/src/funasrruntime.cpp:291-316
+//   SentenceStamps             TimestampSentence        onnxruntime/src/util.cpp:569-637
 #pragma once
 #include <string>
 #include <utility>
@@ -46,6 +47,10 @@ std::string MergeWithStamps(const std::vector<std::string>& pieces, const std::v
 // Joins per-segment Forward() strings (original time order) into the final text and "[[b,e],...]" in ms.
 void StitchSegments(const std::vector<std::string>& msgs, const std::vector<float>& start_s, const std::string& lang,
                     std::string* text, std::string* stamp);
+
+// Punctuated text + "[[b,e],...]" (ms) -> the stamp_sents JSON array: one {"text_seg","punc","start","end","ts_list"} object per
+// punctuation-terminated sentence, plus a last one with "punc":"" for text after the final punctuation mark (BMP text).
+std::string SentenceStamps(const std::string& text, const std::string& stamp);
 
 }  // namespace host
 }  // namespace pf

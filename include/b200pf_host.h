@@ -36,6 +36,12 @@ int b200pf_host_offline_vad_cut(void* h, const int16_t* pcm, int64_t n_samples, 
 /* FunOfflineInferBuffer with the reference's vad_tail_sil / vad_max_len arguments (funasrruntime.h:101-105); text and stamp out. */
 int b200pf_host_offline_infer_buffer_vad(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
                                          char* stamp, int stamp_cap);
+/* FunOfflineInit with the reference's key/value map (com-define.h: "model-dir", "vad-dir", "punc-dir", ... plus the B200 keys
+ * "device", "devices", "max-rows", "max-segments", "micro-batch-us", "vad-speech-noise-thres", "punc-max-tokens"). */
+void* b200pf_host_offline_init_kv(const char* const* keys, const char* const* values, int n, int batch_size);
+/* FunOfflineInferBuffer -> FunASRGetResult / FunASRGetStamp / FunASRGetStampSents (stamp and stamp_sents may be NULL). */
+int b200pf_host_offline_infer_full(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
+                                   char* stamp, int stamp_cap, char* stamp_sents, int sents_cap);
 /* The pool's longest-processing-time-first assignment of segments (sample counts) to n_dev queues; host arithmetic only. */
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign);
 /* Segments decoded per device so far; returns the number of devices (0 for a single-GPU handle). */
@@ -55,6 +61,8 @@ int b200pf_host_offline_infer_buffer_hw(void* h, const char* buf, int n_bytes, i
 /* CompileHotwordEmbedding(handle, hotwords) (funasrruntime.h:118; Paraformer::CompileHotwordEmbedding, paraformer.cpp:592-693):
  * writes rows of `dim` floats, returns the row count (hotwords kept + the blank row) or -1. */
 int b200pf_host_compile_hotwords(void* h_offline, const char* hotwords, float* out, int cap_rows, int dim);
+/* TimestampSentence (util.cpp:569-637): punctuated text + "[[b,e],...]" (ms) -> the stamp_sents JSON array FunASRGetStampSents returns. */
+int b200pf_host_sentence_stamps(const char* text, const char* stamp, char* out, int cap);
 /* ---- punctuation: funasr::CTTransformer mirror (csrc/host/punc_b200.h) -----------------------
  * CTokenizer::Tokenize without jieba (tokenizer.cpp:312-365): text -> token ids (lower-cased lookup, <unk> otherwise).  No GPU. */
 int b200pf_host_punc_tokenize(const char* const* tokens, int n_tokens, const char* text, int32_t* ids, int cap);

@@ -68,6 +68,12 @@ int ref_greedy_with_stamps(void* v, const int* ids, int n, const float* us_alpha
   return CopyOut(funasr::PostProcess(raw_char, timestamp_list), out, cap);
 }
 
+// funasr::TimestampSentence (util.cpp:569-637): punctuated text + "[[b,e],...]" -> the stamp_sents JSON array
+int ref_timestamp_sentence(const char* text, const char* stamp, char* out, int cap) {
+  std::string t(text), s(stamp);
+  return CopyOut(funasr::TimestampSentence(t, s), out, cap);
+}
+
 // ---- ParaformerOnline::GetPosEmb / CifSearch, called on an object whose constructor (ORT sessions) is bypassed --------
 // Zero-filled storage is a valid state for the std::vector members of libstdc++; the scalar members the two functions
 // read are set explicitly.  chunk_size {0, T, 0} + is_last_chunk reproduces the offline predictor: no alpha is zeroed

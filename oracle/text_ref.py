@@ -35,8 +35,17 @@ def lib():
         L.ref_pos_emb.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int]
         L.ref_e2e_vad_offline.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.c_int]
         L.ref_e2e_vad_online.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_int), C.c_int]
+        L.ref_timestamp_sentence.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         _lib = L
     return _lib
+
+
+def timestamp_sentence(text, stamp):
+    """funasr::TimestampSentence (util.cpp:569-637)."""
+    buf = C.create_string_buffer(64 * (len(text.encode("utf-8")) + len(stamp)) + 4096)
+    n = lib().ref_timestamp_sentence(text.encode("utf-8"), stamp.encode("utf-8"), buf, len(buf))
+    assert n >= 0
+    return buf.value.decode("utf-8", "replace")
 
 
 def e2e_vad(sil_prob, max_end_sil=800, max_seg_ms=15000, thres=0.8, chunk_frames=None):

@@ -187,8 +187,22 @@ def main():
         vg["opts_%d" % k] = np.asarray(opts, np.float64)
         vg["segs_%d" % k] = T.e2e_vad(p, opts[0], opts[1], opts[2], chunk_frames=100)
     np.savez_compressed(os.path.join(HERE, "vad_segments_golden.npz"), **vg)
+    # TimestampSentence (util.cpp:569-637)
+    sent_cases = []
+    sr = np.random.default_rng(77)
+    alphabet = list("一丁七万丈三上下不与") + ["，", "。", "？", "、", ",", "?", "!", ".", " ", "a", "b", "hello", "World", "3", "9", "'", "-", "&", "　", "é", "<unk>"]
+    for k in range(300):
+        text = "".join(alphabet[int(sr.integers(len(alphabet)))] for _ in range(int(sr.integers(0, 40))))
+        t, pairs = 0, []
+        for _ in range(int(sr.integers(0, 45))):
+            a = t + int(sr.integers(0, 300))
+            t = a + int(sr.integers(10, 500))
+            pairs.append("[%d,%d]" % (a, t))
+        stamp = "" if k % 50 == 0 else ("[]" if k % 77 == 0 else "[" + ",".join(pairs) + "]")
+        sent_cases.append(dict(text=text, stamp=stamp, out=T.timestamp_sentence(text, stamp)))
     with open(os.path.join(HERE, "text_golden.json"), "w", encoding="utf-8") as f:
-        json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases),
+        json.dump(dict(source="reference onnxruntime/src/{vocab,util}.cpp compiled in place (oracle/Makefile ref)", text=text_cases, stamps=stamp_cases,
+                       sents=sent_cases),
                   f, ensure_ascii=False)
     make_am_golden(synth)
     make_punc_golden(synth)

@@ -107,3 +107,30 @@ def test_stitch_matches_oracle(capi):
             starts.append(float(np.float32(rng.uniform(0, 100))))
         for lang in ("zh-cn", "en-bpe"):
             assert capi.host_stitch(msgs, starts, lang) == P.stitch_offline(msgs, starts, lang)
+
+
+def test_sentence_stamps_match_reference_golden(capi):
+    """pf::host::SentenceStamps against strings from the reference's compiled TimestampSentence (util.cpp:569-637)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_golden.json"), encoding="utf-8"))
+    assert len(g["sents"]) >= 200
+    for c in g["sents"]:
+        assert capi.host_sentence_stamps(c["text"], c["stamp"]) == c["out"], c["text"]
+
+
+def test_sentence_stamps_match_live_reference_when_built(capi):
+    from oracle import text_ref as T
+    if not T.available():
+        pytest.skip("oracle/_ref/libfunasr_text_ref.so not built (needs /root/reference)")
+    rng = np.random.default_rng(0)
+    alphabet = list("一丁七万丈三上下不与") + ["，", "。", "？", "、", ",", "?", "!", ".", " ", "a", "b", "hello", "World", "3", "9", "'", "-", "&", "　", "é", "ü"]
+    for k in range(2000):
+        text = "".join(alphabet[int(rng.integers(len(alphabet)))] for _ in range(int(rng.integers(0, 40))))
+        t, pairs = 0, []
+        for _ in range(int(rng.integers(0, 45))):
+            a = t + int(rng.integers(0, 300))
+            t = a + int(rng.integers(10, 500))
+            pairs.append("[%d,%d]" % (a, t))
+        stamp = "" if k % 50 == 0 else ("[]" if k % 77 == 0 else "[" + ",".join(pairs) + "]")
+        assert capi.host_sentence_stamps(text, stamp) == T.timestamp_sentence(text, stamp), (text, stamp)

@@ -221,3 +221,35 @@ def test_host_addpunc_end_to_end(capi, synth, gpu, tmp_path):
     assert host.add_punc("", "zh-cn") == ""
     host.close()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_offline_shim_vad_asr_punc_chain(capi, synth, gpu, tmp_path):
+    """FunOfflineInit with vad-dir + model-dir + punc-dir: one FunOfflineInferBuffer call runs VAD cut -> batched Paraformer ->
+    stitching -> punctuation -> per-sentence stamps, the reference's offline request path (funasrruntime.cpp:208-340)."""
+    vd, md, pd = str(tmp_path / "vad"), str(tmp_path / "am"), str(tmp_path / "punc")
+    synth.write_synthetic_vad_dir(vd, seed=0)
+    cfg, W, means, vars_, am_toks = synth.write_synthetic_model_dir(md, dict(n_enc=2, n_dec=2, timestamp=1), seed=0, jitter_ln=True)
+    # the punctuation vocabulary must know the acoustic model's characters: reuse its CJK range (U+4E00...)
+    synth.write_synthetic_punc_dir(pd, dict(vocab=20000), seed=5)
+    parts = []
+    for i, (n_speech, n_sil) in enumerate([(48000, 24000), (80000, 40000), (160000, 32000)]):
+        parts += [synth.make_audio(n_speech, 70 + i), np.zeros(n_sil, np.int16)]
+    pcm = np.concatenate(parts)
+    eng = capi.VadEngine(vd, max_frames=20000)
+    p0, _, _, _ = eng.scores(pcm, np.array([0, len(pcm)], np.int64))
+    eng.close()
+    thres = float(np.clip(1.0 - 2.0 * np.median(p0), 0.05, 0.95))
+    base = {"vad-dir": vd, "vad-speech-noise-thres": "%.6f" % thres}
+    plain = capi.OfflineHandle(md, max_rows=8192, max_segments=256, batch_size=8, options=base)
+    full = capi.OfflineHandle(md, max_rows=8192, max_segments=256, batch_size=8, options=dict(base, **{"punc-dir": pd}))
+    punc = capi.HostPunc(pd)
+    t0, st0, ss0 = plain.infer_full(pcm, 500, 15000)
+    t1, st1, ss1 = full.infer_full(pcm, 500, 15000)
+    assert len(t0) > 0 and st0.startswith("[[") and st1 == st0
+    assert t1.replace(" ", "") == punc.add_punc(t0, "zh-cn").replace(" ", "") and t1 != t0
+    assert ss0 == capi.host_sentence_stamps(t0, st0) and ss1 == capi.host_sentence_stamps(t1, st1)
+    assert json.loads(ss1)[0]["ts_list"][0] == json.loads(st1)[0]
+    assert sum(len(s["ts_list"]) for s in json.loads(ss1)) <= len(json.loads(st1))
+    for h in (plain, full, punc):
+        h.close()
