@@ -296,9 +296,14 @@ def make_punc_tokens(vocab):
     n_latin = min(2000, max(8, vocab // 8))
     toks += [chr(0x4E00 + i) for i in range(min(20000, vocab - 1 - n_latin))]
     i = 0
-    while len(toks) < vocab:
-        a, b, c, d = i % 26, (i // 26) % 26, (i // 676) % 26, i // 17576
-        toks.append(chr(97 + a) + chr(97 + b) + (chr(97 + c) if i % 3 else "") + (str(d) if d else ""))
+    while len(toks) < vocab:                 # bijective base-26 words: a .. z, aa, ab, ...
+        n, w = i, ""
+        while True:
+            w = chr(97 + n % 26) + w
+            n = n // 26 - 1
+            if n < 0:
+                break
+        toks.append(w)
         i += 1
     assert len(toks) == vocab and len(set(toks)) == vocab
     return toks
