@@ -168,13 +168,17 @@ void PuncJob::Consume(const int32_t* punc_in, int n) {
     new_str_.push_back(in_str_[k]);
     if (punc[k] != kNotPunc) new_str_.push_back(tok_->Id2Punc(punc[k]));
   }
-  sent_out_ = new_str_;
-  if (last && !new_str_.empty()) {
-    const std::string& tail = new_str_.back();
-    if (tail == tok_->Id2Punc(kComma) || tail == tok_->Id2Punc(kDun)) {
-      sent_out_.back() = tok_->Id2Punc(kPeriod);
-    } else if (tail != tok_->Id2Punc(kPeriod) && tail != tok_->Id2Punc(kQuestion)) {
-      sent_out_.push_back(tok_->Id2Punc(kPeriod));
+  // the reference copies the whole output after every mini-sentence (NewSentenceOut = NewString, quadratic in the text length); only
+  // the copy made after the LAST one is ever read, and only that one gets the tail fix-up
+  if (last) {
+    sent_out_ = new_str_;
+    if (!new_str_.empty()) {
+      const std::string& tail = new_str_.back();
+      if (tail == tok_->Id2Punc(kComma) || tail == tok_->Id2Punc(kDun)) {
+        sent_out_.back() = tok_->Id2Punc(kPeriod);
+      } else if (tail != tok_->Id2Punc(kPeriod) && tail != tok_->Id2Punc(kQuestion)) {
+        sent_out_.push_back(tok_->Id2Punc(kPeriod));
+      }
     }
   }
   pos_ += kMiniSentence;

@@ -217,6 +217,11 @@ struct b200pf_punc {
   float *x = nullptr, *qkv = nullptr, *logits = nullptr;
   __nv_bfloat16 *h = nullptr, *ctx = nullptr, *f1 = nullptr;
   int* d_punc = nullptr;
+  // pinned staging: one upload (ids | row info | tiles) and one download per call, no pageable-memory bounce
+  uint8_t* h_in = nullptr;
+  uint8_t* d_in = nullptr;
+  int* h_punc = nullptr;
+  size_t in_bytes = 0;
   int64_t launches = 0;
 };
 
@@ -255,7 +260,7 @@ int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_
   cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, device);
   PCK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking), "cudaStreamCreate");
   bool ok = true;
-  auto fail_cleanup = [&]() { for (void* a : p->allocs) cudaFree(a); cudaStreamDestroy(p->stream); };
+  auto fail_cleanup = [&]() { for (void* a : p->allocs) cudaFree(a); cudaFreeHost(p->h_in); cudaFreeHost(p->h_punc); cudaStreamDestroy(p->stream); };
   auto dalloc = [&](size_t bytes) -> void* {
     void* d = nullptr;
     if (!ok) return nullptr;
@@ -333,8 +338,12 @@ int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_
     p->pe = (float*)up(pe.data(), pe.size() * 4);
   }
   const size_t R = (size_t)p->max_tokens;
-  p->d_ids = (int*)dalloc(R * 4); p->d_row_info = (int2*)dalloc(R * 8);
-  p->d_tiles = (int4*)dalloc((R / P_QTILE + P_MAX_SEQ + 1) * 16);
+  const size_t max_tiles = R / P_QTILE + P_MAX_SEQ + 1;
+  p->in_bytes = R * 4 + R * 8 + max_tiles * 16 + 1024;
+  p->d_in = (uint8_t*)dalloc(p->in_bytes);
+  if (ok && (cudaMallocHost((void**)&p->h_in, p->in_bytes) != cudaSuccess || cudaMallocHost((void**)&p->h_punc, R * 4) != cudaSuccess)) {
+    ok = false; err = "cudaMallocHost failed (punctuation staging)"; cudaGetLastError();
+  }
   p->x = (float*)dalloc(R * D * 4); p->qkv = (float*)dalloc(R * 3 * D * 4); p->logits = (float*)dalloc(R * p->n_out_p * 4);
   p->h = (__nv_bfloat16*)dalloc(R * Dp * 2); p->ctx = (__nv_bfloat16*)dalloc(R * Dp * 2); p->f1 = (__nv_bfloat16*)dalloc(R * p->Fp * 2);
   p->d_punc = (int*)dalloc(R * 4);
@@ -350,6 +359,8 @@ void b200pf_punc_destroy(b200pf_punc* p) {
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
   for (void* a : p->allocs) cudaFree(a);
+  cudaFreeHost(p->h_in);
+  cudaFreeHost(p->h_punc);
   cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -373,22 +384,32 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
   if (rows < 0) { set_error("offsets not monotone"); return B200PF_ERR_INVALID; }
   if (rows > p->max_tokens) { set_error("tokens exceed the punctuation engine's capacity"); return B200PF_ERR_CAPACITY; }
   if (rows == 0) return 0;
-  std::vector<int2> info(rows);
-  std::vector<int4> tiles;
+  PCK(cudaSetDevice(p->device), "cudaSetDevice");
+  std::lock_guard<std::mutex> lock(p->mu);
+  // staging layout: ids [rows] | row info [rows] | tiles [n_tiles], 16-byte aligned sections
+  const size_t off_info = ((size_t)rows * 4 + 15) & ~size_t(15), off_tiles = (off_info + (size_t)rows * 8 + 15) & ~size_t(15);
+  int* h_ids = (int*)p->h_in;
+  int2* info = (int2*)(p->h_in + off_info);
+  int4* tiles = (int4*)(p->h_in + off_tiles);
+  const size_t max_tiles = (p->in_bytes - off_tiles) / 16;
+  size_t n_tiles = 0;
+  memcpy(h_ids, ids + base, (size_t)rows * 4);
   for (int i = 0; i < n_seq; ++i) {
     const int T = offsets[i + 1] - offsets[i], r0 = offsets[i] - base;
     if (T < 0) { set_error("offsets not monotone"); return B200PF_ERR_INVALID; }
     if (T > P_MAX_POS) { set_error("a sequence is longer than the position table (4096 tokens)"); return B200PF_ERR_CAPACITY; }
     for (int t = 0; t < T; ++t) info[r0 + t] = make_int2(t, T);
-    for (int q0 = 0; q0 < T; q0 += P_QTILE) tiles.push_back(make_int4(r0 + q0, T - q0 < P_QTILE ? T - q0 : P_QTILE, r0, T));
+    for (int q0 = 0; q0 < T; q0 += P_QTILE) {
+      if (n_tiles >= max_tiles) { set_error("too many attention tiles"); return B200PF_ERR_CAPACITY; }
+      tiles[n_tiles++] = make_int4(r0 + q0, T - q0 < P_QTILE ? T - q0 : P_QTILE, r0, T);
+    }
   }
-  PCK(cudaSetDevice(p->device), "cudaSetDevice");
-  std::lock_guard<std::mutex> lock(p->mu);
   cudaStream_t s = p->stream;
   const int D = p->D, Dp = p->Dp;
-  PCK(cudaMemcpyAsync(p->d_ids, ids + base, (size_t)rows * 4, cudaMemcpyHostToDevice, s), "H2D ids");
-  PCK(cudaMemcpyAsync(p->d_row_info, info.data(), (size_t)rows * 8, cudaMemcpyHostToDevice, s), "H2D rows");
-  PCK(cudaMemcpyAsync(p->d_tiles, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s), "H2D tiles");
+  p->d_ids = (int*)p->d_in;
+  p->d_row_info = (int2*)(p->d_in + off_info);
+  p->d_tiles = (int4*)(p->d_in + off_tiles);
+  PCK(cudaMemcpyAsync(p->d_in, p->h_in, off_tiles + n_tiles * 16, cudaMemcpyHostToDevice, s), "H2D punctuation input");
   int rc = launch_kernel(punc_embed_kernel, dim3(rows), dim3(128), 0, s, (const int*)p->d_ids, (const int2*)p->d_row_info, rows, (const float*)p->embed,
                          p->vocab, (const float*)p->pe, D, sqrtf((float)D), p->x);
   if (rc) return check_cuda((cudaError_t)rc, "punc embed");
@@ -410,7 +431,7 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
     const PLayer& Ly = p->layers[l];
     if ((rc = ln(Ly.ln1_g, Ly.ln1_b))) return check_cuda((cudaError_t)rc, "punc ln1");
     if ((rc = gemm(p->h, Dp, Ly.qkv, 3 * D, 0, nullptr, 0, p->qkv, 3 * D, nullptr))) return check_cuda((cudaError_t)rc, "punc gemm qkv");
-    rc = launch_kernel(punc_attn_kernel, dim3((unsigned)tiles.size(), p->H), dim3(128), 0, s, (const float*)p->qkv, (const int4*)p->d_tiles, D, p->dk, scale,
+    rc = launch_kernel(punc_attn_kernel, dim3((unsigned)n_tiles, p->H), dim3(128), 0, s, (const float*)p->qkv, (const int4*)p->d_tiles, D, p->dk, scale,
                        p->ctx, Dp);
     if (rc) return check_cuda((cudaError_t)rc, "punc attention");
     // x += v + fsmn(v): after the attention kernel has been queued (it does not read x), before the out-projection accumulates into x
@@ -428,10 +449,11 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
   rc = launch_kernel(punc_argmax_kernel, dim3((rows + 255) / 256), dim3(256), 0, s, (const float*)p->logits, rows, p->n_out_p, p->n_punc - 1, p->d_punc);
   if (rc) return check_cuda((cudaError_t)rc, "punc argmax");
   ++n_launch;
-  PCK(cudaMemcpyAsync(punc_out + base, p->d_punc, (size_t)rows * 4, cudaMemcpyDeviceToHost, s), "D2H punc");
+  PCK(cudaMemcpyAsync(p->h_punc, p->d_punc, (size_t)rows * 4, cudaMemcpyDeviceToHost, s), "D2H punc");
   std::vector<float> lg;
   if (logits_out) { lg.resize((size_t)rows * p->n_out_p); PCK(cudaMemcpyAsync(lg.data(), p->logits, lg.size() * 4, cudaMemcpyDeviceToHost, s), "D2H logits"); }
   PCK(cudaStreamSynchronize(s), "punc forward");
+  memcpy(punc_out + base, p->h_punc, (size_t)rows * 4);
   if (logits_out)
     for (int r = 0; r < rows; ++r) memcpy(logits_out + (size_t)(base + r) * p->n_punc, lg.data() + (size_t)r * p->n_out_p, (size_t)p->n_punc * 4);
   p->launches += n_launch;
