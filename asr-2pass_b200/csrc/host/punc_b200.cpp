@@ -252,7 +252,7 @@ std::vector<std::string> CTTransformerB200::AddPuncBatch(const std::vector<std::
   for (const std::string& t : texts) jobs.emplace_back(&tok_, t.c_str(), language);
   std::vector<int32_t> ids, offs, punc;
   std::vector<size_t> who;
-  size_t next = 0;   // jobs are admitted in order; a round carries as many as fit the engine
+  // a round carries the current mini-sentence of as many active requests as fit the engine, in request order
   for (;;) {
     ids.clear(); offs.assign(1, 0); who.clear();
     for (size_t j = 0; j < jobs.size(); ++j) {
@@ -266,7 +266,6 @@ std::vector<std::string> CTTransformerB200::AddPuncBatch(const std::vector<std::
       offs.push_back((int32_t)ids.size());
       who.push_back(j);
     }
-    (void)next;
     if (who.empty()) break;
     punc.assign(ids.size(), 0);
     if (b200pf_punc_infer(engine_, ids.data(), offs.data(), (int)who.size(), punc.data(), nullptr) != 0) {
