@@ -122,7 +122,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_mb_create", "b200pf_host_mb_create_mock", "b200pf_host_mb_destroy", "b200pf_host_mb_forward",
                 "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
                 "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords", "b200pf_host_punc_tokenize",
-                "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_add",
+                "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_rounds", "b200pf_host_punc_add",
                 "b200pf_host_punc_add_batch", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
                 "b200pf_host_offline_infer_full"]
 
@@ -178,6 +178,8 @@ def host_lib():
     H.b200pf_host_punc_create.restype = C.c_void_p
     H.b200pf_host_punc_destroy.argtypes = [C.c_void_p]
     H.b200pf_host_punc_destroy.restype = None
+    H.b200pf_host_punc_rounds.argtypes = [C.c_void_p]
+    H.b200pf_host_punc_rounds.restype = C.c_longlong
     H.b200pf_host_punc_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     H.b200pf_host_punc_add_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, c_i32p]
     H.b200pf_host_mb_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -485,6 +487,10 @@ class HostPunc:
             self.close()
         except Exception:
             pass
+
+    @property
+    def rounds(self):
+        return int(host_lib().b200pf_host_punc_rounds(self.h))
 
     def add_punc(self, text, lang="zh-cn"):
         raw = text.encode("utf-8")

@@ -225,6 +225,7 @@ void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens) 
   if (!p->Init(punc_dir, &err)) { fprintf(stderr, "b200pf_host_punc_create: %s\n", err.c_str()); return nullptr; }
   return p.release();
 }
+long long b200pf_host_punc_rounds(void* h) { return h ? ((funasr_b200::CTTransformerB200*)h)->rounds() : 0; }
 void b200pf_host_punc_destroy(void* h) { delete (funasr_b200::CTTransformerB200*)h; }
 int b200pf_host_punc_add(void* h, const char* text, const char* lang, char* out, int cap) {
   if (!h) return -1;

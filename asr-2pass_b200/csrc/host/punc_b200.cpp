@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <sstream>
 
 namespace funasr_b200 {
@@ -213,8 +214,25 @@ std::string AddPuncWith(const PuncTokenizer& tok, const char* text, const std::s
   return job.Result();
 }
 
+struct CTTransformerB200::Ticket {
+  Ticket(const PuncTokenizer* tok, const char* text, const std::string& language) : job(tok, text, language) {}
+  PuncJob job;
+  bool done = false, failed = false;
+};
+
 CTTransformerB200::~CTTransformerB200() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_work_.notify_all();
+  if (worker_.joinable()) worker_.join();   // finishes the jobs it still holds
   if (engine_) b200pf_punc_destroy(engine_);
+}
+
+long long CTTransformerB200::rounds() const {
+  std::lock_guard<std::mutex> lk(mu_);
+  return rounds_;
 }
 
 bool CTTransformerB200::Init(const std::string& punc_dir, std::string* err) {
@@ -231,6 +249,7 @@ bool CTTransformerB200::Init(const std::string& punc_dir, std::string* err) {
     return false;
   }
   tok_.Open(tokens, punc);
+  worker_ = std::thread(&CTTransformerB200::Run, this);
   return true;
 }
 
@@ -243,39 +262,81 @@ void CTTransformerB200::InitPunc(const std::string& punc_model, const std::strin
   }
 }
 
+// One engine call: the current mini-sentence of as many active jobs as fit, in arrival order; jobs that do not fit wait a round.
+void CTTransformerB200::RunRound(std::vector<Ticket*>* active) {
+  std::vector<int32_t> ids, offs(1, 0), punc;
+  std::vector<Ticket*> who;
+  for (Ticket* t : *active) {
+    const std::vector<int32_t>& in = t->job.Input();
+    if ((int)in.size() > max_tokens_) {
+      fprintf(stderr, "CTTransformerB200: a sentence cache outgrew the engine (%zu tokens)\n", in.size());
+      t->failed = true;
+      continue;
+    }
+    if ((int)(ids.size() + in.size()) > max_tokens_ || who.size() >= 16384) break;
+    ids.insert(ids.end(), in.begin(), in.end());
+    offs.push_back((int32_t)ids.size());
+    who.push_back(t);
+  }
+  if (who.empty()) return;
+  punc.assign(ids.size(), 0);
+  if (b200pf_punc_infer(engine_, ids.data(), offs.data(), (int)who.size(), punc.data(), nullptr) != 0) {
+    fprintf(stderr, "Error when run punc forword: %s\n", b200pf_last_error());   // the reference logs and answers "" (ct-transformer.cpp:197-201)
+    for (Ticket* t : who) t->failed = true;
+    return;
+  }
+  for (size_t k = 0; k < who.size(); ++k) who[k]->job.Consume(punc.data() + offs[k], offs[k + 1] - offs[k]);
+}
+
+void CTTransformerB200::Run() {
+  std::vector<Ticket*> active;
+  std::unique_lock<std::mutex> lk(mu_);
+  for (;;) {
+    cv_work_.wait(lk, [&] { return stop_ || !pending_.empty() || !active.empty(); });
+    if (pending_.empty() && active.empty()) return;   // stop_ and nothing left
+    while (!pending_.empty()) { active.push_back(pending_.front()); pending_.pop_front(); }
+    lk.unlock();
+    RunRound(&active);
+    lk.lock();
+    ++rounds_;
+    bool any_done = false;
+    for (size_t i = 0; i < active.size();) {
+      Ticket* t = active[i];
+      if (t->failed || !t->job.Active()) {
+        t->done = true;
+        any_done = true;
+        active.erase(active.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+    if (any_done) cv_done_.notify_all();
+  }
+}
+
 std::vector<std::string> CTTransformerB200::AddPuncBatch(const std::vector<std::string>& texts, const std::string& language, int* rounds) {
   std::vector<std::string> out(texts.size());
   if (rounds) *rounds = 0;
   if (!engine_) { fprintf(stderr, "CTTransformerB200: not initialised\n"); return out; }
-  std::vector<PuncJob> jobs;
-  jobs.reserve(texts.size());
-  for (const std::string& t : texts) jobs.emplace_back(&tok_, t.c_str(), language);
-  std::vector<int32_t> ids, offs, punc;
-  std::vector<size_t> who;
-  // a round carries the current mini-sentence of as many active requests as fit the engine, in request order
-  for (;;) {
-    ids.clear(); offs.assign(1, 0); who.clear();
-    for (size_t j = 0; j < jobs.size(); ++j) {
-      if (!jobs[j].Active()) continue;
-      const std::vector<int32_t>& in = jobs[j].Input();
-      if ((int)(ids.size() + in.size()) > max_tokens_ || who.size() >= 16384) {
-        if (who.empty()) { fprintf(stderr, "CTTransformerB200: a sentence cache outgrew the engine (%zu tokens)\n", in.size()); return out; }
-        break;
-      }
-      ids.insert(ids.end(), in.begin(), in.end());
-      offs.push_back((int32_t)ids.size());
-      who.push_back(j);
+  std::vector<std::unique_ptr<Ticket>> tickets;
+  tickets.reserve(texts.size());
+  for (const std::string& t : texts) tickets.emplace_back(new Ticket(&tok_, t.c_str(), language));   // tokenised on the caller's thread
+  long long r0;
+  {
+    std::unique_lock<std::mutex> lk(mu_);
+    r0 = rounds_;
+    for (auto& t : tickets) {
+      if (t->job.Active()) pending_.push_back(t.get()); else t->done = true;   // empty text: nothing to run
     }
-    if (who.empty()) break;
-    punc.assign(ids.size(), 0);
-    if (b200pf_punc_infer(engine_, ids.data(), offs.data(), (int)who.size(), punc.data(), nullptr) != 0) {
-      fprintf(stderr, "Error when run punc forword: %s\n", b200pf_last_error());   // the reference logs and carries on with "" (ct-transformer.cpp:197-201)
-      return out;
-    }
-    if (rounds) ++*rounds;
-    for (size_t k = 0; k < who.size(); ++k) jobs[who[k]].Consume(punc.data() + offs[k], offs[k + 1] - offs[k]);
+    cv_work_.notify_all();
+    cv_done_.wait(lk, [&] {
+      for (auto& t : tickets)
+        if (!t->done) return false;
+      return true;
+    });
+    if (rounds) *rounds = (int)(rounds_ - r0);
   }
-  for (size_t j = 0; j < jobs.size(); ++j) out[j] = jobs[j].Result();
+  for (size_t j = 0; j < tickets.size(); ++j) out[j] = tickets[j]->failed ? std::string() : tickets[j]->job.Result();
   return out;
 }
 

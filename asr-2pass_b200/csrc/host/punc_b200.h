@@ -4,12 +4,19 @@
 //
 // The reference punctuates one request at a time: AddPunc walks the text in 20-token mini-sentences, and every step is one
 // onnxruntime call whose input depends on the previous step's output (the unfinished sentence is carried over).  That chain
-// cannot be shortened, but it can be shared: AddPuncBatch advances MANY requests in lock step, one engine call per round carrying
-// the current mini-sentence of every request that still has one.  AddPunc(text) is the batch of one.
+// cannot be shortened, but it can be shared: every request -- from AddPunc on any thread, or the many of one AddPuncBatch call --
+// becomes a job of ONE dispatcher thread that advances all jobs in lock step, one engine call per round carrying the current
+// mini-sentence of every job that still has one.  Requests join at any round and leave when their text is finished (continuous
+// batching), so the decoder threads of a server that reach punc_handle->AddPunc at the same time (funasrruntime.cpp:317-320)
+// share the network's ~40 launches per round instead of queueing behind each other.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -80,11 +87,21 @@ class CTTransformerB200 : public PuncModel {
   std::vector<std::string> AddPuncBatch(const std::vector<std::string>& texts, const std::string& language = "zh-cn", int* rounds = nullptr);
   const PuncTokenizer& tokenizer() const { return tok_; }
   b200pf_punc* engine() const { return engine_; }
+  long long rounds() const;   // engine calls made so far
 
  private:
+  struct Ticket;
+  void Run();
+  void RunRound(std::vector<Ticket*>* active);
   int device_, max_tokens_;
   b200pf_punc* engine_ = nullptr;
   PuncTokenizer tok_;
+  mutable std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::deque<Ticket*> pending_;
+  bool stop_ = false;
+  long long rounds_ = 0;
+  std::thread worker_;
 };
 
 // The walk with any network (tests drive it with a scripted one on machines without a GPU).

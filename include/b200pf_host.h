@@ -75,6 +75,8 @@ int b200pf_host_punc_add_scripted(const char* const* tokens, int n_tokens, const
  * round for all of them); results are written back to back, each NUL-terminated; returns the bytes used. */
 void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens);
 void b200pf_host_punc_destroy(void* h);
+/* Engine calls (lock-step rounds) made so far: concurrent add calls share rounds. */
+long long b200pf_host_punc_rounds(void* h);
 int b200pf_host_punc_add(void* h, const char* text, const char* lang, char* out, int cap);
 int b200pf_host_punc_add_batch(void* h, const char* const* texts, int n, const char* lang, char* out, int cap, int* rounds);
 /* The host half of CompileHotwordEmbedding alone (paraformer.cpp:600-648; no GPU): hotword string -> ids [n][10] + lengths [n],

@@ -219,6 +219,22 @@ def test_host_addpunc_end_to_end(capi, synth, gpu, tmp_path):
     assert batch == [s for i, s in enumerate(singles) if i % 4 != 3]
     assert rounds == max(int(np.ceil(len(tok.tokenize(t)[1]) / 20)) for t in zh)      # lock step: as many rounds as the longest text
     assert host.add_punc("", "zh-cn") == ""
+    # continuous batching: concurrent AddPunc calls from several threads join the same lock-step rounds
+    import threading
+    r0 = host.rounds
+    got = [None] * len(zh)
+
+    def work(i):
+        got[i] = host.add_punc(zh[i], "zh-cn")
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(zh))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got == batch
+    solo = sum(int(np.ceil(len(tok.tokenize(t)[1]) / 20)) for t in zh)
+    assert host.rounds - r0 < solo                      # rounds were shared
     host.close()
     eng.close()
 
