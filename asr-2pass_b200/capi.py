@@ -54,7 +54,7 @@ EXPORTS = [
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
     "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
     "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln", "b200pf_vad_create", "b200pf_vad_destroy", "b200pf_vad_scores_s16",
-    "b200pf_punc_create", "b200pf_punc_destroy", "b200pf_punc_info", "b200pf_punc_infer", "b200pf_punc_launches",
+    "b200pf_punc_create", "b200pf_punc_destroy", "b200pf_punc_info", "b200pf_punc_infer", "b200pf_punc_infer_vad", "b200pf_punc_launches",
 ]
 
 
@@ -123,7 +123,8 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_mb_stats", "b200pf_host_offline_init_devices", "b200pf_host_partition", "b200pf_host_segments_per_device", "b200pf_host_funasr_infer", "b200pf_host_vad_segments",
                 "b200pf_host_offline_init_vad", "b200pf_host_offline_vad_cut", "b200pf_host_offline_infer_buffer_vad", "b200pf_host_pack_hotwords", "b200pf_host_punc_tokenize",
                 "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_rounds", "b200pf_host_punc_add",
-                "b200pf_host_punc_add_batch", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
+                "b200pf_host_punc_add_batch", "b200pf_host_punc_online_add_scripted", "b200pf_host_punc_online_create",
+                "b200pf_host_punc_online_destroy", "b200pf_host_punc_online_add", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
                 "b200pf_host_offline_infer_full"]
 
 
@@ -178,6 +179,13 @@ def host_lib():
     H.b200pf_host_punc_create.restype = C.c_void_p
     H.b200pf_host_punc_destroy.argtypes = [C.c_void_p]
     H.b200pf_host_punc_destroy.restype = None
+    H.b200pf_host_punc_online_add_scripted.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p,
+                                                       C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_punc_online_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    H.b200pf_host_punc_online_create.restype = C.c_void_p
+    H.b200pf_host_punc_online_destroy.argtypes = [C.c_void_p]
+    H.b200pf_host_punc_online_destroy.restype = None
+    H.b200pf_host_punc_online_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
     H.b200pf_host_punc_rounds.argtypes = [C.c_void_p]
     H.b200pf_host_punc_rounds.restype = C.c_longlong
     H.b200pf_host_punc_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -461,11 +469,60 @@ class HostPuncTokenizer:
         assert n >= 0
         return ids[:n].tolist()
 
+    def add_punc_online_scripted(self, text, cache, seed, every):
+        """The realtime walk (AddPuncOnlineWith) with the scripted network seeded by seed + 13 * vad_pos; cache updated in place."""
+        raw, cin = text.encode("utf-8"), _cache_join(cache)
+        cap = 16 * (len(raw) + len(cin)) + 4096
+        buf, cbuf = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        n = host_lib().b200pf_host_punc_online_add_scripted(self.tokens, self.n, self.punc, self.n_punc, raw, cin, seed, every, buf, cap, cbuf, cap)
+        assert n >= 0
+        cache[:] = _cache_split(cbuf.value)
+        return buf.value.decode("utf-8", "replace")
+
     def add_punc_scripted(self, text, lang, seed, every):
         raw = text.encode("utf-8")
         buf = C.create_string_buffer(16 * len(raw) + 4096)
         n = host_lib().b200pf_host_punc_add_scripted(self.tokens, self.n, self.punc, self.n_punc, raw, lang.encode(), seed, every, buf, len(buf))
         assert n >= 0
+        return buf.value.decode("utf-8", "replace")
+
+
+def _cache_join(cache):
+    return b"".join(w + b"\x01" for w in cache)
+
+
+def _cache_split(raw):
+    return raw.split(b"\x01")[:-1]
+
+
+class HostPuncOnline:
+    """funasr_b200::CTTransformerOnlineB200 (the realtime punctuation model): add_punc(text, cache) with cache a list of bytes,
+    updated in place."""
+
+    def __init__(self, punc_dir, device=0, max_tokens=0):
+        self.h = host_lib().b200pf_host_punc_online_create(punc_dir.encode(), device, max_tokens)
+        if not self.h:
+            raise B200PFError("CTTransformerOnline init failed: " + lib().b200pf_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self.h:
+            host_lib().b200pf_host_punc_online_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_punc(self, text, cache):
+        raw, cin = text.encode("utf-8"), _cache_join(cache)
+        cap = 16 * (len(raw) + len(cin)) + 4096
+        buf, cbuf = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        n = host_lib().b200pf_host_punc_online_add(self.h, raw, cin, buf, cap, cbuf, cap)
+        if n < 0:
+            raise B200PFError("AddPunc (online) failed")
+        cache[:] = _cache_split(cbuf.value)
         return buf.value.decode("utf-8", "replace")
 
 
@@ -662,6 +719,7 @@ class PuncEngine:
         L.b200pf_punc_destroy.restype = None
         L.b200pf_punc_info.argtypes = [C.c_void_p, c_i32p, c_i32p, c_i32p, c_i32p]
         L.b200pf_punc_infer.argtypes = [C.c_void_p, c_i32p, c_i32p, C.c_int, c_i32p, c_f32p]
+        L.b200pf_punc_infer_vad.argtypes = [C.c_void_p, c_i32p, c_i32p, c_i32p, C.c_int, c_i32p, c_f32p]
         L.b200pf_punc_launches.argtypes = [C.c_void_p]
         L.b200pf_punc_launches.restype = C.c_longlong
         _check(L.b200pf_punc_create(punc_dir.encode(), device, max_tokens, C.byref(self.h)))
@@ -684,12 +742,18 @@ class PuncEngine:
     def launches(self):
         return int(lib().b200pf_punc_launches(self.h))
 
-    def infer(self, ids, offsets, logits=False):
-        """-> (punc ids int32 [T], logits [T, n_punc] or None) for sequences ids[offsets[i]:offsets[i+1]]."""
+    def infer(self, ids, offsets, logits=False, vad_pos=None):
+        """-> (punc ids int32 [T], logits [T, n_punc] or None) for sequences ids[offsets[i]:offsets[i+1]]; vad_pos [n_seq]: the
+        realtime model's VadMask position per sequence (b200pf_punc_infer_vad)."""
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
         out = np.zeros(max(1, len(ids)), np.int32)
         lg = np.zeros((max(1, len(ids)), self.n_punc), np.float32) if logits else None
+        if vad_pos is not None:
+            vp = np.ascontiguousarray(vad_pos, dtype=np.int32)
+            assert len(vp) == len(offsets) - 1
+            _check(lib().b200pf_punc_infer_vad(self.h, _p(ids, c_i32p), _p(offsets, c_i32p), _p(vp, c_i32p), len(offsets) - 1, _p(out, c_i32p), _p(lg)))
+            return out[:len(ids)], (lg[:len(ids)] if lg is not None else None)
         _check(lib().b200pf_punc_infer(self.h, _p(ids, c_i32p), _p(offsets, c_i32p), len(offsets) - 1, _p(out, c_i32p), _p(lg)))
         return out[:len(ids)], (lg[:len(ids)] if lg is not None else None)
 

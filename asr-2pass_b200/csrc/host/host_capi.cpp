@@ -219,6 +219,57 @@ int b200pf_host_punc_add_scripted(const char* const* tokens, int n_tokens, const
   };
   return CopyOut(funasr_b200::AddPuncWith(tk, text, lang ? lang : "zh-cn", infer), out, cap);
 }
+namespace {
+std::vector<std::string> SplitCache(const char* s) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (const char* c = s ? s : ""; *c; ++c) {
+    if (*c == '\x01') { out.push_back(cur); cur.clear(); } else cur += *c;
+  }
+  return out;
+}
+std::string JoinCache(const std::vector<std::string>& v) {
+  std::string s;
+  for (const std::string& w : v) s += w + '\x01';
+  return s;
+}
+}  // namespace
+int b200pf_host_punc_online_add_scripted(const char* const* tokens, int n_tokens, const char* const* punc_list, int n_punc, const char* text,
+                                         const char* cache_in, int seed, int every, char* out, int cap, char* cache_out, int cache_cap) {
+  funasr_b200::PuncTokenizer tk;
+  tk.Open(std::vector<std::string>(tokens, tokens + n_tokens), std::vector<std::string>(punc_list, punc_list + n_punc));
+  std::vector<std::string> cache = SplitCache(cache_in);
+  auto infer = [&](const std::vector<int32_t>& ids, int vad_pos) {   // tests/test_punc.py::scripted_punc with seed + 13 * vad_pos
+    std::vector<int32_t> r(ids.size());
+    const int sd = seed + 13 * vad_pos;
+    for (size_t pos = 0; pos < ids.size(); ++pos) {
+      uint32_t h = (uint32_t)((uint64_t)(uint32_t)ids[pos] * 2654435761ull + (uint64_t)pos * 40503ull + (uint64_t)sd * 97ull);
+      h = (h >> 7) & 0xFFFF;
+      if (every && h % (uint32_t)every == 0) r[pos] = h % 3 ? 3 : 4;
+      else if (h % 11 == 1) r[pos] = 2;
+      else if (h % 37 == 2) r[pos] = 0;
+      else r[pos] = 1;
+    }
+    return r;
+  };
+  const int n = CopyOut(funasr_b200::AddPuncOnlineWith(tk, text, &cache, infer), out, cap);
+  if (CopyOut(JoinCache(cache), cache_out, cache_cap) < 0) return -1;
+  return n;
+}
+void* b200pf_host_punc_online_create(const char* punc_dir, int device, int max_tokens) {
+  std::unique_ptr<funasr_b200::CTTransformerOnlineB200> p(new funasr_b200::CTTransformerOnlineB200(device, max_tokens));
+  std::string err;
+  if (!p->Init(punc_dir, &err)) { fprintf(stderr, "b200pf_host_punc_online_create: %s\n", err.c_str()); return nullptr; }
+  return p.release();
+}
+void b200pf_host_punc_online_destroy(void* h) { delete (funasr_b200::CTTransformerOnlineB200*)h; }
+int b200pf_host_punc_online_add(void* h, const char* text, const char* cache_in, char* out, int cap, char* cache_out, int cache_cap) {
+  if (!h) return -1;
+  std::vector<std::string> cache = SplitCache(cache_in);
+  const int n = CopyOut(((funasr_b200::CTTransformerOnlineB200*)h)->AddPunc(text, cache, "zh-cn"), out, cap);
+  if (CopyOut(JoinCache(cache), cache_out, cache_cap) < 0) return -1;
+  return n;
+}
 void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens) {
   std::unique_ptr<funasr_b200::CTTransformerB200> p(new funasr_b200::CTTransformerB200(device, max_tokens));
   std::string err;

@@ -345,4 +345,120 @@ std::string CTTransformerB200::AddPunc(const char* sz_input, std::string languag
   return r.empty() ? std::string() : r[0];
 }
 
+// ---- realtime model -------------------------------------------------------------------------------------------------------
+std::string AddPuncOnlineWith(const PuncTokenizer& tok, const char* text, std::vector<std::string>* cache,
+                              const std::function<std::vector<int32_t>(const std::vector<int32_t>&, int)>& infer) {
+  // full text = cached words + this text, with a space between two ASCII neighbours (ct-transformer-online.cpp:46-53)
+  std::string full;
+  for (const std::string& w : *cache) full += w;
+  const char* in = text ? text : "";
+  if (!full.empty() && !(static_cast<unsigned char>(full.back()) & 0x80) && in[0] != 0 && !(static_cast<unsigned char>(in[0]) & 0x80)) full += " ";
+  full += in;
+  std::vector<std::string> pieces;
+  std::vector<int32_t> ids;
+  tok.Tokenize(full.c_str(), &pieces, &ids);
+  const int n_cache = (int)cache->size();   // the VAD position of every network call of this request
+  const int n_total = (int)std::ceil((float)ids.size() / kMiniSentence);
+  std::vector<int32_t> remain_ids, punc_all;
+  std::vector<std::string> remain_str, words;
+  for (size_t pos = 0; pos < ids.size(); pos += kMiniSentence) {
+    const size_t end = std::min(ids.size(), pos + (size_t)kMiniSentence);
+    std::vector<int32_t> in_ids(remain_ids);
+    in_ids.insert(in_ids.end(), ids.begin() + pos, ids.begin() + end);
+    std::vector<std::string> in_str(remain_str);
+    in_str.insert(in_str.end(), pieces.begin() + pos, pieces.begin() + end);
+    std::vector<int32_t> punc = infer(in_ids, n_cache);
+    if (punc.size() != in_ids.size()) return "";
+    if ((int)(pos / kMiniSentence) < n_total - 1) {
+      int sent_end = -1, last_comma = -1;
+      for (int k = (int)punc.size() - 2; k > 0; --k) {
+        const std::string& p = tok.Id2Punc(punc[k]);
+        if (p == tok.Id2Punc(kPeriod) || p == tok.Id2Punc(kQuestion)) { sent_end = k; break; }
+        if (last_comma < 0 && p == tok.Id2Punc(kComma)) last_comma = k;
+      }
+      if (sent_end < 0 && (int)in_str.size() > kCachePopLimit && last_comma > 0) {
+        sent_end = last_comma;
+        punc[sent_end] = kPeriod;
+      }
+      remain_str.assign(in_str.begin() + (sent_end + 1), in_str.end());
+      remain_ids.assign(in_ids.begin() + (sent_end + 1), in_ids.end());
+      in_str.resize((size_t)(sent_end + 1));
+      punc.resize((size_t)(sent_end + 1));
+    }
+    words.insert(words.end(), in_str.begin(), in_str.end());
+    punc_all.insert(punc_all.end(), punc.begin(), punc.end());
+  }
+  // output: the words after the cached ones, each followed by its mark unless that is "_"; the mark of the LAST cached word is
+  // emitted too (the skip counter reaches the cache size on that word, ct-transformer-online.cpp:106-121)
+  std::string out_last;          // the last piece appended, to drop a trailing mark
+  std::vector<std::string> out;
+  int skipped = 0;
+  for (size_t i = 0; i < words.size(); ++i) {
+    if (!HighBit(words[i]) && i + 1 < words.size() && !HighBit(words[i + 1])) words[i] += " ";
+    if (skipped < n_cache) ++skipped; else out.push_back(words[i]);
+    if (skipped >= n_cache) {
+      const std::string& mark = tok.Id2Punc(punc_all[i]);
+      if (mark != "_") out.push_back(mark);
+    }
+  }
+  int sent_end = -1;
+  for (int i = (int)punc_all.size() - 2; i > 0; --i)
+    if (punc_all[i] == kPeriod || punc_all[i] == kQuestion) { sent_end = i; break; }
+  cache->assign(words.begin() + (sent_end + 1), words.end());
+  if (!out.empty()) {
+    bool is_mark = false;
+    for (int k = 0; k < tok.NumPunc(); ++k) is_mark = is_mark || out.back() == tok.Id2Punc(k);
+    if (is_mark) out.pop_back();   // a trailing mark waits for the next call
+  }
+  std::string res;
+  for (const std::string& w : out) res += w;
+  return res;
+}
+
+CTTransformerOnlineB200::~CTTransformerOnlineB200() {
+  if (engine_) b200pf_punc_destroy(engine_);
+}
+
+bool CTTransformerOnlineB200::Init(const std::string& punc_dir, std::string* err) {
+  std::vector<std::string> tokens, punc;
+  if (!ReadStringArray(punc_dir + "/tokens.json", &tokens) || tokens.empty()) { if (err) *err = punc_dir + "/tokens.json: not a JSON array of strings"; return false; }
+  if (!ReadStringArray(punc_dir + "/punc_list.json", &punc) || punc.empty()) { if (err) *err = punc_dir + "/punc_list.json: not a JSON array of strings"; return false; }
+  if (b200pf_punc_create(punc_dir.c_str(), device_, max_tokens_, &engine_) != 0) { if (err) *err = b200pf_last_error(); return false; }
+  int vocab = 0, n_punc = 0;
+  b200pf_punc_info(engine_, &vocab, &n_punc, nullptr, &max_tokens_);
+  if (vocab != (int)tokens.size() || n_punc != (int)punc.size() || n_punc < 6) {
+    if (err) *err = "punctuation model / tokens.json / punc_list.json sizes disagree";
+    b200pf_punc_destroy(engine_);
+    engine_ = nullptr;
+    return false;
+  }
+  tok_.Open(tokens, punc);
+  return true;
+}
+
+void CTTransformerOnlineB200::InitPunc(const std::string& punc_model, const std::string& punc_config, const std::string& token_file, int thread_num) {
+  (void)punc_config; (void)token_file; (void)thread_num;
+  std::string err;
+  if (!Init(DirOf(punc_model), &err)) {
+    fprintf(stderr, "Error when load punc model: %s\n", err.c_str());
+    exit(-1);
+  }
+}
+
+std::string CTTransformerOnlineB200::AddPunc(const char* sz_input, std::vector<std::string>& arr_cache, std::string language) {
+  (void)language;   // the realtime model does not map symbols for en-bpe (ct-transformer-online.cpp:40-137)
+  if (!engine_) { fprintf(stderr, "CTTransformerOnlineB200: not initialised\n"); return ""; }
+  b200pf_punc* eng = engine_;
+  return AddPuncOnlineWith(tok_, sz_input, &arr_cache, [eng](const std::vector<int32_t>& ids, int vad_pos) {
+    std::vector<int32_t> punc(ids.size(), 0);
+    const int32_t offs[2] = {0, (int32_t)ids.size()};
+    const int32_t vp[1] = {vad_pos};
+    if (ids.empty() || b200pf_punc_infer_vad(eng, ids.data(), offs, vp, 1, punc.data(), nullptr) != 0) {
+      fprintf(stderr, "Error when run punc onnx forword: %s\n", b200pf_last_error());
+      punc.clear();
+    }
+    return punc;
+  });
+}
+
 }  // namespace funasr_b200

@@ -104,6 +104,29 @@ class CTTransformerB200 : public PuncModel {
   std::thread worker_;
 };
 
+// funasr::CTTransformerOnline (ct-transformer-online.{h,cpp}): the realtime punctuation model -- what the 2-pass server applies to
+// both its online and its offline-leg results (funasrruntime.cpp:545,610).  AddPunc(text, cache) punctuates `cache + text`, returns
+// the part that belongs to `text` and leaves in `cache` the words after the last sentence end.  The network sees the reference's
+// VadMask (vad_pos = the number of cached words) in every layer and needs sanm_shift in punc.b200pf (b200pf_punc_infer_vad).
+class CTTransformerOnlineB200 : public PuncModel {
+ public:
+  explicit CTTransformerOnlineB200(int device = 0, int max_tokens = 0) : device_(device), max_tokens_(max_tokens) { is_online = true; }
+  ~CTTransformerOnlineB200() override;
+  bool Init(const std::string& punc_dir, std::string* err);
+  void InitPunc(const std::string& punc_model, const std::string& punc_config, const std::string& token_file, int thread_num) override;
+  std::string AddPunc(const char* sz_input, std::vector<std::string>& arr_cache, std::string language = "zh-cn") override;
+  const PuncTokenizer& tokenizer() const { return tok_; }
+
+ private:
+  int device_, max_tokens_;
+  b200pf_punc* engine_ = nullptr;
+  PuncTokenizer tok_;
+};
+
+// The realtime walk with any network: infer(ids, vad_pos) -> class per token.
+std::string AddPuncOnlineWith(const PuncTokenizer& tok, const char* text, std::vector<std::string>* cache,
+                              const std::function<std::vector<int32_t>(const std::vector<int32_t>&, int)>& infer);
+
 // The walk with any network (tests drive it with a scripted one on machines without a GPU).
 std::string AddPuncWith(const PuncTokenizer& tok, const char* text, const std::string& language,
                         const std::function<std::vector<int32_t>(const std::vector<int32_t>&)>& infer);

@@ -78,64 +78,118 @@ punc_ln_kernel(const float* __restrict__ x, int rows, int D, int Dp, const float
     out[(size_t)r * Dp + c] = __float2bfloat16(c < D ? (xr[c] - mean) * rstd * gamma[c] + beta[c] : 0.f);
 }
 
-// FSMN memory on V (columns [2D, 3D) of qkv): x[t, c] += v[t, c] + sum_k w[k][c] v[t + k - left, c], taps outside the sequence are zero
-__global__ void __launch_bounds__(128)
-punc_fsmn_kernel(const float* __restrict__ qkv, const int2* __restrict__ row_info, int rows, int D, int K, const float* __restrict__ w_t /*[K][D]*/,
-                 float* __restrict__ x) {
+// FSMN memory on V (columns [2D, 3D) of qkv): x[t, c] += v[t, c] + sum_k w[k][c] v[t + k - left, c], taps outside the sequence are zero;
+// left = (K - 1) / 2 + sanm_shift (0 for the offline model: symmetric; 5 with K = 11 for the realtime model: causal).
+// One thread per (row, 4 channels): float4 loads of V (the K neighbouring rows come from L1 / L2), float4 read-modify-write of x.
+__global__ void __launch_bounds__(256)
+punc_fsmn_kernel(const float* __restrict__ qkv, const int2* __restrict__ row_info, int rows, int D, int K, int left,
+                 const float* __restrict__ w_t /*[K][D]*/, float* __restrict__ x) {
   pdl_wait();
   pdl_launch_dependents();
-  const int r = blockIdx.x;
-  if (r >= rows) return;
+  const int d4 = D >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * d4) return;
+  const int r = (int)(idx / d4), c = ((int)(idx - (long long)r * d4)) << 2;
   const int2 inf = row_info[r];    // {t, T}
-  const int left = (K - 1) / 2;
   const size_t ld = (size_t)3 * D;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    float acc = qkv[(size_t)r * ld + 2 * D + c];
-    for (int k = 0; k < K; ++k) {
-      const int tt = inf.x + k - left;
-      if (tt >= 0 && tt < inf.y) acc += w_t[(size_t)k * D + c] * qkv[(size_t)(r + k - left) * ld + 2 * D + c];
-    }
-    x[(size_t)r * D + c] += acc;
+  const float* v = qkv + 2 * D + c;
+  float4 acc = *reinterpret_cast<const float4*>(v + (size_t)r * ld);
+  for (int k = 0; k < K; ++k) {
+    const int tt = inf.x + k - left;
+    if (tt < 0 || tt >= inf.y) continue;
+    const float4 w = *reinterpret_cast<const float4*>(w_t + (size_t)k * D + c);
+    const float4 u = *reinterpret_cast<const float4*>(v + (size_t)(r + k - left) * ld);
+    acc.x += w.x * u.x; acc.y += w.y * u.y; acc.z += w.z * u.z; acc.w += w.w * u.w;
   }
+  float4* xo = reinterpret_cast<float4*>(x + (size_t)r * D + c);
+  float4 xv = *xo;
+  xv.x += acc.x; xv.y += acc.y; xv.z += acc.z; xv.w += acc.w;
+  *xo = xv;
 }
 
 // Softmax attention inside each sequence, head dimension dk <= 64.  Block = (tile of 16 queries of one sequence, head); the K / V
 // rows of the sequence stream through shared memory 32 keys at a time; a warp owns one query at a time: lane j scores key j of the
 // chunk, the running maximum / sum are warp-reduced (online softmax), and lane d accumulates output dimensions d and d + 32.
 __global__ void __launch_bounds__(128)
-punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, int D, int dk, float scale, __nv_bfloat16* __restrict__ ctx, int Dp) {
+punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, const int* __restrict__ tile_vad, int D, int dk, float scale,
+                 __nv_bfloat16* __restrict__ ctx, int Dp) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float Ks[32][P_MAX_DK + 1];
-  __shared__ float Vs[32][P_MAX_DK];
+  __shared__ __align__(16) float Vs[32][P_MAX_DK];
   __shared__ float Qs[P_QTILE][P_MAX_DK];
   const int4 tl = tiles[blockIdx.x];     // {first row of the tile, queries in the tile, first row of the sequence, sequence length}
+  // realtime model (CTTransformerOnline::VadMask, ct-transformer-online.cpp:219-233): with 0 < vad_pos < T, queries before
+  // vad_pos - 1 do not see keys from vad_pos on; everything else sees the whole sequence
+  const int vad_pos = tile_vad[blockIdx.x];
+  const int q_first = tl.x - tl.z;       // position of the tile's first query inside its sequence
   const int h = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t ld = (size_t)3 * D;
   const int col = h * dk;
-  for (int i = threadIdx.x; i < P_QTILE * dk; i += blockDim.x) {
-    const int q = i / dk, d = i - q * dk;
-    Qs[q][d] = q < tl.y ? qkv[(size_t)(tl.x + q) * ld + col + d] * scale : 0.f;
+  const bool vec = (dk & 3) == 0;           // rows of a head are 16-byte aligned (D % 4 == 0 always)
+  const int dk4 = dk >> 2;
+  if (vec) {
+    for (int i = threadIdx.x; i < P_QTILE * dk4; i += blockDim.x) {
+      const int q = i / dk4, d = (i - q * dk4) << 2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < tl.y) v = *reinterpret_cast<const float4*>(qkv + (size_t)(tl.x + q) * ld + col + d);
+      Qs[q][d] = v.x * scale; Qs[q][d + 1] = v.y * scale; Qs[q][d + 2] = v.z * scale; Qs[q][d + 3] = v.w * scale;
+    }
+  } else {
+    for (int i = threadIdx.x; i < P_QTILE * dk; i += blockDim.x) {
+      const int q = i / dk, d = i - q * dk;
+      Qs[q][d] = q < tl.y ? qkv[(size_t)(tl.x + q) * ld + col + d] * scale : 0.f;
+    }
   }
   float m[4], l[4], a0[4], a1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; a0[i] = 0.f; a1[i] = 0.f; }
   for (int k0 = 0; k0 < tl.w; k0 += 32) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * dk; i += blockDim.x) {
-      const int j = i / dk, d = i - j * dk;
-      const bool ok = k0 + j < tl.w;
-      const size_t row = (size_t)(tl.z + k0 + j) * ld;
-      Ks[j][d] = ok ? qkv[row + D + col + d] : 0.f;
-      Vs[j][d] = ok ? qkv[row + 2 * D + col + d] : 0.f;
+    if (vec) {
+      // 32 keys x dk floats of K and of V: all global loads of the chunk are issued before the first shared-memory store
+      float4 kr[4], vr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * 128;
+        kr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vr[u] = kr[u];
+        if (i < 32 * dk4) {
+          const int j = i / dk4, d = (i - j * dk4) << 2;
+          if (k0 + j < tl.w) {
+            const float* row = qkv + (size_t)(tl.z + k0 + j) * ld + col + d;
+            kr[u] = *reinterpret_cast<const float4*>(row + D);
+            vr[u] = *reinterpret_cast<const float4*>(row + 2 * D);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * 128;
+        if (i < 32 * dk4) {
+          const int j = i / dk4, d = (i - j * dk4) << 2;
+          Ks[j][d] = kr[u].x; Ks[j][d + 1] = kr[u].y; Ks[j][d + 2] = kr[u].z; Ks[j][d + 3] = kr[u].w;
+          *reinterpret_cast<float4*>(&Vs[j][d]) = vr[u];
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < 32 * dk; i += blockDim.x) {
+        const int j = i / dk, d = i - j * dk;
+        const bool ok = k0 + j < tl.w;
+        const size_t row = (size_t)(tl.z + k0 + j) * ld;
+        Ks[j][d] = ok ? qkv[row + D + col + d] : 0.f;
+        Vs[j][d] = ok ? qkv[row + 2 * D + col + d] : 0.f;
+      }
     }
     __syncthreads();
-    const bool key_ok = k0 + lane < tl.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = warp * 4 + i;
       if (q >= tl.y) break;          // warp-uniform
+      const int k_end = (vad_pos > 0 && vad_pos < tl.w && q_first + q < vad_pos - 1) ? vad_pos : tl.w;
+      if (k0 >= k_end) continue;     // warp-uniform: this chunk is entirely masked for the query
+      const bool key_ok = k0 + lane < k_end;
       float s = 0.f;
       for (int d = 0; d < dk; ++d) s += Qs[q][d] * Ks[lane][d];
       s = key_ok ? s : -INFINITY;
@@ -202,7 +256,7 @@ struct PLayer {
 
 struct b200pf_punc {
   int device = 0, num_sms = 148, max_tokens = 0;
-  int vocab = 0, D = 0, Dp = 0, H = 0, dk = 0, F = 0, Fp = 0, L = 0, K = 0, n_punc = 0, n_out_p = 8;
+  int vocab = 0, D = 0, Dp = 0, H = 0, dk = 0, F = 0, Fp = 0, L = 0, K = 0, n_punc = 0, n_out_p = 8, shift = 0;
   float eps = 1e-12f;
   cudaStream_t stream = nullptr;
   std::mutex mu;
@@ -246,10 +300,10 @@ int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_
   std::unique_ptr<b200pf_punc> p(new b200pf_punc);
   p->device = device;
   p->vocab = cfgi("vocab", 0); p->D = cfgi("d_model", 0); p->H = cfgi("n_heads", 0); p->F = cfgi("d_ff", 0);
-  p->L = cfgi("n_layers", 0); p->K = cfgi("kernel", 11); p->n_punc = cfgi("n_punc", 6);
+  p->L = cfgi("n_layers", 0); p->K = cfgi("kernel", 11); p->n_punc = cfgi("n_punc", 6); p->shift = cfgi("sanm_shift", 0);
   { auto it = wf.cfg.find("ln_eps"); if (it != wf.cfg.end()) p->eps = (float)it->second; }
   if (p->vocab <= 0 || p->D <= 0 || p->H <= 0 || p->F <= 0 || p->L <= 0 || p->D % p->H || (p->D & 3) || (p->F & 7) || p->D / p->H > P_MAX_DK ||
-      p->n_punc < 2 || p->n_punc > 8 || p->K < 1 || p->K > 31 || !(p->K & 1)) {
+      p->n_punc < 2 || p->n_punc > 8 || p->K < 1 || p->K > 31 || !(p->K & 1) || p->shift < 0 || (p->K - 1) / 2 + p->shift > p->K - 1) {
     set_error("punc.b200pf: unsupported configuration (need d_model % n_heads == 0, d_model % 4 == 0, d_ff % 8 == 0, head dim <= 64, n_punc <= 8)");
     return B200PF_ERR_IO;
   }
@@ -339,7 +393,7 @@ int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_
   }
   const size_t R = (size_t)p->max_tokens;
   const size_t max_tiles = R / P_QTILE + P_MAX_SEQ + 1;
-  p->in_bytes = R * 4 + R * 8 + max_tiles * 16 + 1024;
+  p->in_bytes = R * 4 + R * 8 + max_tiles * 20 + 1024;
   p->d_in = (uint8_t*)dalloc(p->in_bytes);
   if (ok && (cudaMallocHost((void**)&p->h_in, p->in_bytes) != cudaSuccess || cudaMallocHost((void**)&p->h_punc, R * 4) != cudaSuccess)) {
     ok = false; err = "cudaMallocHost failed (punctuation staging)"; cudaGetLastError();
@@ -377,6 +431,11 @@ int b200pf_punc_info(const b200pf_punc* p, int* vocab, int* n_punc, int* d_model
 long long b200pf_punc_launches(const b200pf_punc* p) { return p ? p->launches : 0; }
 
 int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets, int n_seq, int32_t* punc_out, float* logits_out) {
+  return b200pf_punc_infer_vad(p, ids, offsets, nullptr, n_seq, punc_out, logits_out);
+}
+
+int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* offsets, const int32_t* vad_pos, int n_seq, int32_t* punc_out,
+                          float* logits_out) {
   if (!p || !offsets || n_seq < 0 || (n_seq > 0 && !ids) || !punc_out) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   if (n_seq > P_MAX_SEQ) { set_error("too many sequences in one call"); return B200PF_ERR_CAPACITY; }
   if (n_seq == 0) return 0;
@@ -386,12 +445,17 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
   if (rows == 0) return 0;
   PCK(cudaSetDevice(p->device), "cudaSetDevice");
   std::lock_guard<std::mutex> lock(p->mu);
-  // staging layout: ids [rows] | row info [rows] | tiles [n_tiles], 16-byte aligned sections
+  // staging layout: ids [rows] | row info [rows] | tiles [n_tiles] | per-tile vad_pos [n_tiles], 16-byte aligned sections
   const size_t off_info = ((size_t)rows * 4 + 15) & ~size_t(15), off_tiles = (off_info + (size_t)rows * 8 + 15) & ~size_t(15);
+  size_t want_tiles = 0;
+  for (int i = 0; i < n_seq; ++i) want_tiles += (size_t)((offsets[i + 1] - offsets[i] + P_QTILE - 1) / P_QTILE);
+  const size_t off_vad = off_tiles + want_tiles * 16;
+  if (off_vad + want_tiles * 4 > p->in_bytes) { set_error("too many attention tiles"); return B200PF_ERR_CAPACITY; }
   int* h_ids = (int*)p->h_in;
   int2* info = (int2*)(p->h_in + off_info);
   int4* tiles = (int4*)(p->h_in + off_tiles);
-  const size_t max_tiles = (p->in_bytes - off_tiles) / 16;
+  int* tile_vad = (int*)(p->h_in + off_vad);
+  const size_t max_tiles = want_tiles;
   size_t n_tiles = 0;
   memcpy(h_ids, ids + base, (size_t)rows * 4);
   for (int i = 0; i < n_seq; ++i) {
@@ -401,6 +465,7 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
     for (int t = 0; t < T; ++t) info[r0 + t] = make_int2(t, T);
     for (int q0 = 0; q0 < T; q0 += P_QTILE) {
       if (n_tiles >= max_tiles) { set_error("too many attention tiles"); return B200PF_ERR_CAPACITY; }
+      tile_vad[n_tiles] = vad_pos ? vad_pos[i] : 0;
       tiles[n_tiles++] = make_int4(r0 + q0, T - q0 < P_QTILE ? T - q0 : P_QTILE, r0, T);
     }
   }
@@ -409,7 +474,8 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
   p->d_ids = (int*)p->d_in;
   p->d_row_info = (int2*)(p->d_in + off_info);
   p->d_tiles = (int4*)(p->d_in + off_tiles);
-  PCK(cudaMemcpyAsync(p->d_in, p->h_in, off_tiles + n_tiles * 16, cudaMemcpyHostToDevice, s), "H2D punctuation input");
+  const int* d_tile_vad = (const int*)(p->d_in + off_vad);
+  PCK(cudaMemcpyAsync(p->d_in, p->h_in, off_vad + n_tiles * 4, cudaMemcpyHostToDevice, s), "H2D punctuation input");
   int rc = launch_kernel(punc_embed_kernel, dim3(rows), dim3(128), 0, s, (const int*)p->d_ids, (const int2*)p->d_row_info, rows, (const float*)p->embed,
                          p->vocab, (const float*)p->pe, D, sqrtf((float)D), p->x);
   if (rc) return check_cuda((cudaError_t)rc, "punc embed");
@@ -431,12 +497,12 @@ int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets
     const PLayer& Ly = p->layers[l];
     if ((rc = ln(Ly.ln1_g, Ly.ln1_b))) return check_cuda((cudaError_t)rc, "punc ln1");
     if ((rc = gemm(p->h, Dp, Ly.qkv, 3 * D, 0, nullptr, 0, p->qkv, 3 * D, nullptr))) return check_cuda((cudaError_t)rc, "punc gemm qkv");
-    rc = launch_kernel(punc_attn_kernel, dim3((unsigned)n_tiles, p->H), dim3(128), 0, s, (const float*)p->qkv, (const int4*)p->d_tiles, D, p->dk, scale,
+    rc = launch_kernel(punc_attn_kernel, dim3((unsigned)n_tiles, p->H), dim3(128), 0, s, (const float*)p->qkv, (const int4*)p->d_tiles, d_tile_vad, D, p->dk, scale,
                        p->ctx, Dp);
     if (rc) return check_cuda((cudaError_t)rc, "punc attention");
     // x += v + fsmn(v): after the attention kernel has been queued (it does not read x), before the out-projection accumulates into x
-    rc = launch_kernel(punc_fsmn_kernel, dim3(rows), dim3(128), 0, s, (const float*)p->qkv, (const int2*)p->d_row_info, rows, D, p->K,
-                       (const float*)Ly.fsmn_w, p->x);
+    rc = launch_kernel(punc_fsmn_kernel, dim3((unsigned)(((long long)rows * (D >> 2) + 255) / 256)), dim3(256), 0, s, (const float*)p->qkv, (const int2*)p->d_row_info, rows, D, p->K,
+                       (p->K - 1) / 2 + p->shift, (const float*)Ly.fsmn_w, p->x);
     if (rc) return check_cuda((cudaError_t)rc, "punc fsmn");
     n_launch += 2;
     if ((rc = gemm(p->ctx, Dp, Ly.out, D, 0, nullptr, 0, p->x, D, p->x))) return check_cuda((cudaError_t)rc, "punc gemm out");

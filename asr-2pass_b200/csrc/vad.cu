@@ -26,48 +26,76 @@ namespace {
 
 constexpr int V_IN = 400, V_A1 = 144, V_LIN = 256, V_PROJ = 128, V_O1 = 144, V_OUT = 248, V_LORDER = 20, V_LAYERS = 4;
 
-// LFR m=5 n=1 + CMVN: X[t][80 j + m] = (fb[clamp(t + j - 2, 0, n_fb - 1)][m] + mean) * var  -> bf16 [rows, 400]
+// LFR m=5 n=1 + CMVN: X[t][80 j + m] = (fb[clamp(t + j - 2, 0, n_fb - 1)][m] + mean) * var  -> bf16 [rows, 400].
+// One thread per 4 consecutive mel bins of one output row (float4 in, 4 bf16 out); 8 rows per block.
 __global__ void __launch_bounds__(128)
 vad_lfr_cmvn_kernel(const float* __restrict__ fb, const int2* __restrict__ row_info, const int* __restrict__ row_start, int rows,
                     const float* __restrict__ mean, const float* __restrict__ var, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
   pdl_wait();
   pdl_launch_dependents();
-  const int r = blockIdx.x;
-  if (r >= rows) return;
-  const int2 inf = row_info[r];          // {t, T}
-  const int base = row_start[r];         // first fbank frame of this recording
-  for (int c = threadIdx.x; c < V_IN; c += blockDim.x) {
-    const int j = c / 80, m = c - 80 * j;
+  const int q = threadIdx.x;               // 100 float4 groups per row
+  if (q >= V_IN / 4) return;
+  const int c = q * 4, j = c / 80, m = c - 80 * j;
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), va = *reinterpret_cast<const float4*>(var + c);
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = blockIdx.x * 8 + rr;
+    if (r >= rows) return;
+    const int2 inf = row_info[r];          // {t, T}
     int f = inf.x + j - 2;
     f = f < 0 ? 0 : (f > inf.y - 1 ? inf.y - 1 : f);
-    const float v = __fmul_rn(__fadd_rn(fb[(size_t)(base + f) * 80 + m], mean[c]), var[c]);
-    out[(size_t)r * V_IN + c] = __float2bfloat16(v);
-    if (out_f32) out_f32[(size_t)r * V_IN + c] = v;
+    const float4 x = *reinterpret_cast<const float4*>(fb + (size_t)(row_start[r] + f) * 80 + m);
+    float4 v;
+    v.x = __fmul_rn(__fadd_rn(x.x, mu.x), va.x); v.y = __fmul_rn(__fadd_rn(x.y, mu.y), va.y);
+    v.z = __fmul_rn(__fadd_rn(x.z, mu.z), va.z); v.w = __fmul_rn(__fadd_rn(x.w, mu.w), va.w);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + (size_t)r * V_IN + c) = pk;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)r * V_IN + c) = v;
   }
 }
 
-// causal FSMN memory block: y[t][c] = x[t][c] + sum_{k<20} w[c][k] x[t - 19 + k][c] (rows before the recording start are zero)
-__global__ void __launch_bounds__(128)
+// causal FSMN memory block: y[t][c] = x[t][c] + sum_{k<20} w[c][k] x[t - 19 + k][c] (rows before the recording start are zero).
+// A block stages 64 output rows plus their 19 predecessors in shared memory (one coalesced pass over x) and every thread owns
+// two channels of 8 consecutive rows.
+constexpr int VF_ROWS = 64;
+__global__ void __launch_bounds__(512)
 vad_fsmn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w_t /*[20][128]*/, const int2* __restrict__ row_info, int rows,
                 __nv_bfloat16* __restrict__ y) {
   pdl_wait();
   pdl_launch_dependents();
-  const int c = threadIdx.x;
-  const int r0 = blockIdx.x * 32;
-  float w[V_LORDER];
+  __shared__ __nv_bfloat162 tile[VF_ROWS + V_LORDER - 1][V_PROJ / 2];
+  __shared__ int t_of[VF_ROWS];
+  const int r0 = blockIdx.x * VF_ROWS;
+  const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(x);
+  for (int i = threadIdx.x; i < (VF_ROWS + V_LORDER - 1) * (V_PROJ / 2); i += blockDim.x) {
+    const int rr = i / (V_PROJ / 2), cc = i - rr * (V_PROJ / 2);
+    const int r = r0 - (V_LORDER - 1) + rr;
+    tile[rr][cc] = (r >= 0 && r < rows) ? x2[(size_t)r * (V_PROJ / 2) + cc] : __floats2bfloat162_rn(0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < VF_ROWS; i += blockDim.x) t_of[i] = r0 + i < rows ? row_info[r0 + i].x : 0;
+  __syncthreads();
+  const int cc = threadIdx.x & 63, g = threadIdx.x >> 6;     // channel pair, row group (8 groups of 8 rows)
+  float2 w[V_LORDER];
 #pragma unroll
-  for (int k = 0; k < V_LORDER; ++k) w[k] = w_t[k * V_PROJ + c];
-  for (int rr = 0; rr < 32; ++rr) {
-    const int r = r0 + rr;
+  for (int k = 0; k < V_LORDER; ++k) w[k] = make_float2(w_t[k * V_PROJ + 2 * cc], w_t[k * V_PROJ + 2 * cc + 1]);
+#pragma unroll 2
+  for (int i = 0; i < 8; ++i) {
+    const int rr = g * 8 + i, r = r0 + rr;
     if (r >= rows) return;
-    const int t = row_info[r].x;
-    float acc = __bfloat162float(x[(size_t)r * V_PROJ + c]);
+    const int t = t_of[rr];
+    float2 acc = __bfloat1622float2(tile[rr + V_LORDER - 1][cc]);
 #pragma unroll
     for (int k = 0; k < V_LORDER; ++k) {
       const int back = V_LORDER - 1 - k;   // tap k looks `back` frames into the past
-      if (back <= t) acc += w[k] * __bfloat162float(x[(size_t)(r - back) * V_PROJ + c]);
+      if (back <= t) {
+        const float2 v = __bfloat1622float2(tile[rr + k][cc]);
+        acc.x += w[k].x * v.x;
+        acc.y += w[k].y * v.y;
+      }
     }
-    y[(size_t)r * V_PROJ + c] = __float2bfloat16(acc);
+    reinterpret_cast<__nv_bfloat162*>(y)[(size_t)r * (V_PROJ / 2) + cc] = __floats2bfloat162_rn(acc.x, acc.y);
   }
 }
 
@@ -281,7 +309,7 @@ int b200pf_vad_scores_s16(b200pf_vad* v, const int16_t* pcm, const int64_t* offs
   if (feats && !v->x400_f32) VCK(cudaMalloc((void**)&v->x400_f32, (size_t)v->max_frames * V_IN * 4), "cudaMalloc(vad feats)");
   int rc = fbank_launch(v->d_pcm, 0, v->d_sample_off, v->d_fb_off, n_rec, frames, v->ft, v->fb, s);
   if (rc) return check_cuda((cudaError_t)rc, "vad fbank");
-  rc = launch_kernel(vad_lfr_cmvn_kernel, dim3(frames), dim3(128), 0, s, (const float*)v->fb, (const int2*)v->d_row_info, (const int*)v->d_row_start,
+  rc = launch_kernel(vad_lfr_cmvn_kernel, dim3((frames + 7) / 8), dim3(128), 0, s, (const float*)v->fb, (const int2*)v->d_row_info, (const int*)v->d_row_start,
                      frames, (const float*)v->mean, (const float*)v->var, v->x400, feats ? v->x400_f32 : (float*)nullptr);
   if (rc) return check_cuda((cudaError_t)rc, "vad lfr");
   auto gemm = [&](const __nv_bfloat16* A, int lda, const Linear& W, int relu, __nv_bfloat16* ob, int ldo, float* of, int ldof) {
@@ -295,7 +323,7 @@ int b200pf_vad_scores_s16(b200pf_vad* v, const int16_t* pcm, const int64_t* offs
   if ((rc = gemm(v->a1, V_A1, v->in2, 1, v->a2, V_LIN, nullptr, 0))) return check_cuda((cudaError_t)rc, "vad gemm in2");
   for (int l = 0; l < V_LAYERS; ++l) {
     if ((rc = gemm(v->a2, V_LIN, v->proj[l], 0, v->p, V_PROJ, nullptr, 0))) return check_cuda((cudaError_t)rc, "vad gemm proj");
-    rc = launch_kernel(vad_fsmn_kernel, dim3((frames + 31) / 32), dim3(128), 0, s, (const __nv_bfloat16*)v->p, (const float*)v->fsmn_w[l],
+    rc = launch_kernel(vad_fsmn_kernel, dim3((frames + VF_ROWS - 1) / VF_ROWS), dim3(512), 0, s, (const __nv_bfloat16*)v->p, (const float*)v->fsmn_w[l],
                        (const int2*)v->d_row_info, frames, v->mbuf);
     if (rc) return check_cuda((cudaError_t)rc, "vad fsmn");
     if ((rc = gemm(v->mbuf, V_PROJ, v->aff[l], 1, v->a2, V_LIN, nullptr, 0))) return check_cuda((cudaError_t)rc, "vad gemm affine");

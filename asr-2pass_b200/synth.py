@@ -246,7 +246,7 @@ def write_synthetic_model_dir(path, cfg=None, seed=0, jitter_ln=False, lang="zh-
 
 
 # ---- CT-Transformer punctuation model ---------------------------------------------------------
-PUNC_CFG = dict(vocab=272727, d_model=256, n_heads=8, d_ff=1024, n_layers=4, kernel=11, n_punc=6, ln_eps=1e-12)
+PUNC_CFG = dict(vocab=272727, d_model=256, n_heads=8, d_ff=1024, n_layers=4, kernel=11, n_punc=6, ln_eps=1e-12, sanm_shift=0)
 PUNC_LIST = ["<unk>", "_", "，", "。", "？", "、"]
 
 

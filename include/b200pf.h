@@ -188,6 +188,12 @@ int b200pf_punc_info(const b200pf_punc* p, int* vocab, int* n_punc, int* d_model
  * receives the first maximum over classes [0, n_punc - 1) of every token -- the reference's Argmax(row, row + CANDIDATE_NUM - 1)
  * never selects the last class (ct-transformer.cpp:191-195).  logits_out (optional) [offsets[n_seq], n_punc]. */
 int b200pf_punc_infer(b200pf_punc* p, const int32_t* ids, const int32_t* offsets, int n_seq, int32_t* punc_out, float* logits_out);
+/* The realtime model (CTTransformerOnline::Infer, ct-transformer-online.cpp:139-217): the same call with the reference's VadMask per
+ * sequence -- with 0 < vad_pos[i] < T_i, tokens before vad_pos[i] - 1 do not attend to tokens from vad_pos[i] on (:219-233; the
+ * reference feeds this mask to BOTH mask inputs of its session).  vad_pos NULL = no mask.  The realtime model's causal FSMN comes
+ * from the config key sanm_shift of punc.b200pf (left context (kernel - 1) / 2 + sanm_shift). */
+int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* offsets, const int32_t* vad_pos, int n_seq, int32_t* punc_out,
+                          float* logits_out);
 /* Kernels launched by b200pf_punc_infer so far. */
 long long b200pf_punc_launches(const b200pf_punc* p);
 

@@ -73,6 +73,13 @@ int b200pf_host_punc_add_scripted(const char* const* tokens, int n_tokens, const
 /* CTTransformerInit / CTTransformerInfer(PUNC_OFFLINE) / CTTransformerUninit (funasrruntime.h:92-96) over the B200 punctuation
  * engine: <punc_dir>/{punc.b200pf, tokens.json, punc_list.json}.  add_batch punctuates n texts in lock step (one engine call per
  * round for all of them); results are written back to back, each NUL-terminated; returns the bytes used. */
+/* The realtime model, funasr::CTTransformerOnline (ct-transformer-online.cpp): AddPunc(text, cache).  The word cache travels as one
+ * string, every word followed by '\x01'.  _scripted: the walk with the scripted network (seed + 13 * vad_pos), no GPU. */
+int b200pf_host_punc_online_add_scripted(const char* const* tokens, int n_tokens, const char* const* punc_list, int n_punc, const char* text,
+                                         const char* cache_in, int seed, int every, char* out, int cap, char* cache_out, int cache_cap);
+void* b200pf_host_punc_online_create(const char* punc_dir, int device, int max_tokens);
+void b200pf_host_punc_online_destroy(void* h);
+int b200pf_host_punc_online_add(void* h, const char* text, const char* cache_in, char* out, int cap, char* cache_out, int cache_cap);
 void* b200pf_host_punc_create(const char* punc_dir, int device, int max_tokens);
 void b200pf_host_punc_destroy(void* h);
 /* Engine calls (lock-step rounds) made so far: concurrent add calls share rounds. */

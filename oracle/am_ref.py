@@ -48,6 +48,10 @@ def lib():
         L.ref_punc_create.argtypes = [C.c_char_p] * 3
         L.ref_punc_destroy.argtypes = [C.c_void_p]
         L.ref_punc_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_punc_online_create.restype = C.c_void_p
+        L.ref_punc_online_create.argtypes = [C.c_char_p] * 3
+        L.ref_punc_online_destroy.argtypes = [C.c_void_p]
+        L.ref_punc_online_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -142,4 +146,30 @@ class RefPunc:
     def close(self):
         if self.h:
             lib().ref_punc_destroy(self.h)
+            self.h = None
+
+
+class RefPuncOnline:
+    """funasr::CTTransformerOnline: AddPunc(text, cache, lang); the session gets (ids, lengths, vad_mask, sub_masks)."""
+
+    def __init__(self, model_dir, net, tag="0"):
+        d = os.path.abspath(model_dir)
+        pm = os.path.join(d, "punc_online_%s.onnx" % tag)
+        register_network(pm, 4, 1, net)
+        self.h = lib().ref_punc_online_create(pm.encode(), os.path.join(d, "config.yaml").encode(), os.path.join(d, "tokens.json").encode())
+
+    def add_punc(self, text, cache, lang="zh-cn"):
+        """cache: list of bytes, updated in place.  Returns the punctuated text of this call."""
+        raw = text.encode("utf-8")
+        cin = b"".join(w + b"\x01" for w in cache)
+        cap = max(1 << 16, 16 * (len(raw) + len(cin)) + 64)
+        buf, cbuf = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        n = lib().ref_punc_online_add(self.h, raw, cin, lang.encode(), buf, cap, cbuf, cap)
+        assert n >= 0
+        cache[:] = [w for w in cbuf.value.split(b"\x01")[:-1]]
+        return buf.value.decode("utf-8", "replace")
+
+    def close(self):
+        if self.h:
+            lib().ref_punc_online_destroy(self.h)
             self.h = None

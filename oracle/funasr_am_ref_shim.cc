@@ -62,4 +62,25 @@ void ref_punc_destroy(void* h) { delete (funasr::CTTransformer*)h; }
 int ref_punc_add(void* h, const char* text, const char* lang, char* out, int cap) {
   return CopyOut(((funasr::CTTransformer*)h)->AddPunc(text, std::string(lang)), out, cap);
 }
+
+// funasr::CTTransformerOnline (ct-transformer-online.cpp): the realtime punctuation model the 2-pass server uses for both legs
+// (funasrruntime.cpp:545,610).  The word cache travels as one string, words separated by '\x01'.
+void* ref_punc_online_create(const char* punc_model, const char* punc_config, const char* token_file) {
+  funasr::CTTransformerOnline* p = new funasr::CTTransformerOnline();
+  p->InitPunc(punc_model, punc_config, token_file, 1);
+  return p;
+}
+void ref_punc_online_destroy(void* h) { delete (funasr::CTTransformerOnline*)h; }
+int ref_punc_online_add(void* h, const char* text, const char* cache_in, const char* lang, char* out, int cap, char* cache_out, int cache_cap) {
+  std::vector<std::string> cache;
+  std::string cur;
+  for (const char* c = cache_in; *c; ++c) {
+    if (*c == '\x01') { cache.push_back(cur); cur.clear(); } else cur += *c;
+  }
+  const int n = CopyOut(((funasr::CTTransformerOnline*)h)->AddPunc(text, cache, std::string(lang)), out, cap);
+  std::string joined;
+  for (const std::string& w : cache) joined += w + '\x01';
+  if (CopyOut(joined, cache_out, cache_cap) < 0) return -1;
+  return n;
+}
 }  // extern "C"

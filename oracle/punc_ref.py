@@ -57,9 +57,37 @@ def param_shapes(cfg):
     return out
 
 
-def forward(ids, W, cfg, emu=False):
-    """ids int [T] -> logits float32 [T, n_punc].  emu=True rounds to bf16 where the CUDA path stores bf16."""
+def vad_mask(T, vad_pos):
+    """CTTransformerOnline::VadMask (ct-transformer-online.cpp:219-233): [T, T] of ones; with 0 < vad_pos < T rows before
+    vad_pos - 1 are zero from column vad_pos on."""
+    m = np.ones((T, T), np.float32)
+    if 0 < vad_pos < T:
+        m[:max(0, vad_pos - 1), vad_pos:] = 0.0
+    return m
+
+
+def _fsmn_shift(v, w, K, shift):
+    left = (K - 1) // 2 + shift
+    x = torch.nn.functional.pad(v.t()[None], (left, K - 1 - left))
+    return torch.nn.functional.conv1d(x, w, None, groups=w.shape[0])[0].t() + v
+
+
+def _mha_masked(q, k, v, H, scale, mask):
+    T, D = q.shape
+    dk = D // H
+    qh, kh, vh = (t.reshape(T, H, dk).transpose(0, 1) for t in (q, k, v))
+    s = (qh @ kh.transpose(1, 2)) * scale
+    if mask is not None:
+        s = s.masked_fill(torch.as_tensor(mask)[None] == 0, float("-inf"))
+    return (torch.softmax(s, dim=-1) @ vh).transpose(0, 1).reshape(T, D)
+
+
+def forward(ids, W, cfg, emu=False, mask=None):
+    """ids int [T] -> logits float32 [T, n_punc].  emu=True rounds to bf16 where the CUDA path stores bf16.  mask [T, T]
+    (realtime model): the attention mask of EVERY layer -- the reference feeds its VadMask to both the vad_mask and the
+    sub_masks input of the session (ct-transformer-online.cpp:163-183); cfg["sanm_shift"] shifts the FSMN window left."""
     D, H = cfg["d_model"], cfg["n_heads"]
+    shift = int(cfg.get("sanm_shift", 0))
     ids = torch.as_tensor(np.asarray(ids), dtype=torch.long)
     T = ids.shape[0]
     x = W["embed.weight"][ids] * (D ** 0.5) + R.pos_enc(T, D)
@@ -69,8 +97,8 @@ def forward(ids, W, cfg, emu=False):
         h = R._ln(x, W, p + ".norm1", cfg["ln_eps"])
         qkv = R._lin(h, W, p + ".self_attn.linear_q_k_v", emu)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
-        mem = R._fsmn(v, W[p + ".self_attn.fsmn_block.weight"], cfg["kernel"])
-        att = R._rb(R._mha_scaled(q, k, v, H, scale, False), emu)
+        mem = _fsmn_shift(v, W[p + ".self_attn.fsmn_block.weight"], cfg["kernel"], shift)
+        att = R._rb(_mha_masked(q, k, v, H, scale, mask), emu)
         x = x + R._lin(att, W, p + ".self_attn.linear_out", emu) + mem        # in_size == size: the residual applies in layer 0 too
         h2 = R._ln(x, W, p + ".norm2", cfg["ln_eps"])
         f1 = R._rb(torch.relu(R._lin(h2, W, p + ".feed_forward.w_1", emu)), emu)
@@ -198,3 +226,63 @@ def add_punc(text, tok: Tokenizer, infer, language="zh-cn"):
         for zh, en in (("，", b","), ("。", b"."), ("、", b","), ("？", b"?")):
             res = res.replace(zh.encode("utf-8"), en)
     return res.decode("utf-8", "replace")
+
+
+def add_punc_online(text, cache, tok: Tokenizer, infer, language="zh-cn"):
+    """funasr::CTTransformerOnline::AddPunc (ct-transformer-online.cpp:40-137).  cache: list of bytes (words kept from earlier
+    calls), updated IN PLACE like arr_cache.  infer(ids, vad_pos) -> class per token; vad_pos = len(cache) at call time for every
+    mini-sentence of the call."""
+    P = [p.encode("utf-8") for p in tok.punc]
+    raw = text.encode("utf-8") if isinstance(text, str) else text
+    full = b"".join(cache)
+    if len(full) > 0 and not (full[-1] & 0x80) and len(raw) > 0 and not (raw[0] & 0x80):
+        full += b" "
+    full += raw
+    pieces, ids = tok.tokenize(full)
+    n_cache = len(cache)
+    n_total = int(math.ceil(np.float32(len(ids)) / TOKEN_LEN))
+    remain_ids, remain_str = [], []
+    punc_ids, punc_strs, words = [], [], []
+    for i in range(0, len(ids), TOKEN_LEN):
+        in_ids = remain_ids + ids[i:i + TOKEN_LEN]
+        in_str = remain_str + pieces[i:i + TOKEN_LEN]
+        punc = list(infer(in_ids, n_cache))
+        if i // TOKEN_LEN < n_total - 1:
+            sent_end, last_comma = -1, -1
+            for k in range(len(punc) - 2, 0, -1):
+                if P[punc[k]] == P[PERIOD] or P[punc[k]] == P[QUESTION]:
+                    sent_end = k
+                    break
+                if last_comma < 0 and P[punc[k]] == P[COMMA]:
+                    last_comma = k
+            if sent_end < 0 and len(in_str) > CACHE_POP_TRIGGER_LIMIT and last_comma > 0:
+                sent_end = last_comma
+                punc[sent_end] = PERIOD
+            remain_str = in_str[sent_end + 1:]
+            remain_ids = in_ids[sent_end + 1:]
+            in_str = in_str[:sent_end + 1]
+            punc = punc[:sent_end + 1]
+        punc_strs += [P[c] for c in punc]
+        words += in_str
+        punc_ids += punc
+    out, punc_out, skip = [], [], 0
+    for i in range(len(words)):
+        if not (words[i][0] & 0x80) and i + 1 < len(words) and not (words[i + 1][0] & 0x80):
+            words[i] = words[i] + b" "
+        if skip < n_cache:
+            skip += 1
+        else:
+            out.append(words[i])
+        if skip >= n_cache:
+            punc_out.append(punc_strs[i])
+            if punc_strs[i] != b"_":
+                out.append(punc_strs[i])
+    sent_end = -1
+    for i in range(len(punc_strs) - 2, 0, -1):
+        if punc_ids[i] == PERIOD or punc_ids[i] == QUESTION:
+            sent_end = i
+            break
+    cache[:] = words[sent_end + 1:]
+    if len(out) > 0 and out[-1] in P:
+        out = out[:-1]
+    return b"".join(out).decode("utf-8", "replace")

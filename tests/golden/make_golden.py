@@ -241,9 +241,29 @@ def make_punc_golden(synth):
             state.update(seed=s, every=every, seen=[])
             cases.append(dict(text=text, lang=lang, seed=s, every=every, out=ref.add_punc(text, lang), ids=ids))
     ref.close()
+    # the realtime model (ct-transformer-online.cpp): multi-turn sessions with the word cache carried from call to call
+    ost = dict(seed=0, every=0, vad_pos=0)
+
+    def onet(ins):
+        cls = TP._online_script(ins[0][0], ost["seed"], ost["every"], ost["vad_pos"])
+        lg = np.full((1, len(cls), 6), -5.0, np.float32)
+        lg[0, np.arange(len(cls)), cls] = 5.0
+        lg[0, :, 5] = 9.0
+        return [lg]
+
+    oref = A.RefPuncOnline(d, onet, tag="golden")
+    online = []
+    for s, turns in TP._online_sessions(synth, toks, 40):
+        cache, rec = [], []
+        for text, every in turns:
+            ost.update(seed=s, every=every, vad_pos=len(cache))
+            out = oref.add_punc(text, cache)
+            rec.append(dict(text=text, every=every, out=out, cache=[w.decode("utf-8", "replace") for w in cache]))
+        online.append(dict(seed=s, turns=rec))
+    oref.close()
     with open(os.path.join(HERE, "punc_golden.json"), "w", encoding="utf-8") as f:
-        json.dump(dict(source="reference onnxruntime/src/{ct-transformer,tokenizer}.cpp compiled in place over oracle/fake_ort.cc; scripted network",
-                       vocab=TP.SMALL["vocab"], cases=cases), f, ensure_ascii=False)
+        json.dump(dict(source="reference onnxruntime/src/{ct-transformer,ct-transformer-online,tokenizer}.cpp compiled in place over oracle/fake_ort.cc; scripted network",
+                       vocab=TP.SMALL["vocab"], cases=cases, online=online), f, ensure_ascii=False)
 
 
 def make_am_golden(synth):

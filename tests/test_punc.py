@@ -127,6 +127,76 @@ def test_host_walk_matches_reference_golden(capi, synth):
         assert host.add_punc_scripted(c["text"], c["lang"], c["seed"], c["every"]) == c["out"], c["text"][:60]
 
 
+def _online_script(ids, seed, every, vad_pos):
+    return scripted_punc(ids, seed + 13 * vad_pos, every)
+
+
+def _online_sessions(synth, toks, n_sessions, turns=6):
+    for s in range(n_sessions):
+        rng = np.random.default_rng(5000 + s)
+        out = []
+        for turn in range(turns):
+            k = int(rng.integers(0, 70 if s % 9 else 300))
+            out.append((synth.make_text(k, 100 * s + turn, toks) if rng.random() > 0.1 else "", [0, 50, 7][turn % 3]))
+        yield s, out
+
+
+def test_online_walk_matches_live_reference(capi, synth, tmp_path):
+    """The realtime model's AddPunc(text, cache) -- oracle restatement AND C++ host mirror -- against the reference's compiled
+    ct-transformer-online.cpp over multi-turn sessions, with a scripted network that depends on the VAD position, and a check that
+    the mask the reference hands to its session is VadMask(T, cache size) on both mask inputs."""
+    if not A.available():
+        pytest.skip("oracle/_ref/libfunasr_am_ref.so not built (needs /root/reference)")
+    d = str(tmp_path)
+    cfg, W, toks = synth.write_synthetic_punc_dir(d, SMALL, seed=0)
+    tok = PR.Tokenizer(toks)
+    host = capi.HostPuncTokenizer(toks, synth.PUNC_LIST)
+    st = dict(seed=0, every=0, vad_pos=0, bad=0, masked=0)
+
+    def net(ins):
+        ids, lens, vm, sm = ins
+        T = ids.shape[1]
+        assert vm.shape == (1, 1, T, T) and np.array_equal(vm, sm) and int(lens[0]) == T
+        if not np.array_equal(vm[0, 0], PR.vad_mask(T, st["vad_pos"])):
+            st["bad"] += 1
+        st["masked"] += int((vm == 0).any())
+        cls = _online_script(ids[0], st["seed"], st["every"], st["vad_pos"])
+        lg = np.full((1, T, 6), -5.0, np.float32)
+        lg[0, np.arange(T), cls] = 5.0
+        lg[0, :, 5] = 9.0
+        return [lg]
+
+    ref = A.RefPuncOnline(d, net, tag="live")
+    n = 0
+    for s, turns in _online_sessions(synth, toks, 80):
+        c_ref, c_or, c_host = [], [], []
+        for text, every in turns:
+            st.update(seed=s, every=every, vad_pos=len(c_ref))
+            a = ref.add_punc(text, c_ref)
+            b = PR.add_punc_online(text, c_or, tok, lambda ids, v: _online_script(ids, s, every, v))
+            c = host.add_punc_online_scripted(text, c_host, s, every)
+            assert a == b == c, (s, text[:40])
+            assert c_ref == c_or == c_host
+            n += 1
+    assert n == 480 and st["bad"] == 0 and st["masked"] > 50
+    ref.close()
+
+
+def test_online_walk_matches_reference_golden(capi, synth):
+    g = json.load(open(os.path.join(HERE, "golden", "punc_golden.json"), encoding="utf-8"))
+    toks = synth.make_punc_tokens(int(g["vocab"]))
+    tok = PR.Tokenizer(toks)
+    host = capi.HostPuncTokenizer(toks, synth.PUNC_LIST)
+    assert len(g["online"]) >= 30
+    for sess in g["online"]:
+        c_or, c_host = [], []
+        for turn in sess["turns"]:
+            b = PR.add_punc_online(turn["text"], c_or, tok, lambda ids, v: _online_script(ids, sess["seed"], turn["every"], v))
+            c = host.add_punc_online_scripted(turn["text"], c_host, sess["seed"], turn["every"])
+            assert b == c == turn["out"], turn["text"][:40]
+            assert [w.decode("utf-8", "replace") for w in c_or] == turn["cache"] == [w.decode("utf-8", "replace") for w in c_host]
+
+
 def test_oracle_addpunc_matches_reference_golden(synth):
     g = json.load(open(os.path.join(HERE, "golden", "punc_golden.json"), encoding="utf-8"))
     toks = synth.make_punc_tokens(int(g["vocab"]))
@@ -269,3 +339,37 @@ def test_offline_shim_vad_asr_punc_chain(capi, synth, gpu, tmp_path):
     assert sum(len(s["ts_list"]) for s in json.loads(ss1)) <= len(json.loads(st1))
     for h in (plain, full, punc):
         h.close()
+
+
+@pytest.mark.gpu
+def test_realtime_punc_network_and_host(capi, synth, gpu, tmp_path):
+    """The realtime model: VadMask attention + causal FSMN (sanm_shift) through the C ABI against the fp32 oracle, and
+    CTTransformerOnlineB200::AddPunc over a multi-turn session against the oracle walk driven by the GPU's own classes."""
+    d = str(tmp_path)
+    cfg, W, toks = synth.write_synthetic_punc_dir(d, dict(vocab=20000, n_layers=3, sanm_shift=5), seed=7)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    eng = capi.PuncEngine(d, max_tokens=4096)
+    rng = np.random.default_rng(1)
+    lens = [1, 5, 20, 33, 47, 64, 130, 9]
+    vps = [0, 3, 7, 32, 1, 70, 66, 8]           # incl. vad_pos <= 1 and >= T: no mask
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    ids = rng.integers(0, cfg["vocab"], offs[-1]).astype(np.int32)
+    cls, lg = eng.infer(ids, offs, logits=True, vad_pos=vps)
+    worst = 0.0
+    for i, n in enumerate(lens):
+        ref = PR.forward(ids[offs[i]:offs[i + 1]], Wt, cfg, mask=PR.vad_mask(n, vps[i])).numpy()
+        worst = max(worst, float(np.abs(lg[offs[i]:offs[i + 1]] - ref).max()))
+    print("realtime punc: max |logit - oracle| = %.4f" % worst)
+    assert worst <= 3e-2
+    cls0, lg0 = eng.infer(ids, offs, logits=True)               # without the mask the masked sequences change
+    assert not np.array_equal(lg0[offs[3]:offs[4]], lg[offs[3]:offs[4]]) and np.array_equal(lg0[offs[4]:offs[5]], lg[offs[4]:offs[5]])
+    host = capi.HostPuncOnline(d, max_tokens=4096)
+    tok = PR.Tokenizer(toks)
+    c_host, c_or = [], []
+    for turn in range(8):
+        text = synth.make_text(int(rng.integers(5, 90)), 900 + turn, toks)
+        got = host.add_punc(text, c_host)
+        exp = PR.add_punc_online(text, c_or, tok, lambda t, v: eng.infer(np.asarray(t, np.int32), np.array([0, len(t)], np.int32), vad_pos=[v])[0].tolist())
+        assert got == exp and c_host == c_or, turn
+    host.close()
+    eng.close()
