@@ -444,11 +444,16 @@ struct PuncResult {  // FUNASR_PUNC_RESULT, commonfunc.h
 
 FUNASR_HANDLE CTTransformerInit(std::map<std::string, std::string>& model_path, int thread_num, PUNC_TYPE type) {
   (void)thread_num;
-  if (type != PUNC_OFFLINE) { fprintf(stderr, "CTTransformerInit: the online (realtime) punctuation model stays on the reference host path\n"); return nullptr; }
   auto it = model_path.find("punc-dir");
   if (it == model_path.end()) { fprintf(stderr, "CTTransformerInit: punc-dir missing\n"); return nullptr; }
-  std::unique_ptr<funasr_b200::CTTransformerB200> p(new funasr_b200::CTTransformerB200(ToInt(model_path, "device", 0), ToInt(model_path, "punc-max-tokens", 0)));
   std::string err;
+  const int device = ToInt(model_path, "device", 0), max_tokens = ToInt(model_path, "punc-max-tokens", 0);
+  if (type == PUNC_ONLINE) {   // CreatePuncModel: PUNC_ONLINE -> CTTransformerOnline (punc-model.cpp)
+    std::unique_ptr<funasr_b200::CTTransformerOnlineB200> p(new funasr_b200::CTTransformerOnlineB200(device, max_tokens));
+    if (!p->Init(it->second, &err)) { fprintf(stderr, "CTTransformerInit: %s\n", err.c_str()); return nullptr; }
+    return (funasr_b200::PuncModel*)p.release();
+  }
+  std::unique_ptr<funasr_b200::CTTransformerB200> p(new funasr_b200::CTTransformerB200(device, max_tokens));
   if (!p->Init(it->second, &err)) { fprintf(stderr, "CTTransformerInit: %s\n", err.c_str()); return nullptr; }
   return (funasr_b200::PuncModel*)p.release();
 }

@@ -61,7 +61,8 @@ void FunASRFreeResult(FUNASR_RESULT result);
 const float FunASRGetRetSnippetTime(FUNASR_RESULT result);
 
 // PUNC (funasrruntime.h:92-96): model_path["punc-dir"] = <dir>/{punc.b200pf, tokens.json, punc_list.json}; extra keys "device",
-// "punc-max-tokens".  Only PUNC_OFFLINE (CTTransformer) is built; the realtime variant (CTTransformerOnline) is not.
+// "punc-max-tokens".  PUNC_OFFLINE -> CTTransformerB200, PUNC_ONLINE -> CTTransformerOnlineB200 (the realtime model with its word
+// cache in the result object, funasrruntime.cpp:193-198).
 FUNASR_HANDLE CTTransformerInit(std::map<std::string, std::string>& model_path, int thread_num, PUNC_TYPE type = PUNC_OFFLINE);
 FUNASR_RESULT CTTransformerInfer(FUNASR_HANDLE handle, const char* sz_sentence, FUNASR_MODE mode, QM_CALLBACK fn_callback,
                                  PUNC_TYPE type = PUNC_OFFLINE, FUNASR_RESULT pre_result = nullptr);
