@@ -134,3 +134,42 @@ def test_sentence_stamps_match_live_reference_when_built(capi):
             pairs.append("[%d,%d]" % (a, t))
         stamp = "" if k % 50 == 0 else ("[]" if k % 77 == 0 else "[" + ",".join(pairs) + "]")
         assert capi.host_sentence_stamps(text, stamp) == T.timestamp_sentence(text, stamp), (text, stamp)
+
+
+def test_checkpoint_converter_round_trip(synth, tmp_path):
+    """tools/convert_funasr.py on synthetic state_dicts (no real checkpoint exists offline): dimensions are recovered from the tensor
+    shapes, flags from the presence of the config-3 tensors, and the written file holds the same bytes."""
+    import importlib.util
+    import json
+    import torch
+    mf = importlib.import_module("asr-2pass_b200.modelfile")
+    spec = importlib.util.spec_from_file_location("convert_funasr", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "convert_funasr.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    d = str(tmp_path)
+    cfg, W = synth.make_weights(dict(n_enc=3, n_dec=2, timestamp=1, contextual=1, d_model=64, d_ff=128, feat_dim=80, vocab=300, n_heads=4), seed=1)
+    sd = {k: torch.from_numpy(v) for k, v in W.items()}
+    sd["some.unused.buffer"] = torch.zeros(3)
+    torch.save({"state_dict": sd}, os.path.join(d, "am.pt"))
+    with open(os.path.join(d, "am.yaml"), "w") as f:
+        f.write("encoder_conf:\n  attention_heads: 4\npredictor_conf:\n  threshold: 1.0\n  tail_threshold: 0.45\n")
+    conv.main(["am", "--checkpoint", os.path.join(d, "am.pt"), "--config", os.path.join(d, "am.yaml"), "--out-dir", os.path.join(d, "am")])
+    c2, W2 = mf.read_weights(os.path.join(d, "am", "model.b200pf"))
+    for k in ("feat_dim", "d_model", "n_heads", "d_ff", "n_enc", "n_dec", "kernel", "vocab", "timestamp", "contextual"):
+        assert int(c2[k]) == int(cfg[k]), k
+    assert set(W2) == set(W) and all(np.array_equal(W2[k], W[k]) for k in W)
+    pcfg, PW = synth.make_punc_weights(dict(vocab=500, d_model=64, n_heads=4, d_ff=128, n_layers=3, sanm_shift=5), seed=2)
+    torch.save({k: torch.from_numpy(v) for k, v in PW.items()}, os.path.join(d, "punc.pt"))
+    with open(os.path.join(d, "punc.yaml"), "w", encoding="utf-8") as f:
+        f.write("encoder_conf:\n  attention_heads: 4\n  sanm_shfit: 5\nmodel_conf:\n  punc_list:\n" + "".join('  - "%s"\n' % p for p in synth.PUNC_LIST))
+    conv.main(["punc", "--checkpoint", os.path.join(d, "punc.pt"), "--config", os.path.join(d, "punc.yaml"), "--out-dir", os.path.join(d, "punc")])
+    c3, W3 = mf.read_weights(os.path.join(d, "punc", "punc.b200pf"))
+    assert {k: int(c3[k]) for k in ("vocab", "d_model", "n_heads", "d_ff", "n_layers", "kernel", "n_punc", "sanm_shift")} == \
+        {k: int(pcfg[k]) for k in ("vocab", "d_model", "n_heads", "d_ff", "n_layers", "kernel", "n_punc", "sanm_shift")}
+    assert json.load(open(os.path.join(d, "punc", "punc_list.json"), encoding="utf-8")) == synth.PUNC_LIST
+    assert all(np.array_equal(W3[k], PW[k]) for k in PW)
+    VW = synth.make_vad_weights(3)
+    torch.save({k: torch.from_numpy(v) for k, v in VW.items()}, os.path.join(d, "vad.pt"))
+    conv.main(["vad", "--checkpoint", os.path.join(d, "vad.pt"), "--out-dir", os.path.join(d, "vad")])
+    _, W4 = mf.read_weights(os.path.join(d, "vad", "vad.b200pf"))
+    assert all(np.array_equal(W4[k], VW[k]) for k in VW)
