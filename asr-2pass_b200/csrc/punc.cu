@@ -115,9 +115,9 @@ punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, 
                  __nv_bfloat16* __restrict__ ctx, int Dp) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ float Ks[32][P_MAX_DK + 1];
+  __shared__ __align__(16) float Ks[32][P_MAX_DK + 4];   // row stride 68 floats: float4 reads of 8 consecutive rows hit 32 distinct banks
   __shared__ __align__(16) float Vs[32][P_MAX_DK];
-  __shared__ float Qs[P_QTILE][P_MAX_DK];
+  __shared__ __align__(16) float Qs[P_QTILE][P_MAX_DK];
   const int4 tl = tiles[blockIdx.x];     // {first row of the tile, queries in the tile, first row of the sequence, sequence length}
   // realtime model (CTTransformerOnline::VadMask, ct-transformer-online.cpp:219-233): with 0 < vad_pos < T, queries before
   // vad_pos - 1 do not see keys from vad_pos on; everything else sees the whole sequence
@@ -169,7 +169,7 @@ punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, 
         const int i = threadIdx.x + u * 128;
         if (i < 32 * dk4) {
           const int j = i / dk4, d = (i - j * dk4) << 2;
-          Ks[j][d] = kr[u].x; Ks[j][d + 1] = kr[u].y; Ks[j][d + 2] = kr[u].z; Ks[j][d + 3] = kr[u].w;
+          *reinterpret_cast<float4*>(&Ks[j][d]) = kr[u];
           *reinterpret_cast<float4*>(&Vs[j][d]) = vr[u];
         }
       }
@@ -191,7 +191,14 @@ punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, 
       if (k0 >= k_end) continue;     // warp-uniform: this chunk is entirely masked for the query
       const bool key_ok = k0 + lane < k_end;
       float s = 0.f;
-      for (int d = 0; d < dk; ++d) s += Qs[q][d] * Ks[lane][d];
+      if (vec) {
+        for (int d = 0; d < dk; d += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(&Qs[q][d]), b = *reinterpret_cast<const float4*>(&Ks[lane][d]);
+          s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+      } else {
+        for (int d = 0; d < dk; ++d) s += Qs[q][d] * Ks[lane][d];
+      }
       s = key_ok ? s : -INFINITY;
       float mx = s;
 #pragma unroll
@@ -205,10 +212,16 @@ punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, 
       l[i] = l[i] * corr + ps;
       m[i] = m_new;
       float acc0 = a0[i] * corr, acc1 = a1[i] * corr;
-      for (int j = 0; j < 32; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, p, j);
-        acc0 += pj * Vs[j][lane];
-        if (dk > 32) acc1 += pj * Vs[j][lane + 32 < P_MAX_DK ? lane + 32 : lane];
+      if (dk > 32) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, p, j);
+          acc0 += pj * Vs[j][lane];
+          acc1 += pj * Vs[j][lane + 32];
+        }
+      } else {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) acc0 += __shfl_sync(0xffffffffu, p, j) * Vs[j][lane];
       }
       a0[i] = acc0;
       a1[i] = acc1;

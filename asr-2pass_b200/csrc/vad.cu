@@ -65,14 +65,29 @@ vad_fsmn_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w
                 __nv_bfloat16* __restrict__ y) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ __nv_bfloat162 tile[VF_ROWS + V_LORDER - 1][V_PROJ / 2];
+  __shared__ __align__(16) __nv_bfloat162 tile[VF_ROWS + V_LORDER - 1][V_PROJ / 2];
   __shared__ int t_of[VF_ROWS];
   const int r0 = blockIdx.x * VF_ROWS;
-  const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(x);
-  for (int i = threadIdx.x; i < (VF_ROWS + V_LORDER - 1) * (V_PROJ / 2); i += blockDim.x) {
-    const int rr = i / (V_PROJ / 2), cc = i - rr * (V_PROJ / 2);
-    const int r = r0 - (V_LORDER - 1) + rr;
-    tile[rr][cc] = (r >= 0 && r < rows) ? x2[(size_t)r * (V_PROJ / 2) + cc] : __floats2bfloat162_rn(0.f, 0.f);
+  // 83 rows x 256 B as 16-byte pieces: every thread issues its (up to 3) global loads before the first shared-memory store
+  constexpr int kPieces = (VF_ROWS + V_LORDER - 1) * (V_PROJ / 8);
+  uint4 piece[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + u * 512;
+    piece[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < kPieces) {
+      const int rr = i / (V_PROJ / 8), c8 = i - rr * (V_PROJ / 8);
+      const int r = r0 - (V_LORDER - 1) + rr;
+      if (r >= 0 && r < rows) piece[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * V_PROJ + c8 * 8);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + u * 512;
+    if (i < kPieces) {
+      const int rr = i / (V_PROJ / 8), c8 = i - rr * (V_PROJ / 8);
+      *reinterpret_cast<uint4*>(&tile[rr][c8 * 4]) = piece[u];
+    }
   }
   for (int i = threadIdx.x; i < VF_ROWS; i += blockDim.x) t_of[i] = r0 + i < rows ? row_info[r0 + i].x : 0;
   __syncthreads();
