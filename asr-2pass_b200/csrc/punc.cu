@@ -12,6 +12,7 @@
 // residual stream, LN statistics, softmax and the classifier output are fp32.  The other kernels here are small and bandwidth /
 // latency bound: sequences are tens to hundreds of tokens.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -238,6 +239,177 @@ punc_attn_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, 
   }
 }
 
+// ---- tensor-core attention (the product path) ----------------------------------------------------------------------------
+// mma.sync.m16n8k8 TF32 (fp32 operands, 10-bit mantissa, fp32 accumulate).  Block = (64-query tile of one sequence, head), one
+// warp per 16 queries; K / V of the sequence stream through shared memory 64 keys at a time (row stride 68 floats: every fragment
+// load below touches 32 distinct banks); Q fragments live in registers.  S = Q K^T for the chunk sits in the accumulator layout
+// (row g / g + 8, keys 2t, 2t + 1 of each 8-key block); the same registers are the A operand of P V once the key order of the V
+// fragment follows that layout (k index t -> key 2t, t + 4 -> key 2t + 1), so P never leaves the registers.  Online softmax
+// across chunks; the realtime model's VadMask is a per-row key limit.
+constexpr int PT_Q = 64, PT_K = 64, PT_LD = 68;
+
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int NB>   // NB = head dim rounded up to a multiple of 8, divided by 8 (4, 6 or 8)
+__global__ void __launch_bounds__(128)
+punc_attn_mma_kernel(const float* __restrict__ qkv, const int4* __restrict__ tiles, const int* __restrict__ tile_vad, int D, int dk, float scale,
+                     __nv_bfloat16* __restrict__ ctx, int Dp) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ __align__(16) float Ks[PT_K][PT_LD];
+  __shared__ __align__(16) float Vs[PT_K][PT_LD];
+  const int4 tl = tiles[blockIdx.x];     // {first row of the tile, queries in the tile, first row of the sequence, sequence length}
+  const int vad_pos = tile_vad[blockIdx.x];
+  const int h = blockIdx.y, col = h * dk;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const size_t ld = (size_t)3 * D;
+  const int q_first = tl.x - tl.z;                 // position of the tile's first query inside its sequence
+  const int q0 = warp * 16 + g, q1 = q0 + 8;       // this thread's two query rows inside the tile
+  const bool warp_on = warp * 16 < tl.y;
+  // Q fragments (scaled): a[db] = {Q[q0][8db + t], Q[q1][8db + t], Q[q0][8db + t + 4], Q[q1][8db + t + 4]}
+  uint32_t qa[NB][4];
+#pragma unroll
+  for (int db = 0; db < NB; ++db) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = (e & 1) ? q1 : q0, d = db * 8 + t + ((e & 2) ? 4 : 0);
+      const float v = (q < tl.y && d < dk) ? qkv[(size_t)(tl.x + q) * ld + col + d] * scale : 0.f;
+      qa[db][e] = __float_as_uint(v);
+    }
+  }
+  auto k_end_of = [&](int q) { return (vad_pos > 0 && vad_pos < tl.w && q_first + q < vad_pos - 1) ? vad_pos : tl.w; };
+  const int kend0 = k_end_of(q0), kend1 = k_end_of(q1);
+  float o[NB][4];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) { o[nb][0] = 0.f; o[nb][1] = 0.f; o[nb][2] = 0.f; o[nb][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const bool vec = (dk & 3) == 0;
+  for (int k0 = 0; k0 < tl.w; k0 += PT_K) {
+    __syncthreads();
+    if (vec) {
+      const int dk4 = dk >> 2, n4 = PT_K * dk4;
+      for (int i0 = 0; i0 < n4; i0 += 128 * 4) {
+        float4 kr[4], vr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + threadIdx.x + u * 128;
+          kr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vr[u] = kr[u];
+          if (i < n4) {
+            const int j = i / dk4, d = (i - j * dk4) << 2;
+            if (k0 + j < tl.w) {
+              const float* row = qkv + (size_t)(tl.z + k0 + j) * ld + col + d;
+              kr[u] = *reinterpret_cast<const float4*>(row + D);
+              vr[u] = *reinterpret_cast<const float4*>(row + 2 * D);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + threadIdx.x + u * 128;
+          if (i < n4) {
+            const int j = i / dk4, d = (i - j * dk4) << 2;
+            *reinterpret_cast<float4*>(&Ks[j][d]) = kr[u];
+            *reinterpret_cast<float4*>(&Vs[j][d]) = vr[u];
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < PT_K * dk; i += 128) {
+        const int j = i / dk, d = i - j * dk;
+        const bool ok = k0 + j < tl.w;
+        const size_t row = (size_t)(tl.z + k0 + j) * ld;
+        Ks[j][d] = ok ? qkv[row + D + col + d] : 0.f;
+        Vs[j][d] = ok ? qkv[row + 2 * D + col + d] : 0.f;
+      }
+    }
+    if (dk < NB * 8) {   // zero the padding columns the fragments read
+      const int pad = NB * 8 - dk;
+      for (int i = threadIdx.x; i < PT_K * pad; i += 128) {
+        const int j = i / pad, d = dk + (i - j * pad);
+        Ks[j][d] = 0.f;
+        Vs[j][d] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (!warp_on) continue;
+    // S = Q K^T for 64 keys: 8 key blocks x NB dim blocks
+    float sc[8][4];
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      sc[kb][0] = 0.f; sc[kb][1] = 0.f; sc[kb][2] = 0.f; sc[kb][3] = 0.f;
+#pragma unroll
+      for (int db = 0; db < NB; ++db) {
+        const uint32_t b0 = __float_as_uint(Ks[kb * 8 + g][db * 8 + t]), b1 = __float_as_uint(Ks[kb * 8 + g][db * 8 + t + 4]);
+        mma_tf32_1688(sc[kb], qa[db], b0, b1);
+      }
+    }
+    // mask, running maximum, exponentials (accumulator layout: [0],[1] row q0 keys 2t, 2t+1; [2],[3] row q1)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const int key = k0 + kb * 8 + 2 * t;
+      if (key >= kend0) sc[kb][0] = -INFINITY;
+      if (key + 1 >= kend0) sc[kb][1] = -INFINITY;
+      if (key >= kend1) sc[kb][2] = -INFINITY;
+      if (key + 1 >= kend1) sc[kb][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sc[kb][0], sc[kb][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[kb][2], sc[kb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    // a row whose every key so far is masked keeps maximum -inf: use 0 as the reference so that exp(-inf - 0) = 0
+    const float r0 = mn0 == -INFINITY ? 0.f : mn0, r1 = mn1 == -INFINITY ? 0.f : mn1;
+    const float c0 = expf(m0 - r0), c1 = expf(m1 - r1);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      sc[kb][0] = expf(sc[kb][0] - r0); sc[kb][1] = expf(sc[kb][1] - r0);
+      sc[kb][2] = expf(sc[kb][2] - r1); sc[kb][3] = expf(sc[kb][3] - r1);
+      s0 += sc[kb][0] + sc[kb][1];
+      s1 += sc[kb][2] + sc[kb][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    l0 = l0 * c0 + s0; l1 = l1 * c1 + s1;
+    m0 = mn0; m1 = mn1;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1; }
+    // O += P V: A = P in accumulator order (k index t <-> key 2t, t + 4 <-> key 2t + 1), B rows follow the same key order
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      const uint32_t pa[4] = {__float_as_uint(sc[kb][0]), __float_as_uint(sc[kb][2]), __float_as_uint(sc[kb][1]), __float_as_uint(sc[kb][3])};
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const uint32_t b0 = __float_as_uint(Vs[kb * 8 + 2 * t][nb * 8 + g]), b1 = __float_as_uint(Vs[kb * 8 + 2 * t + 1][nb * 8 + g]);
+        mma_tf32_1688(o[nb], pa, b0, b1);
+      }
+    }
+  }
+  if (!warp_on) return;
+  // accumulator layout of O: [0],[1] -> row q0, dims 8nb + 2t, 8nb + 2t + 1; [2],[3] -> row q1
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    const int d = nb * 8 + 2 * t;
+    if (q0 < tl.y) {
+      __nv_bfloat16* dst = ctx + (size_t)(tl.x + q0) * Dp + col;
+      if (d < dk) dst[d] = __float2bfloat16(o[nb][0] * i0);
+      if (d + 1 < dk) dst[d + 1] = __float2bfloat16(o[nb][1] * i0);
+    }
+    if (q1 < tl.y) {
+      __nv_bfloat16* dst = ctx + (size_t)(tl.x + q1) * Dp + col;
+      if (d < dk) dst[d] = __float2bfloat16(o[nb][2] * i1);
+      if (d + 1 < dk) dst[d + 1] = __float2bfloat16(o[nb][3] * i1);
+    }
+  }
+}
+
 // first maximum over classes [0, n_cand) of logits [rows, ld]
 __global__ void __launch_bounds__(256)
 punc_argmax_kernel(const float* __restrict__ logits, int rows, int ld, int n_cand, int* __restrict__ out) {
@@ -460,8 +632,10 @@ int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* off
   std::lock_guard<std::mutex> lock(p->mu);
   // staging layout: ids [rows] | row info [rows] | tiles [n_tiles] | per-tile vad_pos [n_tiles], 16-byte aligned sections
   const size_t off_info = ((size_t)rows * 4 + 15) & ~size_t(15), off_tiles = (off_info + (size_t)rows * 8 + 15) & ~size_t(15);
+  static const bool scalar_attn = getenv("B200PF_PUNC_SCALAR_ATTN") != nullptr;   // the CUDA-core kernel, kept for comparison
+  const int qtile = scalar_attn ? P_QTILE : PT_Q;
   size_t want_tiles = 0;
-  for (int i = 0; i < n_seq; ++i) want_tiles += (size_t)((offsets[i + 1] - offsets[i] + P_QTILE - 1) / P_QTILE);
+  for (int i = 0; i < n_seq; ++i) want_tiles += (size_t)((offsets[i + 1] - offsets[i] + qtile - 1) / qtile);
   const size_t off_vad = off_tiles + want_tiles * 16;
   if (off_vad + want_tiles * 4 > p->in_bytes) { set_error("too many attention tiles"); return B200PF_ERR_CAPACITY; }
   int* h_ids = (int*)p->h_in;
@@ -476,10 +650,10 @@ int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* off
     if (T < 0) { set_error("offsets not monotone"); return B200PF_ERR_INVALID; }
     if (T > P_MAX_POS) { set_error("a sequence is longer than the position table (4096 tokens)"); return B200PF_ERR_CAPACITY; }
     for (int t = 0; t < T; ++t) info[r0 + t] = make_int2(t, T);
-    for (int q0 = 0; q0 < T; q0 += P_QTILE) {
+    for (int q0 = 0; q0 < T; q0 += qtile) {
       if (n_tiles >= max_tiles) { set_error("too many attention tiles"); return B200PF_ERR_CAPACITY; }
       tile_vad[n_tiles] = vad_pos ? vad_pos[i] : 0;
-      tiles[n_tiles++] = make_int4(r0 + q0, T - q0 < P_QTILE ? T - q0 : P_QTILE, r0, T);
+      tiles[n_tiles++] = make_int4(r0 + q0, T - q0 < qtile ? T - q0 : qtile, r0, T);
     }
   }
   cudaStream_t s = p->stream;
@@ -510,8 +684,15 @@ int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* off
     const PLayer& Ly = p->layers[l];
     if ((rc = ln(Ly.ln1_g, Ly.ln1_b))) return check_cuda((cudaError_t)rc, "punc ln1");
     if ((rc = gemm(p->h, Dp, Ly.qkv, 3 * D, 0, nullptr, 0, p->qkv, 3 * D, nullptr))) return check_cuda((cudaError_t)rc, "punc gemm qkv");
-    rc = launch_kernel(punc_attn_kernel, dim3((unsigned)n_tiles, p->H), dim3(128), 0, s, (const float*)p->qkv, (const int4*)p->d_tiles, d_tile_vad, D, p->dk, scale,
-                       p->ctx, Dp);
+    {
+      const dim3 grid((unsigned)n_tiles, p->H);
+      const float* q = p->qkv;
+      const int4* tl = p->d_tiles;
+      if (scalar_attn) rc = launch_kernel(punc_attn_kernel, grid, dim3(128), 0, s, q, tl, d_tile_vad, D, p->dk, scale, p->ctx, Dp);
+      else if (p->dk <= 32) rc = launch_kernel(punc_attn_mma_kernel<4>, grid, dim3(128), 0, s, q, tl, d_tile_vad, D, p->dk, scale, p->ctx, Dp);
+      else if (p->dk <= 48) rc = launch_kernel(punc_attn_mma_kernel<6>, grid, dim3(128), 0, s, q, tl, d_tile_vad, D, p->dk, scale, p->ctx, Dp);
+      else rc = launch_kernel(punc_attn_mma_kernel<8>, grid, dim3(128), 0, s, q, tl, d_tile_vad, D, p->dk, scale, p->ctx, Dp);
+    }
     if (rc) return check_cuda((cudaError_t)rc, "punc attention");
     // x += v + fsmn(v): after the attention kernel has been queued (it does not read x), before the out-projection accumulates into x
     rc = launch_kernel(punc_fsmn_kernel, dim3((unsigned)(((long long)rows * (D >> 2) + 255) / 256)), dim3(256), 0, s, (const float*)p->qkv, (const int2*)p->d_row_info, rows, D, p->K,

@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--segments", type=int, default=1024)
-    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "98304")))
+    ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "196608")))
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): BASELINE.json configs[1]; config5: 32 segments x 60 s per GPU "
                          "(configs[4]: 256 x 60 s over 8 GPUs, T = 1000 LFR frames) - an extra measurement, not the headline")
@@ -310,21 +310,28 @@ def main():
     barrier()
 
     # ---- leg 2: end to end through the C ABI with host buffers (`e2e`) ----
-    def step_e2e():
-        # double-buffered: stage batch i+1 on the copy stream while batch i computes; collect = D2H + sync
-        batches[0].stage_s16(host_pcm[0].data_ptr(), host_offs[0], stream=copy_stream.cuda_stream)
-        for i, b in enumerate(batches):
-            if i + 1 < len(batches):
-                batches[i + 1].stage_s16(host_pcm[i + 1].data_ptr(), host_offs[i + 1], stream=copy_stream.cuda_stream)
-            b.run()
-            b.collect()
+    # second set of batch objects (device PCM + layout + result buffers) so that consecutive steps ping-pong: the next item of
+    # the stream is always staged into an object whose previous results were already collected
+    batches_b = [capi.Batch(eng, hp.numel() + 64) for hp in host_pcm]
+    sets = (batches, batches_b)
 
-    for _ in range(max(1, args.warmup - 1)):
-        step_e2e()
+    def run_e2e(n_steps):
+        # double-buffered across batches AND steps: while one batch computes, the NEXT batch of the stream (the next step's first
+        # batch after the last one) is staged on the copy stream; collect = D2H + sync.  Every step's host->device copies and
+        # result reads happen inside this call.
+        seq = [(s, i) for s in range(n_steps) for i in range(len(batches))]
+        sets[0][0].stage_s16(host_pcm[0].data_ptr(), host_offs[0], stream=copy_stream.cuda_stream)
+        for k, (s_, i) in enumerate(seq):
+            if k + 1 < len(seq):
+                s2, j = seq[k + 1]
+                sets[s2 & 1][j].stage_s16(host_pcm[j].data_ptr(), host_offs[j], stream=copy_stream.cuda_stream)
+            sets[s_ & 1][i].run()
+            sets[s_ & 1][i].collect()
+
+    run_e2e(max(1, args.warmup - 1))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / args.steps
     barrier()
