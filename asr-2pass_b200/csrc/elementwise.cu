@@ -122,17 +122,15 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
 
-// <= 128 registers (44 bytes of spill): one FSMN CTA then fits next to two resident attention CTAs (2 x 24.6K + 16.4K
-// registers = one SM), which is what lets the two kernels really run side by side (engine.cu, "overlap").
-__global__ void __launch_bounds__(128, 4)
-fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
-            const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
-            __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int nrows = rows_dev ? *rows_dev : rows;
-  const int r0 = blockIdx.x * FSMN_RUN;
-  if (r0 >= nrows) return;
+// FAST: the whole window of the run (rows r0 - 5 .. r0 + RUN + 4) lies inside ONE segment, so every tap of every output exists and
+// no per-row bookkeeping is needed -- loads, conversions, 22 packed FMAs per row and the store.  About four out of five runs of the
+// benchmark workload take this path (segments are 33-333 rows, a window is 32); the general path handles segment edges, gap rows
+// and the batch tail.  Both paths apply the same FMAs in the same order to an output, so results do not depend on which one a row
+// falls into (batch invariance).  Measured: 11.6 -> 11.4 ms of FSMN time per step -- the kernel is not bound by that bookkeeping.
+template <bool FAST>
+__device__ __forceinline__ void fsmn_run(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
+                                         const int2* __restrict__ row_info, int nrows, int r0, int mode,
+                                         __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
   const int c = threadIdx.x * 4;
   float2 w[11][2];
 #pragma unroll
@@ -155,9 +153,13 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
     for (int ii = 0; ii < 11; ++ii) {
       const int i = step * 11 + ii;
       const int rin = r0 - 5 + i;
-      const bool in_range = rin >= 0 && rin < nrows && i < FSMN_RUN + 10;
-      inf[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
-      rw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
+      if (FAST) {
+        if (i < FSMN_RUN + 10) rw[ii] = *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c);
+      } else {
+        const bool in_range = rin >= 0 && rin < nrows && i < FSMN_RUN + 10;
+        inf[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
+        rw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
+      }
     }
   };
   load_step(0, info[0], raw[0]);
@@ -170,34 +172,50 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
 #pragma unroll
     for (int ii = 0; ii < 11; ++ii) {
       const int i = step * 11 + ii;
-      const int2 inf = info[cur][ii];
-      if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
-        // bf16 -> fp32 is a 16-bit shift
-        const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
-        const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
-        cur_valid |= 1u << ii;
-        if (inf.x >= 5 && inf.x + 5 < inf.y) {
-          // interior frame: all 11 neighbours are in the same segment
+      if (FAST) {
+        if (i < FSMN_RUN + 10) {
+          const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
+          const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
 #pragma unroll
           for (int d = -5; d <= 5; ++d) {
             const int o = i - 5 - d;
-            if (o >= 0 && o < FSMN_RUN) {  // static: outputs of other runs are not accumulated here
+            if (o >= 0 && o < FSMN_RUN) {
               const int slot = ((ii - 5 - d) % 11 + 11) % 11;
               ffma2(acc[slot][0], w[d + 5][0], x0);
               ffma2(acc[slot][1], w[d + 5][1], x1);
             }
           }
-        } else {
+        }
+      } else {
+        const int2 inf = info[cur][ii];
+        if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
+          // bf16 -> fp32 is a 16-bit shift
+          const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
+          const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
+          cur_valid |= 1u << ii;
+          if (inf.x >= 5 && inf.x + 5 < inf.y) {
+            // interior frame: all 11 neighbours are in the same segment
 #pragma unroll
-          for (int d = -5; d <= 5; ++d) {
-            const int o = i - 5 - d;
-            if (o >= 0 && o < FSMN_RUN) {
-              // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
-              const bool ok = (inf.x - d) >= 0 && (inf.x - d) < inf.y;
-              const int slot = ((ii - 5 - d) % 11 + 11) % 11;
-              if (ok) {
+            for (int d = -5; d <= 5; ++d) {
+              const int o = i - 5 - d;
+              if (o >= 0 && o < FSMN_RUN) {  // static: outputs of other runs are not accumulated here
+                const int slot = ((ii - 5 - d) % 11 + 11) % 11;
                 ffma2(acc[slot][0], w[d + 5][0], x0);
                 ffma2(acc[slot][1], w[d + 5][1], x1);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int d = -5; d <= 5; ++d) {
+              const int o = i - 5 - d;
+              if (o >= 0 && o < FSMN_RUN) {
+                // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
+                const bool ok = (inf.x - d) >= 0 && (inf.x - d) < inf.y;
+                const int slot = ((ii - 5 - d) % 11 + 11) % 11;
+                if (ok) {
+                  ffma2(acc[slot][0], w[d + 5][0], x0);
+                  ffma2(acc[slot][1], w[d + 5][1], x1);
+                }
               }
             }
           }
@@ -207,9 +225,9 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
       const int o = i - 10;
       const int slot_done = (ii + 1) % 11;
       if (o >= 0 && o < FSMN_RUN) {
-        if (r0 + o < nrows) {
+        if (FAST || r0 + o < nrows) {
           const int rout = r0 + o;
-          const bool out_valid = (ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u);
+          const bool out_valid = FAST ? true : ((ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u));
           if (mode == 0) {
             uint2 pk = make_uint2(0, 0);
             if (out_valid) { pk.x = pack2(acc[slot_done][0].x, acc[slot_done][0].y); pk.y = pack2(acc[slot_done][1].x, acc[slot_done][1].y); }
@@ -227,6 +245,27 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
     }
     prev_valid = cur_valid;
   }
+}
+
+// <= 128 registers: one FSMN CTA then fits next to two resident attention CTAs (2 x 24.6K + 16.4K registers = one SM), which is
+// what lets the two kernels run side by side (engine.cu, "overlap").
+__global__ void __launch_bounds__(128, 4)
+fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
+            const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
+            __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int nrows = rows_dev ? *rows_dev : rows;
+  const int r0 = blockIdx.x * FSMN_RUN;
+  if (r0 >= nrows) return;
+  // block-uniform: first and last row of the window are frames of the same segment (rows of a segment are consecutive)
+  bool fast = false;
+  if (r0 >= 5 && r0 + FSMN_RUN + 4 < nrows) {
+    const int2 a = row_info[r0 - 5], b = row_info[r0 + FSMN_RUN + 4];
+    fast = a.x >= 0 && b.x == a.x + FSMN_RUN + 9 && b.y == a.y;
+  }
+  if (fast) fsmn_run<true>(in, ld_in, col0, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
+  else fsmn_run<false>(in, ld_in, col0, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
 }
 
 // ------------------------------------------------------------------------------------------------
