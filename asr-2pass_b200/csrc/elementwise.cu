@@ -128,7 +128,7 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2
 // and the batch tail.  Both paths apply the same FMAs in the same order to an output, so results do not depend on which one a row
 // falls into (batch invariance).  Measured: 11.6 -> 11.4 ms of FSMN time per step -- the kernel is not bound by that bookkeeping.
 template <bool FAST>
-__device__ __forceinline__ void fsmn_run(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
+__device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], const float* __restrict__ w_t,
                                          const int2* __restrict__ row_info, int nrows, int r0, int mode,
                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
   const int c = threadIdx.x * 4;
@@ -147,35 +147,32 @@ __device__ __forceinline__ void fsmn_run(const __nv_bfloat16* __restrict__ in, i
   // complete after input i = o + 10.  Everything below is fully unrolled, so o and the ring slot are static.
   constexpr int NSTEP = (FSMN_RUN + 10 + 10) / 11;
   int2 info[2][11];
-  uint2 raw[2][11];
-  auto load_step = [&](int step, int2 (&inf)[11], uint2 (&rw)[11]) {
+  auto load_step = [&](int step, int2 (&inf)[11]) {   // general path only: the rows' (frame, length) pairs, one step ahead
+    if constexpr (!FAST) {
 #pragma unroll
-    for (int ii = 0; ii < 11; ++ii) {
-      const int i = step * 11 + ii;
-      const int rin = r0 - 5 + i;
-      if (FAST) {
-        if (i < FSMN_RUN + 10) rw[ii] = *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c);
-      } else {
+      for (int ii = 0; ii < 11; ++ii) {
+        const int i = step * 11 + ii;
+        const int rin = r0 - 5 + i;
         const bool in_range = rin >= 0 && rin < nrows && i < FSMN_RUN + 10;
         inf[ii] = in_range ? row_info[rin] : make_int2(-1, 0);
-        rw[ii] = in_range ? *reinterpret_cast<const uint2*>(in + (size_t)rin * ld_in + col0 + c) : make_uint2(0, 0);
       }
     }
   };
-  load_step(0, info[0], raw[0]);
+  load_step(0, info[0]);
   unsigned prev_valid = 0;  // bit ii: input ii of the previous step was a real frame row
 #pragma unroll
   for (int step = 0; step < NSTEP; ++step) {
     const int cur = step & 1;
-    if (step + 1 < NSTEP) load_step(step + 1, info[cur ^ 1], raw[cur ^ 1]);  // in flight while this step computes
+    if (step + 1 < NSTEP) load_step(step + 1, info[cur ^ 1]);  // in flight while this step computes
     unsigned cur_valid = 0;
 #pragma unroll
     for (int ii = 0; ii < 11; ++ii) {
       const int i = step * 11 + ii;
       if (FAST) {
         if (i < FSMN_RUN + 10) {
-          const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
-          const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
+          const uint2 rw = tile[i][threadIdx.x];
+          const float2 x0 = make_float2(__uint_as_float(rw.x << 16), __uint_as_float(rw.x & 0xffff0000u));
+          const float2 x1 = make_float2(__uint_as_float(rw.y << 16), __uint_as_float(rw.y & 0xffff0000u));
 #pragma unroll
           for (int d = -5; d <= 5; ++d) {
             const int o = i - 5 - d;
@@ -190,8 +187,9 @@ __device__ __forceinline__ void fsmn_run(const __nv_bfloat16* __restrict__ in, i
         const int2 inf = info[cur][ii];
         if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
           // bf16 -> fp32 is a 16-bit shift
-          const float2 x0 = make_float2(__uint_as_float(raw[cur][ii].x << 16), __uint_as_float(raw[cur][ii].x & 0xffff0000u));
-          const float2 x1 = make_float2(__uint_as_float(raw[cur][ii].y << 16), __uint_as_float(raw[cur][ii].y & 0xffff0000u));
+          const uint2 rw = tile[i < FSMN_RUN + 10 ? i : 0][threadIdx.x];
+          const float2 x0 = make_float2(__uint_as_float(rw.x << 16), __uint_as_float(rw.x & 0xffff0000u));
+          const float2 x1 = make_float2(__uint_as_float(rw.y << 16), __uint_as_float(rw.y & 0xffff0000u));
           cur_valid |= 1u << ii;
           if (inf.x >= 5 && inf.x + 5 < inf.y) {
             // interior frame: all 11 neighbours are in the same segment
@@ -264,8 +262,27 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
     const int2 a = row_info[r0 - 5], b = row_info[r0 + FSMN_RUN + 4];
     fast = a.x >= 0 && b.x == a.x + FSMN_RUN + 9 && b.y == a.y;
   }
-  if (fast) fsmn_run<true>(in, ld_in, col0, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
-  else fsmn_run<false>(in, ld_in, col0, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
+  // the window (RUN + 10 rows x 512 channels, 32 KB) goes to shared memory through cp.async: every 16-byte piece of it is in
+  // flight at once, no registers are held for it, and the compute loops below read it back conflict-free (8 bytes per lane)
+  __shared__ __align__(16) uint2 tile[FSMN_RUN + 10][128];
+  constexpr int kPieces = (FSMN_RUN + 10) * 64;   // 16-byte pieces
+  for (int p = threadIdx.x; p < kPieces; p += 128) {
+    const int row = p >> 6, piece = p & 63;
+    const int rin = r0 - 5 + row;
+    uint2* dst = &tile[row][piece * 2];
+    if (rin >= 0 && rin < nrows) {
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(in + (size_t)rin * ld_in + col0 + piece * 8) : "memory");
+    } else {
+      dst[0] = make_uint2(0, 0);
+      dst[1] = make_uint2(0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (fast) fsmn_run<true>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
+  else fsmn_run<false>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
 }
 
 // ------------------------------------------------------------------------------------------------
