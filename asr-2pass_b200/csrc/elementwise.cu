@@ -511,10 +511,102 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
     out[i] = __float2bfloat16(in[i]);
 }
 
+// LayerNorm over 512 fp32 columns with the rows staged through shared memory by cp.async: a warp owns 4 consecutive rows, every
+// lane issues the 16 16-byte copies of its own elements up front (one commit group per row: 8 KB per warp, 64 KB per CTA and
+// 192 KB per SM in flight -- three times what register loads allowed) and normalises row k as soon as group k has landed.  A
+// lane reads back only what it copied itself, so no barrier is needed; the arithmetic is that of layernorm_kernel<512, false>.
+constexpr int LNS_ROWS_PER_WARP = 4, LNS_WARPS = 8, LNS_SMEM = LNS_WARPS * LNS_ROWS_PER_WARP * 512 * 4;
+__global__ void __launch_bounds__(256)
+layernorm512_staged_kernel(const float* __restrict__ in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                           const int2* __restrict__ row_info, int zero_gap) {
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float lns_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = rows_dev ? *rows_dev : rows;
+  const int row0 = (blockIdx.x * LNS_WARPS + warp) * LNS_ROWS_PER_WARP;
+  if (row0 >= nrows) return;
+  float* mine = lns_smem + (size_t)warp * LNS_ROWS_PER_WARP * 512;
+#pragma unroll
+  for (int k = 0; k < LNS_ROWS_PER_WARP; ++k) {
+    if (row0 + k < nrows) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(mine + k * 512 + c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in + (size_t)(row0 + k) * 512 + c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float4 g[4], b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    g[i] = *reinterpret_cast<const float4*>(gamma + (lane + 32 * i) * 4);
+    b[i] = *reinterpret_cast<const float4*>(beta + (lane + 32 * i) * 4);
+  }
+#pragma unroll
+  for (int k = 0; k < LNS_ROWS_PER_WARP; ++k) {
+    if (k == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else if (k == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (k == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int row = row0 + k;
+    if (row >= nrows) break;
+    const bool gap = zero_gap && row_info && row_info[row].x < 0;
+    float v[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 f = *reinterpret_cast<const float4*>(mine + k * 512 + (lane + 32 * i) * 4);
+      v[i * 4] = f.x; v[i * 4 + 1] = f.y; v[i * 4 + 2] = f.z; v[i * 4 + 3] = f.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sum += v[i * 4 + e];
+    }
+    const float mean = warp_sum(sum) / 512.0f;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float d = v[i * 4 + e] - mean; sq += d * d; }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / 512.0f + eps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      float o[4];
+      o[0] = (v[i * 4] - mean) * rstd * g[i].x + b[i].x;
+      o[1] = (v[i * 4 + 1] - mean) * rstd * g[i].y + b[i].y;
+      o[2] = (v[i * 4 + 2] - mean) * rstd * g[i].z + b[i].z;
+      o[3] = (v[i * 4 + 3] - mean) * rstd * g[i].w + b[i].w;
+      if (gap) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; o[3] = 0.f; }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * 512 + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (out_bf16) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * 512 + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+  }
+}
+
 template <int D>
 int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, const float* gamma, const float* beta,
                 float eps, __nv_bfloat16* ob, float* of, const int2* ri, int zg, cudaStream_t s) {
   const int blocks = (rows + 7) / 8;
+  if (D == 512 && !in_is_bf16 && rows >= 4096) {   // large fp32 LayerNorms (the residual stream): staged loads
+    static const bool plain = getenv("B200PF_LN_PLAIN") != nullptr;
+    if (!plain) {
+      static bool attr_set[64] = {};
+      if (first_use_on_device(attr_set)) {
+        cudaError_t err = cudaFuncSetAttribute(layernorm512_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LNS_SMEM);
+        if (err != cudaSuccess) return (int)err;
+      }
+      const int per = LNS_WARPS * LNS_ROWS_PER_WARP;
+      return launch_kernel(layernorm512_staged_kernel, dim3((rows + per - 1) / per), dim3(256), LNS_SMEM, s, (const float*)in, rows, rows_dev, gamma, beta,
+                           eps, ob, of, ri, zg);
+    }
+  }
   if (in_is_bf16)
     return launch_kernel(layernorm_kernel<D, true>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
   return launch_kernel(layernorm_kernel<D, false>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
