@@ -36,8 +36,10 @@ __constant__ double2 c_w16[8] = {
     {-0.92387953251128673848, -0.38268343236508989280}};
 
 struct FbSmem {
-  double2 buf[FB_FRAMES][NFFT / 2];     // per frame: 256 complex doubles (transpose + partner exchange)
+  double2 buf[FB_FRAMES][16 * 17];      // per frame: 256 complex doubles as 16 rows of 16 (+1 pad: the transposed read of the
+                                        // 16 x 16 exchange, one row per lane, would otherwise be an 8-way bank conflict)
   double2 tw[NFFT / 2];                 // exp(-2 pi i k / 512)
+  double2 tw1[NFFT / 2];                // pass-1 twiddles W_256^(sub k1) at [k1][sub]: one conflict-free row per k1
   float window[WIN];
   float power[FB_FRAMES][NFFT / 2 + 8];
   float mel_w[1024];
@@ -88,7 +90,12 @@ fbank_kernel(const void* __restrict__ pcm, const int64_t* __restrict__ sample_of
   const int sub = lane & 15;                       // lane within the frame's half-warp
   const unsigned hmask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;
   const int slot = (threadIdx.x >> 5) * 2 + (lane >> 4);
-  for (int i = threadIdx.x; i < NFFT / 2; i += blockDim.x) S.tw[i] = t.twiddle[i];
+  for (int i = threadIdx.x; i < NFFT / 2; i += blockDim.x) {
+    S.tw[i] = t.twiddle[i];
+    const int j = 2 * (i & 15) * (i >> 4);           // W_256^m = W_512^(2m); W_512^(j) = -W_512^(j-256)
+    const double2 w = t.twiddle[j & 255];
+    S.tw1[i] = (j >= 256) ? make_double2(-w.x, -w.y) : w;
+  }
   for (int i = threadIdx.x; i < WIN; i += blockDim.x) S.window[i] = t.window[i];
   for (int i = threadIdx.x; i < mel_w_total; i += blockDim.x) S.mel_w[i] = t.mel_w[i];
   for (int i = threadIdx.x; i < NBIN; i += blockDim.x) { S.mel_range[i] = t.mel_range[i]; S.mel_w_off[i] = t.mel_w_off[i]; }
@@ -149,27 +156,25 @@ fbank_kernel(const void* __restrict__ pcm, const int64_t* __restrict__ sample_of
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
       const double2 y = v[brev4(k1)];
-      const int j = 2 * sub * k1;                      // W_256^m = W_512^(2m); W_512^(j) = -W_512^(j-256)
-      double2 w = S.tw[j & 255];
-      if (j >= 256) w = make_double2(-w.x, -w.y);
-      buf[k1 * 16 + sub] = (j == 0) ? y : cmul(y, w);
+      buf[k1 * 17 + sub] = (sub * k1 == 0) ? y : cmul(y, S.tw1[k1 * 16 + sub]);
     }
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf[sub * 16 + n2];   // lane = k1, values over n2
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf[sub * 17 + n2];   // lane = k1, values over n2
     __syncwarp();
     // pass 2: DFT over n2 -> Z[k1 + 16 k2]
     fft16(v);
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) buf[sub + 16 * k2] = v[brev4(k2)];
+    for (int k2 = 0; k2 < 16; ++k2) buf[sub + 17 * k2] = v[brev4(k2)];   // Z[k], k = sub + 16 k2, at row k2, column sub
     __syncwarp();
     // real-FFT recombination: X[k] = (Z[k] + conj Z[256-k])/2 - i W_512^k (Z[k] - conj Z[256-k])/2
     // ComputePowerSpectrum (feature-functions.cc:28-47) on the float-narrowed spectrum
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int k = sub + 16 * j;
-      const double2 zk = buf[k];
-      const double2 zc = buf[(256 - k) & 255];
+      const int kc = (256 - k) & 255;
+      const double2 zk = buf[j * 17 + sub];
+      const double2 zc = buf[(kc >> 4) * 17 + (kc & 15)];
       const double2 xe_ = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y - zc.y));
       const double2 xo_ = make_double2(0.5 * (zk.y + zc.y), -0.5 * (zk.x - zc.x));   // -i/2 (Z[k] - conj Z[N-k])
       const double2 w = S.tw[k];
