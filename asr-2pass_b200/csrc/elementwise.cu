@@ -590,6 +590,90 @@ layernorm512_staged_kernel(const float* __restrict__ in, int rows, const int* __
   }
 }
 
+// The decoder's LayerNorm(2048) on the bf16 FFN hidden rows, staged the same way: a warp owns 2 rows (8 KB), copies them with
+// cp.async (one commit group per row) and normalises row k when it has landed; arithmetic of layernorm_kernel<2048, true>.
+constexpr int LNB_ROWS_PER_WARP = 2, LNB_SMEM = LNS_WARPS * LNB_ROWS_PER_WARP * 2048 * 2;
+__global__ void __launch_bounds__(256)
+layernorm2048_staged_kernel(const __nv_bfloat16* in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float eps, __nv_bfloat16* out_bf16, float* __restrict__ out_f32) {
+  // in and out_bf16 may be the same buffer (the decoder normalises its FFN hidden rows in place): a lane writes only the
+  // elements it copied itself, after it has read them from shared memory
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) float lns_smem[];
+  __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(lns_smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrows = rows_dev ? *rows_dev : rows;
+  const int row0 = (blockIdx.x * LNS_WARPS + warp) * LNB_ROWS_PER_WARP;
+  if (row0 >= nrows) return;
+  __nv_bfloat16* mine = base + (size_t)warp * LNB_ROWS_PER_WARP * 2048;
+#pragma unroll
+  for (int k = 0; k < LNB_ROWS_PER_WARP; ++k) {
+    if (row0 + k < nrows) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(mine + k * 2048 + c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(in + (size_t)(row0 + k) * 2048 + c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+#pragma unroll
+  for (int k = 0; k < LNB_ROWS_PER_WARP; ++k) {
+    if (k == 0) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int row = row0 + k;
+    if (row >= nrows) break;
+    float v[64];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = *reinterpret_cast<const uint4*>(mine + k * 2048 + (lane + 32 * i) * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i * 8 + 2 * e] = __low2float(h[e]); v[i * 8 + 2 * e + 1] = __high2float(h[e]); }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i * 8 + e];
+    }
+    const float mean = warp_sum(sum) / 2048.0f;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i * 8 + e] - mean; sq += d * d; }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / 2048.0f + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c + e);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c + e);
+        o[e] = (v[i * 8 + e] - mean) * rstd * g.x + b.x;
+        o[e + 1] = (v[i * 8 + e + 1] - mean) * rstd * g.y + b.y;
+        o[e + 2] = (v[i * 8 + e + 2] - mean) * rstd * g.z + b.z;
+        o[e + 3] = (v[i * 8 + e + 3] - mean) * rstd * g.w + b.w;
+      }
+      if (out_f32) {
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * 2048 + c) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(out_f32 + (size_t)row * 2048 + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (out_bf16) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 2048 + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+}
+
 template <int D>
 int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, const float* gamma, const float* beta,
                 float eps, __nv_bfloat16* ob, float* of, const int2* ri, int zg, cudaStream_t s) {
@@ -605,6 +689,19 @@ int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, c
       const int per = LNS_WARPS * LNS_ROWS_PER_WARP;
       return launch_kernel(layernorm512_staged_kernel, dim3((rows + per - 1) / per), dim3(256), LNS_SMEM, s, (const float*)in, rows, rows_dev, gamma, beta,
                            eps, ob, of, ri, zg);
+    }
+  }
+  if (D == 2048 && in_is_bf16 && rows >= 4096 && !ri) {   // the decoder's FFN LayerNorm on large batches: staged loads
+    static const bool plain = getenv("B200PF_LN_PLAIN") != nullptr;
+    if (!plain) {
+      static bool attr_set[64] = {};
+      if (first_use_on_device(attr_set)) {
+        cudaError_t err = cudaFuncSetAttribute(layernorm2048_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_SMEM);
+        if (err != cudaSuccess) return (int)err;
+      }
+      const int per = LNS_WARPS * LNB_ROWS_PER_WARP;
+      return launch_kernel(layernorm2048_staged_kernel, dim3((rows + per - 1) / per), dim3(256), LNB_SMEM, s, (const __nv_bfloat16*)in, rows, rows_dev,
+                           gamma, beta, eps, ob, of);
     }
   }
   if (in_is_bf16)
