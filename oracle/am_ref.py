@@ -52,6 +52,10 @@ def lib():
         L.ref_punc_online_create.argtypes = [C.c_char_p] * 3
         L.ref_punc_online_destroy.argtypes = [C.c_void_p]
         L.ref_punc_online_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.ref_vad_create.restype = C.c_void_p
+        L.ref_vad_create.argtypes = [C.c_char_p] * 3
+        L.ref_vad_destroy.argtypes = [C.c_void_p]
+        L.ref_vad_cutsplit.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
         _lib = L
     return _lib
 
@@ -172,4 +176,49 @@ class RefPuncOnline:
     def close(self):
         if self.h:
             lib().ref_punc_online_destroy(self.h)
+            self.h = None
+
+
+VAD_CONFIG_YAML = """frontend: WavFrontendOnline
+frontend_conf:
+  fs: 16000
+  window: hamming
+  n_mels: 80
+  frame_length: 25
+  frame_shift: 10
+  dither: 0.0
+  lfr_m: 5
+  lfr_n: 1
+model_conf:
+  max_end_silence_time: 800
+  max_single_segment_time: 60000
+  speech_noise_thres: %.6f
+"""
+
+
+class RefVad:
+    """funasr::FsmnVad + FsmnVadOnline driven like Audio::CutSplit (audio.cpp:1172-1226).  vad_dir holds am.mvn; config.yaml
+    (the keys FsmnVad::LoadConfigFromYaml reads, fsmn-vad.cpp:21-52) and an empty model file are written here.  The session
+    gets (feats [1,T,400], 4 caches [1,128,19,1]) and must return (scores [1,T,248], 4 caches)."""
+
+    def __init__(self, vad_dir, net, speech_noise_thres=0.6, tag="0"):
+        d = os.path.abspath(vad_dir)
+        vm = os.path.join(d, "vad_%s.onnx" % tag)
+        cfg = os.path.join(d, "vad_config_%s.yaml" % tag)
+        with open(cfg, "w") as f:
+            f.write(VAD_CONFIG_YAML % speech_noise_thres)
+        register_network(vm, 5, 5, net)
+        self.h = lib().ref_vad_create(vm.encode(), os.path.join(d, "am.mvn").encode(), cfg.encode())
+
+    def cut_split(self, pcm_f32, vad_tail_sil=800, vad_max_len=15000):
+        x = np.ascontiguousarray(pcm_f32, dtype=np.float32)
+        out = np.zeros((len(x) // 160 + 8, 2), np.int32)
+        n = lib().ref_vad_cutsplit(self.h, x.ctypes.data_as(C.POINTER(C.c_float)), len(x), vad_tail_sil, vad_max_len,
+                                   out.ctypes.data_as(C.POINTER(C.c_int)), len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib().ref_vad_destroy(self.h)
             self.h = None

@@ -83,4 +83,49 @@ int ref_punc_online_add(void* h, const char* text, const char* cache_in, const c
   if (CopyOut(joined, cache_out, cache_cap) < 0) return -1;
   return n;
 }
+
+// funasr::FsmnVad + funasr::FsmnVadOnline (fsmn-vad.cpp, fsmn-vad-online.cpp): the VAD cut of the offline path exactly as
+// Audio::CutSplit drives it (audio.cpp:1172-1226) -- the recording in 1 s pieces through FsmnVadOnline::Infer (the reference's own
+// online fbank / LFR caches, FSMN caches through the session, E2E scorer), start / end frames paired into segments (ms).
+void* ref_vad_create(const char* vad_model, const char* vad_cmvn, const char* vad_config) {
+  funasr::FsmnVad* v = new funasr::FsmnVad();
+  v->InitVad(vad_model, vad_cmvn, vad_config, 1);
+  return v;
+}
+void ref_vad_destroy(void* h) { delete (funasr::FsmnVad*)h; }
+int ref_vad_cutsplit(void* h, const float* pcm, int speech_len, int vad_tail_sil, int vad_max_len, int* seg_ms, int cap) {
+  funasr::FsmnVad* vad = (funasr::FsmnVad*)h;
+  vad->SetConfig(vad_tail_sil, vad_max_len);                       // FunOfflineInferBuffer, funasrruntime.cpp:219-220
+  std::unique_ptr<funasr::VadModel> online(new funasr::FsmnVadOnline(vad));
+  const int dest_sample_rate = 16000;
+  int step = dest_sample_rate * 1;
+  bool is_final = false;
+  std::vector<std::vector<int>> vad_segments;
+  for (int sample_offset = 0; sample_offset < speech_len; sample_offset += std::min(step, speech_len - sample_offset)) {
+    if (sample_offset + step >= speech_len - 1) {
+      step = speech_len - sample_offset;
+      is_final = true;
+    } else {
+      is_final = false;
+    }
+    std::vector<float> pcm_data(pcm + sample_offset, pcm + sample_offset + step);
+    std::vector<std::vector<int>> cut = online->Infer(pcm_data, is_final);
+    vad_segments.insert(vad_segments.end(), cut.begin(), cut.end());
+  }
+  int start = -1, end = -1, n = 0;
+  for (const std::vector<int>& sg : vad_segments) {
+    if (sg.size() != 2) break;
+    if (sg[0] != -1) start = sg[0];
+    if (sg[1] != -1) end = sg[1];
+    if (start != -1 && end != -1) {
+      if (n >= cap) return -1;
+      seg_ms[2 * n] = start;
+      seg_ms[2 * n + 1] = end;
+      ++n;
+      start = -1;
+      end = -1;
+    }
+  }
+  return n;
+}
 }  // extern "C"

@@ -187,3 +187,52 @@ def test_offline_shim_vad_cut_path(capi, synth, gpu, tmp_path):
     if len(h.vad_cut(sil, 800, 15000)) == 0:
         assert h.infer_buffer_vad(sil, 800, 15000)[0] == ""
     h.close()
+
+
+def test_whole_recording_vad_equals_reference_cutsplit(capi, synth, tmp_path):
+    """The one structural deviation of the VAD path -- scores for the WHOLE recording in one pass + SegmentVad, instead of the
+    reference's 1 s pieces through FsmnVadOnline (online fbank / LFR caches, FSMN caches through the session, incremental E2E
+    scorer) -- checked against the reference's own compiled fsmn-vad.cpp / fsmn-vad-online.cpp / e2e-vad.h driven exactly like
+    Audio::CutSplit (audio.cpp:1172-1226), with the oracle network behind the session: same frame count, same features, same
+    segments."""
+    import torch
+    from oracle import am_ref as A
+    if not A.available():
+        pytest.skip("oracle/_ref/libfunasr_am_ref.so not built (needs /root/reference)")
+    d = str(tmp_path)
+    W, means, vars_ = synth.write_synthetic_vad_dir(d, seed=0)
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    log = dict(feats=[])
+
+    def net(ins):
+        feats = ins[0][0]
+        caches = [torch.from_numpy(c[0, :, :, 0].copy()) for c in ins[1:5]]
+        assert all(c.shape == (1, 128, 19, 1) for c in ins[1:5])
+        scores, nc = V.forward(feats, Wt, caches)
+        log["feats"].append(feats.copy())
+        return [scores.numpy()[None].astype(np.float32)] + [c.numpy()[None, :, :, None].astype(np.float32) for c in nc]
+
+    rng = np.random.default_rng(3)
+    n_seg_total = 0
+    for case in range(6):
+        parts = []
+        for i in range(int(rng.integers(1, 6))):
+            parts += [synth.make_audio(int(rng.integers(4000, 120000)), 300 + 10 * case + i), np.zeros(int(rng.integers(3000, 40000)), np.int16)]
+        pcm = np.concatenate(parts)[: None if case % 2 else -int(rng.integers(1, 159))]
+        if case == 5:
+            pcm = pcm[:9000]                                    # shorter than one 1 s piece
+        x = pcm.astype(np.float32) / np.float32(32768)
+        feats = V.lfr_cmvn(F.fbank(x), means, vars_)
+        scores, _ = V.forward(feats, Wt)
+        p0 = scores.numpy()[:, 0]
+        thres = float(np.clip(1.0 - 2.0 * np.quantile(p0, [0.5, 0.3, 0.7][case % 3]), 0.05, 0.95))
+        ref = A.RefVad(d, net, speech_noise_thres=thres, tag="c%d" % case)
+        for tail, mx in ((800, 15000), (250, 3000)):
+            log["feats"] = []
+            segs = ref.cut_split(x, tail, mx)
+            seen = np.concatenate(log["feats"])
+            assert seen.shape == feats.shape and np.abs(seen - feats).max() <= 1e-4       # frames and features of the chunked front end
+            assert np.array_equal(segs, capi.host_vad_segments(p0, tail, mx, thres)), (case, tail, mx)
+            n_seg_total += len(segs)
+        ref.close()
+    assert n_seg_total >= 10
