@@ -56,6 +56,11 @@ def lib():
         L.ref_vad_create.argtypes = [C.c_char_p] * 3
         L.ref_vad_destroy.argtypes = [C.c_void_p]
         L.ref_vad_cutsplit.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+        L.ref_offline_init.restype = C.c_void_p
+        L.ref_offline_init.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int]
+        L.ref_offline_uninit.argtypes = [C.c_void_p]
+        L.ref_offline_infer_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                               C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -221,4 +226,45 @@ class RefVad:
     def close(self):
         if self.h:
             lib().ref_vad_destroy(self.h)
+            self.h = None
+
+
+class RefOffline:
+    """The reference's exported offline API: FunOfflineInit on real model directories (offline-stream.cpp) and
+    FunOfflineInferBuffer (funasrruntime.cpp:208-340).  Each directory gets an empty model.onnx (the reference only checks that
+    the file exists; the session behind it is the given callable); the VAD directory also gets the config.yaml FsmnVad reads."""
+
+    def __init__(self, am_dir, am_net, am_outputs=2, vad_dir=None, vad_net=None, vad_thres=0.6, punc_dir=None, punc_net=None):
+        kv = {"model-dir": os.path.abspath(am_dir)}
+        am = os.path.join(kv["model-dir"], "model.onnx")
+        open(am, "ab").close()
+        register_network(am, 2, am_outputs, am_net)
+        if vad_dir is not None:
+            kv["vad-dir"] = os.path.abspath(vad_dir)
+            vm = os.path.join(kv["vad-dir"], "model.onnx")
+            open(vm, "ab").close()
+            with open(os.path.join(kv["vad-dir"], "config.yaml"), "w") as f:
+                f.write(VAD_CONFIG_YAML % vad_thres)
+            register_network(vm, 5, 5, vad_net)
+        if punc_dir is not None:
+            kv["punc-dir"] = os.path.abspath(punc_dir)
+            pm = os.path.join(kv["punc-dir"], "model.onnx")
+            open(pm, "ab").close()
+            register_network(pm, 2, 1, punc_net)
+        keys = (C.c_char_p * len(kv))(*[k.encode() for k in kv])
+        vals = (C.c_char_p * len(kv))(*[v.encode() for v in kv.values()])
+        self.h = lib().ref_offline_init(keys, vals, len(kv))
+        assert self.h
+
+    def infer_buffer(self, pcm16, vad_tail_sil=800, vad_max_len=60000, cap=1 << 22):
+        """-> (text, stamp, stamp_sents) of FunASRGetResult / FunASRGetStamp / FunASRGetStampSents."""
+        raw = np.ascontiguousarray(pcm16, dtype="<i2")
+        t, st, ss = C.create_string_buffer(cap), C.create_string_buffer(cap), C.create_string_buffer(4 * cap)
+        n = lib().ref_offline_infer_buffer(self.h, C.c_void_p(raw.ctypes.data), raw.nbytes, vad_tail_sil, vad_max_len, t, cap, st, cap, ss, 4 * cap)
+        assert n >= 0, n
+        return t.value.decode("utf-8", "replace"), st.value.decode("utf-8"), ss.value.decode("utf-8", "replace")
+
+    def close(self):
+        if self.h:
+            lib().ref_offline_uninit(self.h)
             self.h = None

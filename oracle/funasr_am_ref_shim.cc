@@ -128,4 +128,24 @@ int ref_vad_cutsplit(void* h, const float* pcm, int speech_len, int vad_tail_sil
   }
   return n;
 }
+
+// The reference's exported offline API itself (funasrruntime.cpp: FunOfflineInit :36-40, FunOfflineInferBuffer :208-340) on an
+// OfflineStream built from real model directories (offline-stream.cpp): LoadPcmwav, CutSplit, length sort, FetchDynamic,
+// Paraformer::Forward per segment, stitching, punctuation, TimestampSentence -- with every session served by fake_ort.cc.
+void* ref_offline_init(const char* const* keys, const char* const* values, int n) {
+  std::map<std::string, std::string> mp;
+  for (int i = 0; i < n; ++i) mp[keys[i]] = values[i];
+  return FunOfflineInit(mp, 1, false, 1);
+}
+void ref_offline_uninit(void* h) { FunOfflineUninit(h); }
+int ref_offline_infer_buffer(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap, char* stamp,
+                             int stamp_cap, char* sents, int sents_cap) {
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  FUNASR_RESULT r = FunOfflineInferBuffer(h, buf, n_bytes, RASR_NONE, nullptr, hw, 16000, "pcm", true, vad_tail_sil, vad_max_len);
+  if (!r) return -1;
+  const int n = CopyOut(FunASRGetResult(r, 0), text, text_cap);
+  if (CopyOut(FunASRGetStamp(r), stamp, stamp_cap) < 0 || CopyOut(FunASRGetStampSents(r), sents, sents_cap) < 0) return -2;
+  FunASRFreeResult(r);
+  return n;
+}
 }  // extern "C"

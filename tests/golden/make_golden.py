@@ -323,6 +323,29 @@ def make_am_golden(synth):
                     arrays["feats_%s_%d" % (name, k)] = seen["feats"][0]
             out["forward"].append(case)
         m.close()
+    # the reference's exported offline API end to end (tests/test_am_ref_cpu.py::test_reference_offline_api_end_to_end)
+    capi = importlib.import_module("asr-2pass_b200.capi")
+    root = tempfile.mkdtemp(prefix="offline_golden_")
+    m = TA._offline_setup(synth, root)
+    V, PR = m["V"], m["PR"]
+
+    def vad_net(ins):
+        caches = [torch.from_numpy(c[0, :, :, 0].copy()) for c in ins[1:5]]
+        sc, nc = V.forward(ins[0][0], m["VWt"], caches)
+        return [sc.numpy()[None].astype(np.float32)] + [c.numpy()[None, :, :, None].astype(np.float32) for c in nc]
+
+    def punc_net(ins):
+        return [PR.forward(ins[0][0], m["PWt"], m["pcfg"]).numpy()[None].astype(np.float32)]
+
+    out["offline"] = []
+    for case in TA.OFFLINE_CASES:
+        pcm = TA._offline_audio(synth, case)
+        thres, ns, _, _, _ = TA._oracle_offline(capi, m, pcm, case)
+        ref = A.RefOffline(m["amd"], TA._net(m["pc"], m["Wt"], {}), am_outputs=4, vad_dir=m["vd"], vad_net=vad_net, vad_thres=thres,
+                           punc_dir=m["pd"], punc_net=punc_net)
+        text, stamp, sents = ref.infer_buffer(pcm, case["tail"], case["max_len"])
+        ref.close()
+        out["offline"].append(dict(text=text, stamp=stamp, stamp_sents=sents, n_segments=ns, thres=thres))
     np.savez_compressed(os.path.join(HERE, "am_forward_golden.npz"), **arrays)
     with open(os.path.join(HERE, "am_forward_golden.json"), "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)

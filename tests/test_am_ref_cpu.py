@@ -132,3 +132,95 @@ def test_hotword_packing_matches_reference_golden(capi, synth, tmp_path):
         ids, lens = capi.host_pack_hotwords(toks, case["text"], sd)
         assert ids.tolist() == case["ids"], case["text"]
         assert lens.tolist() == case["lengths"], case["text"]
+
+
+# ---- the reference's exported offline API end to end (funasrruntime.cpp FunOfflineInit / FunOfflineInferBuffer) ---------------
+OFFLINE_PUNC = dict(vocab=20000, d_model=64, n_heads=4, d_ff=128, n_layers=2)
+OFFLINE_CASES = [dict(bursts=[(48000, 24000), (80000, 40000), (160000, 32000)], seed=70, tail=500, max_len=15000, q=0.5),
+                 dict(bursts=[(30000, 9000), (12000, 30000), (90000, 5000), (20000, 16000)], seed=90, tail=250, max_len=3000, q=0.4),
+                 dict(bursts=[(8000, 0)], seed=95, tail=800, max_len=60000, q=0.5)]
+
+
+def _offline_setup(synth, root):
+    from oracle import punc_ref as PR
+    from oracle import vad_ref as V
+    amd, vd, pd = (os.path.join(root, x) for x in ("am", "vad", "punc"))
+    for x in (amd, vd, pd):
+        os.makedirs(x)
+    pc, Wt, means, vars_, toks = _model(synth, amd, dict(timestamp=1))
+    VW, vmeans, vvars = synth.write_synthetic_vad_dir(vd, seed=0)
+    VWt = {k: torch.from_numpy(v) for k, v in VW.items()}
+    pcfg, PW, ptoks = synth.write_synthetic_punc_dir(pd, OFFLINE_PUNC, seed=5)
+    PWt = {k: torch.from_numpy(v) for k, v in PW.items()}
+    return dict(amd=amd, vd=vd, pd=pd, pc=pc, Wt=Wt, means=means, vars=vars_, toks=toks, VWt=VWt, vmeans=vmeans, vvars=vvars, pcfg=pcfg,
+                PWt=PWt, ptoks=ptoks, PR=PR, V=V)
+
+
+def _offline_audio(synth, case):
+    parts = []
+    for i, (ns, nsil) in enumerate(case["bursts"]):
+        parts += [synth.make_audio(ns, case["seed"] + i), np.zeros(nsil, np.int16)]
+    return np.concatenate(parts)
+
+
+def _oracle_offline(capi, m, pcm, case):
+    """The oracle's composition of the offline request path: whole-recording VAD scores -> SegmentVad -> per segment fbank / LFR /
+    network / greedy search with stamps (in ascending-length order, like the reference calls Forward) -> stitching -> AddPunc ->
+    sentence stamps."""
+    PR, V = m["PR"], m["V"]
+    x = pcm.astype(np.float32) / np.float32(32768)
+    p0 = V.forward(V.lfr_cmvn(F.fbank(x), m["vmeans"], m["vvars"]), m["VWt"])[0].numpy()[:, 0]
+    thres = float(np.clip(1.0 - 2.0 * np.quantile(p0, case["q"]), 0.05, 0.95))
+    segs = capi.host_vad_segments(p0, case["tail"], case["max_len"], thres)
+    v = P.Vocab(m["toks"])
+    msgs = [None] * len(segs)
+    for i in sorted(range(len(segs)), key=lambda k: int(segs[k][1]) - int(segs[k][0])):
+        seg = x[int(segs[i][0]) * 16:int(segs[i][1]) * 16]
+        o = R.forward(F.lfr_cmvn(F.fbank(seg), m["means"], m["vars"]), m["Wt"], m["pc"], want_taps=False)
+        msgs[i] = P.greedy_search_text(v, o["ids"], "zh-cn", o["us_alphas"].numpy(), o["us_peaks"].numpy())
+    text, stamp = P.stitch_offline(msgs, [float(int(s[0]) * 16) / 16000 for s in segs], "zh-cn")
+    tok = PR.Tokenizer(m["ptoks"])
+    text = PR.add_punc(text, tok, lambda ids: PR.infer_ids(PR.forward(ids, m["PWt"], m["pcfg"]).numpy()), "zh-cn")
+    sents = capi.host_sentence_stamps(text, stamp) if stamp else ""
+    return thres, len(segs), text, stamp, sents
+
+
+def test_reference_offline_api_end_to_end(capi, synth, tmp_path):
+    """The reference's OWN FunOfflineInit / FunOfflineInferBuffer (funasrruntime.cpp, offline-stream.cpp, audio.cpp, fsmn-vad*.cpp,
+    paraformer.cpp, ct-transformer.cpp, util.cpp compiled in place) on model directories whose sessions are served by the oracle's
+    networks: LoadPcmwav, CutSplit, length sort + un-permute, Forward per segment, stitching, punctuation, TimestampSentence.  Its
+    text / stamp / stamp_sents must equal the oracle's composition of the same path."""
+    needs_ref()
+    m = _offline_setup(synth, str(tmp_path))
+    V, PR = m["V"], m["PR"]
+
+    def vad_net(ins):
+        caches = [torch.from_numpy(c[0, :, :, 0].copy()) for c in ins[1:5]]
+        sc, nc = V.forward(ins[0][0], m["VWt"], caches)
+        return [sc.numpy()[None].astype(np.float32)] + [c.numpy()[None, :, :, None].astype(np.float32) for c in nc]
+
+    def punc_net(ins):
+        return [PR.forward(ins[0][0], m["PWt"], m["pcfg"]).numpy()[None].astype(np.float32)]
+
+    n_seg = 0
+    for k, case in enumerate(OFFLINE_CASES):
+        pcm = _offline_audio(synth, case)
+        thres, ns, text, stamp, sents = _oracle_offline(capi, m, pcm, case)
+        # a fresh handle per case: the threshold lives in the VAD directory's config.yaml
+        ref = A.RefOffline(m["amd"], _net(m["pc"], m["Wt"], {}), am_outputs=4, vad_dir=m["vd"], vad_net=vad_net, vad_thres=thres,
+                           punc_dir=m["pd"], punc_net=punc_net)
+        got = ref.infer_buffer(pcm, case["tail"], case["max_len"])
+        ref.close()
+        assert got == (text, stamp, sents), k
+        n_seg += ns
+    assert n_seg >= 5
+
+
+def test_oracle_offline_flow_matches_reference_golden(capi, synth, tmp_path):
+    """Same comparison against the strings the reference's API produced in the build container (am_forward_golden.json)."""
+    g = json.load(open(GOLD, encoding="utf-8"))
+    m = _offline_setup(synth, str(tmp_path))
+    assert len(g["offline"]) == len(OFFLINE_CASES)
+    for case, gold in zip(OFFLINE_CASES, g["offline"]):
+        _, ns, text, stamp, sents = _oracle_offline(capi, m, _offline_audio(synth, case), case)
+        assert (text, stamp, sents) == (gold["text"], gold["stamp"], gold["stamp_sents"]) and ns == gold["n_segments"]
