@@ -11,9 +11,10 @@ timestamp post-processing on the Paraformer::Forward path.
 PARITY PINNED for Vector2StringV2 / Vector2String / TimestampOnnx / PostProcess: the reference's own vocab.cpp and util.cpp
 are compiled in place into oracle/_ref/libfunasr_text_ref.so (oracle/Makefile, oracle/text_ref.py) and this file reproduces
 them string for string on thousands of random inputs (tests/test_oracle_cpu.py, live when oracle/_ref is built) and on the
-committed vectors generated from the compiled reference (tests/golden/text_golden.json).  stitch_offline and fetch_dynamic
-follow the source line by line (funasrruntime.cpp / audio.cpp do not compile stand-alone: ffmpeg, ORT sessions) and stay
-unpinned.  float arithmetic is done in numpy float32 where the C++ uses float, and `std::to_string(float)` is reproduced as
+committed vectors generated from the compiled reference (tests/golden/text_golden.json).  stitch_offline is pinned through the
+reference's own FunOfflineInferBuffer, which runs end to end over the stand-in onnxruntime (oracle/am_ref.py RefOffline,
+tests/test_am_ref_cpu.py::test_reference_offline_api_end_to_end); fetch_dynamic follows audio.cpp line by line (on the reference's
+CPU path it only ever forms batches of one, so its grouping cannot be observed there).  float arithmetic is done in numpy float32 where the C++ uses float, and `std::to_string(float)` is reproduced as
 '%f' of the float promoted to double.
 """
 import numpy as np

@@ -11,7 +11,10 @@ reference's call-site contract only: feature dim 400 = 80 mel x LFR 5 (com-defin
 (fsmn-vad.cpp:96-100,127-133), output dim consumed as scores[t][sil_pdf_id] with sil_pdf_ids = {0} (e2e-vad.h:602-608).
 
 The front end (fbank 80, LFR m=5 n=1, CMVN) is FsmnVad::FbankKaldi / LfrCmvn (fsmn-vad.cpp:137-224): the fbank is the same
-knf configuration as the acoustic model's (oracle/frontend.py), the LFR is restated below.
+knf configuration as the acoustic model's (oracle/frontend.py), the LFR is restated below.  Front end, cache interface and the
+equivalence "whole recording in one pass == the reference's 1 s pieces through FsmnVadOnline" ARE pinned: the reference's own
+fsmn-vad.cpp / fsmn-vad-online.cpp, compiled in place and driven like Audio::CutSplit with `forward` behind the session, see the
+same frames and features and cut the same segments (tests/test_vad.py::test_whole_recording_vad_equals_reference_cutsplit).
 """
 import numpy as np
 import torch
