@@ -23,7 +23,10 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("feat_dim", "d_model", "n_heads", "d_ff", "n_enc", "n_dec", "kernel", "vocab", "pred_residual")] + \
                [(n, C.c_float) for n in ("cif_threshold", "tail_threshold", "ln_eps")] + \
-               [(n, C.c_int32) for n in ("sample_rate", "max_rows", "max_segments", "timestamp", "contextual")]
+               [(n, C.c_int32) for n in ("sample_rate", "max_rows", "max_segments", "timestamp", "contextual", "precision")]
+
+
+PREC_BF16, PREC_FP16 = 0, 1
 
 
 class Result(C.Structure):
@@ -46,14 +49,14 @@ def build_library(verbose=False):
 
 
 EXPORTS = [
-    "b200pf_last_error", "b200pf_version", "b200pf_device_count", "b200pf_model_dir_probe", "b200pf_engine_create", "b200pf_engine_destroy",
+    "b200pf_last_error", "b200pf_version", "b200pf_device_count", "b200pf_model_dir_probe", "b200pf_engine_create", "b200pf_engine_create_prec", "b200pf_op_set_precision", "b200pf_engine_destroy",
     "b200pf_engine_config", "b200pf_engine_vocab_size", "b200pf_engine_token", "b200pf_engine_lang",
     "b200pf_engine_set_option", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_engine_copy_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
     "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
     "b200pf_batch_stage_f32", "b200pf_batch_stage_s16_ptrs", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
-    "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
-    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_op_gemm_ln", "b200pf_vad_create", "b200pf_vad_destroy", "b200pf_vad_scores_s16",
+    "b200pf_op_layernorm", "b200pf_op_attention", "b200pf_op_attention_bench", "b200pf_op_fsmn", "b200pf_op_cif", "b200pf_op_frontend",
+    "b200pf_batch_set_hotwords", "b200pf_engine_hotword_embed", "b200pf_op_lstm", "b200pf_op_us_peaks", "b200pf_op_lstm_bench", "b200pf_op_logprob_topk", "b200pf_vad_create", "b200pf_vad_destroy", "b200pf_vad_scores_s16",
     "b200pf_punc_create", "b200pf_punc_destroy", "b200pf_punc_info", "b200pf_punc_infer", "b200pf_punc_infer_vad", "b200pf_punc_launches",
 ]
 
@@ -68,6 +71,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     L.b200pf_last_error.restype = C.c_char_p
     L.b200pf_engine_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.b200pf_engine_create_prec.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.b200pf_model_dir_probe.argtypes = [C.c_char_p, C.POINTER(Config), c_i32p, c_i32p]
     L.b200pf_engine_destroy.argtypes = [C.c_void_p]
     L.b200pf_engine_destroy.restype = None
@@ -106,6 +110,7 @@ def lib():
     L.b200pf_op_layernorm.argtypes = [C.c_int, c_f32p, C.c_int, C.c_int, c_f32p, c_f32p, C.c_float, C.c_int, c_f32p, c_f32p]
     L.b200pf_op_attention.argtypes = [C.c_int, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, c_i32p, c_i32p, C.c_int, C.c_int,
                                       C.c_int64, C.c_int64, C.c_int, c_f32p]
+    L.b200pf_op_attention_bench.argtypes = [C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, C.POINTER(C.c_double)]
     L.b200pf_op_fsmn.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, C.c_int, c_f32p]
     L.b200pf_op_cif.argtypes = [C.c_int, c_f32p, c_f32p, c_i32p, C.c_int, C.c_float, c_i32p, c_f32p, c_f32p, c_i32p, C.c_int64]
     L.b200pf_op_frontend.argtypes = [C.c_void_p, c_i16p, C.c_int64, c_f32p, c_f32p]
@@ -604,11 +609,13 @@ def device_count():
 
 
 class Engine:
-    """One GPU: resident bf16 weights + workspace (replaces Paraformer::InitAsr, paraformer.cpp:21-53)."""
+    """One GPU: resident 16-bit weights + workspace (replaces Paraformer::InitAsr, paraformer.cpp:21-53).
+    prec: None = the library default (fp16 operands; env B200PF_PREC overrides), "bf16" / "fp16" or PREC_* to force one."""
 
-    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0):
+    def __init__(self, model_dir, device=0, max_rows=0, max_segments=0, prec=None):
         self.h = C.c_void_p()
-        _check(lib().b200pf_engine_create(model_dir.encode(), device, max_rows, max_segments, C.byref(self.h)))
+        p = -1 if prec is None else ({"bf16": PREC_BF16, "fp16": PREC_FP16}[prec] if isinstance(prec, str) else int(prec))
+        _check(lib().b200pf_engine_create_prec(model_dir.encode(), device, max_rows, max_segments, p, C.byref(self.h)))
         self.cfg = Config()
         _check(lib().b200pf_engine_config(self.h, C.byref(self.cfg)))
 
@@ -876,6 +883,11 @@ class Batch:
 
 
 # ---- single-operator wrappers (parity tests) ---------------------------------------------------------
+def op_set_precision(prec):
+    """16-bit operand format of the op_* entry points of this process: "bf16" / "fp16" (the default, like the engine)."""
+    _check(lib().b200pf_op_set_precision({"bf16": PREC_BF16, "fp16": PREC_FP16}[prec] if isinstance(prec, str) else int(prec)))
+
+
 def op_gemm(A, W, bias=None, add=None, res=None, relu=0, out_bf16=False, argmax=False, device=0, general=False):
     A, W = _f32(A), _f32(W)
     M, K = A.shape
@@ -898,17 +910,6 @@ def op_lstm(x, seq_off, seq_len, w_ih, w_hh, b_ih, b_hh, bf16_out=False, device=
     _check(lib().b200pf_op_lstm(device, _p(x), x.shape[0], _p(so, c_i32p), _p(sl, c_i32p), len(so), n_dir, _p(w_ih), _p(w_hh),
                                 _p(b_ih), _p(b_hh), int(bf16_out), _p(out)))
     return out
-
-
-def op_gemm_ln(x, gamma, beta, W, bias=None, relu=0, eps=1e-12, iters=0, device=0):
-    """LN(x) @ W^T (+bias)(+relu) -> bf16, the fused LayerNorm + GEMM kernel.  Returns (out fp32 [M,N], ms per launch or None)."""
-    x, gamma, beta, W, bias = _f32(x), _f32(gamma), _f32(beta), _f32(W), _f32(bias)
-    M, N = x.shape[0], W.shape[0]
-    out = np.zeros((M, N), np.float32)
-    ms = C.c_float(0)
-    _check(lib().b200pf_op_gemm_ln(device, _p(x), _p(gamma), _p(beta), C.c_float(eps), _p(W), _p(bias), M, N, int(relu), int(iters),
-                                   _p(out), C.byref(ms)))
-    return out, (ms.value if iters > 0 else None)
 
 
 def op_logprob_topk(logits, k, device=0):
@@ -970,6 +971,14 @@ def op_attention(q, k, v, q_off, q_len, kv_off, kv_len, n_heads=4, impl=0, devic
     _check(lib().b200pf_op_attention(device, _p(q), _p(k), _p(v), _p(q_off, c_i32p), _p(q_len, c_i32p), _p(kv_off, c_i32p),
                                      _p(kv_len, c_i32p), len(q_len), n_heads, q.shape[0], k.shape[0], impl, _p(out)))
     return out
+
+
+def op_attention_bench(seg_T, n_heads=4, cross=False, impl=0, iters=20, device=0):
+    """(ms per launch, algorithmic FLOPs per launch) of the attention kernel on engine-shaped random operands."""
+    t = np.ascontiguousarray(seg_T, dtype=np.int32)
+    ms, fl = C.c_float(), C.c_double()
+    _check(lib().b200pf_op_attention_bench(device, _p(t, c_i32p), len(t), n_heads, int(bool(cross)), impl, iters, C.byref(ms), C.byref(fl)))
+    return ms.value, fl.value
 
 
 def op_fsmn(x, w, seg_off, device=0):

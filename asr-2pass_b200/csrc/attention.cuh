@@ -1,5 +1,5 @@
-// Variable-length multi-head attention on tcgen05/TMEM (head dim 128), one CTA per
-// (segment, 128-row query tile, head).  Serves both the SAN-M encoder self-attention (q,k,v slices of
+// Variable-length multi-head attention on tcgen05/TMEM (head dim 128): persistent CTAs walking
+// (segment, 128-row query tile) work items, all heads of an item pipelined through one CTA.  Serves both the SAN-M encoder self-attention (q,k,v slices of
 // the fused QKV buffer) and the decoder cross-attention (q from decoder tokens, k/v from the encoder
 // memory).  Replaces the MatMul-Softmax-MatMul subgraphs of the reference's ONNX model
 // (Ort::Session::Run, onnxruntime/src/paraformer.cpp:541).
@@ -32,8 +32,8 @@ struct AttnProblem {
   int n_work = 0;
   int n_heads = 4;
   float scale = 0.08838834764831845f;  // 128^-1/2
-  int online = 2;                      // 2: single pass, all heads pipelined through one CTA (product); 1: single pass, one CTA
-                                       // per head; 0: exact two-pass variant, one CTA per head
+  int f16 = 0;                         // 0: q, kv, out are bf16; 1: IEEE fp16 (the engine's precision 1)
+  int num_sms = 0;                     // SMs of the device (0 -> 148): the persistent grid is 2 CTAs per SM
 };
 
 int attention_tcgen05(const AttnProblem& p, cudaStream_t stream);

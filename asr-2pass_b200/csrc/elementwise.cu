@@ -1,14 +1,10 @@
 // K3 LayerNorm, K6 FSMN memory block, K7/K8 CIF predictor tail, K11 argmax decode.  See kernels.cuh.
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "ptx.cuh"
 
 namespace pf {
 namespace {
-
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -19,7 +15,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (two-pass mean / variance in fp32).
 // ------------------------------------------------------------------------------------------------
-template <int D, bool IN_BF16>
+template <int D, bool IN_BF16, bool F16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
@@ -43,9 +39,9 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
     if (vi < NVEC) {
       if (IN_BF16) {
         const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + (size_t)row * D + vi * 8);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { v[i * 8 + 2 * k] = __low2float(h[k]); v[i * 8 + 2 * k + 1] = __high2float(h[k]); }
+        for (int k = 0; k < 4; ++k) { const float2 f = unpack_h2<F16>(uw[k]); v[i * 8 + 2 * k] = f.x; v[i * 8 + 2 * k + 1] = f.y; }
       } else {
         const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + (size_t)row * D + vi * 4);
         v[i * 4] = f.x; v[i * 4 + 1] = f.y; v[i * 4 + 2] = f.z; v[i * 4 + 3] = f.w;
@@ -94,10 +90,7 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
       if (out_bf16) {
         uint32_t pk[VW / 2];
 #pragma unroll
-        for (int k = 0; k < VW / 2; ++k) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
-          pk[k] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        for (int k = 0; k < VW / 2; ++k) pk[k] = pack_h2<F16>(o[2 * k], o[2 * k + 1]);
         if (VW == 8)
           *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * D + c) = make_uint4(pk[0], pk[1], pk[VW / 2 - 2], pk[VW / 2 - 1]);
         else
@@ -127,7 +120,7 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2
 // benchmark workload take this path (segments are 33-333 rows, a window is 32); the general path handles segment edges, gap rows
 // and the batch tail.  Both paths apply the same FMAs in the same order to an output, so results do not depend on which one a row
 // falls into (batch invariance).  Measured: 11.6 -> 11.4 ms of FSMN time per step -- the kernel is not bound by that bookkeeping.
-template <bool FAST>
+template <bool FAST, bool F16>
 __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], const float* __restrict__ w_t,
                                          const int2* __restrict__ row_info, int nrows, int r0, int mode,
                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
@@ -171,8 +164,8 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
       if (FAST) {
         if (i < FSMN_RUN + 10) {
           const uint2 rw = tile[i][threadIdx.x];
-          const float2 x0 = make_float2(__uint_as_float(rw.x << 16), __uint_as_float(rw.x & 0xffff0000u));
-          const float2 x1 = make_float2(__uint_as_float(rw.y << 16), __uint_as_float(rw.y & 0xffff0000u));
+          const float2 x0 = unpack_h2<F16>(rw.x);
+          const float2 x1 = unpack_h2<F16>(rw.y);
 #pragma unroll
           for (int d = -5; d <= 5; ++d) {
             const int o = i - 5 - d;
@@ -186,10 +179,9 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
       } else {
         const int2 inf = info[cur][ii];
         if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
-          // bf16 -> fp32 is a 16-bit shift
           const uint2 rw = tile[i < FSMN_RUN + 10 ? i : 0][threadIdx.x];
-          const float2 x0 = make_float2(__uint_as_float(rw.x << 16), __uint_as_float(rw.x & 0xffff0000u));
-          const float2 x1 = make_float2(__uint_as_float(rw.y << 16), __uint_as_float(rw.y & 0xffff0000u));
+          const float2 x0 = unpack_h2<F16>(rw.x);
+          const float2 x1 = unpack_h2<F16>(rw.y);
           cur_valid |= 1u << ii;
           if (inf.x >= 5 && inf.x + 5 < inf.y) {
             // interior frame: all 11 neighbours are in the same segment
@@ -228,7 +220,7 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
           const bool out_valid = FAST ? true : ((ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u));
           if (mode == 0) {
             uint2 pk = make_uint2(0, 0);
-            if (out_valid) { pk.x = pack2(acc[slot_done][0].x, acc[slot_done][0].y); pk.y = pack2(acc[slot_done][1].x, acc[slot_done][1].y); }
+            if (out_valid) { pk.x = pack_h2<F16>(acc[slot_done][0].x, acc[slot_done][0].y); pk.y = pack_h2<F16>(acc[slot_done][1].x, acc[slot_done][1].y); }
             *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
           } else if (out_valid) {
             float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
@@ -247,6 +239,7 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
 
 // <= 128 registers: one FSMN CTA then fits next to two resident attention CTAs (2 x 24.6K + 16.4K registers = one SM), which is
 // what lets the two kernels run side by side (engine.cu, "overlap").
+template <bool F16>
 __global__ void __launch_bounds__(128, 4)
 fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
@@ -281,8 +274,8 @@ fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const flo
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  if (fast) fsmn_run<true>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
-  else fsmn_run<false>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
+  if (fast) fsmn_run<true, F16>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
+  else fsmn_run<false, F16>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -504,11 +497,19 @@ logprob_topk_kernel(const float* __restrict__ logits, int V, const int* __restri
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+template <bool F16>
+__global__ void f32_to_h16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int64_t n) {
   pdl_wait();
   pdl_launch_dependents();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(in[i]);
+    out[i] = pack_h1<F16>(in[i]);
+}
+template <bool F16>
+__global__ void h16_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = unpack_h2<F16>((uint32_t)in[i]).x;
 }
 
 // LayerNorm over 512 fp32 columns with the rows staged through shared memory by cp.async: a warp owns 4 consecutive rows, every
@@ -516,6 +517,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 // 192 KB per SM in flight -- three times what register loads allowed) and normalises row k as soon as group k has landed.  A
 // lane reads back only what it copied itself, so no barrier is needed; the arithmetic is that of layernorm_kernel<512, false>.
 constexpr int LNS_ROWS_PER_WARP = 4, LNS_WARPS = 8, LNS_SMEM = LNS_WARPS * LNS_ROWS_PER_WARP * 512 * 4;
+template <bool F16>
 __global__ void __launch_bounds__(256)
 layernorm512_staged_kernel(const float* __restrict__ in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
                            const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32,
@@ -583,8 +585,7 @@ layernorm512_staged_kernel(const float* __restrict__ in, int rows, const int* __
       if (gap) { o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; o[3] = 0.f; }
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * 512 + c) = make_float4(o[0], o[1], o[2], o[3]);
       if (out_bf16) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
-        *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * 512 + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * 512 + c) = make_uint2(pack_h2<F16>(o[0], o[1]), pack_h2<F16>(o[2], o[3]));
       }
     }
   }
@@ -593,6 +594,7 @@ layernorm512_staged_kernel(const float* __restrict__ in, int rows, const int* __
 // The decoder's LayerNorm(2048) on the bf16 FFN hidden rows, staged the same way: a warp owns 2 rows (8 KB), copies them with
 // cp.async (one commit group per row) and normalises row k when it has landed; arithmetic of layernorm_kernel<2048, true>.
 constexpr int LNB_ROWS_PER_WARP = 2, LNB_SMEM = LNS_WARPS * LNB_ROWS_PER_WARP * 2048 * 2;
+template <bool F16>
 __global__ void __launch_bounds__(256)
 layernorm2048_staged_kernel(const __nv_bfloat16* in, int rows, const int* __restrict__ rows_dev, const float* __restrict__ gamma,
                             const float* __restrict__ beta, float eps, __nv_bfloat16* out_bf16, float* __restrict__ out_f32) {
@@ -630,9 +632,9 @@ layernorm2048_staged_kernel(const __nv_bfloat16* in, int rows, const int* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 u = *reinterpret_cast<const uint4*>(mine + k * 2048 + (lane + 32 * i) * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { v[i * 8 + 2 * e] = __low2float(h[e]); v[i * 8 + 2 * e + 1] = __high2float(h[e]); }
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack_h2<F16>(uw[e]); v[i * 8 + 2 * e] = f.x; v[i * 8 + 2 * e + 1] = f.y; }
 #pragma unroll
       for (int e = 0; e < 8; ++e) sum += v[i * 8 + e];
     }
@@ -664,70 +666,68 @@ layernorm2048_staged_kernel(const __nv_bfloat16* in, int rows, const int* __rest
       if (out_bf16) {
         uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-        }
+        for (int e = 0; e < 4; ++e) pk[e] = pack_h2<F16>(o[2 * e], o[2 * e + 1]);
         *reinterpret_cast<uint4*>(out_bf16 + (size_t)row * 2048 + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
 }
 
-template <int D>
+template <int D, bool F16>
 int ln_dispatch(const void* in, int in_is_bf16, int rows, const int* rows_dev, const float* gamma, const float* beta,
                 float eps, __nv_bfloat16* ob, float* of, const int2* ri, int zg, cudaStream_t s) {
   const int blocks = (rows + 7) / 8;
-  if (D == 512 && !in_is_bf16 && rows >= 4096) {   // large fp32 LayerNorms (the residual stream): staged loads
-    static const bool plain = getenv("B200PF_LN_PLAIN") != nullptr;
-    if (!plain) {
-      static bool attr_set[64] = {};
-      if (first_use_on_device(attr_set)) {
-        cudaError_t err = cudaFuncSetAttribute(layernorm512_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LNS_SMEM);
-        if (err != cudaSuccess) return (int)err;
-      }
-      const int per = LNS_WARPS * LNS_ROWS_PER_WARP;
-      return launch_kernel(layernorm512_staged_kernel, dim3((rows + per - 1) / per), dim3(256), LNS_SMEM, s, (const float*)in, rows, rows_dev, gamma, beta,
-                           eps, ob, of, ri, zg);
-    }
+  static const bool plain = getenv("B200PF_LN_PLAIN") != nullptr;
+  if (D == 512 && !in_is_bf16 && rows >= 4096 && !plain) {   // large fp32 LayerNorms (the residual stream): staged loads
+    static PerDeviceOnce once;
+    const int rc = once_per_device(once, [] {
+      return (int)cudaFuncSetAttribute(layernorm512_staged_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNS_SMEM);
+    });
+    if (rc) return rc;
+    const int per = LNS_WARPS * LNS_ROWS_PER_WARP;
+    return launch_kernel(layernorm512_staged_kernel<F16>, dim3((rows + per - 1) / per), dim3(256), LNS_SMEM, s, (const float*)in, rows, rows_dev, gamma,
+                         beta, eps, ob, of, ri, zg);
   }
-  if (D == 2048 && in_is_bf16 && rows >= 4096 && !ri) {   // the decoder's FFN LayerNorm on large batches: staged loads
-    static const bool plain = getenv("B200PF_LN_PLAIN") != nullptr;
-    if (!plain) {
-      static bool attr_set[64] = {};
-      if (first_use_on_device(attr_set)) {
-        cudaError_t err = cudaFuncSetAttribute(layernorm2048_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_SMEM);
-        if (err != cudaSuccess) return (int)err;
-      }
-      const int per = LNS_WARPS * LNB_ROWS_PER_WARP;
-      return launch_kernel(layernorm2048_staged_kernel, dim3((rows + per - 1) / per), dim3(256), LNB_SMEM, s, (const __nv_bfloat16*)in, rows, rows_dev,
-                           gamma, beta, eps, ob, of);
-    }
+  if (D == 2048 && in_is_bf16 && rows >= 4096 && !ri && !plain) {   // the decoder's FFN LayerNorm on large batches: staged loads
+    static PerDeviceOnce once;
+    const int rc = once_per_device(once, [] {
+      return (int)cudaFuncSetAttribute(layernorm2048_staged_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNB_SMEM);
+    });
+    if (rc) return rc;
+    const int per = LNS_WARPS * LNB_ROWS_PER_WARP;
+    return launch_kernel(layernorm2048_staged_kernel<F16>, dim3((rows + per - 1) / per), dim3(256), LNB_SMEM, s, (const __nv_bfloat16*)in, rows,
+                         rows_dev, gamma, beta, eps, ob, of);
   }
   if (in_is_bf16)
-    return launch_kernel(layernorm_kernel<D, true>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
-  return launch_kernel(layernorm_kernel<D, false>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
+    return launch_kernel(layernorm_kernel<D, true, F16>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
+  return launch_kernel(layernorm_kernel<D, false, F16>, dim3(blocks), dim3(256), 0, s, in, rows, rows_dev, gamma, beta, eps, ob, of, ri, zg);
 }
 
 }  // namespace
 
 int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_dev, int D, const float* gamma,
                      const float* beta, float eps, __nv_bfloat16* out_bf16, float* out_f32, const int2* row_info,
-                     int zero_gap, cudaStream_t s) {
+                     int zero_gap, cudaStream_t s, int f16) {
   if (rows <= 0) return 0;
+#define PF_LN_CASE(DD)                                                                                                          \
+  case DD:                                                                                                                      \
+    return f16 ? ln_dispatch<DD, true>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s) \
+               : ln_dispatch<DD, false>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
   switch (D) {
-    case 512: return ln_dispatch<512>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
-    case 560: return ln_dispatch<560>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
-    case 2048: return ln_dispatch<2048>(in, in_is_bf16, rows, rows_dev, gamma, beta, eps, out_bf16, out_f32, row_info, zero_gap, s);
+    PF_LN_CASE(512)
+    PF_LN_CASE(560)
+    PF_LN_CASE(2048)
     default: return (int)cudaErrorInvalidValue;
   }
+#undef PF_LN_CASE
 }
 
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
-                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s) {
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16) {
   if (rows <= 0) return 0;
-  return launch_kernel(fsmn_kernel, dim3((rows + FSMN_RUN - 1) / FSMN_RUN), dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev,
-                       mode, out_bf16, y_f32);
+  const dim3 grid((rows + FSMN_RUN - 1) / FSMN_RUN);
+  if (f16) return launch_kernel(fsmn_kernel<true>, grid, dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
+  return launch_kernel(fsmn_kernel<false>, grid, dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
 }
 
 int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,
@@ -765,11 +765,20 @@ int logprob_topk_launch(const float* logits, int V, const int* n_dev, int cap, i
   return launch_kernel(logprob_topk_kernel, dim3((cap + 7) / 8), dim3(256), 0, s, logits, V, n_dev, cap, k, lse, lp, ids);
 }
 
-int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s) {
+int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s, int f16) {
   if (n <= 0) return 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  return launch_kernel(f32_to_bf16_kernel, dim3((int)blocks), dim3(256), 0, s, in, out, n);
+  if (f16) return launch_kernel(f32_to_h16_kernel<true>, dim3((int)blocks), dim3(256), 0, s, in, reinterpret_cast<uint16_t*>(out), n);
+  return launch_kernel(f32_to_h16_kernel<false>, dim3((int)blocks), dim3(256), 0, s, in, reinterpret_cast<uint16_t*>(out), n);
+}
+
+int h16_to_f32_launch(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t s, int f16) {
+  if (n <= 0) return 0;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (f16) return launch_kernel(h16_to_f32_kernel<true>, dim3((int)blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t*>(in), out, n);
+  return launch_kernel(h16_to_f32_kernel<false>, dim3((int)blocks), dim3(256), 0, s, reinterpret_cast<const uint16_t*>(in), out, n);
 }
 
 }  // namespace pf

@@ -31,6 +31,26 @@ static uint16_t f32_to_bf16_rne(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// IEEE fp16 with round-to-nearest-even, saturating to +-65504 like the device-side cvt.rn.satfinite (ptx.cuh pack_h2)
+static uint16_t f32_to_f16_rne_sat(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);           // NaN
+  if (u >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);          // >= 65520 rounds past the largest finite value: saturate
+  if (u < 0x38800000u) {                                            // below 2^-14: subnormal half (or zero)
+    if (u < 0x33000000u) return sign;                               // < 2^-25 rounds to zero
+    const int shift = 126 - (int)(u >> 23);                         // 14 .. 24
+    const uint32_t mant = (u & 0x7fffffu) | 0x800000u;
+    const uint32_t q = mant >> shift, rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    return (uint16_t)(sign | (q + ((rem > half || (rem == half && (q & 1u))) ? 1u : 0u)));
+  }
+  const uint32_t v = u - 0x38000000u;                               // re-bias the exponent (127 -> 15)
+  return (uint16_t)(sign | ((v + 0xfffu + ((v >> 13) & 1u)) >> 13));
+}
+uint16_t f32_to_h16(float f, int f16) { return f16 ? f32_to_f16_rne_sat(f) : f32_to_bf16_rne(f); }
+
 int num_fbank_frames(int64_t n) { return n < 400 ? 0 : (int)(1 + (n - 400) / 160); }
 int num_lfr_frames(int64_t n) {
   const int nfb = num_fbank_frames(n);
@@ -86,7 +106,7 @@ struct Loader {
   }
   __nv_bfloat16* up_bf16(const float* h, size_t n) {
     std::vector<uint16_t> tmp(n);
-    for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_bf16_rne(h[i]);
+    for (size_t i = 0; i < n; ++i) tmp[i] = f32_to_h16(h[i], e->f16);
     void* d = e->warena.take(n * 2);
     if (!d) { fail("weight arena exhausted"); return nullptr; }
     if (cudaMemcpy(d, tmp.data(), n * 2, cudaMemcpyHostToDevice) != cudaSuccess) fail("weight upload failed");
@@ -217,8 +237,17 @@ int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tok
 }
 
 int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out) {
+  return b200pf_engine_create_prec(model_dir, device, max_rows, max_segments, -1, out);
+}
+
+int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out) {
   if (!model_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
   *out = nullptr;
+  if (precision < 0) {   // default: fp16 operands (meets the stated 1e-2 tolerance); B200PF_PREC overrides
+    const char* env = getenv("B200PF_PREC");
+    precision = (env && (strcmp(env, "bf16") == 0 || strcmp(env, "0") == 0)) ? B200PF_PREC_BF16 : B200PF_PREC_FP16;
+  }
+  if (precision != B200PF_PREC_BF16 && precision != B200PF_PREC_FP16) { set_error("precision must be 0 (bf16) or 1 (fp16)"); return B200PF_ERR_INVALID; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
     cudaGetLastError();
@@ -244,6 +273,8 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
 
   b200pf_config& c = e->cfg;
   fill_config(wf, fs, &c);
+  e->f16 = precision == B200PF_PREC_FP16 ? 1 : 0;
+  c.precision = precision;
   c.max_rows = max_rows > 0 ? max_rows : 32768;
   c.max_segments = max_segments > 0 ? max_segments : 4096;
   if (c.feat_dim != 560 || c.d_model != 512 || c.n_heads != 4 || c.d_ff != 2048 || c.kernel != 11 || (c.vocab & 3) ||
@@ -401,8 +432,7 @@ int b200pf_engine_create(const char* model_dir, int device, int max_rows, int ma
             ws_take(e.get(), &e->cif_cur, R) && ws_take(e.get(), &e->cif_rem, R) && ws_take(e.get(), &e->fire_val, R) &&
             ws_take(e.get(), &e->fire_row, R) && ws_take(e.get(), &e->amax, R) && ws_take(e.get(), &e->tok_info, R);
   if (ok && c.timestamp)
-    ok = ws_take(e.get(), &e->us_gx, R * 3 * 4096) && ws_take(e.get(), &e->us_h, R * 3 * 1024) && ws_take(e.get(), &e->us_a2, R * 3) &&
-         ws_take(e.get(), &e->us_alphas, R * 3) && ws_take(e.get(), &e->us_peaks, R * 3);
+    ok = ws_take(e.get(), &e->us_gx, R * 3 * 4096) && ws_take(e.get(), &e->us_h, R * 3 * 1024) && ws_take(e.get(), &e->us_a2, R * 3);
   if (ok && c.contextual) ok = ws_take(e.get(), &e->hw_kv, (size_t)B200PF_MAX_HOTWORDS * 1024);
   if (!ok) { set_error("workspace arena exhausted"); return B200PF_ERR_CUDA; }
   CK(cudaMemset(e->ws.base, 0, bytes), "cudaMemset(workspace)");
@@ -421,9 +451,6 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   cudaFree(e->tap_emb);
   cudaFree(e->tap_logits);
   cudaFree(e->full_logits);
-  cudaFree(e->topk_lse);
-  cudaFree(e->topk_lp);
-  cudaFree(e->topk_id);
   cudaStreamSynchronize(e->side);
   cudaStreamDestroy(e->side);
   cudaStreamSynchronize(e->copy);
@@ -468,18 +495,11 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   if (strcmp(key, "logprob_topk") == 0) {
     if (value < 0 || value > B200PF_MAX_TOPK) { set_error("logprob_topk must be in [0, 32]"); return B200PF_ERR_INVALID; }
     CK(cudaSetDevice(e->device), "cudaSetDevice");
-    if (value > 0 && !e->topk_lp) {
+    if (value > 0 && !e->full_logits) {
       const size_t R = (size_t)e->cfg.max_rows;
       CK(cudaMalloc((void**)&e->full_logits, R * (size_t)e->cfg.vocab * 4), "cudaMalloc(logits)");
-      CK(cudaMalloc((void**)&e->topk_lse, R * 4), "cudaMalloc(topk)");
-      CK(cudaMalloc((void**)&e->topk_lp, R * B200PF_MAX_TOPK * 4), "cudaMalloc(topk)");
-      CK(cudaMalloc((void**)&e->topk_id, R * B200PF_MAX_TOPK * 4), "cudaMalloc(topk)");
     }
     e->topk = value;
-    return 0;
-  }
-  if (strcmp(key, "attn_online") == 0) {
-    e->attn_online = value < 0 ? 0 : (value > 2 ? 2 : value);
     return 0;
   }
   if (strcmp(key, "profile") == 0) {
@@ -544,7 +564,12 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   b->h_zero = (int*)(b->h_meta + o_zero);             b->d_zero = (const int*)(b->d_meta + o_zero);
   b->h_hw_len = (int*)(b->h_meta + o_hwlen);          b->d_hw_len = (const int*)(b->d_meta + o_hwlen);
   memset(b->h_meta, 0, off);
-  if (e->cfg.timestamp) CK(cudaMallocHost((void**)&b->h_us, R * 3 * 2 * sizeof(float)), "cudaMallocHost(us)");
+  if (e->cfg.timestamp) {
+    // results live per batch (not in the engine's workspace): run(A), run(B), collect(A) must return A's own values
+    CK(cudaMallocHost((void**)&b->h_us, R * 3 * 2 * sizeof(float)), "cudaMallocHost(us)");
+    CK(cudaMalloc((void**)&b->d_us_alphas, R * 3 * 2 * sizeof(float)), "cudaMalloc(us)");
+    b->d_us_peaks = b->d_us_alphas + R * 3;
+  }
   if (e->cfg.contextual) CK(cudaMalloc((void**)&b->d_hw, (size_t)B200PF_MAX_HOTWORDS * 512 * 2), "cudaMalloc(hotwords)");
   CK(cudaMalloc((void**)&b->d_n_tok, (2 * S + 2 + 2 * R + 16) * 4), "cudaMalloc(results)");
   b->d_tok_off = b->d_n_tok + S;
@@ -568,6 +593,8 @@ void b200pf_batch_destroy(b200pf_batch* b) {
   cudaFreeHost(b->h_res);
   if (b->h_us) cudaFreeHost(b->h_us);
   if (b->h_topk) cudaFreeHost(b->h_topk);
+  if (b->d_us_alphas) cudaFree(b->d_us_alphas);
+  if (b->d_topk_lse) cudaFree(b->d_topk_lse);
   if (b->d_hw) cudaFree(b->d_hw);
   cudaEventDestroy(b->staged);
   delete b;
@@ -626,7 +653,7 @@ int b200pf_batch_set_hotwords(b200pf_batch* b, const float* hw_emb, int n_hw, in
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   if (n_hw > 0) {
     std::vector<uint16_t> tmp((size_t)n_hw * dim);
-    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = f32_to_bf16_rne(hw_emb[i]);
+    for (size_t i = 0; i < tmp.size(); ++i) tmp[i] = f32_to_h16(hw_emb[i], e->f16);
     CK(cudaStreamSynchronize(e->stream), "sync");  // a forward that still reads the previous embeddings may be in flight
     CK(cudaMemcpy(b->d_hw, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice), "H2D hotwords");
   }
@@ -666,12 +693,12 @@ int b200pf_engine_hotword_embed(b200pf_engine* e, const int32_t* ids, const int3
   if ((rc = (int)cudaMemsetAsync(d_h, 0, b_h, s))) return fin(rc, "memset");
   if ((rc = embed_gather_launch(e->hw_table, e->cfg.vocab, d_ids, (int)rows, d_x, s))) return fin(rc, "embed gather");
   GemmProblem gp;
-  gp.A = d_x; gp.lda = D; gp.rows_a = (int64_t)rows; gp.W = e->hw_ih.w; gp.ldw = D; gp.M = (int)rows; gp.N = 4 * D; gp.K = D;
+  gp.A = d_x; gp.lda = D; gp.rows_a = (int64_t)rows; gp.W = e->hw_ih.w; gp.ldw = D; gp.M = (int)rows; gp.N = 4 * D; gp.K = D; gp.f16 = e->f16;
   GemmEpilogue ge;
   ge.bias = e->hw_ih.b; ge.out_bf16 = d_gx; ge.ld_out_bf16 = 4 * D;
   if ((rc = gemm_bf16_tcgen05(gp, ge, e->num_sms, s))) return fin(rc, "hotword input projection");
   LstmParams lp;
-  lp.gx = d_gx; lp.ld_gx = 4 * D; lp.whh = e->hw_hh; lp.seq_off = d_off; lp.seq_len = d_len; lp.n_seq = n_words; lp.n_dir = 1;
+  lp.f16 = e->f16; lp.gx = d_gx; lp.ld_gx = 4 * D; lp.whh = e->hw_hh; lp.seq_off = d_off; lp.seq_len = d_len; lp.n_seq = n_words; lp.n_dir = 1;
   lp.out_f32 = d_h; lp.ld_out_f32 = D;
   if ((rc = lstm_launch(lp, s))) return fin(rc, "hotword lstm");
   std::vector<float> h(rows * D);
@@ -788,7 +815,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
                   const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0, int cat = 2) {
     GemmProblem p;
     p.A = A; p.lda = lda; p.rows_a = rows_a; p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
-    p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0;
+    p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0; p.f16 = e->f16;
     ++nl;
     const int h = prof_begin(cat, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
     const int rc = gemm_bf16_tcgen05(p, ep, sms, s);
@@ -807,11 +834,11 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   ap.kv = e->qkv; ap.kv_rows = M; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
   ap.out = e->att; ap.ldo = D;
   ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
-  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads; ap.online = e->attn_online;
+  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads; ap.f16 = e->f16; ap.num_sms = sms;
   for (int l = 0; l < c.n_enc; ++l) {
     const EncLayer& w = e->enc[l];
     const float* xin = l == 0 ? e->x0 : e->x;
-    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln1");
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln1");
     { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
       CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
     // The FSMN memory block and the attention both depend only on the QKV projection: run them concurrently
@@ -825,7 +852,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
       CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
     }
     if (fork && e->overlap == 2) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
-    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs), "fsmn");
+    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs, e->f16), "fsmn");
     if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
     if (!(fork && e->overlap == 2)) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
@@ -833,14 +860,14 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
       if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
       ep.out_f32 = e->x; ep.ld_out_f32 = D;
       CKL(gemm(e->att, D, M, w.out, M, nullptr, ep, 0, 0, 9), "gemm out"); }
-    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ln2");
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln2");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
       CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep, 0, 0, 10), "gemm ffn1"); }
     { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
       CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep, 0, 0, 11), "gemm ffn2"); }
   }
   LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
-                             b->d_row_info, 1, s), "after_norm");
+                             b->d_row_info, 1, s, e->f16), "after_norm");
 
   // ---- CIF predictor ----
   { GemmEpilogue ep; ep.bias = e->pred_conv.b; ep.out_f32 = e->x; ep.ld_out_f32 = D;
@@ -862,12 +889,12 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     { GemmEpilogue ep; ep.bias = e->blstm_ih.b; ep.out_bf16 = e->us_gx; ep.ld_out_bf16 = 8 * D;
       CKL(gemm(up, D, (int64_t)3 * M, e->blstm_ih, 3 * M, nullptr, ep, 0, 0, 15), "gemm blstm input"); }
     LstmParams lp;
-    lp.gx = e->us_gx; lp.ld_gx = 8 * D; lp.whh = e->blstm_hh; lp.seq_off = b->d_us_off; lp.seq_len = b->d_us_len; lp.n_seq = S;
+    lp.f16 = e->f16; lp.gx = e->us_gx; lp.ld_gx = 8 * D; lp.whh = e->blstm_hh; lp.seq_off = b->d_us_off; lp.seq_len = b->d_us_len; lp.n_seq = S;
     lp.n_dir = 2; lp.reverse_mask = 2; lp.out_bf16 = e->us_h; lp.ld_out = 2 * D;
     LAUNCH(14, 2.0 * 3 * (M - S) * 2 * 4 * D * D, lstm_launch(lp, s), "blstm");
-    LAUNCH(15, (double)3 * M * 1024 * 2, us_alpha_launch(e->us_h, 3 * M, e->us_out_w, e->us_out_b, e->smooth2, e->noise2, e->us_a2, s), "us_alpha");
+    LAUNCH(15, (double)3 * M * 1024 * 2, us_alpha_launch(e->us_h, 3 * M, e->us_out_w, e->us_out_b, e->smooth2, e->noise2, e->us_a2, s, e->f16), "us_alpha");
     LAUNCH(15, (double)3 * M * 12, us_peak_launch(e->us_a2, b->d_us_off, b->d_us_len, b->d_n_tok, S, (float)((double)c.cif_threshold - 1e-4),
-                                                 e->us_alphas, e->us_peaks, s), "us_peak");
+                                                 b->d_us_alphas, b->d_us_peaks, s), "us_peak");
   }
 
   // ---- SAN-M decoder ----
@@ -878,12 +905,12 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
   cp.out = e->att; cp.ldo = D;
   cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
-  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.online = e->attn_online;
+  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
   auto dec_ffn = [&](const DecLayer& w) -> int {
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln1");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
       CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w1"); }
-    LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s), "dec ln ff");
+    LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s, e->f16), "dec ln ff");
     { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
       CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
     return 0;
@@ -891,9 +918,9 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   for (int l = 0; l < c.n_dec; ++l) {
     const DecLayer& w = e->dec[l];
     { int rc = dec_ffn(w); if (rc) return rc; }
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln2");
-    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s), "dec fsmn");
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec ln3");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln2");
+    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16), "dec fsmn");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln3");
     { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
       CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }
     { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
@@ -908,7 +935,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
       __nv_bfloat16* cat = e->qkv;  // [Lcap, 1024]; the cross k/v it held were consumed by the attention above
       { GemmEpilogue ep; ep.bias = w.out.b; ep.out_bf16 = cat; ep.ld_out_bf16 = 2 * D;
         CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm out"); }
-      LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, e->bias_ln3.g, e->bias_ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "ctx ln3");
+      LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, e->bias_ln3.g, e->bias_ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ctx ln3");
       { GemmEpilogue ep; ep.bias = e->bias_q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
         CKL(gemm(e->hb, D, Lcap, e->bias_q, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm q"); }
       { GemmEpilogue ep; ep.bias = e->bias_kv.b; ep.out_bf16 = e->hw_kv; ep.ld_out_bf16 = 2 * D;
@@ -923,15 +950,22 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
     }
   }
   { int rc = dec_ffn(e->dec3); if (rc) return rc; }
-  LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s), "dec after_norm");
+  LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec after_norm");
   CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
   float* logits_out = e->taps ? e->tap_logits : (e->topk > 0 ? e->full_logits : nullptr);
   { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
     if (logits_out) { ep.out_f32 = logits_out; ep.ld_out_f32 = c.vocab; }
     CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep, 0, 0, 13), "gemm vocab"); }
   LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
-  if (e->topk > 0)
-    LAUNCH(6, Lest * c.vocab * 4 * 2, logprob_topk_launch(logits_out, c.vocab, Ldev, Lcap, e->topk, e->topk_lse, e->topk_lp, e->topk_id, s), "logprob topk");
+  if (e->topk > 0) {
+    if (!b->d_topk_lse) {   // first use on this batch: per-batch result buffers (see b200pf_batch_create)
+      const size_t R = (size_t)c.max_rows;
+      CK(cudaMalloc((void**)&b->d_topk_lse, R * (4 + 2 * 4 * B200PF_MAX_TOPK)), "cudaMalloc(topk)");
+      b->d_topk_lp = b->d_topk_lse + R;
+      b->d_topk_id = (int*)(b->d_topk_lp + R * B200PF_MAX_TOPK);
+    }
+    LAUNCH(6, Lest * c.vocab * 4 * 2, logprob_topk_launch(logits_out, c.vocab, Ldev, Lcap, e->topk, b->d_topk_lse, b->d_topk_lp, b->d_topk_id, s), "logprob topk");
+  }
   b->topk_run = e->topk;
   return 0;
 }
@@ -953,20 +987,20 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
     CK(cudaMemcpyAsync(h_ids, b->d_ids, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H ids");
     CK(cudaMemcpyAsync(h_frame, b->d_tok_frame, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H frames");
     if (e->cfg.timestamp && res->us_alphas && res->us_peaks) {
-      CK(cudaMemcpyAsync(b->h_us, e->us_alphas, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_alphas");
-      CK(cudaMemcpyAsync(b->h_us + R * 3, e->us_peaks, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_peaks");
+      CK(cudaMemcpyAsync(b->h_us, b->d_us_alphas, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_alphas");
+      CK(cudaMemcpyAsync(b->h_us + R * 3, b->d_us_peaks, (size_t)b->rows * 3 * 4, cudaMemcpyDeviceToHost, s), "D2H us_peaks");
     }
   }
   const int tk = b->topk_run;
-  const bool want_topk = tk > 0 && res->topk_logprob && res->topk_ids && b->n_seg > 0;
+  const bool want_topk = tk > 0 && res->topk_logprob && res->topk_ids && b->n_seg > 0 && b->d_topk_lse;
   float* h_lse = nullptr; float* h_lp = nullptr; int* h_tid = nullptr;
   if (want_topk) {
     if (!b->h_topk) CK(cudaMallocHost((void**)&b->h_topk, R * (4 + 2 * 4 * B200PF_MAX_TOPK)), "cudaMallocHost(topk)");
     h_lse = (float*)b->h_topk; h_lp = h_lse + R; h_tid = (int*)(h_lp + R * B200PF_MAX_TOPK);
     // token count is only known on the device: copy the capacity-bounded prefix that can hold tokens (<= rows)
-    CK(cudaMemcpyAsync(h_lse, e->topk_lse, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H lse");
-    CK(cudaMemcpyAsync(h_lp, e->topk_lp, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk lp");
-    CK(cudaMemcpyAsync(h_tid, e->topk_id, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk ids");
+    CK(cudaMemcpyAsync(h_lse, b->d_topk_lse, (size_t)b->rows * 4, cudaMemcpyDeviceToHost, s), "D2H lse");
+    CK(cudaMemcpyAsync(h_lp, b->d_topk_lp, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk lp");
+    CK(cudaMemcpyAsync(h_tid, b->d_topk_id, (size_t)b->rows * tk * 4, cudaMemcpyDeviceToHost, s), "D2H topk ids");
   }
   CK(cudaStreamSynchronize(s), "forward");
   res->topk_k = want_topk ? tk : 0;

@@ -19,6 +19,7 @@ void set_error(const std::string& msg);
 int check_cuda(cudaError_t e, const char* what);  // 0 or B200PF_ERR_CUDA (and sets the error text)
 int num_fbank_frames(int64_t n_samples);  // feature-window.cc:73-87 (snip_edges)
 int num_lfr_frames(int64_t n_samples);    // paraformer.cpp:424
+uint16_t f32_to_h16(float f, int f16);    // host-side round-to-nearest-even to bf16 (0) or saturating IEEE fp16 (1)
 
 struct Linear {
   __nv_bfloat16* w = nullptr;  // [out, in] bf16
@@ -64,7 +65,7 @@ struct b200pf_engine {
   cudaStream_t copy = nullptr;          // host<->device staging of the NEXT batch (b200pf_engine_copy_stream)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 2;
-  int attn_online = 2;
+  int f16 = 1;                          // 16-bit operand format of weights and activations: 0 bf16, 1 IEEE fp16 (cfg.precision)
   std::string lang = "zh-cn";
   std::vector<std::string> tokens;
   std::mutex mu;  // one forward at a time per engine (the workspace is shared)
@@ -115,7 +116,7 @@ struct b200pf_engine {
   // config-3 workspace
   __nv_bfloat16* us_gx = nullptr;       // [3R, 4096] bf16  BiLSTM input projection
   __nv_bfloat16* us_h = nullptr;        // [3R, 1024] bf16  BiLSTM output
-  float *us_a2 = nullptr, *us_alphas = nullptr, *us_peaks = nullptr;   // [3R]
+  float* us_a2 = nullptr;               // [3R] alpha2 before the per-segment rescale (results: b200pf_batch::d_us_*)
   __nv_bfloat16* hw_kv = nullptr;       // [max_hotwords, 1024] bf16  bias_decoder k/v of the hotword embeddings
   // per-category CUDA-event timing of the launches (option "profile")
   int profile = 0;
@@ -131,10 +132,7 @@ struct b200pf_engine {
   float* tap_logits = nullptr;  // [R, vocab]
   // pruned posteriors (option "logprob_topk" = k)
   int topk = 0;
-  float* full_logits = nullptr;   // [R, vocab] fp32, only allocated when topk > 0 (shared with tap_logits when taps are on)
-  float* topk_lse = nullptr;      // [R]
-  float* topk_lp = nullptr;       // [R, 32]
-  int* topk_id = nullptr;         // [R, 32]
+  float* full_logits = nullptr;   // [R, vocab] fp32, only allocated when topk > 0 (scratch of one run; results: b200pf_batch::d_topk_*)
 };
 
 struct b200pf_batch {
@@ -167,7 +165,12 @@ struct b200pf_batch {
   uint8_t* h_res = nullptr;   // pinned: n_tok[S] tok_off[S+1] ids[R] tok_frame[R]
   float* h_us = nullptr;      // pinned: us_alphas[3R] us_peaks[3R] (timestamp models)
   uint8_t* h_topk = nullptr;  // pinned: lse[R] lp[R*32] ids[R*32], allocated on first use
-  __nv_bfloat16* d_hw = nullptr;  // [max_hotwords, 512] bf16 hotword embeddings of this batch (contextual models)
+  float* d_us_alphas = nullptr;   // [3R] timestamp models: us_alphas / us_cif_peak of THIS batch (one allocation)
+  float* d_us_peaks = nullptr;    // [3R]
+  float* d_topk_lse = nullptr;    // [R]      pruned posteriors of THIS batch (one allocation, made on the first run that asks)
+  float* d_topk_lp = nullptr;     // [R, 32]
+  int* d_topk_id = nullptr;       // [R, 32]
+  __nv_bfloat16* d_hw = nullptr;  // [max_hotwords, 512] 16-bit hotword embeddings of this batch (contextual models)
   int n_hw = 0;
   int topk_run = 0;   // k the last run produced pruned posteriors with
   // staged state

@@ -1,3 +1,5 @@
+// EXPERIMENT, not compiled into libb200pf.so (round 1 measured it slower than LayerNorm + GEMM as two kernels, DESIGN.md 3a').
+// It needs `gemm_ln_bf16_tcgen05` declared in gemm.cuh and a b200pf_op_gemm_ln entry point to be built again.
 // EXPERIMENT - correct (tests/test_gpu_parity.py::test_gemm_with_fused_layernorm) but NOT on the product path: measured
 // 234 us (QKV, 61 k rows) / 262 us (FFN1) against 84 + 27 us / 108 + 27 us for the LayerNorm kernel followed by the plain
 // GEMM (tools/bench_gemm_ln.py).  Two warps per CTA cannot keep enough loads in flight to pull a 256 KB fp32 tile in the

@@ -281,13 +281,13 @@ bool fbank_tables_host(std::vector<float>* window_o, std::vector<double>* tw_o, 
 int fbank_launch(const void* pcm, int is_f32, const int64_t* sample_off, const int* fb_off, int n_seg,
                  int n_frames_total, const FrontendTables& t, float* fb, cudaStream_t s) {
   if (n_frames_total <= 0) return 0;
-  static bool attr_set[64] = {};
-  if (first_use_on_device(attr_set)) {
-    cudaError_t e1 = cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
-    cudaError_t e2 = cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
-    if (e1 != cudaSuccess) return (int)e1;
-    if (e2 != cudaSuccess) return (int)e2;
-  }
+  static PerDeviceOnce once;
+  const int rc = once_per_device(once, [] {
+    cudaError_t err = cudaFuncSetAttribute(fbank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(fbank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FbSmem));
+    return (int)err;
+  });
+  if (rc) return rc;
   int blocks = (n_frames_total + FB_FRAMES - 1) / FB_FRAMES;
   const int cap = 148 * 2 * 8;
   if (blocks > cap) blocks = cap;

@@ -47,7 +47,8 @@ struct KArgs {
 //   2  bias (+ReLU) (+bf16 addend) -> fp32 through TMA; when the residual is the output buffer itself (x += ..., every
 //      out-projection and FFN2) the tile leaves as a TMA REDUCE-ADD, so the SMs never load the residual stream: the
 //      read-modify-write of x happens in L2.
-template <int EPI>
+// F16: the 16-bit operands and outputs are IEEE fp16 instead of bf16 (engine precision 1, see ptx.cuh pack_h2).
+template <int EPI, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, KArgs a) {
@@ -129,7 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_h16(F16, 2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -212,8 +213,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
               }
               if (e.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-              pk[hh * 16 + 2 * g] = pack_bf16x2(v0, v1);
-              pk[hh * 16 + 2 * g + 1] = pack_bf16x2(v2, v3);
+              pk[hh * 16 + 2 * g] = pack_h2<F16>(v0, v1);
+              pk[hh * 16 + 2 * g + 1] = pack_h2<F16>(v2, v3);
             }
           }
           if (c64 == 0) {  // the second half's TMEM loads fly while this half is stored
@@ -296,8 +297,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (e.add_bf16) {
               const uint4 aa = add[c * 4 + (g >> 1)];
               const uint32_t w0 = (g & 1) ? aa.z : aa.x, w1 = (g & 1) ? aa.w : aa.y;
-              v0 += __uint_as_float(w0 << 16); v1 += __uint_as_float(w0 & 0xffff0000u);
-              v2 += __uint_as_float(w1 << 16); v3 += __uint_as_float(w1 & 0xffff0000u);
+              const float2 a0 = unpack_h2<F16>(w0), a1 = unpack_h2<F16>(w1);
+              v0 += a0.x; v1 += a0.y; v2 += a1.x; v3 += a1.y;
             }
             v[4 * g] = v0; v[4 * g + 1] = v1; v[4 * g + 2] = v2; v[4 * g + 3] = v3;
           }
@@ -408,9 +409,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (e.add_bf16) {
             const uint32_t w0 = (g & 1) ? add[g >> 1].z : add[g >> 1].x;
             const uint32_t w1 = (g & 1) ? add[g >> 1].w : add[g >> 1].y;
-            const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&w0);
-            const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&w1);
-            v0 += __low2float(p0); v1 += __high2float(p0); v2 += __low2float(p1); v3 += __high2float(p1);
+            const float2 a0 = unpack_h2<F16>(w0), a1 = unpack_h2<F16>(w1);
+            v0 += a0.x; v1 += a0.y; v2 += a1.x; v3 += a1.y;
           }
           if (e.res_f32) {
             v0 += res[g].x; v1 += res[g].y; v2 += res[g].z; v3 += res[g].w;
@@ -442,8 +442,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.out_bf16) {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            sts128(my_row + g * 16, pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
-                   pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+            sts128(my_row + g * 16, pack_h2<F16>(v[8 * g], v[8 * g + 1]), pack_h2<F16>(v[8 * g + 2], v[8 * g + 3]),
+                   pack_h2<F16>(v[8 * g + 4], v[8 * g + 5]), pack_h2<F16>(v[8 * g + 6], v[8 * g + 7]));
           warp_sync_smem();
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -519,18 +519,18 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if ((p.N & 3) || (p.lda & 7) || (p.ldw & 7)) return (int)cudaErrorInvalidValue;
   if (e.out_bf16 && ((p.N & 7) || (e.ld_out_bf16 & 7))) return (int)cudaErrorInvalidValue;
   if (e.add_bf16 && ((p.N & 7) || (e.ld_add & 7))) return (int)cudaErrorInvalidValue;
-  static bool attr_set[64] = {};
-  if (first_use_on_device(attr_set)) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err != cudaSuccess) return (int)err;
-  }
+  static PerDeviceOnce once;
+  int rc = once_per_device(once, [] {
+    cudaError_t err = cudaSuccess;
+    auto set = [&](auto kernel) { if (err == cudaSuccess) err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); };
+    set(gemm_tcgen05_kernel<0, false>); set(gemm_tcgen05_kernel<1, false>); set(gemm_tcgen05_kernel<2, false>);
+    set(gemm_tcgen05_kernel<0, true>); set(gemm_tcgen05_kernel<1, true>); set(gemm_tcgen05_kernel<2, true>);
+    return (int)err;
+  });
+  if (rc) return rc;
   CUtensorMap tmA, tmB;
   const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;
-  int rc = make_tmap_bf16_sw128(&tmA, p.A, (uint64_t)(p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
+  rc = make_tmap_bf16_sw128(&tmA, p.A, (uint64_t)(p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
   if (rc) return rc;
   rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
@@ -556,9 +556,15 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
-  if (fast) return launch_kernel(gemm_tcgen05_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
-  if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
-  return launch_kernel(gemm_tcgen05_kernel<0>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, tmC, a);
+  const dim3 g(grid), b(kThreads);
+  if (p.f16) {
+    if (fast) return launch_kernel(gemm_tcgen05_kernel<1, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+    if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+    return launch_kernel(gemm_tcgen05_kernel<0, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+  }
+  if (fast) return launch_kernel(gemm_tcgen05_kernel<1, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+  if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+  return launch_kernel(gemm_tcgen05_kernel<0, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
 }
 
 }  // namespace pf

@@ -39,15 +39,11 @@ struct GemmProblem {
   // (p + a_row_shift0).  a_k_wrap = 0 -> plain GEMM.
   int a_k_wrap = 0;
   int a_row_shift0 = 0;
+  int f16 = 0;                       // 0: A, W, the 16-bit output and addend are bf16; 1: IEEE fp16 (same storage type in the signatures)
 };
 
 // Returns cudaError_t as int.  `num_sms` caps the persistent grid.
 int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, cudaStream_t stream);
-
-// LayerNorm fused into its consumer GEMM (gemm_ln.cu): out[M,N] = bf16(act(LN(x)[M,512] W[N,512]^T + bias)), x fp32.
-// N % 256 == 0.  Replaces layernorm_launch + gemm_bf16_tcgen05 for the encoder's LN1 -> QKV and LN2 -> FFN1.
-int gemm_ln_bf16_tcgen05(const float* x, int ldx, int M, const float* gamma, const float* beta, float eps, const __nv_bfloat16* W, int N,
-                         const float* bias, int relu, __nv_bfloat16* out, int ld_out, int num_sms, cudaStream_t stream);
 
 // 2-D bf16 row-major tensor map with 128-byte swizzle, box = [box_rows x 64 elements].
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,

@@ -9,6 +9,9 @@
 
 namespace pf {
 
+// 16-bit operand storage: every `__nv_bfloat16*` below is 2-byte storage whose FORMAT is chosen by the trailing `f16` argument
+// (0 = bf16, 1 = IEEE fp16: the engine's precision 1, see ptx.cuh pack_h2); "bf16" in the parameter names is historical.
+//
 // Packed row layout shared by all kernels: segment i owns rows [row_off[i], row_off[i] + T_i) followed
 // by ONE gap row (zero features; it doubles as the CIF tail frame, tail_threshold 0.45).
 // row_info[r] = {t, T}: frame index inside its segment and the segment's frame count; t = -1 on gap rows.
@@ -45,14 +48,14 @@ int lfr_cmvn_posenc_launch(const float* fb, const int* fb_off, const int* row_se
 //     fp32.  zero_gap: rows with row_info.t < 0 are written as zeros.  rows_dev (optional) overrides rows.
 int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_dev, int D, const float* gamma,
                      const float* beta, float eps, __nv_bfloat16* out_bf16, float* out_f32, const int2* row_info,
-                     int zero_gap, cudaStream_t s);
+                     int zero_gap, cudaStream_t s, int f16 = 0);
 
 // K6  FSMN memory block: depthwise conv1d k=11 (zero padded at SEGMENT edges) + identity.
 //     mode 0 (encoder): out_bf16[r][c] = conv(v)[r][c] + v[r][c]
 //     mode 1 (decoder): y_f32[r][c]   += conv(x)[r][c] + x[r][c]
 //     in: bf16 [rows][ld_in] starting at column col0; w_t: [11][512] fp32 (tap-major transpose of fsmn_block.weight).
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
-                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s);
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16 = 0);
 
 // K7  alpha = sigmoid(h . w + b) on frame rows, tail_threshold on gap rows (CifPredictorV2).
 int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,
@@ -96,6 +99,7 @@ struct LstmParams {
   float* out_f32 = nullptr;            // same layout, fp32                                             (optional)
   int ld_out_f32 = 0;
   int dbg = 0;                         // micro-benchmark ablations only (B200PF_LSTM_DBG); 0 in the product
+  int f16 = 0;                         // gx, whh and out_bf16 are IEEE fp16 instead of bf16
 };
 int lstm_launch(const LstmParams& p, cudaStream_t s);
 int lstm_max_active_clusters();  // co-resident 16-CTA clusters on the current device (diagnostics)
@@ -103,7 +107,7 @@ int lstm_max_active_clusters();  // co-resident 16-CTA clusters on the current d
 // K13 timestamp head tail (CifPredictorV3.get_upsample_timestmap): alpha2 = relu(sigmoid(h . w + b) * smooth - noise)
 //     over the BiLSTM output h [rows, 1024] bf16 ...
 int us_alpha_launch(const __nv_bfloat16* h, int rows, const float* w, const float* b, float smooth, float noise, float* alpha,
-                    cudaStream_t s);
+                    cudaStream_t s, int f16 = 0);
 //     ... then per segment: us_alphas = alpha2 * token_num / sum(alpha2); us_cif_peak = cif_wo_hidden(us_alphas, threshold)
 //     (the arrays TimestampOnnx consumes, src/util.cpp:838-870).
 int us_peak_launch(const float* alpha2, const int* seq_off, const int* seq_len, const int* n_tok, int n_seg, float threshold,
@@ -116,7 +120,8 @@ int embed_gather_launch(const __nv_bfloat16* table, int vocab, const int* ids, i
 //     by (value descending, index ascending).  logits [cap, V] fp32; outputs lse [cap], lp / ids [cap, k].
 int logprob_topk_launch(const float* logits, int V, const int* n_dev, int cap, int k, float* lse, float* lp, int* ids, cudaStream_t s);
 
-// fp32 -> bf16 conversion (weight upload)
-int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s);
+// fp32 <-> 16-bit storage conversion (weight upload, test taps)
+int f32_to_bf16_launch(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t s, int f16 = 0);
+int h16_to_f32_launch(const __nv_bfloat16* in, float* out, int64_t n, cudaStream_t s, int f16 = 0);
 
 }  // namespace pf

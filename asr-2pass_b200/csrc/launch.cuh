@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace pf {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -18,13 +21,24 @@ inline bool pdl_enabled() {
 }
 
 // cudaFuncSetAttribute applies to the CURRENT device only: with one engine per GPU inside one process (MultiGpuParaformer)
-// every device needs its own call.  `flags` is a per-call-site static array; returns true the first time on each device.
-inline bool first_use_on_device(bool (&flags)[64]) {
+// every device needs its own call, and two host threads may reach their first launch on one device at the same time (the VAD
+// engine under its own lock next to the acoustic model).  `once` is a per-call-site static; `init` runs exactly once per device,
+// under a lock, and the device is only marked done after it succeeded -- later launches take the lock-free path.
+struct PerDeviceOnce {
+  std::mutex mu;
+  std::atomic<bool> done[64];
+  PerDeviceOnce() { for (auto& d : done) d.store(false); }
+};
+template <class F>
+inline int once_per_device(PerDeviceOnce& once, F&& init) {
   int d = 0;
-  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
-  if (flags[d]) return false;
-  flags[d] = true;
-  return true;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return init();
+  if (once.done[d].load(std::memory_order_acquire)) return 0;
+  std::lock_guard<std::mutex> lock(once.mu);
+  if (once.done[d].load(std::memory_order_relaxed)) return 0;
+  const int rc = init();
+  if (rc == 0) once.done[d].store(true, std::memory_order_release);
+  return rc;
 }
 
 template <typename... KArgs, typename... Args>

@@ -39,10 +39,16 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+template <bool F16>
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
@@ -57,6 +63,7 @@ __device__ __forceinline__ void st_cluster_128(uint32_t addr, uint4 v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+template <bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_kernel(LstmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -158,14 +165,14 @@ lstm_kernel(LstmParams p) {
         ldmatrix_x4(blk + n0 * 64 + ((ch ^ ((n0 >> 1) & 3)) << 4), b01);
         ldmatrix_x4(blk + n1 * 64 + ((ch ^ ((n1 >> 1) & 3)) << 4), b23);
       }
-      mma_bf16_16816(acc[0][0], a0, b01[0], b01[1]);
-      mma_bf16_16816(acc[0][1], a0, b01[2], b01[3]);
-      mma_bf16_16816(acc[0][2], a0, b23[0], b23[1]);
-      mma_bf16_16816(acc[0][3], a0, b23[2], b23[3]);
-      mma_bf16_16816(acc[1][0], a1, b01[0], b01[1]);
-      mma_bf16_16816(acc[1][1], a1, b01[2], b01[3]);
-      mma_bf16_16816(acc[1][2], a1, b23[0], b23[1]);
-      mma_bf16_16816(acc[1][3], a1, b23[2], b23[3]);
+      mma_bf16_16816<F16>(acc[0][0], a0, b01[0], b01[1]);
+      mma_bf16_16816<F16>(acc[0][1], a0, b01[2], b01[3]);
+      mma_bf16_16816<F16>(acc[0][2], a0, b23[0], b23[1]);
+      mma_bf16_16816<F16>(acc[0][3], a0, b23[2], b23[3]);
+      mma_bf16_16816<F16>(acc[1][0], a1, b01[0], b01[1]);
+      mma_bf16_16816<F16>(acc[1][1], a1, b01[2], b01[3]);
+      mma_bf16_16816<F16>(acc[1][2], a1, b23[0], b23[1]);
+      mma_bf16_16816<F16>(acc[1][3], a1, b23[2], b23[3]);
     }
 
     // split-K: hand the two n-tiles the partner warp finalises to it, keep n-tiles {2 kh, 2 kh + 1}
@@ -194,10 +201,10 @@ lstm_kernel(LstmParams p) {
     for (int x = 0; x < 4; ++x) {
       const int jj = x >> 1, c = x & 1;
       const bool act = k < c_len[x];
-      const float gi = (kh ? acc[0][2 + jj][c] : acc[0][jj][c]) + __uint_as_float((uint32_t)gxv[x][0] << 16);
-      const float gf = (kh ? acc[0][2 + jj][2 + c] : acc[0][jj][2 + c]) + __uint_as_float((uint32_t)gxv[x][1] << 16);
-      const float gg = (kh ? acc[1][2 + jj][c] : acc[1][jj][c]) + __uint_as_float((uint32_t)gxv[x][2] << 16);
-      const float go = (kh ? acc[1][2 + jj][2 + c] : acc[1][jj][2 + c]) + __uint_as_float((uint32_t)gxv[x][3] << 16);
+      const float gi = (kh ? acc[0][2 + jj][c] : acc[0][jj][c]) + unpack_h2<F16>((uint32_t)gxv[x][0]).x;
+      const float gf = (kh ? acc[0][2 + jj][2 + c] : acc[0][jj][2 + c]) + unpack_h2<F16>((uint32_t)gxv[x][1]).x;
+      const float gg = (kh ? acc[1][2 + jj][c] : acc[1][jj][c]) + unpack_h2<F16>((uint32_t)gxv[x][2]).x;
+      const float go = (kh ? acc[1][2 + jj][2 + c] : acc[1][jj][2 + c]) + unpack_h2<F16>((uint32_t)gxv[x][3]).x;
       float h = 0.f;
       if (act) {
         c_state[x] = sigmoidf_(gf) * c_state[x] + sigmoidf_(gi) * tanhf_(gg);
@@ -208,8 +215,7 @@ lstm_kernel(LstmParams p) {
         }
       }
       const int sl = 16 * kh + 8 * jj + 2 * q + c;
-      const __nv_bfloat16 hb16 = __float2bfloat16(h);
-      *reinterpret_cast<__nv_bfloat16*>(sH + ((k + 1) & 1) * kHBytes + rank * 2048 + sl * 64 + ((ug ^ ((sl >> 1) & 3)) << 4) + gid * 2) = hb16;
+      *reinterpret_cast<uint16_t*>(sH + ((k + 1) & 1) * kHBytes + rank * 2048 + sl * 64 + ((ug ^ ((sl >> 1) & 3)) << 4) + gid * 2) = pack_h1<F16>(h);
     }
     __syncthreads();
 
@@ -238,183 +244,8 @@ lstm_kernel(LstmParams p) {
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// tcgen05 variant (experiment, not the default: see lstm_launch).  Same cluster-of-16 decomposition, but the per-step slab product runs on the 5th-gen
-// tensor core: D[128 gate rows x 32 sequences] (TMEM, 32 columns) = W slab [128 x 512] x h_{t-1}^T, both operands K-major
-// SWIZZLE_128B tiles in shared memory, 32 tcgen05.mma (M128 N32 K16) per step issued by one thread.  Slab row
-// R = 32 gate + unit, so warp `gate` (TMEM lane quarter `gate`) reads that gate for 32 units x 32 sequences, adds the
-// input projection, applies its non-linearity (tanh for g, sigmoid otherwise) and parks the result in shared memory;
-// after one CTA barrier each thread updates 8 (unit, sequence) cells whose state lives in its registers, writes the
-// new hidden values into its own 64-byte piece of h_t (K-major: K block rank/2, row = sequence), and the CTA pushes
-// that 2 KB piece to its 15 peers with 16-byte st.shared::cluster.  fence.proxy.async + the cluster barrier make the
-// generic-proxy writes visible to the next step's MMAs.
-// ------------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 128;
-constexpr int kTcW = 128 * 1024;        // 8 K blocks x [128 rows x 128 B]
-constexpr int kTcH = 32 * 1024;         // 8 K blocks x [32 rows x 128 B], per buffer
-constexpr int kTcAct = 4 * 32 * 32 * 4; // [gate][seq][unit] fp32
-constexpr int kTcSmem = kTcW + 2 * kTcH + kTcAct + 2 * kGroup * 4 + 64 + 1024 /*align*/;
-
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-lstm_tc_kernel(LstmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sW = smem;
-  uint8_t* sH = smem + kTcW;
-  float* sAct = reinterpret_cast<float*>(smem + kTcW + 2 * kTcH);
-  int* sOff = reinterpret_cast<int*>(smem + kTcW + 2 * kTcH + kTcAct);
-  int* sLen = sOff + kGroup;
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sLen + kGroup);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t rank = cluster_ctarank();
-  const int task = blockIdx.x / kCluster;
-  const int dir = task % p.n_dir, group = task / p.n_dir;
-  const bool rev = (p.reverse_mask >> dir) & 1;
-  const int s0 = group * kGroup;
-
-  if (tid < kGroup) {
-    const int s = s0 + tid;
-    sOff[tid] = s < p.n_seq ? p.seq_off[s] : 0;
-    sLen[tid] = s < p.n_seq ? p.seq_len[s] : 0;
-  }
-  if (tid == 0) {
-    mbar_init(mma_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 32);
-  {
-    // slab row R = 32 gate + unit  <-  W_hh row gate*512 + 32 rank + unit;  K block kb, 16-byte chunk j of row R at
-    // kb*16384 + R*128 + ((j ^ (R & 7)) << 4)
-    const __nv_bfloat16* wsrc = p.whh + (size_t)dir * 2048 * 512;
-    for (int idx = tid; idx < 128 * 64; idx += kTcThreads) {
-      const int R = idx >> 6, c = idx & 63;          // c: 16-byte chunk along K (64 per row)
-      const int grow = (R >> 5) * 512 + (int)rank * 32 + (R & 31);
-      const uint4 v = ldg128_nc(wsrc + (size_t)grow * 512 + c * 8);
-      const int kb = c >> 3, j = c & 7;
-      *reinterpret_cast<uint4*>(sW + kb * 16384 + R * 128 + ((j ^ (R & 7)) << 4)) = v;
-    }
-    for (int idx = tid; idx < 2 * kTcH / 16; idx += kTcThreads) reinterpret_cast<uint4*>(sH)[idx] = make_uint4(0, 0, 0, 0);
-  }
-  asm volatile("fence.proxy.async;" ::: "memory");
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
-  int steps = 0;
-#pragma unroll 1
-  for (int i = 0; i < kGroup; ++i) steps = max(steps, sLen[i]);
-  cluster_sync_all();
-
-  const int gate = warp, unit = lane;                 // activation phase: this thread's TMEM lane
-  const unsigned short* gx = reinterpret_cast<const unsigned short*>(p.gx);
-  const int gcol = dir * 2048 + gate * 512 + (int)rank * 32 + unit;
-  // cell phase: unit = lane, sequences 8 warp .. 8 warp + 7
-  float c_state[8];
-#pragma unroll
-  for (int x = 0; x < 8; ++x) c_state[x] = 0.f;
-  const uint32_t sW_u = smem_u32(sW), sH_u = smem_u32(sH), sAct_u = smem_u32(sAct);
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 32);
-  // this CTA's piece of h: K block rank/2, chunks (rank & 1) * 4 .. + 3 of each sequence row
-  const uint32_t piece_kb = (rank >> 1) * 4096u, piece_j0 = (rank & 1) * 4u;
-
-  // input-projection terms for (gate, unit) x 32 sequences, fetched ONE STEP AHEAD: the scattered 2-byte loads take
-  // longer than a whole step's MMAs, so they must never be waited for inside the step they belong to
-  unsigned short gxv[32];
-  auto load_gx = [&](int kk, unsigned short (&dst)[32]) {
-#pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      const int len = sLen[s];
-      const int t = rev ? len - 1 - kk : kk;
-      dst[s] = (kk < len && !(p.dbg & 1)) ? __ldg(gx + (size_t)(sOff[s] + t) * p.ld_gx + gcol) : (unsigned short)0;
-    }
-  };
-  load_gx(0, gxv);
-  for (int k = 0; k < steps; ++k) {
-    const uint32_t hb = sH_u + (uint32_t)(k & 1) * kTcH;
-    const uint32_t hn = sH_u + (uint32_t)((k + 1) & 1) * kTcH;
-    if (tid == 0 && !(p.dbg & 16)) {
-      tc_fence_after();
-#pragma unroll
-      for (int kb = 0; kb < 8; ++kb) {
-        const uint64_t da = umma_desc_sw128(sW_u + kb * 16384);
-        const uint64_t db = umma_desc_sw128(hb + kb * 4096);
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) umma_bf16(tmem_d, da + 2 * k16, db + 2 * k16, idesc, (kb | k16) != 0 ? 1u : 0u);
-      }
-      umma_commit(mma_bar);
-    }
-    unsigned short gxn[32];
-    load_gx(k + 1, gxn);
-    if (!(p.dbg & 16)) mbar_wait(mma_bar, (uint32_t)(k & 1));
-    tc_fence_after();
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16), r);
-    tmem_ld_wait();
-    tc_fence_before();
-    // tanh(x) = 2 sigmoid(2x) - 1: one code path for all four gates
-    const float ka = gate == 2 ? 2.f : 1.f, kb2 = gate == 2 ? -1.f : 0.f;
-#pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      const float x = __uint_as_float(r[s]) + __uint_as_float((uint32_t)gxv[s] << 16);
-      const float sg = __fdividef(1.0f, 1.0f + __expf(-ka * x));
-      sAct[(gate * 32 + s) * 32 + unit] = fmaf(ka, sg, kb2);
-    }
-#pragma unroll
-    for (int s = 0; s < 32; ++s) gxv[s] = gxn[s];
-    __syncthreads();
-    // cells (unit = lane, sequence 8 warp + x)
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const int s = warp * 8 + x;
-      const int len = sLen[s];
-      float h = 0.f;
-      if (k < len) {
-        const float gi = sAct[(0 * 32 + s) * 32 + lane], gf = sAct[(1 * 32 + s) * 32 + lane];
-        const float gg = sAct[(2 * 32 + s) * 32 + lane], go = sAct[(3 * 32 + s) * 32 + lane];
-        c_state[x] = gf * c_state[x] + gi * gg;
-        h = go * tanhf_(c_state[x]);
-        if (p.out_f32) {
-          const int t = rev ? len - 1 - k : k;
-          p.out_f32[(size_t)(sOff[s] + t) * p.ld_out_f32 + dir * 512 + (int)rank * 32 + lane] = h;
-        }
-      }
-      const uint32_t j = piece_j0 + (uint32_t)(lane >> 3);
-      *reinterpret_cast<__nv_bfloat16*>(sH + ((k + 1) & 1) * kTcH + piece_kb + s * 128 + ((j ^ (uint32_t)(s & 7)) << 4) + (lane & 7) * 2) =
-          __float2bfloat16(h);
-    }
-    __syncthreads();
-    // push this CTA's 2 KB piece (32 sequences x 4 chunks) to the peers; store the step's output rows
-    {
-      const int s = tid >> 2, c = tid & 3;
-      const uint32_t j = piece_j0 + (uint32_t)c;
-      const uint32_t loc = hn + piece_kb + s * 128 + ((j ^ (uint32_t)(s & 7)) << 4);
-      const uint4 v = lds128(loc);
-      if (!(p.dbg & 2)) {
-#pragma unroll
-        for (int d = 0; d < kCluster; ++d)
-          if ((uint32_t)d != rank) st_cluster_128(mapa_u32(loc, (uint32_t)d), v);
-      }
-      const int len = sLen[s];
-      if (p.out_bf16 && k < len) {
-        const int t = rev ? len - 1 - k : k;
-        stg128(p.out_bf16 + (size_t)(sOff[s] + t) * p.ld_out + dir * 512 + (int)rank * 32 + c * 8, v);
-      }
-    }
-    if (!(p.dbg & 4)) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes (local + remote) -> next step's tcgen05.mma
-    if (!(p.dbg & 8)) cluster_sync_all(); else __syncthreads();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_d, 32);
-  }
-}
-
 // alpha2 = relu(sigmoid(h . w + b) * smooth - noise) over [rows, 1024] bf16; one warp per row.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 us_alpha_kernel(const __nv_bfloat16* __restrict__ h, int rows, const float* __restrict__ w, const float* __restrict__ b,
                 float smooth, float noise, float* __restrict__ alpha) {
@@ -433,8 +264,9 @@ us_alpha_kernel(const __nv_bfloat16* __restrict__ h, int rows, const float* __re
     const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s += __uint_as_float(uu[j] << 16) * ww[2 * j];
-      s += __uint_as_float(uu[j] & 0xffff0000u) * ww[2 * j + 1];
+      const float2 hv = unpack_h2<F16>(uu[j]);
+      s += hv.x * ww[2 * j];
+      s += hv.y * ww[2 * j + 1];
     }
   }
 #pragma unroll
@@ -489,29 +321,20 @@ embed_gather_kernel(const __nv_bfloat16* __restrict__ table, int vocab, const in
 
 }  // namespace
 
-int lstm_launch(const LstmParams& p, cudaStream_t s) {
-  if (p.n_seq <= 0) return 0;
-  if (p.n_dir < 1 || p.n_dir > 2 || (p.ld_gx & 1) || (p.out_bf16 && (p.ld_out & 7))) return (int)cudaErrorInvalidValue;
-  // Product = the mma.sync kernel (5.3-5.5 us per step).  The tcgen05 variant is kept for comparison (B200PF_LSTM_TC=1):
-  // measured 6.5 us per step, of which 2.5 us activation / cell / CTA barriers, 1.1 us the 32 tiny-N MMAs, 1.1 us the DSMEM
-  // broadcast (15 x 2 KB per CTA and step) and the rest cluster-barrier latency (tools/bench_lstm.py, B200PF_LSTM_DBG).
-  static const bool use_mma_sync = getenv("B200PF_LSTM_TC") == nullptr;
-  cudaError_t err;
-  if (use_mma_sync) {
-    err = cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(lstm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  } else {
-    err = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-    if (err != cudaSuccess) return (int)err;
-    err = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  }
-  if (err != cudaSuccess) return (int)err;
+template <bool F16>
+static int lstm_launch_fmt(const LstmParams& p, cudaStream_t s) {
+  static PerDeviceOnce once;
+  const int rc = once_per_device(once, [] {
+    cudaError_t err = cudaFuncSetAttribute(lstm_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(lstm_kernel<F16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    return (int)err;
+  });
+  if (rc) return rc;
   const int groups = (p.n_seq + kGroup - 1) / kGroup;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * p.n_dir * kCluster));
-  cfg.blockDim = dim3(use_mma_sync ? kThreads : kTcThreads);
-  cfg.dynamicSmemBytes = use_mma_sync ? kSmem : kTcSmem;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -520,34 +343,39 @@ int lstm_launch(const LstmParams& p, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (use_mma_sync) return (int)cudaLaunchKernelEx(&cfg, lstm_kernel, p);
-  LstmParams q = p;
-  static const int dbg = getenv("B200PF_LSTM_DBG") ? atoi(getenv("B200PF_LSTM_DBG")) : 0;
-  q.dbg = dbg;
-  return (int)cudaLaunchKernelEx(&cfg, lstm_tc_kernel, q);
+  return (int)cudaLaunchKernelEx(&cfg, lstm_kernel<F16>, p);
+}
+
+// The mma.sync kernel is the product (5.3-5.5 us per step).  A tcgen05 variant of the step was measured slower in round 1
+// (6.5 us; csrc/experiments/lstm_tc_kernel.cuh, not built).
+int lstm_launch(const LstmParams& p, cudaStream_t s) {
+  if (p.n_seq <= 0) return 0;
+  if (p.n_dir < 1 || p.n_dir > 2 || (p.ld_gx & 1) || (p.out_bf16 && (p.ld_out & 7))) return (int)cudaErrorInvalidValue;
+  return p.f16 ? lstm_launch_fmt<true>(p, s) : lstm_launch_fmt<false>(p, s);
 }
 
 int lstm_max_active_clusters() {
-  cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
-  cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaFuncSetAttribute(lstm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaFuncSetAttribute(lstm_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kCluster * 64);
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
 }
 
 int us_alpha_launch(const __nv_bfloat16* h, int rows, const float* w, const float* b, float smooth, float noise, float* alpha,
-                    cudaStream_t s) {
+                    cudaStream_t s, int f16) {
   if (rows <= 0) return 0;
-  return launch_kernel(us_alpha_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, h, rows, w, b, smooth, noise, alpha);
+  if (f16) return launch_kernel(us_alpha_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, s, h, rows, w, b, smooth, noise, alpha);
+  return launch_kernel(us_alpha_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, s, h, rows, w, b, smooth, noise, alpha);
 }
 
 int us_peak_launch(const float* alpha2, const int* seq_off, const int* seq_len, const int* n_tok, int n_seg, float threshold,

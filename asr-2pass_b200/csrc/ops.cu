@@ -1,6 +1,9 @@
 // Single-operator entry points of include/b200pf.h (b200pf_op_*): fp32 host buffers in and out, the product
 // kernels in the middle.  They exist so the GPU parity tests can check every kernel against the CPU oracle
 // in isolation; the serving path never calls them.
+#include <cuda_fp16.h>
+
+#include <algorithm>
 #include <memory>
 #include <vector>
 
@@ -16,6 +19,9 @@ struct DevBuf {
   int alloc(size_t bytes) { return check_cuda(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc"); }
   template <class T> T* as() { return (T*)p; }
 };
+
+// 16-bit operand format the single-operator entry points run in (b200pf_op_set_precision); test infrastructure only
+int g_op_f16 = 1;
 
 int select_device(int device) {
   int n = 0;
@@ -36,7 +42,7 @@ int up_bf16(const float* h, size_t n, DevBuf* tmp, DevBuf* out) {
   int rc = tmp->alloc(n * 4); if (rc) return rc;
   rc = out->alloc(n * 2); if (rc) return rc;
   rc = check_cuda(cudaMemcpy(tmp->p, h, n * 4, cudaMemcpyHostToDevice), "H2D"); if (rc) return rc;
-  rc = f32_to_bf16_launch(tmp->as<float>(), out->as<__nv_bfloat16>(), (int64_t)n, 0);
+  rc = f32_to_bf16_launch(tmp->as<float>(), out->as<__nv_bfloat16>(), (int64_t)n, 0, g_op_f16);
   return rc ? check_cuda((cudaError_t)rc, "f32_to_bf16") : 0;
 }
 int up_f32(const float* h, size_t n, DevBuf* out) {
@@ -49,18 +55,18 @@ int up_raw(const T* h, size_t n, DevBuf* out) {
   return check_cuda(cudaMemcpy(out->p, h, n * sizeof(T), cudaMemcpyHostToDevice), "H2D");
 }
 
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* in, float* out, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __bfloat162float(in[i]);
-}
+// 16-bit results back to fp32 in the format the ops run in
+void widen(const __nv_bfloat16* in, float* out, int64_t n) { h16_to_f32_launch(in, out, n, 0, g_op_f16); }
 
 // pseudo-random bf16 in about [-1, 1): the micro-benchmark must toggle the tensor-core datapath like real activations do
 // (constant operands draw far less power and flatter the clock, hence the TFLOP/s)
-__global__ void fill_random_bf16_kernel(__nv_bfloat16* out, int64_t n, uint32_t seed) {
+__global__ void fill_random_h16_kernel(__nv_bfloat16* out, int64_t n, uint32_t seed, int f16) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint32_t x = (uint32_t)i * 2654435761u + seed;
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    out[i] = __float2bfloat16(((float)(x >> 8) * (1.0f / 8388608.0f)) - 1.0f);
+    const float v = ((float)(x >> 8) * (1.0f / 8388608.0f)) - 1.0f;
+    if (f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(v);
+    else out[i] = __float2bfloat16(v);
   }
 }
 
@@ -74,6 +80,12 @@ int sm_count() { int n = 148, d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&
 
 extern "C" {
 
+int b200pf_op_set_precision(int precision) {
+  if (precision != B200PF_PREC_BF16 && precision != B200PF_PREC_FP16) { set_error("precision must be 0 (bf16) or 1 (fp16)"); return B200PF_ERR_INVALID; }
+  g_op_f16 = precision == B200PF_PREC_FP16 ? 1 : 0;
+  return 0;
+}
+
 int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
                    int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out) {
   RC(select_device(device));
@@ -82,6 +94,7 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   RC(up_bf16(A, (size_t)M * K, &ta, &dA));
   RC(up_bf16(W, (size_t)N * K, &tw, &dW));
   GemmProblem p;
+  p.f16 = g_op_f16;
   p.A = dA.as<__nv_bfloat16>(); p.lda = K; p.rows_a = M; p.W = dW.as<__nv_bfloat16>(); p.ldw = K; p.M = M; p.N = N; p.K = K;
   GemmEpilogue e;
   if (bias) { RC(up_f32(bias, N, &dBias)); e.bias = dBias.as<float>(); }
@@ -104,7 +117,7 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   }
   int rc = gemm_bf16_tcgen05(p, e, sm_count(), 0);
   if (rc) return check_cuda((cudaError_t)rc, "gemm launch");
-  if (out_bf16_round) bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)M * N);
+  if (out_bf16_round) widen(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)M * N);
   if (argmax_out) {
     rc = argmax_decode_launch(dAm.as<unsigned long long>(), nullptr, M, dIds.as<int>(), 0);
     if (rc) return check_cuda((cudaError_t)rc, "argmax decode");
@@ -113,41 +126,6 @@ int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias
   RC(check_cuda(cudaMemcpy(out, dOut.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost), "D2H"));
   if (argmax_out) RC(check_cuda(cudaMemcpy(argmax_out, dIds.p, (size_t)M * 4, cudaMemcpyDeviceToHost), "D2H"));
   return 0;
-}
-
-int b200pf_op_gemm_ln(int device, const float* x, const float* gamma, const float* beta, float eps, const float* W, const float* bias,
-                      int M, int N, int relu, int iters, float* out, float* ms_out) {
-  RC(select_device(device));
-  if (N % 256) { set_error("op_gemm_ln: N % 256 required"); return B200PF_ERR_INVALID; }
-  DevBuf dX, dG, dBt, tw, dW, dBias, dOutB, dOut;
-  RC(up_f32(x, (size_t)M * 512, &dX)); RC(up_f32(gamma, 512, &dG)); RC(up_f32(beta, 512, &dBt));
-  RC(up_bf16(W, (size_t)N * 512, &tw, &dW));
-  if (bias) RC(up_f32(bias, N, &dBias));
-  RC(dOutB.alloc((size_t)M * N * 2)); RC(dOut.alloc((size_t)M * N * 4));
-  const int sms = sm_count();
-  int rc = gemm_ln_bf16_tcgen05(dX.as<float>(), 512, M, dG.as<float>(), dBt.as<float>(), eps, dW.as<__nv_bfloat16>(), N,
-                                bias ? dBias.as<float>() : nullptr, relu, dOutB.as<__nv_bfloat16>(), N, sms, 0);
-  if (rc) return check_cuda((cudaError_t)rc, "gemm_ln launch");
-  RC(sync_ok("op_gemm_ln"));
-  if (iters > 0) {
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    cudaEventRecord(a, 0);
-    for (int i = 0; i < iters; ++i) {
-      rc = gemm_ln_bf16_tcgen05(dX.as<float>(), 512, M, dG.as<float>(), dBt.as<float>(), eps, dW.as<__nv_bfloat16>(), N,
-                                bias ? dBias.as<float>() : nullptr, relu, dOutB.as<__nv_bfloat16>(), N, sms, 0);
-      if (rc) return check_cuda((cudaError_t)rc, "gemm_ln launch");
-    }
-    cudaEventRecord(b, 0);
-    RC(sync_ok("op_gemm_ln"));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    if (ms_out) *ms_out = ms / iters;
-  }
-  bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)M * N);
-  RC(sync_ok("op_gemm_ln"));
-  return check_cuda(cudaMemcpy(out, dOut.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost), "D2H");
 }
 
 int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, float* ms_out) {
@@ -159,13 +137,14 @@ int b200pf_op_gemm_bench(int device, int M, int N, int K, int mode, int iters, f
     RC(check_cuda(cudaMemset(dA.p, 0x3c, (size_t)M * K * 2), "memset")); RC(check_cuda(cudaMemset(dW.p, 0x3c, (size_t)N * K * 2), "memset"));
     RC(check_cuda(cudaMemset(dAdd.p, 0x3c, (size_t)M * N * 2), "memset"));
   } else {
-    fill_random_bf16_kernel<<<1024, 256>>>(dA.as<__nv_bfloat16>(), (int64_t)M * K, 1u);
-    fill_random_bf16_kernel<<<1024, 256>>>(dW.as<__nv_bfloat16>(), (int64_t)N * K, 2u);
-    fill_random_bf16_kernel<<<1024, 256>>>(dAdd.as<__nv_bfloat16>(), (int64_t)M * N, 3u);
+    fill_random_h16_kernel<<<1024, 256>>>(dA.as<__nv_bfloat16>(), (int64_t)M * K, 1u, g_op_f16);
+    fill_random_h16_kernel<<<1024, 256>>>(dW.as<__nv_bfloat16>(), (int64_t)N * K, 2u, g_op_f16);
+    fill_random_h16_kernel<<<1024, 256>>>(dAdd.as<__nv_bfloat16>(), (int64_t)M * N, 3u, g_op_f16);
   }
   RC(check_cuda(cudaMemset(dBias.p, 0, (size_t)N * 4), "memset"));
   RC(check_cuda(cudaMemset(dX.p, 0, (size_t)M * N * 4), "memset")); RC(check_cuda(cudaMemset(dAm.p, 0, (size_t)M * 8), "memset"));
   GemmProblem p;
+  p.f16 = g_op_f16;
   p.A = dA.as<__nv_bfloat16>(); p.lda = K; p.rows_a = M; p.W = dW.as<__nv_bfloat16>(); p.ldw = K; p.M = M; p.N = N; p.K = K;
   GemmEpilogue e;
   e.bias = dBias.as<float>();
@@ -197,6 +176,7 @@ int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bi
   RC(up_f32(bias, C, &dB));
   RC(dOut.alloc((size_t)M * C * 4));
   GemmProblem p;
+  p.f16 = g_op_f16;
   p.A = dX.as<__nv_bfloat16>(); p.lda = C; p.rows_a = M; p.W = dW.as<__nv_bfloat16>(); p.ldw = 3 * C; p.M = M; p.N = C; p.K = 3 * C;
   p.a_k_wrap = C; p.a_row_shift0 = -1;
   GemmEpilogue e;
@@ -217,13 +197,13 @@ int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float
   int rc;
   if (in_bf16) {
     RC(up_bf16(x, n, &tx, &dXb));
-    rc = layernorm_launch(dXb.p, 1, rows, nullptr, D, dG.as<float>(), dB.as<float>(), eps, dOb.as<__nv_bfloat16>(), dO.as<float>(), nullptr, 0, 0);
+    rc = layernorm_launch(dXb.p, 1, rows, nullptr, D, dG.as<float>(), dB.as<float>(), eps, dOb.as<__nv_bfloat16>(), dO.as<float>(), nullptr, 0, 0, g_op_f16);
   } else {
     RC(up_f32(x, n, &dX));
-    rc = layernorm_launch(dX.p, 0, rows, nullptr, D, dG.as<float>(), dB.as<float>(), eps, dOb.as<__nv_bfloat16>(), dO.as<float>(), nullptr, 0, 0);
+    rc = layernorm_launch(dX.p, 0, rows, nullptr, D, dG.as<float>(), dB.as<float>(), eps, dOb.as<__nv_bfloat16>(), dO.as<float>(), nullptr, 0, 0, g_op_f16);
   }
   if (rc) return check_cuda((cudaError_t)rc, "layernorm launch");
-  bf16_to_f32_kernel<<<256, 256>>>(dOb.as<__nv_bfloat16>(), dOb32.as<float>(), (int64_t)n);
+  widen(dOb.as<__nv_bfloat16>(), dOb32.as<float>(), (int64_t)n);
   RC(sync_ok("op_layernorm"));
   if (out_f32) RC(check_cuda(cudaMemcpy(out_f32, dO.p, n * 4, cudaMemcpyDeviceToHost), "D2H"));
   if (out_bf16_as_f32) RC(check_cuda(cudaMemcpy(out_bf16_as_f32, dOb32.p, n * 4, cudaMemcpyDeviceToHost), "D2H"));
@@ -252,17 +232,68 @@ int b200pf_op_attention(int device, const float* q, const float* k, const float*
     for (int q0 = 0; q0 < q_len[s]; q0 += 128) work.push_back(AttnWork{s, q0});
   RC(up_raw(work.data(), work.size(), &dWork));
   AttnProblem p;
+  p.f16 = g_op_f16; p.num_sms = sm_count();
   p.q = dQ.as<__nv_bfloat16>(); p.q_rows = q_rows; p.ldq = D; p.q_col0 = 0;
   p.kv = dKV.as<__nv_bfloat16>(); p.kv_rows = kv_rows; p.ldkv = 2 * D; p.k_col0 = 0; p.v_col0 = D;
   p.out = dOutB.as<__nv_bfloat16>(); p.ldo = D;
   p.q_row_off = dqo.as<int>(); p.q_len = dql.as<int>(); p.kv_row_off = dko.as<int>(); p.kv_len = dkl.as<int>();
   p.work = dWork.as<AttnWork>(); p.n_work = (int)work.size(); p.n_heads = n_heads;
-  p.online = impl == 2 ? 0 : (impl == 3 ? 1 : 2);
   int rc = impl == 1 ? attention_check_kernel(p, 0) : attention_tcgen05(p, 0);
   if (rc) return check_cuda((cudaError_t)rc, "attention launch");
-  bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)q_rows * D);
+  widen(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)q_rows * D);
   RC(sync_ok("op_attention"));
   return check_cuda(cudaMemcpy(out, dOut.p, (size_t)q_rows * D * 4, cudaMemcpyDeviceToHost), "D2H");
+}
+
+// Times the attention kernel alone on device-resident random operands in the engine's layouts: segments of seg_T[i] frames
+// (+ one gap row each).  cross = 0: self-attention over a fused [M,1536] QKV buffer; cross = 1: Lq = (T+1)/2 query rows per
+// segment against a [M,1024] K|V buffer.  Work items longest segment first, as the engine orders them.
+int b200pf_op_attention_bench(int device, const int32_t* seg_T, int n_seg, int n_heads, int cross, int impl, int iters, float* ms_out,
+                              double* flops_out) {
+  RC(select_device(device));
+  const int D = n_heads * 128;
+  std::vector<int> koff(n_seg), klen(n_seg), qoff(n_seg), qlen(n_seg);
+  int M = 0, Lq = 0;
+  double fl = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    koff[s] = M; klen[s] = seg_T[s]; M += seg_T[s] + 1;
+    qlen[s] = cross ? (seg_T[s] + 1) / 2 : seg_T[s];
+    qoff[s] = cross ? Lq : koff[s];
+    Lq += qlen[s];
+    fl += 4.0 * qlen[s] * klen[s] * D;
+  }
+  const int q_rows = cross ? Lq : M;
+  const int ldq = cross ? D : 3 * D, ldkv = cross ? 2 * D : 3 * D;
+  DevBuf dQ, dKV, dO, dqo, dql, dko, dkl, dWork;
+  RC(dKV.alloc((size_t)M * ldkv * 2)); RC(dO.alloc((size_t)q_rows * D * 2));
+  fill_random_h16_kernel<<<1024, 256>>>(dKV.as<__nv_bfloat16>(), (int64_t)M * ldkv, 11u, g_op_f16);
+  if (cross) { RC(dQ.alloc((size_t)q_rows * D * 2)); fill_random_h16_kernel<<<1024, 256>>>(dQ.as<__nv_bfloat16>(), (int64_t)q_rows * D, 12u, g_op_f16); }
+  RC(up_raw(qoff.data(), n_seg, &dqo)); RC(up_raw(qlen.data(), n_seg, &dql)); RC(up_raw(koff.data(), n_seg, &dko)); RC(up_raw(klen.data(), n_seg, &dkl));
+  std::vector<AttnWork> work;
+  for (int s = 0; s < n_seg; ++s)
+    for (int q0 = 0; q0 < seg_T[s]; q0 += 128) work.push_back(AttnWork{s, q0});   // the engine builds the list from T for both uses
+  std::stable_sort(work.begin(), work.end(), [&](const AttnWork& x, const AttnWork& y) { return seg_T[x.seg] > seg_T[y.seg]; });
+  RC(up_raw(work.data(), work.size(), &dWork));
+  AttnProblem p;
+  p.f16 = g_op_f16; p.num_sms = sm_count();
+  p.q = cross ? dQ.as<__nv_bfloat16>() : dKV.as<__nv_bfloat16>(); p.q_rows = q_rows; p.ldq = ldq; p.q_col0 = 0;
+  p.kv = dKV.as<__nv_bfloat16>(); p.kv_rows = M; p.ldkv = ldkv; p.k_col0 = cross ? 0 : D; p.v_col0 = cross ? D : 2 * D;
+  p.out = dO.as<__nv_bfloat16>(); p.ldo = D;
+  p.q_row_off = dqo.as<int>(); p.q_len = dql.as<int>(); p.kv_row_off = dko.as<int>(); p.kv_len = dkl.as<int>();
+  p.work = dWork.as<AttnWork>(); p.n_work = (int)work.size(); p.n_heads = n_heads;
+  for (int i = 0; i < 3; ++i) { int rc = attention_tcgen05(p, 0); if (rc) return check_cuda((cudaError_t)rc, "attention launch"); }
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, 0);
+  for (int i = 0; i < iters; ++i) { int rc = attention_tcgen05(p, 0); if (rc) return check_cuda((cudaError_t)rc, "attention launch"); }
+  cudaEventRecord(b, 0);
+  RC(sync_ok("op_attention_bench"));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (ms_out) *ms_out = ms / iters;
+  if (flops_out) *flops_out = fl;
+  return 0;
 }
 
 int b200pf_op_fsmn(int device, const float* x, const float* w, const int32_t* seg_off, int n_seg, float* out) {
@@ -279,9 +310,9 @@ int b200pf_op_fsmn(int device, const float* x, const float* w, const int32_t* se
   RC(up_f32(wt.data(), wt.size(), &dW));
   RC(up_raw(info.data(), info.size(), &dInfo));
   RC(dOb.alloc((size_t)rows * 512 * 2)); RC(dO.alloc((size_t)rows * 512 * 4));
-  int rc = fsmn_launch(dX.as<__nv_bfloat16>(), 512, 0, dW.as<float>(), dInfo.as<int2>(), rows, nullptr, 0, dOb.as<__nv_bfloat16>(), nullptr, 0);
+  int rc = fsmn_launch(dX.as<__nv_bfloat16>(), 512, 0, dW.as<float>(), dInfo.as<int2>(), rows, nullptr, 0, dOb.as<__nv_bfloat16>(), nullptr, 0, g_op_f16);
   if (rc) return check_cuda((cudaError_t)rc, "fsmn launch");
-  bf16_to_f32_kernel<<<256, 256>>>(dOb.as<__nv_bfloat16>(), dO.as<float>(), (int64_t)rows * 512);
+  widen(dOb.as<__nv_bfloat16>(), dO.as<float>(), (int64_t)rows * 512);
   RC(sync_ok("op_fsmn"));
   return check_cuda(cudaMemcpy(out, dO.p, (size_t)rows * 512 * 4, cudaMemcpyDeviceToHost), "D2H");
 }
@@ -335,19 +366,21 @@ int b200pf_op_lstm(int device, const float* x, int rows, const int32_t* seq_off,
   RC(check_cuda(cudaMemset(dOut.p, 0, (size_t)rows * 512 * n_dir * 4), "memset"));
   RC(check_cuda(cudaMemset(dOutB.p, 0, (size_t)rows * 512 * n_dir * 2), "memset"));
   GemmProblem gp;
+  gp.f16 = g_op_f16;
   gp.A = dX.as<__nv_bfloat16>(); gp.lda = 512; gp.rows_a = rows; gp.W = dWih.as<__nv_bfloat16>(); gp.ldw = 512; gp.M = rows; gp.N = G; gp.K = 512;
   GemmEpilogue ge;
   ge.bias = dB.as<float>(); ge.out_bf16 = dGx.as<__nv_bfloat16>(); ge.ld_out_bf16 = G;
   int rc = gemm_bf16_tcgen05(gp, ge, sm_count(), 0);
   if (rc) return check_cuda((cudaError_t)rc, "lstm input projection");
   LstmParams lp;
+  lp.f16 = g_op_f16;
   lp.gx = dGx.as<__nv_bfloat16>(); lp.ld_gx = G; lp.whh = dWhh.as<__nv_bfloat16>(); lp.seq_off = dOff.as<int>(); lp.seq_len = dLen.as<int>();
   lp.n_seq = n_seq; lp.n_dir = n_dir; lp.reverse_mask = n_dir == 2 ? 2 : 0;
   lp.out_bf16 = dOutB.as<__nv_bfloat16>(); lp.ld_out = 512 * n_dir;
   if (!bf16_out) { lp.out_f32 = dOut.as<float>(); lp.ld_out_f32 = 512 * n_dir; }
   rc = lstm_launch(lp, 0);
   if (rc) return check_cuda((cudaError_t)rc, "lstm launch");
-  if (bf16_out) bf16_to_f32_kernel<<<256, 256>>>(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)rows * 512 * n_dir);
+  if (bf16_out) widen(dOutB.as<__nv_bfloat16>(), dOut.as<float>(), (int64_t)rows * 512 * n_dir);
   RC(sync_ok("op_lstm"));
   return check_cuda(cudaMemcpy(out, dOut.p, (size_t)rows * 512 * n_dir * 4, cudaMemcpyDeviceToHost), "D2H");
 }
@@ -359,12 +392,13 @@ int b200pf_op_lstm_bench(int device, int n_seq, int len, int n_dir, int iters, f
   const int G = 2048 * n_dir;
   DevBuf dGx, dWhh, dOff, dLen, dOut;
   RC(dGx.alloc(rows * G * 2)); RC(dWhh.alloc((size_t)G * 512 * 2)); RC(dOut.alloc(rows * 512 * n_dir * 2));
-  fill_random_bf16_kernel<<<1024, 256>>>(dGx.as<__nv_bfloat16>(), (int64_t)rows * G, 5u);
-  fill_random_bf16_kernel<<<1024, 256>>>(dWhh.as<__nv_bfloat16>(), (int64_t)G * 512, 6u);  // |w| < 1: saturating, still finite
+  fill_random_h16_kernel<<<1024, 256>>>(dGx.as<__nv_bfloat16>(), (int64_t)rows * G, 5u, g_op_f16);
+  fill_random_h16_kernel<<<1024, 256>>>(dWhh.as<__nv_bfloat16>(), (int64_t)G * 512, 6u, g_op_f16);  // |w| < 1: saturating, still finite
   std::vector<int> off(n_seq), ln(n_seq, len);
   for (int i = 0; i < n_seq; ++i) off[i] = i * len;
   RC(up_raw(off.data(), off.size(), &dOff)); RC(up_raw(ln.data(), ln.size(), &dLen));
   LstmParams lp;
+  lp.f16 = g_op_f16;
   lp.gx = dGx.as<__nv_bfloat16>(); lp.ld_gx = G; lp.whh = dWhh.as<__nv_bfloat16>(); lp.seq_off = dOff.as<int>(); lp.seq_len = dLen.as<int>();
   lp.n_seq = n_seq; lp.n_dir = n_dir; lp.reverse_mask = n_dir == 2 ? 2 : 0; lp.out_bf16 = dOut.as<__nv_bfloat16>(); lp.ld_out = 512 * n_dir;
   int rc = lstm_launch(lp, 0);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -164,11 +165,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
-// Instruction descriptor, kind::f16: D=f32 (bit4), A=B=bf16 (bits 7,10), a/b major bits 15/16
-// (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// Instruction descriptor, kind::f16: D=f32 (bit4), A / B format at bits [7,10) / [10,13) (0 = IEEE fp16, 1 = bf16),
+// a/b major bits 15/16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_h16(bool f16, int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+  return umma_idesc_h16(false, M, N, a_mn_major, b_mn_major);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; single thread issues.
@@ -282,6 +286,37 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// The 16-bit operand storage of the forward is bf16 (engine precision 0, north_star's literal format) or IEEE fp16
+// (precision 1: three more mantissa bits at the same tensor-core rate; conversions saturate to +-65504 instead of
+// overflowing to infinity).  F16 selects the format at compile time in every kernel that packs or unpacks operands.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  if constexpr (F16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  } else {
+    return pack_bf16x2(lo, hi);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+  if constexpr (F16) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  } else {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  }
+}
+template <bool F16>
+__device__ __forceinline__ uint16_t pack_h1(float x) {
+  if constexpr (F16) {
+    return (uint16_t)(pack_h2<true>(x, 0.f) & 0xffffu);
+  } else {
+    const __nv_bfloat16 b = __float2bfloat16(x);
+    return *reinterpret_cast<const uint16_t*>(&b);
+  }
 }
 
 }  // namespace pf

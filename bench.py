@@ -242,8 +242,6 @@ def main():
     eng = capi.Engine(tmp, device=local, max_rows=args.max_rows, max_segments=4096)
     if os.environ.get("B200PF_OVERLAP"):
         eng.set_option("overlap", int(os.environ["B200PF_OVERLAP"]))
-    if os.environ.get("B200PF_ATTN_ONLINE"):
-        eng.set_option("attn_online", int(os.environ["B200PF_ATTN_ONLINE"]))
     groups = make_batches(lens, args.max_rows, 4096, capi)
     audio_s = float(lens.sum()) / 16000.0
 

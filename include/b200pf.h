@@ -41,7 +41,15 @@ typedef struct b200pf_config {
   int32_t max_segments;
   int32_t timestamp;       /* 1: the 4-output model (us_alphas, us_cif_peak; paraformer.cpp:549-563) */
   int32_t contextual;      /* 1: the hotword model (bias_embed input, paraformer.cpp:515-531; model_eb, :592-693) */
+  int32_t precision;       /* B200PF_PREC_*: 16-bit operand format of the engine's weights and activations */
 } b200pf_config;
+
+/* Tensor-core operand format (tcgen05 kind::f16 takes either at the same rate; accumulation, residual streams, LayerNorm
+ * statistics, softmax and CIF are fp32 in both).  FP16 is the default: IEEE half has three more mantissa bits than bf16 and
+ * keeps encoder output and logits within the 1e-2 relative tolerance against the fp32 reference graph (bf16 operands give
+ * 2-4 % on the logits); conversions saturate at +-65504.  BF16 is north_star's literal format. */
+#define B200PF_PREC_BF16 0
+#define B200PF_PREC_FP16 1
 
 #define B200PF_MAX_HOTWORDS 4096  /* rows of the hotword embedding a batch may carry (incl. the blank row) */
 #define B200PF_HOTWORD_LEN 10     /* max_hotword_len, paraformer.cpp:600 */
@@ -88,6 +96,9 @@ int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tok
  * tokens.json, model.b200pf}, uploads bf16 weights to `device`, allocates workspace for batches of up to
  * max_rows packed rows / max_segments segments (0 -> defaults 32768 / 4096). */
 int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out);
+/* Same with the operand format chosen explicitly (B200PF_PREC_BF16 / B200PF_PREC_FP16; -1 = the default, which the environment
+ * variable B200PF_PREC=bf16|fp16 overrides). */
+int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out);
 void b200pf_engine_destroy(b200pf_engine* e);
 int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out);
 /* Vocabulary access for the host-side detokeniser (Vocab, onnxruntime/src/vocab.cpp:46-63). */
@@ -96,8 +107,7 @@ const char* b200pf_engine_token(const b200pf_engine* e, int id);
 const char* b200pf_engine_lang(const b200pf_engine* e);
 /* Options: "taps" (0/1) keeps fp32 intermediates of the next runs for b200pf_batch_tap; "overlap" (0 off, 1 FSMN enqueued
  * first, 2 = default: attention enqueued first) runs the FSMN memory block on a low-priority side stream concurrently
- * with the attention kernel; "attn_online" selects the attention kernel (2 = default: single pass, heads pipelined per CTA; 1: single pass, CTA
- * per head; 0: two-pass);
+ * with the attention kernel;
  * "logprob_topk" = k (0..32, default 0) also produces pruned log-softmax posteriors per token (b200pf_result.topk_*);
  * "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
@@ -145,7 +155,10 @@ int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* 
 int b200pf_batch_stage_s16_ptrs(b200pf_batch* b, const int16_t* const* seg, const int64_t* len, int n_seg, void* stream);
 /* Enqueue the whole forward (fbank -> ... -> argmax) for the staged batch.  Asynchronous. */
 int b200pf_batch_run(b200pf_batch* b, void* stream);
-/* Copy results to the host (device->host on `stream`), synchronise, unpack.  */
+/* Copy results to the host (device->host on `stream`), synchronise, unpack.  Every result of a batch -- ids, fire frames,
+ * us_alphas / us_peaks, pruned posteriors -- lives in the batch object, so run(A), run(B), collect(A) on one engine returns
+ * A's own values.  Debug taps (b200pf_batch_tap) are the exception: they read the engine's workspace and are only valid until
+ * the next run on that engine. */
 int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream);
 /* stage + run + collect. */
 int b200pf_forward_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, b200pf_result* res);
@@ -198,16 +211,15 @@ int b200pf_punc_infer_vad(b200pf_punc* p, const int32_t* ids, const int32_t* off
 long long b200pf_punc_launches(const b200pf_punc* p);
 
 /* ---- single-operator entry points (fp32 host buffers in/out; used by the parity tests) -------------- */
+/* 16-bit operand format the b200pf_op_* calls of this process run in (B200PF_PREC_*; default FP16, like the engine).  Wherever
+ * the comments below say "bf16" read "the selected 16-bit format". */
+int b200pf_op_set_precision(int precision);
 /* C = A[M,K] * W[N,K]^T (+bias) (+relu: 1 after bias, 2 after all adds) (+add[M,N] rounded to bf16)
  * (+res[M,N] fp32).  A and W are rounded to bf16 on upload.  out_bf16_round: 1 rounds the result to bf16; 0 = fp32 with the
  * residual applied in place (the TMA epilogues, as in the forward); 2 = fp32 through the general epilogue.
  * argmax_out (optional, [M]) receives the fused greedy argmax (first maximum wins, util.cpp:63-74). */
 int b200pf_op_gemm(int device, const float* A, const float* W, const float* bias, const float* add, const float* res,
                    int M, int N, int K, int relu, int out_bf16_round, float* out, int32_t* argmax_out);
-/* LayerNorm fused into its consumer GEMM: out[M,N] = bf16(act(LN(x[M,512]; gamma, beta, eps) W[N,512]^T + bias)) widened to fp32;
- * N % 256 == 0.  iters > 0 additionally times that many launches (ms_out = milliseconds per launch). */
-int b200pf_op_gemm_ln(int device, const float* x, const float* gamma, const float* beta, float eps, const float* W, const float* bias,
-                      int M, int N, int relu, int iters, float* out, float* ms_out);
 /* Times `iters` back-to-back launches of the GEMM on device-resident dummy operands (CUDA events); mode 0: bias ->
  * bf16, 1: bias+ReLU -> bf16, 2: bias + fp32 residual in place, 3: bias + bf16 addend + fp32 residual in place,
  * 4: bias + fused argmax only.  ms_out = average milliseconds per launch. */
@@ -217,11 +229,16 @@ int b200pf_op_conv3(int device, const float* X, const float* Wr, const float* bi
 int b200pf_op_layernorm(int device, const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
                         int in_bf16, float* out_f32, float* out_bf16_as_f32);
 /* q [sum Tq,H*128], k,v [sum Tk,H*128]; segment s owns rows q_off[s].. and kv_off[s]..; impl 0 = tcgen05
- * kernel (product: single pass, running maximum, all heads pipelined through one CTA), 1 = CUDA-core cross-check,
- * 2 = tcgen05 exact two-pass variant, 3 = tcgen05 single pass with one CTA per head. */
+ * kernel (product: persistent, single pass with a running maximum, all heads of a work item pipelined through one CTA),
+ * 1 = CUDA-core cross-check. */
 int b200pf_op_attention(int device, const float* q, const float* k, const float* v, const int32_t* q_off,
                         const int32_t* q_len, const int32_t* kv_off, const int32_t* kv_len, int n_seg, int n_heads,
                         int64_t q_rows, int64_t kv_rows, int impl, float* out);
+/* Times `iters` launches of the attention kernel on device-resident random operands laid out like the engine's buffers:
+ * segments of seg_T[i] LFR frames; cross = 0 self-attention (fused QKV rows), 1 = decoder cross-attention with (T+1)/2 query
+ * rows per segment.  ms_out = milliseconds per launch, flops_out = 4 * sum(Tq * Tk) * 128 * n_heads. */
+int b200pf_op_attention_bench(int device, const int32_t* seg_T, int n_seg, int n_heads, int cross, int impl, int iters, float* ms_out,
+                              double* flops_out);
 /* depthwise k=11 conv + identity over segments seg_off[n_seg+1]; x [rows,512], w [512,11]. */
 int b200pf_op_fsmn(int device, const float* x, const float* w, const int32_t* seg_off, int n_seg, float* out);
 /* CIF: alphas [sum (T_i+1)] (tail already appended), hidden [sum (T_i+1), 512]; seg_off[n_seg+1] over those rows.

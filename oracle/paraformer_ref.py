@@ -26,10 +26,10 @@ semantics, the 4-output timestamp form, the [10, N, D] hotword output and its ro
 compiled Paraformer::Forward / CompileHotwordEmbedding run with this file as the network behind their sessions
 (oracle/am_ref.py, oracle/fake_ort.cc) and produce the strings the oracle's host restatement predicts (tests/test_am_ref_cpu.py).
 
-`emulate_bf16=True` rounds to bfloat16 exactly where the CUDA path stores bf16 (GEMM operands and the
-bf16 activation buffers), keeping every reduction in fp32.  It is a second oracle used to separate
-"kernel is wrong" from "bf16 rounding moved a value"; the acceptance tolerances are stated against the
-plain fp32 oracle.
+`emulate_bf16=True` (or "bf16" / "fp16") rounds to that 16-bit format exactly where the CUDA path stores
+16-bit values (GEMM operands and the 16-bit activation buffers), keeping every reduction in fp32.  It is a
+second oracle used to separate "kernel is wrong" from "operand rounding moved a value"; the acceptance
+tolerances are stated against the plain fp32 oracle.
 """
 from __future__ import annotations
 
@@ -143,7 +143,15 @@ def param_shapes(cfg: PfConfig):
 
 
 def _rb(x, on):
-    return x.bfloat16().float() if on else x
+    """Round to the CUDA path's 16-bit operand format where `on` says so: False / None = fp32 (no rounding), True / "bf16" =
+    bfloat16, "fp16" = IEEE half saturating at +-65504 like the device's cvt.rn.satfinite."""
+    if not on:
+        return x
+    if on is True or on == "bf16":
+        return x.bfloat16().float()
+    if on == "fp16":
+        return x.clamp(-65504.0, 65504.0).half().float()
+    raise ValueError("unknown emulation mode %r" % (on,))
 
 
 def pos_enc(T: int, depth: int) -> torch.Tensor:

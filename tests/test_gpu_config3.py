@@ -9,7 +9,7 @@ Tolerances:
   * us_alphas vs the fp32 oracle                                     : <= 3e-2 relative to the largest alpha
   * a timestamp peak may move by one upsampled frame (20 ms) where the oracle's running sum is within the
     accumulated alpha deviation of the threshold
-  * logits of the contextual decoder                                 : same 4e-2 as the plain decoder
+  * logits of the contextual decoder                                 : same 1e-2 as the plain decoder
 """
 import os
 
@@ -24,8 +24,9 @@ pytestmark = pytest.mark.gpu
 
 
 def bf(x):
+    """Round to the engine's default 16-bit operand format (IEEE fp16; include/b200pf.h B200PF_PREC_FP16)."""
     import torch
-    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).bfloat16().float().numpy()
+    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).half().float().numpy()
 
 
 def rel(a, b):
@@ -66,7 +67,7 @@ def test_lstm_kernel(capi, gpu, n_dir):
     for o, L in zip(offs, lens):
         covered[o:o + L] = True
         for d in range(n_dir):
-            ref = _oracle_lstm(x[o:o + L], w_ih, w_hh, b_ih, b_hh, d, emu=True)
+            ref = _oracle_lstm(x[o:o + L], w_ih, w_hh, b_ih, b_hh, d, emu="fp16")
             got = out[o:o + L, d * 512:(d + 1) * 512]
             assert np.abs(got - ref).max() <= 2e-2, (L, d, np.abs(got - ref).max())
             ref32 = _oracle_lstm(x[o:o + L], w_ih, w_hh, b_ih, b_hh, d, emu=False)
@@ -121,7 +122,7 @@ def test_hotword_embedding_against_oracle(capi, cfg3):
     rng = np.random.default_rng(0)
     ids, lens = _hotword_ids(rng, 100, cfg3["pc"].vocab)
     got = cfg3["eng"].hotword_embed(ids, lens)
-    ref = R.select_hotword_rows(R.hotword_embed(ids, cfg3["W"], emu=True), lens).numpy()
+    ref = R.select_hotword_rows(R.hotword_embed(ids, cfg3["W"], emu="fp16"), lens).numpy()
     assert got.shape == (101, 512)
     assert np.abs(got - ref).max() <= 2e-2
     ref32 = R.select_hotword_rows(R.hotword_embed(ids, cfg3["W"]), lens).numpy()
@@ -197,11 +198,11 @@ def test_forward_config3_small_model(capi, synth, cfg3):
         assert np.array_equal(ids, [F.find_max(lg[j])[1] for j in range(len(ids))])
         if np.array_equal(fr, fr_o):
             lg_o = o["logits"].numpy()
-            assert rel(lg, lg_o) <= 4e-2
+            assert rel(lg, lg_o) <= 1e-2
             top2 = np.sort(lg_o, axis=1)[:, -2:]
             gap = top2[:, 1] - top2[:, 0]
             for j, (a, c) in enumerate(zip(ids, o["ids"])):
-                assert a == c or gap[j] < 0.15, (i, j, gap[j])
+                assert a == c or gap[j] < 0.06, (i, j, gap[j])
 
 
 def test_config3_against_committed_golden(capi, cfg3):
@@ -222,7 +223,7 @@ def test_config3_against_committed_golden(capi, cfg3):
             assert abs(len(_peaks(res["us_peaks"])) - len(_peaks(c3["us_peaks_%d" % n]))) <= 1
             ids = res["token_ids"]
             bad = [(j, c3["top_gap_%d" % n][j]) for j in range(len(ids)) if ids[j] != c3["ids_%d" % n][j]]
-            assert all(gap < 0.15 for _, gap in bad), bad
+            assert all(gap < 0.06 for _, gap in bad), bad
 
 
 def test_hotwords_change_the_logits_and_batch_invariance(capi, synth, cfg3):

@@ -5,15 +5,17 @@ Tolerances (stated once, used below):
   * integer / index work (CIF fire frames given alphas, token embeddings given alphas, argmax given logits,
     frame counts, batching)                                              : bit exact
   * fbank, LFR+CMVN                                                       : <= 1e-4 absolute (north_star)
-  * GEMM / attention / LayerNorm / FSMN kernels vs a reference fed the SAME bf16-rounded operands : <= 4e-3
-    relative (one bf16 output rounding), fp32-output GEMMs <= 1e-5
-  * encoder output vs the plain fp32 oracle                               : <= 1e-2 relative (north_star, bf16)
-  * logits vs the plain fp32 oracle                                       : <= 4e-2 relative.  bf16 operand
-    rounding ALONE (fp32 arithmetic, CPU) already moves the 16-layer decoder's logits by 1.4-1.8e-2 on
-    these random-init weights (oracle emulate_bf16; DESIGN.md "Precision"), so 1e-2 is not reachable in bf16.
+  * GEMM / attention / LayerNorm / FSMN kernels vs a reference fed the SAME 16-bit-rounded operands : <= 4e-3
+    relative (one 16-bit output rounding), fp32-output GEMMs <= 1e-5.  Every kernel test runs in both operand
+    formats of the engine (fixture `prec`: IEEE fp16 = the default, bf16 = north_star's literal format).
+  * encoder output and logits vs the plain fp32 oracle                    : <= 1e-2 relative (north_star) in the
+    default fp16 operand format.  bf16 operands reach 1e-2 on the encoder output but only 2-4e-2 on the logits
+    (operand rounding alone, in fp32 arithmetic on the CPU, moves them by 1.4-1.8e-2: oracle emulate_bf16);
+    tests/test_gpu_parity_fullsize.py keeps that mode covered.
   * token ids / fire frames vs the fp32 oracle: equal, except where the oracle itself is at a tie:
-    a fire may move by one frame only if the oracle's integrate value is within 2e-2 of the threshold;
-    a token id may differ only if the oracle's top-2 logit gap at that row is < 0.15 (logit std ~0.58).
+    a fire may move by one frame only if the oracle's integrate value is within the accumulated alpha deviation of
+    the threshold; a token id may differ only if the oracle's top-2 logit gap at that row is within twice the
+    logit tolerance.  Mismatch RATES are bounded in tests/test_gpu_parity_fullsize.py.
 """
 import os
 
@@ -29,9 +31,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+_PREC = ["fp16"]   # 16-bit operand format the op_* entry points currently run in (fixture `prec`)
+
+
 def bf(x):
+    """Round to the 16-bit operand format under test (the name is historical: fp16 is the default format, bf16 the other)."""
     import torch
-    return torch.from_numpy(np.ascontiguousarray(x, np.float32)).bfloat16().float().numpy()
+    t = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+    return (t.half() if _PREC[0] == "fp16" else t.bfloat16()).float().numpy()
+
+
+@pytest.fixture(params=["fp16", "bf16"])
+def prec(request, capi):
+    """Every kernel test runs in both operand formats of the engine (include/b200pf.h B200PF_PREC_*)."""
+    capi.op_set_precision(request.param)
+    _PREC[0] = request.param
+    yield request.param
+    capi.op_set_precision("fp16")
+    _PREC[0] = "fp16"
 
 
 def rel(a, b):
@@ -43,7 +60,7 @@ def rel(a, b):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(1, 256, 64), (128, 256, 512), (300, 512, 560), (1000, 1536, 512), (2500, 2048, 512),
                                    (513, 512, 2048), (129, 1024, 512)])
-def test_gemm_tcgen05(capi, gpu, shape):
+def test_gemm_tcgen05(capi, gpu, shape, prec):
     M, N, K = shape
     rng = np.random.default_rng(M + N + K)
     A = rng.standard_normal((M, K)).astype(np.float32)
@@ -61,26 +78,7 @@ def test_gemm_tcgen05(capi, gpu, shape):
     assert rel(capi.op_gemm(A, W, bias=bias, res=res, relu=2, out_bf16=True), bf(np.maximum(ref + bias + res, 0))) <= 4e-3
 
 
-@pytest.mark.parametrize("shape", [(1, 256), (100, 512), (256, 1536), (257, 2048), (1000, 1536), (5000, 2048), (20000, 1536)])
-def test_gemm_with_fused_layernorm(capi, gpu, shape):
-    """LN -> GEMM fused (gemm_ln.cu) against LayerNorm in fp32, rounded to bf16, times bf16 weights."""
-    import torch
-    M, N = shape
-    rng = np.random.default_rng(M + N)
-    x = (rng.standard_normal((M, 512)) * rng.uniform(0.5, 4.0, (M, 1)) + rng.uniform(-2, 2, (M, 1))).astype(np.float32)
-    g = rng.uniform(0.5, 1.5, 512).astype(np.float32)
-    b = rng.uniform(-0.5, 0.5, 512).astype(np.float32)
-    W = (rng.standard_normal((N, 512)) / np.sqrt(512)).astype(np.float32)
-    bias = rng.standard_normal(N).astype(np.float32)
-    ln = torch.nn.functional.layer_norm(torch.from_numpy(x), (512,), torch.from_numpy(g), torch.from_numpy(b), 1e-12).numpy()
-    ref = np.maximum(bf(ln) @ bf(W).T + bias, 0)
-    out, _ = capi.op_gemm_ln(x, g, b, W, bias=bias, relu=1)
-    assert rel(out, bf(ref)) <= 6e-3      # a bf16 rounding of LN(x) that falls the other way moves one product term
-    out2, _ = capi.op_gemm_ln(x, g, b, W)
-    assert rel(out2, bf(bf(ln) @ bf(W).T)) <= 6e-3
-
-
-def test_gemm_vocab_argmax_first_max_wins(capi, gpu):
+def test_gemm_vocab_argmax_first_max_wins(capi, gpu, prec):
     rng = np.random.default_rng(7)
     M, N, K = 257, 8404, 512
     A = rng.standard_normal((M, K)).astype(np.float32)
@@ -95,7 +93,7 @@ def test_gemm_vocab_argmax_first_max_wins(capi, gpu):
     assert not np.any(am == 4000) and not np.any(am == 8403)
 
 
-def test_conv3_as_shifted_gemm(capi, gpu):
+def test_conv3_as_shifted_gemm(capi, gpu, prec):
     import torch
     rng = np.random.default_rng(1)
     lens = [50, 130, 7, 1]
@@ -116,7 +114,7 @@ def test_conv3_as_shifted_gemm(capi, gpu):
 
 
 @pytest.mark.parametrize("D", [512, 560, 2048])
-def test_layernorm(capi, gpu, D):
+def test_layernorm(capi, gpu, D, prec):
     import torch
     rng = np.random.default_rng(D)
     x = (rng.standard_normal((77, D)) * 3 + 1).astype(np.float32)
@@ -145,8 +143,8 @@ def _attn_ref(q, k, v, q_off, q_len, kv_off, kv_len, H=4):
 
 @pytest.mark.parametrize("case", [([33], [33]), ([1], [1]), ([64], [64]), ([65], [65]), ([128], [128]), ([129], [129]), ([167], [167]),
                                   ([200, 1, 64, 129], [200, 1, 64, 129]), ([40, 90], [83, 167]), ([1000], [1000])])
-@pytest.mark.parametrize("impl", [0, 1, 2, 3])
-def test_attention(capi, gpu, case, impl):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention(capi, gpu, case, impl, prec):
     q_lens, kv_lens = case
     rng = np.random.default_rng(sum(q_lens) + 13 * sum(kv_lens))
     q_off = np.concatenate([[0], np.cumsum(q_lens)[:-1]]).astype(np.int32)
@@ -159,10 +157,10 @@ def test_attention(capi, gpu, case, impl):
     assert rel(out, ref) <= 8e-3  # bf16 P (product kernel) + bf16 output rounding
 
 
-@pytest.mark.parametrize("impl", [0, 2, 3])
-def test_attention_large_scores_force_the_running_maximum_to_move(capi, gpu, impl):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_attention_large_scores_force_the_running_maximum_to_move(capi, gpu, impl, prec):
     """Scores grow along the keys (each 64-key block's maximum is far above the previous one), so the single-pass kernel
-    must take its rare path: rescale O and l in TMEM.  Both tcgen05 variants against the fp32 softmax."""
+    must take its rare path: rescale O and l in TMEM.  The tcgen05 kernel and the CUDA-core cross-check against the fp32 softmax."""
     rng = np.random.default_rng(21)
     q_lens, kv_lens = [130, 70, 200], [300, 129, 640]
     q_off = np.concatenate([[0], np.cumsum(q_lens)[:-1]]).astype(np.int32)
@@ -181,7 +179,7 @@ def test_attention_large_scores_force_the_running_maximum_to_move(capi, gpu, imp
     assert rel(out, ref) <= 8e-3
 
 
-def test_fsmn(capi, gpu):
+def test_fsmn(capi, gpu, prec):
     import torch
     rng = np.random.default_rng(4)
     lens = [1, 5, 11, 40, 300]
@@ -258,7 +256,7 @@ def _oracle(model, pcm16):
     return feats, R.forward(feats, model["W"], model["pc"])
 
 
-def _check_segment(b, res, i, model, o, enc_tol=1e-2, logit_tol=4e-2):
+def _check_segment(b, res, i, model, o, enc_tol=1e-2, logit_tol=1e-2):
     T = o["enc"].shape[0]
     assert res["lfr_frames"][i] == T
     enc = b.tap("enc", i)
@@ -297,7 +295,7 @@ def _check_segment(b, res, i, model, o, enc_tol=1e-2, logit_tol=4e-2):
         gap = top2[:, 1] - top2[:, 0]
         for j, (a, c) in enumerate(zip(ids, o["ids"])):
             if a != c and moved == 0:
-                assert gap[j] < 0.15, (i, j, gap[j])
+                assert gap[j] <= 2.0 * logit_tol * np.abs(lg_o).max(), (i, j, gap[j])
         # the fused argmax is exact on the GPU's own logits (first maximum wins)
         assert np.array_equal(ids, [F.find_max(lg[j])[1] for j in range(len(ids))])
 
@@ -329,7 +327,7 @@ def test_small_model_against_committed_golden(capi, small):
         if res["token_counts"][0] == mg["token_num_%d" % n][0]:
             ids = res["token_ids"]
             bad = [(j, mg["top_gap_%d" % n][j]) for j in range(len(ids)) if ids[j] != mg["ids_%d" % n][j]]
-            assert all(gap < 0.15 for _, gap in bad), bad
+            assert all(gap < 0.06 for _, gap in bad), bad
 
 
 def test_batch_invariance_and_input_formats(capi, synth, small):
@@ -385,7 +383,7 @@ def test_forward_full_paraformer_large(capi, synth, gpu, tmp_path_factory):
     for i in range(3):
         _, o = _oracle(model, pcm[offs[i]:offs[i + 1]])
         assert abs(int(res["token_counts"][i]) - o["token_num"]) <= 1
-        _check_segment(b, res, i, model, o, enc_tol=1.2e-2, logit_tol=5e-2)
+        _check_segment(b, res, i, model, o)        # 1e-2 on encoder output and logits (north_star)
     # 591 launches: 2 front end + 50 x 8 encoder + 6 predictor + 16 x 11 decoder + 7 tail
     assert b.launches == 2 + 50 * 8 + 6 + 16 * 11 + 7
     eng.close()

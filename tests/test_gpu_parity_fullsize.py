@@ -1,0 +1,123 @@
+"""Full-size parity (-m gpu): the NAMED architecture (50 + 16 layers, 215.8 M parameters, random init) on segments drawn
+across BASELINE.json configs[1]'s whole length range plus two 60 s segments (configs[4], T = 1000), CUDA path vs the fp32
+oracle (oracle/paraformer_ref.py, run in a process pool: tests/oracle_pool.py).
+
+Acceptance, as north_star states it (tolerances written here, used below):
+  * encoder output and logits: max-abs error relative to the tensor's max-abs <= 1e-2            (ENC_TOL, LOGIT_TOL)
+  * token count: equal, unless the oracle's own sum of alphas is within the accumulated alpha deviation of an integer
+  * CIF fire frames: bit-exact wherever the oracle's integrate value is farther from the threshold than the accumulated alpha
+    deviation; elsewhere a fire may move by one frame.  At most FIRE_RATE of all fires may move.
+  * token ids: bit-exact wherever the oracle's top-1 margin over the GPU's pick exceeds 2 * LOGIT_TOL * max|logit| (the GPU
+    may only pick another id where the two logits tie within the stated tolerance); at most ID_RATE of all tokens may differ.
+The same statistics are printed by bench.py (`parity` object) on its cpu_baseline sample.
+"""
+import numpy as np
+import pytest
+
+from oracle_pool import oracle_forward_many
+
+pytestmark = pytest.mark.gpu
+
+ENC_TOL = 1e-2
+LOGIT_TOL = 1e-2
+ID_RATE = 0.03     # measured: ~1 % of tokens sit at an fp32 tie narrower than the tolerance (random-init logits, top-2 gap median 0.07)
+FIRE_RATE = 0.01
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def compare_segment(o, T, enc, alphas, fires_gpu, ids_gpu, fire_frames_gpu, logits_gpu, stats):
+    """Accumulates parity statistics of one segment into `stats` and asserts the per-segment rules."""
+    assert T == o["T"]
+    stats["enc_rel"] = max(stats["enc_rel"], rel(enc, o["enc"]))
+    al_o = o["alphas"]
+    stats["alpha_abs"] = max(stats["alpha_abs"], float(np.abs(alphas - al_o).max()))
+    drift = np.abs(np.cumsum(alphas.astype(np.float64)) - np.cumsum(al_o.astype(np.float64)))
+    fr_o = np.where(o["fires"] >= 1.0)[0]
+    fr = np.asarray(fire_frames_gpu)
+    stats["segments"] += 1
+    stats["fires"] += len(fr_o)
+    s_o = float(al_o.astype(np.float64).sum())
+    if len(fr) != len(fr_o):
+        # a token more or less: only if the oracle's own total sits within the accumulated deviation of an integer
+        assert abs(len(fr) - len(fr_o)) == 1 and min(s_o - np.floor(s_o), np.ceil(s_o) - s_o) <= drift.max() + 1e-3, (len(fr), len(fr_o), s_o)
+        stats["count_moved"] += 1
+        stats["fires_moved"] += 1
+        return
+    moved = 0
+    for a, c in zip(fr, fr_o):
+        if a != c:
+            lo, hi = min(a, c), max(a, c)
+            margin = min(abs(o["fires"][a] - 1.0), abs(o["fires"][c] - 1.0))
+            assert hi - lo == 1 and margin <= drift[:hi + 1].max() + 1e-3, (a, c, margin, drift[:hi + 1].max())
+            moved += 1
+    stats["fires_moved"] += moved
+    if moved or len(fr) == 0:
+        return          # the decoder saw different token embeddings: ids / logits are not comparable row by row
+    lg_o = o["logits"]
+    stats["tokens"] += len(ids_gpu)
+    stats["logit_rel"] = max(stats["logit_rel"], rel(logits_gpu, lg_o))
+    tol_abs = 2.0 * LOGIT_TOL * float(np.abs(lg_o).max())
+    for j, (a, c) in enumerate(zip(ids_gpu, o["ids"])):
+        if a != c:
+            stats["ids_differ"] += 1
+            assert lg_o[j, c] - lg_o[j, a] <= tol_abs, (j, a, c, float(lg_o[j, c] - lg_o[j, a]), tol_abs)
+    # the fused argmax is exact on the GPU's own logits (first maximum wins, util.cpp:63-74)
+    assert np.array_equal(ids_gpu, logits_gpu.argmax(1))
+
+
+def new_stats():
+    return dict(segments=0, tokens=0, fires=0, ids_differ=0, fires_moved=0, count_moved=0, enc_rel=0.0, logit_rel=0.0, alpha_abs=0.0)
+
+
+def test_full_size_model_on_configs1_sample_and_max_length_segments(capi, synth, gpu, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("fullparity"))
+    synth.write_synthetic_model_dir(d, None, seed=0)
+    lens_all = synth.segment_lengths(1024)
+    pick = np.argsort(lens_all, kind="stable")[np.linspace(0, 1023, 64).astype(int)]     # 64 segments across the 2-20 s range
+    lens = [int(lens_all[i]) for i in pick] + [960000, 960000]                             # + 2 x 60 s: T = 1000 (configs[4])
+    segs = [synth.make_audio(n, 5000 + k) for k, n in enumerate(lens)]
+    oracle = oracle_forward_many(segs, None, seed=0)
+    eng = capi.Engine(d, max_rows=16384, max_segments=128)
+    assert eng.cfg.precision == capi.PREC_FP16        # the default operand format is the one that meets the stated tolerance
+    eng.set_option("taps", 1)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    b = capi.Batch(eng, int(offs[-1]) + 64)
+    res = b.forward_s16(np.concatenate(segs), offs)
+    stats = new_stats()
+    for i, o in enumerate(oracle):
+        s, e = res["token_offsets"][i], res["token_offsets"][i + 1]
+        compare_segment(o, int(res["lfr_frames"][i]), b.tap("enc", i), b.tap("alphas", i), b.tap("fires", i), res["token_ids"][s:e],
+                        res["fire_frames"][s:e], b.tap("logits", i), stats)
+    print("full-size parity:", stats)
+    assert stats["segments"] == 66 and stats["tokens"] > 3000
+    assert stats["enc_rel"] <= ENC_TOL and stats["logit_rel"] <= LOGIT_TOL
+    assert stats["ids_differ"] <= ID_RATE * stats["tokens"]
+    assert stats["fires_moved"] <= max(2, FIRE_RATE * stats["fires"])
+    b.close()
+    eng.close()
+
+
+def test_bf16_operand_mode_is_the_looser_one(capi, synth, gpu, tmp_path_factory):
+    """Precision 0 (north_star's literal bf16 operands) stays available and works, but only reaches 2-4 % on the logits --
+    the reason it is not the default."""
+    d = str(tmp_path_factory.mktemp("bf16mode"))
+    synth.write_synthetic_model_dir(d, None, seed=0)
+    lens = [160000, 52800]
+    segs = [synth.make_audio(n, 1234 + k) for k, n in enumerate(lens)]
+    oracle = oracle_forward_many(segs, None, seed=0, procs=2)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    errs = {}
+    for prec in ("bf16", "fp16"):
+        eng = capi.Engine(d, max_rows=2048, max_segments=16, prec=prec)
+        assert eng.cfg.precision == (capi.PREC_BF16 if prec == "bf16" else capi.PREC_FP16)
+        eng.set_option("taps", 1)
+        b = capi.Batch(eng, int(offs[-1]) + 64)
+        res = b.forward_s16(np.concatenate(segs), offs)
+        errs[prec] = max(rel(b.tap("enc", i), o["enc"]) for i, o in enumerate(oracle))
+        assert abs(int(res["token_counts"][0]) - oracle[0]["token_num"]) <= 1
+        b.close()
+        eng.close()
+    assert errs["fp16"] <= 2.5e-3 and errs["bf16"] <= 1.2e-2 and errs["fp16"] < 0.5 * errs["bf16"]
