@@ -1,9 +1,9 @@
 // tcgen05 flash attention, head dim 128, variable length, non-causal with key-length masking (see attention.cuh).
 //
-// PERSISTENT kernel: 2 CTAs per SM, each walking a static round-robin share of the (segment, 128-query tile) work items,
-// longest segment first.  Inside a CTA three roles run ONE continuous stream of (item, head, 64-key block) steps, so barrier
-// set-up, the TMEM allocation and the first-load latency are paid once per CTA and the loads of the next head / item are in
-// flight while the current one finishes:
+// PERSISTENT kernel: 2 CTAs per SM, each walking a static share of the work units -- one head of one (segment, 128-query tile)
+// item, costliest first, dealt out as a snake.  Inside a CTA three roles run ONE continuous stream of (unit, 64-key block)
+// steps, so barrier set-up, the TMEM allocation and the first-load latency are paid once per CTA and the loads of the next
+// unit are in flight while the current one finishes:
 //
 //   warp 0      : TMA producer.  Q per head (single buffer); K and V in SEPARATE 2-stage rings: a K stage is free as soon
 //                 as S = Q K^T of its block has completed (early), a V stage only after P V -- with one combined ring the
@@ -16,7 +16,11 @@
 //                 rescaled in TMEM) when the true maximum moved by more than 8 in the log2 domain.  Full 64-key blocks take
 //                 a mask-free path (packed FFMA2 / FADD2, 3-input max); only the last block of a segment is masked.
 //                 Warps whose 32 query rows lie beyond the segment only keep the barrier protocol going.
-//   P (probabilities, 16-bit) goes through a swizzled shared-memory tile; O / l is applied once per head.
+//   P (probabilities, 16-bit) never touches shared memory: each softmax thread writes its row back into the TMEM columns its
+//   scores came from (tcgen05.st, two values per 32-bit column) and P V reads its A operand from there (tcgen05.mma with A in
+//   TMEM).  That takes 32 KB per key block off the shared-memory pipe -- which, not the tensor pipe, bounds this kernel (Q is
+//   re-read for every 64-key S tile) -- and replaces the generic->async proxy fence by a tcgen05 fence.  O / l is applied once
+//   per head.
 #include "attention.cuh"
 #include "gemm.cuh"
 #include "launch.cuh"
@@ -28,11 +32,10 @@ namespace {
 constexpr int BQ = 128, BKV = 64, HD = 128, KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * HD * 2;       // 32768: two 128x64 swizzled boxes
 constexpr int K_BYTES = BKV * HD * 2;      // 16384: two 64x64 boxes
-constexpr int P_BYTES = BQ * BKV * 2;      // 16384
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 256;
-// 112 KB + barriers: two CTAs fit one SM (2 x 256 TMEM columns), so one CTA's softmax is covered by the other's MMAs.
-constexpr int kSmemBytes = Q_BYTES + 2 * KV_STAGES * K_BYTES + P_BYTES + 256;
+// 96 KB + barriers: two CTAs fit one SM (2 x 256 TMEM columns), so one CTA's softmax is covered by the other's MMAs.
+constexpr int kSmemBytes = Q_BYTES + 2 * KV_STAGES * K_BYTES + 256;
 
 struct AArgs {
   const int* q_row_off;
@@ -45,6 +48,7 @@ struct AArgs {
   int q_col0, k_col0, v_col0;
   int n_work, n_heads;
   float scale_log2e;
+  int dbg;   // micro-benchmark ablations only (B200PF_ATTN_DBG): 1 = no exponentials; 0 in the product
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -73,26 +77,31 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
-// The (item, head, key block) stream of one CTA.  All three roles walk it with their own copy; `g` counts key blocks and
-// `hc` heads since the CTA started -- every ring stage and barrier phase is derived from them.
+// The (work unit, key block) stream of one CTA; a unit is one head of one (segment, query tile) item.  All three roles walk it
+// with their own copy; `g` counts key blocks and `hc` units since the CTA started -- every ring stage and barrier phase is
+// derived from them.
 struct Stream {
   const AArgs& a;
-  int cta, n_cta, round;
+  int cta, n_cta, round, n_units;
   int q0, Tq, Tk, nb, q_row, kv_row;
   int h, j, g, hc;
   bool valid;
-  __device__ Stream(const AArgs& args, int cta_, int n_cta_) : a(args), cta(cta_), n_cta(n_cta_), round(0), h(0), j(0), g(0), hc(0) { valid = load_item(); }
-  // Items are sorted longest segment first; round r hands item r * n_cta + (cta or n_cta - 1 - cta) to this CTA (a snake, so
-  // no CTA gets the longer item of every round).
-  __device__ bool load_item() {
+  __device__ Stream(const AArgs& args, int cta_, int n_cta_) : a(args), cta(cta_), n_cta(n_cta_), round(0), j(0), g(0), hc(0) {
+    n_units = a.n_work * a.n_heads;
+    valid = load_unit();
+  }
+  // Items are sorted by cost (longest segment first) and the heads of an item are consecutive units; round r hands unit
+  // r * n_cta + (cta or n_cta - 1 - cta) to this CTA -- a snake, so no CTA gets the longer unit of every round.
+  __device__ bool load_unit() {
     for (;; ++round) {
-      const int item = round * n_cta + ((round & 1) ? n_cta - 1 - cta : cta);
-      if (round * n_cta >= a.n_work) return false;
-      if (item >= a.n_work) continue;
-      const AttnWork w = a.work[item];
+      if (round * n_cta >= n_units) return false;
+      const int unit = round * n_cta + ((round & 1) ? n_cta - 1 - cta : cta);
+      if (unit >= n_units) continue;
+      const AttnWork w = a.work[unit / a.n_heads];
       Tq = a.q_len[w.seg];
       Tk = a.kv_len[w.seg];
       if (w.q0 < Tq && Tk > 0) {
+        h = unit % a.n_heads;
         q0 = w.q0;
         nb = (Tk + BKV - 1) / BKV;
         q_row = a.q_row_off[w.seg] + w.q0;
@@ -106,11 +115,8 @@ struct Stream {
     if (++j == nb) {
       j = 0;
       ++hc;
-      if (++h == a.n_heads) {
-        h = 0;
-        ++round;
-        valid = load_item();
-      }
+      ++round;
+      valid = load_unit();
     }
   }
   __device__ int keys() const { const int n = Tk - j * BKV; return n < BKV ? n : BKV; }    // valid keys of this block
@@ -124,8 +130,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint8_t* sQ = smem;
   uint8_t* sK = smem + Q_BYTES;
   uint8_t* sV = sK + KV_STAGES * K_BYTES;
-  uint8_t* sP = sV + KV_STAGES * K_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * K_BYTES);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* q_full = bars;                  // 1
   uint64_t* q_empty = bars + 1;             // 1
@@ -134,8 +139,9 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* v_full = bars + 6;              // 2
   uint64_t* v_empty = bars + 8;             // 2
   uint64_t* s_full = bars + 10;             // 2
-  uint64_t* s_empty = bars + 12;            // 2
-  uint64_t* p_full = bars + 14;             // 1
+  uint64_t* p_full = bars + 12;             // 2: one per S / P buffer.  A softmax warp may run one block ahead of a slower one (S of
+                                            // block g + 1 is ready early); it then arrives on the OTHER barrier.  Two blocks ahead is
+                                            // impossible: S of block g + 2 needs P V of block g, which needs all four arrivals.
   uint64_t* p_empty = bars + 15;            // 1
   uint64_t* o_full = bars + 16;             // 1
   uint64_t* o_empty = bars + 17;            // 1
@@ -148,8 +154,8 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); }
-    mbar_init(p_full, 4); mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
+    mbar_init(&p_full[0], 4); mbar_init(&p_full[1], 4); mbar_init(p_empty, 1);
     mbar_init(o_full, 1); mbar_init(o_empty, 4);
     fence_barrier_init();
   }
@@ -206,16 +212,21 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const uint32_t q_addr = smem_u32(sQ);
       Stream s_it(a, blockIdx.x, gridDim.x);    // next block whose S is to be issued
       Stream pv_it(a, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
-      auto issue_s = [&]() {
+      auto issue_s = [&](bool after_pv) {
         const int g = s_it.g, stage = g % KV_STAGES, sb = g & 1;
         if (s_it.j == 0) mbar_wait(q_full, (uint32_t)(s_it.hc & 1));
         mbar_wait(&k_full[stage], (uint32_t)((g / KV_STAGES) & 1));
-        mbar_wait(&s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+        // S buffer sb still holds P of block g - 2, the A operand of that block's P V.  No wait is needed: that MMA was issued
+        // earlier by this same thread and the tensor pipe executes a thread's MMAs in issue order, so this S cannot overwrite the
+        // columns before P V has read them (an explicit wait on its commit cost a barrier round trip per key block: the
+        // micro-benchmark's barrier skeleton alone ran at 0.77 us per block with it).
+        (void)after_pv;
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + stage * K_BYTES);
         const uint32_t idesc = idesc_s0 | ((uint32_t)(s_it.keys16() >> 3) << 17);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
+          if ((a.dbg & 4) && ks > 0) break;
           const uint64_t da = umma_desc_sw128(q_addr + (ks >> 2) * (Q_BYTES / 2)) + 2 * (ks & 3);
           const uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (K_BYTES / 2)) + 2 * (ks & 3);
           umma_bf16(tmem_base + sb * BKV, da, db, idesc, ks != 0 ? 1u : 0u);
@@ -225,34 +236,33 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (s_it.j + 1 == s_it.nb) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
         s_it.advance();
       };
-      if (s_it.valid) issue_s();
+      if (s_it.valid) issue_s(false);
       while (pv_it.valid) {
         // S of the next block goes first so that it runs under this block's softmax -- unless it opens a new head whose Q
         // has not landed yet: then P V must not queue up behind that wait.
         bool deferred = false;
         if (s_it.valid) {
           if (s_it.j == 0 && !mbar_try_wait(q_full, (uint32_t)(s_it.hc & 1))) deferred = true;
-          else issue_s();
+          else issue_s(false);
         }
         const int g = pv_it.g, stage = g % KV_STAGES;
-        mbar_wait(p_full, (uint32_t)(g & 1));
+        mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1));
         if (pv_it.j == 0) mbar_wait(o_empty, (uint32_t)((pv_it.hc & 1) ^ 1));   // the previous head's O has been read out
         mbar_wait(&v_full[stage], (uint32_t)((g / KV_STAGES) & 1));
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP);
+        const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);   // P sits where S of this block was: 8 columns per 16 keys
         const uint32_t v_addr = smem_u32(sV + stage * K_BYTES);
-        const int ksteps = pv_it.keys16() >> 4;
+        const int ksteps = (a.dbg & 8) ? 0 : pv_it.keys16() >> 4;
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t da = umma_desc_sw128(p_addr) + 2 * ks;
           // V tile: 64 keys x 128 d as two [64 x 64] boxes 8 KB apart; 16 keys = 2048 B per K step
           const uint64_t db = umma_desc_sw128_mn(v_addr + ks * 2048, K_BYTES / 2);
-          umma_bf16(tmem_o, da, db, idesc_pv, (pv_it.j | ks) != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_o, p_tmem + 8 * ks, db, idesc_pv, (pv_it.j | ks) != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[stage]);
         umma_commit(p_empty);
         if (pv_it.j + 1 == pv_it.nb) umma_commit(o_full);
         pv_it.advance();
-        if (deferred) issue_s();
+        if (deferred) issue_s(true);
       }
     }
     __syncwarp();
@@ -260,13 +270,12 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t prow = smem_u32(sP + row * 128);
     const float2 sc2 = make_float2(a.scale_log2e, a.scale_log2e);
     uint32_t r[32], r2[32];
     float m = -INFINITY, l = 0.f, m_used = 0.f;
     for (Stream st(a, blockIdx.x, gridDim.x); st.valid; st.advance()) {
       const int g = st.g, sb = g & 1;
-      const bool warp_active = st.q0 + quarter * 32 < st.Tq;   // warp-uniform: does this warp own any real query row?
+      const bool warp_active = st.q0 + quarter * 32 < st.Tq && !(a.dbg & 16);   // warp-uniform: does this warp own any real query row?
       if (st.j == 0) { m = -INFINITY; l = 0.f; m_used = 0.f; }
       mbar_wait(&s_full[sb], (uint32_t)((g >> 1) & 1));
       tc_fence_after();
@@ -277,10 +286,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (warp_active) {
         tmem_ld_32x32(tmem_base + lane_addr + sb * BKV, r);
         tmem_ld_32x32(tmem_base + lane_addr + sb * BKV + 32, r2);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[sb]);   // the scores are in registers
+        tmem_ld_wait();   // the scores are in registers; their TMEM columns will take P below
         if (nvalid == BKV) {
           // ---- full block: no masks ----
           float mb0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r2[0]));
@@ -306,8 +312,8 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int c = 0; c < 32; c += 2) {
             const float2 x = ffma2(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), sc2, mc2);
             const float2 y = ffma2(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), sc2, mc2);
-            const float2 p = make_float2(ex2(x.x), ex2(x.y));
-            const float2 q = make_float2(ex2(y.x), ex2(y.y));
+            const float2 p = a.dbg & 1 ? x : make_float2(ex2(x.x), ex2(x.y));
+            const float2 q = a.dbg & 1 ? y : make_float2(ex2(y.x), ex2(y.y));
             la = fadd2(la, p);
             lb = fadd2(lb, q);
             pk[c >> 1] = pack_h2<F16>(p.x, p.y);
@@ -343,14 +349,12 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             pk[16 + (c >> 1)] = pack_h2<F16>(p2, p3);
           }
         }
-      } else {
-        if (lane == 0) mbar_arrive(&s_empty[sb]);
       }
-      // P V of the previous block has completed once p_empty flips: P's buffer is free and O is quiescent
-      mbar_wait(p_empty, (uint32_t)((g & 1) ^ 1));
       if (warp_active) {
         if (__any_sync(0xffffffffu, need)) {
-          // rare: this warp's 32 rows of O are rescaled in TMEM (rows that did not move use factor 1)
+          // rare: this warp's 32 rows of O are rescaled in TMEM (rows that did not move use factor 1).  O is quiescent once
+          // P V of the previous block has completed (p_empty); `need` is never set on a head's first block.
+          mbar_wait(p_empty, (uint32_t)((g & 1) ^ 1));
           tc_fence_after();
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
@@ -368,16 +372,20 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           tmem_st_wait();
           tc_fence_before();
         }
-        // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7)); chunks past the
-        // block's MMA extent are never read
-        const int nch = ((nvalid + 15) & ~15) >> 3;
+        // P row -> the TMEM columns S came from: column c of the block's buffer holds keys 2c, 2c + 1 (columns past the block's
+        // MMA extent are written too -- zeros -- and never read)
+        {
+          uint32_t lo[16], hi[16];
 #pragma unroll
-        for (int jc = 0; jc < 8; ++jc)
-          if (jc < nch) sts128(prow + ((jc ^ (row & 7)) << 4), pk[4 * jc], pk[4 * jc + 1], pk[4 * jc + 2], pk[4 * jc + 3]);
-        fence_proxy_async_smem();
+          for (int c = 0; c < 16; ++c) { lo[c] = pk[c]; hi[c] = pk[16 + c]; }
+          tmem_st_32x16(tmem_base + lane_addr + sb * BKV, lo);
+          tmem_st_32x16(tmem_base + lane_addr + sb * BKV + 16, hi);
+        }
+        tmem_st_wait();
+        tc_fence_before();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
       if (st.j + 1 == st.nb) {
         // ---- this head's output ----
         mbar_wait(o_full, (uint32_t)(st.hc & 1));
@@ -474,6 +482,8 @@ AArgs make_args(const AttnProblem& p) {
   a.q_col0 = p.q_col0; a.k_col0 = p.k_col0; a.v_col0 = p.v_col0;
   a.n_work = p.n_work; a.n_heads = p.n_heads;
   a.scale_log2e = p.scale * 1.4426950408889634f;
+  static const int dbg = getenv("B200PF_ATTN_DBG") ? atoi(getenv("B200PF_ATTN_DBG")) : 0;
+  a.dbg = dbg;
   return a;
 }
 
@@ -494,8 +504,9 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   rc = make_tmap_bf16_sw128(&tmKV, p.kv, (uint64_t)p.kv_rows, (uint64_t)p.ldkv, (uint64_t)p.ldkv, BKV);
   if (rc) return rc;
   const AArgs a = make_args(p);
-  const int resident = 2 * (p.num_sms > 0 ? p.num_sms : 148);
-  const dim3 grid(p.n_work < resident ? p.n_work : resident);
+  static const int ctas_per_sm = getenv("B200PF_ATTN_CTAS") ? atoi(getenv("B200PF_ATTN_CTAS")) : 2;
+  const int resident = ctas_per_sm * (p.num_sms > 0 ? p.num_sms : 148), units = p.n_work * p.n_heads;
+  const dim3 grid(units < resident ? units : resident);
   if (p.f16) return launch_kernel(attn_heads_kernel<true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
   return launch_kernel(attn_heads_kernel<false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
 }

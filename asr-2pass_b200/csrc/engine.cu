@@ -547,7 +547,7 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 63) & ~size_t(63); return o; };
   const size_t o_sample = carve((S + 1) * 8), o_fb = carve((S + 1) * 4), o_row = carve((S + 1) * 4), o_T = carve(S * 4),
-               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8), o_usoff = carve(S * 4), o_uslen = carve(S * 4),
+               o_rseg = carve(R * 4), o_rinfo = carve(R * 8), o_work = carve(R * 8), o_workx = carve(R * 8), o_usoff = carve(S * 4), o_uslen = carve(S * 4),
                o_zero = carve(S * 4), o_hwlen = carve(S * 4);
   b->meta_bytes = off;
   CK(cudaMallocHost((void**)&b->h_meta, off), "cudaMallocHost(meta)");
@@ -559,6 +559,7 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   b->h_row_seg = (int*)(b->h_meta + o_rseg);          b->d_row_seg = (const int*)(b->d_meta + o_rseg);
   b->h_row_info = (int2*)(b->h_meta + o_rinfo);       b->d_row_info = (const int2*)(b->d_meta + o_rinfo);
   b->h_work = (AttnWork*)(b->h_meta + o_work);        b->d_work = (const AttnWork*)(b->d_meta + o_work);
+  b->h_work_x = (AttnWork*)(b->h_meta + o_workx);     b->d_work_x = (const AttnWork*)(b->d_meta + o_workx);
   b->h_us_off = (int*)(b->h_meta + o_usoff);          b->d_us_off = (const int*)(b->d_meta + o_usoff);
   b->h_us_len = (int*)(b->h_meta + o_uslen);          b->d_us_len = (const int*)(b->d_meta + o_uslen);
   b->h_zero = (int*)(b->h_meta + o_zero);             b->d_zero = (const int*)(b->d_meta + o_zero);
@@ -636,6 +637,11 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
   // attention work items longest segment first: a CTA's run time grows with its segment's key count, and the grid is only
   // ~2.3 waves deep, so the long items must not be the ones that start last
   std::stable_sort(b->h_work, b->h_work + nwork, [&](const AttnWork& x, const AttnWork& y) { return b->h_seg_T[x.seg] > b->h_seg_T[y.seg]; });
+  // The decoder's cross-attention has L_i <= T_i query rows, a count only the device knows: tiles with q0 >= L_i are skipped by
+  // the kernel.  Ordered by (q0, longest first) the skipped tiles of every q0 group sit together at the group's short end, so
+  // the kernel's static deal spreads them evenly over the CTAs instead of handing some CTAs nothing but skipped tiles.
+  memcpy(b->h_work_x, b->h_work, (size_t)nwork * sizeof(AttnWork));
+  std::stable_sort(b->h_work_x, b->h_work_x + nwork, [](const AttnWork& x, const AttnWork& y) { return x.q0 < y.q0; });
   b->h_sample_off[ns] = 0;
   b->h_fb_off[ns] = frames;
   b->h_row_off[ns] = rows;
@@ -905,7 +911,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
   cp.out = e->att; cp.ldo = D;
   cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
-  cp.work = b->d_work; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
+  cp.work = b->d_work_x; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
   auto dec_ffn = [&](const DecLayer& w) -> int {
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln1");
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;

@@ -155,7 +155,8 @@ struct b200pf_batch {
   int* h_hw_len = nullptr;         const int* d_hw_len = nullptr;   // [S] n_hw
   int* h_row_seg = nullptr;        const int* d_row_seg = nullptr;
   int2* h_row_info = nullptr;      const int2* d_row_info = nullptr;
-  pf::AttnWork* h_work = nullptr;  const pf::AttnWork* d_work = nullptr;
+  pf::AttnWork* h_work = nullptr;  const pf::AttnWork* d_work = nullptr;      // self-attention tiles, longest segment first
+  pf::AttnWork* h_work_x = nullptr; const pf::AttnWork* d_work_x = nullptr;   // cross-attention: the same tiles by (q0, longest first)
   // device results
   int* d_n_tok = nullptr;     // [S]
   int* d_tok_off = nullptr;   // [S+1]

@@ -273,6 +273,7 @@ int b200pf_op_attention_bench(int device, const int32_t* seg_T, int n_seg, int n
   for (int s = 0; s < n_seg; ++s)
     for (int q0 = 0; q0 < seg_T[s]; q0 += 128) work.push_back(AttnWork{s, q0});   // the engine builds the list from T for both uses
   std::stable_sort(work.begin(), work.end(), [&](const AttnWork& x, const AttnWork& y) { return seg_T[x.seg] > seg_T[y.seg]; });
+  if (cross) std::stable_sort(work.begin(), work.end(), [](const AttnWork& x, const AttnWork& y) { return x.q0 < y.q0; });   // as the engine does
   RC(up_raw(work.data(), work.size(), &dWork));
   AttnProblem p;
   p.f16 = g_op_f16; p.num_sms = sm_count();

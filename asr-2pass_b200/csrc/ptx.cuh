@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace pf {
 
@@ -83,10 +84,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("b200pf: mbarrier wait timed out: block %d thread %d barrier@smem+%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
+    if (++spins > (1u << 26)) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
