@@ -130,7 +130,8 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_punc_add_scripted", "b200pf_host_punc_create", "b200pf_host_punc_destroy", "b200pf_host_punc_rounds", "b200pf_host_punc_add",
                 "b200pf_host_punc_add_batch", "b200pf_host_punc_online_add_scripted", "b200pf_host_punc_online_create",
                 "b200pf_host_punc_online_destroy", "b200pf_host_punc_online_add", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
-                "b200pf_host_offline_infer_full"]
+                "b200pf_host_offline_infer_full", "b200pf_host_tpass_init_kv", "b200pf_host_tpass_online_init", "b200pf_host_tpass_uninit",
+                "b200pf_host_tpass_online_uninit", "b200pf_host_tpass_infer", "b200pf_host_vad_segments_streaming", "b200pf_host_expand_posteriors"]
 
 
 def host_lib():
@@ -174,6 +175,18 @@ def host_lib():
     H.b200pf_host_pack_hotwords.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, c_i32p, c_i32p, C.c_int]
     H.b200pf_host_offline_init_kv.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int]
     H.b200pf_host_offline_init_kv.restype = C.c_void_p
+    H.b200pf_host_tpass_init_kv.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int]
+    H.b200pf_host_tpass_init_kv.restype = C.c_void_p
+    H.b200pf_host_tpass_online_init.argtypes = [C.c_void_p]
+    H.b200pf_host_tpass_online_init.restype = C.c_void_p
+    H.b200pf_host_tpass_uninit.argtypes = [C.c_void_p]
+    H.b200pf_host_tpass_uninit.restype = None
+    H.b200pf_host_tpass_online_uninit.argtypes = [C.c_void_p]
+    H.b200pf_host_tpass_online_uninit.restype = None
+    H.b200pf_host_tpass_infer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                          C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    H.b200pf_host_expand_posteriors.argtypes = [c_f32p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p]
+    H.b200pf_host_vad_segments_streaming.argtypes = [c_f32p, C.c_int, c_i32p, C.c_int, C.c_int, C.c_int, C.c_float, c_i32p, C.c_int]
     H.b200pf_host_offline_infer_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
                                                  C.c_char_p, C.c_int]
     H.b200pf_host_sentence_stamps.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -373,6 +386,74 @@ class OfflineHandle:
         if n < 0:
             raise B200PFError("FunOfflineInferBuffer returned nullptr")
         return t.value.decode("utf-8"), st.value.decode("utf-8")
+
+
+class TpassStream:
+    """FunTpassInit + one FunTpassOnlineInit connection per `connect()` (the 2-pass server's handles); infer() = one
+    FunTpassInferBuffer call -> dict(msg, tpass_msg, stamp, stamp_sents)."""
+
+    def __init__(self, model_dir, vad_dir, punc_dir=None, device=0, options=None):
+        kv = {"model-dir": model_dir, "vad-dir": vad_dir, "device": str(device)}
+        if punc_dir:
+            kv["punc-dir"] = punc_dir
+        kv.update(options or {})
+        keys = (C.c_char_p * len(kv))(*[k.encode() for k in kv])
+        vals = (C.c_char_p * len(kv))(*[str(v).encode() for v in kv.values()])
+        self.h = host_lib().b200pf_host_tpass_init_kv(keys, vals, len(kv))
+        if not self.h:
+            raise B200PFError("FunTpassInit failed")
+        self._conns = []
+
+    def connect(self):
+        c = host_lib().b200pf_host_tpass_online_init(self.h)
+        if not c:
+            raise B200PFError("FunTpassOnlineInit failed")
+        self._conns.append(c)
+        return dict(h=c, cache=C.create_string_buffer(1 << 16))
+
+    def infer(self, conn, pcm16, finished, mode=2, vad_tail_sil=800, vad_max_len=60000, cap=1 << 20):
+        pcm16 = np.ascontiguousarray(pcm16, dtype="<i2")
+        msg, tp, st, ss = (C.create_string_buffer(cap) for _ in range(4))
+        n = host_lib().b200pf_host_tpass_infer(self.h, conn["h"], C.c_void_p(pcm16.ctypes.data), pcm16.nbytes, int(bool(finished)), mode, vad_tail_sil,
+                                               vad_max_len, conn["cache"], len(conn["cache"]), msg, cap, tp, cap, st, cap, ss, cap)
+        if n < 0:
+            raise B200PFError("FunTpassInferBuffer returned nullptr")
+        return dict(msg=msg.value.decode("utf-8", "replace"), tpass_msg=tp.value.decode("utf-8", "replace"), stamp=st.value.decode("utf-8"),
+                    stamp_sents=ss.value.decode("utf-8", "replace"))
+
+    def close(self):
+        if self.h:
+            for c in self._conns:
+                host_lib().b200pf_host_tpass_online_uninit(c)
+            self._conns = []
+            host_lib().b200pf_host_tpass_uninit(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_expand_posteriors(topk_logprob, topk_ids, vocab):
+    """pf::host::ExpandPrunedPosteriors: [rows, k] pruned posteriors -> dense [rows, vocab] log-softmax rows."""
+    lp = np.ascontiguousarray(topk_logprob, dtype=np.float32)
+    ids = np.ascontiguousarray(topk_ids, dtype=np.int32)
+    rows, k = lp.shape
+    out = np.zeros((rows, vocab), np.float32)
+    host_lib().b200pf_host_expand_posteriors(_p(lp), _p(ids, c_i32p), rows, k, vocab, _p(out))
+    return out
+
+
+def host_vad_segments_streaming(sil_prob, chunk_lens, max_end_sil=800, max_seg_ms=15000, thres=0.8):
+    """pf::host::StreamingVad fed in chunks of chunk_lens frames (the last chunk final) -> [(start_ms, end_ms)]."""
+    p = np.ascontiguousarray(sil_prob, dtype=np.float32)
+    cl = np.ascontiguousarray(chunk_lens, dtype=np.int32)
+    out = np.zeros(2 * max(16, len(p) // 10 + 16), np.int32)
+    n = host_lib().b200pf_host_vad_segments_streaming(_p(p), len(p), _p(cl, c_i32p), len(cl), max_end_sil, max_seg_ms, C.c_float(thres), _p(out, c_i32p),
+                                                      len(out) // 2)
+    return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n)]
 
 
 class MicroBatcher:

@@ -813,7 +813,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   };
   auto prof_end = [&](int h) { if (h >= 0) cudaEventRecord(e->prof_recs[h].b, s); };
   // the decoder's row count lives on the device; for the FLOP estimate use tokens ~ frames / 2 (random init)
-  const double Lest = 0.5 * (M - S);
+  const double Lest = b->last_tokens >= 0 && b->last_tokens_rows == M ? (double)b->last_tokens : 0.5 * (M - S);   // exact once this layout was collected
   double sumT2 = 0;
   for (int i = 0; i < S; ++i) sumT2 += (double)b->h_seg_T[i] * b->h_seg_T[i];
 
@@ -1054,6 +1054,8 @@ int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
   if (res->us_offsets) res->us_offsets[b->n_seg_in] = (int32_t)us_out;
   if (res->token_offsets) res->token_offsets[b->n_seg_in] = (int32_t)out;
   res->n_tokens = out;
+  b->last_tokens = out;
+  b->last_tokens_rows = b->rows;
   b->flops = fl;
   b->collected = true;
   return 0;

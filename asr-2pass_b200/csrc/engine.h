@@ -182,6 +182,8 @@ struct b200pf_batch {
   int rows = 0, n_frames = 0, n_work = 0;
   int64_t launches = 0;
   double flops = 0.0;
+  int64_t last_tokens = -1;     // tokens of the last collected run and the row count it belonged to (profiling: exact decoder FLOPs)
+  int last_tokens_rows = -1;
   cudaEvent_t staged = nullptr;
   bool collected = false;
 };

@@ -417,9 +417,181 @@ bool LoadAudioFile(const char* path, int default_rate, std::vector<char>* data_o
 }
 }  // namespace
 
-const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE) {
-  OfflineHandle* h = (OfflineHandle*)handle;
+namespace {
+// ---- 2-pass stream: the OFFLINE (correction) leg of FunTpassInferBuffer (funasrruntime.cpp:492-639) -----------------------------
+// TpassStream (tpass-stream.h) owns the offline acoustic model, the VAD and the realtime punctuation model; the streaming acoustic
+// model (ParaformerOnline) is not part of this path and is not built here: the online partial results (`msg`) stay empty, the
+// corrected `tpass_msg` / `stamp` / `stamp_sents` of every closed VAD segment are produced exactly like the reference's FetchTpass
+// loop produces them.
+struct TpassHandle {
+  OfflineHandle* offline = nullptr;                                   // acoustic model (+ micro-batcher) and the VAD network
+  std::unique_ptr<funasr_b200::CTTransformerOnlineB200> punc_online;  // TpassStream::punc_online_handle (may be absent)
+  ~TpassHandle() { delete offline; }
+};
+
+// TpassOnlineStream (tpass-online-stream.h): the per-connection state -- here the audio not yet consumed and the VAD state machine.
+struct TpassOnlineHandle {
+  TpassHandle* parent;
+  pf::host::StreamingVad vad;
+  std::vector<short> pcm;          // samples [base, base + pcm.size()) of the stream
+  long long base = 0;              // global index of pcm[0]
+  long long total = 0;             // samples received since the stream started
+  int scored = 0;                  // 10 ms frames whose silence probability is final and has been pushed into `vad`
+  explicit TpassOnlineHandle(TpassHandle* p, const pf::host::VadOptions& o) : parent(p), vad(o) {}
+  void Restart() { vad.Reset(); pcm.clear(); base = 0; total = 0; scored = 0; }
+};
+
+constexpr int kVadLookbackFrames = 100;   // > the VAD network's left context (4 FSMN layers x 19 taps + 2 LFR frames = 78 frames)
+constexpr int kVadRightFrames = 2;        // LFR 5/1 looks two frames ahead: the last two frames of an unfinished stream are provisional
+}  // namespace
+
+FUNASR_HANDLE FunTpassInit(std::map<std::string, std::string>& model_path, int thread_num) {
+  // keys as TpassStream reads them (tpass-stream.cpp): "model-dir" (offline AM), "vad-dir", "punc-dir" (the REALTIME punctuation
+  // model here), "online-model-dir" (ignored: the streaming AM stays on the reference host), "itn-dir" / "lm-dir" (ignored)
+  if (model_path.find("vad-dir") == model_path.end()) { fprintf(stderr, "FunTpassInit: vad-dir missing (the 2-pass stream is cut by the VAD)\n"); return nullptr; }
+  std::map<std::string, std::string> off(model_path);
+  off.erase("punc-dir");   // the offline handle's own punctuation hook is the OFFLINE model; the 2-pass stream uses the realtime one
+  std::unique_ptr<TpassHandle> t(new TpassHandle);
+  t->offline = (OfflineHandle*)FunOfflineInit(off, thread_num, false, 1);
+  if (!t->offline) return nullptr;
+  auto pd = model_path.find("punc-dir");
+  if (pd != model_path.end() && !pd->second.empty()) {
+    t->punc_online.reset(new funasr_b200::CTTransformerOnlineB200(ToInt(model_path, "device", 0), ToInt(model_path, "punc-max-tokens", 0)));
+    std::string err;
+    if (!t->punc_online->Init(pd->second, &err)) { fprintf(stderr, "FunTpassInit: punc-dir %s: %s\n", pd->second.c_str(), err.c_str()); return nullptr; }
+  }
+  return t.release();
+}
+
+FUNASR_HANDLE FunTpassOnlineInit(FUNASR_HANDLE tpass_handle, std::vector<int> chunk_size) {
+  (void)chunk_size;   // the streaming model's chunking; the offline leg is cut by the VAD alone
+  TpassHandle* t = (TpassHandle*)tpass_handle;
+  if (!t) return nullptr;
+  pf::host::VadOptions vo;
+  vo.speech_noise_thres = t->offline->vad_thres;
+  return new TpassOnlineHandle(t, vo);
+}
+
+void FunTpassUninit(FUNASR_HANDLE handle) { delete (TpassHandle*)handle; }
+void FunTpassOnlineUninit(FUNASR_HANDLE handle) { delete (TpassOnlineHandle*)handle; }
+
+FUNASR_RESULT FunTpassInferBuffer(FUNASR_HANDLE handle, FUNASR_HANDLE online_handle, const char* sz_buf, int n_len,
+                                  std::vector<std::vector<std::string>>& punc_cache, bool input_finished, int sampling_rate,
+                                  std::string wav_format, ASR_TYPE mode, const std::vector<std::vector<float>>& hw_emb, bool itn,
+                                  int vad_tail_sil, int vad_max_len, FUNASR_DEC_HANDLE dec_handle, std::string svs_lang, bool svs_itn) {
+  (void)itn; (void)dec_handle; (void)svs_lang; (void)svs_itn;
+  TpassHandle* t = (TpassHandle*)handle;
+  TpassOnlineHandle* o = (TpassOnlineHandle*)online_handle;
+  if (!t || !o) return nullptr;                                                     // funasrruntime.cpp:500-501
+  OfflineHandle* h = t->offline;
+  if (!(wav_format == "pcm" || wav_format == "PCM")) { fprintf(stderr, "Wrong wav_format: %s\n", wav_format.c_str()); return nullptr; }
+  if (sampling_rate != h->model()->GetAsrSampleRate()) { fprintf(stderr, "FunTpassInferBuffer: resampling stays on the reference host path\n"); return nullptr; }
+  if (punc_cache.size() < 2) punc_cache.resize(2);
+  o->vad.SetOptions(vad_tail_sil, vad_max_len);                                      // vad_online_handle->SetConfig (:506)
+  const long long n = n_len / 2;
+  const unsigned char* bytes = (const unsigned char*)sz_buf;
+  const size_t old = o->pcm.size();
+  o->pcm.resize(old + (size_t)n);
+  for (long long i = 0; i < n; ++i) o->pcm[old + i] = (short)((bytes[2 * i + 1] << 8) | bytes[2 * i]);   // LoadPcmwavOnline
+  o->total += n;
+  RecogResult* res = new RecogResult;
+  res->snippet_time = (float)n / h->model()->GetAsrSampleRate();
+
+  // ---- VAD: silence probabilities of the frames that became final with this chunk, then the E2E state machine ----
+  const int f_total = o->total >= 400 ? (int)(1 + (o->total - 400) / 160) : 0;
+  const int f_final = input_finished ? f_total : std::max(o->scored, f_total - kVadRightFrames);
+  std::vector<std::pair<int, int>> closed;
+  if (f_final > o->scored || (input_finished && f_total > 0 && f_final == o->scored)) {
+    const int w0 = std::max((int)(o->base / 160), std::max(0, o->scored - kVadLookbackFrames));   // first frame of the scoring window
+    const long long s0 = (long long)w0 * 160 - o->base;                                           // its first sample inside pcm
+    const long long ns = (long long)o->pcm.size() - s0;
+    const int wf = ns >= 400 ? (int)(1 + (ns - 400) / 160) : 0;
+    std::vector<float> sil((size_t)std::max(1, wf));
+    if (wf > 0) {
+      int64_t off[2] = {0, (int64_t)ns};
+      int32_t frame_off[2] = {0, 0};
+      std::lock_guard<std::mutex> lk(h->vad_mu);
+      if (b200pf_vad_scores_s16(h->vad, (const int16_t*)o->pcm.data() + s0, off, 1, sil.data(), (int64_t)sil.size(), frame_off, nullptr, nullptr) != 0) {
+        fprintf(stderr, "FunTpassInferBuffer: VAD: %s\n", b200pf_last_error());
+        delete res;
+        return nullptr;
+      }
+    }
+    const int first = o->scored - w0, count = f_final - o->scored;
+    if (count > 0 && first >= 0 && first + count <= wf) closed = o->vad.Push(sil.data() + first, count, input_finished);
+    else if (input_finished) closed = o->vad.Push(sil.data(), 0, true);
+    o->scored = f_final;
+  }
+
+  // ---- the offline leg: every closed VAD segment through the offline model (FetchTpass loop, :570-636) ----
+  if (mode != ASR_ONLINE) {
+    std::string cur_stamp = "[";
+    const long long per_ms = h->model()->GetAsrSampleRate() / 1000;
+    for (const auto& sg : closed) {
+      const long long sb = std::max<long long>(o->base, std::min<long long>(o->total, sg.first * per_ms));
+      const long long se = std::max<long long>(sb, std::min<long long>(o->total, sg.second * per_ms));
+      if (se <= sb) continue;
+      const long long len = se - sb;
+      std::vector<float> fl((size_t)len);
+      const short* src = o->pcm.data() + (sb - o->base);
+      for (long long i = 0; i < len; ++i) fl[i] = (float)src[i] / 32768.0f;
+      float* buff[1] = {fl.data()};
+      int l[1] = {(int)len};
+      std::vector<std::string> msgs = h->batcher ? h->batcher->Forward(buff, l, true, hw_emb, nullptr, 1)
+                                                 : h->model()->Forward(buff, l, true, hw_emb, nullptr, 1);
+      std::string msg = msgs.empty() ? std::string() : msgs[0];
+      // "text | b0, e0,b1, e1,..." (PostProcess, util.cpp:820-835): seconds relative to the segment
+      std::string stamps;
+      const size_t bar = msg.find(" | ");
+      if (bar != std::string::npos) { stamps = msg.substr(bar + 3); msg = msg.substr(0, bar); }
+      if (msg.empty() && stamps.empty() && msgs.empty()) continue;
+      if (!stamps.empty()) {
+        std::vector<std::string> parts;
+        size_t p0 = 0;
+        while (p0 <= stamps.size()) {
+          size_t q = stamps.find(',', p0);
+          if (q == std::string::npos) q = stamps.size();
+          if (q > p0) parts.push_back(stamps.substr(p0, q - p0));
+          p0 = q + 1;
+        }
+        for (size_t i = 0; i + 1 < parts.size(); i += 2) {
+          const float begin = std::stof(parts[i]) + (float)sg.first / 1000.0f;       // frame->global_start is in ms
+          const float end = std::stof(parts[i + 1]) + (float)sg.first / 1000.0f;
+          cur_stamp += "[" + std::to_string((int)(1000 * begin)) + "," + std::to_string((int)(1000 * end)) + "],";
+        }
+      }
+      if (cur_stamp != "[") {
+        cur_stamp.erase(cur_stamp.length() - 1);
+        res->stamp += cur_stamp + "]";
+      }
+      std::string msg_punc = msg;
+      if (t->punc_online) {
+        msg_punc = t->punc_online->AddPunc(msg.c_str(), punc_cache[1], h->model()->GetLang());
+        if (input_finished) msg_punc += "\xe3\x80\x82";                            // "。" (:612-614)
+      }
+      res->tpass_msg = msg_punc;                                                     // the reference keeps the LAST segment's text per call
+      if (!res->stamp.empty()) res->stamp_sents = pf::host::SentenceStamps(res->tpass_msg, res->stamp);
+    }
+  }
+
+  // ---- drop what can no longer be needed: audio before the open segment and before the scoring look-back ----
+  long long keep_from = (long long)std::max(0, o->scored - kVadLookbackFrames) * 160;
+  const int open_ms = o->vad.open_start_ms();
+  if (open_ms >= 0) keep_from = std::min<long long>(keep_from, (long long)open_ms * 16);
+  keep_from = std::max(keep_from, o->base);
+  if (keep_from - o->base > (1 << 20)) {   // trim in large steps only
+    o->pcm.erase(o->pcm.begin(), o->pcm.begin() + (size_t)(keep_from - o->base));
+    o->base = keep_from;
+  }
+  if (input_finished) o->Restart();        // audio->ResetIndex() (:641-643)
+  return res;
+}
+
+const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE mode) {
   std::vector<std::vector<float>> emb;
+  if (!handle) return emb;
+  if (mode == ASR_ONLINE) { fprintf(stderr, "Not implement: Online model does not support Hotword yet!\n"); return emb; }   // funasrruntime.cpp:482-486
+  OfflineHandle* h = mode == ASR_TWO_PASS ? ((TpassHandle*)handle)->offline : (OfflineHandle*)handle;
   if (!h) return emb;
   return h->model()->CompileHotwordEmbedding(hotwords);
 }

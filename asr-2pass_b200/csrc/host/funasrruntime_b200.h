@@ -52,6 +52,24 @@ FUNASR_RESULT FunOfflineInfer(FUNASR_HANDLE handle, const char* sz_filename, FUN
 const std::vector<std::vector<float>> CompileHotwordEmbedding(FUNASR_HANDLE handle, std::string& hotwords, ASR_TYPE mode = ASR_OFFLINE);
 void FunOfflineUninit(FUNASR_HANDLE handle);
 
+// 2-pass stream (funasrruntime.h:121-132).  The OFFLINE leg of FunTpassInferBuffer -- VAD-closed segments through the offline
+// acoustic model, realtime punctuation, timestamps and stamp_sents (funasrruntime.cpp:568-639) -- is served here, so
+// websocket-server-2pass links against this library and its "offline" and "2pass" modes receive the corrected results
+// ("mode":"2pass-offline").  The streaming acoustic model (ParaformerOnline, the "2pass-online" partial results) is outside this
+// path: `FunASRGetResult` of a 2-pass result is empty and mode ASR_ONLINE returns no text.  model_path keys: "model-dir",
+// "vad-dir" (required), "punc-dir" (the realtime CT-Transformer), plus the extra keys of FunOfflineInit ("device",
+// "micro-batch-us": batch-1 calls of all connections merged by the MicroBatcher); "online-model-dir", "itn-dir", "lm-dir" are ignored.
+FUNASR_HANDLE FunTpassInit(std::map<std::string, std::string>& model_path, int thread_num);
+FUNASR_HANDLE FunTpassOnlineInit(FUNASR_HANDLE tpass_handle, std::vector<int> chunk_size = {5, 10, 5});
+FUNASR_RESULT FunTpassInferBuffer(FUNASR_HANDLE handle, FUNASR_HANDLE online_handle, const char* sz_buf, int n_len,
+                                  std::vector<std::vector<std::string>>& punc_cache, bool input_finished = true, int sampling_rate = 16000,
+                                  std::string wav_format = "pcm", ASR_TYPE mode = ASR_TWO_PASS,
+                                  const std::vector<std::vector<float>>& hw_emb = {{0.0}}, bool itn = true, int vad_tail_sil = 800,
+                                  int vad_max_len = 60000, FUNASR_DEC_HANDLE dec_handle = nullptr, std::string svs_lang = "auto",
+                                  bool svs_itn = true);
+void FunTpassUninit(FUNASR_HANDLE handle);
+void FunTpassOnlineUninit(FUNASR_HANDLE handle);
+
 const char* FunASRGetResult(FUNASR_RESULT result, int n_index);
 const char* FunASRGetStamp(FUNASR_RESULT result);
 const char* FunASRGetStampSents(FUNASR_RESULT result);

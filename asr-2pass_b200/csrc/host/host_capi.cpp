@@ -9,6 +9,7 @@
 #include <thread>
 
 #include "funasrruntime_b200.h"
+#include "logprob_adapter.h"
 #include "micro_batcher.h"
 #include "multi_gpu.h"
 #include "paraformer_b200.h"
@@ -119,6 +120,67 @@ int b200pf_host_offline_infer_full(void* h, const char* buf, int n_bytes, int va
   if (stamp_sents) CopyOut(FunASRGetStampSents(r), stamp_sents, sents_cap);
   FunASRFreeResult(r);
   return n;
+}
+// ---- 2-pass stream hooks (FunTpassInit / FunTpassOnlineInit / FunTpassInferBuffer) ----
+void* b200pf_host_tpass_init_kv(const char* const* keys, const char* const* values, int n) {
+  std::map<std::string, std::string> mp;
+  for (int i = 0; i < n; ++i) mp[keys[i]] = values[i];
+  return FunTpassInit(mp, 1);
+}
+void* b200pf_host_tpass_online_init(void* tpass) { return FunTpassOnlineInit(tpass); }
+void b200pf_host_tpass_uninit(void* tpass) { FunTpassUninit(tpass); }
+void b200pf_host_tpass_online_uninit(void* online) { FunTpassOnlineUninit(online); }
+// One FunTpassInferBuffer call.  cache_io carries punc_cache[1] (the offline leg's realtime-punctuation word cache) in and out as
+// '\n'-joined words.  Returns the length of tpass_msg (>= 0) or -1 when the call returned nullptr.
+int b200pf_host_tpass_infer(void* tpass, void* online, const char* buf, int n_bytes, int input_finished, int mode, int vad_tail_sil,
+                            int vad_max_len, char* cache_io, int cache_cap, char* msg, int msg_cap, char* tpass_msg, int tpass_cap, char* stamp,
+                            int stamp_cap, char* stamp_sents, int sents_cap) {
+  std::vector<std::vector<std::string>> cache(2);
+  if (cache_io) {
+    std::string c(cache_io), cur;
+    for (char ch : c) { if (ch == '\n') { cache[1].push_back(cur); cur.clear(); } else cur.push_back(ch); }
+    if (!cur.empty()) cache[1].push_back(cur);
+  }
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  FUNASR_RESULT r = FunTpassInferBuffer(tpass, online, buf, n_bytes, cache, input_finished != 0, 16000, "pcm", (ASR_TYPE)mode, hw, true, vad_tail_sil,
+                                        vad_max_len);
+  if (!r) return -1;
+  if (msg) CopyOut(FunASRGetResult(r, 0), msg, msg_cap);
+  const int n = CopyOut(FunASRGetTpassResult(r, 0), tpass_msg, tpass_cap);
+  if (stamp) CopyOut(FunASRGetStamp(r), stamp, stamp_cap);
+  if (stamp_sents) CopyOut(FunASRGetStampSents(r), stamp_sents, sents_cap);
+  FunASRFreeResult(r);
+  if (cache_io) {
+    std::string joined;
+    for (size_t i = 0; i < cache[1].size(); ++i) { if (i) joined.push_back('\n'); joined += cache[1][i]; }
+    CopyOut(joined.c_str(), cache_io, cache_cap);
+  }
+  return n;
+}
+// The VAD state machine fed in chunks (pf::host::StreamingVad): chunk_len[k] frames per Push, the last one flagged final.
+// out receives [start_ms, end_ms] pairs; returns the number of segments.
+int b200pf_host_vad_segments_streaming(const float* sil_prob, int n_frames, const int* chunk_len, int n_chunks, int max_end_sil_ms, int max_seg_ms,
+                                       float thres, int* out, int cap) {
+  pf::host::VadOptions vo;
+  vo.max_end_silence_ms = max_end_sil_ms; vo.max_single_segment_ms = max_seg_ms; vo.speech_noise_thres = thres;
+  pf::host::StreamingVad sv(vo);
+  int pos = 0, n_out = 0;
+  for (int k = 0; k < n_chunks; ++k) {
+    const int len = std::min(chunk_len[k], n_frames - pos);
+    const bool fin = k == n_chunks - 1;
+    for (const auto& sg : sv.Push(sil_prob + pos, len, fin)) {
+      if (n_out < cap) { out[2 * n_out] = sg.first; out[2 * n_out + 1] = sg.second; }
+      ++n_out;
+    }
+    pos += len;
+  }
+  return n_out;
+}
+int b200pf_host_expand_posteriors(const float* topk_logprob, const int32_t* topk_ids, int rows, int k, int vocab, float* dense) {
+  std::vector<float> d;
+  pf::host::ExpandPrunedPosteriors(topk_logprob, topk_ids, rows, k, vocab, &d);
+  memcpy(dense, d.data(), d.size() * sizeof(float));
+  return 0;
 }
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign) {
   std::vector<int> a;

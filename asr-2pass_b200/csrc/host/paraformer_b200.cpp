@@ -1,5 +1,10 @@
 #include "paraformer_b200.h"
 
+#include "logprob_adapter.h"
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+#include "wfst-decoder.h"   // funasr::WfstDecoder (onnxruntime/src/wfst-decoder.h:59-84)
+#endif
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,6 +45,14 @@ bool ParaformerB200::Init(const std::string& model_dir, std::string* err) {
   use_hotword_ = cfg.contextual != 0;
   has_timestamp_ = cfg.timestamp != 0;
   for (size_t i = 0; i < vocab_->tokens().size(); ++i) token_id_.emplace(vocab_->tokens()[i], (int)i);  // PhoneSet: first id wins
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+  // the reference's decoders read its own Vocab / PhoneSet (Paraformer::InitAsr, paraformer.cpp:36-40)
+  const std::string token_file = model_dir + "/tokens.json";
+  ref_vocab_.reset(new funasr::Vocab(token_file.c_str()));
+  ref_phone_set_.reset(new funasr::PhoneSet(token_file.c_str()));
+  phone_set_ = ref_phone_set_.get();
+  lm_vocab = nullptr;
+#endif
   return true;
 }
 
@@ -177,13 +190,52 @@ std::vector<std::vector<float>> ParaformerB200::CompileHotwordEmbedding(std::str
   return result;
 }
 
-std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg) {
+bool ParaformerB200::UseLmDecoder(void* wfst_decoder) const {
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+  return wfst_decoder != nullptr && lm_ != nullptr;
+#else
+  (void)wfst_decoder;
+  return false;   // the stand-alone shim has no LM decoder: FunASRWfstDecoderInit returns nullptr there
+#endif
+}
+
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+void ParaformerB200::InitLm(const std::string& lm_file, const std::string& lm_cfg_file, const std::string& lex_file,
+                            const std::string& lm_units_file) {
+  lm_ = std::shared_ptr<fst::Fst<fst::StdArc>>(fst::Fst<fst::StdArc>::Read(lm_file));
+  if (!lm_) { fprintf(stderr, "Failed to load lm file %s\n", lm_file.c_str()); return; }
+  lm_vocab = new funasr::Vocab(lm_cfg_file.c_str(), lex_file.c_str());
+  if (!lm_units_file.empty()) phone_set_ = new funasr::PhoneSet(lm_units_file.c_str());
+}
+#endif
+
+std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg, void* wfst_decoder) {
   std::vector<std::string> out(n_seg);
   last_ids_.assign(n_seg, std::vector<int>());
   for (int i = 0; i < n_seg; ++i) {
     const int cnt = r.token_counts[i];
     if (r.lfr_frames[i] <= 0) continue;  // empty features -> "" (paraformer.cpp:477-480)
     std::vector<int> ids(r.token_ids + r.token_offsets[i], r.token_ids + r.token_offsets[i] + cnt);
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+    if (UseLmDecoder(wfst_decoder) && r.topk_k > 0) {
+      // BeamSearch + FinalizeDecode (paraformer.cpp:565-578) on log-softmax rows rebuilt from the pruned posteriors
+      std::vector<float> dense;
+      const int V = b200pf_engine_vocab_size(engine_);
+      pf::host::ExpandPrunedPosteriors(r.topk_logprob + (size_t)r.token_offsets[i] * r.topk_k, r.topk_ids + (size_t)r.token_offsets[i] * r.topk_k,
+                                       cnt, r.topk_k, V, &dense);
+      funasr::WfstDecoder* dec = (funasr::WfstDecoder*)wfst_decoder;
+      out[i] = dec->Search(dense.data(), cnt, V);
+      if (has_timestamp_) {
+        std::vector<float> us_alphas(r.us_alphas + r.us_offsets[i], r.us_alphas + r.us_offsets[i + 1]);
+        std::vector<float> us_peaks(r.us_peaks + r.us_offsets[i], r.us_peaks + r.us_offsets[i + 1]);
+        out[i] = dec->FinalizeDecode(true, us_alphas, us_peaks);
+      } else {
+        out[i] = dec->FinalizeDecode();
+      }
+      last_ids_[i].swap(ids);
+      continue;
+    }
+#endif
     if (!has_timestamp_) {
       out[i] = vocab_->ToText(ids, language_);  // GreedySearch, paraformer.cpp:386-397
     } else {
@@ -240,9 +292,9 @@ bool ParaformerB200::StageSlot(int k, const int16_t* pcm, const int64_t* offsets
   return true;
 }
 
-bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out) {
-  std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_), us_offs(n + 1);
-  std::vector<float> us_a, us_p;
+bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder) {
+  std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_), us_offs(n + 1), tk_ids;
+  std::vector<float> us_a, us_p, tk_lp, tk_lse;
   b200pf_result r;
   memset(&r, 0, sizeof(r));
   r.token_counts = counts.data(); r.token_offsets = offs.data(); r.lfr_frames = frames.data();
@@ -252,8 +304,12 @@ bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out) {
     us_a.resize((size_t)3 * max_rows_); us_p.resize((size_t)3 * max_rows_);
     r.us_alphas = us_a.data(); r.us_peaks = us_p.data(); r.cap_us = (int64_t)3 * max_rows_;
   }
+  if (UseLmDecoder(wfst_decoder)) {   // the LM decoder reads pruned posteriors instead of greedy ids
+    tk_lp.resize((size_t)max_rows_ * B200PF_MAX_TOPK); tk_ids.resize((size_t)max_rows_ * B200PF_MAX_TOPK); tk_lse.resize((size_t)max_rows_);
+    r.topk_logprob = tk_lp.data(); r.topk_ids = tk_ids.data(); r.token_lse = tk_lse.data();
+  }
   if (b200pf_batch_collect(slots_[k].batch, &r, nullptr) != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
-  *out = Decode(r, n);
+  *out = Decode(r, n, wfst_decoder);
   return true;
 }
 
@@ -262,12 +318,22 @@ bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out) {
 // (paraformer.cpp:582-587).  Results keep the caller's order.
 std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
                                                 const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16,
-                                                const int64_t* len16) {
+                                                const int64_t* len16, void* wfst_decoder) {
   std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
   if (n_seg <= 0 || !engine_) return results;
   std::lock_guard<std::mutex> lock(mu_);
+  {  // pruned posteriors are only computed for calls that decode with the LM
+    const int want = UseLmDecoder(wfst_decoder) ? B200PF_MAX_TOPK : 0;
+    if (want != topk_on_) { b200pf_engine_set_option(engine_, "logprob_topk", want); topk_on_ = want; }
+  }
   struct Sub { int start, end; int64_t samples; };
   std::vector<Sub> subs;
+  // The reference's argument form -- float samples in pageable memory, 4 bytes each -- is copied by the driver through its own
+  // staging buffer at a fraction of the PCIe rate, and the calling thread waits for it.  Sub-batches are therefore capped well
+  // below the engine's capacity on this path, so that the copy of sub-batch i+1 runs while the GPU computes sub-batch i (one
+  // engine-sized batch would expose the whole copy: 708 MB for the configs[1] workload).  B200PF_F32_SUB_ROWS overrides.
+  static const int64_t f32_rows = getenv("B200PF_F32_SUB_ROWS") ? atoll(getenv("B200PF_F32_SUB_ROWS")) : 40960;
+  const int64_t row_cap = (!pcm && !seg16 && f32_rows > 0 && f32_rows < max_rows_) ? f32_rows : (int64_t)max_rows_;
   int start = 0;
   while (start < n_seg) {
     int64_t rows = 0, samples = 0;
@@ -276,7 +342,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
       const int64_t ns = seg16 ? len16[end] : (pcm ? offsets[end + 1] - offsets[end] : (int64_t)len[end]);
       const int T = b200pf_num_lfr_frames(ns);
       const int64_t r = T > 0 ? T + 1 : 0;
-      if (end > start && rows + r > max_rows_) break;
+      if (end > start && rows + r > row_cap) break;
       rows += r;
       samples += ns;
       ++end;
@@ -301,7 +367,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
     if (i + 1 < subs.size()) ok[i + 1] = stage(i + 1);                  // host copies while the GPU computes sub-batch i
     if (running) {
       std::vector<std::string> part;
-      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part))
+      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder))
         for (int k = 0; k < subs[i].end - subs[i].start; ++k) results[subs[i].start + k] = part[k];
     }
   }
@@ -311,8 +377,8 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
 std::vector<std::string> ParaformerB200::Forward(float** din, int* len, bool input_finished,
                                                  const std::vector<std::vector<float>>& hw_emb, void* wfst_decoder,
                                                  int batch_in) {
-  (void)input_finished; (void)wfst_decoder;
-  return RunAll(nullptr, nullptr, din, len, batch_in, hw_emb);
+  (void)input_finished;
+  return RunAll(nullptr, nullptr, din, len, batch_in, hw_emb, nullptr, nullptr, wfst_decoder);
 }
 
 std::string ParaformerB200::Forward(float* din, int len, bool input_finished, const std::vector<std::vector<float>>& hw_emb,

@@ -17,6 +17,19 @@
 #include "../../../include/b200pf.h"
 #include "text.h"
 
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+// Built INSIDE the reference tree: the base classes are the reference's own funasr::Model
+// (onnxruntime/include/model.h:13-46) and funasr::WfstDecodable (onnxruntime/src/wfst-decodable.h:17-28), so that
+// OfflineStream / TpassStream can hold a ParaformerB200 in their asr_handle and FunASRWfstDecoderInit's dynamic_cast
+// (funasrruntime.cpp:841) finds the decoder interface.  tests/test_boundary_cpu.py compiles this variant against the reference's
+// headers.
+#include "model.h"
+#include "wfst-decodable.h"
+namespace funasr_b200 {
+using Model = funasr::Model;
+}
+#define B200PF_MODEL_BASES public funasr::Model, public funasr::WfstDecodable
+#else
 namespace funasr_b200 {
 
 class Model {  // subset of funasr::Model used on the offline Paraformer path (model.h:13-46)
@@ -42,6 +55,12 @@ class Model {  // subset of funasr::Model used on the offline Paraformer path (m
   virtual int GetBatchSize() = 0;
 };
 
+}  // namespace funasr_b200
+#define B200PF_MODEL_BASES public Model
+#endif
+
+namespace funasr_b200 {
+
 // Host half of Paraformer::CompileHotwordEmbedding (paraformer.cpp:600-648): hotword string -> id matrix [n, B200PF_HOTWORD_LEN]
 // and lengths, blank row last.  Pure host code (pinned against the reference's compiled function, tests/test_host_cpu.py).
 void PackHotwords(const std::string& hotwords, const std::unordered_map<std::string, int>& token_id,
@@ -50,7 +69,7 @@ void PackHotwords(const std::string& hotwords, const std::unordered_map<std::str
 // SegDict::SegDict (seg_dict.cpp:19-38): "word \t piece piece ..." per line.
 void LoadSegDict(const std::string& path, std::unordered_map<std::string, std::vector<std::string>>* out);
 
-class ParaformerB200 : public Model {
+class ParaformerB200 : B200PF_MODEL_BASES {
  public:
   // device: CUDA ordinal; max_rows / max_segments: engine capacity (0 = defaults)
   explicit ParaformerB200(int device = 0, int max_rows = 0, int max_segments = 0);
@@ -98,13 +117,29 @@ class ParaformerB200 : public Model {
   void SetBatchSize(int batch_size) override { batch_size_ = batch_size; }
   int GetBatchSize() override { return batch_size_; }
 
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+  // funasr::WfstDecodable (wfst-decodable.h:17-28), as the reference's Paraformer implements it (paraformer.h:77-80): the
+  // reference's own Vocab / PhoneSet over the model directory's tokens.json; no LM is loaded here, so FunASRWfstDecoderInit
+  // builds the CtcPrefixDecoder branch (funasrruntime.cpp:843-850).
+  std::shared_ptr<fst::Fst<fst::StdArc>> GetLm() const override { return lm_; }
+  funasr::Vocab* GetVocab() const override { return ref_vocab_.get(); }
+  funasr::PhoneSet* GetPhoneSet() const override { return ref_phone_set_.get(); }
+  funasr::Vocab* GetLmVocab() const override { return lm_vocab; }
+  funasr::Vocab* GetVocab() override { return ref_vocab_.get(); }             // funasr::Model's non-const accessors (model.h:40-42)
+  funasr::PhoneSet* GetPhoneSet() override { return ref_phone_set_.get(); }
+  // Paraformer::InitLm (paraformer.cpp:156-176): TLG.fst + lexicon.  With an LM loaded, Forward(..., wfst_decoder) feeds the
+  // reference's own WfstDecoder::Search with rows rebuilt from the engine's pruned posteriors (logprob_adapter.h) instead of
+  // the greedy ids -- the branch at paraformer.cpp:565-578.
+  void InitLm(const std::string& lm_file, const std::string& lm_cfg_file, const std::string& lex_file, const std::string& lm_units_file) override;
+#endif
+
   b200pf_engine* engine() { return engine_; }
   pf::host::Detokenizer* vocab() { return vocab_.get(); }
   // token ids / CIF fire frames of the last Forward on this thread's call (debug / tests)
   const std::vector<std::vector<int>>& last_ids() const { return last_ids_; }
 
  private:
-  std::vector<std::string> Decode(const b200pf_result& r, int n_seg);
+  std::vector<std::string> Decode(const b200pf_result& r, int n_seg, void* wfst_decoder);
   // engine-sized sub-batches through the C ABI, double buffered: pcm16 (offsets) or float (din/len)
   struct Slot {
     b200pf_batch* batch = nullptr;
@@ -114,10 +149,11 @@ class ParaformerB200 : public Model {
   };
   bool StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
                  const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr, const int64_t* len16 = nullptr);
-  bool CollectSlot(int k, int n, std::vector<std::string>* out);
+  bool CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder);
   std::vector<std::string> RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
                                   const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr,
-                                  const int64_t* len16 = nullptr);
+                                  const int64_t* len16 = nullptr, void* wfst_decoder = nullptr);
+  bool UseLmDecoder(void* wfst_decoder) const;   // an LM is loaded and the caller passed a decoder handle (paraformer.cpp:565)
 
   int device_, max_rows_, max_segments_;
   b200pf_engine* engine_ = nullptr;
@@ -129,9 +165,14 @@ class ParaformerB200 : public Model {
   std::mutex mu_;  // Forward is called concurrently by decoder threads on one handle (websocket-server.cpp:387-403)
   std::vector<std::vector<int>> last_ids_;
   bool use_hotword_ = false, has_timestamp_ = false;
+  int topk_on_ = 0;   // engine option "logprob_topk" as this object last set it
   int d_model_ = 512;
   std::unordered_map<std::string, std::vector<std::string>> seg_dict_;
   std::unordered_map<std::string, int> token_id_;  // PhoneSet::String2Id (phone-set.cpp:38-68)
+#ifdef B200PF_WITH_REFERENCE_HEADERS
+  std::unique_ptr<funasr::Vocab> ref_vocab_;
+  std::unique_ptr<funasr::PhoneSet> ref_phone_set_;
+#endif
 };
 
 }  // namespace funasr_b200

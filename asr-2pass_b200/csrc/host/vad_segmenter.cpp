@@ -160,5 +160,54 @@ std::vector<std::pair<int, int>> SegmentVad(const float* sil_prob, int n_frames,
   return segs;
 }
 
+// ---- the same machine fed incrementally (the 2-pass stream: FsmnVadOnline + Audio::Split, audio.cpp:1242-1370) ----
+struct StreamingVad::Impl {
+  VadOptions opt;
+  Machine m;
+  int next_frame = 0;
+  size_t reported = 0;     // segments of m.out already handed to the caller
+  explicit Impl(const VadOptions& o) : opt(o), m(opt) {}
+};
+
+StreamingVad::StreamingVad(const VadOptions& opt) : impl_(new Impl(opt)) {}
+StreamingVad::~StreamingVad() { delete impl_; }
+
+void StreamingVad::Reset() {
+  const VadOptions o = impl_->opt;
+  delete impl_;
+  impl_ = new Impl(o);
+}
+
+void StreamingVad::SetOptions(int max_end_silence_ms, int max_single_segment_ms) {
+  impl_->opt.max_end_silence_ms = max_end_silence_ms;       // Machine holds a reference to impl_->opt
+  impl_->opt.max_single_segment_ms = max_single_segment_ms;
+}
+
+int StreamingVad::frames() const { return impl_->next_frame; }
+
+int StreamingVad::open_start_ms() const {
+  const Machine& m = impl_->m;
+  if (!m.out.empty() && !m.out.back().closed && impl_->reported < m.out.size()) return m.out.back().start_ms;
+  return -1;
+}
+
+std::vector<std::pair<int, int>> StreamingVad::Push(const float* sil_prob, int n_frames, bool last_is_final) {
+  Machine& m = impl_->m;
+  for (int i = 0; i < n_frames; ++i) {
+    const int f = impl_->next_frame++;
+    m.Step(f, FrameIsSpeech(sil_prob[i], impl_->opt.speech_noise_thres), last_is_final && i == n_frames - 1);
+  }
+  std::vector<std::pair<int, int>> segs;
+  while (impl_->reported < m.out.size() && m.out[impl_->reported].closed) {
+    segs.emplace_back(m.out[impl_->reported].start_ms, m.out[impl_->reported].end_ms);
+    ++impl_->reported;
+  }
+  if (last_is_final) {
+    // an unclosed tail (a start confirmed on the very last frame) is dropped, as in SegmentVad
+    impl_->reported = m.out.size();
+  }
+  return segs;
+}
+
 }  // namespace host
 }  // namespace pf

@@ -21,5 +21,26 @@ struct VadOptions {
 // sil_prob[t] = probability of pdf 0 (silence) of 10 ms frame t.  Returns [start_ms, end_ms) pairs in time order.
 std::vector<std::pair<int, int>> SegmentVad(const float* sil_prob, int n_frames, const VadOptions& opt);
 
+// The same state machine fed chunk by chunk -- what the 2-pass stream does (FsmnVadOnline::Forward per chunk, Audio::Split,
+// audio.cpp:1242-1370): Push() takes the silence probabilities of the NEXT frames and returns the segments that closed on
+// them; the frame flagged final closes an open segment like the last frame of SegmentVad.  Fed any chunking of the same
+// scores it returns, in total, exactly SegmentVad's segments (tests/test_vad.py).
+class StreamingVad {
+ public:
+  explicit StreamingVad(const VadOptions& opt);
+  ~StreamingVad();
+  StreamingVad(const StreamingVad&) = delete;
+  StreamingVad& operator=(const StreamingVad&) = delete;
+  std::vector<std::pair<int, int>> Push(const float* sil_prob, int n_frames, bool last_is_final);
+  void SetOptions(int max_end_silence_ms, int max_single_segment_ms);   // VadModel::SetConfig, per call like the reference
+  void Reset();                 // a new stream (Audio::ResetIndex after input_finished)
+  int frames() const;           // frames consumed so far
+  int open_start_ms() const;    // start of the segment currently open, or -1
+
+ private:
+  struct Impl;
+  Impl* impl_;
+};
+
 }  // namespace host
 }  // namespace pf

@@ -4,14 +4,20 @@
 
 Workload = BASELINE.json configs[1]: 1024 synthetic VAD segments of 2-20 s (seeded speech-like noise),
 length-sorted and packed into batches, random-init Paraformer-large weights (215.8 M parameters).
-One "step" = one pass of the hot path over the whole workload (every rank takes an equal share of the
-length-sorted segments; segments are independent, so there is no collective on the data path).
+One "step" = one pass of the hot path over the whole workload (every rank runs the full per-GPU workload;
+segments are independent, so there is no collective on the data path).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--segments S]
 
-Prints ONE JSON line (see the keys below).  `value` is measured with the PCM already resident in HBM;
-`e2e` goes through the C ABI with pinned HOST buffers, host->device PCM copies and device->host result
-copies inside the timed region.
+Prints ONE JSON line.  Keys beyond the contract:
+  value               PCM already resident in HBM (CUDA events)
+  e2e                 through the C ABI with pinned HOST int16 buffers, H2D + D2H inside the timed region
+  e2e_model_forward   through the reference-facing funasr::Model::Forward(float**, int*, ...) of the host library, pageable
+                      float buffers in, text strings out (what a reference caller passes and receives)
+  parity              the timed CUDA path checked against the fp32 oracle on the cpu_baseline sample (asr-2pass_b200/parity.py)
+  cpu_baseline        the oracle port on the host cores, fixed sample, fp32 and the int8 stand-in, per-core figures
+  config4 / config5   the PRODUCT's multi-GPU path (one handle, per-GPU queues: MultiGpuParaformer) driven by rank 0 over all N
+                      GPUs on BASELINE.json configs[3] (1 h stream, arrival order) and configs[4] (256 x 60 s): strong scaling
 """
 import argparse
 import importlib
@@ -31,6 +37,8 @@ if ROOT not in sys.path:
 
 METRIC = "RTFx (audio s/s) Paraformer-large offline batched"
 UNIT = "audio_s/s"
+CPU_SAMPLE = 96          # segments of the fixed cpu_baseline / parity sample (the same indices on every box)
+PARITY_TENSORS = 24      # of those, how many also carry encoder output and logits for the tensor comparisons
 
 
 def rank_env():
@@ -45,6 +53,38 @@ def load_peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def lfr_frames(n):
+    """T of a segment with n samples (feature-window.cc:73-87 snip_edges, paraformer.cpp:424) -- host arithmetic."""
+    nfb = 0 if n < 400 else 1 + (int(n) - 400) // 160
+    return (nfb + 5) // 6 if nfb > 0 else 0
+
+
+def make_batches(lens, max_rows, max_segments, capi=None):
+    """Length-sorted (ascending, as Audio::CutSplit sorts, audio.cpp:1233-1238) greedy packing into batches of
+    at most max_rows packed rows."""
+    order = np.argsort(lens, kind="stable")
+    batches, cur, rows = [], [], 0
+    for i in order:
+        T = lfr_frames(int(lens[i]))
+        r = T + 1 if T > 0 else 0
+        if cur and (rows + r > max_rows or len(cur) >= max_segments):
+            batches.append(cur)
+            cur, rows = [], 0
+        cur.append(int(i))
+        rows += r
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+def workload_config(args, lens, workload):
+    """The `config` object: only what defines the workload, so that both arms print the same one."""
+    return dict(workload=workload, segments=int(len(lens)), audio_s_per_gpu=float(lens.sum()) / 16000.0,
+                max_rows=args.max_rows, batches=len(make_batches(lens, args.max_rows, 4096)),
+                l2="inputs+weights per step (>= 790 MB) exceed the 126 MB L2; no explicit flush",
+                sharding="each rank runs the full per-GPU workload (weak scaling), no collective")
+
+
 # ----------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port (fp32 PyTorch restatement + C front end), reference harness pattern:
 # P worker processes x 1 intra-op thread, each pulling segments from a shared index
@@ -54,23 +94,39 @@ _CPU = {}
 
 
 def _cpu_worker(args):
-    idx_list, = args
+    idx_list, which, keep = args
     import torch
     torch.set_num_threads(1)
     from oracle import frontend as F
     from oracle import paraformer_ref as R
+    W = _CPU["Wq"] if which == "int8" else _CPU["W"]
     t0 = time.time()
-    n_tok = 0
+    outs = []
     for i in idx_list:
         pcm = _CPU["segs"][i]
         feats = F.lfr_cmvn(F.fbank(pcm), _CPU["means"], _CPU["vars"])
-        o = R.forward(feats, _CPU["W"], _CPU["pc"], want_taps=False)
-        n_tok += len(o["ids"])
-    return time.time() - t0, n_tok
+        o = R.forward(feats, W, _CPU["pc"], want_taps=False)
+        if keep:
+            lg = o["logits"].numpy()
+            top2 = np.sort(lg, axis=1)[:, -2:] if lg.shape[0] else np.zeros((0, 2), np.float32)
+            r = dict(i=i, T=int(feats.shape[0]), alphas=o["alphas"].numpy(), fires=o["fires"].numpy(), ids=np.asarray(o["ids"], np.int32),
+                     top_gap=(top2[:, 1] - top2[:, 0]).astype(np.float32), logit_absmax=float(np.abs(lg).max()) if lg.size else 0.0)
+            if i < PARITY_TENSORS:
+                r["enc"] = o["enc"].numpy()
+                r["logits"] = lg
+            outs.append(r)
+    return time.time() - t0, outs
 
 
-def cpu_baseline(synth, cfg, W, means, vars_, seg_pcm16, budget_s=20.0, procs=None):
-    """Times the oracle on a bounded sample of the workload.  Must run BEFORE CUDA is initialised (fork)."""
+def sample_indices(lens):
+    """The fixed sample: CPU_SAMPLE segments spread evenly over the length-sorted workload (identical on every box)."""
+    order = np.argsort(lens, kind="stable")
+    return [int(order[k]) for k in np.linspace(0, len(lens) - 1, num=min(len(lens), CPU_SAMPLE)).astype(int)]
+
+
+def cpu_baseline(cfg, W, means, vars_, seg_pcm16, procs=None, int8=True, keep=True):
+    """Times the oracle on the fixed sample (fp32, then the int8 stand-in on the first half of it) and returns its outputs for
+    the parity check.  Must run BEFORE CUDA is initialised (fork)."""
     import multiprocessing as mp
 
     import torch
@@ -79,31 +135,41 @@ def cpu_baseline(synth, cfg, W, means, vars_, seg_pcm16, budget_s=20.0, procs=No
     F.lib()
     P = procs or min(os.cpu_count() or 1, 32)
     pc = R.PfConfig.from_dict(cfg)
-    _CPU.update(W={k: torch.from_numpy(v) for k, v in W.items()}, pc=pc, means=means, vars=vars_)
-    # probe one segment to size the sample to ~budget_s of work per worker
-    probe = seg_pcm16[len(seg_pcm16) // 2].astype(np.float32) / np.float32(32768)
-    _CPU["segs"] = [probe]
-    torch.set_num_threads(1)
-    t, _ = _cpu_worker(([0],))
-    per_audio_s = t / (len(probe) / 16000.0)
-    n_per = 1
-    order = np.linspace(0, len(seg_pcm16) - 1, num=min(len(seg_pcm16), 8 * P)).astype(int)  # spread over lengths
-    mean_len = float(np.mean([len(seg_pcm16[i]) for i in order])) / 16000.0
-    n_per = max(1, int(budget_s / max(per_audio_s * mean_len, 1e-6)))
-    take = order[: min(len(order), n_per * P)]
-    _CPU["segs"] = [seg_pcm16[i].astype(np.float32) / np.float32(32768) for i in take]
-    audio_s = sum(len(s) for s in _CPU["segs"]) / 16000.0
-    chunks = [list(range(w, len(take), P)) for w in range(P)]
-    chunks = [c for c in chunks if c]
+    Wt = {k: torch.from_numpy(v) for k, v in W.items()}
+    # shuffle the (length-sorted) sample with a fixed seed: the interleaved assignment below then gives every worker the same mix
+    perm = np.random.default_rng(7).permutation(len(seg_pcm16))
+    _CPU.update(W=Wt, pc=pc, means=means, vars=vars_, segs=[seg_pcm16[j].astype(np.float32) / np.float32(32768) for j in perm])
+    if int8:
+        _CPU["Wq"] = R.quantize_dynamic_int8(Wt)
     ctx = mp.get_context("fork")
-    t0 = time.time()
-    with ctx.Pool(len(chunks)) as pool:
-        res = pool.map(_cpu_worker, [(c,) for c in chunks])
-    wall = time.time() - t0
-    max_thread = max(r[0] for r in res)  # reference: total_time = max over threads of summed inference time
-    return dict(value=audio_s / max_thread, unit=UNIT, cores=len(chunks), kind="port",
-                sample="%d segments (%.0f audio-s) of the workload, fp32 PyTorch restatement + C front end, %d procs x 1 thread, wall %.1fs"
-                       % (len(take), audio_s, len(chunks), wall))
+    n = len(seg_pcm16)
+
+    def run(which, count, keep_out):
+        chunks = [c for c in (list(range(w, count, P)) for w in range(P)) if c]
+        t0 = time.time()
+        with ctx.Pool(len(chunks)) as pool:
+            res = pool.map(_cpu_worker, [(c, which, keep_out) for c in chunks])
+        wall = time.time() - t0
+        audio = sum(len(_CPU["segs"][i]) for i in range(count)) / 16000.0
+        max_thread = max(r[0] for r in res)   # reference: total_time = max over threads of summed inference time
+        outs = [None] * len(seg_pcm16)
+        for r in res:
+            for o in r[1]:
+                outs[int(perm[o["i"]])] = o     # back to the caller's order
+        return audio / max_thread, len(chunks), audio, wall, outs
+
+    v32, cores, audio32, wall32, outs = run("fp32", n, keep)
+    cb = dict(value=v32, unit=UNIT, cores=cores, kind="port", rtfx_per_core=v32 / cores,
+              sample="fixed sample: %d segments (%.0f audio-s) spread evenly over the length-sorted workload; fp32 PyTorch restatement + C "
+                     "front end, %d procs x 1 thread (decoder-thread-num = %d, intra-op 1), wall %.1fs" % (n, audio32, cores, cores, wall32))
+    if int8:
+        n8 = max(1, n // 2)
+        v8, c8, audio8, wall8, _ = run("int8", n8, False)
+        cb["int8"] = dict(value=v8, unit=UNIT, cores=c8, rtfx_per_core=v8 / c8, kind="stand-in",
+                          sample="%d segments of the same sample (%.0f audio-s), wall %.1fs; STAND-IN for the reference's deployed "
+                                 "model_quant.onnx: PyTorch dynamic int8 Linear on every projection of the port (onnxruntime and the "
+                                 "exported graph are absent here), same harness" % (n8, audio8, wall8))
+    return cb, outs
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -136,22 +202,62 @@ def clocks_summary(samples):
                 reasons=sorted(reasons))
 
 
-def make_batches(lens, max_rows, max_segments, capi):
-    """Length-sorted (ascending, as Audio::CutSplit sorts, audio.cpp:1233-1238) greedy packing into batches of
-    at most max_rows packed rows."""
-    order = np.argsort(lens, kind="stable")
-    batches, cur, rows = [], [], 0
-    for i in order:
-        T = capi.lib().b200pf_num_lfr_frames(int(lens[i]))
-        r = T + 1 if T > 0 else 0
-        if cur and (rows + r > max_rows or len(cur) >= max_segments):
-            batches.append(cur)
-            cur, rows = [], 0
-        cur.append(int(i))
-        rows += r
-    if cur:
-        batches.append(cur)
-    return batches
+def make_stream(seconds=3600.0, seed=4242):
+    """configs[3]: speech bursts U[2,20] s separated by silences U[0.3,1.0] s; boundaries = the generator's ground truth."""
+    rng = np.random.default_rng(seed)
+    t, segs = 0.0, []
+    while True:
+        t += float(rng.uniform(0.3, 1.0))
+        d = round(float(rng.uniform(2.0, 20.0)) * 100.0) / 100.0
+        if t + d > seconds:
+            break
+        segs.append((int(t * 16000), int((t + d) * 16000)))
+        t += d
+    return segs
+
+
+def product_multigpu(capi, synth, model_dir, n_gpus, steps):
+    """The product's own multi-GPU path: ONE handle (FunOfflineInit with devices = 0..N-1 -> MultiGpuParaformer: per-GPU worker,
+    engine and queue, longest-processing-time-first assignment, no collective) driven from this process over all N GPUs with
+    host int16 PCM in and text out.  Strong scaling: the job is fixed, N grows."""
+    out = {}
+    h = capi.OfflineHandle(model_dir, max_rows=65536, max_segments=4096, batch_size=4096, devices=list(range(n_gpus)))
+    # configs[3]: 1 h stream, VAD segments in arrival order
+    segs = make_stream()
+    pcm = np.zeros(3600 * 16000, np.int16)
+    blk = None
+    for k, (b, e) in enumerate(segs):
+        if k % 16 == 0:
+            blk = synth.make_audio(21 * 16000 * 16, 77 + k)
+        o = (k % 16) * 21 * 16000
+        pcm[b:e] = blk[o:o + (e - b)]
+    sb, se = [s[0] for s in segs], [s[1] for s in segs]
+    h.infer_segments(pcm, sb[:32], se[:32])
+    h.infer_segments(pcm, sb, se)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        text = h.infer_segments(pcm, sb, se)
+    dt = (time.perf_counter() - t0) / steps
+    out["config4"] = dict(workload="configs[3]: 1 h synthetic stream, %d ground-truth VAD segments (%.0f s of speech) in arrival order through "
+                                   "FunOfflineInferSegmentsB200 on one handle" % (len(segs), sum(e - b for b, e in segs) / 16000.0),
+                          n_gpus=n_gpus, wall_s=dt, value=3600.0 / dt, unit="stream_s/s", chars=len(text), scaling="strong",
+                          segments_per_gpu=h.segments_per_device())
+    del pcm
+    # configs[4]: 256 segments x 60 s (T = 1000 LFR frames)
+    one = synth.make_audio(960000, 4321)
+    pcm5 = np.tile(one, 256)
+    b5 = [i * 960000 for i in range(256)]
+    e5 = [(i + 1) * 960000 for i in range(256)]
+    h.infer_segments(pcm5, b5, e5)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        text = h.infer_segments(pcm5, b5, e5)
+    dt = (time.perf_counter() - t0) / steps
+    out["config5"] = dict(workload="configs[4]: 256 segments x 60 s (T = 1000) through FunOfflineInferSegmentsB200 on one handle",
+                          n_gpus=n_gpus, wall_s=dt, value=256 * 60.0 / dt, unit=UNIT, chars=len(text), scaling="strong",
+                          segments_per_gpu=h.segments_per_device())
+    h.close()
+    return out
 
 
 def main():
@@ -172,16 +278,18 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--segments", type=int, default=1024)
     ap.add_argument("--max-rows", type=int, default=int(os.environ.get("B200PF_MAX_ROWS", "196608")))
+    ap.add_argument("--prec", default=None, choices=["fp16", "bf16"], help="operand format (default: the library's, fp16)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2 (default, the bench line): BASELINE.json configs[1]; config5: 32 segments x 60 s per GPU "
                          "(configs[4]: 256 x 60 s over 8 GPUs, T = 1000 LFR frames) - an extra measurement, not the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="ignored (kept for old command lines): the CPU sample is fixed")
+    ap.add_argument("--no-multigpu-product", action="store_true")
     args = ap.parse_args()
     rank, local, world = rank_env()
     synth = importlib.import_module("asr-2pass_b200.synth")
 
-    # ---- workload (identical on every rank; each rank then takes its share) ----
+    # ---- workload (identical on every rank) ----
     lens = synth.segment_lengths(args.segments)
     cfg, W = synth.make_weights()
     means, vars_ = synth.make_cmvn()
@@ -190,26 +298,29 @@ def main():
         args.segments = 32
         lens = np.full(32, 960000, np.int64)
         workload = "configs[4]: max-length stress, 32 segments x 60 s per GPU (256 over 8 GPUs), T = 1000 LFR frames"
+    config = workload_config(args, lens, workload)
 
     if args.impl == "reference":
         # The reference's own CPU implementation cannot be built or installed here (its neural graph lives in an
         # external model.onnx executed by a stripped libonnxruntime), so this arm times the oracle
-        # port of the same path on the host cores, as the tier framing prescribes.
+        # port of the same path on the host cores, as the tier framing prescribes: every step = the fixed sample.
         if rank != 0:
             return
         pcm, offs = synth.make_segments(args.segments)
-        segs = [pcm[offs[i]:offs[i + 1]] for i in range(args.segments)]
+        idx = sample_indices(lens)
+        segs = [pcm[offs[i]:offs[i + 1]] for i in idx]
         vals = []
         for step in range(args.warmup + args.steps):
-            cb = cpu_baseline(synth, cfg, W, means, vars_, segs, budget_s=max(2.0, args.cpu_budget / max(1, args.steps)))
+            cb, _ = cpu_baseline(cfg, W, means, vars_, segs, int8=(step == args.warmup + args.steps - 1), keep=False)
             if step >= args.warmup:
                 vals.append(cb)
         v = float(np.mean([c["value"] for c in vals]))
         cb = vals[-1]
         cb["value"] = v
+        cb["rtfx_per_core"] = v / cb["cores"]
         emit(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                   ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                  data="synthetic", impl="reference", config=dict(workload=workload), cpu_baseline=cb,
+                  data="synthetic", impl="reference", config=config, cpu_baseline=cb,
                   e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0)))
         return
 
@@ -219,10 +330,10 @@ def main():
         one = synth.make_audio(960000, 4321)
         pcm = np.tile(one, 32)
         args.no_cpu_baseline = True
-    cb = None
+    cb, oracle_outs, sample = None, None, None
     if rank == 0 and world == 1 and args.gpus == 1 and not args.no_cpu_baseline:
-        segs = [pcm[offs[i]:offs[i + 1]] for i in range(args.segments)]
-        cb = cpu_baseline(synth, cfg, W, means, vars_, segs, budget_s=args.cpu_budget)  # before CUDA init (fork)
+        sample = sample_indices(lens)
+        cb, oracle_outs = cpu_baseline(cfg, W, means, vars_, [pcm[offs[i]:offs[i + 1]] for i in sample])  # before CUDA init (fork)
 
     import torch
     import torch.distributed as dist
@@ -230,8 +341,10 @@ def main():
     if capi.device_count() < 1:
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")
 
     # weak scaling: every rank processes the full per-GPU workload (its own copy of the 1024 segments,
     # differently seeded would change nothing for timing); whole-job audio = world x per-rank audio.
@@ -239,10 +352,11 @@ def main():
     mf = importlib.import_module("asr-2pass_b200.modelfile")
     mf.write_model_dir(tmp, cfg, W, means, vars_, synth.make_tokens(int(cfg["vocab"])))
     del W
-    eng = capi.Engine(tmp, device=local, max_rows=args.max_rows, max_segments=4096)
+    eng = capi.Engine(tmp, device=local, max_rows=args.max_rows, max_segments=4096, prec=args.prec)
+    dtype = "fp16" if eng.cfg.precision == capi.PREC_FP16 else "bf16"
     if os.environ.get("B200PF_OVERLAP"):
         eng.set_option("overlap", int(os.environ["B200PF_OVERLAP"]))
-    groups = make_batches(lens, args.max_rows, 4096, capi)
+    groups = make_batches(lens, args.max_rows, 4096)
     audio_s = float(lens.sum()) / 16000.0
 
     # per-batch contiguous pinned host PCM (length-sorted order) and device-resident copies
@@ -337,13 +451,79 @@ def main():
 
     h2d = int(sum(hp.numel() * 2 for hp in host_pcm))
     n_tok = int(sum(r["n_tokens"] for r in results))
-    d2h = int(sum((2 * len(g) + 1) * 4 for g in groups) + 2 * 4 * sum(
-        sum((capi.lib().b200pf_num_lfr_frames(int(lens[i])) + 1) for i in g) for g in groups))
+    d2h = int(sum((2 * len(g) + 1) * 4 for g in groups) + 2 * 4 * sum(sum(lfr_frames(int(lens[i])) + 1 for i in g) for g in groups))
+
+    # ---- leg 3 (rank 0, N = 1): the reference-facing Model::Forward(float**, int*) of the host library: pageable float in, text out ----
+    mf_leg = None
+    if rank == 0 and world == 1:
+        for b in batches_b:
+            b.close()
+        h = capi.OfflineHandle(tmp, device=local, max_rows=65536, max_segments=4096, batch_size=4096)
+        order = np.argsort(lens, kind="stable")      # the reference sorts the VAD segments by length before Forward (audio.cpp:1233-1238)
+        fsegs = [pcm[offs[i]:offs[i + 1]].astype(np.float32) / np.float32(32768) for i in order]
+        h.model_forward(fsegs[:64])
+        h.model_forward(fsegs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            texts = h.model_forward(fsegs)
+        dt = (time.perf_counter() - t0) / args.steps
+        mf_leg = dict(value=audio_s / dt, unit=UNIT, ms_per_step=dt * 1e3, h2d_bytes_per_step=int(sum(len(s) * 4 for s in fsegs)),
+                      d2h_bytes_per_step=d2h, strings=sum(1 for t in texts if t),
+                      api="funasr::Model::Forward(float** din, int* len, ...) on one handle: pageable float host buffers in, text out")
+        h.close()
+        del fsegs
+
+    # ---- parity of the timed path on the cpu_baseline sample (rank 0, N = 1) ----
+    parity = None
+    if oracle_outs is not None:
+        P = importlib.import_module("asr-2pass_b200.parity")
+        engp = capi.Engine(tmp, device=local, max_rows=32768, max_segments=256, prec=args.prec)
+        engp.set_option("taps", 1)
+        segs = [pcm[offs[i]:offs[i + 1]] for i in sample]
+        so = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int64)
+        bp = capi.Batch(engp, int(so[-1]) + 64)
+        rp = bp.forward_s16(np.concatenate(segs), so)
+        stats = P.new_stats()
+        for k, o in enumerate(oracle_outs):
+            s, e = rp["token_offsets"][k], rp["token_offsets"][k + 1]
+            P.compare_segment(o, int(rp["lfr_frames"][k]), rp["token_ids"][s:e], rp["fire_frames"][s:e], stats,
+                              enc=bp.tap("enc", k) if "enc" in o else None, alphas=bp.tap("alphas", k),
+                              logits=bp.tap("logits", k) if "logits" in o else None, logit_tol=1e-2, strict=False)
+        parity = P.summarize(stats)
+        parity["tolerances"] = dict(enc_rel=1e-2, logit_rel=1e-2, note="ids may differ only where the oracle's top-1 margin over the GPU's pick is "
+                                    "<= 2e-2 * max|logit|; a fire may move one frame only inside the accumulated alpha deviation")
+        parity["reference"] = ("fp32 oracle (oracle/paraformer_ref.py) on the cpu_baseline sample; encoder output and logits compared on "
+                               "%d segments of it" % stats["logit_segments"])
+        # and the ids of the TIMED batches equal the parity batch's (the engine is batch invariant)
+        pos = {}
+        for g, r in zip(groups, results):
+            for k, i in enumerate(g):
+                pos[i] = r["token_ids"][r["token_offsets"][k]:r["token_offsets"][k + 1]]
+        parity["timed_batches_equal_parity_batch"] = bool(all(np.array_equal(pos[i], rp["token_ids"][rp["token_offsets"][k]:rp["token_offsets"][k + 1]])
+                                                              for k, i in enumerate(sample)))
+        bp.close()
+        engp.close()
 
     t = torch.tensor([ms_resident, t_e2e * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_resident, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- the product's multi-GPU path, driven by rank 0 over all N GPUs while the other ranks wait on the CPU ----
+    for b in batches:
+        b.close()
+    eng.close()
+    torch.cuda.synchronize()
+    multi = None
+    if world > 1:
+        dist.barrier(group=cpu_group)         # every rank has released its engine; waiting ranks hold no GPU work from here on
+    if rank == 0 and not args.no_multigpu_product and args.workload == "config2":
+        try:
+            multi = product_multigpu(capi, synth, tmp, world, max(2, min(args.steps, 3)))
+        except Exception as ex:   # reported, never hidden
+            multi = dict(multigpu_product_error=str(ex))
+    if world > 1:
+        dist.barrier(group=cpu_group)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,22 +551,27 @@ def main():
         v["frac"] = v["achieved"] / (tflops_peak if v["unit"] == "TFLOP/s" else hbm)
     out = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-        data="synthetic",
-        config=dict(workload=workload, audio_s_per_gpu=audio_s, batches=len(batches), max_rows=args.max_rows,
-                    l2="inputs+weights per step (>= 790 MB) exceed the 126 MB L2; no explicit flush",
-                    tokens=n_tok, sharding="each rank runs the full per-GPU workload (weak scaling), no collective"),
+        ms_per_step=ms_resident, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dtype,
+        dtype_note="16-bit tensor-core operands (tcgen05 kind::f16: IEEE fp16 by default, bf16 with --prec bf16 -- same rate), fp32 "
+                   "accumulation, residual streams, LayerNorm statistics, softmax and CIF",
+        data="synthetic", config=config, tokens_per_step=n_tok,
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
         gpu_launches=int(launches * args.steps),
         roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all %d GEMM launches of a step)" % (g["launches"] // args.steps), achieved=gemm_tf, peak=tflops_peak, unit="TFLOP/s",
                       frac=gemm_tf / tflops_peak, traffic=traffic,
-                      note="sum of 2*M*N*K over the GEMM launches of a step / their CUDA-event time, vs %s sustained bf16 peak; "
+                      note="sum of 2*M*N*K over the GEMM launches of a step / their CUDA-event time, vs %s sustained 16-bit dense peak; "
                            "whole step: %.1f TFLOP/s (%.3f of peak)" % (which, step_tf, step_tf / tflops_peak)),
         kernels=kernels,
         clocks=clocks_summary(samples),
     )
+    if mf_leg is not None:
+        out["e2e_model_forward"] = mf_leg
+    if parity is not None:
+        out["parity"] = parity
     if cb is not None:
         out["cpu_baseline"] = cb
+    if multi is not None:
+        out.update(multi)
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -42,6 +42,23 @@ void* b200pf_host_offline_init_kv(const char* const* keys, const char* const* va
 /* FunOfflineInferBuffer -> FunASRGetResult / FunASRGetStamp / FunASRGetStampSents (stamp and stamp_sents may be NULL). */
 int b200pf_host_offline_infer_full(void* h, const char* buf, int n_bytes, int vad_tail_sil, int vad_max_len, char* text, int text_cap,
                                    char* stamp, int stamp_cap, char* stamp_sents, int sents_cap);
+/* 2-pass stream (funasrruntime.h:121-132; the offline leg of FunTpassInferBuffer, funasrruntime.cpp:568-639).  Keys as FunTpassInit
+ * reads them ("model-dir", "vad-dir", "punc-dir", ...).  b200pf_host_tpass_infer = one FunTpassInferBuffer call on one connection:
+ * mode 0 = ASR_OFFLINE, 1 = ASR_ONLINE, 2 = ASR_TWO_PASS; cache_io = punc_cache[1] as '\n'-joined words, in and out. */
+void* b200pf_host_tpass_init_kv(const char* const* keys, const char* const* values, int n);
+void* b200pf_host_tpass_online_init(void* tpass);
+void b200pf_host_tpass_uninit(void* tpass);
+void b200pf_host_tpass_online_uninit(void* online);
+int b200pf_host_tpass_infer(void* tpass, void* online, const char* buf, int n_bytes, int input_finished, int mode, int vad_tail_sil,
+                            int vad_max_len, char* cache_io, int cache_cap, char* msg, int msg_cap, char* tpass_msg, int tpass_cap, char* stamp,
+                            int stamp_cap, char* stamp_sents, int sents_cap);
+/* pf::host::StreamingVad fed chunk_len[k] frames per call, the last chunk final: [start_ms, end_ms] pairs, any chunking of the same
+ * scores gives b200pf_host_vad_segments' result. */
+int b200pf_host_vad_segments_streaming(const float* sil_prob, int n_frames, const int* chunk_len, int n_chunks, int max_end_sil_ms, int max_seg_ms,
+                                       float thres, int* out, int cap);
+/* pf::host::ExpandPrunedPosteriors: b200pf_result.topk_logprob / topk_ids [rows, k] -> dense log-softmax rows [rows, vocab] in the
+ * layout WfstDecoder::Search (wfst-decoder.cpp:27-57) and CtcPrefixDecoder::CtcSearch (ctc-prefix-decoder.cpp:157) read. */
+int b200pf_host_expand_posteriors(const float* topk_logprob, const int32_t* topk_ids, int rows, int k, int vocab, float* dense);
 /* The pool's longest-processing-time-first assignment of segments (sample counts) to n_dev queues; host arithmetic only. */
 int b200pf_host_partition(const int* len, int n, int n_dev, int* assign);
 /* Segments decoded per device so far; returns the number of devices (0 for a single-GPU handle). */

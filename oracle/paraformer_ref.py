@@ -170,10 +170,41 @@ def _ln(x, W, p, eps):
 
 
 def _lin(x, W, p, emu, bias=True):
+    q = W.get(p + ".__int8__")
+    if q is not None:          # int8 stand-in (quantize_dynamic_int8): the module carries its own bias
+        return q(x)
     y = _rb(x, emu) @ _rb(W[p + ".weight"], emu).t()
     if bias and (p + ".bias") in W:
         y = y + W[p + ".bias"]
     return y
+
+
+def quantize_dynamic_int8(W):
+    """STAND-IN for the reference's deployed `model_quant.onnx` (offline-stream.cpp:75-77; websocket/run_server_offline.sh
+    deploys quantize=true): onnxruntime's quantize_dynamic turns the MatMul / Gemm nodes into dynamic int8 kernels (per-tensor
+    uint8 activations, int8 weights).  Neither onnxruntime nor the exported graph exist here, so the same matmuls of this
+    restatement -- every nn.Linear-shaped projection that goes through `_lin` -- are replaced by PyTorch's dynamic int8 Linear
+    (torch.ao.nn.quantized.dynamic.Linear, fbgemm / oneDNN kernels).  It measures PyTorch's int8 kernels, not ORT's: a labelled
+    stand-in for the CPU baseline's int8 row, never a parity oracle.  Returns a new weight dict."""
+    import warnings
+    import torch.nn as nn
+    out = dict(W)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from torch.ao.quantization import quantize_dynamic
+        for name, w in W.items():
+            if not name.endswith(".weight") or w.dim() != 2 or name in ("predictor.cif_output.weight", "predictor.cif_output2.weight", "bias_embed.weight"):
+                continue
+            if "weight_ih" in name or "weight_hh" in name:
+                continue
+            pfx = name[:-7]
+            lin = nn.Linear(w.shape[1], w.shape[0], bias=(pfx + ".bias") in W)
+            with torch.no_grad():
+                lin.weight.copy_(w)
+                if lin.bias is not None:
+                    lin.bias.copy_(W[pfx + ".bias"])
+            out[pfx + ".__int8__"] = quantize_dynamic(nn.Sequential(lin), {nn.Linear}, dtype=torch.qint8)[0]
+    return out
 
 
 def _fsmn(v, w, K):

@@ -123,3 +123,30 @@ def test_reference_style_rtf_harness_runs(capi, synth, model, tmp_path):
         j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
         assert j["wavs"] == 6 and abs(j["audio_s"] - sum([16000, 52800, 33000, 24000, 80000, 20000]) / 16000.0) < 1e-2
         assert "speedup" in r.stdout and "total_rtf" in r.stdout
+
+
+def test_reference_unmodified_rtf_harness_and_header_caller_run_on_the_gpu(capi, synth, model, tmp_path):
+    """oracle/_ref/funasr-onnx-offline-rtf-ref is the reference's UNMODIFIED onnxruntime/bin/funasr-onnx-offline-rtf.cpp, and
+    oracle/_ref/boundary_link_check a caller compiled against the reference's own funasrruntime.h -- both linked against
+    libfunasr_b200.so in the build container (oracle/Makefile `boundary`, tests/test_boundary_cpu.py).  Here they RUN on the B200:
+    the reference's own harness decodes a wav.scp with three threads on one handle and exits 0 (its LOG(INFO) lines go to the
+    stand-in glog sink, so the exit status is the check); the header caller runs one FunOfflineInferBuffer request."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "funasr-onnx-offline-rtf-ref")
+    chk = os.path.join(root, "oracle", "_ref", "boundary_link_check")
+    if not (os.path.exists(exe) and os.path.exists(chk)):
+        pytest.skip("oracle/_ref binaries are built in the container that holds /root/reference")
+    scp = os.path.join(str(tmp_path), "wav.scp")
+    with open(scp, "w") as f:
+        for k, n in enumerate([16000, 52800, 33000, 24000]):
+            path = os.path.join(str(tmp_path), "r%d.wav" % k)
+            with wave.open(path, "wb") as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+                w.writeframes(synth.make_audio(n, 90 + k).astype("<i2").tobytes())
+            f.write("r%d %s\n" % (k, path))
+    r = subprocess.run([exe, "--model-dir", model["dir"], "--wav-path", scp, "--thread-num", "3", "--quantize", "false"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-800:]
+    r = subprocess.run([chk, model["dir"]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "boundary_link_check ok" in r.stdout and "text_bytes=" in r.stdout, (r.stdout + r.stderr)[-800:]

@@ -330,6 +330,37 @@ def test_small_model_against_committed_golden(capi, small):
             assert all(gap < 0.06 for _, gap in bad), bad
 
 
+def test_peaky_cases_are_bit_exact(capi, synth, gpu, tmp_path_factory):
+    """Committed cases (tests/golden/peaky_cases.json, made by tests/golden/make_peaky_cases.py from the fp32 oracle) on the
+    "peaky" small model, chosen so that every row's top-1 margin (>= 0.05), every CIF integrate value (>= 0.01 from the
+    threshold) and the token count clear their thresholds by far more than the CUDA path's rounding error: ids, fire frames
+    and counts must be EXACTLY the oracle's, in both operand formats, alone and batched together."""
+    import json
+    g = json.load(open(os.path.join(GOLD, "peaky_cases.json")))
+    m = g["model"]
+    d = str(tmp_path_factory.mktemp("peaky"))
+    cfg, W = synth.make_weights(m["cfg"], m["seed"], m["jitter_ln"])
+    getattr(synth, m["transform"])(W)
+    modelfile = __import__("importlib").import_module("asr-2pass_b200.modelfile")
+    modelfile.write_model_dir(d, cfg, W, *synth.make_cmvn(int(cfg["feat_dim"])), synth.make_tokens(int(cfg["vocab"])))
+    assert len(g["cases"]) >= 5
+    segs = [synth.make_audio(c["n_samples"], c["audio_seed"]) for c in g["cases"]]
+    offs = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int64)
+    for prec in ("fp16", "bf16"):
+        eng = capi.Engine(d, max_rows=2048, max_segments=64, prec=prec)
+        b = capi.Batch(eng, int(offs[-1]) + 64)
+        res = b.forward_s16(np.concatenate(segs), offs)
+        for i, c in enumerate(g["cases"]):
+            s, e = res["token_offsets"][i], res["token_offsets"][i + 1]
+            assert res["lfr_frames"][i] == c["T"] and res["token_counts"][i] == c["L"]
+            assert list(res["token_ids"][s:e]) == c["ids"], (prec, i)
+            assert list(res["fire_frames"][s:e]) == c["fire_frames"], (prec, i)
+            r1 = b.forward_s16(segs[i], np.array([0, len(segs[i])], np.int64))      # alone: the same
+            assert list(r1["token_ids"]) == c["ids"] and list(r1["fire_frames"]) == c["fire_frames"]
+        b.close()
+        eng.close()
+
+
 def test_batch_invariance_and_input_formats(capi, synth, small):
     """A segment's result does not depend on what it is batched with (the reference's ORT path is batch-1),
     nor on whether PCM arrives as int16 or as the reference's float/32768."""

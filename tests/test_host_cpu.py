@@ -173,3 +173,27 @@ def test_checkpoint_converter_round_trip(synth, tmp_path):
     conv.main(["vad", "--checkpoint", os.path.join(d, "vad.pt"), "--out-dir", os.path.join(d, "vad")])
     _, W4 = mf.read_weights(os.path.join(d, "vad", "vad.b200pf"))
     assert all(np.array_equal(W4[k], VW[k]) for k in VW)
+
+
+def test_pruned_posteriors_expand_to_the_rows_the_lm_decoders_read(capi):
+    """SURVEY.md §8(f) rank 3 host side: pf::host::ExpandPrunedPosteriors rebuilds the dense log-softmax rows WfstDecoder::Search
+    (wfst-decoder.cpp:27-57) / CtcPrefixDecoder::CtcSearch (ctc-prefix-decoder.cpp:157) read from the engine's top-k output: the k
+    listed classes keep their exact log-probabilities, every row stays a normalised distribution, no unlisted class outranks a
+    listed one, and a top-10 prune of the rebuilt row (CtcPrefixDecoder's first_beam_size) equals the top-10 of the full row."""
+    from oracle import paraformer_ref as R
+    rng = np.random.default_rng(5)
+    V, k = 8404, 16
+    logits = (rng.standard_normal((23, V)) * 2.5).astype(np.float32)
+    logits[4] *= 6.0                                  # a peaky row: the listed classes hold nearly all the mass
+    lse, lp, ids = R.logprob_topk(logits, k)
+    full = logits - lse[:, None]
+    dense = capi.host_expand_posteriors(lp, ids, V)
+    assert dense.shape == (23, V) and np.isfinite(dense).all()
+    for r in range(23):
+        assert np.array_equal(dense[r, ids[r]], lp[r].astype(np.float32))                     # listed classes: exact
+        assert abs(float(np.exp(dense[r].astype(np.float64)).sum()) - 1.0) <= 1e-4             # still a distribution
+        rest = np.delete(dense[r], ids[r])
+        assert np.all(rest == rest[0]) and rest[0] <= lp[r].min() + 1e-6                      # the rest: one floor value below the list
+        top_full = np.lexsort((np.arange(V), -full[r]))[:10]
+        top_dense = np.lexsort((np.arange(V), -dense[r]))[:10]
+        assert np.array_equal(top_full, top_dense)

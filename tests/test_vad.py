@@ -72,6 +72,27 @@ def test_vad_segmenter_matches_reference_compiled_golden(capi):
     assert total > 50
 
 
+def test_streaming_vad_equals_whole_recording_for_any_chunking(capi):
+    """pf::host::StreamingVad (the 2-pass stream's form: scores pushed chunk by chunk, segments reported as they close) returns,
+    in total, exactly the segments the reference's compiled E2EVadModel produced for the same scores -- for chunks of 1 frame,
+    60 frames (the 2-pass server's 600 ms), 100 frames and random sizes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vad_segments_golden.npz"))
+    rng = np.random.default_rng(3)
+    for k in range(24):
+        mes, msl, th = g["opts_%d" % k]
+        p = g["p_%d" % k]
+        ref = [tuple(int(v) for v in r) for r in g["segs_%d" % k]]
+        for chunks in ([1] * len(p), [60] * (len(p) // 60 + 1), [100] * (len(p) // 100 + 1), list(rng.integers(1, 300, len(p) // 20 + 2))):
+            c, tot = [], 0
+            for n in chunks:                       # trim the list to cover exactly len(p) frames
+                if tot >= len(p):
+                    break
+                c.append(int(min(n, len(p) - tot)))
+                tot += c[-1]
+            assert capi.host_vad_segments_streaming(p, c, int(mes), int(msl), float(th)) == ref, (k, c[:4])
+
+
 def test_vad_segmenter_matches_live_reference_when_built(capi):
     from oracle import text_ref as T
     if not T.available():
@@ -187,6 +208,51 @@ def test_offline_shim_vad_cut_path(capi, synth, gpu, tmp_path):
     if len(h.vad_cut(sil, 800, 15000)) == 0:
         assert h.infer_buffer_vad(sil, 800, 15000)[0] == ""
     h.close()
+
+
+@pytest.mark.gpu
+def test_tpass_offline_leg_equals_offline_api_on_the_same_stream(capi, synth, gpu, tmp_path):
+    """FunTpassInit / FunTpassOnlineInit / FunTpassInferBuffer (funasrruntime.h:121-132), the 2-pass server's entry points: a stream
+    fed in 600 ms chunks closes the SAME VAD segments as the whole recording through FunOfflineInferBuffer, and every closed
+    segment's corrected text (`tpass_msg`, mode "2pass-offline") is the offline model's text for that segment.  The streaming
+    model's partial results are outside this path: `msg` stays empty."""
+    import os
+    vd, md = str(tmp_path / "vad"), str(tmp_path / "am")
+    os.makedirs(vd), os.makedirs(md)
+    synth.write_synthetic_vad_dir(vd, seed=0)
+    synth.write_synthetic_model_dir(md, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    parts = []
+    for i, (n_speech, n_sil) in enumerate([(48000, 24000), (80000, 40000), (16000, 16000), (160000, 32000), (64000, 44000)]):
+        parts += [synth.make_audio(n_speech, 70 + i), np.zeros(n_sil, np.int16)]
+    pcm = np.concatenate(parts)
+    eng = capi.VadEngine(vd, max_frames=20000)
+    p0, _, _, _ = eng.scores(pcm, np.array([0, len(pcm)], np.int64))
+    eng.close()
+    thres = float(np.clip(1.0 - 2.0 * np.median(p0), 0.05, 0.95))
+    h = capi.OfflineHandle(md, max_rows=8192, max_segments=256, batch_size=8, vad_dir=vd, vad_thres=thres)
+    cut = h.vad_cut(pcm, 800, 15000)
+    expect = []
+    for b, e in cut:
+        bs, es = min(int(b) * 16, len(pcm)), min(int(e) * 16, len(pcm))
+        t = h.infer_segments(pcm, [bs], [es])
+        expect.append(t[0] if isinstance(t, tuple) else t)
+    h.close()
+    assert len(expect) >= 3
+    tp = capi.TpassStream(md, vd, options={"vad-speech-noise-thres": thres, "max-rows": 8192, "max-segments": 256})
+    for chunk in (9600, 16000, 4000):                 # 600 ms (the server's chunking), 1 s, 250 ms
+        conn = tp.connect()
+        got = []
+        for s in range(0, len(pcm), chunk):
+            last = s + chunk >= len(pcm)
+            r = tp.infer(conn, pcm[s:s + chunk], finished=last, mode=2, vad_tail_sil=800, vad_max_len=15000)
+            assert r["msg"] == ""
+            if r["tpass_msg"] or r["stamp"]:
+                got.append(r["tpass_msg"])
+        assert [g.replace(" ", "") for g in got] == [e.replace(" ", "") for e in expect], chunk
+        # the connection is reusable after input_finished (Audio::ResetIndex): the same stream again gives the same texts
+        r = tp.infer(conn, pcm[:200000], finished=True, mode=0)
+        assert r["tpass_msg"] != "" or len(expect) == 0
+    tp.close()
 
 
 def test_whole_recording_vad_equals_reference_cutsplit(capi, synth, tmp_path):
