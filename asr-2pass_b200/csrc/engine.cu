@@ -616,7 +616,6 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
     if (T <= 0) continue;  // reference: empty features -> "" (paraformer.cpp:477-480)
     if (ns >= e->cfg.max_segments) { set_error("batch exceeds max_segments"); return B200PF_ERR_CAPACITY; }
     if (rows + T + 1 > e->cfg.max_rows) { set_error("batch exceeds max_rows"); return B200PF_ERR_CAPACITY; }
-    if (T > e->ft.pe_rows) { set_error("segment longer than the position-encoding table (2048 LFR frames)"); return B200PF_ERR_CAPACITY; }
     b->dev_of_in[i] = ns;
     b->h_sample_off[ns] = sample_start[i];
     b->h_fb_off[ns] = frames;

@@ -221,8 +221,23 @@ lfr_cmvn_posenc_kernel(const float* __restrict__ fb, const int* __restrict__ fb_
     f.y = __fmul_rn(__fadd_rn(v.y, mu.y), va.y);
     f.z = __fmul_rn(__fadd_rn(v.z, mu.z), va.z);
     f.w = __fmul_rn(__fadd_rn(v.w, mu.w), va.w);
-    const int pr = info.x < t.pe_rows ? info.x : t.pe_rows - 1;
-    const float4 pe = *reinterpret_cast<const float4*>(t.pos_enc + (size_t)pr * FEAT + c);
+    float4 pe;
+    if (info.x < t.pe_rows) {
+      pe = *reinterpret_cast<const float4*>(t.pos_enc + (size_t)info.x * FEAT + c);
+    } else {
+      // beyond the table (a recording decoded as ONE segment, > 2048 frames = 123 s): the same formula the table was built with
+      // (paraformer-online.cpp:240-268: positions from 1, timescales exp(-i ln(1e4) / (depth/2 - 1)), sines then cosines)
+      constexpr int half = FEAT / 2;
+      const float inc = (float)(-(log(10000.0) / (half - 1)));
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int col = c + q, i = col < half ? col : col - half;
+        const float st = (float)(info.x + 1) * expf((float)i * inc);
+        v[q] = col < half ? sinf(st) : cosf(st);
+      }
+      pe = make_float4(v[0], v[1], v[2], v[3]);
+    }
     o.x = __fadd_rn(__fmul_rn(f.x, scale), pe.x);
     o.y = __fadd_rn(__fmul_rn(f.y, scale), pe.y);
     o.z = __fadd_rn(__fmul_rn(f.z, scale), pe.z);

@@ -355,6 +355,13 @@ FUNASR_RESULT FunASRInferBuffer(FUNASR_HANDLE handle, const char* sz_buf, int n_
   const unsigned char* bytes = (const unsigned char*)sz_buf;
   for (int i = 0; i < n; ++i) pcm[i] = (float)(short)((bytes[2 * i + 1] << 8) | bytes[2 * i]) / 32768.0f;  // Audio::LoadPcmwav
   res->msg += m->Forward(pcm.data(), n, input_finished);   // Audio::Fetch yields the whole audio once (no VAD on this API)
+  if (funasr_b200::ParaformerB200::last_failed_segments() > 0) {
+    // the recording did not fit the engine (this API decodes it as ONE segment: max-rows LFR frames, 60 ms each): a real error,
+    // not an empty transcript.  FunOfflineInferBuffer cuts long recordings (VAD or vad_max_len) and has no such limit.
+    fprintf(stderr, "FunASRInferBuffer: %.1f s of audio exceed the engine's capacity; raise \"max-rows\" or use FunOfflineInferBuffer\n", res->snippet_time);
+    delete res;
+    return nullptr;
+  }
   return res;
 }
 

@@ -13,11 +13,14 @@
 namespace funasr_b200 {
 
 namespace {
+thread_local int tl_failed_segments = 0;
 std::string DirOf(const std::string& path) {
   const size_t p = path.find_last_of('/');
   return p == std::string::npos ? std::string(".") : path.substr(0, p);
 }
 }  // namespace
+
+int ParaformerB200::last_failed_segments() { return tl_failed_segments; }
 
 ParaformerB200::ParaformerB200(int device, int max_rows, int max_segments)
     : device_(device), max_rows_(max_rows), max_segments_(max_segments) {}
@@ -320,6 +323,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
                                                 const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16,
                                                 const int64_t* len16, void* wfst_decoder) {
   std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
+  tl_failed_segments = 0;
   if (n_seg <= 0 || !engine_) return results;
   std::lock_guard<std::mutex> lock(mu_);
   {  // pruned posteriors are only computed for calls that decode with the LM
@@ -365,11 +369,15 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
       if (!running) fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error());
     }
     if (i + 1 < subs.size()) ok[i + 1] = stage(i + 1);                  // host copies while the GPU computes sub-batch i
+    bool done = false;
     if (running) {
       std::vector<std::string> part;
-      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder))
+      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder)) {
         for (int k = 0; k < subs[i].end - subs[i].start; ++k) results[subs[i].start + k] = part[k];
+        done = true;
+      }
     }
+    if (!done) tl_failed_segments += subs[i].end - subs[i].start;
   }
   return results;
 }

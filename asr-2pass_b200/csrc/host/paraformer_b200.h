@@ -135,6 +135,10 @@ class ParaformerB200 : B200PF_MODEL_BASES {
 
   b200pf_engine* engine() { return engine_; }
   pf::host::Detokenizer* vocab() { return vocab_.get(); }
+  // Segments of this THREAD's last Forward / ForwardPcm16 / ForwardSegments16 call that could not be decoded (their strings are
+  // "", as the reference returns for an inference exception, paraformer.cpp:582-587) -- e.g. a segment that does not fit the
+  // engine's capacity.  Lets the buffer APIs tell "nothing recognised" from "not decoded".
+  static int last_failed_segments();
   // token ids / CIF fire frames of the last Forward on this thread's call (debug / tests)
   const std::vector<std::vector<int>>& last_ids() const { return last_ids_; }
 

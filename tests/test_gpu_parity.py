@@ -420,6 +420,30 @@ def test_forward_full_paraformer_large(capi, synth, gpu, tmp_path_factory):
     eng.close()
 
 
+def test_recording_longer_than_the_position_table_as_one_segment(capi, synth, gpu, tmp_path_factory):
+    """FunASRInferBuffer decodes a whole recording as ONE segment (no VAD on that API, funasrruntime.cpp:57-114).  Beyond the 2048
+    rows of the precomputed table the position encoding is evaluated in the kernel: a 135 s segment (T = 2250) agrees with the
+    oracle like any other, and a recording that exceeds the engine's capacity is a real error, not an empty transcript."""
+    import torch
+    d = str(tmp_path_factory.mktemp("long"))
+    cfg, W, means, vars_, toks = synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    model = dict(W={k: torch.from_numpy(v) for k, v in W.items()}, pc=R.PfConfig.from_dict(cfg), means=means, vars=vars_)
+    eng = capi.Engine(d, max_rows=4096, max_segments=8)
+    eng.set_option("taps", 1)
+    pcm = synth.make_audio(16000 * 135, 9)
+    b = capi.Batch(eng, len(pcm) + 16)
+    res = b.forward_s16(pcm, np.array([0, len(pcm)], np.int64))
+    assert res["lfr_frames"][0] == 2250
+    _, o = _oracle(model, pcm)
+    _check_segment(b, res, 0, model, o)
+    b.close()
+    eng.close()
+    text = capi.funasr_infer(d, pcm16=pcm, max_rows=4096)                  # fits: decoded as one segment
+    assert len(text) > 100
+    with pytest.raises(capi.B200PFError):                                  # does not fit: an error, not ""
+        capi.funasr_infer(d, pcm16=pcm, max_rows=1024)
+
+
 def test_max_length_segment_full_size_properties(capi, synth, small):
     """60 s (vad_max_len) segment, T = 1000: size-independent properties instead of an oracle comparison."""
     pcm = synth.make_audio(960000, 77)

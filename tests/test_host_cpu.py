@@ -158,6 +158,19 @@ def test_checkpoint_converter_round_trip(synth, tmp_path):
     for k in ("feat_dim", "d_model", "n_heads", "d_ff", "n_enc", "n_dec", "kernel", "vocab", "timestamp", "contextual"):
         assert int(c2[k]) == int(cfg[k]), k
     assert set(W2) == set(W) and all(np.array_equal(W2[k], W[k]) for k in W)
+    # hyper-parameters the kernels hard-code: a config.yaml that carries another value stops the conversion instead of
+    # producing a model file that decodes wrong text
+    for bad in ("predictor_conf:\n  smooth_factor: 0.8\n", "predictor_conf:\n  noise_threshold: 0.01\n", "encoder_conf:\n  sanm_shfit: 3\n",
+                "predictor_conf:\n  use_cif1_cnn: true\n", "predictor_conf:\n  upsample_type: cnn\n", "decoder_conf:\n  sanm_shfit: 5\n",
+                "frontend_conf:\n  lfr_m: 5\n"):
+        with open(os.path.join(d, "bad.yaml"), "w") as f:
+            f.write(bad)
+        with pytest.raises(SystemExit, match="unsupported"):
+            conv.main(["am", "--checkpoint", os.path.join(d, "am.pt"), "--config", os.path.join(d, "bad.yaml"), "--out-dir", os.path.join(d, "bad")])
+    with open(os.path.join(d, "ok.yaml"), "w") as f:      # the supported values, spelled out, pass
+        f.write("encoder_conf:\n  sanm_shfit: 0\n  attention_heads: 4\npredictor_conf:\n  smooth_factor: 1.0\n  noise_threshold: 0\n  use_cif1_cnn: false\n"
+                "  upsample_type: cnn_blstm\n  upsample_times: 3\nfrontend_conf:\n  lfr_m: 7\n  lfr_n: 6\n")
+    conv.main(["am", "--checkpoint", os.path.join(d, "am.pt"), "--config", os.path.join(d, "ok.yaml"), "--out-dir", os.path.join(d, "ok")])
     pcfg, PW = synth.make_punc_weights(dict(vocab=500, d_model=64, n_heads=4, d_ff=128, n_layers=3, sanm_shift=5), seed=2)
     torch.save({k: torch.from_numpy(v) for k, v in PW.items()}, os.path.join(d, "punc.pt"))
     with open(os.path.join(d, "punc.yaml"), "w", encoding="utf-8") as f:

@@ -237,6 +237,7 @@ def test_tpass_offline_leg_equals_offline_api_on_the_same_stream(capi, synth, gp
         t = h.infer_segments(pcm, [bs], [es])
         expect.append(t[0] if isinstance(t, tuple) else t)
     h.close()
+    expect = [e for e in expect if e.replace(" ", "")]        # a call whose segment decodes to nothing reports nothing
     assert len(expect) >= 3
     tp = capi.TpassStream(md, vd, options={"vad-speech-noise-thres": thres, "max-rows": 8192, "max-segments": 256})
     for chunk in (9600, 16000, 4000):                 # 600 ms (the server's chunking), 1 s, 250 ms
@@ -246,7 +247,7 @@ def test_tpass_offline_leg_equals_offline_api_on_the_same_stream(capi, synth, gp
             last = s + chunk >= len(pcm)
             r = tp.infer(conn, pcm[s:s + chunk], finished=last, mode=2, vad_tail_sil=800, vad_max_len=15000)
             assert r["msg"] == ""
-            if r["tpass_msg"] or r["stamp"]:
+            if r["tpass_msg"].replace(" ", ""):
                 got.append(r["tpass_msg"])
         assert [g.replace(" ", "") for g in got] == [e.replace(" ", "") for e in expect], chunk
         # the connection is reusable after input_finished (Audio::ResetIndex): the same stream again gives the same texts

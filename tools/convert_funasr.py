@@ -8,7 +8,9 @@ wrapped as {"state_dict": ...} / {"model": ...}) and, when given, the model's co
     python tools/convert_funasr.py punc --checkpoint model.pt [--config config.yaml] --out-dir <punc-dir>    -> punc.b200pf, punc_list.json
 
 The reference's other files (am.mvn, tokens.json, config.yaml, seg_dict) are used as they are; put them in the same directory.
-No real checkpoint is available offline, so this tool is exercised on synthetic state_dicts only (tests/test_host_cpu.py)."""
+No real checkpoint is available offline, so this tool is exercised on synthetic state_dicts only (tests/test_host_cpu.py):
+PARITY WITH REAL EXPORTED WEIGHTS IS UNVERIFIED.  The acoustic network's restatement (oracle/paraformer_ref.py) is itself unpinned;
+hyper-parameters the kernels hard-code are checked against config.yaml (check_supported) and a mismatch stops the conversion."""
 import argparse
 import importlib
 import json
@@ -45,7 +47,44 @@ def count(sd, prefix, suffix):
     return n
 
 
+def check_supported(y):
+    """The engine's kernels fix some of the architecture's hyper-parameters (elementwise.cu cif_alpha_kernel: smooth_factor 1.0 /
+    noise_threshold 0.0; fsmn_kernel: symmetric taps, sanm_shfit 0; the timestamp head reads the encoder output, i.e.
+    use_cif1_cnn false with upsample_type cnn_blstm; ln_eps 1e-12 and the V2 predictor without the +enc residual are written into
+    the file).  A checkpoint trained with other values would convert and then produce wrong text, so every such key that
+    config.yaml carries is checked here and the conversion stops on the first value the engine does not implement."""
+    enc, pred, dec = y.get("encoder_conf", {}) or {}, y.get("predictor_conf", {}) or {}, y.get("decoder_conf", {}) or {}
+    want = [
+        ("encoder_conf.sanm_shfit", enc.get("sanm_shfit", enc.get("sanm_shift")), 0),
+        ("encoder_conf.normalize_before", enc.get("normalize_before"), True),
+        ("encoder_conf.input_layer", enc.get("input_layer"), "pe"),
+        ("encoder_conf.selfattention_layer_type", enc.get("selfattention_layer_type"), "sanm"),
+        ("decoder_conf.sanm_shfit", dec.get("sanm_shfit", dec.get("sanm_shift")), 0),
+        ("predictor_conf.smooth_factor", pred.get("smooth_factor"), 1.0),
+        ("predictor_conf.noise_threshold", pred.get("noise_threshold"), 0.0),
+        ("predictor_conf.l_order", pred.get("l_order"), 1),
+        ("predictor_conf.r_order", pred.get("r_order"), 1),
+        ("predictor_conf.use_cif1_cnn", pred.get("use_cif1_cnn"), False),
+        ("predictor_conf.upsample_type", pred.get("upsample_type"), "cnn_blstm"),
+        ("predictor_conf.upsample_times", pred.get("upsample_times"), 3),
+        ("frontend_conf.lfr_m", (y.get("frontend_conf", {}) or {}).get("lfr_m"), 7),
+        ("frontend_conf.lfr_n", (y.get("frontend_conf", {}) or {}).get("lfr_n"), 6),
+        ("frontend_conf.n_mels", (y.get("frontend_conf", {}) or {}).get("n_mels"), 80),
+        ("frontend_conf.window", (y.get("frontend_conf", {}) or {}).get("window"), "hamming"),
+    ]
+    for key, got, need in want:
+        if got is None:
+            continue                       # not in this config.yaml: the upstream default is the supported value
+        same = (abs(float(got) - float(need)) < 1e-9) if isinstance(need, float) else (got == need)
+        if not same:
+            raise SystemExit("unsupported %s = %r: the B200 engine implements %r only (tools/convert_funasr.py check_supported)" % (key, got, need))
+    name = str(y.get("predictor", "") or "")
+    if name and "cif" not in name.lower():
+        raise SystemExit("unsupported predictor %r" % name)
+
+
 def am_config(sd, y, n_heads):
+    check_supported(y)
     enc, pred, dec = y.get("encoder_conf", {}) or {}, y.get("predictor_conf", {}) or {}, y.get("decoder_conf", {}) or {}
     cfg = dict(
         feat_dim=sd["encoder.encoders0.0.norm1.weight"].shape[0], d_model=sd["encoder.after_norm.weight"].shape[0],
