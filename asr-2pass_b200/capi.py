@@ -51,7 +51,7 @@ def build_library(verbose=False):
 EXPORTS = [
     "b200pf_last_error", "b200pf_version", "b200pf_device_count", "b200pf_model_dir_probe", "b200pf_engine_create", "b200pf_engine_create_prec", "b200pf_op_set_precision", "b200pf_engine_destroy",
     "b200pf_engine_config", "b200pf_engine_vocab_size", "b200pf_engine_token", "b200pf_engine_lang",
-    "b200pf_engine_set_option", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_engine_copy_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
+    "b200pf_engine_set_option", "b200pf_engine_graph_stats", "b200pf_engine_profile_read", "b200pf_engine_stream", "b200pf_engine_copy_stream", "b200pf_num_fbank_frames", "b200pf_num_lfr_frames",
     "b200pf_rows_for", "b200pf_batch_create", "b200pf_batch_destroy", "b200pf_batch_stage_s16",
     "b200pf_batch_stage_f32", "b200pf_batch_stage_s16_ptrs", "b200pf_batch_run", "b200pf_batch_collect", "b200pf_forward_s16", "b200pf_forward_f32",
     "b200pf_batch_launches", "b200pf_batch_flops", "b200pf_batch_tap", "b200pf_op_gemm", "b200pf_op_gemm_bench", "b200pf_op_conv3",
@@ -719,6 +719,13 @@ class Engine:
         _check(lib().b200pf_engine_set_option(self.h, key.encode(), int(value)))
         if key == "logprob_topk":
             self._topk = int(value)
+
+    def graph_stats(self):
+        """(graphs captured, graph replays, graphs cached) of the small-batch CUDA-graph path."""
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_int()
+        lib().b200pf_engine_graph_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]
+        _check(lib().b200pf_engine_graph_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(captures=a.value, replays=b.value, cached=c.value)
 
     def profile_read(self, reset=True):
         names = (C.c_char_p * 16)()

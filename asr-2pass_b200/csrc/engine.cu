@@ -176,6 +176,8 @@ bool ws_take(b200pf_engine* e, T** p, size_t n) {
 
 }  // namespace
 
+static void destroy_graphs(b200pf_engine* e, const void* batch);
+
 extern "C" {
 
 const char* b200pf_last_error(void) { return last_error().c_str(); }
@@ -445,6 +447,7 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
+  destroy_graphs(e, nullptr);
   cudaFree(e->warena.base);
   cudaFree(e->ws.base);
   cudaFree(e->tap_feats);
@@ -473,6 +476,13 @@ const char* b200pf_engine_token(const b200pf_engine* e, int id) {
 }
 const char* b200pf_engine_lang(const b200pf_engine* e) { return e ? e->lang.c_str() : ""; }
 void* b200pf_engine_stream(b200pf_engine* e) { return e ? (void*)e->stream : nullptr; }
+int b200pf_engine_graph_stats(const b200pf_engine* e, long long* captures, long long* replays, int* cached) {
+  if (!e) { set_error("null engine"); return B200PF_ERR_INVALID; }
+  if (captures) *captures = e->graph_captures;
+  if (replays) *replays = e->graph_replays;
+  if (cached) { int n = 0; for (const auto& kv : e->graphs) n += kv.second.exec != nullptr; *cached = n; }
+  return 0;
+}
 void* b200pf_engine_copy_stream(b200pf_engine* e) { return e ? (void*)e->copy : nullptr; }
 
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
@@ -504,6 +514,14 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   }
   if (strcmp(key, "profile") == 0) {
     e->profile = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(key, "graphs") == 0) {
+    e->use_graphs = value ? 1 : 0;
+    return 0;
+  }
+  if (strcmp(key, "graph_max_rows") == 0) {
+    e->graph_max_rows = value < 0 ? 0 : value;
     return 0;
   }
   set_error(std::string("unknown option ") + key);
@@ -543,7 +561,7 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   b->e = e;
   b->max_samples = max_samples;
   const size_t S = (size_t)e->cfg.max_segments, R = (size_t)e->cfg.max_rows;
-  CK(cudaMalloc(&b->d_pcm, (size_t)max_samples * 4 + 64), "cudaMalloc(pcm)");
+  CK(cudaMalloc(&b->d_pcm, (size_t)max_samples * 4 + (512 << 10)), "cudaMalloc(pcm)");   // slack: padded graph buckets read frames past the last segment
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 63) & ~size_t(63); return o; };
   const size_t o_sample = carve((S + 1) * 8), o_fb = carve((S + 1) * 4), o_row = carve((S + 1) * 4), o_T = carve(S * 4),
@@ -587,6 +605,7 @@ void b200pf_batch_destroy(b200pf_batch* b) {
   if (!b) return;
   cudaSetDevice(b->e->device);
   cudaStreamSynchronize(b->e->stream);
+  { std::lock_guard<std::mutex> lock(b->e->mu); destroy_graphs(b->e, b); }
   cudaFree(b->d_pcm);
   cudaFree(b->d_meta);
   cudaFree(b->d_n_tok);
@@ -645,6 +664,22 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
   b->h_fb_off[ns] = frames;
   b->h_row_off[ns] = rows;
   b->n_seg = ns; b->rows = rows; b->n_frames = frames; b->n_work = nwork;
+  b->rows_run = rows; b->n_frames_run = frames; b->n_work_run = nwork;
+  b->graph_ok = false;
+  if (e->use_graphs && ns > 0 && rows <= e->graph_max_rows) {
+    // Small batch: pad the layout to a bucket so that the captured graph of the forward can be shared by every batch that
+    // falls into it.  Rows [rows, rows_run) are gap rows (every kernel writes zeros / ignores them), the extra attention work
+    // items point past their segment (skipped by the kernel) and the front end runs over 6 frames per padded row.
+    const int rr = std::min(e->cfg.max_rows, (rows + 31) & ~31);
+    const int nw = ns + rr / 128;
+    const int64_t need_pcm = (int64_t)6 * rr * 160 + 400 + (int64_t)ns * 416;   // samples the padded front end may touch (per-segment leftovers and start alignment included)
+    if (nw <= e->cfg.max_rows && need_pcm * 4 <= b->max_samples * 4 + (512 << 10)) {
+      for (int r = rows; r < rr; ++r) { b->h_row_seg[r] = -1; b->h_row_info[r] = make_int2(-1, 0); }
+      for (int k = nwork; k < nw; ++k) { b->h_work[k].seg = 0; b->h_work[k].q0 = 1 << 30; b->h_work_x[k].seg = 0; b->h_work_x[k].q0 = 1 << 30; }
+      b->rows_run = rr; b->n_work_run = nw; b->n_frames_run = 6 * rr;
+      b->graph_ok = true;
+    }
+  }
   b->collected = false;
   return 0;
 }
@@ -778,6 +813,214 @@ int b200pf_batch_stage_s16_ptrs(b200pf_batch* b, const int16_t* const* seg, cons
   return 0;
 }
 
+}  // extern "C"
+
+// Enqueues the whole forward of a staged batch on `s` (no host synchronisation).  `capturing`: the stream is being captured
+// into a CUDA graph -- no event timing, no side stream.
+static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
+  b200pf_engine* e = b->e;
+  const b200pf_config& c = e->cfg;
+  const int M = b->rows_run, D = c.d_model, S = b->n_seg, sms = e->num_sms;
+  const int Lcap = M;  // tokens <= frames
+  int64_t& nl = b->launches;
+
+  // optional CUDA-event bracket around one launch: category, algorithmic work (FLOPs or bytes)
+  auto prof_begin = [&](int cat, double work) -> int {
+    if (!e->profile || capturing) return -1;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+      if (!e->prof_pool.empty()) { ev[i] = e->prof_pool.back(); e->prof_pool.pop_back(); }
+      else if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
+    }
+    e->prof_recs.push_back({ev[0], ev[1], cat, work});
+    cudaEventRecord(ev[0], s);
+    return (int)e->prof_recs.size() - 1;
+  };
+  auto prof_end = [&](int h) { if (h >= 0) cudaEventRecord(e->prof_recs[h].b, s); };
+  // the decoder's row count lives on the device; for the FLOP estimate use tokens ~ frames / 2 (random init)
+  const double Lest = b->last_tokens >= 0 && b->last_tokens_rows == M ? (double)b->last_tokens : 0.5 * (M - S);   // exact once this layout was collected
+  double sumT2 = 0;
+  for (int i = 0; i < S; ++i) sumT2 += (double)b->h_seg_T[i] * b->h_seg_T[i];
+
+  // cap_a / cap_c: rows the A buffer / the output buffers hold (tensor-map extents are whole tiles inside them, so that the
+  // maps of every batch size come out of the cache)
+  const int64_t R = c.max_rows;
+  auto gemm = [&](const __nv_bfloat16* A, int lda, int64_t cap_a, const Linear& W, int Mrows, const int* m_dev,
+                  const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0, int cat = 2, int64_t cap_c = 0) {
+    GemmProblem p;
+    p.A = A; p.lda = lda; p.rows_a = cap_a; p.rows_c = cap_c > 0 ? cap_c : R;
+    p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
+    p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0; p.f16 = e->f16;
+    ++nl;
+    const int h = prof_begin(cat, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
+    const int rc = gemm_bf16_tcgen05(p, ep, sms, s);
+    prof_end(h);
+    return rc;
+  };
+
+  // ---- K1 front end ----
+  LAUNCH(0, (double)b->n_frames * (160 * 2 + 80 * 4), fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames_run, e->ft, e->fb, s), "fbank");
+  LAUNCH(0, (double)M * 560 * 4 * 2, lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
+                                   e->taps ? e->tap_feats : nullptr, s), "lfr_cmvn");
+
+  // ---- SAN-M encoder ----
+  AttnProblem ap;
+  // tensor-map row extents: whole 256-row tiles inside the buffers (a few distinct values -> cached maps); rows past M are
+  // never used (masked keys, query rows that are not written)
+  const int64_t Mext = std::min<int64_t>(R, ((int64_t)M + 255) & ~int64_t(255));
+  ap.q = e->qkv; ap.q_rows = Mext; ap.ldq = 3 * D; ap.q_col0 = 0;
+  ap.kv = e->qkv; ap.kv_rows = Mext; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
+  ap.out = e->att; ap.ldo = D;
+  ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
+  ap.work = b->d_work; ap.n_work = b->n_work_run; ap.n_heads = c.n_heads; ap.f16 = e->f16; ap.num_sms = sms;
+  for (int l = 0; l < c.n_enc; ++l) {
+    const EncLayer& w = e->enc[l];
+    const float* xin = l == 0 ? e->x0 : e->x;
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln1");
+    { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
+      CKL(gemm(e->hb, w.din, R, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
+    // The FSMN memory block and the attention both depend only on the QKV projection: run them concurrently
+    // (CUDA-core FMA work next to tensor-core / MUFU work) and join before the output projection.
+    // overlap 1: FSMN enqueued first; overlap 2: attention enqueued first, so its CTAs (two per SM) take the SMs and the
+    // FSMN CTAs fill the register space left over (one per SM) instead of the other way round.
+    const bool fork = e->overlap && !e->profile && !capturing;
+    cudaStream_t fs = fork ? e->side : s;
+    if (fork) {
+      CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
+      CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
+    }
+    if (fork && e->overlap == 2) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
+    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs, e->f16), "fsmn");
+    if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
+    if (!(fork && e->overlap == 2)) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
+    if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
+    { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
+      if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
+      ep.out_f32 = e->x; ep.ld_out_f32 = D;
+      CKL(gemm(e->att, D, R, w.out, M, nullptr, ep, 0, 0, 9), "gemm out"); }
+    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln2");
+    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
+      CKL(gemm(e->hb, D, R, w.w1, M, nullptr, ep, 0, 0, 10), "gemm ffn1"); }
+    { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
+      CKL(gemm(e->ffn, c.d_ff, R, w.w2, M, nullptr, ep, 0, 0, 11), "gemm ffn2"); }
+  }
+  LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
+                             b->d_row_info, 1, s, e->f16), "after_norm");
+
+  // ---- CIF predictor ----
+  { GemmEpilogue ep; ep.bias = e->pred_conv.b; ep.out_f32 = e->x; ep.ld_out_f32 = D;
+    if (c.pred_residual) { ep.res_f32 = e->enc_f32; ep.ld_res = D; ep.relu = 2; } else { ep.relu = 1; }
+    CKL(gemm(e->enc_bf16, D, R, e->pred_conv, M, nullptr, ep, D, -1), "gemm cif_conv"); }
+  LAUNCH(5, (double)M * 512 * 4, cif_alpha_launch(e->x, M, e->pred_out_w, e->pred_out_b, b->d_row_info, c.tail_threshold, e->alpha, s), "cif_alpha");
+  LAUNCH(5, (double)M * 512 * 4, cif_fire_launch(e->alpha, b->d_row_off, b->d_seg_T, S, c.cif_threshold, e->cif_cur, e->cif_rem, e->fire_val,
+                            b->d_n_tok, e->fire_row, s), "cif_fire");
+  LAUNCH(5, (double)M * 512 * 4, cif_scan_launch(b->d_n_tok, S, b->d_tok_off, b->d_tok_total, s), "cif_scan");
+  LAUNCH(5, (double)M * 512 * 4, cif_embed_launch(e->enc_f32, e->cif_cur, e->cif_rem, e->fire_row, b->d_row_off, b->d_tok_off, S, Lcap, e->y,
+                             e->tok_info, b->d_tok_frame, s), "cif_embed");
+  if (e->taps) CK(cudaMemcpyAsync(e->tap_emb, e->y, (size_t)Lcap * D * 4, cudaMemcpyDeviceToDevice, s), "tap emb");
+
+  // ---- timestamp head (config 3, a16): ConvTranspose x3 -> BiLSTM -> alpha2 -> rescale to token_num -> cif_wo_hidden ----
+  if (c.timestamp) {
+    __nv_bfloat16* up = e->qkv;  // [M, 1536] == [3M, 512]; free between the encoder and the decoder
+    { GemmEpilogue ep; ep.bias = e->us_cnn.b; ep.out_bf16 = up; ep.ld_out_bf16 = 3 * D;
+      CKL(gemm(e->enc_bf16, D, R, e->us_cnn, M, nullptr, ep, 0, 0, 15), "gemm upsample"); }
+    { GemmEpilogue ep; ep.bias = e->blstm_ih.b; ep.out_bf16 = e->us_gx; ep.ld_out_bf16 = 8 * D;
+      CKL(gemm(up, D, 3 * R, e->blstm_ih, 3 * M, nullptr, ep, 0, 0, 15, 3 * R), "gemm blstm input"); }
+    LstmParams lp;
+    lp.f16 = e->f16; lp.gx = e->us_gx; lp.ld_gx = 8 * D; lp.whh = e->blstm_hh; lp.seq_off = b->d_us_off; lp.seq_len = b->d_us_len; lp.n_seq = S;
+    lp.n_dir = 2; lp.reverse_mask = 2; lp.out_bf16 = e->us_h; lp.ld_out = 2 * D;
+    LAUNCH(14, 2.0 * 3 * (M - S) * 2 * 4 * D * D, lstm_launch(lp, s), "blstm");
+    LAUNCH(15, (double)3 * M * 1024 * 2, us_alpha_launch(e->us_h, 3 * M, e->us_out_w, e->us_out_b, e->smooth2, e->noise2, e->us_a2, s, e->f16), "us_alpha");
+    LAUNCH(15, (double)3 * M * 12, us_peak_launch(e->us_a2, b->d_us_off, b->d_us_len, b->d_n_tok, S, (float)((double)c.cif_threshold - 1e-4),
+                                                 b->d_us_alphas, b->d_us_peaks, s), "us_peak");
+  }
+
+  // ---- SAN-M decoder ----
+  const int* Ldev = b->d_tok_total;
+  float* tbuf = e->x0;  // [Lcap, 512] fp32 scratch
+  AttnProblem cp;
+  cp.q = e->mem; cp.q_rows = Mext; cp.ldq = D; cp.q_col0 = 0;
+  cp.kv = e->qkv; cp.kv_rows = Mext; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
+  cp.out = e->att; cp.ldo = D;
+  cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
+  cp.work = b->d_work_x; cp.n_work = b->n_work_run; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
+  auto dec_ffn = [&](const DecLayer& w) -> int {
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln1");
+    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
+      CKL(gemm(e->hb, D, R, w.w1, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w1"); }
+    LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s, e->f16), "dec ln ff");
+    { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
+      CKL(gemm(e->ffn, c.d_ff, R, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
+    return 0;
+  };
+  for (int l = 0; l < c.n_dec; ++l) {
+    const DecLayer& w = e->dec[l];
+    { int rc = dec_ffn(w); if (rc) return rc; }
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln2");
+    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16), "dec fsmn");
+    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln3");
+    { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
+      CKL(gemm(e->hb, D, R, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }
+    { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
+      CKL(gemm(e->enc_bf16, D, R, w.kv, M, nullptr, ep, 0, 0, 12), "dec gemm kv"); }
+    LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
+    if (!(c.contextual && l == c.n_dec - 1)) {
+      GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
+      CKL(gemm(e->att, D, R, w.out, Lcap, Ldev, ep, 0, 0, 12), "dec gemm out");
+    } else {
+      // ContextualParaformerDecoder (a16): y is x_self_attn here.  cat = [x_src_attn ; cx] with
+      // cx = bias_decoder(x_self_attn, hotword embeddings); y = x_self_attn + bias_output(cat).
+      __nv_bfloat16* cat = e->qkv;  // [Lcap, 1024]; the cross k/v it held were consumed by the attention above
+      { GemmEpilogue ep; ep.bias = w.out.b; ep.out_bf16 = cat; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(e->att, D, R, w.out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm out"); }
+      LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, e->bias_ln3.g, e->bias_ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ctx ln3");
+      { GemmEpilogue ep; ep.bias = e->bias_q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
+        CKL(gemm(e->hb, D, R, e->bias_q, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm q"); }
+      { GemmEpilogue ep; ep.bias = e->bias_kv.b; ep.out_bf16 = e->hw_kv; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(b->d_hw, D, B200PF_MAX_HOTWORDS, e->bias_kv, b->n_hw, nullptr, ep, 0, 0, 12, B200PF_MAX_HOTWORDS), "ctx gemm kv"); }
+      AttnProblem bp = cp;
+      bp.kv = e->hw_kv; bp.kv_rows = B200PF_MAX_HOTWORDS; bp.kv_row_off = b->d_zero; bp.kv_len = b->d_hw_len;
+      LAUNCH(3, 4.0 * Lest * b->n_hw * 512, attention_tcgen05(bp, s), "bias attention");
+      { GemmEpilogue ep; ep.bias = e->bias_out.b; ep.out_bf16 = cat + D; ep.ld_out_bf16 = 2 * D;
+        CKL(gemm(e->att, D, R, e->bias_out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias out"); }
+      { GemmEpilogue ep; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
+        CKL(gemm(cat, 2 * D, R, e->bias_output, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias_output"); }
+    }
+  }
+  { int rc = dec_ffn(e->dec3); if (rc) return rc; }
+  LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec after_norm");
+  CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
+  float* logits_out = e->taps ? e->tap_logits : (e->topk > 0 ? e->full_logits : nullptr);
+  { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
+    if (logits_out) { ep.out_f32 = logits_out; ep.ld_out_f32 = c.vocab; }
+    CKL(gemm(e->hb, D, R, e->vocab, Lcap, Ldev, ep, 0, 0, 13), "gemm vocab"); }
+  LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
+  if (e->topk > 0) {
+    if (!b->d_topk_lse) {   // first use on this batch: per-batch result buffers (see b200pf_batch_create)
+      const size_t R = (size_t)c.max_rows;
+      CK(cudaMalloc((void**)&b->d_topk_lse, R * (4 + 2 * 4 * B200PF_MAX_TOPK)), "cudaMalloc(topk)");
+      b->d_topk_lp = b->d_topk_lse + R;
+      b->d_topk_id = (int*)(b->d_topk_lp + R * B200PF_MAX_TOPK);
+    }
+    LAUNCH(6, Lest * c.vocab * 4 * 2, logprob_topk_launch(logits_out, c.vocab, Ldev, Lcap, e->topk, b->d_topk_lse, b->d_topk_lp, b->d_topk_id, s), "logprob topk");
+  }
+  b->topk_run = e->topk;
+  return 0;
+}
+
+static void destroy_graphs(b200pf_engine* e, const void* batch) {
+  for (auto it = e->graphs.begin(); it != e->graphs.end();) {
+    if (!batch || std::get<0>(it->first) == batch) {
+      if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+      it = e->graphs.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+extern "C" {
+
 int b200pf_batch_run(b200pf_batch* b, void* stream) {
   if (!b) { set_error("null batch"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
@@ -794,184 +1037,47 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
   }
   std::lock_guard<std::mutex> lock(e->mu);
   CK(cudaStreamWaitEvent(s, b->staged, 0), "cudaStreamWaitEvent");
-  const int M = b->rows, D = c.d_model, S = b->n_seg, sms = e->num_sms;
-  const int Lcap = M;  // tokens <= frames
-  int64_t& nl = b->launches;
+  if (!(b->graph_ok && e->use_graphs && !e->profile)) return enqueue_forward(b, s, false);
 
-  // optional CUDA-event bracket around one launch: category, algorithmic work (FLOPs or bytes)
-  auto prof_begin = [&](int cat, double work) -> int {
-    if (!e->profile) return -1;
-    cudaEvent_t ev[2];
-    for (int i = 0; i < 2; ++i) {
-      if (!e->prof_pool.empty()) { ev[i] = e->prof_pool.back(); e->prof_pool.pop_back(); }
-      else if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
-    }
-    e->prof_recs.push_back({ev[0], ev[1], cat, work});
-    cudaEventRecord(ev[0], s);
-    return (int)e->prof_recs.size() - 1;
-  };
-  auto prof_end = [&](int h) { if (h >= 0) cudaEventRecord(e->prof_recs[h].b, s); };
-  // the decoder's row count lives on the device; for the FLOP estimate use tokens ~ frames / 2 (random init)
-  const double Lest = b->last_tokens >= 0 && b->last_tokens_rows == M ? (double)b->last_tokens : 0.5 * (M - S);   // exact once this layout was collected
-  double sumT2 = 0;
-  for (int i = 0; i < S; ++i) sumT2 += (double)b->h_seg_T[i] * b->h_seg_T[i];
-
-  auto gemm = [&](const __nv_bfloat16* A, int lda, int64_t rows_a, const Linear& W, int Mrows, const int* m_dev,
-                  const GemmEpilogue& ep, int k_wrap = 0, int shift0 = 0, int cat = 2) {
-    GemmProblem p;
-    p.A = A; p.lda = lda; p.rows_a = rows_a; p.W = W.w; p.ldw = W.in; p.M = Mrows; p.N = W.out; p.K = W.in; p.m_dev = m_dev;
-    p.a_k_wrap = k_wrap; p.a_row_shift0 = shift0; p.f16 = e->f16;
-    ++nl;
-    const int h = prof_begin(cat, 2.0 * (m_dev ? Lest : (double)Mrows) * W.out * W.in);
-    const int rc = gemm_bf16_tcgen05(p, ep, sms, s);
-    prof_end(h);
-    return rc;
-  };
-
-  // ---- K1 front end ----
-  LAUNCH(0, (double)b->n_frames * (160 * 2 + 80 * 4), fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames, e->ft, e->fb, s), "fbank");
-  LAUNCH(0, (double)M * 560 * 4 * 2, lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
-                                   e->taps ? e->tap_feats : nullptr, s), "lfr_cmvn");
-
-  // ---- SAN-M encoder ----
-  AttnProblem ap;
-  ap.q = e->qkv; ap.q_rows = M; ap.ldq = 3 * D; ap.q_col0 = 0;
-  ap.kv = e->qkv; ap.kv_rows = M; ap.ldkv = 3 * D; ap.k_col0 = D; ap.v_col0 = 2 * D;
-  ap.out = e->att; ap.ldo = D;
-  ap.q_row_off = b->d_row_off; ap.q_len = b->d_seg_T; ap.kv_row_off = b->d_row_off; ap.kv_len = b->d_seg_T;
-  ap.work = b->d_work; ap.n_work = b->n_work; ap.n_heads = c.n_heads; ap.f16 = e->f16; ap.num_sms = sms;
-  for (int l = 0; l < c.n_enc; ++l) {
-    const EncLayer& w = e->enc[l];
-    const float* xin = l == 0 ? e->x0 : e->x;
-    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(xin, 0, M, nullptr, w.din, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln1");
-    { GemmEpilogue ep; ep.bias = w.qkv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 3 * D;
-      CKL(gemm(e->hb, w.din, M, w.qkv, M, nullptr, ep, 0, 0, 8), "gemm qkv"); }
-    // The FSMN memory block and the attention both depend only on the QKV projection: run them concurrently
-    // (CUDA-core FMA work next to tensor-core / MUFU work) and join before the output projection.
-    // overlap 1: FSMN enqueued first; overlap 2: attention enqueued first, so its CTAs (two per SM) take the SMs and the
-    // FSMN CTAs fill the register space left over (one per SM) instead of the other way round.
-    const bool fork = e->overlap && !e->profile;
-    cudaStream_t fs = fork ? e->side : s;
-    if (fork) {
-      CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
-      CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
-    }
-    if (fork && e->overlap == 2) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
-    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs, e->f16), "fsmn");
-    if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
-    if (!(fork && e->overlap == 2)) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
-    if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
-    { GemmEpilogue ep; ep.bias = w.out.b; ep.add_bf16 = e->mem; ep.ld_add = D;
-      if (l > 0) { ep.res_f32 = e->x; ep.ld_res = D; }  // layer 0: 560 != 512, no residual
-      ep.out_f32 = e->x; ep.ld_out_f32 = D;
-      CKL(gemm(e->att, D, M, w.out, M, nullptr, ep, 0, 0, 9), "gemm out"); }
-    LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ln2");
-    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
-      CKL(gemm(e->hb, D, M, w.w1, M, nullptr, ep, 0, 0, 10), "gemm ffn1"); }
-    { GemmEpilogue ep; ep.bias = w.w2.b; ep.res_f32 = e->x; ep.ld_res = D; ep.out_f32 = e->x; ep.ld_out_f32 = D;
-      CKL(gemm(e->ffn, c.d_ff, M, w.w2, M, nullptr, ep, 0, 0, 11), "gemm ffn2"); }
-  }
-  LAUNCH(1, (double)M * 512 * 6, layernorm_launch(e->x, 0, M, nullptr, D, e->enc_after.g, e->enc_after.b, c.ln_eps, e->enc_bf16, e->enc_f32,
-                             b->d_row_info, 1, s, e->f16), "after_norm");
-
-  // ---- CIF predictor ----
-  { GemmEpilogue ep; ep.bias = e->pred_conv.b; ep.out_f32 = e->x; ep.ld_out_f32 = D;
-    if (c.pred_residual) { ep.res_f32 = e->enc_f32; ep.ld_res = D; ep.relu = 2; } else { ep.relu = 1; }
-    CKL(gemm(e->enc_bf16, D, M, e->pred_conv, M, nullptr, ep, D, -1), "gemm cif_conv"); }
-  LAUNCH(5, (double)M * 512 * 4, cif_alpha_launch(e->x, M, e->pred_out_w, e->pred_out_b, b->d_row_info, c.tail_threshold, e->alpha, s), "cif_alpha");
-  LAUNCH(5, (double)M * 512 * 4, cif_fire_launch(e->alpha, b->d_row_off, b->d_seg_T, S, c.cif_threshold, e->cif_cur, e->cif_rem, e->fire_val,
-                            b->d_n_tok, e->fire_row, s), "cif_fire");
-  LAUNCH(5, (double)M * 512 * 4, cif_scan_launch(b->d_n_tok, S, b->d_tok_off, b->d_tok_total, s), "cif_scan");
-  LAUNCH(5, (double)M * 512 * 4, cif_embed_launch(e->enc_f32, e->cif_cur, e->cif_rem, e->fire_row, b->d_row_off, b->d_tok_off, S, Lcap, e->y,
-                             e->tok_info, b->d_tok_frame, s), "cif_embed");
-  if (e->taps) CK(cudaMemcpyAsync(e->tap_emb, e->y, (size_t)Lcap * D * 4, cudaMemcpyDeviceToDevice, s), "tap emb");
-
-  // ---- timestamp head (config 3, a16): ConvTranspose x3 -> BiLSTM -> alpha2 -> rescale to token_num -> cif_wo_hidden ----
-  if (c.timestamp) {
-    __nv_bfloat16* up = e->qkv;  // [M, 1536] == [3M, 512]; free between the encoder and the decoder
-    { GemmEpilogue ep; ep.bias = e->us_cnn.b; ep.out_bf16 = up; ep.ld_out_bf16 = 3 * D;
-      CKL(gemm(e->enc_bf16, D, M, e->us_cnn, M, nullptr, ep, 0, 0, 15), "gemm upsample"); }
-    { GemmEpilogue ep; ep.bias = e->blstm_ih.b; ep.out_bf16 = e->us_gx; ep.ld_out_bf16 = 8 * D;
-      CKL(gemm(up, D, (int64_t)3 * M, e->blstm_ih, 3 * M, nullptr, ep, 0, 0, 15), "gemm blstm input"); }
-    LstmParams lp;
-    lp.f16 = e->f16; lp.gx = e->us_gx; lp.ld_gx = 8 * D; lp.whh = e->blstm_hh; lp.seq_off = b->d_us_off; lp.seq_len = b->d_us_len; lp.n_seq = S;
-    lp.n_dir = 2; lp.reverse_mask = 2; lp.out_bf16 = e->us_h; lp.ld_out = 2 * D;
-    LAUNCH(14, 2.0 * 3 * (M - S) * 2 * 4 * D * D, lstm_launch(lp, s), "blstm");
-    LAUNCH(15, (double)3 * M * 1024 * 2, us_alpha_launch(e->us_h, 3 * M, e->us_out_w, e->us_out_b, e->smooth2, e->noise2, e->us_a2, s, e->f16), "us_alpha");
-    LAUNCH(15, (double)3 * M * 12, us_peak_launch(e->us_a2, b->d_us_off, b->d_us_len, b->d_n_tok, S, (float)((double)c.cif_threshold - 1e-4),
-                                                 b->d_us_alphas, b->d_us_peaks, s), "us_peak");
-  }
-
-  // ---- SAN-M decoder ----
-  const int* Ldev = b->d_tok_total;
-  float* tbuf = e->x0;  // [Lcap, 512] fp32 scratch
-  AttnProblem cp;
-  cp.q = e->mem; cp.q_rows = Lcap; cp.ldq = D; cp.q_col0 = 0;
-  cp.kv = e->qkv; cp.kv_rows = M; cp.ldkv = 2 * D; cp.k_col0 = 0; cp.v_col0 = D;
-  cp.out = e->att; cp.ldo = D;
-  cp.q_row_off = b->d_tok_off; cp.q_len = b->d_n_tok; cp.kv_row_off = b->d_row_off; cp.kv_len = b->d_seg_T;
-  cp.work = b->d_work_x; cp.n_work = b->n_work; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
-  auto dec_ffn = [&](const DecLayer& w) -> int {
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln1");
-    { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
-      CKL(gemm(e->hb, D, Lcap, w.w1, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w1"); }
-    LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s, e->f16), "dec ln ff");
-    { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
-      CKL(gemm(e->ffn, c.d_ff, Lcap, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
+  // ---- small batch: replay (or capture) the CUDA graph of its bucket ----
+  const int flags = (e->taps ? 1 : 0) | (b->pcm_is_f32 ? 2 : 0) | (e->topk << 2) | (s == e->stream ? 0 : 1 << 12);
+  const b200pf_engine::GraphKey key(b, b->rows_run, b->n_seg, b->n_work_run, b->n_hw, flags);
+  b200pf_engine::GraphEntry& g = e->graphs[key];
+  g.last_use = ++e->graph_clock;
+  if (g.exec) {
+    CK(cudaGraphLaunch(g.exec, s), "cudaGraphLaunch");
+    b->launches = g.launches;
+    b->topk_run = e->topk;
+    ++e->graph_replays;
     return 0;
-  };
-  for (int l = 0; l < c.n_dec; ++l) {
-    const DecLayer& w = e->dec[l];
-    { int rc = dec_ffn(w); if (rc) return rc; }
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln2");
-    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16), "dec fsmn");
-    LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln3");
-    { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
-      CKL(gemm(e->hb, D, Lcap, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }
-    { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
-      CKL(gemm(e->enc_bf16, D, M, w.kv, M, nullptr, ep, 0, 0, 12), "dec gemm kv"); }
-    LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
-    if (!(c.contextual && l == c.n_dec - 1)) {
-      GemmEpilogue ep; ep.bias = w.out.b; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
-      CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "dec gemm out");
-    } else {
-      // ContextualParaformerDecoder (a16): y is x_self_attn here.  cat = [x_src_attn ; cx] with
-      // cx = bias_decoder(x_self_attn, hotword embeddings); y = x_self_attn + bias_output(cat).
-      __nv_bfloat16* cat = e->qkv;  // [Lcap, 1024]; the cross k/v it held were consumed by the attention above
-      { GemmEpilogue ep; ep.bias = w.out.b; ep.out_bf16 = cat; ep.ld_out_bf16 = 2 * D;
-        CKL(gemm(e->att, D, Lcap, w.out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm out"); }
-      LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, e->bias_ln3.g, e->bias_ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "ctx ln3");
-      { GemmEpilogue ep; ep.bias = e->bias_q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
-        CKL(gemm(e->hb, D, Lcap, e->bias_q, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm q"); }
-      { GemmEpilogue ep; ep.bias = e->bias_kv.b; ep.out_bf16 = e->hw_kv; ep.ld_out_bf16 = 2 * D;
-        CKL(gemm(b->d_hw, D, b->n_hw, e->bias_kv, b->n_hw, nullptr, ep, 0, 0, 12), "ctx gemm kv"); }
-      AttnProblem bp = cp;
-      bp.kv = e->hw_kv; bp.kv_rows = b->n_hw; bp.kv_row_off = b->d_zero; bp.kv_len = b->d_hw_len;
-      LAUNCH(3, 4.0 * Lest * b->n_hw * 512, attention_tcgen05(bp, s), "bias attention");
-      { GemmEpilogue ep; ep.bias = e->bias_out.b; ep.out_bf16 = cat + D; ep.ld_out_bf16 = 2 * D;
-        CKL(gemm(e->att, D, Lcap, e->bias_out, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias out"); }
-      { GemmEpilogue ep; ep.res_f32 = e->y; ep.ld_res = D; ep.out_f32 = e->y; ep.ld_out_f32 = D;
-        CKL(gemm(cat, 2 * D, Lcap, e->bias_output, Lcap, Ldev, ep, 0, 0, 12), "ctx gemm bias_output"); }
-    }
   }
-  { int rc = dec_ffn(e->dec3); if (rc) return rc; }
-  LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, e->dec_after.g, e->dec_after.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec after_norm");
-  CK(cudaMemsetAsync(e->amax, 0, (size_t)Lcap * 8, s), "memset argmax");
-  float* logits_out = e->taps ? e->tap_logits : (e->topk > 0 ? e->full_logits : nullptr);
-  { GemmEpilogue ep; ep.bias = e->vocab.b; ep.argmax = e->amax;
-    if (logits_out) { ep.out_f32 = logits_out; ep.ld_out_f32 = c.vocab; }
-    CKL(gemm(e->hb, D, Lcap, e->vocab, Lcap, Ldev, ep, 0, 0, 13), "gemm vocab"); }
-  LAUNCH(6, Lest * 12, argmax_decode_launch(e->amax, Ldev, Lcap, b->d_ids, s), "argmax decode");
-  if (e->topk > 0) {
-    if (!b->d_topk_lse) {   // first use on this batch: per-batch result buffers (see b200pf_batch_create)
-      const size_t R = (size_t)c.max_rows;
-      CK(cudaMalloc((void**)&b->d_topk_lse, R * (4 + 2 * 4 * B200PF_MAX_TOPK)), "cudaMalloc(topk)");
-      b->d_topk_lp = b->d_topk_lse + R;
-      b->d_topk_id = (int*)(b->d_topk_lp + R * B200PF_MAX_TOPK);
-    }
-    LAUNCH(6, Lest * c.vocab * 4 * 2, logprob_topk_launch(logits_out, c.vocab, Ldev, Lcap, e->topk, b->d_topk_lse, b->d_topk_lp, b->d_topk_id, s), "logprob topk");
+  if (g.seen++ == 0) return enqueue_forward(b, s, false);   // first sight of this bucket: plain launches (also runs every lazy initialisation)
+  // second sight: capture, instantiate, launch
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return enqueue_forward(b, s, false); }
+  const int rc = enqueue_forward(b, s, true);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g.seen = -(1 << 30);   // do not try again for this bucket
+    if (rc != 0) return rc;
+    return enqueue_forward(b, s, false);
   }
-  b->topk_run = e->topk;
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) { cudaGetLastError(); g.seen = -(1 << 30); return enqueue_forward(b, s, false); }
+  g.exec = exec;
+  g.launches = b->launches;
+  ++e->graph_captures;
+  if (e->graphs.size() > 64) {   // keep the most recently used buckets
+    auto victim = e->graphs.end();
+    for (auto it = e->graphs.begin(); it != e->graphs.end(); ++it)
+      if (it->second.exec && it->second.exec != exec && (victim == e->graphs.end() || it->second.last_use < victim->second.last_use)) victim = it;
+    if (victim != e->graphs.end()) { cudaGraphExecDestroy(victim->second.exec); e->graphs.erase(victim); }
+  }
+  CK(cudaGraphLaunch(exec, s), "cudaGraphLaunch");
   return 0;
 }
 

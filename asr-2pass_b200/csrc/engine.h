@@ -3,8 +3,10 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <map>
 #include <memory>
 #include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -118,6 +120,16 @@ struct b200pf_engine {
   __nv_bfloat16* us_h = nullptr;        // [3R, 1024] bf16  BiLSTM output
   float* us_a2 = nullptr;               // [3R] alpha2 before the per-segment rescale (results: b200pf_batch::d_us_*)
   __nv_bfloat16* hw_kv = nullptr;       // [max_hotwords, 1024] bf16  bias_decoder k/v of the hotword embeddings
+  // CUDA graphs of the forward for SMALL batches (options "graphs", "graph_max_rows"): a batch-1 forward is ~600 dependent
+  // launches, i.e. bound by launch latency; its layout is padded to a bucket (rows to a multiple of 32, with gap rows) so that
+  // batches of similar size share one captured graph, which replays with a single launch call.
+  int use_graphs = 1;
+  int graph_max_rows = 4096;
+  typedef std::tuple<const void*, int, int, int, int, int> GraphKey;   // batch, rows_run, segments, work items, hotwords, flags
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t last_use = 0; int seen = 0; };
+  std::map<GraphKey, GraphEntry> graphs;
+  uint64_t graph_clock = 0;
+  long long graph_replays = 0, graph_captures = 0;
   // per-category CUDA-event timing of the launches (option "profile")
   int profile = 0;
   struct ProfRec { cudaEvent_t a, b; int cat; double work; };
@@ -180,6 +192,9 @@ struct b200pf_batch {
   std::vector<int> dev_of_in;   // caller index -> device segment or -1
   std::vector<int> T_in;        // caller index -> T
   int rows = 0, n_frames = 0, n_work = 0;
+  int rows_run = 0, n_frames_run = 0, n_work_run = 0;   // what the kernels are launched over: == the real counts, or the padded
+                                                        // bucket of a graph-able small batch (extra rows are gap rows)
+  bool graph_ok = false;
   int64_t launches = 0;
   double flops = 0.0;
   int64_t last_tokens = -1;     // tokens of the last collected run and the row count it belonged to (profiling: exact decoder FLOPs)

@@ -13,6 +13,9 @@
 //                 columns into a swizzled 4 KB smem tile and one lane issues cp.async.bulk.tensor (full 128-byte
 //                 lines, no LSU / register traffic, asynchronous).  The general path stages through a per-warp smem
 //                 tile so every global load and store is a run of full 32-byte sectors; optional fused argmax.
+#include <mutex>
+#include <unordered_map>
+
 #include "gemm.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -492,16 +495,37 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
-                           uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
-
-int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                         uint32_t box_rows, uint32_t box_cols) {
-  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_rows, box_cols);
-}
+// Tensor maps are pure functions of (address, extents, pitch, box, type) and encoding one costs the host 1-2 us; a forward makes
+// ~900 of them (three per GEMM, two per attention launch), which is most of the host time of a latency-bound batch-1 call.
+// They are cached by exactly those fields; callers keep the set of distinct extents small by rounding row extents up to whole
+// tiles inside their buffers' capacity (see gemm_bf16_tcgen05).  An entry never goes stale: it describes addresses, not contents.
+namespace {
+struct TmapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; int dt;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols && dt == o.dt;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 1315423911ull + k.ld * 2654435761ull + ((uint64_t)k.box_rows << 32) + ((uint64_t)k.box_cols << 8) + (uint64_t)k.dt);
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
 
 static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
                            uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, (int)dt};
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; return 0; }
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[2] = {cols, rows};
@@ -511,7 +535,24 @@ static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_by
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();   // a bound, not a policy: steady-state forwards use a few hundred entries
+  g_tmap_cache.emplace(key, *out);
+  return 0;
+}
+
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_rows, box_cols);
+}
+
+// Row extent of a tensor map over a buffer that holds `cap` rows of which `used` matter: whole 256-row tiles, so that a handful
+// of extents covers every batch size (cache hits), never more than the buffer holds.  cap <= used (unknown capacity): exact.
+static uint64_t tile_extent(int64_t used, int64_t cap) {
+  if (cap <= used) return (uint64_t)used;
+  const int64_t r = (used + 255) & ~int64_t(255);
+  return (uint64_t)(r < cap ? r : cap);
 }
 
 int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, cudaStream_t stream) {
@@ -530,7 +571,7 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (rc) return rc;
   CUtensorMap tmA, tmB;
   const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;
-  rc = make_tmap_bf16_sw128(&tmA, p.A, (uint64_t)(p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
+  rc = make_tmap_bf16_sw128(&tmA, p.A, tile_extent(p.M, p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
   if (rc) return rc;
   rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
@@ -543,10 +584,10 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
                       (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (e.ld_out_f32 & 3) == 0;
   CUtensorMap tmC = tmA;  // placeholder for the general path
   if (fast) {
-    rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);
+    rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, tile_extent(p.M, p.rows_c), (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);
     if (rc) return rc;
   } else if (f32tma) {
-    rc = make_tmap_sw128(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.out_f32, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)e.ld_out_f32, 32, 32);
+    rc = make_tmap_sw128(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.out_f32, tile_extent(p.M, p.rows_c), (uint64_t)p.N, (uint64_t)e.ld_out_f32, 32, 32);
     if (rc) return rc;
   }
   KArgs a;

@@ -29,7 +29,8 @@ struct GemmEpilogue {
 
 struct GemmProblem {
   const __nv_bfloat16* A = nullptr;  // [rows_a, lda]
-  int64_t rows_a = 0;                // rows addressable through the tensor map (>= M)
+  int64_t rows_a = 0;                // rows the A buffer holds (>= M; 0 = M): tensor-map extents are whole tiles inside it
+  int64_t rows_c = 0;                // rows the output buffers hold (0 = M: exact extent, the last tile's stores are clipped at M)
   int lda = 0;
   const __nv_bfloat16* W = nullptr;  // [N, ldw]
   int ldw = 0;

@@ -118,6 +118,11 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
  * milliseconds, algorithmic work (FLOPs for the two tensor-core categories, bytes for the rest) and launch
  * counts; `reset` clears the accumulators.  Arrays have 16 entries. */
 int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, double* ms, double* work, long long* launches);
+/* Small batches (rows <= option "graph_max_rows", default 4096; option "graphs" = 0 turns it off) run as CUDA graphs: the layout
+ * is padded to a bucket (rows to a multiple of 32 with gap rows), the first batch of a bucket is launched kernel by kernel, the
+ * second is captured and every later one replays the graph with one launch call.  Results are bit-identical either way.
+ * Counters: graphs captured / replays so far / graphs currently cached. */
+int b200pf_engine_graph_stats(const b200pf_engine* e, long long* captures, long long* replays, int* cached);
 /* The CUDA stream (cudaStream_t) the engine enqueues on when `stream` arguments are NULL. */
 void* b200pf_engine_stream(b200pf_engine* e);
 /* A second stream owned by the engine, meant for b200pf_batch_stage_*: copies of the next batch then overlap the
