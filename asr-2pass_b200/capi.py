@@ -131,7 +131,7 @@ HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf
                 "b200pf_host_punc_add_batch", "b200pf_host_punc_online_add_scripted", "b200pf_host_punc_online_create",
                 "b200pf_host_punc_online_destroy", "b200pf_host_punc_online_add", "b200pf_host_sentence_stamps", "b200pf_host_offline_init_kv",
                 "b200pf_host_offline_infer_full", "b200pf_host_tpass_init_kv", "b200pf_host_tpass_online_init", "b200pf_host_tpass_uninit",
-                "b200pf_host_tpass_online_uninit", "b200pf_host_tpass_infer", "b200pf_host_vad_segments_streaming", "b200pf_host_expand_posteriors"]
+                "b200pf_host_tpass_online_uninit", "b200pf_host_tpass_infer", "b200pf_host_vad_segments_streaming", "b200pf_host_expand_posteriors", "b200pf_host_model_forward_timed"]
 
 
 def host_lib():
@@ -358,6 +358,21 @@ class OfflineHandle:
         if r < 0:
             raise B200PFError("Model::Forward failed")
         return buf.value.decode("utf-8").split("\n")
+
+    def model_forward_timed(self, segments_f32, iters=3):
+        """Mean milliseconds per Model::Forward(float**, int*) call, timed inside the host library (no ctypes marshalling in the
+        timed region), and the number of non-empty strings of the last call."""
+        segs = [np.ascontiguousarray(s, dtype=np.float32) for s in segments_f32]
+        n = len(segs)
+        ptrs = (c_f32p * n)(*[s.ctypes.data_as(c_f32p) for s in segs])
+        lens = np.asarray([len(s) for s in segs], np.int32)
+        ms = C.c_double()
+        H = host_lib()
+        H.b200pf_host_model_forward_timed.argtypes = [C.c_void_p, C.POINTER(c_f32p), c_i32p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        r = H.b200pf_host_model_forward_timed(self.h, ptrs, _p(lens, c_i32p), n, int(iters), C.byref(ms))
+        if r < 0:
+            raise B200PFError("Model::Forward failed")
+        return ms.value, r
 
     def segments_per_device(self):
         out = (C.c_longlong * 16)()

@@ -64,7 +64,8 @@ struct b200pf_engine {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;          // FSMN memory block runs here, concurrently with the attention kernel
-  cudaStream_t copy = nullptr;          // host<->device staging of the NEXT batch (b200pf_engine_copy_stream)
+  cudaStream_t copy = nullptr;          // host->device staging of the NEXT batch (b200pf_engine_copy_stream)
+  cudaStream_t d2h = nullptr;           // device->host result reads of a FINISHED batch (b200pf_batch_collect), while the next one computes
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 2;
   int f16 = 1;                          // 16-bit operand format of weights and activations: 0 bf16, 1 IEEE fp16 (cfg.precision)
@@ -178,6 +179,7 @@ struct b200pf_batch {
   uint8_t* h_res = nullptr;   // pinned: n_tok[S] tok_off[S+1] ids[R] tok_frame[R]
   float* h_us = nullptr;      // pinned: us_alphas[3R] us_peaks[3R] (timestamp models)
   uint8_t* h_topk = nullptr;  // pinned: lse[R] lp[R*32] ids[R*32], allocated on first use
+  int16_t* h_stage = nullptr; // pinned int16 staging of float input (b200pf_batch_stage_f32 fast path), allocated on first use
   float* d_us_alphas = nullptr;   // [3R] timestamp models: us_alphas / us_cif_peak of THIS batch (one allocation)
   float* d_us_peaks = nullptr;    // [3R]
   float* d_topk_lse = nullptr;    // [R]      pruned posteriors of THIS batch (one allocation, made on the first run that asks)
@@ -200,5 +202,6 @@ struct b200pf_batch {
   int64_t last_tokens = -1;     // tokens of the last collected run and the row count it belonged to (profiling: exact decoder FLOPs)
   int last_tokens_rows = -1;
   cudaEvent_t staged = nullptr;
+  cudaEvent_t done = nullptr;   // recorded after the last kernel of b200pf_batch_run: collect waits for THIS batch only
   bool collected = false;
 };

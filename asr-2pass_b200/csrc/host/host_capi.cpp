@@ -376,6 +376,27 @@ int b200pf_host_model_forward_hw(void* h_offline, const float* const* din, const
   for (int i = 0; i < n; ++i) { if (i) joined += "\n"; joined += r[i]; }
   return CopyOut(joined, out, cap);
 }
+// Times `iters` calls of Model::Forward(float**, int*, ...) from C++ (std::chrono around the virtual call, strings included): what a
+// reference caller pays per call, without the ctypes marshalling of the Python test harness.  ms_out = mean milliseconds per call;
+// returns the number of non-empty result strings of the last call.
+int b200pf_host_model_forward_timed(void* h_offline, const float* const* din, const int* len, int n, int iters, double* ms_out) {
+  funasr_b200::Model* m = FunOfflineModel(h_offline);
+  if (!m || iters <= 0) return -1;
+  std::vector<float*> ptrs(n);
+  for (int i = 0; i < n; ++i) ptrs[i] = const_cast<float*>(din[i]);
+  std::vector<int> l(len, len + n);
+  std::vector<std::vector<float>> hw(1, std::vector<float>(512, 0.f));
+  int nonempty = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int it = 0; it < iters; ++it) {
+    std::vector<std::string> r = m->Forward(ptrs.data(), l.data(), true, hw, nullptr, n);
+    if (it == iters - 1)
+      for (const auto& x : r) nonempty += !x.empty();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (ms_out) *ms_out = std::chrono::duration<double, std::milli>(t1 - t0).count() / iters;
+  return nonempty;
+}
 // Model::Forward over float segments (the plugin seam itself): returns the '\n'-joined result strings.
 int b200pf_host_model_forward(void* h_offline, const float* const* din, const int* len, int n, char* out, int cap) {
   funasr_b200::Model* m = FunOfflineModel(h_offline);

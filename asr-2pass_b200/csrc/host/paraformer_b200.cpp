@@ -332,12 +332,20 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
   }
   struct Sub { int start, end; int64_t samples; };
   std::vector<Sub> subs;
-  // The reference's argument form -- float samples in pageable memory, 4 bytes each -- is copied by the driver through its own
-  // staging buffer at a fraction of the PCIe rate, and the calling thread waits for it.  Sub-batches are therefore capped well
-  // below the engine's capacity on this path, so that the copy of sub-batch i+1 runs while the GPU computes sub-batch i (one
-  // engine-sized batch would expose the whole copy: 708 MB for the configs[1] workload).  B200PF_F32_SUB_ROWS overrides.
-  static const int64_t f32_rows = getenv("B200PF_F32_SUB_ROWS") ? atoll(getenv("B200PF_F32_SUB_ROWS")) : 40960;
-  const int64_t row_cap = (!pcm && !seg16 && f32_rows > 0 && f32_rows < max_rows_) ? f32_rows : (int64_t)max_rows_;
+  // Host buffers are usually pageable: the driver copies them through its own staging buffer at a fraction of the PCIe rate and
+  // the calling thread waits for it.  A call whose segments would fit ONE engine-sized batch would expose that whole copy (708 MB
+  // of float samples for the configs[1] workload).  Larger calls are therefore cut into sub-batches that GROW geometrically
+  // from 8192 rows (x 4 each, up to the engine's capacity): only the first, small copy is exposed, every later copy runs while
+  // the GPU computes the sub-batch before it, and most rows still travel in large batches.  B200PF_SUB_ROWS fixes the cap instead.
+  static const int64_t env_rows = getenv("B200PF_SUB_ROWS") ? atoll(getenv("B200PF_SUB_ROWS")) : 0;
+  int64_t total_rows = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    const int64_t ns = seg16 ? len16[i] : (pcm ? offsets[i + 1] - offsets[i] : (int64_t)len[i]);
+    const int T = b200pf_num_lfr_frames(ns);
+    total_rows += T > 0 ? T + 1 : 0;
+  }
+  const bool grow = env_rows <= 0 && total_rows > 16384;
+  int64_t row_cap = grow ? std::min<int64_t>(max_rows_, 8192) : (env_rows > 0 ? std::min<int64_t>(max_rows_, env_rows) : (int64_t)max_rows_);
   int start = 0;
   while (start < n_seg) {
     int64_t rows = 0, samples = 0;
@@ -353,6 +361,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
     }
     subs.push_back(Sub{start, end, samples});
     start = end;
+    if (grow) row_cap = std::min<int64_t>(max_rows_, row_cap * 4);
   }
   auto stage = [&](size_t i) {
     const Sub& sb = subs[i];
@@ -360,17 +369,22 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
     return StageSlot((int)(i & 1), pcm, pcm ? offsets + sb.start : nullptr, pcm ? nullptr : din + sb.start, pcm ? nullptr : len + sb.start,
                      sb.end - sb.start, sb.samples, hw_emb);
   };
-  std::vector<char> ok(subs.size(), 0);
-  ok[0] = stage(0);
-  for (size_t i = 0; i < subs.size(); ++i) {
-    bool running = false;
+  // Software pipeline over two slots: sub-batch i+1 is staged AND enqueued before sub-batch i is collected, so the GPU goes
+  // from one forward straight into the next while the host reads i's results and builds its strings (a batch's results live in
+  // its own buffers; collect waits for that batch's completion event only).
+  std::vector<char> ok(subs.size(), 0), running(subs.size(), 0);
+  auto launch = [&](size_t i) {
+    ok[i] = stage(i);
     if (ok[i]) {
-      running = b200pf_batch_run(slots_[i & 1].batch, nullptr) == 0;   // asynchronous; waits for the slot's staged event
-      if (!running) fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error());
+      running[i] = b200pf_batch_run(slots_[i & 1].batch, nullptr) == 0;   // asynchronous; waits for the slot's staged event
+      if (!running[i]) fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error());
     }
-    if (i + 1 < subs.size()) ok[i + 1] = stage(i + 1);                  // host copies while the GPU computes sub-batch i
+  };
+  launch(0);
+  for (size_t i = 0; i < subs.size(); ++i) {
+    if (i + 1 < subs.size()) launch(i + 1);          // slot (i+1)&1 was collected one iteration ago
     bool done = false;
-    if (running) {
+    if (running[i]) {
       std::vector<std::string> part;
       if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder)) {
         for (int k = 0; k < subs[i].end - subs[i].start; ++k) results[subs[i].start + k] = part[k];

@@ -56,6 +56,9 @@ int b200pf_host_tpass_infer(void* tpass, void* online, const char* buf, int n_by
  * scores gives b200pf_host_vad_segments' result. */
 int b200pf_host_vad_segments_streaming(const float* sil_prob, int n_frames, const int* chunk_len, int n_chunks, int max_end_sil_ms, int max_seg_ms,
                                        float thres, int* out, int cap);
+/* `iters` calls of funasr::Model::Forward(float** din, int* len, ...) timed inside the library (mean milliseconds per call in *ms_out,
+ * result strings built); returns the number of non-empty strings of the last call, -1 on a bad handle. */
+int b200pf_host_model_forward_timed(void* h_offline, const float* const* din, const int* len, int n, int iters, double* ms_out);
 /* pf::host::ExpandPrunedPosteriors: b200pf_result.topk_logprob / topk_ids [rows, k] -> dense log-softmax rows [rows, vocab] in the
  * layout WfstDecoder::Search (wfst-decoder.cpp:27-57) and CtcPrefixDecoder::CtcSearch (ctc-prefix-decoder.cpp:157) read. */
 int b200pf_host_expand_posteriors(const float* topk_logprob, const int32_t* topk_ids, int rows, int k, int vocab, float* dense);

@@ -379,6 +379,16 @@ def test_batch_invariance_and_input_formats(capi, synth, small):
     assert np.array_equal(rf["token_ids"], res["token_ids"]) and np.array_equal(rf["fire_frames"], res["fire_frames"])
     r2 = b.forward_s16(np.concatenate(segs), offs)                 # run-to-run determinism
     assert np.array_equal(r2["token_ids"], res["token_ids"])
+    # float input that is NOT int16 / 32768 (e.g. resampled audio) cannot take the exact int16 staging path: it is copied as
+    # float, and the front end follows the reference's float arithmetic (paraformer.cpp:312-314) to the same 1e-4
+    eng = small["eng"]
+    xf = [(s.astype(np.float32) / np.float32(32768)) * np.float32(0.37) + np.float32(1e-5) for s in segs[:2]]
+    eng.set_option("taps", 1)
+    rf2 = b.forward_f32(xf)
+    for i, x in enumerate(xf):
+        fb = F.fbank(x)
+        assert np.abs(b.tap("fbank", i) - fb).max() <= 1e-4
+    assert rf2["token_counts"][0] > 0
 
 
 def test_capacity_and_argument_errors(capi, synth, small):
