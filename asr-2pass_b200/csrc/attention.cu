@@ -49,6 +49,7 @@ struct AArgs {
   int n_work, n_heads;
   float scale_log2e;
   int dbg;   // micro-benchmark ablations only (B200PF_ATTN_DBG): 1 = no exponentials; 0 in the product
+  long long* trace;   // ablation 64: CTA 0 writes clock64() stamps of its first 64 key blocks here (4 per block)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -176,9 +177,11 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (lane == 0) {
       Stream st(a, blockIdx.x, gridDim.x);
       int pend_r = 0, pend_c = 0, pend_g = -1;   // V load of the previous block: K runs one block ahead of V
+      bool pend_skip = false;
       auto load_v = [&]() {
         const int stage = pend_g % KV_STAGES;
         mbar_wait(&v_empty[stage], (uint32_t)(((pend_g / KV_STAGES) & 1) ^ 1));
+        if (pend_skip) { mbar_arrive(&v_full[stage]); return; }   // ablation 32: pretend the sibling query tile loaded this block
         mbar_arrive_expect_tx(&v_full[stage], K_BYTES);
         uint8_t* dst = sV + stage * K_BYTES;
         tma_load_2d(dst, &tmKV, &v_full[stage], pend_c, pend_r);
@@ -194,12 +197,17 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int stage = st.g % KV_STAGES;
         const int r = st.kv_row + st.j * BKV;
         mbar_wait(&k_empty[stage], (uint32_t)(((st.g / KV_STAGES) & 1) ^ 1));
-        mbar_arrive_expect_tx(&k_full[stage], K_BYTES);
-        uint8_t* dst = sK + stage * K_BYTES;
-        tma_load_2d(dst, &tmKV, &k_full[stage], a.k_col0 + st.h * HD, r);
-        tma_load_2d(dst + K_BYTES / 2, &tmKV, &k_full[stage], a.k_col0 + st.h * HD + 64, r);
+        const bool skip = (a.dbg & 32) && (st.q0 & 128);
+        if (skip) {
+          mbar_arrive(&k_full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&k_full[stage], K_BYTES);
+          uint8_t* dst = sK + stage * K_BYTES;
+          tma_load_2d(dst, &tmKV, &k_full[stage], a.k_col0 + st.h * HD, r);
+          tma_load_2d(dst + K_BYTES / 2, &tmKV, &k_full[stage], a.k_col0 + st.h * HD + 64, r);
+        }
         if (pend_g >= 0) load_v();
-        pend_r = r; pend_c = a.v_col0 + st.h * HD; pend_g = st.g;
+        pend_r = r; pend_c = a.v_col0 + st.h * HD; pend_g = st.g; pend_skip = skip;
         st.advance();
       }
       if (pend_g >= 0) load_v();
@@ -214,8 +222,10 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       Stream pv_it(a, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
       auto issue_s = [&](bool after_pv) {
         const int g = s_it.g, stage = g % KV_STAGES, sb = g & 1;
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 4] = clock64();   // issue_s(g) entered
         if (s_it.j == 0) mbar_wait(q_full, (uint32_t)(s_it.hc & 1));
         mbar_wait(&k_full[stage], (uint32_t)((g / KV_STAGES) & 1));
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 5] = clock64();   // K of block g is there
         // S buffer sb still holds P of block g - 2, the A operand of that block's P V.  No wait is needed: that MMA was issued
         // earlier by this same thread and the tensor pipe executes a thread's MMAs in issue order, so this S cannot overwrite the
         // columns before P V has read them (an explicit wait on its commit cost a barrier round trip per key block: the
@@ -232,6 +242,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_bf16(tmem_base + sb * BKV, da, db, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[sb]);
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 0] = clock64();   // S of block g committed
         umma_commit(&k_empty[stage]);
         if (s_it.j + 1 == s_it.nb) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
         s_it.advance();
@@ -247,8 +258,10 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         const int g = pv_it.g, stage = g % KV_STAGES;
         mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1));
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 3] = clock64();         // MMA thread saw P of block g
         if (pv_it.j == 0) mbar_wait(o_empty, (uint32_t)((pv_it.hc & 1) ^ 1));   // the previous head's O has been read out
         mbar_wait(&v_full[stage], (uint32_t)((g / KV_STAGES) & 1));
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 6] = clock64();   // V of block g is there
         tc_fence_after();
         const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);   // P sits where S of this block was: 8 columns per 16 keys
         const uint32_t v_addr = smem_u32(sV + stage * K_BYTES);
@@ -260,6 +273,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         umma_commit(&v_empty[stage]);
         umma_commit(p_empty);
+        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 7] = clock64();   // P V of block g issued and committed
         if (pv_it.j + 1 == pv_it.nb) umma_commit(o_full);
         pv_it.advance();
         if (deferred) issue_s(true);
@@ -278,6 +292,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const bool warp_active = st.q0 + quarter * 32 < st.Tq && !(a.dbg & 16);   // warp-uniform: does this warp own any real query row?
       if (st.j == 0) { m = -INFINITY; l = 0.f; m_used = 0.f; }
       mbar_wait(&s_full[sb], (uint32_t)((g >> 1) & 1));
+      if ((a.dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 1] = clock64();   // softmax warp saw S of block g
       tc_fence_after();
       const int nvalid = st.keys();
       bool need = false;
@@ -385,6 +400,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_before();
       }
       __syncwarp();
+      if ((a.dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 2] = clock64();   // softmax warp arrives for block g
       if (lane == 0) mbar_arrive(&p_full[sb]);
       if (st.j + 1 == st.nb) {
         // ---- this head's output ----
@@ -484,6 +500,12 @@ AArgs make_args(const AttnProblem& p) {
   a.scale_log2e = p.scale * 1.4426950408889634f;
   static const int dbg = getenv("B200PF_ATTN_DBG") ? atoi(getenv("B200PF_ATTN_DBG")) : 0;
   a.dbg = dbg;
+  a.trace = nullptr;
+  if (dbg & 64) {
+    static long long* buf = nullptr;
+    if (!buf) { cudaMalloc((void**)&buf, 64 * 8 * sizeof(long long)); cudaMemset(buf, 0, 64 * 8 * sizeof(long long)); }
+    a.trace = buf;
+  }
   return a;
 }
 
@@ -509,6 +531,15 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   const dim3 grid(units < resident ? units : resident);
   if (p.f16) return launch_kernel(attn_heads_kernel<true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
   return launch_kernel(attn_heads_kernel<false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+}
+
+// ablation 64: the stamps of the last launch (host copy), for tools/bench_attn.py
+extern "C" int b200pf_attn_trace_read(long long* out) {
+  AttnProblem dummy;
+  const AArgs a = make_args(dummy);
+  if (!a.trace) return -1;
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpy(out, a.trace, 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
 }
 
 int attention_check_kernel(const AttnProblem& p, cudaStream_t stream) {
