@@ -35,7 +35,11 @@ constexpr int K_BYTES = BKV * HD * 2;      // 16384: two 64x64 boxes
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 256;
 // 96 KB + barriers: two CTAs fit one SM (2 x 256 TMEM columns), so one CTA's softmax is covered by the other's MMAs.
-constexpr int kSmemBytes = Q_BYTES + 2 * KV_STAGES * K_BYTES + 256;
+// + this CTA's unit table (below): every role reads its units from shared memory instead of chasing work[] -> q_len[] ->
+// row_off[] through global memory at each unit boundary (seven role streams x ~1.5 us of dependent loads per unit, for
+// units that last 3-4 key blocks on the benchmark's segment lengths).
+constexpr int kMaxUnits = 192;             // one table entry per thread of the CTA; later rounds fall back to global loads
+constexpr int kSmemBytes = Q_BYTES + 2 * KV_STAGES * K_BYTES + 256 + kMaxUnits * 32;
 
 struct AArgs {
   const int* q_row_off;
@@ -81,32 +85,47 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 // The (work unit, key block) stream of one CTA; a unit is one head of one (segment, query tile) item.  All three roles walk it
 // with their own copy; `g` counts key blocks and `hc` units since the CTA started -- every ring stage and barrier phase is
 // derived from them.
+struct UnitRec { int q0, Tq, Tk, q_row, kv_row, h, valid, pad; };   // 32 bytes
+
 struct Stream {
   const AArgs& a;
+  const UnitRec* table;
   int cta, n_cta, round, n_units;
   int q0, Tq, Tk, nb, q_row, kv_row;
   int h, j, g, hc;
   bool valid;
-  __device__ Stream(const AArgs& args, int cta_, int n_cta_) : a(args), cta(cta_), n_cta(n_cta_), round(0), j(0), g(0), hc(0) {
+  __device__ Stream(const AArgs& args, const UnitRec* table_, int cta_, int n_cta_)
+      : a(args), table(table_), cta(cta_), n_cta(n_cta_), round(0), j(0), g(0), hc(0) {
     n_units = a.n_work * a.n_heads;
     valid = load_unit();
+  }
+  // Round r of CTA `cta`: the unit's record, straight from global memory (table fill and rounds beyond the table).
+  static __device__ UnitRec fetch(const AArgs& a, int n_units, int n_cta, int cta, int round) {
+    UnitRec u;
+    u.valid = 0;
+    const int unit = round * n_cta + ((round & 1) ? n_cta - 1 - cta : cta);
+    if (round * n_cta >= n_units || unit >= n_units) return u;
+    const AttnWork w = a.work[unit / a.n_heads];
+    u.Tq = a.q_len[w.seg];
+    u.Tk = a.kv_len[w.seg];
+    if (w.q0 < u.Tq && u.Tk > 0) {
+      u.valid = 1;
+      u.h = unit % a.n_heads;
+      u.q0 = w.q0;
+      u.q_row = a.q_row_off[w.seg] + w.q0;
+      u.kv_row = a.kv_row_off[w.seg];
+    }
+    return u;
   }
   // Items are sorted by cost (longest segment first) and the heads of an item are consecutive units; round r hands unit
   // r * n_cta + (cta or n_cta - 1 - cta) to this CTA -- a snake, so no CTA gets the longer unit of every round.
   __device__ bool load_unit() {
     for (;; ++round) {
       if (round * n_cta >= n_units) return false;
-      const int unit = round * n_cta + ((round & 1) ? n_cta - 1 - cta : cta);
-      if (unit >= n_units) continue;
-      const AttnWork w = a.work[unit / a.n_heads];
-      Tq = a.q_len[w.seg];
-      Tk = a.kv_len[w.seg];
-      if (w.q0 < Tq && Tk > 0) {
-        h = unit % a.n_heads;
-        q0 = w.q0;
+      const UnitRec u = round < kMaxUnits ? table[round] : fetch(a, n_units, n_cta, cta, round);
+      if (u.valid) {
+        h = u.h; q0 = u.q0; Tq = u.Tq; Tk = u.Tk; q_row = u.q_row; kv_row = u.kv_row;
         nb = (Tk + BKV - 1) / BKV;
-        q_row = a.q_row_off[w.seg] + w.q0;
-        kv_row = a.kv_row_off[w.seg];
         return true;
       }
     }
@@ -147,6 +166,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* o_full = bars + 16;             // 1
   uint64_t* o_empty = bars + 17;            // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  UnitRec* units = reinterpret_cast<UnitRec*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1 && lane == 0) {
@@ -172,68 +192,80 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const uint32_t tmem_o = tmem_base + 128;
   pdl_wait();   // q_len of the decoder is produced by the CIF kernels; nothing above touches activations
   pdl_launch_dependents();
+  {
+    static_assert(kMaxUnits == kThreads, "one table entry per thread");
+    const int n_units = a.n_work * a.n_heads;
+    const UnitRec u = Stream::fetch(a, n_units, gridDim.x, blockIdx.x, threadIdx.x);
+    units[threadIdx.x] = u;
+  }
+  __syncthreads();
 
+  // Warps 0 and 1 run CONVERGED: all 32 lanes walk the stream and wait on the barriers; only the TMA / tcgen05 instructions
+  // sit under elect_one().  Inside an `if (lane == 0)` region the compiler has to wrap every UTCHMMA / UTCBAR / UTMALDG in a
+  // "waterfall" loop (ELECT + branch, operands through per-thread registers): ~75 cycles per instruction, and with 12 MMAs and 4
+  // commits per 64-key block the issuing thread alone took ~2300 cycles per block (clock64 trace, tools/trace_attn.py) -- more
+  // than the tensor pipe (512) or the softmax (~1000) need.
   if (warp == 0) {
-    if (lane == 0) {
-      Stream st(a, blockIdx.x, gridDim.x);
-      int pend_r = 0, pend_c = 0, pend_g = -1;   // V load of the previous block: K runs one block ahead of V
-      bool pend_skip = false;
-      auto load_v = [&]() {
-        const int stage = pend_g % KV_STAGES;
-        mbar_wait(&v_empty[stage], (uint32_t)(((pend_g / KV_STAGES) & 1) ^ 1));
-        if (pend_skip) { mbar_arrive(&v_full[stage]); return; }   // ablation 32: pretend the sibling query tile loaded this block
+    Stream st(a, units, blockIdx.x, gridDim.x);
+    int pend_r = 0, pend_c = 0, pend_g = -1;   // V load of the previous block: K runs one block ahead of V
+    auto load_v = [&]() {
+      const int stage = pend_g % KV_STAGES;
+      mbar_wait(&v_empty[stage], (uint32_t)(((pend_g / KV_STAGES) & 1) ^ 1));
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[stage], K_BYTES);
         uint8_t* dst = sV + stage * K_BYTES;
         tma_load_2d(dst, &tmKV, &v_full[stage], pend_c, pend_r);
         tma_load_2d(dst + K_BYTES / 2, &tmKV, &v_full[stage], pend_c + 64, pend_r);
-      };
-      while (st.valid) {
-        if (st.j == 0) {
-          mbar_wait(q_empty, (uint32_t)((st.hc & 1) ^ 1));
+      }
+      __syncwarp();
+    };
+    while (st.valid) {
+      if (st.j == 0) {
+        mbar_wait(q_empty, (uint32_t)((st.hc & 1) ^ 1));
+        if (elect_one()) {
           mbar_arrive_expect_tx(q_full, Q_BYTES);
           tma_load_2d(sQ, &tmQ, q_full, a.q_col0 + st.h * HD, st.q_row);
           tma_load_2d(sQ + Q_BYTES / 2, &tmQ, q_full, a.q_col0 + st.h * HD + 64, st.q_row);
         }
-        const int stage = st.g % KV_STAGES;
-        const int r = st.kv_row + st.j * BKV;
-        mbar_wait(&k_empty[stage], (uint32_t)(((st.g / KV_STAGES) & 1) ^ 1));
-        const bool skip = (a.dbg & 32) && (st.q0 & 128);
-        if (skip) {
-          mbar_arrive(&k_full[stage]);
-        } else {
-          mbar_arrive_expect_tx(&k_full[stage], K_BYTES);
-          uint8_t* dst = sK + stage * K_BYTES;
-          tma_load_2d(dst, &tmKV, &k_full[stage], a.k_col0 + st.h * HD, r);
-          tma_load_2d(dst + K_BYTES / 2, &tmKV, &k_full[stage], a.k_col0 + st.h * HD + 64, r);
-        }
-        if (pend_g >= 0) load_v();
-        pend_r = r; pend_c = a.v_col0 + st.h * HD; pend_g = st.g; pend_skip = skip;
-        st.advance();
+        __syncwarp();
       }
+      const int stage = st.g % KV_STAGES;
+      const int r = st.kv_row + st.j * BKV;
+      mbar_wait(&k_empty[stage], (uint32_t)(((st.g / KV_STAGES) & 1) ^ 1));
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&k_full[stage], K_BYTES);
+        uint8_t* dst = sK + stage * K_BYTES;
+        tma_load_2d(dst, &tmKV, &k_full[stage], a.k_col0 + st.h * HD, r);
+        tma_load_2d(dst + K_BYTES / 2, &tmKV, &k_full[stage], a.k_col0 + st.h * HD + 64, r);
+      }
+      __syncwarp();
       if (pend_g >= 0) load_v();
+      pend_r = r; pend_c = a.v_col0 + st.h * HD; pend_g = st.g;
+      st.advance();
     }
-    __syncwarp();
+    if (pend_g >= 0) load_v();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s0 = umma_idesc_h16(F16, BQ, 0);           // N filled in per block
-      constexpr uint32_t idesc_pv = umma_idesc_h16(F16, BQ, HD, 0, 1);    // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      Stream s_it(a, blockIdx.x, gridDim.x);    // next block whose S is to be issued
-      Stream pv_it(a, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
-      auto issue_s = [&](bool after_pv) {
-        const int g = s_it.g, stage = g % KV_STAGES, sb = g & 1;
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 4] = clock64();   // issue_s(g) entered
-        if (s_it.j == 0) mbar_wait(q_full, (uint32_t)(s_it.hc & 1));
-        mbar_wait(&k_full[stage], (uint32_t)((g / KV_STAGES) & 1));
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 5] = clock64();   // K of block g is there
-        // S buffer sb still holds P of block g - 2, the A operand of that block's P V.  No wait is needed: that MMA was issued
-        // earlier by this same thread and the tensor pipe executes a thread's MMAs in issue order, so this S cannot overwrite the
-        // columns before P V has read them (an explicit wait on its commit cost a barrier round trip per key block: the
-        // micro-benchmark's barrier skeleton alone ran at 0.77 us per block with it).
-        (void)after_pv;
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + stage * K_BYTES);
-        const uint32_t idesc = idesc_s0 | ((uint32_t)(s_it.keys16() >> 3) << 17);
+    constexpr uint32_t idesc_s0 = umma_idesc_h16(F16, BQ, 0);           // N filled in per block
+    constexpr uint32_t idesc_pv = umma_idesc_h16(F16, BQ, HD, 0, 1);    // B (= V) is MN-major
+    const uint32_t q_addr = smem_u32(sQ);
+    const bool tracing = (a.dbg & 64) && blockIdx.x == 0 && lane == 0;
+    Stream s_it(a, units, blockIdx.x, gridDim.x);    // next block whose S is to be issued
+    Stream pv_it(a, units, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
+    auto issue_s = [&]() {
+      const int g = s_it.g, stage = g % KV_STAGES, sb = g & 1;
+      if (tracing && g < 64) a.trace[8 * g + 4] = clock64();   // issue_s(g) entered
+      if (s_it.j == 0) mbar_wait(q_full, (uint32_t)(s_it.hc & 1));
+      mbar_wait(&k_full[stage], (uint32_t)((g / KV_STAGES) & 1));
+      if (tracing && g < 64) a.trace[8 * g + 5] = clock64();   // K of block g is there
+      // S buffer sb still holds P of block g - 2, the A operand of that block's P V.  No wait is needed: that MMA was issued
+      // earlier by this same thread and the tensor pipe executes a thread's MMAs in issue order, so this S cannot overwrite the
+      // columns before P V has read them (an explicit wait on its commit cost a barrier round trip per key block: the
+      // micro-benchmark's barrier skeleton alone ran at 0.77 us per block with it).
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(sK + stage * K_BYTES);
+      const uint32_t idesc = idesc_s0 | ((uint32_t)(s_it.keys16() >> 3) << 17);
+      const bool last = s_it.j + 1 == s_it.nb;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           if ((a.dbg & 4) && ks > 0) break;
@@ -242,44 +274,51 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_bf16(tmem_base + sb * BKV, da, db, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[sb]);
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 0] = clock64();   // S of block g committed
         umma_commit(&k_empty[stage]);
-        if (s_it.j + 1 == s_it.nb) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
-        s_it.advance();
-      };
-      if (s_it.valid) issue_s(false);
-      while (pv_it.valid) {
-        // S of the next block goes first so that it runs under this block's softmax -- unless it opens a new head whose Q
-        // has not landed yet: then P V must not queue up behind that wait.
-        bool deferred = false;
-        if (s_it.valid) {
-          if (s_it.j == 0 && !mbar_try_wait(q_full, (uint32_t)(s_it.hc & 1))) deferred = true;
-          else issue_s(false);
+        if (last) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
+      }
+      __syncwarp();
+      if (tracing && g < 64) a.trace[8 * g + 0] = clock64();   // S of block g committed
+      s_it.advance();
+    };
+    if (s_it.valid) issue_s();
+    while (pv_it.valid) {
+      // S of the next block goes first so that it runs under this block's softmax -- unless it opens a new head whose Q
+      // has not landed yet: then P V must not queue up behind that wait.  (Lane 0 decides for the warp.)
+      bool deferred = false;
+      if (s_it.valid) {
+        if (s_it.j == 0) {
+          const int ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(q_full, (uint32_t)(s_it.hc & 1)), 0);
+          deferred = !ready;
         }
-        const int g = pv_it.g, stage = g % KV_STAGES;
-        mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1));
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 3] = clock64();         // MMA thread saw P of block g
-        if (pv_it.j == 0) mbar_wait(o_empty, (uint32_t)((pv_it.hc & 1) ^ 1));   // the previous head's O has been read out
-        mbar_wait(&v_full[stage], (uint32_t)((g / KV_STAGES) & 1));
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 6] = clock64();   // V of block g is there
-        tc_fence_after();
-        const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);   // P sits where S of this block was: 8 columns per 16 keys
-        const uint32_t v_addr = smem_u32(sV + stage * K_BYTES);
-        const int ksteps = (a.dbg & 8) ? 0 : pv_it.keys16() >> 4;
+        if (!deferred) issue_s();
+      }
+      const int g = pv_it.g, stage = g % KV_STAGES;
+      mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1));
+      if (tracing && g < 64) a.trace[8 * g + 3] = clock64();         // MMA warp saw P of block g
+      if (pv_it.j == 0) mbar_wait(o_empty, (uint32_t)((pv_it.hc & 1) ^ 1));   // the previous head's O has been read out
+      mbar_wait(&v_full[stage], (uint32_t)((g / KV_STAGES) & 1));
+      if (tracing && g < 64) a.trace[8 * g + 6] = clock64();   // V of block g is there
+      tc_fence_after();
+      const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);   // P sits where S of this block was: 8 columns per 16 keys
+      const uint32_t v_addr = smem_u32(sV + stage * K_BYTES);
+      const int ksteps = (a.dbg & 8) ? 0 : pv_it.keys16() >> 4;
+      const bool first = pv_it.j == 0, last = pv_it.j + 1 == pv_it.nb;
+      if (elect_one()) {
         for (int ks = 0; ks < ksteps; ++ks) {
           // V tile: 64 keys x 128 d as two [64 x 64] boxes 8 KB apart; 16 keys = 2048 B per K step
           const uint64_t db = umma_desc_sw128_mn(v_addr + ks * 2048, K_BYTES / 2);
-          umma_bf16_ts(tmem_o, p_tmem + 8 * ks, db, idesc_pv, (pv_it.j | ks) != 0 ? 1u : 0u);
+          umma_bf16_ts(tmem_o, p_tmem + 8 * ks, db, idesc_pv, (!first || ks != 0) ? 1u : 0u);
         }
         umma_commit(&v_empty[stage]);
         umma_commit(p_empty);
-        if ((a.dbg & 64) && blockIdx.x == 0 && g < 64) a.trace[8 * g + 7] = clock64();   // P V of block g issued and committed
-        if (pv_it.j + 1 == pv_it.nb) umma_commit(o_full);
-        pv_it.advance();
-        if (deferred) issue_s(true);
+        if (last) umma_commit(o_full);
       }
+      __syncwarp();
+      if (tracing && g < 64) a.trace[8 * g + 7] = clock64();   // P V of block g issued and committed
+      pv_it.advance();
+      if (deferred) issue_s();
     }
-    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -287,7 +326,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float2 sc2 = make_float2(a.scale_log2e, a.scale_log2e);
     uint32_t r[32], r2[32];
     float m = -INFINITY, l = 0.f, m_used = 0.f;
-    for (Stream st(a, blockIdx.x, gridDim.x); st.valid; st.advance()) {
+    for (Stream st(a, units, blockIdx.x, gridDim.x); st.valid; st.advance()) {
       const int g = st.g, sb = g & 1;
       const bool warp_active = st.q0 + quarter * 32 < st.Tq && !(a.dbg & 16);   // warp-uniform: does this warp own any real query row?
       if (st.j == 0) { m = -INFINITY; l = 0.f; m_used = 0.f; }

@@ -1,4 +1,5 @@
 // K3 LayerNorm, K6 FSMN memory block, K7/K8 CIF predictor tail, K11 argmax decode.  See kernels.cuh.
+#include "gemm.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -102,11 +103,12 @@ layernorm_kernel(const void* __restrict__ in, int rows, const int* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------
 // FSMN: depthwise conv k=11 along time inside a segment + identity.
-// One thread owns 4 channels and walks a run of FSMN_RUN consecutive rows: every input row is loaded ONCE
+// One thread owns 2 channels and walks a run of FSMN_RUN consecutive rows: every input row is read ONCE
 // and scattered into a ring of 11 open output accumulators (registers), so the kernel streams
 // (RUN+10)/RUN rows per output row instead of 11.
 // ------------------------------------------------------------------------------------------------
 constexpr int FSMN_RUN = 22;  // multiple of 11 keeps the ring indices static
+constexpr int FSMN_THREADS = 256;
 
 // packed fp32x2 FMA (sm_100): two FMAs per issued instruction
 __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2& b) {
@@ -114,27 +116,26 @@ __device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2
       : "+l"(reinterpret_cast<unsigned long long&>(acc))
       : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
 }
+// y[0..1] += v, fire and forget (the add happens in L2; every element is touched by exactly one thread, once per launch)
+__device__ __forceinline__ void red_add_f32x2(float* p, float2 v) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 
 // FAST: the whole window of the run (rows r0 - 5 .. r0 + RUN + 4) lies inside ONE segment, so every tap of every output exists and
-// no per-row bookkeeping is needed -- loads, conversions, 22 packed FMAs per row and the store.  About four out of five runs of the
+// no per-row bookkeeping is needed -- loads, conversions, 11 packed FMAs per row and the store.  About four out of five runs of the
 // benchmark workload take this path (segments are 33-333 rows, a window is 32); the general path handles segment edges, gap rows
 // and the batch tail.  Both paths apply the same FMAs in the same order to an output, so results do not depend on which one a row
-// falls into (batch invariance).  Measured: 11.6 -> 11.4 ms of FSMN time per step -- the kernel is not bound by that bookkeeping.
+// falls into (batch invariance).
+// `tile` points at this thread's 2 channels of window row 0; consecutive rows are FSMN_TILE_LD words apart.
+constexpr int FSMN_TILE_LD = 128;
 template <bool FAST, bool F16>
-__device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], const float* __restrict__ w_t,
+__device__ __forceinline__ void fsmn_run(const uint32_t* __restrict__ tile, const float2 (&w)[11],
                                          const int2* __restrict__ row_info, int nrows, int r0, int mode,
                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
-  const int c = threadIdx.x * 4;
-  float2 w[11][2];
+  const int c = threadIdx.x * 2;
+  float2 acc[11];
 #pragma unroll
-  for (int j = 0; j < 11; ++j) {
-    const float4 t = *reinterpret_cast<const float4*>(w_t + j * 512 + c);
-    w[j][0] = make_float2(t.x, t.y); w[j][1] = make_float2(t.z, t.w);
-  }
-  w[5][0].x += 1.0f; w[5][0].y += 1.0f; w[5][1].x += 1.0f; w[5][1].y += 1.0f;  // identity branch
-  float2 acc[11][2];
-#pragma unroll
-  for (int s = 0; s < 11; ++s) { acc[s][0] = make_float2(0.f, 0.f); acc[s][1] = make_float2(0.f, 0.f); }
+  for (int s = 0; s < 11; ++s) acc[s] = make_float2(0.f, 0.f);
 
   // input i (row r0 - 5 + i) feeds outputs o = i - 5 - d, d = -5..5, with tap j = d + 5; output o is
   // complete after input i = o + 10.  Everything below is fully unrolled, so o and the ring slot are static.
@@ -163,25 +164,20 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
       const int i = step * 11 + ii;
       if (FAST) {
         if (i < FSMN_RUN + 10) {
-          const uint2 rw = tile[i][threadIdx.x];
-          const float2 x0 = unpack_h2<F16>(rw.x);
-          const float2 x1 = unpack_h2<F16>(rw.y);
+          const float2 x = unpack_h2<F16>(tile[i * FSMN_TILE_LD]);
 #pragma unroll
           for (int d = -5; d <= 5; ++d) {
             const int o = i - 5 - d;
             if (o >= 0 && o < FSMN_RUN) {
               const int slot = ((ii - 5 - d) % 11 + 11) % 11;
-              ffma2(acc[slot][0], w[d + 5][0], x0);
-              ffma2(acc[slot][1], w[d + 5][1], x1);
+              ffma2(acc[slot], w[d + 5], x);
             }
           }
         }
       } else {
         const int2 inf = info[cur][ii];
         if (inf.x >= 0) {  // gap rows and rows outside the batch contribute nothing
-          const uint2 rw = tile[i < FSMN_RUN + 10 ? i : 0][threadIdx.x];
-          const float2 x0 = unpack_h2<F16>(rw.x);
-          const float2 x1 = unpack_h2<F16>(rw.y);
+          const float2 x = unpack_h2<F16>(tile[(i < FSMN_RUN + 10 ? i : 0) * FSMN_TILE_LD]);
           cur_valid |= 1u << ii;
           if (inf.x >= 5 && inf.x + 5 < inf.y) {
             // interior frame: all 11 neighbours are in the same segment
@@ -190,8 +186,7 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
               const int o = i - 5 - d;
               if (o >= 0 && o < FSMN_RUN) {  // static: outputs of other runs are not accumulated here
                 const int slot = ((ii - 5 - d) % 11 + 11) % 11;
-                ffma2(acc[slot][0], w[d + 5][0], x0);
-                ffma2(acc[slot][1], w[d + 5][1], x1);
+                ffma2(acc[slot], w[d + 5], x);
               }
             }
           } else {
@@ -202,10 +197,7 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
                 // output row rin - d lies in the same segment iff its frame index t - d is inside [0, T)
                 const bool ok = (inf.x - d) >= 0 && (inf.x - d) < inf.y;
                 const int slot = ((ii - 5 - d) % 11 + 11) % 11;
-                if (ok) {
-                  ffma2(acc[slot][0], w[d + 5][0], x0);
-                  ffma2(acc[slot][1], w[d + 5][1], x1);
-                }
+                if (ok) ffma2(acc[slot], w[d + 5], x);
               }
             }
           }
@@ -219,63 +211,89 @@ __device__ __forceinline__ void fsmn_run(const uint2 (*__restrict__ tile)[128], 
           const int rout = r0 + o;
           const bool out_valid = FAST ? true : ((ii >= 5) ? ((cur_valid >> (ii - 5)) & 1u) : ((prev_valid >> (ii + 6)) & 1u));
           if (mode == 0) {
-            uint2 pk = make_uint2(0, 0);
-            if (out_valid) { pk.x = pack_h2<F16>(acc[slot_done][0].x, acc[slot_done][0].y); pk.y = pack_h2<F16>(acc[slot_done][1].x, acc[slot_done][1].y); }
-            *reinterpret_cast<uint2*>(out_bf16 + (size_t)rout * 512 + c) = pk;
+            const uint32_t pk = out_valid ? pack_h2<F16>(acc[slot_done].x, acc[slot_done].y) : 0u;
+            *reinterpret_cast<uint32_t*>(out_bf16 + (size_t)rout * 512 + c) = pk;
           } else if (out_valid) {
-            float4* yp = reinterpret_cast<float4*>(y_f32 + (size_t)rout * 512 + c);
-            float4 v = *yp;
-            v.x += acc[slot_done][0].x; v.y += acc[slot_done][0].y; v.z += acc[slot_done][1].x; v.w += acc[slot_done][1].y;
-            *yp = v;
+            red_add_f32x2(y_f32 + (size_t)rout * 512 + c, acc[slot_done]);
           }
         }
-        acc[slot_done][0] = make_float2(0.f, 0.f);
-        acc[slot_done][1] = make_float2(0.f, 0.f);
+        acc[slot_done] = make_float2(0.f, 0.f);
       }
     }
     prev_valid = cur_valid;
   }
 }
 
-// <= 128 registers: one FSMN CTA then fits next to two resident attention CTAs (2 x 24.6K + 16.4K registers = one SM), which is
-// what lets the two kernels run side by side (engine.cu, "overlap").
+// PERSISTENT: 2 CTAs per SM, each walking windows blockIdx.x, blockIdx.x + gridDim.x, ... (neighbouring CTAs work on
+// neighbouring rows at the same time, so the 10 halo rows two windows share are L2 hits).  A window (RUN + 10 rows x 512
+// channels, 32 KB) is fetched by ONE thread with two TMA box loads (rows before the batch / beyond the tensor map arrive as
+// zeros) into a 3-stage ring: two windows are always in flight per CTA (128 KB per SM) while the third is being computed, so
+// the loads no longer stop while a CTA computes and stores (round 1: load everything, wait, compute, exit -- 0.45 of HBM).
+// The "is this window inside one segment" test of window k + 1 is loaded while window k is computed, and the decoder's
+// `y += ...` leaves as a vector RED, so nothing in the loop waits on global memory.
+constexpr int FSMN_WIN = FSMN_RUN + 10;
+constexpr int FSMN_STAGES = 3;
+constexpr int FSMN_STAGE_BYTES = FSMN_WIN * 512 * 2;           // two [FSMN_WIN x 256] boxes
+constexpr int FSMN_SMEM = FSMN_STAGES * FSMN_STAGE_BYTES + 64;
+
 template <bool F16>
-__global__ void __launch_bounds__(128, 4)
-fsmn_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int col0, const float* __restrict__ w_t,
+__global__ void __launch_bounds__(FSMN_THREADS, 2)
+fsmn_kernel(const __grid_constant__ CUtensorMap tm_in, int col0, const float* __restrict__ w_t,
             const int2* __restrict__ row_info, int rows, const int* __restrict__ rows_dev, int mode,
             __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ y_f32) {
+  extern __shared__ __align__(128) uint8_t fsmn_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsmn_smem + FSMN_STAGES * FSMN_STAGE_BYTES);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FSMN_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_in);
+  }
+  const int c = threadIdx.x * 2;
+  float2 w[11];   // constants: loaded before the dependency wait
+#pragma unroll
+  for (int j = 0; j < 11; ++j) w[j] = *reinterpret_cast<const float2*>(w_t + j * 512 + c);
+  w[5].x += 1.0f; w[5].y += 1.0f;  // identity branch
+  __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
   const int nrows = rows_dev ? *rows_dev : rows;
-  const int r0 = blockIdx.x * FSMN_RUN;
-  if (r0 >= nrows) return;
-  // block-uniform: first and last row of the window are frames of the same segment (rows of a segment are consecutive)
-  bool fast = false;
-  if (r0 >= 5 && r0 + FSMN_RUN + 4 < nrows) {
-    const int2 a = row_info[r0 - 5], b = row_info[r0 + FSMN_RUN + 4];
-    fast = a.x >= 0 && b.x == a.x + FSMN_RUN + 9 && b.y == a.y;
+  const int n_win = (nrows + FSMN_RUN - 1) / FSMN_RUN;
+  auto issue = [&](int k) {   // this CTA's k-th window
+    const int win = blockIdx.x + k * gridDim.x;
+    if (win >= n_win) return;
+    const int stage = k % FSMN_STAGES;
+    uint8_t* dst = fsmn_smem + stage * FSMN_STAGE_BYTES;
+    mbar_arrive_expect_tx(&full[stage], FSMN_STAGE_BYTES);
+    tma_load_2d(dst, &tm_in, &full[stage], col0, win * FSMN_RUN - 5);
+    tma_load_2d(dst + FSMN_STAGE_BYTES / 2, &tm_in, &full[stage], col0 + 256, win * FSMN_RUN - 5);
+  };
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < FSMN_STAGES - 1; ++k) issue(k);
   }
-  // the window (RUN + 10 rows x 512 channels, 32 KB) goes to shared memory through cp.async: every 16-byte piece of it is in
-  // flight at once, no registers are held for it, and the compute loops below read it back conflict-free (8 bytes per lane)
-  __shared__ __align__(16) uint2 tile[FSMN_RUN + 10][128];
-  constexpr int kPieces = (FSMN_RUN + 10) * 64;   // 16-byte pieces
-  for (int p = threadIdx.x; p < kPieces; p += 128) {
-    const int row = p >> 6, piece = p & 63;
-    const int rin = r0 - 5 + row;
-    uint2* dst = &tile[row][piece * 2];
-    if (rin >= 0 && rin < nrows) {
-      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(in + (size_t)rin * ld_in + col0 + piece * 8) : "memory");
-    } else {
-      dst[0] = make_uint2(0, 0);
-      dst[1] = make_uint2(0, 0);
-    }
+  // block-uniform: first and last row of a window are frames of the same segment (rows of a segment are consecutive)
+  auto edge_rows = [&](int win, int2& a, int2& b) {
+    const int r0 = win * FSMN_RUN;
+    a = make_int2(-1, 0); b = make_int2(-1, 0);
+    if (win < n_win && r0 >= 5 && r0 + FSMN_RUN + 4 < nrows) { a = row_info[r0 - 5]; b = row_info[r0 + FSMN_RUN + 4]; }
+  };
+  int2 ea, eb;
+  edge_rows(blockIdx.x, ea, eb);
+  // this thread's channels inside a stage: box (threadIdx.x >> 7), 4 bytes at column 2 (threadIdx.x & 127)
+  const int t_off = (threadIdx.x >> 7) * (FSMN_STAGE_BYTES / 2) + (threadIdx.x & 127) * 4;
+  for (int k = 0;; ++k) {
+    const int win = blockIdx.x + k * gridDim.x;
+    if (win >= n_win) break;
+    if (threadIdx.x == 0) issue(k + FSMN_STAGES - 1);   // its stage was released by the barrier that ended iteration k - 1
+    const bool fast = ea.x >= 0 && eb.x == ea.x + FSMN_RUN + 9 && eb.y == ea.y;
+    edge_rows(win + gridDim.x, ea, eb);                 // next window's test: in flight during this window's FMAs
+    const int stage = k % FSMN_STAGES;
+    mbar_wait(&full[stage], (uint32_t)((k / FSMN_STAGES) & 1));
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(fsmn_smem + stage * FSMN_STAGE_BYTES + t_off);
+    const int r0 = win * FSMN_RUN;
+    if (fast) fsmn_run<true, F16>(tile, w, row_info, nrows, r0, mode, out_bf16, y_f32);
+    else fsmn_run<false, F16>(tile, w, row_info, nrows, r0, mode, out_bf16, y_f32);
+    __syncthreads();
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (fast) fsmn_run<true, F16>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
-  else fsmn_run<false, F16>(tile, w_t, row_info, nrows, r0, mode, out_bf16, y_f32);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,11 +741,22 @@ int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_d
 }
 
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
-                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16) {
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16, int num_sms) {
   if (rows <= 0) return 0;
-  const dim3 grid((rows + FSMN_RUN - 1) / FSMN_RUN);
-  if (f16) return launch_kernel(fsmn_kernel<true>, grid, dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
-  return launch_kernel(fsmn_kernel<false>, grid, dim3(128), 0, s, in, ld_in, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
+  static PerDeviceOnce once;
+  int rc = once_per_device(once, [] {
+    cudaError_t err = cudaFuncSetAttribute(fsmn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSMN_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(fsmn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSMN_SMEM);
+    return (int)err;
+  });
+  if (rc) return rc;
+  CUtensorMap tm;
+  rc = make_tmap_bf16_plain(&tm, in, (uint64_t)rows, (uint64_t)(col0 + 512), (uint64_t)ld_in, FSMN_WIN, 256);
+  if (rc) return rc;
+  const int n_win = (rows + FSMN_RUN - 1) / FSMN_RUN, resident = 2 * (num_sms > 0 ? num_sms : 148);
+  const dim3 grid(n_win < resident ? n_win : resident);
+  if (f16) return launch_kernel(fsmn_kernel<true>, grid, dim3(FSMN_THREADS), FSMN_SMEM, s, tm, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
+  return launch_kernel(fsmn_kernel<false>, grid, dim3(FSMN_THREADS), FSMN_SMEM, s, tm, col0, w_t, row_info, rows, rows_dev, mode, out_bf16, y_f32);
 }
 
 int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,

@@ -52,6 +52,29 @@ static uint16_t f32_to_f16_rne_sat(float f) {
   return (uint16_t)(sign | ((v + 0xfffu + ((v >> 13) & 1u)) >> 13));
 }
 uint16_t f32_to_h16(float f, int f16) { return f16 ? f32_to_f16_rne_sat(f) : f32_to_bf16_rne(f); }
+float h16_to_f32(uint16_t h, int f16) {
+  uint32_t u;
+  if (!f16) {
+    u = (uint32_t)h << 16;
+  } else {
+    const uint32_t sign = ((uint32_t)h & 0x8000u) << 16, ex = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    if (ex == 0) {
+      if (man == 0) { u = sign; }
+      else {   // subnormal half: man * 2^-24
+        float v = (float)man * 5.9604644775390625e-8f;
+        memcpy(&u, &v, 4);
+        u |= sign;
+      }
+    } else if (ex == 31) {
+      u = sign | 0x7f800000u | (man << 13);
+    } else {
+      u = sign | ((ex + 112u) << 23) | (man << 13);
+    }
+  }
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
 
 int num_fbank_frames(int64_t n) { return n < 400 ? 0 : (int)(1 + (n - 400) / 160); }
 int num_lfr_frames(int64_t n) {
@@ -346,6 +369,28 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
     w.w1 = L.linear(p + ".feed_forward.w_1", Fd, D);
     w.lnff = L.norm(p + ".feed_forward.norm", Fd);
     w.w2 = L.linear(p + ".feed_forward.w_2", D, Fd, false);
+    {
+      auto g = L.get(p + ".feed_forward.norm.weight", {Fd}), bt = L.get(p + ".feed_forward.norm.bias", {Fd});
+      auto w2 = L.get(p + ".feed_forward.w_2.weight", {D, Fd});
+      if (g && bt && w2) {
+        std::vector<float> folded((size_t)D * Fd), csum(D), bias(D);
+        for (int n = 0; n < D; ++n) {
+          double cs = 0.0, bb = 0.0;
+          for (int k = 0; k < Fd; ++k) {
+            const float wv = w2->data[(size_t)n * Fd + k];
+            const float f = wv * g->data[k];
+            folded[(size_t)n * Fd + k] = f;
+            cs += (double)h16_to_f32(f32_to_h16(f, e->f16), e->f16);
+            bb += (double)bt->data[k] * (double)wv;
+          }
+          csum[n] = (float)cs; bias[n] = (float)bb;
+        }
+        w.w2f.out = D; w.w2f.in = Fd;
+        w.w2f.w = L.up_bf16(folded.data(), folded.size());
+        w.w2f.b = L.up_f32(bias.data(), D);
+        w.w2_csum = L.up_f32(csum.data(), D);
+      }
+    }
     if (attn) {
       w.ln2 = L.norm(p + ".norm2", D);
       w.fsmn_wt = L.fsmn(p + ".self_attn.fsmn_block", D, K);
@@ -425,7 +470,7 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
   // ---- workspace ----
   const size_t R = (size_t)c.max_rows;
   size_t bytes = R * (6 * 80 * 4 + 560 * 4 + 512 * 4 + 560 * 2 + 1536 * 2 + 512 * 2 + 512 * 2 + 2048 * 2 + 512 * 4 + 512 * 2 +
-                      512 * 4 + 4 * 4 + 4 + 8 + 8) + (1 << 20);
+                      512 * 4 + 4 * 4 + 4 + 8 + 8 + 16 * 8) + (1 << 20);
   if (c.timestamp) bytes += R * 3 * (4096 * 2 + 1024 * 2 + 3 * 4) + (1 << 16);
   if (c.contextual) bytes += (size_t)B200PF_MAX_HOTWORDS * 1024 * 2 + (1 << 16);
   CK(cudaMalloc((void**)&e->ws.base, bytes), "cudaMalloc(workspace)");
@@ -435,7 +480,8 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
             ws_take(e.get(), &e->att, R * 512) && ws_take(e.get(), &e->ffn, R * 2048) && ws_take(e.get(), &e->enc_f32, R * 512) &&
             ws_take(e.get(), &e->enc_bf16, R * 512) && ws_take(e.get(), &e->y, R * 512) && ws_take(e.get(), &e->alpha, R) &&
             ws_take(e.get(), &e->cif_cur, R) && ws_take(e.get(), &e->cif_rem, R) && ws_take(e.get(), &e->fire_val, R) &&
-            ws_take(e.get(), &e->fire_row, R) && ws_take(e.get(), &e->amax, R) && ws_take(e.get(), &e->tok_info, R);
+            ws_take(e.get(), &e->fire_row, R) && ws_take(e.get(), &e->amax, R) && ws_take(e.get(), &e->tok_info, R) &&
+            ws_take(e.get(), &e->ffn_stats, R * 16);
   if (ok && c.timestamp)
     ok = ws_take(e.get(), &e->us_gx, R * 3 * 4096) && ws_take(e.get(), &e->us_h, R * 3 * 1024) && ws_take(e.get(), &e->us_a2, R * 3);
   if (ok && c.contextual) ok = ws_take(e.get(), &e->hw_kv, (size_t)B200PF_MAX_HOTWORDS * 1024);
@@ -505,6 +551,10 @@ int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value) {
   }
   if (strcmp(key, "overlap") == 0) {
     e->overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
+    return 0;
+  }
+  if (strcmp(key, "ffn_ln_fold") == 0) {
+    e->ffn_ln_fold = value ? 1 : 0;
     return 0;
   }
   if (strcmp(key, "logprob_topk") == 0) {
@@ -952,7 +1002,7 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
       CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
     }
     if (fork && e->overlap == 2) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
-    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs, e->f16), "fsmn");
+    LAUNCH(4, (double)M * 512 * 4, fsmn_launch(e->qkv, 3 * D, 2 * D, w.fsmn_wt, b->d_row_info, M, nullptr, 0, e->mem, nullptr, fs, e->f16, sms), "fsmn");
     if (fork) CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
     if (!(fork && e->overlap == 2)) LAUNCH(3, 4.0 * sumT2 * 512, attention_tcgen05(ap, s), "attention");
     if (fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");
@@ -1008,8 +1058,18 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
   cp.work = b->d_work_x; cp.n_work = b->n_work_run; cp.n_heads = c.n_heads; cp.f16 = e->f16; cp.num_sms = sms;
   auto dec_ffn = [&](const DecLayer& w) -> int {
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln1.g, w.ln1.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln1");
+    // feed_forward.norm folded into the two GEMMs around it: w_1's epilogue leaves per-row partial sums of the rounded hidden,
+    // w_2 (pre-multiplied by gamma) normalises in its epilogue -- the [L, 2048] hidden is written once and read once
+    const bool fold = e->ffn_ln_fold && w.w2f.w && (c.d_ff % 256) == 0 && c.d_ff / 128 <= 16 && (D % 256) == 0;
     { GemmEpilogue ep; ep.bias = w.w1.b; ep.relu = 1; ep.out_bf16 = e->ffn; ep.ld_out_bf16 = c.d_ff;
+      if (fold) { ep.row_stats_out = e->ffn_stats; ep.stats_slots = c.d_ff / 128; }
       CKL(gemm(e->hb, D, R, w.w1, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w1"); }
+    if (fold) {
+      GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D; ep.bias = w.w2f.b;
+      ep.ln_stats = e->ffn_stats; ep.ln_slots = c.d_ff / 128; ep.ln_dim = c.d_ff; ep.ln_eps = c.ln_eps; ep.ln_csum = w.w2_csum;
+      CKL(gemm(e->ffn, c.d_ff, R, w.w2f, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2 (ln folded)");
+      return 0;
+    }
     LAUNCH(1, Lest * 2048 * 4, layernorm_launch(e->ffn, 1, Lcap, Ldev, c.d_ff, w.lnff.g, w.lnff.b, c.ln_eps, e->ffn, nullptr, nullptr, 0, s, e->f16), "dec ln ff");
     { GemmEpilogue ep; ep.out_f32 = tbuf; ep.ld_out_f32 = D;
       CKL(gemm(e->ffn, c.d_ff, R, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
@@ -1019,7 +1079,7 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
     const DecLayer& w = e->dec[l];
     { int rc = dec_ffn(w); if (rc) return rc; }
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln2");
-    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16), "dec fsmn");
+    LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16, sms), "dec fsmn");
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln3");
     { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
       CKL(gemm(e->hb, D, R, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }

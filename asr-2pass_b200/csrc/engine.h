@@ -22,6 +22,7 @@ int check_cuda(cudaError_t e, const char* what);  // 0 or B200PF_ERR_CUDA (and s
 int num_fbank_frames(int64_t n_samples);  // feature-window.cc:73-87 (snip_edges)
 int num_lfr_frames(int64_t n_samples);    // paraformer.cpp:424
 uint16_t f32_to_h16(float f, int f16);    // host-side round-to-nearest-even to bf16 (0) or saturating IEEE fp16 (1)
+float h16_to_f32(uint16_t h, int f16);    // exact widening of the same formats
 
 struct Linear {
   __nv_bfloat16* w = nullptr;  // [out, in] bf16
@@ -41,6 +42,10 @@ struct EncLayer {
 struct DecLayer {
   Norm ln1, lnff, ln2, ln3;
   Linear w1, w2, q, kv, out;
+  // feed_forward.norm folded into w_2 (engine option ffn_ln_fold, gemm.cuh): w2f = w_2 . diag(gamma) in the operand format,
+  // w2f.b[n] = sum_k beta[k] w_2[n][k], w2_csum[n] = sum_k w2f[n][k] of the ROUNDED folded weights
+  Linear w2f;
+  float* w2_csum = nullptr;
   float* fsmn_wt = nullptr;
   bool has_attn = true;
 };
@@ -68,6 +73,7 @@ struct b200pf_engine {
   cudaStream_t d2h = nullptr;           // device->host result reads of a FINISHED batch (b200pf_batch_collect), while the next one computes
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int overlap = 2;
+  int ffn_ln_fold = 1;                  // decoder feed-forward LayerNorm(2048) applied inside the w_2 GEMM epilogue (no pass over the hidden)
   int f16 = 1;                          // 16-bit operand format of weights and activations: 0 bf16, 1 IEEE fp16 (cfg.precision)
   std::string lang = "zh-cn";
   std::vector<std::string> tokens;
@@ -109,6 +115,7 @@ struct b200pf_engine {
   __nv_bfloat16* mem = nullptr;     // [R, 512] bf16   FSMN memory (decoder: cross q)
   __nv_bfloat16* att = nullptr;     // [R, 512] bf16
   __nv_bfloat16* ffn = nullptr;     // [R, 2048] bf16
+  float2* ffn_stats = nullptr;      // [R, 16] (sum, sum of squares) per 128-column span of a decoder feed-forward hidden row
   float* enc_f32 = nullptr;         // [R, 512]
   __nv_bfloat16* enc_bf16 = nullptr;
   float* y = nullptr;               // [R, 512] decoder residual stream

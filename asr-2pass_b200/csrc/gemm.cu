@@ -106,33 +106,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_tiles = (M + 2 * BM - 1) / (2 * BM);
   const int total = m_tiles * n_tiles;
 
+  // Warps 0 and 1 run converged and put only the TMA / tcgen05 instructions under elect_one(): inside an `if (lane == 0)` region
+  // the compiler wraps each of them in a per-thread "waterfall" loop (ELECT + branch), ~75 cycles per instruction (attention.cu).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < total; tile += n_pairs) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int m0 = m_blk * 2 * BM + (int)cta * BM;
-        const int n0 = n_blk * BN + (int)cta * (BN / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < total; tile += n_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m0 = m_blk * 2 * BM + (int)cta * BM;
+      const int n0 = n_blk * BN + (int)cta * (BN / 2);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const int k0 = kb * BK;
+        int ac0 = k0, ac1 = m0;
+        if (a.a_k_wrap > 0) {
+          const int pass = k0 / a.a_k_wrap;
+          ac0 = k0 - pass * a.a_k_wrap;
+          ac1 += pass + a.a_row_shift0;
+        }
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
-          const int k0 = kb * BK;
-          int ac0 = k0, ac1 = m0;
-          if (a.a_k_wrap > 0) {
-            const int pass = k0 / a.a_k_wrap;
-            ac0 = k0 - pass * a.a_k_wrap;
-            ac1 += pass + a.a_row_shift0;
-          }
           tma_load_2d_2cta(sA + stage * A_BYTES, &tmA, &full[stage], ac0, ac1);
           tma_load_2d_2cta(sB + stage * B_BYTES, &tmB, &full[stage], k0, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_h16(F16, 2 * BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -147,20 +149,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
           const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle atom (address field is >>4)
-            umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 B per 16-element K step inside the 128 B swizzle atom (address field is >>4)
+              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta_mc(&empty[stage], 0x3);
+            if (kb + 1 == k_blocks) umma_commit_2cta_mc(&tfull[acc], 0x3);
           }
-          umma_commit_2cta_mc(&empty[stage], 0x3);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta_mc(&tfull[acc], 0x3);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may address
@@ -192,6 +196,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
         uint32_t ra[32], rb[32];
+        float st1 = 0.f, st2 = 0.f;   // row_stats_out: this row's sum / sum of squares over the warp's 128 columns
         if (e.dbg == 3) {  // micro-benchmark only: no TMEM reads
 #pragma unroll
           for (int i = 0; i < 32; ++i) { ra[i] = 0; rb[i] = 0; }
@@ -218,6 +223,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (e.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
               pk[hh * 16 + 2 * g] = pack_h2<F16>(v0, v1);
               pk[hh * 16 + 2 * g + 1] = pack_h2<F16>(v2, v3);
+              if (e.row_stats_out) {   // of the values the consumer GEMM will read
+                const float2 q0 = unpack_h2<F16>(pk[hh * 16 + 2 * g]), q1 = unpack_h2<F16>(pk[hh * 16 + 2 * g + 1]);
+                st1 += (q0.x + q0.y) + (q1.x + q1.y);
+                st2 = fmaf(q0.x, q0.x, st2); st2 = fmaf(q0.y, q0.y, st2); st2 = fmaf(q1.x, q1.x, st2); st2 = fmaf(q1.y, q1.y, st2);
+              }
             }
           }
           if (c64 == 0) {  // the second half's TMEM loads fly while this half is stored
@@ -242,6 +252,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
         }
+        if (e.row_stats_out && row_base + lane < M)
+          e.row_stats_out[(size_t)(row_base + lane) * e.stats_slots + (col_base >> 7)] = make_float2(st1, st2);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -262,7 +274,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.bias) {
           const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
           sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          if (e.ln_stats) {
+            const uint4 cs = ldg128_nc(e.ln_csum + col_base + lane * 4);
+            sts128(sbias + 512 + lane * 16, cs.x, cs.y, cs.z, cs.w);
+          }
           warp_sync_smem();
+        }
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (e.ln_stats && row_ok) {   // the row's partial sums, combined in slot order
+          const float2* sp = e.ln_stats + (size_t)row * e.ln_slots;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < e.ln_slots; ++i) { const float2 t = sp[i]; s1 += t.x; s2 += t.y; }
+          const float inv = 1.f / (float)e.ln_dim;
+          ln_mean = s1 * inv;
+          ln_rstd = rsqrtf(fmaxf(s2 * inv - ln_mean * ln_mean, 0.f) + e.ln_eps);
         }
         // this thread's row of the addend for the whole 128-column span: issued before the accumulator is even ready
         uint4 add[16];
@@ -292,6 +317,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int g = 0; g < 8; ++g) {
             float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]);
             float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
+            if (e.ln_stats) {
+              const float4 cs = lds128f(sbias + 512 + (c * 32 + 4 * g) * 4);
+              v0 = ln_rstd * (v0 - ln_mean * cs.x); v1 = ln_rstd * (v1 - ln_mean * cs.y);
+              v2 = ln_rstd * (v2 - ln_mean * cs.z); v3 = ln_rstd * (v3 - ln_mean * cs.w);
+            }
             if (e.bias) {
               const float4 bb = lds128f(sbias + (c * 32 + 4 * g) * 4);
               v0 += bb.x; v1 += bb.y; v2 += bb.z; v3 += bb.w;
@@ -519,8 +549,8 @@ std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 }  // namespace
 
 static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_bytes, const void* base, uint64_t rows, uint64_t cols,
-                           uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
-  const TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, (int)dt};
+                           uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols, bool swizzle = true) {
+  const TmapKey key{base, rows, cols, ld_elems, box_rows, box_cols, (int)dt | (swizzle ? 0 : 0x100)};
   {
     std::lock_guard<std::mutex> lock(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
@@ -533,7 +563,8 @@ static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_by
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lock(g_tmap_mu);
@@ -545,6 +576,11 @@ static int make_tmap_sw128(CUtensorMap* out, CUtensorMapDataType dt, int elem_by
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                          uint32_t box_rows, uint32_t box_cols) {
   return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_rows, box_cols);
+}
+
+int make_tmap_bf16_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_sw128(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld_elems, box_rows, box_cols, false);
 }
 
 // Row extent of a tensor map over a buffer that holds `cap` rows of which `used` matter: whole 256-row tiles, so that a handful
@@ -582,6 +618,8 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   const bool f32tma = !fast && !no_f32_tma && e.out_f32 && !e.out_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 && e.dbg == 0 &&
                       (e.res_f32 == nullptr || (e.res_f32 == e.out_f32 && e.ld_res == e.ld_out_f32)) &&
                       (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (e.ld_out_f32 & 3) == 0;
+  if (e.row_stats_out && !fast) return (int)cudaErrorInvalidValue;                       // only the bf16 TMA epilogue writes row sums
+  if (e.ln_stats && (!f32tma || !e.bias || !e.ln_csum)) return (int)cudaErrorInvalidValue;  // only the fp32 TMA epilogue applies them
   CUtensorMap tmC = tmA;  // placeholder for the general path
   if (fast) {
     rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, tile_extent(p.M, p.rows_c), (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);

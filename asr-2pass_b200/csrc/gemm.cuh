@@ -25,6 +25,18 @@ struct GemmEpilogue {
   int dbg = 0;                            // micro-benchmark / tests only: 1 = skip global stores, 2 = skip the whole epilogue body,
                                           // 3 = bf16 TMA epilogue without TMEM reads, 4 = force the general epilogue
   unsigned long long* argmax = nullptr;   // [M] packed (ordered value << 32 | ~index); caller zero-fills
+  // LayerNorm folded across two GEMMs (decoder feed-forward: h = relu(y W1 + b1); LN(h) W2 without a LayerNorm pass over h):
+  //   producer (bf16 TMA epilogue only): row_stats_out[row * stats_slots + col / 128] = (sum, sum of squares) of the row's 128
+  //     ROUNDED outputs of that column span -- plain stores, one slot per span, so the result does not depend on scheduling;
+  //   consumer (fp32 TMA epilogue only), W pre-multiplied by gamma along K:
+  //     out = rstd * (acc - mean * ln_csum[col]) + bias[col], mean / rstd from the row's ln_slots partial sums over ln_dim
+  //     columns, ln_csum[col] = sum_k W'[col][k] (of the rounded folded weights), bias = sum_k beta[k] W[col][k].
+  float2* row_stats_out = nullptr;
+  int stats_slots = 0;
+  const float2* ln_stats = nullptr;
+  int ln_slots = 0, ln_dim = 0;
+  float ln_eps = 0.f;
+  const float* ln_csum = nullptr;         // [N]
 };
 
 struct GemmProblem {
@@ -49,6 +61,10 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
 // 2-D bf16 row-major tensor map with 128-byte swizzle, box = [box_rows x 64 elements].
 int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                          uint32_t box_rows, uint32_t box_cols = 64);
+
+// Same without swizzle: the box lands row-major in shared memory ([box_rows][box_cols], box_cols <= 256).
+int make_tmap_bf16_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                         uint32_t box_rows, uint32_t box_cols);
 
 __device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
   uint32_t u = __float_as_uint(v);

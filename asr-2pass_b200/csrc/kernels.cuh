@@ -55,7 +55,7 @@ int layernorm_launch(const void* in, int in_is_bf16, int rows, const int* rows_d
 //     mode 1 (decoder): y_f32[r][c]   += conv(x)[r][c] + x[r][c]
 //     in: bf16 [rows][ld_in] starting at column col0; w_t: [11][512] fp32 (tap-major transpose of fsmn_block.weight).
 int fsmn_launch(const __nv_bfloat16* in, int ld_in, int col0, const float* w_t, const int2* row_info, int rows,
-                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16 = 0);
+                const int* rows_dev, int mode, __nv_bfloat16* out_bf16, float* y_f32, cudaStream_t s, int f16 = 0, int num_sms = 0);
 
 // K7  alpha = sigmoid(h . w + b) on frame rows, tail_threshold on gap rows (CifPredictorV2).
 int cif_alpha_launch(const float* h, int M, const float* w, const float* b, const int2* row_info, float tail,

@@ -425,8 +425,18 @@ def test_forward_full_paraformer_large(capi, synth, gpu, tmp_path_factory):
         _, o = _oracle(model, pcm[offs[i]:offs[i + 1]])
         assert abs(int(res["token_counts"][i]) - o["token_num"]) <= 1
         _check_segment(b, res, i, model, o)        # 1e-2 on encoder output and logits (north_star)
-    # 591 launches: 2 front end + 50 x 8 encoder + 6 predictor + 16 x 11 decoder + 7 tail
+    # 574 launches: 2 front end + 50 x 8 encoder + 6 predictor + 16 x 10 decoder + 6 tail (the feed-forward LayerNorm of the 17
+    # decoder FFNs is folded into the GEMMs around it, engine option ffn_ln_fold)
+    assert b.launches == 2 + 50 * 8 + 6 + 16 * 10 + 6
+    # the same forward with the LayerNorm as its own pass: same bar against the oracle, (nearly) the same ids
+    eng.set_option("ffn_ln_fold", 0)
+    res0 = b.forward_s16(pcm, offs)
     assert b.launches == 2 + 50 * 8 + 6 + 16 * 11 + 7
+    for i in range(3):
+        _, o = _oracle(model, pcm[offs[i]:offs[i + 1]])
+        _check_segment(b, res0, i, model, o)
+    assert list(res0["token_counts"]) == list(res["token_counts"])
+    assert np.mean(np.asarray(res0["token_ids"]) != np.asarray(res["token_ids"])) <= 0.02
     eng.close()
 
 
