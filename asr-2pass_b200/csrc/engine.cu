@@ -242,7 +242,7 @@ static void fill_config(const WeightFile& wf, int fs, b200pf_config* c) {
   c->contextual = (int)cfgv("contextual", 0);
 }
 
-int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors) {
+static int b200pf_model_dir_probe_impl(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors) {
   if (!model_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
   const std::string dir(model_dir);
   std::string err, lang;
@@ -262,12 +262,25 @@ int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tok
   if (n_tensors) *n_tensors = (int)wf.tensors.size();
   return 0;
 }
+// Parsing a hostile or truncated model directory may throw (std::bad_alloc, std::invalid_argument from the text parsers);
+// nothing may unwind through the C ABI: it becomes an error code with the text in b200pf_last_error().
+int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors) {
+  try {
+    return b200pf_model_dir_probe_impl(model_dir, out, n_tokens, n_tensors);
+  } catch (const std::exception& ex) {
+    set_error(std::string("b200pf_model_dir_probe: ") + ex.what());
+    return B200PF_ERR_IO;
+  } catch (...) {
+    set_error("b200pf_model_dir_probe: unknown exception");
+    return B200PF_ERR_IO;
+  }
+}
 
 int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out) {
   return b200pf_engine_create_prec(model_dir, device, max_rows, max_segments, -1, out);
 }
 
-int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out) {
+static int b200pf_engine_create_prec_impl(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out) {
   if (!model_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
   *out = nullptr;
   if (precision < 0) {   // default: fp16 operands (meets the stated 1e-2 tolerance); B200PF_PREC overrides
@@ -293,7 +306,9 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
   if (!read_weight_file(dir + "/model.b200pf", &wf, &err)) { set_error(err); return B200PF_ERR_IO; }
   std::vector<float> means, vars;
   if (!read_am_mvn(dir + "/am.mvn", &means, &vars, &err)) { set_error(err); return B200PF_ERR_IO; }
-  std::unique_ptr<b200pf_engine> e(new b200pf_engine);
+  // every failure path below releases what was created so far (streams, events, arenas) through the destroy entry point
+  struct EngineDel { void operator()(b200pf_engine* p) const { b200pf_engine_destroy(p); } };
+  std::unique_ptr<b200pf_engine, EngineDel> e(new b200pf_engine);
   if (!read_tokens_json(dir + "/tokens.json", &e->tokens, &err)) { set_error(err); return B200PF_ERR_IO; }
   int fs = 16000;
   if (!read_config_yaml(dir + "/config.yaml", &fs, &e->lang, &err)) { set_error(err); return B200PF_ERR_IO; }
@@ -462,9 +477,7 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
   if (L.ok) build_frontend_tables(e.get(), L, means, vars);
   if (!L.ok) {
     set_error(L.err);
-    cudaFree(e->warena.base);
-    cudaStreamDestroy(e->stream);
-    return B200PF_ERR_IO;
+    return B200PF_ERR_IO;   // the deleter releases the arena, the streams and the events
   }
 
   // ---- workspace ----
@@ -491,11 +504,24 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
   *out = e.release();
   return B200PF_OK;
 }
+// Parsing a hostile or truncated model directory may throw (std::bad_alloc, std::invalid_argument from the text parsers);
+// nothing may unwind through the C ABI: it becomes an error code with the text in b200pf_last_error().
+int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out) {
+  try {
+    return b200pf_engine_create_prec_impl(model_dir, device, max_rows, max_segments, precision, out);
+  } catch (const std::exception& ex) {
+    set_error(std::string("b200pf_engine_create: ") + ex.what());
+    return B200PF_ERR_IO;
+  } catch (...) {
+    set_error("b200pf_engine_create: unknown exception");
+    return B200PF_ERR_IO;
+  }
+}
 
-void b200pf_engine_destroy(b200pf_engine* e) {
+void b200pf_engine_destroy(b200pf_engine* e) {   // also the clean-up of a partially constructed engine: every member may be null
   if (!e) return;
   cudaSetDevice(e->device);
-  cudaStreamSynchronize(e->stream);
+  if (e->stream) cudaStreamSynchronize(e->stream);
   destroy_graphs(e, nullptr);
   cudaFree(e->warena.base);
   cudaFree(e->ws.base);
@@ -503,15 +529,13 @@ void b200pf_engine_destroy(b200pf_engine* e) {
   cudaFree(e->tap_emb);
   cudaFree(e->tap_logits);
   cudaFree(e->full_logits);
-  cudaStreamSynchronize(e->side);
-  cudaStreamDestroy(e->side);
-  cudaStreamSynchronize(e->copy);
-  cudaStreamDestroy(e->copy);
-  cudaStreamSynchronize(e->d2h);
-  cudaStreamDestroy(e->d2h);
-  cudaEventDestroy(e->ev_fork);
-  cudaEventDestroy(e->ev_join);
-  cudaStreamDestroy(e->stream);
+  for (cudaStream_t st : {e->side, e->copy, e->d2h}) {
+    if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  cudaGetLastError();
   delete e;
 }
 

@@ -32,18 +32,31 @@ bool read_weight_file(const std::string& path, WeightFile* out, std::string* err
     out->cfg[r.key] = r.value;
   }
   if (fread(&n_t, 4, 1, f) != 1 || n_t > (1u << 20)) return fail("bad tensor count");
+  uint64_t file_size = 0;
+  {
+    const long pos = ftell(f);
+    if (pos < 0 || fseek(f, 0, SEEK_END) != 0) return fail("seek");
+    const long end = ftell(f);
+    if (end < 0 || fseek(f, pos, SEEK_SET) != 0) return fail("seek");
+    file_size = (uint64_t)end;
+  }
   std::vector<TensorRec> recs(n_t);
   if (n_t && fread(recs.data(), sizeof(TensorRec), n_t, f) != n_t) return fail("truncated tensor table");
   for (auto& r : recs) {
     r.name[95] = 0;
     if (r.ndim > 4) return fail("bad ndim");
     HostTensor t;
-    int64_t n = 1;
-    for (uint32_t d = 0; d < r.ndim; ++d) { t.shape.push_back((int64_t)r.dims[d]); n *= (int64_t)r.dims[d]; }
-    if ((uint64_t)n * 4 != r.nbytes) return fail(std::string("size mismatch for ") + r.name);
+    uint64_t n = 1;
+    for (uint32_t d = 0; d < r.ndim; ++d) {
+      // every dimension and the running product are bounded by the file size before anything is multiplied further or allocated
+      if (r.dims[d] > file_size || (r.dims[d] != 0 && n > file_size / r.dims[d])) return fail(std::string("bad shape for ") + r.name);
+      t.shape.push_back((int64_t)r.dims[d]);
+      n *= r.dims[d];
+    }
+    if (n * 4 != r.nbytes || r.offset > file_size || r.nbytes > file_size - r.offset) return fail(std::string("size mismatch for ") + r.name);
     t.data.resize(n);
     if (fseek(f, (long)r.offset, SEEK_SET) != 0) return fail("seek");
-    if (n && fread(t.data.data(), 4, n, f) != (size_t)n) return fail(std::string("truncated data for ") + r.name);
+    if (n && fread(t.data.data(), 4, (size_t)n, f) != (size_t)n) return fail(std::string("truncated data for ") + r.name);
     out->tensors[r.name] = std::move(t);
   }
   fclose(f);

@@ -468,7 +468,7 @@ struct b200pf_punc {
 
 extern "C" {
 
-int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_punc** out) {
+static int b200pf_punc_create_impl(const char* punc_dir, int device, int max_tokens, b200pf_punc** out) {
   if (!punc_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
   *out = nullptr;
   int ndev = 0;
@@ -591,6 +591,19 @@ int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_
   PCK(cudaDeviceSynchronize(), "punc init");
   *out = p.release();
   return 0;
+}
+// Parsing a hostile or truncated model directory may throw (std::bad_alloc, std::invalid_argument from the text parsers);
+// nothing may unwind through the C ABI: it becomes an error code with the text in b200pf_last_error().
+int b200pf_punc_create(const char* punc_dir, int device, int max_tokens, b200pf_punc** out) {
+  try {
+    return b200pf_punc_create_impl(punc_dir, device, max_tokens, out);
+  } catch (const std::exception& ex) {
+    set_error(std::string("b200pf_punc_create: ") + ex.what());
+    return B200PF_ERR_IO;
+  } catch (...) {
+    set_error("b200pf_punc_create: unknown exception");
+    return B200PF_ERR_IO;
+  }
 }
 
 void b200pf_punc_destroy(b200pf_punc* p) {

@@ -178,7 +178,7 @@ struct b200pf_vad {
 
 extern "C" {
 
-int b200pf_vad_create(const char* vad_dir, int device, int max_frames, b200pf_vad** out) {
+static int b200pf_vad_create_impl(const char* vad_dir, int device, int max_frames, b200pf_vad** out) {
   if (!vad_dir || !out) { set_error("null argument"); return B200PF_ERR_INVALID; }
   *out = nullptr;
   int ndev = 0;
@@ -270,6 +270,19 @@ int b200pf_vad_create(const char* vad_dir, int device, int max_frames, b200pf_va
   VCK(cudaDeviceSynchronize(), "vad init");
   *out = v.release();
   return 0;
+}
+// Parsing a hostile or truncated model directory may throw (std::bad_alloc, std::invalid_argument from the text parsers);
+// nothing may unwind through the C ABI: it becomes an error code with the text in b200pf_last_error().
+int b200pf_vad_create(const char* vad_dir, int device, int max_frames, b200pf_vad** out) {
+  try {
+    return b200pf_vad_create_impl(vad_dir, device, max_frames, out);
+  } catch (const std::exception& ex) {
+    set_error(std::string("b200pf_vad_create: ") + ex.what());
+    return B200PF_ERR_IO;
+  } catch (...) {
+    set_error("b200pf_vad_create: unknown exception");
+    return B200PF_ERR_IO;
+  }
 }
 
 void b200pf_vad_destroy(b200pf_vad* v) {

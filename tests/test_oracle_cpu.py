@@ -433,6 +433,55 @@ def test_model_dir_errors_are_reported(capi, tmp_path):
         capi.model_dir_probe(str(tmp_path / "nope"))
 
 
+def test_hostile_model_files_become_error_codes(capi, synth, tmp_path):
+    """Nothing may unwind through the C ABI: a tensor table whose shape overflows, a table that points past the end of the file,
+    and text files the number parsers reject all come back as B200PFError (an error code + text), never as a crash."""
+    import shutil
+    import struct
+    good = str(tmp_path / "good")
+    synth.write_synthetic_model_dir(good, dict(n_enc=1, n_dec=1))
+
+    def variant(name):
+        d = str(tmp_path / name)
+        shutil.copytree(good, d)
+        return d
+
+    def weights(recs):
+        out = b"B2PFWTS1" + struct.pack("<I", 0) + struct.pack("<I", len(recs))
+        for name, dims, offset, nbytes in recs:
+            out += name.encode().ljust(96, b"\0") + struct.pack("<I", len(dims)) + struct.pack("<4Q", *(list(dims) + [0] * (4 - len(dims))))
+            out += struct.pack("<QQ", offset, nbytes)
+        return out
+
+    d = variant("overflow")      # 2^33 x 2^33 elements: the product wraps to 0 in 64 bits once multiplied by 4
+    open(os.path.join(d, "model.b200pf"), "wb").write(weights([("encoder.x", (1 << 33, 1 << 33), 0, 0)]))
+    with pytest.raises(capi.B200PFError, match="bad shape|size mismatch"):
+        capi.model_dir_probe(d)
+    d = variant("huge")          # consistent sizes, but far more data than the file holds: no allocation may be attempted
+    open(os.path.join(d, "model.b200pf"), "wb").write(weights([("encoder.x", (1 << 20, 1 << 20), 256, 4 << 40)]))
+    with pytest.raises(capi.B200PFError, match="bad shape|size mismatch"):
+        capi.model_dir_probe(d)
+    d = variant("offset")
+    open(os.path.join(d, "model.b200pf"), "wb").write(weights([("encoder.x", (4,), 1 << 50, 16)]))
+    with pytest.raises(capi.B200PFError, match="size mismatch"):
+        capi.model_dir_probe(d)
+    d = variant("mvn")           # std::stof would throw on this
+    txt = open(os.path.join(d, "am.mvn")).read().split("\n")
+    for i, line in enumerate(txt):
+        if line.startswith("<LearnRateCoef>"):
+            parts = line.split()
+            parts[3] = "not-a-number"
+            txt[i] = " ".join(parts)
+            break
+    open(os.path.join(d, "am.mvn"), "w").write("\n".join(txt))
+    with pytest.raises(capi.B200PFError):
+        capi.model_dir_probe(d)
+    d = variant("tokens")        # std::stoul would throw on this escape
+    open(os.path.join(d, "tokens.json"), "w").write('["<blank>", "\\uZZZZ"]')
+    with pytest.raises(capi.B200PFError):
+        capi.model_dir_probe(d)
+
+
 def test_compute_entry_points_fail_loudly_without_device(capi, synth, tmp_path):
     if capi.device_count() > 0:
         pytest.skip("a B200 is present")
