@@ -518,11 +518,17 @@ int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, i
   }
 }
 
+static void free_batch_resources(b200pf_batch* b);
 void b200pf_engine_destroy(b200pf_engine* e) {   // also the clean-up of a partially constructed engine: every member may be null
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   destroy_graphs(e, nullptr);
+  {
+    std::lock_guard<std::mutex> lock(e->batches_mu);
+    for (b200pf_batch* b : e->live_batches) { free_batch_resources(b); b->e = nullptr; }
+    e->live_batches.clear();
+  }
   cudaFree(e->warena.base);
   cudaFree(e->ws.base);
   cudaFree(e->tap_feats);
@@ -636,7 +642,8 @@ int b200pf_engine_profile_read(b200pf_engine* e, int reset, const char** names, 
 int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** out) {
   if (!e || !out || max_samples <= 0) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   CK(cudaSetDevice(e->device), "cudaSetDevice");
-  std::unique_ptr<b200pf_batch> b(new b200pf_batch);
+  struct BatchDel { void operator()(b200pf_batch* p) const { free_batch_resources(p); delete p; } };   // failure paths release what exists
+  std::unique_ptr<b200pf_batch, BatchDel> b(new b200pf_batch);
   b->e = e;
   b->max_samples = max_samples;
   const size_t S = (size_t)e->cfg.max_segments, R = (size_t)e->cfg.max_rows;
@@ -677,15 +684,13 @@ int b200pf_batch_create(b200pf_engine* e, int64_t max_samples, b200pf_batch** ou
   CK(cudaMallocHost((void**)&b->h_res, (2 * S + 2 + 2 * R + 16) * 4), "cudaMallocHost(results)");
   CK(cudaEventCreateWithFlags(&b->staged, cudaEventDisableTiming), "cudaEventCreate");
   CK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming), "cudaEventCreate");
+  { std::lock_guard<std::mutex> lock(e->batches_mu); e->live_batches.insert(b.get()); }
   *out = b.release();
   return 0;
 }
 
-void b200pf_batch_destroy(b200pf_batch* b) {
-  if (!b) return;
-  cudaSetDevice(b->e->device);
-  cudaStreamSynchronize(b->e->stream);
-  { std::lock_guard<std::mutex> lock(b->e->mu); destroy_graphs(b->e, b); }
+// Device / pinned memory and events of a batch (its engine's device is current).
+static void free_batch_resources(b200pf_batch* b) {
   cudaFree(b->d_pcm);
   cudaFree(b->d_meta);
   cudaFree(b->d_n_tok);
@@ -697,8 +702,26 @@ void b200pf_batch_destroy(b200pf_batch* b) {
   if (b->d_us_alphas) cudaFree(b->d_us_alphas);
   if (b->d_topk_lse) cudaFree(b->d_topk_lse);
   if (b->d_hw) cudaFree(b->d_hw);
-  cudaEventDestroy(b->staged);
-  cudaEventDestroy(b->done);
+  if (b->staged) cudaEventDestroy(b->staged);
+  if (b->done) cudaEventDestroy(b->done);
+  b->d_pcm = nullptr; b->d_meta = nullptr; b->d_n_tok = nullptr; b->h_meta = nullptr; b->h_res = nullptr;
+  b->h_us = nullptr; b->h_topk = nullptr; b->h_stage = nullptr; b->d_us_alphas = nullptr; b->d_topk_lse = nullptr; b->d_hw = nullptr;
+  b->staged = nullptr; b->done = nullptr;
+}
+
+// A batch outliving its engine (a caller -- or a garbage collector -- destroying them in the wrong order) must not touch freed
+// memory: b200pf_engine_destroy releases the resources of the batches that are still alive and orphans them (b->e = nullptr);
+// every batch entry point refuses an orphan, and destroying one only frees the struct.
+void b200pf_batch_destroy(b200pf_batch* b) {
+  if (!b) return;
+  if (b->e) {
+    b200pf_engine* e = b->e;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    { std::lock_guard<std::mutex> lock(e->mu); destroy_graphs(e, b); }
+    { std::lock_guard<std::mutex> lock(e->batches_mu); e->live_batches.erase(b); }
+    free_batch_resources(b);
+  }
   delete b;
 }
 
@@ -767,7 +790,7 @@ static int build_layout(b200pf_batch* b, const std::vector<int64_t>& n_samples, 
 }
 
 int b200pf_batch_set_hotwords(b200pf_batch* b, const float* hw_emb, int n_hw, int dim) {
-  if (!b || n_hw < 0 || (n_hw > 0 && !hw_emb)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || n_hw < 0 || (n_hw > 0 && !hw_emb)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   if (!e->cfg.contextual) { set_error("model has no hotword (contextual) decoder"); return B200PF_ERR_INVALID; }
   if (n_hw > B200PF_MAX_HOTWORDS) { set_error("too many hotwords"); return B200PF_ERR_CAPACITY; }
@@ -833,7 +856,7 @@ int b200pf_engine_hotword_embed(b200pf_engine* e, const int32_t* ids, const int3
 }
 
 int b200pf_batch_stage_s16(b200pf_batch* b, const int16_t* pcm, const int64_t* offsets, int n_seg, void* stream) {
-  if (!b || !offsets || n_seg < 0 || (n_seg > 0 && !pcm)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || !offsets || n_seg < 0 || (n_seg > 0 && !pcm)) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -864,7 +887,7 @@ static bool f32_to_s16_exact(const float* src, int16_t* dst, int64_t n) {
 }
 
 int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* len, int n_seg, void* stream) {
-  if (!b || n_seg < 0 || (n_seg > 0 && (!din || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || n_seg < 0 || (n_seg > 0 && (!din || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -925,7 +948,7 @@ int b200pf_batch_stage_f32(b200pf_batch* b, const float* const* din, const int* 
 }
 
 int b200pf_batch_stage_s16_ptrs(b200pf_batch* b, const int16_t* const* seg, const int64_t* len, int n_seg, void* stream) {
-  if (!b || n_seg < 0 || (n_seg > 0 && (!seg || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || n_seg < 0 || (n_seg > 0 && (!seg || !len))) { set_error("bad argument"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -1168,7 +1191,7 @@ static void destroy_graphs(b200pf_engine* e, const void* batch) {
 extern "C" {
 
 int b200pf_batch_run(b200pf_batch* b, void* stream) {
-  if (!b) { set_error("null batch"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e) { set_error(b ? "the batch's engine was destroyed" : "null batch"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
@@ -1233,7 +1256,7 @@ int b200pf_batch_run(b200pf_batch* b, void* stream) {
 }
 
 int b200pf_batch_collect(b200pf_batch* b, b200pf_result* res, void* stream) {
-  if (!b || !res) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || !res) { set_error("null argument (or the batch's engine was destroyed)"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   CK(cudaSetDevice(e->device), "cudaSetDevice");
   // Results are read on the engine's device->host stream once THIS batch's last kernel has finished (b->done): a forward of
@@ -1340,7 +1363,7 @@ int64_t b200pf_batch_launches(const b200pf_batch* b) { return b ? b->launches : 
 double b200pf_batch_flops(const b200pf_batch* b) { return b ? b->flops : 0.0; }
 
 int b200pf_batch_tap(b200pf_batch* b, const char* name, int seg, float* out, int64_t cap, int64_t shape[2]) {
-  if (!b || !name || !out || !shape) { set_error("null argument"); return B200PF_ERR_INVALID; }
+  if (!b || !b->e || !name || !out || !shape) { set_error("null argument (or the batch's engine was destroyed)"); return B200PF_ERR_INVALID; }
   b200pf_engine* e = b->e;
   if (!e->taps || !b->collected) { set_error("taps need option taps=1 before run and a collected batch"); return B200PF_ERR_INVALID; }
   if (seg < 0 || seg >= b->n_seg_in) { set_error("bad segment index"); return B200PF_ERR_INVALID; }

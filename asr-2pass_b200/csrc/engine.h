@@ -7,6 +7,7 @@
 #include <memory>
 #include <mutex>
 #include <tuple>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -72,6 +73,8 @@ struct b200pf_engine {
   cudaStream_t copy = nullptr;          // host->device staging of the NEXT batch (b200pf_engine_copy_stream)
   cudaStream_t d2h = nullptr;           // device->host result reads of a FINISHED batch (b200pf_batch_collect), while the next one computes
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::mutex batches_mu;
+  std::set<b200pf_batch*> live_batches; // orphaned (resources freed, b->e = nullptr) by b200pf_engine_destroy
   int overlap = 2;
   int ffn_ln_fold = 1;                  // decoder feed-forward LayerNorm(2048) applied inside the w_2 GEMM epilogue (no pass over the hidden)
   int f16 = 1;                          // 16-bit operand format of weights and activations: 0 bf16, 1 IEEE fp16 (cfg.precision)

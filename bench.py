@@ -18,6 +18,7 @@ Prints ONE JSON line.  Keys beyond the contract:
   cpu_baseline        the oracle port on the host cores, fixed sample, fp32 and the int8 stand-in, per-core figures
   config4 / config5   the PRODUCT's multi-GPU path (one handle, per-GPU queues: MultiGpuParaformer) driven by rank 0 over all N
                       GPUs on BASELINE.json configs[3] (1 h stream, arrival order) and configs[4] (256 x 60 s): strong scaling
+  config3             BASELINE.json configs[2] on rank 0's GPU: contextual decoder + 100 hotwords + timestamp head on 256 segments
 """
 import argparse
 import importlib
@@ -257,6 +258,74 @@ def product_multigpu(capi, synth, model_dir, n_gpus, steps):
                           n_gpus=n_gpus, wall_s=dt, value=256 * 60.0 / dt, unit=UNIT, chars=len(text), scaling="strong",
                           segments_per_gpu=h.segments_per_device())
     h.close()
+    return out
+
+
+def config3_leg(capi, synth, steps, n_segments=256, max_rows=65536):
+    """BASELINE.json configs[2]: contextual Paraformer + 100 hotwords + timestamp head (random-init full-size weights) on the first
+    `n_segments` segments of the configs[1] workload, device-resident PCM, one GPU.  Times what a forward with hotwords and
+    timestamps costs (bias decoder, upsampling + BiLSTM head, us_alphas / us_peaks out) next to the hotword compiler."""
+    import tempfile
+    import torch
+    mf = importlib.import_module("asr-2pass_b200.modelfile")
+    pcm, offs = synth.make_segments(1024)
+    lens = synth.segment_lengths(1024)[:n_segments]
+    cfg, W = synth.make_weights(dict(timestamp=1, contextual=1))
+    means, vars_ = synth.make_cmvn()
+    tmp = tempfile.mkdtemp(prefix="b200pf_c3_")
+    mf.write_model_dir(tmp, cfg, W, means, vars_, synth.make_tokens(int(cfg["vocab"])))
+    del W
+    eng = capi.Engine(tmp, max_rows=max_rows, max_segments=4096)
+    rng = np.random.default_rng(0)
+    ids = np.zeros((101, 10), np.int32)
+    ln = np.zeros(101, np.int32)
+    for j in range(100):
+        L = int(rng.integers(2, 7))
+        ids[j, :L] = rng.integers(3, 8403, L)
+        ln[j] = L
+    ids[100, 0], ln[100] = 1, 1
+    eng.hotword_embed(ids, ln)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    hw = eng.hotword_embed(ids, ln)
+    ev1.record()
+    ev1.synchronize()
+    hw_ms = ev0.elapsed_time(ev1)
+    groups = make_batches(lens, max_rows, 4096, capi)
+    batches = []
+    for g in groups:
+        buf = np.concatenate([pcm[offs[i]:offs[i + 1]] for i in g])
+        ho = np.concatenate([[0], np.cumsum([lens[i] for i in g])]).astype(np.int64)
+        b = capi.Batch(eng, len(buf) + 64)
+        b.set_hotwords(hw)
+        b.stage_s16(buf, ho)
+        batches.append(b)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream)
+    for _ in range(3):
+        for b in batches:
+            b.run()
+    res = [b.collect() for b in batches]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(steps):
+            for b in batches:
+                b.run()
+        ev1.record()
+    ev1.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    audio = float(lens.sum()) / 16000.0
+    out = dict(workload="configs[2]: contextual Paraformer + 100 hotwords + timestamps, first %d segments of the configs[1] workload "
+                        "(%.0f audio-s), random-init full-size weights, device-resident PCM" % (n_segments, audio),
+               ms_per_step=ms, value=audio / (ms / 1e3), unit=UNIT, tokens=int(sum(r["n_tokens"] for r in res)),
+               timestamp_peaks=int(sum(int((np.asarray(r.get("us_peaks", [])) >= 1.0 - 1e-4).sum()) for r in res)),
+               launches=int(sum(b.launches for b in batches)), hotword_compile_ms=hw_ms)
+    for b in batches:
+        b.close()
+    eng.close()
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 
@@ -521,6 +590,10 @@ def main():
             multi = product_multigpu(capi, synth, tmp, world, max(2, min(args.steps, 3)))
         except Exception as ex:   # reported, never hidden
             multi = dict(multigpu_product_error=str(ex))
+        try:
+            multi = dict(multi or {}, config3=config3_leg(capi, synth, max(2, min(args.steps, 3))))
+        except Exception as ex:
+            multi = dict(multi or {}, config3=dict(error=str(ex)))
     if world > 1:
         dist.barrier(group=cpu_group)
     if rank != 0:

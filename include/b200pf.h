@@ -93,12 +93,16 @@ int b200pf_device_count(void);
 int b200pf_model_dir_probe(const char* model_dir, b200pf_config* out, int* n_tokens, int* n_tensors);
 
 /* Replaces Paraformer::InitAsr (paraformer.cpp:21-53): reads <model_dir>/{am.mvn, config.yaml,
- * tokens.json, model.b200pf}, uploads bf16 weights to `device`, allocates workspace for batches of up to
+ * tokens.json, model.b200pf}, uploads 16-bit weights (fp16 by default, see b200pf_engine_create_prec) to `device`, allocates workspace for batches of up to
  * max_rows packed rows / max_segments segments (0 -> defaults 32768 / 4096). */
 int b200pf_engine_create(const char* model_dir, int device, int max_rows, int max_segments, b200pf_engine** out);
 /* Same with the operand format chosen explicitly (B200PF_PREC_BF16 / B200PF_PREC_FP16; -1 = the default, which the environment
  * variable B200PF_PREC=bf16|fp16 overrides). */
 int b200pf_engine_create_prec(const char* model_dir, int device, int max_rows, int max_segments, int precision, b200pf_engine** out);
+/* Batches of this engine that are still alive are orphaned: their device and pinned memory is released here, every later call
+ * on them returns B200PF_ERR_INVALID, and b200pf_batch_destroy only frees the handle.  The creating entry points
+ * (b200pf_engine_create*, b200pf_vad_create, b200pf_punc_create, b200pf_model_dir_probe) never unwind: a malformed model
+ * directory becomes B200PF_ERR_IO with the text in b200pf_last_error(). */
 void b200pf_engine_destroy(b200pf_engine* e);
 int b200pf_engine_config(const b200pf_engine* e, b200pf_config* out);
 /* Vocabulary access for the host-side detokeniser (Vocab, onnxruntime/src/vocab.cpp:46-63). */
@@ -109,6 +113,7 @@ const char* b200pf_engine_lang(const b200pf_engine* e);
  * first, 2 = default: attention enqueued first) runs the FSMN memory block on a low-priority side stream concurrently
  * with the attention kernel;
  * "logprob_topk" = k (0..32, default 0) also produces pruned log-softmax posteriors per token (b200pf_result.topk_*);
+ * "ffn_ln_fold" (default 1) applies the decoder feed-forward LayerNorm inside the w_1 / w_2 GEMM epilogues (0: as its own pass);
  * "profile" see below. */
 int b200pf_engine_set_option(b200pf_engine* e, const char* key, int value);
 /* Option "profile" = 1 brackets every launch of b200pf_batch_run with CUDA events on the launching stream.

@@ -405,6 +405,26 @@ def test_capacity_and_argument_errors(capi, synth, small):
     assert r["n_tokens"] == 0
 
 
+def test_batch_outliving_its_engine_is_refused_not_a_crash(capi, synth, gpu, tmp_path_factory):
+    """b200pf_engine_destroy orphans the batches that are still alive (include/b200pf.h): their entry points return an error and
+    destroying them later only frees the handle.  Driven through the raw C ABI -- the Python wrapper closes batches first."""
+    import ctypes as C
+    d = str(tmp_path_factory.mktemp("orphan"))
+    synth.write_synthetic_model_dir(d, dict(n_enc=1, n_dec=1))
+    eng = capi.Engine(d, max_rows=2048, max_segments=16)
+    b = capi.Batch(eng, 48000)
+    pcm = synth.make_audio(32000, 3)
+    offs = np.array([0, 32000], np.int64)
+    assert b.forward_s16(pcm, offs)["n_tokens"] >= 0
+    L = capi.lib()
+    L.b200pf_engine_destroy(eng.h)          # engine first: the batch is now an orphan
+    eng.h = C.c_void_p()
+    eng._batches = []
+    with pytest.raises(capi.B200PFError):
+        b.forward_s16(pcm, offs)
+    b.close()                               # frees the handle only; must not touch the engine's memory
+
+
 def test_forward_full_paraformer_large(capi, synth, gpu, tmp_path_factory):
     """The named architecture (50 + 16 layers, 215.8 M parameters): config[0]'s 10 s segment plus a short and a
     long one, against the fp32 oracle."""
