@@ -143,9 +143,12 @@ struct Stream {
   __device__ int keys16() const { return (keys() + 15) & ~15; }                            // MMA extent of this block
 };
 
-template <bool F16>
+// DBG: the ablation / trace switches (B200PF_ATTN_DBG) exist only in a second instantiation; the product kernel carries none of
+// their branches.
+template <bool F16, bool DBG>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AArgs a) {
+  const int dbg = DBG ? a.dbg : 0;
   extern __shared__ __align__(1024) uint8_t smem[];   // SWIZZLE_128B tiles need 1024-byte alignment (checked below)
   uint8_t* sQ = smem;
   uint8_t* sK = smem + Q_BYTES;
@@ -248,7 +251,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr uint32_t idesc_s0 = umma_idesc_h16(F16, BQ, 0);           // N filled in per block
     constexpr uint32_t idesc_pv = umma_idesc_h16(F16, BQ, HD, 0, 1);    // B (= V) is MN-major
     const uint32_t q_addr = smem_u32(sQ);
-    const bool tracing = (a.dbg & 64) && blockIdx.x == 0 && lane == 0;
+    const bool tracing = DBG && (dbg & 64) && blockIdx.x == 0 && lane == 0;
     Stream s_it(a, units, blockIdx.x, gridDim.x);    // next block whose S is to be issued
     Stream pv_it(a, units, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
     auto issue_s = [&]() {
@@ -268,7 +271,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
-          if ((a.dbg & 4) && ks > 0) break;
+          if ((dbg & 4) && ks > 0) break;
           const uint64_t da = umma_desc_sw128(q_addr + (ks >> 2) * (Q_BYTES / 2)) + 2 * (ks & 3);
           const uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (K_BYTES / 2)) + 2 * (ks & 3);
           umma_bf16(tmem_base + sb * BKV, da, db, idesc, ks != 0 ? 1u : 0u);
@@ -302,7 +305,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       const uint32_t p_tmem = tmem_base + (uint32_t)((g & 1) * BKV);   // P sits where S of this block was: 8 columns per 16 keys
       const uint32_t v_addr = smem_u32(sV + stage * K_BYTES);
-      const int ksteps = (a.dbg & 8) ? 0 : pv_it.keys16() >> 4;
+      const int ksteps = (dbg & 8) ? 0 : pv_it.keys16() >> 4;
       const bool first = pv_it.j == 0, last = pv_it.j + 1 == pv_it.nb;
       if (elect_one()) {
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -328,10 +331,10 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     float m = -INFINITY, l = 0.f, m_used = 0.f;
     for (Stream st(a, units, blockIdx.x, gridDim.x); st.valid; st.advance()) {
       const int g = st.g, sb = g & 1;
-      const bool warp_active = st.q0 + quarter * 32 < st.Tq && !(a.dbg & 16);   // warp-uniform: does this warp own any real query row?
+      const bool warp_active = st.q0 + quarter * 32 < st.Tq && !(dbg & 16);   // warp-uniform: does this warp own any real query row?
       if (st.j == 0) { m = -INFINITY; l = 0.f; m_used = 0.f; }
       mbar_wait(&s_full[sb], (uint32_t)((g >> 1) & 1));
-      if ((a.dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 1] = clock64();   // softmax warp saw S of block g
+      if (DBG && (dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 1] = clock64();   // softmax warp saw S of block g
       tc_fence_after();
       const int nvalid = st.keys();
       bool need = false;
@@ -366,8 +369,8 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           for (int c = 0; c < 32; c += 2) {
             const float2 x = ffma2(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), sc2, mc2);
             const float2 y = ffma2(make_float2(__uint_as_float(r2[c]), __uint_as_float(r2[c + 1])), sc2, mc2);
-            const float2 p = a.dbg & 1 ? x : make_float2(ex2(x.x), ex2(x.y));
-            const float2 q = a.dbg & 1 ? y : make_float2(ex2(y.x), ex2(y.y));
+            const float2 p = dbg & 1 ? x : make_float2(ex2(x.x), ex2(x.y));
+            const float2 q = dbg & 1 ? y : make_float2(ex2(y.x), ex2(y.y));
             la = fadd2(la, p);
             lb = fadd2(lb, q);
             pk[c >> 1] = pack_h2<F16>(p.x, p.y);
@@ -439,7 +442,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_before();
       }
       __syncwarp();
-      if ((a.dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 2] = clock64();   // softmax warp arrives for block g
+      if (DBG && (dbg & 64) && blockIdx.x == 0 && g < 64 && threadIdx.x == 64) a.trace[8 * g + 2] = clock64();   // softmax warp arrives for block g
       if (lane == 0) mbar_arrive(&p_full[sb]);
       if (st.j + 1 == st.nb) {
         // ---- this head's output ----
@@ -554,8 +557,10 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   if (p.n_work <= 0) return 0;
   static PerDeviceOnce once;
   int rc = once_per_device(once, [] {
-    cudaError_t err = cudaFuncSetAttribute(attn_heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(attn_heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t err = cudaSuccess;
+    auto set = [&](auto kernel) { if (err == cudaSuccess) err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); };
+    set(attn_heads_kernel<false, false>); set(attn_heads_kernel<true, false>);
+    set(attn_heads_kernel<false, true>); set(attn_heads_kernel<true, true>);
     return (int)err;
   });
   if (rc) return rc;
@@ -568,8 +573,12 @@ int attention_tcgen05(const AttnProblem& p, cudaStream_t stream) {
   static const int ctas_per_sm = getenv("B200PF_ATTN_CTAS") ? atoi(getenv("B200PF_ATTN_CTAS")) : 2;
   const int resident = ctas_per_sm * (p.num_sms > 0 ? p.num_sms : 148), units = p.n_work * p.n_heads;
   const dim3 grid(units < resident ? units : resident);
-  if (p.f16) return launch_kernel(attn_heads_kernel<true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
-  return launch_kernel(attn_heads_kernel<false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+  if (a.dbg) {   // micro-benchmark ablations / trace only
+    if (p.f16) return launch_kernel(attn_heads_kernel<true, true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+    return launch_kernel(attn_heads_kernel<false, true>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+  }
+  if (p.f16) return launch_kernel(attn_heads_kernel<true, false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
+  return launch_kernel(attn_heads_kernel<false, false>, grid, dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, a);
 }
 
 // ablation 64: the stamps of the last launch (host copy), for tools/bench_attn.py
