@@ -475,7 +475,7 @@ class MicroBatcher:
     """funasr_b200::MicroBatcher through its C hooks: merges concurrent batch-1 Forward calls (the 2-pass offline leg,
     funasrruntime.cpp:570-586) into batched forwards.  offline=None builds the host-only mock model (tests)."""
 
-    def __init__(self, offline=None, max_wait_us=20000, max_batch=256, max_rows=32768, mock_latency_us=0):
+    def __init__(self, offline=None, max_wait_us=5000, max_batch=256, max_rows=32768, mock_latency_us=0):
         self._offline = offline
         if offline is None:
             self.h = host_lib().b200pf_host_mb_create_mock(max_wait_us, max_batch, max_rows, mock_latency_us)

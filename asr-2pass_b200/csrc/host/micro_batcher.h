@@ -34,7 +34,8 @@
 namespace funasr_b200 {
 
 struct MicroBatcherOptions {
-  int max_wait_us = 20000;   // deadline for the oldest waiting segment (20-50 ms)
+  int max_wait_us = 5000;    // deadline for the oldest waiting segment.  5 ms: a batch-1 forward itself takes 4 ms, and the sweep in
+                             // profiles/r02_microbatch_sweep.txt gives 41.8 k RTFx / 3.9 ms mean wait at 5 ms against 22.2 k / 18.7 ms at 20 ms
   int max_batch = 256;       // segments per batch
   int max_rows = 32768;      // packed LFR rows (T + 1 per segment) per batch; must not exceed the engine's max_rows
 };
