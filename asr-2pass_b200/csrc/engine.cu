@@ -1017,6 +1017,8 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
     return rc;
   };
 
+  const bool small = M <= 8192;   // launch-latency regime: independent kernels are forked onto the side stream (also under capture)
+
   // ---- K1 front end ----
   LAUNCH(0, (double)b->n_frames * (160 * 2 + 80 * 4), fbank_launch(b->d_pcm, b->pcm_is_f32, b->d_sample_off, b->d_fb_off, S, b->n_frames_run, e->ft, e->fb, s), "fbank");
   LAUNCH(0, (double)M * 560 * 4 * 2, lfr_cmvn_posenc_launch(e->fb, b->d_fb_off, b->d_row_seg, b->d_row_info, M, e->ft, sqrtf((float)D), e->x0,
@@ -1042,7 +1044,9 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
     // (CUDA-core FMA work next to tensor-core / MUFU work) and join before the output projection.
     // overlap 1: FSMN enqueued first; overlap 2: attention enqueued first, so its CTAs (two per SM) take the SMs and the
     // FSMN CTAs fill the register space left over (one per SM) instead of the other way round.
-    const bool fork = e->overlap && !e->profile && !capturing;
+    // Small batches are latency bound (a few CTAs per kernel): there the fork also happens inside a captured graph -- the side
+    // stream joins the capture through the event -- and the two kernels really run side by side.
+    const bool fork = e->overlap && !e->profile && (!capturing || small);
     cudaStream_t fs = fork ? e->side : s;
     if (fork) {
       CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
@@ -1122,15 +1126,30 @@ static int enqueue_forward(b200pf_batch* b, cudaStream_t s, bool capturing) {
       CKL(gemm(e->ffn, c.d_ff, R, w.w2, Lcap, Ldev, ep, 0, 0, 12), "dec gemm w2"); }
     return 0;
   };
+  // Small batches: the cross-attention k/v projection depends on the encoder output only, so it runs on the side stream next to
+  // the layer's feed-forward / FSMN / q-projection chain (five dependent launches) and joins before the cross attention.  (Its
+  // output buffer was last read by the previous layer's cross attention, which precedes the fork point on `s`.)
+  const bool kv_fork = small && e->overlap && !e->profile;
   for (int l = 0; l < c.n_dec; ++l) {
     const DecLayer& w = e->dec[l];
+    if (kv_fork) {
+      CK(cudaEventRecord(e->ev_fork, s), "cudaEventRecord");
+      CK(cudaStreamWaitEvent(e->side, e->ev_fork, 0), "cudaStreamWaitEvent");
+      GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
+      GemmProblem p;
+      p.A = e->enc_bf16; p.lda = D; p.rows_a = R; p.rows_c = R; p.W = w.kv.w; p.ldw = w.kv.in; p.M = M; p.N = w.kv.out; p.K = w.kv.in; p.f16 = e->f16;
+      ++nl;
+      CKL(gemm_bf16_tcgen05(p, ep, sms, e->side), "dec gemm kv");
+      CK(cudaEventRecord(e->ev_join, e->side), "cudaEventRecord");
+    }
     { int rc = dec_ffn(w); if (rc) return rc; }
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(tbuf, 0, Lcap, Ldev, D, w.ln2.g, w.ln2.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln2");
     LAUNCH(4, Lest * 512 * 10, fsmn_launch(e->hb, D, 0, w.fsmn_wt, e->tok_info, Lcap, Ldev, 1, nullptr, e->y, s, e->f16, sms), "dec fsmn");
     LAUNCH(1, Lest * 512 * 6, layernorm_launch(e->y, 0, Lcap, Ldev, D, w.ln3.g, w.ln3.b, c.ln_eps, e->hb, nullptr, nullptr, 0, s, e->f16), "dec ln3");
     { GemmEpilogue ep; ep.bias = w.q.b; ep.out_bf16 = e->mem; ep.ld_out_bf16 = D;
       CKL(gemm(e->hb, D, R, w.q, Lcap, Ldev, ep, 0, 0, 12), "dec gemm q"); }
-    { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
+    if (kv_fork) CK(cudaStreamWaitEvent(s, e->ev_join, 0), "cudaStreamWaitEvent");   // the k/v projection forked at the top of the layer
+    else { GemmEpilogue ep; ep.bias = w.kv.b; ep.out_bf16 = e->qkv; ep.ld_out_bf16 = 2 * D;
       CKL(gemm(e->enc_bf16, D, R, w.kv, M, nullptr, ep, 0, 0, 12), "dec gemm kv"); }
     LAUNCH(3, 2.0 * sumT2 * 512, attention_tcgen05(cp, s), "cross attention");
     if (!(c.contextual && l == c.n_dec - 1)) {

@@ -51,10 +51,15 @@ struct KArgs {
 //      out-projection and FFN2) the tile leaves as a TMA REDUCE-ADD, so the SMs never load the residual stream: the
 //      read-modify-write of x happens in L2.
 // F16: the 16-bit operands and outputs are IEEE fp16 instead of bf16 (engine precision 1, see ptx.cuh pack_h2).
-template <int EPI, bool F16>
+//   3  = 1 + per-row partial sums of the rounded outputs (LayerNorm fold, producer side; GemmEpilogue::row_stats_out)
+//   4  = 2 + LayerNorm applied from those sums (consumer side; GemmEpilogue::ln_stats) -- separate instantiations, so that the
+//        hot epilogues 1 and 2 carry none of the fold's branches or registers
+template <int EPI_, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, KArgs a) {
+  constexpr int EPI = EPI_ == 3 ? 1 : (EPI_ == 4 ? 2 : EPI_);
+  constexpr bool kRowSums = EPI_ == 3, kLnApply = EPI_ == 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -223,7 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (e.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
               pk[hh * 16 + 2 * g] = pack_h2<F16>(v0, v1);
               pk[hh * 16 + 2 * g + 1] = pack_h2<F16>(v2, v3);
-              if (e.row_stats_out) {   // of the values the consumer GEMM will read
+              if constexpr (kRowSums) {   // of the values the consumer GEMM will read
                 const float2 q0 = unpack_h2<F16>(pk[hh * 16 + 2 * g]), q1 = unpack_h2<F16>(pk[hh * 16 + 2 * g + 1]);
                 st1 += (q0.x + q0.y) + (q1.x + q1.y);
                 st2 = fmaf(q0.x, q0.x, st2); st2 = fmaf(q0.y, q0.y, st2); st2 = fmaf(q1.x, q1.x, st2); st2 = fmaf(q1.y, q1.y, st2);
@@ -252,7 +257,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
         }
-        if (e.row_stats_out && row_base + lane < M)
+        if (kRowSums && row_base + lane < M)
           e.row_stats_out[(size_t)(row_base + lane) * e.stats_slots + (col_base >> 7)] = make_float2(st1, st2);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -274,14 +279,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (e.bias) {
           const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
           sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
-          if (e.ln_stats) {
+          if constexpr (kLnApply) {
             const uint4 cs = ldg128_nc(e.ln_csum + col_base + lane * 4);
             sts128(sbias + 512 + lane * 16, cs.x, cs.y, cs.z, cs.w);
           }
           warp_sync_smem();
         }
         float ln_mean = 0.f, ln_rstd = 1.f;
-        if (e.ln_stats && row_ok) {   // the row's partial sums, combined in slot order
+        if (kLnApply && row_ok) {   // the row's partial sums, combined in slot order
           const float2* sp = e.ln_stats + (size_t)row * e.ln_slots;
           float s1 = 0.f, s2 = 0.f;
           for (int i = 0; i < e.ln_slots; ++i) { const float2 t = sp[i]; s1 += t.x; s2 += t.y; }
@@ -317,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int g = 0; g < 8; ++g) {
             float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]);
             float v2 = __uint_as_float(r[4 * g + 2]), v3 = __uint_as_float(r[4 * g + 3]);
-            if (e.ln_stats) {
+            if constexpr (kLnApply) {
               const float4 cs = lds128f(sbias + 512 + (c * 32 + 4 * g) * 4);
               v0 = ln_rstd * (v0 - ln_mean * cs.x); v1 = ln_rstd * (v1 - ln_mean * cs.y);
               v2 = ln_rstd * (v2 - ln_mean * cs.z); v3 = ln_rstd * (v3 - ln_mean * cs.w);
@@ -601,7 +606,9 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
     cudaError_t err = cudaSuccess;
     auto set = [&](auto kernel) { if (err == cudaSuccess) err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); };
     set(gemm_tcgen05_kernel<0, false>); set(gemm_tcgen05_kernel<1, false>); set(gemm_tcgen05_kernel<2, false>);
+    set(gemm_tcgen05_kernel<3, false>); set(gemm_tcgen05_kernel<4, false>);
     set(gemm_tcgen05_kernel<0, true>); set(gemm_tcgen05_kernel<1, true>); set(gemm_tcgen05_kernel<2, true>);
+    set(gemm_tcgen05_kernel<3, true>); set(gemm_tcgen05_kernel<4, true>);
     return (int)err;
   });
   if (rc) return rc;
@@ -637,11 +644,15 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
   const dim3 g(grid), b(kThreads);
   if (p.f16) {
+    if (fast && e.row_stats_out) return launch_kernel(gemm_tcgen05_kernel<3, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
     if (fast) return launch_kernel(gemm_tcgen05_kernel<1, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+    if (f32tma && e.ln_stats) return launch_kernel(gemm_tcgen05_kernel<4, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
     if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
     return launch_kernel(gemm_tcgen05_kernel<0, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
   }
+  if (fast && e.row_stats_out) return launch_kernel(gemm_tcgen05_kernel<3, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
   if (fast) return launch_kernel(gemm_tcgen05_kernel<1, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+  if (f32tma && e.ln_stats) return launch_kernel(gemm_tcgen05_kernel<4, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
   if (f32tma) return launch_kernel(gemm_tcgen05_kernel<2, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
   return launch_kernel(gemm_tcgen05_kernel<0, false>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
 }
