@@ -99,7 +99,11 @@ std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool
   if (nd == 1) return models_[0]->Forward(din, len, input_finished, hw_emb, wfst_decoder, batch_in);
   std::vector<int> assign;
   PartitionSegments(len, batch_in, nd, &assign);
-  struct Share { std::vector<float*> ptr; std::vector<int> len, idx; std::vector<std::string> out; };
+  // Greedy path: the workers return token ids (SegmentRaw) and the text is built HERE, in the caller's order, through the first
+  // model's detokeniser -- so that sharding changes no character of what a one-GPU handle returns (the reference's Vocab carries
+  // a leading-space decision from one call to the next).  With an LM decoder handle the workers decode themselves.
+  const bool central_text = wfst_decoder == nullptr;
+  struct Share { std::vector<float*> ptr; std::vector<int> len, idx; std::vector<std::string> out; std::vector<SegmentRaw> raw; };
   std::vector<Share> share(nd);
   for (int i = 0; i < batch_in; ++i) {
     Share& s = share[assign[i]];
@@ -115,7 +119,8 @@ std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool
     ParaformerB200* m = models_[d].get();
     Worker* w = workers_[d].get();
     Post(d, [=, &hw_emb, &mu, &cv, &pending]() {
-      s->out = m->Forward(s->ptr.data(), s->len.data(), input_finished, hw_emb, wfst_decoder, (int)s->idx.size());
+      if (central_text) s->raw = m->ForwardRaw(s->ptr.data(), s->len.data(), (int)s->idx.size(), hw_emb);
+      else s->out = m->Forward(s->ptr.data(), s->len.data(), input_finished, hw_emb, wfst_decoder, (int)s->idx.size());
       {
         std::lock_guard<std::mutex> wl(w->mu);
         w->segments += (long long)s->idx.size();
@@ -127,6 +132,15 @@ std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool
   {
     std::unique_lock<std::mutex> lk(mu);
     cv.wait(lk, [&] { return pending == 0; });
+  }
+  if (central_text) {
+    std::vector<const SegmentRaw*> by_index(batch_in, nullptr);
+    for (int d = 0; d < nd; ++d)
+      for (size_t k = 0; k < share[d].idx.size() && k < share[d].raw.size(); ++k) by_index[share[d].idx[k]] = &share[d].raw[k];
+    std::lock_guard<std::mutex> lk(text_mu_);
+    for (int i = 0; i < batch_in; ++i)
+      if (by_index[i]) results[i] = models_[0]->TextOf(*by_index[i]);
+    return results;
   }
   for (int d = 0; d < nd; ++d)
     for (size_t k = 0; k < share[d].idx.size(); ++k)
@@ -143,7 +157,7 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
   std::vector<int> len32(n_seg), assign;
   for (int i = 0; i < n_seg; ++i) len32[i] = (int)len[i];
   PartitionSegments(len32.data(), n_seg, nd, &assign);
-  struct Share { std::vector<const int16_t*> ptr; std::vector<int64_t> len; std::vector<int> idx; std::vector<std::string> out; };
+  struct Share { std::vector<const int16_t*> ptr; std::vector<int64_t> len; std::vector<int> idx; std::vector<SegmentRaw> raw; };
   std::vector<Share> share(nd);
   for (int i = 0; i < n_seg; ++i) {
     Share& s = share[assign[i]];
@@ -159,7 +173,7 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
     ParaformerB200* m = models_[d].get();
     Worker* w = workers_[d].get();
     Post(d, [=, &hw_emb, &mu, &cv, &pending]() {
-      s->out = m->ForwardSegments16(s->ptr.data(), s->len.data(), (int)s->idx.size(), hw_emb);
+      s->raw = m->ForwardSegments16Raw(s->ptr.data(), s->len.data(), (int)s->idx.size(), hw_emb);
       {
         std::lock_guard<std::mutex> wl(w->mu);
         w->segments += (long long)s->idx.size();
@@ -172,9 +186,14 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
     std::unique_lock<std::mutex> lk(mu);
     cv.wait(lk, [&] { return pending == 0; });
   }
-  for (int d = 0; d < nd; ++d)
-    for (size_t k = 0; k < share[d].idx.size(); ++k)
-      if (k < share[d].out.size()) results[share[d].idx[k]] = std::move(share[d].out[k]);
+  {   // text in the caller's order through one detokeniser (see Forward above)
+    std::vector<const SegmentRaw*> by_index(n_seg, nullptr);
+    for (int d = 0; d < nd; ++d)
+      for (size_t k = 0; k < share[d].idx.size() && k < share[d].raw.size(); ++k) by_index[share[d].idx[k]] = &share[d].raw[k];
+    std::lock_guard<std::mutex> lk(text_mu_);
+    for (int i = 0; i < n_seg; ++i)
+      if (by_index[i]) results[i] = models_[0]->TextOf(*by_index[i]);
+  }
   return results;
 }
 

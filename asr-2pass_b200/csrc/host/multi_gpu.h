@@ -76,6 +76,7 @@ class MultiGpuParaformer : public Model {
   int max_rows_, max_segments_;
   std::vector<std::unique_ptr<ParaformerB200>> models_;
   std::vector<std::unique_ptr<Worker>> workers_;
+  std::mutex text_mu_;   // the one detokeniser (models_[0]) that turns every call's token ids into text, in the caller's order
 };
 
 }  // namespace funasr_b200

@@ -212,11 +212,24 @@ void ParaformerB200::InitLm(const std::string& lm_file, const std::string& lm_cf
 }
 #endif
 
-std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg, void* wfst_decoder) {
+std::string ParaformerB200::TextOf(const SegmentRaw& seg) {
+  if (!seg.has_features) return std::string();
+  if (!has_timestamp_) return vocab_->ToText(seg.ids, language_);  // GreedySearch, paraformer.cpp:386-397
+  // GreedySearch with is_stamp (paraformer.cpp:398-407): Vector2String -> TimestampOnnx -> PostProcess
+  std::vector<std::string> pieces = vocab_->ToPieces(seg.ids);
+  std::vector<std::string> raw(pieces);
+  std::vector<float> us_alphas(seg.us_alphas), us_peaks(seg.us_peaks);
+  std::string dbg;
+  std::vector<pf::host::Span> spans = pf::host::TimestampFromPeaks(&us_alphas, us_peaks, &pieces, &dbg);
+  return pf::host::MergeWithStamps(raw, spans);
+}
+
+std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg, void* wfst_decoder, SegmentRaw* raw_out) {
   std::vector<std::string> out(n_seg);
   last_ids_.assign(n_seg, std::vector<int>());
   for (int i = 0; i < n_seg; ++i) {
     const int cnt = r.token_counts[i];
+    if (raw_out) raw_out[i] = SegmentRaw();
     if (r.lfr_frames[i] <= 0) continue;  // empty features -> "" (paraformer.cpp:477-480)
     std::vector<int> ids(r.token_ids + r.token_offsets[i], r.token_ids + r.token_offsets[i] + cnt);
 #ifdef B200PF_WITH_REFERENCE_HEADERS
@@ -239,17 +252,16 @@ std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_se
       continue;
     }
 #endif
-    if (!has_timestamp_) {
-      out[i] = vocab_->ToText(ids, language_);  // GreedySearch, paraformer.cpp:386-397
-    } else {
-      // GreedySearch with is_stamp (paraformer.cpp:398-407): Vector2String -> TimestampOnnx -> PostProcess
-      std::vector<std::string> pieces = vocab_->ToPieces(ids);
-      std::vector<std::string> raw(pieces);
-      std::vector<float> us_alphas(r.us_alphas + r.us_offsets[i], r.us_alphas + r.us_offsets[i + 1]);
-      std::vector<float> us_peaks(r.us_peaks + r.us_offsets[i], r.us_peaks + r.us_offsets[i + 1]);
-      std::string dbg;
-      std::vector<pf::host::Span> spans = pf::host::TimestampFromPeaks(&us_alphas, us_peaks, &pieces, &dbg);
-      out[i] = pf::host::MergeWithStamps(raw, spans);
+    {
+      SegmentRaw seg;
+      seg.has_features = true;
+      seg.ids = ids;
+      if (has_timestamp_) {
+        seg.us_alphas.assign(r.us_alphas + r.us_offsets[i], r.us_alphas + r.us_offsets[i + 1]);
+        seg.us_peaks.assign(r.us_peaks + r.us_offsets[i], r.us_peaks + r.us_offsets[i + 1]);
+      }
+      if (raw_out) raw_out[i] = std::move(seg);   // the caller builds the text (MultiGpuParaformer: in the caller's order)
+      else out[i] = TextOf(seg);
     }
     last_ids_[i].swap(ids);
   }
@@ -295,7 +307,7 @@ bool ParaformerB200::StageSlot(int k, const int16_t* pcm, const int64_t* offsets
   return true;
 }
 
-bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder) {
+bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder, SegmentRaw* raw) {
   std::vector<int32_t> counts(n), offs(n + 1), frames(n), ids((size_t)max_rows_), fire((size_t)max_rows_), us_offs(n + 1), tk_ids;
   std::vector<float> us_a, us_p, tk_lp, tk_lse;
   b200pf_result r;
@@ -312,7 +324,7 @@ bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out, vo
     r.topk_logprob = tk_lp.data(); r.topk_ids = tk_ids.data(); r.token_lse = tk_lse.data();
   }
   if (b200pf_batch_collect(slots_[k].batch, &r, nullptr) != 0) { fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error()); return false; }
-  *out = Decode(r, n, wfst_decoder);
+  *out = Decode(r, n, wfst_decoder, raw);
   return true;
 }
 
@@ -321,7 +333,7 @@ bool ParaformerB200::CollectSlot(int k, int n, std::vector<std::string>* out, vo
 // (paraformer.cpp:582-587).  Results keep the caller's order.
 std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
                                                 const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16,
-                                                const int64_t* len16, void* wfst_decoder) {
+                                                const int64_t* len16, void* wfst_decoder, SegmentRaw* raw) {
   std::vector<std::string> results(n_seg > 0 ? n_seg : 0);
   tl_failed_segments = 0;
   if (n_seg <= 0 || !engine_) return results;
@@ -386,7 +398,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
     bool done = false;
     if (running[i]) {
       std::vector<std::string> part;
-      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder)) {
+      if (CollectSlot((int)(i & 1), subs[i].end - subs[i].start, &part, wfst_decoder, raw ? raw + subs[i].start : nullptr)) {
         for (int k = 0; k < subs[i].end - subs[i].start; ++k) results[subs[i].start + k] = part[k];
         done = true;
       }
@@ -414,6 +426,19 @@ std::string ParaformerB200::Forward(float* din, int len, bool input_finished, co
 std::vector<std::string> ParaformerB200::ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
                                                            const std::vector<std::vector<float>>& hw_emb) {
   return RunAll(nullptr, nullptr, nullptr, nullptr, n_seg, hw_emb, seg, len);
+}
+
+std::vector<SegmentRaw> ParaformerB200::ForwardRaw(float** din, int* len, int batch_in, const std::vector<std::vector<float>>& hw_emb) {
+  std::vector<SegmentRaw> raw(batch_in > 0 ? batch_in : 0);
+  RunAll(nullptr, nullptr, din, len, batch_in, hw_emb, nullptr, nullptr, nullptr, raw.data());
+  return raw;
+}
+
+std::vector<SegmentRaw> ParaformerB200::ForwardSegments16Raw(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                                             const std::vector<std::vector<float>>& hw_emb) {
+  std::vector<SegmentRaw> raw(n_seg > 0 ? n_seg : 0);
+  RunAll(nullptr, nullptr, nullptr, nullptr, n_seg, hw_emb, seg, len, nullptr, raw.data());
+  return raw;
 }
 
 std::vector<std::string> ParaformerB200::ForwardPcm16(const int16_t* pcm, const int64_t* offsets, int n_seg,

@@ -69,6 +69,17 @@ void PackHotwords(const std::string& hotwords, const std::unordered_map<std::str
 // SegDict::SegDict (seg_dict.cpp:19-38): "word \t piece piece ..." per line.
 void LoadSegDict(const std::string& path, std::unordered_map<std::string, std::vector<std::string>>* out);
 
+// What the engine returns for one segment before it becomes text: greedy token ids (and, for timestamp models, the upsampled
+// alphas / peaks).  MultiGpuParaformer collects these from its per-GPU workers and turns them into text itself, in the CALLER's
+// order, through ONE detokeniser -- the reference's Vocab carries state from one call to the next (last_is_complete_english_,
+// vocab.cpp:177,259-261,283-288: whether the next text starts with a space), so text built per GPU share would differ from a
+// one-GPU handle's in exactly those spaces.
+struct SegmentRaw {
+  bool has_features = false;   // false: too short for one frame -> "" (paraformer.cpp:477-480)
+  std::vector<int> ids;
+  std::vector<float> us_alphas, us_peaks;
+};
+
 class ParaformerB200 : B200PF_MODEL_BASES {
  public:
   // device: CUDA ordinal; max_rows / max_segments: engine capacity (0 = defaults)
@@ -98,6 +109,13 @@ class ParaformerB200 : B200PF_MODEL_BASES {
   // are, without a host-side gather.
   std::vector<std::string> ForwardSegments16(const int16_t* const* seg, const int64_t* len, int n_seg,
                                              const std::vector<std::vector<float>>& hw_emb = {{0.0}});
+
+  // The same forwards stopped before detokenisation (greedy path only; an LM decoder handle is not taken here).
+  std::vector<SegmentRaw> ForwardRaw(float** din, int* len, int batch_in, const std::vector<std::vector<float>>& hw_emb = {{0.0}});
+  std::vector<SegmentRaw> ForwardSegments16Raw(const int16_t* const* seg, const int64_t* len, int n_seg,
+                                               const std::vector<std::vector<float>>& hw_emb = {{0.0}});
+  // GreedySearch's text for one segment (paraformer.cpp:386-407); advances this object's detokeniser state like the reference's Vocab.
+  std::string TextOf(const SegmentRaw& seg);
 
   void StartUtterance() override {}
   void EndUtterance() override {}
@@ -143,7 +161,7 @@ class ParaformerB200 : B200PF_MODEL_BASES {
   const std::vector<std::vector<int>>& last_ids() const { return last_ids_; }
 
  private:
-  std::vector<std::string> Decode(const b200pf_result& r, int n_seg, void* wfst_decoder);
+  std::vector<std::string> Decode(const b200pf_result& r, int n_seg, void* wfst_decoder, SegmentRaw* raw = nullptr);
   // engine-sized sub-batches through the C ABI, double buffered: pcm16 (offsets) or float (din/len)
   struct Slot {
     b200pf_batch* batch = nullptr;
@@ -153,10 +171,11 @@ class ParaformerB200 : B200PF_MODEL_BASES {
   };
   bool StageSlot(int k, const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n, int64_t samples,
                  const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr, const int64_t* len16 = nullptr);
-  bool CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder);
+  bool CollectSlot(int k, int n, std::vector<std::string>* out, void* wfst_decoder, SegmentRaw* raw = nullptr);
+  // raw != nullptr: [n_seg] records are filled instead of text (the returned strings stay empty)
   std::vector<std::string> RunAll(const int16_t* pcm, const int64_t* offsets, float** din, int* len, int n_seg,
                                   const std::vector<std::vector<float>>& hw_emb, const int16_t* const* seg16 = nullptr,
-                                  const int64_t* len16 = nullptr, void* wfst_decoder = nullptr);
+                                  const int64_t* len16 = nullptr, void* wfst_decoder = nullptr, SegmentRaw* raw = nullptr);
   bool UseLmDecoder(void* wfst_decoder) const;   // an LM is loaded and the caller passed a decoder handle (paraformer.cpp:565)
 
   int device_, max_rows_, max_segments_;

@@ -243,6 +243,16 @@ def product_multigpu(capi, synth, model_dir, n_gpus, steps):
                                    "FunOfflineInferSegmentsB200 on one handle" % (len(segs), sum(e - b for b, e in segs) / 16000.0),
                           n_gpus=n_gpus, wall_s=dt, value=3600.0 / dt, unit="stream_s/s", chars=len(text), scaling="strong",
                           segments_per_gpu=h.segments_per_device())
+    if n_gpus > 1:
+        # self-check of the sharded path on hardware: the same call on a ONE-GPU handle must return the very same text (segments are
+        # independent, the engine is batch invariant, and the pool builds the text in the caller's order through one detokeniser, so
+        # sharding may not change a character).  The call is made twice: like the reference's Vocab, the detokeniser carries a
+        # leading-space decision over from the previous call, so both handles must come from the same previous call.
+        h1 = capi.OfflineHandle(model_dir, max_rows=65536, max_segments=4096, batch_size=4096, devices=[0])
+        h1.infer_segments(pcm, sb, se)
+        text1 = h1.infer_segments(pcm, sb, se)
+        h1.close()
+        out["config4"]["text_equals_1gpu_handle"] = bool(text1 == text)
     del pcm
     # configs[4]: 256 segments x 60 s (T = 1000 LFR frames)
     one = synth.make_audio(960000, 4321)
