@@ -359,18 +359,35 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
   const bool grow = env_rows <= 0 && total_rows > 16384;
   int64_t row_cap = grow ? std::min<int64_t>(max_rows_, 8192) : (env_rows > 0 ? std::min<int64_t>(max_rows_, env_rows) : (int64_t)max_rows_);
   int start = 0;
+  int64_t rows_done = 0;
   while (start < n_seg) {
     int64_t rows = 0, samples = 0;
     int end = start;
-    while (end < n_seg && end - start < max_segments_) {
-      const int64_t ns = seg16 ? len16[end] : (pcm ? offsets[end + 1] - offsets[end] : (int64_t)len[end]);
+    auto seg_rows = [&](int k, int64_t* ns_out) {
+      const int64_t ns = seg16 ? len16[k] : (pcm ? offsets[k + 1] - offsets[k] : (int64_t)len[k]);
       const int T = b200pf_num_lfr_frames(ns);
-      const int64_t r = T > 0 ? T + 1 : 0;
+      *ns_out = ns;
+      return (int64_t)(T > 0 ? T + 1 : 0);
+    };
+    while (end < n_seg && end - start < max_segments_) {
+      int64_t ns;
+      const int64_t r = seg_rows(end, &ns);
       if (end > start && rows + r > row_cap) break;
       rows += r;
       samples += ns;
       ++end;
     }
+    // A small remainder (less than a quarter of this sub-batch) would be one more launch-bound forward: a forward of a few thousand
+    // rows costs ~8 ms whatever its size.  If it still fits the engine, this sub-batch takes it along.
+    const int64_t rest = total_rows - rows_done - rows;
+    if (grow && end < n_seg && rest * 4 <= rows && rows + rest <= max_rows_ && n_seg - start <= max_segments_) {
+      for (; end < n_seg; ++end) {
+        int64_t ns;
+        rows += seg_rows(end, &ns);
+        samples += ns;
+      }
+    }
+    rows_done += rows;
     subs.push_back(Sub{start, end, samples});
     start = end;
     if (grow) row_cap = std::min<int64_t>(max_rows_, row_cap * 4);
