@@ -54,12 +54,19 @@ struct KArgs {
 //   3  = 1 + per-row partial sums of the rounded outputs (LayerNorm fold, producer side; GemmEpilogue::row_stats_out)
 //   4  = 2 + LayerNorm applied from those sums (consumer side; GemmEpilogue::ln_stats) -- separate instantiations, so that the
 //        hot epilogues 1 and 2 carry none of the fold's branches or registers
-template <int EPI_, bool F16>
+// BNT: tile width.  256 everywhere except the small-batch path: when a GEMM has fewer 256-wide tiles than half the CTA pairs
+// (a batch-1 forward: M <= 256, N = 512 -> TWO pairs walk K = 2048 while 72 idle), the TMA epilogues 1 and 2 also exist with
+// 128-wide tiles -- twice the pairs, half the MMA time per K block; the accumulation order over K is unchanged, so results are
+// bit-identical to the wide tiles (batch invariance).
+template <int EPI_, bool F16, int BNT = BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, KArgs a) {
   constexpr int EPI = EPI_ == 3 ? 1 : (EPI_ == 4 ? 2 : EPI_);
   constexpr bool kRowSums = EPI_ == 3, kLnApply = EPI_ == 4;
+  constexpr int WSPAN = BNT / 2;                     // columns an epilogue warp owns (two warps per row quarter)
+  constexpr int B_TILE_BYTES = (BNT / 2) * BK * 2;   // what one CTA loads of W per K block (the stage stride stays B_BYTES)
+  static_assert(BNT == BN || (BNT == 128 && (EPI_ == 1 || EPI_ == 2)), "narrow tiles: TMA epilogues only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -79,7 +86,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const bool leader = cta == 0;
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int N = a.N;
-  const int n_tiles = (N + BN - 1) / BN;
+  const int n_tiles = (N + BNT - 1) / BNT;
   const int k_blocks = (a.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -119,7 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = pair; tile < total; tile += n_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * 2 * BM + (int)cta * BM;
-      const int n0 = n_blk * BN + (int)cta * (BN / 2);
+      const int n0 = n_blk * BNT + (int)cta * (BNT / 2);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         const int k0 = kb * BK;
@@ -130,7 +137,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ac1 += pass + a.a_row_shift0;
         }
         if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B_TILE_BYTES));
           tma_load_2d_2cta(sA + stage * A_BYTES, &tmA, &full[stage], ac0, ac1);
           tma_load_2d_2cta(sB + stage * B_BYTES, &tmB, &full[stage], k0, n0);
         }
@@ -140,7 +147,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_h16(F16, 2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_h16(F16, 2 * BM, BNT);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -148,7 +155,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = pair; tile < total; tile += n_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * BNT;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -191,15 +198,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = pair; tile < total; tile += n_pairs) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int row_base = m_blk * 2 * BM + (int)cta * BM + quarter * 32;
-        const int col_base = n_blk * BN + half * 128;
-        if (e.bias) {  // this warp's 128 bias values: one coalesced load per tile, read back as smem broadcasts
-          const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
-          sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+        const int col_base = n_blk * BNT + half * WSPAN;
+        if (e.bias) {  // this warp's bias values: one coalesced load per tile, read back as smem broadcasts
+          if (lane * 4 < WSPAN) {
+            const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
+            sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          }
           warp_sync_smem();
         }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNT + half * WSPAN);
         uint32_t ra[32], rb[32];
         float st1 = 0.f, st2 = 0.f;   // row_stats_out: this row's sum / sum of squares over the warp's 128 columns
         if (e.dbg == 3) {  // micro-benchmark only: no TMEM reads
@@ -211,7 +220,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32(tbase + 32, rb);
         }
 #pragma unroll
-        for (int c64 = 0; c64 < 2; ++c64) {
+        for (int c64 = 0; c64 < WSPAN / 64; ++c64) {
           tmem_ld_wait();
           uint32_t pk[32];
 #pragma unroll
@@ -235,10 +244,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
-          if (c64 == 0) {  // the second half's TMEM loads fly while this half is stored
+          if (c64 + 1 < WSPAN / 64) {  // the next half's TMEM loads fly while this half is stored
             if (e.dbg != 3) {
-              tmem_ld_32x32(tbase + 64, ra);
-              tmem_ld_32x32(tbase + 96, rb);
+              tmem_ld_32x32(tbase + (c64 + 1) * 64, ra);
+              tmem_ld_32x32(tbase + (c64 + 1) * 64 + 32, rb);
             }
           } else {         // the accumulator is in registers: hand the TMEM buffer back to the MMA issuer
             tc_fence_before();
@@ -275,10 +284,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row_base = m_blk * 2 * BM + (int)cta * BM + quarter * 32;
         const int row = row_base + lane;
         const bool row_ok = row < M;
-        const int col_base = n_blk * BN + half * 128;
+        const int col_base = n_blk * BNT + half * WSPAN;
         if (e.bias) {
-          const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
-          sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          if (lane * 4 < WSPAN) {
+            const uint4 b = ldg128_nc(e.bias + col_base + lane * 4);
+            sts128(sbias + lane * 16, b.x, b.y, b.z, b.w);
+          }
           if constexpr (kLnApply) {
             const uint4 cs = ldg128_nc(e.ln_csum + col_base + lane * 4);
             sts128(sbias + 512 + lane * 16, cs.x, cs.y, cs.z, cs.w);
@@ -295,21 +306,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ln_rstd = rsqrtf(fmaxf(s2 * inv - ln_mean * ln_mean, 0.f) + e.ln_eps);
         }
         // this thread's row of the addend for the whole 128-column span: issued before the accumulator is even ready
-        uint4 add[16];
+        uint4 add[WSPAN / 8];
         if (e.add_bf16) {
           const __nv_bfloat16* ap = e.add_bf16 + (size_t)row * e.ld_add + col_base;
 #pragma unroll
-          for (int g = 0; g < 16; ++g) add[g] = row_ok ? ldg128_nc(ap + 8 * g) : make_uint4(0, 0, 0, 0);
+          for (int g = 0; g < WSPAN / 8; ++g) add[g] = row_ok ? ldg128_nc(ap + 8 * g) : make_uint4(0, 0, 0, 0);
         }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BNT + half * WSPAN);
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(tbase, ra);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < WSPAN / 32; ++c) {
           tmem_ld_wait();
-          if (c + 1 < 4) {
+          if (c + 1 < WSPAN / 32) {
             if (c & 1) tmem_ld_32x32(tbase + (c + 1) * 32, ra); else tmem_ld_32x32(tbase + (c + 1) * 32, rb);
           } else {
             tc_fence_before();
@@ -609,14 +620,14 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
     set(gemm_tcgen05_kernel<3, false>); set(gemm_tcgen05_kernel<4, false>);
     set(gemm_tcgen05_kernel<0, true>); set(gemm_tcgen05_kernel<1, true>); set(gemm_tcgen05_kernel<2, true>);
     set(gemm_tcgen05_kernel<3, true>); set(gemm_tcgen05_kernel<4, true>);
+    set(gemm_tcgen05_kernel<1, false, 128>); set(gemm_tcgen05_kernel<2, false, 128>);
+    set(gemm_tcgen05_kernel<1, true, 128>); set(gemm_tcgen05_kernel<2, true, 128>);
     return (int)err;
   });
   if (rc) return rc;
   CUtensorMap tmA, tmB;
   const int a_cols = p.a_k_wrap > 0 ? p.a_k_wrap : p.K;
   rc = make_tmap_bf16_sw128(&tmA, p.A, tile_extent(p.M, p.rows_a > 0 ? p.rows_a : p.M), (uint64_t)a_cols, (uint64_t)p.lda, BM);
-  if (rc) return rc;
-  rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, BN / 2);
   if (rc) return rc;
   const bool fast = e.out_bf16 && !e.out_f32 && !e.res_f32 && !e.add_bf16 && !e.argmax && e.relu != 2 && (p.N % BN) == 0 && e.dbg != 2 && e.dbg != 4 &&
                     (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0;
@@ -627,6 +638,15 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
                       (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (e.ld_out_f32 & 3) == 0;
   if (e.row_stats_out && !fast) return (int)cudaErrorInvalidValue;                       // only the bf16 TMA epilogue writes row sums
   if (e.ln_stats && (!f32tma || !e.bias || !e.ln_csum)) return (int)cudaErrorInvalidValue;  // only the fp32 TMA epilogue applies them
+  // Narrow tiles for launch-bound problems: fewer 256-wide tiles than half the CTA pairs, a TMA epilogue without the LayerNorm
+  // fold (p.M is the host-side upper bound when the row count lives on the device).  (B200PF_GEMM_NARROW=0 turns it off.)
+  static const bool narrow_ok = !(getenv("B200PF_GEMM_NARROW") && atoi(getenv("B200PF_GEMM_NARROW")) == 0);
+  const int m_tiles256 = (p.M + 2 * BM - 1) / (2 * BM);
+  const bool narrow = narrow_ok && (fast || f32tma) && !e.row_stats_out && !e.ln_stats && (p.N % 128) == 0 &&
+                      4 * m_tiles256 * ((p.N + BN - 1) / BN) <= (num_sms / 2);
+  const int bn = narrow ? 128 : BN;
+  rc = make_tmap_bf16_sw128(&tmB, p.W, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldw, bn / 2);
+  if (rc) return rc;
   CUtensorMap tmC = tmA;  // placeholder for the general path
   if (fast) {
     rc = make_tmap_bf16_sw128(&tmC, e.out_bf16, tile_extent(p.M, p.rows_c), (uint64_t)p.N, (uint64_t)e.ld_out_bf16, 32, 64);
@@ -639,10 +659,18 @@ int gemm_bf16_tcgen05(const GemmProblem& p, const GemmEpilogue& e, int num_sms, 
   a.M = p.M; a.N = p.N; a.K = p.K; a.m_dev = p.m_dev;
   a.a_k_wrap = p.a_k_wrap; a.a_row_shift0 = p.a_row_shift0;
   a.e = e;
-  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + bn - 1) / bn;
   int grid = 2 * m_tiles * n_tiles;  // CTA pairs
   if (grid > (num_sms & ~1)) grid = num_sms & ~1;
   const dim3 g(grid), b(kThreads);
+  if (narrow) {
+    if (p.f16) {
+      if (fast) return launch_kernel(gemm_tcgen05_kernel<1, true, 128>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+      return launch_kernel(gemm_tcgen05_kernel<2, true, 128>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+    }
+    if (fast) return launch_kernel(gemm_tcgen05_kernel<1, false, 128>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+    return launch_kernel(gemm_tcgen05_kernel<2, false, 128>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
+  }
   if (p.f16) {
     if (fast && e.row_stats_out) return launch_kernel(gemm_tcgen05_kernel<3, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
     if (fast) return launch_kernel(gemm_tcgen05_kernel<1, true>, g, b, kSmemBytes, stream, tmA, tmB, tmC, a);
