@@ -254,14 +254,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive_even_cta(&tempty[acc]);
           }
-          if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
+          if (elect_one()) tma_store_wait_read<0>();  // the previous box has left the staging tile (bulk groups are per thread: elect_one picks the same lane every time)
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             sts128(my_stage_row + ((j ^ (lane & 7)) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && e.dbg != 1) {
+          if (e.dbg != 1 && elect_one()) {
             tma_store_2d(&tmC, stage_tile, col_base + c64 * 64, row_base);  // rows / columns past the tensor are clipped
             tma_store_commit();
           }
@@ -271,7 +271,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (lane == 0) tma_store_wait_all();  // the staging tile must outlive the last store
+      if (elect_one()) tma_store_wait_all();  // the staging tile must outlive the last store
       __syncwarp();
     } else if constexpr (EPI == 2) {
       // bias (+ReLU) (+bf16 addend) -> fp32 -> TMA store / reduce-add.  Warp (quarter, half): rows 32 quarter.., columns
@@ -351,14 +351,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             v[4 * g] = v0; v[4 * g + 1] = v1; v[4 * g + 2] = v2; v[4 * g + 3] = v3;
           }
-          if (lane == 0) tma_store_wait_read<0>();
+          if (elect_one()) tma_store_wait_read<0>();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             sts128f(my_stage_row + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             if (reduce) tma_reduce_add_2d(&tmC, stage_tile, col_base + c * 32, row_base);
             else tma_store_2d(&tmC, stage_tile, col_base + c * 32, row_base);
             tma_store_commit();
@@ -367,7 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (lane == 0) tma_store_wait_all();
+      if (elect_one()) tma_store_wait_all();
       __syncwarp();
     } else
     for (int tile = pair; tile < total; tile += n_pairs) {
