@@ -82,3 +82,41 @@ def test_bf16_operand_mode_is_the_looser_one(capi, synth, gpu, tmp_path_factory)
         b.close()
         eng.close()
     assert errs["fp16"] <= 2.5e-3 and errs["bf16"] <= 1.2e-2 and errs["fp16"] < 0.5 * errs["bf16"]
+
+
+def test_full_size_results_do_not_depend_on_batching(capi, synth, gpu, tmp_path_factory):
+    """Batch invariance at FULL size, bit for bit: the same segments as one batch, as batches of 8, reversed, and one at a time --
+    the last takes every small-batch path at once (CUDA graph replay, FSMN and cross-attention k/v projection forked onto the side
+    stream, 128-wide GEMM tiles), the first none of them.  Ids, fire frames, encoder output, alphas and logits must be identical:
+    it is what lets the host library cut, shard and micro-batch calls freely (MultiGpuParaformer, MicroBatcher, RunAll)."""
+    d = str(tmp_path_factory.mktemp("fullinv"))
+    synth.write_synthetic_model_dir(d, None, seed=0)
+    lens_all = synth.segment_lengths(1024)
+    lens = [int(x) for x in lens_all[:: 1024 // 24][:24]]
+    segs = [synth.make_audio(n, 700 + k) for k, n in enumerate(lens)]
+    eng = capi.Engine(d, max_rows=16384, max_segments=64)
+    eng.set_option("taps", 1)
+    b = capi.Batch(eng, int(sum(lens)) + 64)
+
+    def run(order, group):
+        out = {}
+        for g0 in range(0, len(order), group):
+            idx = order[g0:g0 + group]
+            offs = np.concatenate([[0], np.cumsum([lens[i] for i in idx])]).astype(np.int64)
+            r = b.forward_s16(np.concatenate([segs[i] for i in idx]), offs)
+            for k, i in enumerate(idx):
+                s, e = r["token_offsets"][k], r["token_offsets"][k + 1]
+                out[i] = (r["token_ids"][s:e].copy(), r["fire_frames"][s:e].copy(), b.tap("enc", k), b.tap("alphas", k), b.tap("logits", k))
+        return out
+
+    order = list(range(24))
+    ref = run(order, 24)
+    for name, got in (("batches of 8", run(order, 8)), ("reversed", run(order[::-1], 24)), ("one at a time", run(order, 1)),
+                      ("one at a time, again (graph replay)", run(order, 1))):
+        for i in order:
+            for x, y in zip(ref[i], got[i]):
+                assert x.shape == y.shape and np.array_equal(x, y), (name, i)
+    st = eng.graph_stats()
+    assert st["replays"] > 0          # the one-at-a-time runs really went through captured graphs
+    b.close()
+    eng.close()
