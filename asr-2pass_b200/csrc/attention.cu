@@ -32,13 +32,13 @@ namespace {
 constexpr int BQ = 128, BKV = 64, HD = 128, KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * HD * 2;       // 32768: two 128x64 swizzled boxes
 constexpr int K_BYTES = BKV * HD * 2;      // 16384: two 64x64 boxes
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;             // warp 0 TMA, warp 1 S issuer, warps 2-5 softmax, warp 6 P V issuer
 constexpr int kTmemCols = 256;
 // 96 KB + barriers: two CTAs fit one SM (2 x 256 TMEM columns), so one CTA's softmax is covered by the other's MMAs.
 // + this CTA's unit table (below): every role reads its units from shared memory instead of chasing work[] -> q_len[] ->
 // row_off[] through global memory at each unit boundary (seven role streams x ~1.5 us of dependent loads per unit, for
 // units that last 3-4 key blocks on the benchmark's segment lengths).
-constexpr int kMaxUnits = 192;             // one table entry per thread of the CTA; later rounds fall back to global loads
+constexpr int kMaxUnits = 224;             // one table entry per thread of the CTA; later rounds fall back to global loads
 constexpr int kSmemBytes = Q_BYTES + 2 * KV_STAGES * K_BYTES + 256 + kMaxUnits * 32;
 
 struct AArgs {
@@ -158,28 +158,25 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* q_full = bars;                  // 1
   uint64_t* q_empty = bars + 1;             // 1
   uint64_t* k_full = bars + 2;              // 2
-  uint64_t* k_empty = bars + 4;             // 2
-  uint64_t* v_full = bars + 6;              // 2
-  uint64_t* v_empty = bars + 8;             // 2
-  uint64_t* s_full = bars + 10;             // 2
-  uint64_t* p_full = bars + 12;             // 2: one per S / P buffer.  A softmax warp may run one block ahead of a slower one (S of
+  uint64_t* v_full = bars + 4;              // 2
+  uint64_t* s_full = bars + 6;              // 2: S of block g has completed -- for the softmax warps AND for the producer (the K
+                                            // stage of block g, same parity, may be reloaded)
+  uint64_t* p_full = bars + 8;              // 2: one per S / P buffer.  A softmax warp may run one block ahead of a slower one (S of
                                             // block g + 1 is ready early); it then arrives on the OTHER barrier.  Two blocks ahead is
                                             // impossible: S of block g + 2 needs P V of block g, which needs all four arrivals.
-  uint64_t* p_empty = bars + 15;            // 1
-  uint64_t* o_full = bars + 16;             // 1
-  uint64_t* o_empty = bars + 17;            // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* pv_done = bars + 10;            // 2: P V of block g has completed: its V stage may be reloaded (producer), its S / P
+                                            // buffer may take S of block g + 2 (S issuer), O is quiescent (lazy rescale)
+  uint64_t* o_full = bars + 12;             // 1
+  uint64_t* o_empty = bars + 13;            // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   UnitRec* units = reinterpret_cast<UnitRec*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
-    for (int i = 0; i < KV_STAGES; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
-    mbar_init(&p_full[0], 4); mbar_init(&p_full[1], 4); mbar_init(p_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&pv_done[i], 1); }
+    mbar_init(&p_full[0], 4); mbar_init(&p_full[1], 4);
     mbar_init(o_full, 1); mbar_init(o_empty, 4);
     fence_barrier_init();
   }
@@ -213,7 +210,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int pend_r = 0, pend_c = 0, pend_g = -1;   // V load of the previous block: K runs one block ahead of V
     auto load_v = [&]() {
       const int stage = pend_g % KV_STAGES;
-      mbar_wait(&v_empty[stage], (uint32_t)(((pend_g / KV_STAGES) & 1) ^ 1));
+      mbar_wait(&pv_done[stage], (uint32_t)(((pend_g / KV_STAGES) & 1) ^ 1));   // P V of block pend_g - 2 has read this stage
       if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[stage], K_BYTES);
         uint8_t* dst = sV + stage * K_BYTES;
@@ -234,7 +231,7 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       const int stage = st.g % KV_STAGES;
       const int r = st.kv_row + st.j * BKV;
-      mbar_wait(&k_empty[stage], (uint32_t)(((st.g / KV_STAGES) & 1) ^ 1));
+      mbar_wait(&s_full[stage], (uint32_t)(((st.g / KV_STAGES) & 1) ^ 1));      // S of block g - 2 has read this stage
       if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[stage], K_BYTES);
         uint8_t* dst = sK + stage * K_BYTES;
@@ -248,22 +245,20 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     if (pend_g >= 0) load_v();
   } else if (warp == 1) {
+    // ---- S issuer.  The MMA role is split over two warps: one warp doing both spent ~1000 cycles per key block on its own
+    // barrier waits and commits (ablation: with almost no MMA work left the block period only fell from 1723 to ~1000 cycles),
+    // more than the tensor pipe or the softmax need.  Each warp now has two waits, its MMAs and one commit per block.
     constexpr uint32_t idesc_s0 = umma_idesc_h16(F16, BQ, 0);           // N filled in per block
-    constexpr uint32_t idesc_pv = umma_idesc_h16(F16, BQ, HD, 0, 1);    // B (= V) is MN-major
     const uint32_t q_addr = smem_u32(sQ);
     const bool tracing = DBG && (dbg & 64) && blockIdx.x == 0 && lane == 0;
-    Stream s_it(a, units, blockIdx.x, gridDim.x);    // next block whose S is to be issued
-    Stream pv_it(a, units, blockIdx.x, gridDim.x);   // next block whose P V is to be issued
-    auto issue_s = [&]() {
+    for (Stream s_it(a, units, blockIdx.x, gridDim.x); s_it.valid; s_it.advance()) {
       const int g = s_it.g, stage = g % KV_STAGES, sb = g & 1;
-      if (tracing && g < 64) a.trace[8 * g + 4] = clock64();   // issue_s(g) entered
+      if (tracing && g < 64) a.trace[8 * g + 4] = clock64();   // S issuer reaches block g
       if (s_it.j == 0) mbar_wait(q_full, (uint32_t)(s_it.hc & 1));
       mbar_wait(&k_full[stage], (uint32_t)((g / KV_STAGES) & 1));
-      if (tracing && g < 64) a.trace[8 * g + 5] = clock64();   // K of block g is there
-      // S buffer sb still holds P of block g - 2, the A operand of that block's P V.  No wait is needed: that MMA was issued
-      // earlier by this same thread and the tensor pipe executes a thread's MMAs in issue order, so this S cannot overwrite the
-      // columns before P V has read them (an explicit wait on its commit cost a barrier round trip per key block: the
-      // micro-benchmark's barrier skeleton alone ran at 0.77 us per block with it).
+      // S buffer sb still holds P of block g - 2, the A operand of that block's P V, which another warp issues: wait for its commit
+      mbar_wait(&pv_done[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+      if (tracing && g < 64) a.trace[8 * g + 5] = clock64();   // K of block g is there and the S buffer is free
       tc_fence_after();
       const uint32_t k_addr = smem_u32(sK + stage * K_BYTES);
       const uint32_t idesc = idesc_s0 | ((uint32_t)(s_it.keys16() >> 3) << 17);
@@ -277,28 +272,19 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           umma_bf16(tmem_base + sb * BKV, da, db, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[stage]);
         if (last) umma_commit(q_empty);   // Q may be replaced once every S MMA of this head has read it
       }
       __syncwarp();
       if (tracing && g < 64) a.trace[8 * g + 0] = clock64();   // S of block g committed
-      s_it.advance();
-    };
-    if (s_it.valid) issue_s();
-    while (pv_it.valid) {
-      // S of the next block goes first so that it runs under this block's softmax -- unless it opens a new head whose Q
-      // has not landed yet: then P V must not queue up behind that wait.  (Lane 0 decides for the warp.)
-      bool deferred = false;
-      if (s_it.valid) {
-        if (s_it.j == 0) {
-          const int ready = __shfl_sync(0xffffffffu, (int)mbar_try_wait(q_full, (uint32_t)(s_it.hc & 1)), 0);
-          deferred = !ready;
-        }
-        if (!deferred) issue_s();
-      }
+    }
+  } else if (warp == 6) {
+    // ---- P V issuer
+    constexpr uint32_t idesc_pv = umma_idesc_h16(F16, BQ, HD, 0, 1);    // B (= V) is MN-major
+    const bool tracing = DBG && (dbg & 64) && blockIdx.x == 0 && lane == 0;
+    for (Stream pv_it(a, units, blockIdx.x, gridDim.x); pv_it.valid; pv_it.advance()) {
       const int g = pv_it.g, stage = g % KV_STAGES;
       mbar_wait(&p_full[g & 1], (uint32_t)((g >> 1) & 1));
-      if (tracing && g < 64) a.trace[8 * g + 3] = clock64();         // MMA warp saw P of block g
+      if (tracing && g < 64) a.trace[8 * g + 3] = clock64();         // P V issuer saw P of block g
       if (pv_it.j == 0) mbar_wait(o_empty, (uint32_t)((pv_it.hc & 1) ^ 1));   // the previous head's O has been read out
       mbar_wait(&v_full[stage], (uint32_t)((g / KV_STAGES) & 1));
       if (tracing && g < 64) a.trace[8 * g + 6] = clock64();   // V of block g is there
@@ -313,14 +299,11 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           const uint64_t db = umma_desc_sw128_mn(v_addr + ks * 2048, K_BYTES / 2);
           umma_bf16_ts(tmem_o, p_tmem + 8 * ks, db, idesc_pv, (!first || ks != 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty[stage]);
-        umma_commit(p_empty);
+        umma_commit(&pv_done[g & 1]);
         if (last) umma_commit(o_full);
       }
       __syncwarp();
       if (tracing && g < 64) a.trace[8 * g + 7] = clock64();   // P V of block g issued and committed
-      pv_it.advance();
-      if (deferred) issue_s();
     }
   } else {
     const int quarter = warp & 3;
@@ -410,8 +393,8 @@ attn_heads_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (warp_active) {
         if (__any_sync(0xffffffffu, need)) {
           // rare: this warp's 32 rows of O are rescaled in TMEM (rows that did not move use factor 1).  O is quiescent once
-          // P V of the previous block has completed (p_empty); `need` is never set on a head's first block.
-          mbar_wait(p_empty, (uint32_t)((g & 1) ^ 1));
+          // P V of the previous block has completed (pv_done of block g - 1); `need` is never set on a head's first block.
+          mbar_wait(&pv_done[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
           tc_fence_after();
 #pragma unroll 1
           for (int c4 = 0; c4 < 4; ++c4) {
