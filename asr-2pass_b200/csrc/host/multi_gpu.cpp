@@ -1,6 +1,7 @@
 #include "multi_gpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <numeric>
@@ -91,6 +92,26 @@ void MultiGpuParaformer::InitAsr(const std::string& am_model, const std::string&
   }
 }
 
+// The serial pass over a call's segments in the caller's order: the workers prepared each segment's text for both incoming
+// detokeniser states, so this only follows the state chain (what a one-GPU handle's detokeniser would have gone through).
+void MultiGpuParaformer::AssembleText(const std::vector<const SegmentRaw*>& by_index, std::vector<std::string>* results) {
+  pf::host::Detokenizer* vocab = models_[0]->vocab();
+  bool st = vocab->ended_on_english_word();
+  for (size_t i = 0; i < by_index.size(); ++i) {
+    const SegmentRaw* r = by_index[i];
+    if (!r || !r->has_features) continue;   // "" and the state is left alone, as ParaformerB200::Decode does
+    if (r->has_text) {
+      (*results)[i] = r->text[st ? 1 : 0];
+      st = r->ended[st ? 1 : 0];
+    } else {
+      vocab->set_ended_on_english_word(st);
+      (*results)[i] = models_[0]->TextOf(*r);
+      st = vocab->ended_on_english_word();
+    }
+  }
+  vocab->set_ended_on_english_word(st);
+}
+
 std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool input_finished,
                                                      const std::vector<std::vector<float>>& hw_emb, void* wfst_decoder, int batch_in) {
   std::vector<std::string> results(batch_in > 0 ? batch_in : 0);
@@ -138,8 +159,7 @@ std::vector<std::string> MultiGpuParaformer::Forward(float** din, int* len, bool
     for (int d = 0; d < nd; ++d)
       for (size_t k = 0; k < share[d].idx.size() && k < share[d].raw.size(); ++k) by_index[share[d].idx[k]] = &share[d].raw[k];
     std::lock_guard<std::mutex> lk(text_mu_);
-    for (int i = 0; i < batch_in; ++i)
-      if (by_index[i]) results[i] = models_[0]->TextOf(*by_index[i]);
+    AssembleText(by_index, &results);
     return results;
   }
   for (int d = 0; d < nd; ++d)
@@ -154,6 +174,10 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
   if (n_seg <= 0 || models_.empty()) return results;
   const int nd = (int)models_.size();
   if (nd == 1) return models_[0]->ForwardSegments16(seg, len, n_seg, hw_emb);
+  static const bool trace = getenv("B200PF_HOST_TRACE") != nullptr;   // per-phase wall times of every call on stderr
+  using clk = std::chrono::steady_clock;
+  const clk::time_point t0 = clk::now();
+  std::vector<double> worker_ms(nd, 0.0);
   std::vector<int> len32(n_seg), assign;
   for (int i = 0; i < n_seg; ++i) len32[i] = (int)len[i];
   PartitionSegments(len32.data(), n_seg, nd, &assign);
@@ -172,8 +196,10 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
     Share* s = &share[d];
     ParaformerB200* m = models_[d].get();
     Worker* w = workers_[d].get();
-    Post(d, [=, &hw_emb, &mu, &cv, &pending]() {
+    Post(d, [=, &hw_emb, &mu, &cv, &pending, &worker_ms]() {
+      const clk::time_point w0 = clk::now();
       s->raw = m->ForwardSegments16Raw(s->ptr.data(), s->len.data(), (int)s->idx.size(), hw_emb);
+      worker_ms[d] = std::chrono::duration<double, std::milli>(clk::now() - w0).count();
       {
         std::lock_guard<std::mutex> wl(w->mu);
         w->segments += (long long)s->idx.size();
@@ -186,13 +212,20 @@ std::vector<std::string> MultiGpuParaformer::ForwardSegments16(const int16_t* co
     std::unique_lock<std::mutex> lk(mu);
     cv.wait(lk, [&] { return pending == 0; });
   }
+  const clk::time_point t1 = clk::now();
   {   // text in the caller's order through one detokeniser (see Forward above)
     std::vector<const SegmentRaw*> by_index(n_seg, nullptr);
     for (int d = 0; d < nd; ++d)
       for (size_t k = 0; k < share[d].idx.size() && k < share[d].raw.size(); ++k) by_index[share[d].idx[k]] = &share[d].raw[k];
     std::lock_guard<std::mutex> lk(text_mu_);
-    for (int i = 0; i < n_seg; ++i)
-      if (by_index[i]) results[i] = models_[0]->TextOf(*by_index[i]);
+    AssembleText(by_index, &results);
+  }
+  if (trace) {
+    const clk::time_point t2 = clk::now();
+    fprintf(stderr, "[b200pf pool] %d segments on %d GPUs: dispatch + workers %.2f ms (per GPU:", n_seg, nd,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    for (int d = 0; d < nd; ++d) fprintf(stderr, " %.2f", worker_ms[d]);
+    fprintf(stderr, "), text %.2f ms\n", std::chrono::duration<double, std::milli>(t2 - t1).count());
   }
   return results;
 }

@@ -70,6 +70,7 @@ class MultiGpuParaformer : public Model {
     long long segments = 0;
   };
   void Post(int dev, std::function<void()> job);
+  void AssembleText(const std::vector<const SegmentRaw*>& by_index, std::vector<std::string>* results);
   static void Loop(Worker* w);
 
   std::vector<int> devices_;

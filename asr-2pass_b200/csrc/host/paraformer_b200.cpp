@@ -1,5 +1,7 @@
 #include "paraformer_b200.h"
 
+#include <chrono>
+
 #include "logprob_adapter.h"
 #ifdef B200PF_WITH_REFERENCE_HEADERS
 #include "wfst-decoder.h"   // funasr::WfstDecoder (onnxruntime/src/wfst-decoder.h:59-84)
@@ -260,8 +262,17 @@ std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_se
         seg.us_alphas.assign(r.us_alphas + r.us_offsets[i], r.us_alphas + r.us_offsets[i + 1]);
         seg.us_peaks.assign(r.us_peaks + r.us_offsets[i], r.us_peaks + r.us_offsets[i + 1]);
       }
-      if (raw_out) raw_out[i] = std::move(seg);   // the caller builds the text (MultiGpuParaformer: in the caller's order)
-      else out[i] = TextOf(seg);
+      if (raw_out) {   // the caller assembles the text (MultiGpuParaformer: in the caller's order); both variants are prepared here
+        if (has_timestamp_) {
+          seg.text[0] = seg.text[1] = TextOf(seg);   // the stamp path does not go through the stateful detokeniser
+        } else {
+          for (int v = 0; v < 2; ++v) seg.text[v] = vocab_->ToText(seg.ids, language_, v != 0, &seg.ended[v]);
+        }
+        seg.has_text = true;
+        raw_out[i] = std::move(seg);
+      } else {
+        out[i] = TextOf(seg);
+      }
     }
     last_ids_[i].swap(ids);
   }
@@ -409,9 +420,15 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
       if (!running[i]) fprintf(stderr, "ParaformerB200::Forward: %s\n", b200pf_last_error());
     }
   };
+  static const bool trace = getenv("B200PF_HOST_TRACE") != nullptr;   // per-sub-batch wall times on stderr
+  using clk = std::chrono::steady_clock;
+  const clk::time_point t0 = clk::now();
+  auto ms_since = [&](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
   launch(0);
+  if (trace) fprintf(stderr, "[b200pf dev %d] %d segments in %zu sub-batches; first staged + enqueued at %.2f ms\n", device_, n_seg, subs.size(), ms_since(t0));
   for (size_t i = 0; i < subs.size(); ++i) {
     if (i + 1 < subs.size()) launch(i + 1);          // slot (i+1)&1 was collected one iteration ago
+    if (trace && i + 1 < subs.size()) fprintf(stderr, "[b200pf dev %d]   sub-batch %zu (%d segments) staged + enqueued at %.2f ms\n", device_, i + 1, subs[i + 1].end - subs[i + 1].start, ms_since(t0));
     bool done = false;
     if (running[i]) {
       std::vector<std::string> part;
@@ -421,6 +438,7 @@ std::vector<std::string> ParaformerB200::RunAll(const int16_t* pcm, const int64_
       }
     }
     if (!done) tl_failed_segments += subs[i].end - subs[i].start;
+    if (trace) fprintf(stderr, "[b200pf dev %d]   sub-batch %zu (%d segments) collected + decoded at %.2f ms\n", device_, i, subs[i].end - subs[i].start, ms_since(t0));
   }
   return results;
 }

@@ -78,6 +78,11 @@ struct SegmentRaw {
   bool has_features = false;   // false: too short for one frame -> "" (paraformer.cpp:477-480)
   std::vector<int> ids;
   std::vector<float> us_alphas, us_peaks;
+  // Built by the worker that decoded the segment: its text for either incoming detokeniser state (previous text ended on a complete
+  // English word: no / yes) and the state it leaves behind -- the pool's serial pass in the caller's order only picks one.
+  bool has_text = false;
+  std::string text[2];
+  bool ended[2] = {false, true};
 };
 
 class ParaformerB200 : B200PF_MODEL_BASES {

@@ -61,8 +61,17 @@ std::vector<std::string> Detokenizer::ToPieces(const std::vector<int>& ids) cons
 }
 
 std::string Detokenizer::ToText(const std::vector<int>& ids, const std::string& language) {
+  bool ended = ended_on_english_word_;
+  std::string text = ToText(ids, language, ended_on_english_word_, &ended);
+  ended_on_english_word_ = ended;
+  return text;
+}
+
+std::string Detokenizer::ToText(const std::vector<int>& ids, const std::string& language, bool after_english_word, bool* ended_out) const {
   std::vector<std::string> out;
-  const bool lead_space = ended_on_english_word_;  // decided by the previous call
+  const bool lead_space = after_english_word;  // decided by the previous call
+  bool ended_on_english_word_ = after_english_word;   // local copy of the member of the same name: left unchanged by an empty call
+  struct Publish { bool* dst; const bool* src; ~Publish() { if (dst) *dst = *src; } } publish{ended_out, &ended_on_english_word_};
   const size_t n = ids.size();
 
   if (language == "en-bpe") {

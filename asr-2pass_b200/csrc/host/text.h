@@ -25,7 +25,11 @@ class Detokenizer {
   // Stateful like the reference: whether the previous call ended on a complete English word decides if the
   // next call starts with a space (Vocab::last_is_complete_english_, vocab.cpp:177,259-261,283-288).
   std::string ToText(const std::vector<int>& ids, const std::string& language);
+  // The same text for an explicit incoming state; *ended_out is the state the call leaves behind.  Lets a caller build the two
+  // possible texts of a segment ahead of time (in parallel) and pick one when the previous segment's end state is known.
+  std::string ToText(const std::vector<int>& ids, const std::string& language, bool after_english_word, bool* ended_out) const;
   bool ended_on_english_word() const { return ended_on_english_word_; }
+  void set_ended_on_english_word(bool v) { ended_on_english_word_ = v; }
   void ResetState() { ended_on_english_word_ = false; }
 
  private:
