@@ -1,6 +1,7 @@
 #include "paraformer_b200.h"
 
 #include <chrono>
+#include <thread>
 
 #include "logprob_adapter.h"
 #ifdef B200PF_WITH_REFERENCE_HEADERS
@@ -229,6 +230,35 @@ std::string ParaformerB200::TextOf(const SegmentRaw& seg) {
 std::vector<std::string> ParaformerB200::Decode(const b200pf_result& r, int n_seg, void* wfst_decoder, SegmentRaw* raw_out) {
   std::vector<std::string> out(n_seg);
   last_ids_.assign(n_seg, std::vector<int>());
+  // Large greedy batches without stamps: host threads build each segment's text for both incoming detokeniser states, then one
+  // serial pass follows the state chain -- the same strings as the loop below, without 2-3 ms of serial string work behind the
+  // last (largest) sub-batch of a call.
+  if (!raw_out && !has_timestamp_ && !UseLmDecoder(wfst_decoder) && n_seg >= 64) {
+    struct Both { std::string text[2]; bool ended[2]; bool used = false; };
+    std::vector<Both> both(n_seg);
+    const int nth = (int)std::min<unsigned>(4u, std::max(1u, std::thread::hardware_concurrency() / 4));
+    auto work = [&](int t) {
+      for (int i = t; i < n_seg; i += nth) {
+        if (r.lfr_frames[i] <= 0) continue;
+        std::vector<int> ids(r.token_ids + r.token_offsets[i], r.token_ids + r.token_offsets[i] + r.token_counts[i]);
+        for (int v = 0; v < 2; ++v) both[i].text[v] = vocab_->ToText(ids, language_, v != 0, &both[i].ended[v]);
+        both[i].used = true;
+        last_ids_[i].swap(ids);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    bool st = vocab_->ended_on_english_word();
+    for (int i = 0; i < n_seg; ++i) {
+      if (!both[i].used) continue;
+      out[i] = std::move(both[i].text[st ? 1 : 0]);
+      st = both[i].ended[st ? 1 : 0];
+    }
+    vocab_->set_ended_on_english_word(st);
+    return out;
+  }
   for (int i = 0; i < n_seg; ++i) {
     const int cnt = r.token_counts[i];
     if (raw_out) raw_out[i] = SegmentRaw();

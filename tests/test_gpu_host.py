@@ -150,3 +150,21 @@ def test_reference_unmodified_rtf_harness_and_header_caller_run_on_the_gpu(capi,
     assert r.returncode == 0, (r.stdout + r.stderr)[-800:]
     r = subprocess.run([chk, model["dir"]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "boundary_link_check ok" in r.stdout and "text_bytes=" in r.stdout, (r.stdout + r.stderr)[-800:]
+
+
+def test_parallel_text_assembly_equals_the_serial_detokeniser(capi, synth, model):
+    """Calls of >= 64 segments build every segment's text for both incoming detokeniser states on host threads and then follow
+    the state chain; smaller calls run the reference's serial loop.  Same segments, same order, same previous call -> the same
+    strings, spaces included (the state is carried from one call to the next exactly like Vocab::last_is_complete_english_)."""
+    lens = [int(16000 * (1.0 + 0.13 * (i % 11))) for i in range(96)]
+    segs = [synth.make_audio(n, 4100 + i).astype(np.float32) / np.float32(32768) for i, n in enumerate(lens)]
+    big = capi.OfflineHandle(model["dir"], max_rows=4096, max_segments=128, batch_size=128)
+    small = capi.OfflineHandle(model["dir"], max_rows=4096, max_segments=128, batch_size=128)
+    for rnd in range(2):                                   # the second round starts from the state the first one left behind
+        a = big.model_forward(segs)                        # 96 segments: parallel assembly
+        b = []
+        for k in range(0, 96, 32):                         # 32 at a time: the serial loop, same order
+            b += small.model_forward(segs[k:k + 32])
+        assert a == b, [i for i in range(96) if a[i] != b[i]][:5]
+    big.close()
+    small.close()
