@@ -120,7 +120,7 @@ def lib():
 
 HOST_LIB_PATH = os.path.join(_HERE, "lib", "libfunasr_b200.so")
 _host = None
-HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf_host_detok_text", "b200pf_host_timestamp_text",
+HOST_EXPORTS = ["b200pf_host_detok_create", "b200pf_host_detok_destroy", "b200pf_host_detok_text", "b200pf_host_detok_text_state", "b200pf_host_timestamp_text",
                 "b200pf_host_stitch", "b200pf_host_offline_init", "b200pf_host_offline_uninit", "b200pf_host_offline_infer_buffer",
                 "b200pf_host_offline_infer_segments", "b200pf_host_model_forward", "b200pf_host_compile_hotwords",
                 "b200pf_host_init_seg_dict", "b200pf_host_model_forward_hw", "b200pf_host_offline_infer_buffer_hw",
@@ -238,6 +238,16 @@ class HostDetok:
         buf = C.create_string_buffer(1 << 16)
         host_lib().b200pf_host_detok_text(self.h, _p(ids, c_i32p), len(ids), lang.encode(), buf, len(buf))
         return buf.value.decode("utf-8")
+
+    def text_state(self, ids, state_in, lang=""):
+        """(text, state_out) for an explicit incoming state; the object's own state is not touched."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        buf = C.create_string_buffer(1 << 16)
+        so = C.c_int(0)
+        H = host_lib()
+        H.b200pf_host_detok_text_state.argtypes = [C.c_void_p, c_i32p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.c_char_p, C.c_int]
+        H.b200pf_host_detok_text_state(self.h, _p(ids, c_i32p), len(ids), lang.encode(), int(bool(state_in)), C.byref(so), buf, len(buf))
+        return buf.value.decode("utf-8"), bool(so.value)
 
     def timestamp_text(self, ids, us_alphas, us_peaks):
         ids = np.ascontiguousarray(ids, dtype=np.int32)

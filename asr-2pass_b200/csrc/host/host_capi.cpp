@@ -38,6 +38,13 @@ int b200pf_host_detok_text(void* h, const int32_t* ids, int n, const char* lang,
   std::vector<int> v(ids, ids + n);
   return CopyOut(((Detok*)h)->d.ToText(v, lang ? lang : ""), out, cap);
 }
+int b200pf_host_detok_text_state(void* h, const int32_t* ids, int n, const char* lang, int state_in, int* state_out, char* out, int cap) {
+  std::vector<int> v(ids, ids + n);
+  bool ended = state_in != 0;
+  const std::string t = static_cast<const pf::host::Detokenizer&>(((Detok*)h)->d).ToText(v, lang ? lang : "", state_in != 0, &ended);
+  if (state_out) *state_out = ended ? 1 : 0;
+  return CopyOut(t, out, cap);
+}
 int b200pf_host_timestamp_text(void* h, const int32_t* ids, int n, const float* us_alphas, const float* us_peaks, int n_frames,
                                char* out, int cap) {
   Detok* d = (Detok*)h;

@@ -14,6 +14,9 @@ extern "C" {
 void* b200pf_host_detok_create(const char* const* tokens, int n);
 void b200pf_host_detok_destroy(void* h);
 int b200pf_host_detok_text(void* h, const int32_t* ids, int n, const char* lang, char* out, int cap);
+/* The same text for an explicit incoming detokeniser state (did the previous text end on a complete English word); *state_out is
+ * the state the call leaves behind.  Does not touch the handle's own state (what the parallel text assembly relies on). */
+int b200pf_host_detok_text_state(void* h, const int32_t* ids, int n, const char* lang, int state_in, int* state_out, char* out, int cap);
 /* Vector2String + TimestampOnnx + PostProcess (vocab.cpp:98-104, util.cpp:838-963, :720-836). */
 int b200pf_host_timestamp_text(void* h, const int32_t* ids, int n, const float* us_alphas, const float* us_peaks, int n_frames,
                                char* out, int cap);

@@ -41,6 +41,25 @@ def test_detokenizer_matches_oracle_on_random_sequences(capi, toks):
         assert d.text(ids, "zh-cn") == v.vector2string_v2(list(ids), "zh-cn")  # includes the carried-over state
 
 
+def test_text_for_both_incoming_states_reproduces_the_stateful_detokeniser(capi, toks):
+    """What the parallel text assembly relies on (MultiGpuParaformer::AssembleText, ParaformerB200::Decode for large batches):
+    a segment's text for an explicit incoming state plus the state it leaves behind, chained in order, is exactly what the
+    stateful detokeniser (Vocab::Vector2StringV2 with last_is_complete_english_) produces call after call."""
+    rng = np.random.default_rng(3)
+    stateful, pure = capi.HostDetok(toks), capi.HostDetok(toks)
+    st = False
+    flips = 0
+    for k in range(1500):
+        n = int(rng.integers(0, 30))
+        ids = np.where(rng.random(n) < 0.5, rng.integers(7903, 8404, n), rng.integers(0, 8404, n)).astype(np.int32)
+        both = [pure.text_state(ids, s, "zh-cn") for s in (False, True)]
+        want = stateful.text(ids, "zh-cn")
+        assert both[int(st)][0] == want, k
+        flips += both[0][0] != both[1][0]
+        st = both[int(st)][1]
+    assert flips > 50          # the incoming state really matters for many of these sequences
+
+
 def test_detokenizer_en_bpe(capi):
     toks = ["<blank>", "<s>", "</s>", "▁i", "▁he", "llo", "▁wor", "ld", "'m", "<unk>"]
     d, v = capi.HostDetok(toks), P.Vocab(toks)
