@@ -1,17 +1,20 @@
 // tcgen05 flash attention, head dim 128, variable length, non-causal with key-length masking (see attention.cuh).
 //
 // PERSISTENT kernel: 2 CTAs per SM, each walking a static share of the work units -- one head of one (segment, 128-query tile)
-// item, costliest first, dealt out as a snake.  Inside a CTA three roles run ONE continuous stream of (unit, 64-key block)
+// item, costliest first, dealt out as a snake.  Inside a CTA four roles run ONE continuous stream of (unit, 64-key block)
 // steps, so barrier set-up, the TMEM allocation and the first-load latency are paid once per CTA and the loads of the next
-// unit are in flight while the current one finishes:
+// unit are in flight while the current one finishes.  Warps 0, 1 and 6 run converged, with their TMA / tcgen05 instructions
+// under elect_one() (see the note above the role code):
 //
 //   warp 0      : TMA producer.  Q per head (single buffer); K and V in SEPARATE 2-stage rings: a K stage is free as soon
 //                 as S = Q K^T of its block has completed (early), a V stage only after P V -- with one combined ring the
 //                 load of block g+1 could not start before P V of block g-1 had finished and the whole pipeline ran serially
 //                 (ncu, round 2: softmax warps 29 % of their time waiting for S).  K runs one block ahead of V.
-//   warp 1      : MMA issuer (one lane).  S (128 x n x 128, n = keys of the block rounded up to 16) of block g+1 is issued
-//                 before P V (128 x 128 x n) of block g, across head and item boundaries, so the tensor pipe works under the
-//                 softmax.  S is double buffered in TMEM (2 x 64 columns), O takes 128 columns.
+//   warp 1      : S issuer.  S (128 x n x 128, n = keys of the block rounded up to 16) of block g+1 is issued while block g is in
+//                 the softmax, across head and item boundaries, so the tensor pipe works under the softmax.  S is double
+//                 buffered in TMEM (2 x 64 columns); S of block g+2 waits for the commit of P V of block g, whose P it overwrites.
+//   warp 6      : P V issuer (128 x 128 x n into O, 128 TMEM columns).  Its commit frees the V stage (producer), the S / P
+//                 buffer (S issuer) and tells the lazy rescale that O is quiescent.
 //   warps 2..5  : softmax, one query row per thread: single pass with a running maximum that is only advanced (and O, l
 //                 rescaled in TMEM) when the true maximum moved by more than 8 in the log2 domain.  Full 64-key blocks take
 //                 a mask-free path (packed FFMA2 / FADD2, 3-input max); only the last block of a segment is masked.
