@@ -41,3 +41,21 @@ def test_two_gpu_handle_equals_single_gpu(capi, synth, gpu, tmp_path_factory):
     assert strip(got) == strip(ref)
     mb.close()
     two.close()
+
+
+def test_two_gpu_handle_returns_the_one_gpu_text_exactly(capi, synth, gpu, tmp_path_factory):
+    """Spaces included: the pool assembles every call's text in the caller's order through ONE detokeniser state chain (the
+    reference's Vocab carries a leading-space decision from call to call), so for the same sequence of calls a two-GPU handle and
+    a one-GPU handle return identical strings -- sharding changes no character."""
+    if capi.device_count() < 2:
+        pytest.skip("needs two B200s (gpurun --gpus 2)")
+    d = str(tmp_path_factory.mktemp("mg2"))
+    synth.write_synthetic_model_dir(d, dict(n_enc=2, n_dec=2), seed=0, jitter_ln=True)
+    lens = [int(16000 * (1.0 + 0.17 * (i % 13))) for i in range(80)]
+    segs = [synth.make_audio(n, 9100 + i).astype(np.float32) / np.float32(32768) for i, n in enumerate(lens)]
+    one = capi.OfflineHandle(d, max_rows=4096, max_segments=128, batch_size=128)
+    two = capi.OfflineHandle(d, max_rows=4096, max_segments=128, batch_size=128, devices=[0, 1])
+    for call in (segs, segs[10:30], segs[::3], segs):          # the same sequence of calls on both handles
+        assert two.model_forward(call) == one.model_forward(call)
+    one.close()
+    two.close()
